@@ -1,0 +1,110 @@
+// vahana_model.h — types shared by the host engine, the device API and the CPU oracle.
+//
+// Everything here is plain C++14 that compiles under gcc and nvcc.  Transition functors
+// (vahana.jl_b200/csrc/transitions/*.h) are written once against the "Ctx concept"
+// documented in include/vahana_device.cuh and are instantiated twice: with the CUDA
+// context (product) and with the sequential oracle context (tests / CPU baseline).
+//
+// Reference semantics restated here:
+//   AgentID bit packing          /root/reference/src/Agent.jl:30-118
+//   hint names                   /root/reference/src/ModelTypes.jl:81-230
+//   reduce-op identities         /root/reference/src/Helpers.jl:44-81
+//   stencil metrics              /root/reference/src/Raster.jl:82-110
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define VB_HD __host__ __device__ __forceinline__
+#define VB_D __device__ __forceinline__
+#else
+#define VB_HD inline
+#define VB_D inline
+#endif
+
+namespace vb {
+
+typedef uint64_t AgentID;
+
+// Agent.jl:30-64: id = type:8 | rank:20 | nr:36, nr is 1-based.
+enum : int { BITS_TYPE = 8, BITS_PROCESS = 20, BITS_AGENTNR = 36 };
+enum : int { SHIFT_TYPE = BITS_PROCESS + BITS_AGENTNR, SHIFT_RANK = BITS_AGENTNR };
+enum : int { MAX_TYPES = 1 << BITS_TYPE };
+
+VB_HD AgentID agent_id(uint32_t type, uint32_t rank, uint64_t nr) {
+    return ((AgentID)type << SHIFT_TYPE) + ((AgentID)rank << SHIFT_RANK) + nr;   // Agent.jl:67-74
+}
+VB_HD uint32_t type_nr(AgentID id) { return (uint32_t)(id >> SHIFT_TYPE); }                       // Agent.jl:88
+VB_HD uint32_t process_nr(AgentID id) { return (uint32_t)((id >> SHIFT_RANK) & ((1u << BITS_PROCESS) - 1)); }  // :105
+VB_HD uint64_t agent_nr(AgentID id) { return id & ((1ull << BITS_AGENTNR) - 1); }                 // Agent.jl:113
+VB_HD AgentID remove_process(AgentID id) {                                                        // Agent.jl:80-81
+    return id & ~((((AgentID)1 << BITS_PROCESS) - 1) << BITS_AGENTNR);
+}
+
+// Type references used by apply()'s call/read/write/add_existing lists: agent types are
+// their 1-based type id (registration order, ModelTypes.jl:84-89), edge types are
+// VB_EDGE_REF + 0-based registration index.
+enum : int { EDGE_REF = 256 };
+
+enum AgentHint : uint32_t { AGENT_IMMORTAL = 1, AGENT_INDEPENDENT = 2 };
+enum EdgeHint : uint32_t {
+    EDGE_STATELESS = 1, EDGE_IGNORE_FROM = 2, EDGE_SINGLE_EDGE = 4, EDGE_SINGLE_TYPE = 8,
+    EDGE_IGNORE_SOURCE_STATE = 16
+};
+enum Metric : int { CHEBYSHEV = 0, EUCLIDEAN = 1, MANHATTEN = 2 };   // Raster.jl:83 (spelling as in the reference)
+enum ReduceOp : int { OP_SUM = 0, OP_PROD = 1, OP_MIN = 2, OP_MAX = 3, OP_AND = 4, OP_OR = 5 };
+enum DType : int { DT_I64 = 0, DT_F64 = 1, DT_BOOL = 2, DT_I32 = 3, DT_F32 = 4, DT_U8 = 5 };
+
+// Philox4x32-10 — the counter-based generator that stands in for the per-agent
+// pre-generated uniform table (north_star: "identical pre-generated per-agent uniform
+// draws").  uniform(seed, agent slot, k) is a pure function, so the oracle and the
+// kernels read the same table without materialising it.
+struct Philox {
+    static VB_HD void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    static VB_HD void gen(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t (&out)[4]) {
+        uint32_t c[4] = {(uint32_t)ctr_lo, (uint32_t)(ctr_lo >> 32), (uint32_t)ctr_hi, (uint32_t)(ctr_hi >> 32)};
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        for (int i = 0; i < 10; ++i) {
+            round(c, k0, k1);
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+    // 53-bit uniform in [0,1): exact in double, identical on host and device.
+    static VB_HD double uniform(uint64_t seed, uint64_t a, uint64_t b) {
+        uint32_t r[4];
+        gen(seed, a, b, r);
+        const uint64_t bits = (((uint64_t)r[0] << 32) | r[1]) >> 11;
+        return (double)bits * (1.0 / 9007199254740992.0);
+    }
+    static VB_HD uint64_t u64(uint64_t seed, uint64_t a, uint64_t b) {
+        uint32_t r[4];
+        gen(seed, a, b, r);
+        return ((uint64_t)r[0] << 32) | r[1];
+    }
+};
+
+// Largest power-of-two word (<= 16 B) that divides a state size: the SoA column width
+// the engine stores agent and edge states in (see DESIGN.md "data layout").
+VB_HD uint32_t soa_word(uint32_t size) {
+    if (size == 0) return 0;
+    uint32_t w = 16;
+    while (size % w) w >>= 1;
+    return w;
+}
+
+// Raster position (up to 4 dimensions, 1-based like CartesianIndex).
+enum : int { MAX_RASTER_DIMS = 4 };
+struct Pos {
+    int64_t v[MAX_RASTER_DIMS];
+};
+
+}  // namespace vb

@@ -1,0 +1,713 @@
+"""vahana_b200 — host-side mirror of Vahana.jl's API for the transition hot path.
+
+The reference is Julia (absent from this image), so the host side above the C-ABI
+(include/vahana_b200.h) is Python + ctypes, mirroring the reference's names, argument meaning
+and error behaviour (AssertionError where the reference asserts):
+
+    ModelTypes / register_agenttype! / register_edgetype! / register_param!   src/ModelTypes.jl:32-289
+    create_model / create_simulation / finish_init! / apply! / mapreduce      src/Simulation.jl:115-856
+    add_agent(s)! / agentstate / all_agents / num_agents                      src/Agent.jl, src/AgentMethods.jl
+    add_edge(s)! / edges / neighborids / neighborstates / edgestates / num_edges / has_edge
+                                                                              src/Edge.jl, src/EdgeMethods.jl
+    add_raster! / connect_raster_neighbors! / calc_raster / rastervalues / move_to! / cellid
+                                                                              src/Raster.jl
+    get_global / set_global! / push_global! / modify_global!                  src/Global.jl (host-side state)
+
+Everything that touches simulation state goes through the C-ABI of the CUDA engine
+(vahana.jl_b200/csrc/build/libvahana_b200.so).  There is no CPU fallback: if the library is
+missing, creating a simulation fails.  Tests may inject the CPU oracle (oracle/) as `backend=` to use
+the same host code as a checker; the product never does.
+
+Transition functions are CUDA device functors compiled into a model library and referred to by name
+(`apply!(sim, "hk_step", ...)`), see include/vahana_device.cuh.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Any, Iterable, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "csrc", "build", "libvahana_b200.so")
+
+EDGE_REF = 256
+_AGENT_HINTS = {"Immortal": 1, "Independent": 2}
+_EDGE_HINTS = {"Stateless": 1, "IgnoreFrom": 2, "SingleEdge": 4, "SingleType": 8, "IgnoreSourceState": 16}
+_METRICS = {"chebyshev": 0, "euclidean": 1, "manhatten": 2}
+_OPS = {"+": 0, "*": 1, "min": 2, "max": 3, "&": 4, "|": 5}
+_DT = {np.dtype("i8"): 0, np.dtype("f8"): 1, np.dtype("?"): 2, np.dtype("i4"): 3, np.dtype("f4"): 4, np.dtype("u1"): 5}
+_DT_NP = {v: k for k, v in _DT.items()}
+ACC_EDGES, ACC_NEIGHBORIDS, ACC_EDGESTATES, ACC_NUM_EDGES, ACC_HAS_EDGE, ACC_NEIGHBORIDS_ITER, ACC_EDGESTATES_ITER = range(7)
+
+# --- AgentID helpers (src/Agent.jl:30-118) ---------------------------------------------------------
+BITS_TYPE, BITS_PROCESS, BITS_AGENTNR = 8, 20, 36
+SHIFT_TYPE, SHIFT_RANK = BITS_PROCESS + BITS_AGENTNR, BITS_AGENTNR
+
+
+def agent_id(typeid: int, rank: int, nr: int) -> int:
+    return (typeid << SHIFT_TYPE) + (rank << SHIFT_RANK) + nr
+
+
+def type_nr(aid: int) -> int:
+    return int(aid) >> SHIFT_TYPE
+
+
+def process_nr(aid: int) -> int:
+    return (int(aid) >> SHIFT_RANK) & ((1 << BITS_PROCESS) - 1)
+
+
+def agent_nr(aid: int) -> int:
+    return int(aid) & ((1 << BITS_AGENTNR) - 1)
+
+
+# --- config (src/Vahana.jl:42-84) -------------------------------------------------------------------
+class _Config:
+    detect_stateless = False
+    asserts_enabled = True
+    quiet = True
+
+
+config = _Config()
+
+
+def detect_stateless(flag: bool = True) -> None:
+    config.detect_stateless = bool(flag)
+
+
+def enable_asserts(flag: bool = True) -> None:
+    config.asserts_enabled = bool(flag)
+
+
+# --- C-ABI binding ------------------------------------------------------------------------------------
+class _AgentTypeDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("size", C.c_uint32), ("hints", C.c_uint32)]
+
+
+class _EdgeTypeDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("size", C.c_uint32), ("hints", C.c_uint32), ("target_type", C.c_int32),
+                ("size_hint", C.c_uint64)]
+
+
+class _ModelDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("n_agent_types", C.c_uint32), ("agent_types", C.POINTER(_AgentTypeDesc)),
+                ("n_edge_types", C.c_uint32), ("edge_types", C.POINTER(_EdgeTypeDesc)), ("param_size", C.c_uint32)]
+
+
+# every symbol include/vahana_b200.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "vb_last_error", "vb_backend", "vb_init", "vb_shutdown", "vb_comm_unique_id", "vb_comm_init", "vb_comm_rank",
+    "vb_sim_create", "vb_sim_copy", "vb_sim_destroy", "vb_set_param", "vb_set_config", "vb_disable_transition_checks",
+    "vb_add_agents", "vb_add_edges", "vb_remove_edges", "vb_add_raster", "vb_connect_raster_neighbors", "vb_move_to",
+    "vb_cellid", "vb_finish_init", "vb_apply", "vb_has_transition", "vb_load_model_library", "vb_num_agents",
+    "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce",
+    "vb_rastervalues", "vb_calc_raster_num_edges", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
+    "vb_last_apply_stats",
+]
+
+
+class Backend:
+    """A loaded implementation of include/vahana_b200.h."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"vahana_b200: engine library not found at {path}. Build it with `python __graft_entry__.py build` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        self.path = path
+        self.lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        self.lib.vb_last_error.restype = C.c_char_p
+        self.lib.vb_backend.restype = C.c_char_p
+        self.name = self.lib.vb_backend().decode()
+        self._initialized = False
+
+    def check(self, rc: int) -> None:
+        if rc == 0:
+            return
+        msg = self.lib.vb_last_error().decode(errors="replace")
+        if rc == 1:
+            raise AssertionError(msg)
+        if rc == 2:
+            raise ValueError(msg)
+        raise RuntimeError(f"vahana_b200 [{rc}]: {msg}")
+
+    def init(self, device: int = 0) -> None:
+        if not self._initialized:
+            self.check(self.lib.vb_init(C.c_int(device)))
+            self._initialized = True
+
+
+_default_backend: Optional[Backend] = None
+
+
+def load_backend(path: Optional[str] = None) -> Backend:
+    return Backend(path or os.environ.get("VAHANA_B200_LIB", DEFAULT_LIB))
+
+
+def default_backend() -> Backend:
+    """The CUDA engine.  Raises if it has not been built or is not the CUDA implementation."""
+    global _default_backend
+    if _default_backend is None:
+        b = load_backend()
+        if not b.name.startswith("cuda"):
+            raise RuntimeError(f"vahana_b200: {b.path} is not the CUDA engine (backend={b.name})")
+        _default_backend = b
+    return _default_backend
+
+
+# --- ModelTypes (src/ModelTypes.jl) ------------------------------------------------------------------
+def _as_dtype(fields) -> Optional[np.dtype]:
+    if fields is None:
+        return None
+    dt = np.dtype(fields, align=True) if not isinstance(fields, np.dtype) else fields
+    if dt.names is None:
+        raise AssertionError("agent/edge types must be structs (isbitstype)")
+    return dt if dt.itemsize > 0 and len(dt.names) > 0 else None
+
+
+class ModelTypes:
+    def __init__(self):
+        self.agent_names: list[str] = []
+        self.agent_dtypes: dict[str, Optional[np.dtype]] = {}
+        self.agent_hints: dict[str, set] = {}
+        self.edge_names: list[str] = []
+        self.edge_dtypes: dict[str, Optional[np.dtype]] = {}
+        self.edge_hints: dict[str, set] = {}
+        self.edge_kw: dict[str, dict] = {}
+        self.params: list[tuple[str, Any]] = []
+        self.globals: dict[str, Any] = {}
+
+    # register_agenttype!: ModelTypes.jl:81-106
+    def register_agenttype(self, name: str, fields=None, *hints: str) -> "ModelTypes":
+        assert name not in self.agent_dtypes, f"Type {name} is already registered"
+        assert len(self.agent_names) + 1 < 256, "Can not add new type, maximal number of types already registered"
+        for h in hints:
+            assert h in _AGENT_HINTS, f"The agent type hint {h} is unknown for type {name}"
+        self.agent_names.append(name)
+        self.agent_dtypes[name] = _as_dtype(fields)
+        self.agent_hints[name] = set(hints)
+        return self
+
+    # register_edgetype!: ModelTypes.jl:158-230
+    def register_edgetype(self, name: str, fields=None, *hints: str, target: Optional[str] = None, size: int = 0) -> "ModelTypes":
+        assert name not in self.edge_dtypes, f"Type {name} is already registered"
+        hs = set(hints)
+        for h in hs:
+            assert h in list(_EDGE_HINTS) + ["NumEdgesOnly", "HasEdgeOnly"], f"The edge type hint {h} is unknown for type {name}"
+        if "NumEdgesOnly" in hs:
+            hs |= {"Stateless", "IgnoreFrom"}
+        if "HasEdgeOnly" in hs:
+            hs |= {"Stateless", "IgnoreFrom", "SingleEdge"}
+        hs -= {"NumEdgesOnly", "HasEdgeOnly"}
+        if "SingleType" in hs:
+            assert target is not None, f"For type {name} the :SingleType hint is set, but the target keyword is missing"
+        if target is not None:
+            hs.add("SingleType")
+        dt = _as_dtype(fields)
+        if dt is None and "Stateless" not in hs and config.detect_stateless:
+            hs.add("Stateless")
+        assert not ("SingleType" in hs and "SingleEdge" in hs and not ("Stateless" in hs and "IgnoreFrom" in hs)), \
+            "The hints :SingleEdge and :SingleType can be only combined when the type has also the hints :Stateless and :IgnoreFrom"
+        self.edge_names.append(name)
+        self.edge_dtypes[name] = dt
+        self.edge_hints[name] = hs
+        self.edge_kw[name] = {"target": target, "size": int(size)}
+        return self
+
+    def register_param(self, name: str, default) -> "ModelTypes":
+        self.params.append((name, default))
+        return self
+
+    def register_global(self, name: str, default) -> "ModelTypes":
+        self.globals[name] = default
+        return self
+
+
+class Model:
+    def __init__(self, types: ModelTypes, name: str):
+        self.types, self.name = types, name
+        self.immortal = [("Immortal" in types.agent_hints[n]) for n in types.agent_names]
+        pf = []
+        for pname, default in types.params:
+            if isinstance(default, (bool, np.bool_)):
+                pf.append((pname, "?"))
+            elif isinstance(default, (int, np.integer)):
+                pf.append((pname, "i8"))
+            elif isinstance(default, (float, np.floating)):
+                pf.append((pname, "f8"))
+            elif isinstance(default, np.ndarray) or isinstance(default, np.void):
+                pf.append((pname, default.dtype, default.shape) if isinstance(default, np.ndarray) else (pname, default.dtype))
+            else:
+                raise TypeError(f"parameter {pname}: unsupported type {type(default)}")
+        self.param_dtype = np.dtype(pf, align=True) if pf else None
+
+
+def create_model(types: ModelTypes, name: str) -> Model:
+    return Model(types, name)
+
+
+# --- Simulation -----------------------------------------------------------------------------------------
+class Simulation:
+    def __init__(self, model: Model, params: Optional[dict] = None, globals_: Optional[dict] = None,
+                 backend: Optional[Backend] = None, device: int = 0, _handle=None):
+        self.model = model
+        self.backend = backend or default_backend()
+        self.backend.init(device)
+        self.lib = self.backend.lib
+        t = model.types
+        self._aid = {n: i + 1 for i, n in enumerate(t.agent_names)}
+        self._eid = {n: i for i, n in enumerate(t.edge_names)}
+        self.globals = dict(t.globals)
+        self.globals.update(globals_ or {})
+        self.globals_last_change = 0
+        self._params = None
+        if model.param_dtype is not None:
+            self._params = np.zeros((), dtype=model.param_dtype)
+            for pname, default in t.params:
+                self._params[pname] = default
+            for k, v in (params or {}).items():
+                self._params[k] = v
+        if _handle is not None:
+            self.h = _handle
+            return
+        at = (_AgentTypeDesc * max(1, len(t.agent_names)))()
+        for i, n in enumerate(t.agent_names):
+            dt = t.agent_dtypes[n]
+            at[i] = _AgentTypeDesc(n.encode(), dt.itemsize if dt is not None else 0,
+                                   sum(_AGENT_HINTS[h] for h in t.agent_hints[n]))
+        et = (_EdgeTypeDesc * max(1, len(t.edge_names)))()
+        for i, n in enumerate(t.edge_names):
+            dt = t.edge_dtypes[n]
+            tgt = t.edge_kw[n]["target"]
+            et[i] = _EdgeTypeDesc(n.encode(), dt.itemsize if dt is not None else 0,
+                                  sum(_EDGE_HINTS[h] for h in t.edge_hints[n]),
+                                  self._aid[tgt] if tgt is not None else 0, t.edge_kw[n]["size"])
+        self._keep = (at, et)
+        md = _ModelDesc(model.name.encode(), len(t.agent_names), at, len(t.edge_names), et,
+                        self._params.nbytes if self._params is not None else 0)
+        h = C.c_void_p()
+        pbuf = self._params.tobytes() if self._params is not None else None
+        self.backend.check(self.lib.vb_sim_create(C.byref(md), pbuf, C.byref(h)))
+        self.h = h
+        self.lib.vb_set_config(self.h, C.c_int(int(config.asserts_enabled)), C.c_int(1))
+
+    # -- helpers --
+    def _ck(self, rc):
+        self.backend.check(rc)
+
+    def type_id(self, name: str) -> int:
+        return self._aid[name]
+
+    def _ref(self, name: str) -> int:
+        if name in self._aid:
+            return self._aid[name]
+        if name in self._eid:
+            return EDGE_REF + self._eid[name]
+        raise AssertionError(f"type {name} is not registered")
+
+    def _refs(self, names) -> "C.Array":
+        if isinstance(names, str):
+            names = [names]
+        names = list(names or [])
+        arr = (C.c_int * max(1, len(names)))(*[self._ref(n) for n in names])
+        return arr, len(names)
+
+    def _adt(self, name):
+        return self.model.types.agent_dtypes[name]
+
+    def _edt(self, name):
+        return self.model.types.edge_dtypes[name]
+
+    def _state_bytes(self, dt: Optional[np.dtype], values, n: int) -> Optional[np.ndarray]:
+        if dt is None:
+            return None
+        arr = np.asarray(values, dtype=dt) if not (isinstance(values, np.ndarray) and values.dtype == dt) else values
+        arr = np.ascontiguousarray(arr).reshape(-1)
+        assert arr.shape[0] == n
+        return arr
+
+    # -- lifecycle --
+    def finish_simulation(self):
+        if getattr(self, "h", None) is not None:
+            self.lib.vb_sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.finish_simulation()
+        except Exception:
+            pass
+
+    def copy_simulation(self) -> "Simulation":
+        h = C.c_void_p()
+        self._ck(self.lib.vb_sim_copy(self.h, C.byref(h)))
+        s = Simulation(self.model, None, dict(self.globals), self.backend, _handle=h)
+        s._params = None if self._params is None else self._params.copy()
+        return s
+
+    def param(self, name: str):
+        return self._params[name].item() if self._params[name].shape == () else self._params[name]
+
+    def set_param(self, name: str, value) -> "Simulation":
+        self._params[name] = value
+        self._ck(self.lib.vb_set_param(self.h, self._params.tobytes(), C.c_uint32(self._params.nbytes)))
+        return self
+
+    def disable_transition_checks(self, disable: bool):
+        self._ck(self.lib.vb_disable_transition_checks(self.h, C.c_int(int(disable))))
+
+    # -- globals (src/Global.jl:10-74, host-side) --
+    def get_global(self, name):
+        return self.globals[name]
+
+    def set_global(self, name, value):
+        self.globals[name] = value
+        self.globals_last_change = self.num_transitions()
+
+    def push_global(self, name, value):
+        self.globals[name] = list(self.globals[name]) + [value]
+        self.globals_last_change = self.num_transitions()
+
+    def modify_global(self, name, f):
+        self.set_global(name, f(self.globals[name]))
+
+    # -- init phase --
+    def add_agents(self, type_name: str, states=None, n: Optional[int] = None) -> np.ndarray:
+        dt = self._adt(type_name)
+        if dt is None:
+            n = int(n if n is not None else (len(states) if states is not None else 1))
+            buf = None
+        else:
+            arr = np.asarray(states, dtype=dt).reshape(-1)
+            n = arr.shape[0]
+            buf = np.ascontiguousarray(arr)
+        ids = np.zeros(n, dtype=np.uint64)
+        self._ck(self.lib.vb_add_agents(self.h, C.c_int(self._aid[type_name]), buf.ctypes.data_as(C.c_void_p) if buf is not None else None,
+                                        C.c_uint64(n), ids.ctypes.data_as(C.c_void_p)))
+        return ids
+
+    def add_agent(self, type_name: str, state=None) -> int:
+        dt = self._adt(type_name)
+        if dt is None:
+            return int(self.add_agents(type_name, None, 1)[0])
+        if not isinstance(state, (tuple, np.void)):
+            state = (state,)
+        return int(self.add_agents(type_name, np.array([state], dtype=dt))[0])
+
+    def add_edges(self, from_ids, to_ids, edge_name: str, states=None):
+        to = np.ascontiguousarray(np.asarray(to_ids, dtype=np.uint64).reshape(-1))
+        n = to.shape[0]
+        fr = np.ascontiguousarray(np.broadcast_to(np.asarray(from_ids, dtype=np.uint64), (n,)))
+        dt = self._edt(edge_name)
+        buf = None
+        if dt is not None:
+            if states is None:
+                raise AssertionError(f"edge type {edge_name} has a state")
+            arr = np.asarray(states, dtype=dt)
+            buf = np.ascontiguousarray(np.broadcast_to(arr.reshape(-1) if arr.ndim else arr, (n,)))
+        self._ck(self.lib.vb_add_edges(self.h, C.c_int(self._eid[edge_name]), fr.ctypes.data_as(C.c_void_p), to.ctypes.data_as(C.c_void_p),
+                                       buf.ctypes.data_as(C.c_void_p) if buf is not None else None, C.c_uint64(n)))
+
+    def add_edge(self, from_id: int, to_id: int, edge_name: str, state=None):
+        dt = self._edt(edge_name)
+        if dt is not None and state is not None and not isinstance(state, (tuple, np.void)):
+            state = (state,)
+        self.add_edges([from_id], [to_id], edge_name, None if dt is None else np.array([state], dtype=dt))
+
+    def remove_edges(self, *args):
+        """remove_edges!(sim, to, T) or remove_edges!(sim, from, to, T)  (EdgeMethods.jl:527-599)"""
+        if len(args) == 2:
+            to, name = args
+            fr = 0
+        else:
+            fr, to, name = args
+        self._ck(self.lib.vb_remove_edges(self.h, C.c_int(self._eid[name]), C.c_uint64(int(fr)), C.c_uint64(int(to))))
+
+    def add_raster(self, name: str, dims: Sequence[int], type_name: str, agent_constructor) -> np.ndarray:
+        """add_raster!(sim, name, dims, agent_constructor): the constructor is called with the 1-based position
+        tuple of every cell in CartesianIndices (column-major) order, or is an array of states in that order."""
+        dims = tuple(int(d) for d in dims)
+        n = int(np.prod(dims))
+        dt = self._adt(type_name)
+        if callable(agent_constructor):
+            states = np.zeros(n, dtype=dt) if dt is not None else None
+            for i, pos in enumerate(np.ndindex(*dims[::-1])):
+                v = agent_constructor(tuple(p + 1 for p in pos[::-1]))
+                if dt is not None:
+                    states[i] = v if isinstance(v, (tuple, np.void)) else (v,)
+        else:
+            states = None if dt is None else np.ascontiguousarray(np.asarray(agent_constructor, dtype=dt).reshape(-1))
+        ids = np.zeros(n, dtype=np.uint64)
+        d = (C.c_int64 * len(dims))(*dims)
+        self._ck(self.lib.vb_add_raster(self.h, name.encode(), C.c_int(len(dims)), d, C.c_int(self._aid[type_name]),
+                                        states.ctypes.data_as(C.c_void_p) if states is not None else None,
+                                        ids.ctypes.data_as(C.c_void_p)))
+        return ids.reshape(dims, order="F")
+
+    def connect_raster_neighbors(self, name: str, edge_name: str, edge_state=None, distance=1, metric: str = "chebyshev",
+                                 periodic: bool = True):
+        dt = self._edt(edge_name)
+        buf = None
+        if dt is not None:
+            buf = np.array([edge_state if isinstance(edge_state, (tuple, np.void)) else (edge_state,)], dtype=dt)
+        self._ck(self.lib.vb_connect_raster_neighbors(self.h, name.encode(), C.c_int(self._eid[edge_name]), C.c_double(float(distance)),
+                                                      C.c_int(_METRICS[metric]), C.c_int(int(periodic)),
+                                                      buf.ctypes.data_as(C.c_void_p) if buf is not None else None))
+
+    def move_to(self, name: str, aid: int, pos, edge_from_raster: Optional[str], edge_to_raster: Optional[str],
+                state_from=None, state_to=None, distance=0, metric: str = "chebyshev", periodic: bool = True,
+                only_surrounding: bool = False):
+        p = (C.c_int64 * len(pos))(*[int(x) for x in pos])
+
+        def sb(ename, st):
+            if ename is None or self._edt(ename) is None:
+                return None
+            return np.array([st if isinstance(st, (tuple, np.void)) else (st,)], dtype=self._edt(ename))
+        bf, bt = sb(edge_from_raster, state_from), sb(edge_to_raster, state_to)
+        self._ck(self.lib.vb_move_to(self.h, name.encode(), C.c_uint64(int(aid)), p,
+                                     C.c_int(self._eid[edge_from_raster] if edge_from_raster else -1),
+                                     bf.ctypes.data_as(C.c_void_p) if bf is not None else None,
+                                     C.c_int(self._eid[edge_to_raster] if edge_to_raster else -1),
+                                     bt.ctypes.data_as(C.c_void_p) if bt is not None else None,
+                                     C.c_double(float(distance)), C.c_int(_METRICS[metric]), C.c_int(int(periodic)),
+                                     C.c_int(int(only_surrounding))))
+
+    def cellid(self, name: str, pos) -> int:
+        p = (C.c_int64 * len(pos))(*[int(x) for x in pos])
+        out = C.c_uint64()
+        self._ck(self.lib.vb_cellid(self.h, name.encode(), p, C.byref(out)))
+        return out.value
+
+    def finish_init(self):
+        self._ck(self.lib.vb_finish_init(self.h))
+        return self
+
+    # -- apply! (src/Simulation.jl:720-821) --
+    def apply(self, transition: str, call, read, write, add_existing=(), with_edge: Optional[str] = None, seed: int = 0):
+        c, nc = self._refs(call)
+        r, nr = self._refs(read)
+        w, nw = self._refs(write)
+        a, na = self._refs(add_existing)
+        we = self._eid[with_edge] if with_edge is not None else -1
+        self._ck(self.lib.vb_apply(self.h, transition.encode(), c, nc, r, nr, w, nw, a, na, C.c_int(we), C.c_uint64(seed)))
+        return self
+
+    def num_transitions(self) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.vb_num_transitions(self.h, C.byref(n)))
+        return n.value
+
+    def last_apply_stats(self) -> dict:
+        a, b = C.c_double(), C.c_double()
+        er, ea, ac, kl = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.vb_last_apply_stats(self.h, C.byref(a), C.byref(b), C.byref(er), C.byref(ea), C.byref(ac), C.byref(kl)))
+        return {"ms_read_write": a.value, "ms_finish": b.value, "edges_read": er.value, "edges_appended": ea.value,
+                "agents_called": ac.value, "kernel_launches": kl.value}
+
+    # -- agent queries --
+    def num_agents(self, type_name: str) -> int:
+        n = C.c_uint64()
+        self._ck(self.lib.vb_num_agents(self.h, C.c_int(self._aid[type_name]), C.byref(n)))
+        return n.value
+
+    def _all(self, type_name: str):
+        n = C.c_uint64()
+        t = C.c_int(self._aid[type_name])
+        self._ck(self.lib.vb_all_agents(self.h, t, None, None, C.c_uint64(0), C.byref(n)))
+        dt = self._adt(type_name)
+        states = np.zeros(n.value, dtype=dt) if dt is not None else None
+        ids = np.zeros(n.value, dtype=np.uint64)
+        self._ck(self.lib.vb_all_agents(self.h, t, states.ctypes.data_as(C.c_void_p) if states is not None else None,
+                                        ids.ctypes.data_as(C.c_void_p), C.c_uint64(n.value), C.byref(n)))
+        return states, ids
+
+    def all_agents(self, type_name: str) -> np.ndarray:
+        assert self._adt(type_name) is not None, "all_agents can be only called for agent types that have fields"
+        return self._all(type_name)[0]
+
+    def all_agentids(self, type_name: str) -> np.ndarray:
+        return self._all(type_name)[1]
+
+    def agentstate(self, aid: int, type_name: str):
+        dt = self._adt(type_name)
+        out = np.zeros(1, dtype=dt if dt is not None else np.dtype("u1"))
+        self._ck(self.lib.vb_agentstate(self.h, C.c_uint64(int(aid)), C.c_int(self._aid[type_name]), out.ctypes.data_as(C.c_void_p)))
+        return out[0] if dt is not None else ()
+
+    def agentstate_flexible(self, aid: int):
+        return self.agentstate(aid, self.model.types.agent_names[type_nr(aid) - 1])
+
+    # -- edge queries (EdgeMethods.jl:704-892) --
+    def _row(self, to: int, edge_name: str, what: int):
+        e = C.c_int(self._eid[edge_name])
+        n = C.c_int64()
+        self._ck(self.lib.vb_edges_of(self.h, e, C.c_uint64(int(to)), C.c_int(what), None, None, C.c_uint64(0), C.byref(n)))
+        if n.value < 0:
+            return None, None, -1
+        hints = self.model.types.edge_hints[edge_name]
+        if what in (ACC_NUM_EDGES, ACC_HAS_EDGE) or ("Stateless" in hints and "IgnoreFrom" in hints):
+            return None, None, n.value
+        dt = self._edt(edge_name)
+        fr = np.zeros(n.value, dtype=np.uint64)
+        st = np.zeros(n.value, dtype=dt) if dt is not None else None
+        self._ck(self.lib.vb_edges_of(self.h, e, C.c_uint64(int(to)), C.c_int(what), fr.ctypes.data_as(C.c_void_p),
+                                      st.ctypes.data_as(C.c_void_p) if st is not None else None, C.c_uint64(n.value), C.byref(n)))
+        return fr, st, n.value
+
+    def _single(self, edge_name):
+        return "SingleEdge" in self.model.types.edge_hints[edge_name]
+
+    def edges(self, to: int, edge_name: str):
+        """Vector of (from, state) pairs; a single pair for :SingleEdge; None for `nothing`."""
+        fr, st, n = self._row(to, edge_name, ACC_EDGES)
+        if n < 0:
+            return None
+        es = [(int(fr[i]), st[i]) for i in range(n)]
+        return es[0] if self._single(edge_name) else es
+
+    def neighborids(self, to: int, edge_name: str, _what=ACC_NEIGHBORIDS):
+        fr, _, n = self._row(to, edge_name, _what)
+        if n < 0:
+            return None
+        return int(fr[0]) if self._single(edge_name) else [int(x) for x in fr]
+
+    def neighborids_iter(self, to: int, edge_name: str):
+        return self.neighborids(to, edge_name, ACC_NEIGHBORIDS_ITER)
+
+    def edgestates(self, to: int, edge_name: str, _what=ACC_EDGESTATES):
+        _, st, n = self._row(to, edge_name, _what)
+        if n < 0:
+            return None
+        return st[0] if self._single(edge_name) else st
+
+    def edgestates_iter(self, to: int, edge_name: str):
+        return self.edgestates(to, edge_name, ACC_EDGESTATES_ITER)
+
+    def neighborstates(self, to: int, edge_name: str, agent_type: str):
+        ids = self.neighborids(to, edge_name)
+        if ids is None:
+            return None
+        if self._single(edge_name):
+            return self.agentstate(ids, agent_type)
+        return [self.agentstate(i, agent_type) for i in ids]
+
+    def neighborstates_flexible(self, to: int, edge_name: str):
+        ids = self.neighborids(to, edge_name)
+        if ids is None:
+            return None
+        if self._single(edge_name):
+            return self.agentstate_flexible(ids)
+        return [self.agentstate_flexible(i) for i in ids]
+
+    def num_edges(self, *args, write: bool = False) -> int:
+        """num_edges(sim, id, T) (EdgeMethods.jl:850-869) or num_edges(sim, T; write) (Edge.jl:373-389)."""
+        if len(args) == 1:
+            n = C.c_uint64()
+            self._ck(self.lib.vb_num_edges_total(self.h, C.c_int(self._eid[args[0]]), C.c_int(int(write)), C.byref(n)))
+            return n.value
+        to, name = args
+        return self._row(to, name, ACC_NUM_EDGES)[2]
+
+    def has_edge(self, to: int, edge_name: str) -> bool:
+        return self._row(to, edge_name, ACC_HAS_EDGE)[2] >= 1
+
+    def all_edges(self, edge_name: str):
+        n = C.c_uint64()
+        e = C.c_int(self._eid[edge_name])
+        self._ck(self.lib.vb_all_edges(self.h, e, None, None, None, C.c_uint64(0), C.byref(n)))
+        dt = self._edt(edge_name)
+        to = np.zeros(n.value, dtype=np.uint64)
+        fr = np.zeros(n.value, dtype=np.uint64)
+        st = np.zeros(n.value, dtype=dt) if dt is not None else None
+        self._ck(self.lib.vb_all_edges(self.h, e, to.ctypes.data_as(C.c_void_p), fr.ctypes.data_as(C.c_void_p),
+                                       st.ctypes.data_as(C.c_void_p) if st is not None else None, C.c_uint64(n.value), C.byref(n)))
+        return to, fr, st
+
+    def export_csr(self, edge_name: str, target_type: str, nrows: int):
+        off = np.zeros(nrows + 1, dtype=np.uint64)
+        e, t = C.c_int(self._eid[edge_name]), C.c_int(self._aid[target_type])
+        self._ck(self.lib.vb_export_csr(self.h, e, t, off.ctypes.data_as(C.c_void_p), C.c_uint64(nrows), None, None, C.c_uint64(0)))
+        n = int(off[-1])
+        dt = self._edt(edge_name)
+        fr = np.zeros(n, dtype=np.uint64)
+        st = np.zeros(n, dtype=dt) if dt is not None else None
+        self._ck(self.lib.vb_export_csr(self.h, e, t, off.ctypes.data_as(C.c_void_p), C.c_uint64(nrows), fr.ctypes.data_as(C.c_void_p),
+                                        st.ctypes.data_as(C.c_void_p) if st is not None else None, C.c_uint64(n)))
+        return off, fr, st
+
+    # -- mapreduce (AgentMethods.jl:533-565, EdgeMethods.jl:972-994) --
+    def mapreduce(self, field: Optional[str], op: str, type_name: str, datatype=None, init=None, equals=None):
+        """mapreduce(sim, a -> a.field, op, T; datatype, init).  field=None maps every element to 1 (`_ -> 1`);
+        equals=v maps to (a.field == v) (`c -> c.countdown == 0`)."""
+        ref = self._ref(type_name)
+        dt = self._adt(type_name) if ref < EDGE_REF else self._edt(type_name)
+        if ref >= EDGE_REF:
+            assert "Stateless" not in self.model.types.edge_hints[type_name], \
+                f"mapreduce is not defined for the hint combination of {type_name}"
+        if field is None:
+            off, fdt = 0, -1
+            src = np.dtype("i8")
+        else:
+            src = dt.fields[field][0]
+            off, fdt = dt.fields[field][1], _DT[src]
+        if datatype is None:   # val4empty: Helpers.jl:44-50
+            if equals is not None:
+                datatype = np.dtype("i8")
+            elif op in ("&", "|") and src == np.dtype("?"):
+                datatype = np.dtype("?")
+            else:
+                datatype = np.dtype("f8") if src.kind == "f" else np.dtype("i8")
+        rdt = np.dtype(datatype)
+        out = np.zeros(1, dtype=rdt)
+        ib = np.array([init], dtype=rdt) if init is not None else None
+        self._ck(self.lib.vb_mapreduce(self.h, C.c_int(ref), C.c_int(off), C.c_int(fdt), C.c_int(int(equals is not None)),
+                                       C.c_int64(int(equals) if equals is not None else 0), C.c_int(_OPS[op]), C.c_int(_DT[rdt]),
+                                       ib.ctypes.data_as(C.c_void_p) if ib is not None else None, out.ctypes.data_as(C.c_void_p)))
+        return out[0].item()
+
+    # -- raster read-out (Raster.jl:206-387) --
+    def raster_info(self, name: str):
+        nd = C.c_int()
+        dims = (C.c_int64 * 4)()
+        self._ck(self.lib.vb_raster_info(self.h, name.encode(), C.byref(nd), dims, None))
+        return tuple(dims[i] for i in range(nd.value))
+
+    def rastervalues(self, name: str, field: str, type_name: str) -> np.ndarray:
+        dims = self.raster_info(name)
+        dt = self._adt(type_name)
+        fdt, off = dt.fields[field][0], dt.fields[field][1]
+        out = np.zeros(int(np.prod(dims)), dtype=fdt)
+        self._ck(self.lib.vb_rastervalues(self.h, name.encode(), C.c_int(off), C.c_int(_DT[fdt]), out.ctypes.data_as(C.c_void_p)))
+        return out.reshape(dims, order="F")
+
+    def calc_rasterstate(self, name: str, field: str, type_name: str) -> np.ndarray:
+        return self.rastervalues(name, field, type_name)
+
+    def calc_raster_num_edges(self, name: str, edge_name: str) -> np.ndarray:
+        dims = self.raster_info(name)
+        out = np.zeros(int(np.prod(dims)), dtype=np.int64)
+        self._ck(self.lib.vb_calc_raster_num_edges(self.h, name.encode(), C.c_int(self._eid[edge_name]), out.ctypes.data_as(C.c_void_p)))
+        return out.reshape(dims, order="F")
+
+
+def create_simulation(model: Model, params: Optional[dict] = None, globals_: Optional[dict] = None,
+                      backend: Optional[Backend] = None, device: int = 0) -> Simulation:
+    return Simulation(model, params, globals_, backend, device)
+
+
+def add_graph(sim: Simulation, edges_uv: np.ndarray, n: int, agent_type: str, agent_states, edge_type: str, edge_states=None,
+              directed: bool = False) -> np.ndarray:
+    """add_graph!(sim, graph, agent_constructor, edge_constructor) (src/GraphsSupport.jl:34-57): one agent per vertex, then
+    for every edge (u,v) of the graph an edge u->v and, for undirected graphs, v->u, in the graph's edge order."""
+    ids = sim.add_agents(agent_type, agent_states, n)
+    uv = np.asarray(edges_uv, dtype=np.int64).reshape(-1, 2)
+    if directed:
+        fr, to = ids[uv[:, 0]], ids[uv[:, 1]]
+        st = edge_states
+    else:
+        fr = np.stack([ids[uv[:, 0]], ids[uv[:, 1]]], axis=1).reshape(-1)
+        to = np.stack([ids[uv[:, 1]], ids[uv[:, 0]]], axis=1).reshape(-1)
+        st = None if edge_states is None else np.repeat(np.asarray(edge_states), 2)
+    sim.add_edges(fr, to, edge_type, st)
+    return ids

@@ -1,0 +1,93 @@
+// testkit.h — the transition closures of the reference's own test-suite, restated as
+// single-source functors so that tests/ can replay test/core.jl, test/edges.jl,
+// test/edgesiterator.jl, test/remove_agents.jl, test/addexisting.jl, test/independent.jl,
+// test/raster.jl and test/graphs.jl against both the oracle and the CUDA engine.
+// Each functor cites the closure it restates (paths relative to /root/reference).
+#pragma once
+#include "../../../include/vahana_model.h"
+
+namespace testkit {
+
+struct Foo { int64_t foo; };                 // AMortal, AImm, ... (test/core.jl:9-13), Agent (test/edges.jl:13)
+struct FooBool { int64_t foo; bool b; };     // ADefault (test/core.jl:14-17)
+struct EFoo { int64_t foo; };                // ESDict / EdgeD... (test/core.jl:24, test/edges.jl:15-30)
+
+// do state,_,_ -> nothing   (test/core.jl:144-146,150-152)
+template <class S> struct KillAll {
+    using State = S;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx&, S&, vb::AgentID) const { return false; }
+};
+// identity / no-op closures (test/core.jl:101-103 on rank 0, test/edges.jl:349-350,377-378)
+template <class S> struct Identity {
+    using State = S;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx&, S&, vb::AgentID) const { return true; }
+};
+// state.foo < 6 ? state : nothing   (test/core.jl:223-229)
+struct KeepFooLt6 {
+    using State = Foo;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx&, Foo& s, vb::AgentID) const { return s.foo < 6; }
+};
+// state.foo % 2 == 0 ? state : nothing   (test/core.jl:256-258)
+struct KeepEvenFoo {
+    using State = Foo;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx&, Foo& s, vb::AgentID) const { return s.foo % 2 == 0; }
+};
+// create_sum_state_neighbors(edgetype): sum of n.foo over neighborstates_flexible (test/core.jl:71-83).
+// `foo` is the first field of every agent type of the model, so the flexible lookup is a field read
+// at offset 0 of whatever type the neighbour id carries.
+template <int E> struct SumStateNeighbors {
+    using State = Foo;
+    static constexpr bool kCooperative = true;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& self, vb::AgentID id) const {
+        int64_t s = 0;
+        ctx.for_each_neighbor(E, id, [&](vb::AgentID from) {
+            s += ctx.template agentfield<int64_t>((int)vb::type_nr(from), from, 0);
+        });
+        self.foo = ctx.sum(s);
+        return true;
+    }
+};
+// ADefault(state.foo, false)   (test/core.jl:425-427)
+struct SetBoolFalse {
+    using State = FooBool;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx&, FooBool& s, vb::AgentID) const { s.b = false; return true; }
+};
+// ADefault(state.foo, mod(id, 2) == 1)   (test/core.jl:433-435)
+struct SetBoolIdOdd {
+    using State = FooBool;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx&, FooBool& s, vb::AgentID id) const { s.b = (id % 2) == 1; return true; }
+};
+// @test num_edges(sim, id, ET) == n  inside the closure (test/edges.jl:338-346): the count is
+// stored in the agent so the host can assert on it.
+template <int E> struct StoreNumEdges {
+    using State = Foo;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& s, vb::AgentID id) const { s.foo = ctx.num_edges(E, id); return true; }
+};
+// add_edges!(sim, id, edges(sim, id, ET))   (test/edges.jl:357-359,367-369)
+template <int E> struct ReaddEdges {
+    using State = Foo;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
+        ctx.template for_each_edge<EFoo>(E, id, [&](vb::AgentID from, const EFoo& st) { ctx.add_edge(E, from, id, st); });
+        return true;
+    }
+};
+// add_edge!(sim, id, id, t())  (test/edges.jl:253-266): used for the read/write permission checks
+template <int E, bool kStateful> struct AddSelfLoop {
+    using State = Foo;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
+        if (kStateful) ctx.add_edge(E, id, id, EFoo{0});
+        else ctx.add_edge(E, id, id);
+        return true;
+    }
+};
+
+}  // namespace testkit
