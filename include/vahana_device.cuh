@@ -1,0 +1,563 @@
+// vahana_device.cuh — device-side API of the B200 engine: what a model's transition functor sees
+// (the "Ctx concept"), the kernels that run it, and the registration macro that turns a functor
+// into the handle vb_apply launches.
+//
+// A transition is the CUDA counterpart of the Julia closure `f(state, id, sim)` that the reference
+// calls once per agent (src/AgentMethods.jl:193-207, src/Simulation.jl:774-788):
+//
+//     struct Step : vb::TransitionBase {
+//         using State = HKAgent;                           // struct of the called agent type
+//         static constexpr bool kCooperative = true;       // warp-per-agent gather (else thread-per-agent)
+//         using EdgeWrites = vb::IntList<E_FOO>;           // edge types add_edge is called on (must be in `write`)
+//         using AgentWrites = vb::IntList<T_BAR>;          // agent types add_agent is called on
+//         template <class Ctx> VB_HD bool operator()(Ctx& ctx, State& self, vb::AgentID id) const;
+//     };                                                   // return false == `nothing` (the agent dies)
+//
+// Ctx concept (identical surface in oracle/vahana_oracle.hpp, class vo::Ctx):
+//     param<P>()                                   param(sim, ...)              src/Simulation.jl:587
+//     uniform(k)                                   k-th pre-generated uniform of this agent (Philox table)
+//     num_edges(E,id) has_edge(E,id)               src/EdgeMethods.jl:850-892
+//     for_each_neighbor(E,id,f(from))              neighborids(_iter)           :717-761
+//     neighbor_at(E,id,k)                          neighborids(...)[k+1]
+//     for_each_edge<S>(E,id,f(from,state))         edges                        :704-715
+//     for_each_edgestate<S>(E,id,f(state))         edgestates(_iter)            :804-848
+//     agentstate<A>(T,id)  agentfield<F>(T,id,off) agentstate(_flexible)        src/AgentMethods.jl:91-154
+//     for_each_neighborstate<A>(E,T,id,f(state))   neighborstates(_iter)        :764-802
+//     add_edge(E,from,to[,state])                  add_edge!                    :388-523
+//     add_agent<A>(T,state) -> id                  add_agent!                   src/AgentMethods.jl:65-89
+//     move_to(raster,id,pos,Efrom,Eto,...) cellid(raster,pos)                   src/Raster.jl:403-477
+//     sum(x) max(x) min(x) lanes() lane() leader() cooperative group of the agent (1 lane in the oracle)
+//
+// In a cooperative functor all lanes of the group run the functor for the same agent; for_each_* hand
+// each lane a strided share of the row and sum()/max()/min() combine the lanes' partials.  Writes
+// (state, add_edge, add_agent) are performed by the leader lane and must sit outside for_each_*.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vahana_model.h"
+
+namespace vb {
+
+enum : int { MAX_AGENT_TYPES = 16, MAX_EDGE_TYPES = 32, MAX_RASTERS = 4, MAX_PARAM_BYTES = 512 };
+enum : int { MAX_EDGE_WRITES = 6, MAX_AGENT_WRITES = 3 };
+enum EdgeKind : uint8_t { KIND_CSR = 0, KIND_COUNT = 1, KIND_FLAG = 2 };
+enum Mode : int { MODE_DIRECT = 0, MODE_COUNT = 1, MODE_EMIT = 2 };
+enum DevError : uint32_t {
+    DERR_EDGE_NOT_READABLE = 1, DERR_AGENT_NOT_READABLE = 2, DERR_AGENT_TYPE_MISMATCH = 4, DERR_AGENT_DIED = 8,
+    DERR_IMMORTAL_DIED = 16, DERR_ACCESSOR_UNAVAILABLE = 32, DERR_BAD_ID = 64, DERR_EDGE_NOT_DECLARED = 128,
+    DERR_SINGLETYPE_MISMATCH = 256, DERR_RASTER_POS = 512, DERR_INDEX = 1024
+};
+
+// ---- device views of the simulation state (filled by the engine, read by every kernel) -----------
+// Composite index: every agent slot of the rank has one dense 32-bit index  comp = base[type] + slot
+// (slot = nr - 1).  CSR columns (edge sources), CSR rows of edge types without :SingleType, and the
+// append logs all use it: 4 B per reference instead of an 8 B AgentID (SURVEY.md §8d byte model).
+struct AgentView {
+    uint8_t* state_r;         // SoA word columns: column c at state + c * cap * word
+    uint8_t* state_w;
+    uint8_t* died_r;          // 1 B per slot, nullptr for :Immortal
+    uint8_t* died_w;
+    const uint32_t* reuse;    // read.reuseable (slots, 0-based), LIFO: pop from the end
+    uint32_t cap;             // allocated slots
+    uint32_t nslots_r;        // length(read.state)
+    uint32_t n_reuse;         // entries of `reuse` still available to this call (after earlier pops)
+    uint32_t next0;           // first never-used slot (= nextid - 1) before this call's births
+    uint32_t size, word, ncols;
+    uint8_t immortal, independent, readable, writeable;
+};
+struct EdgeView {
+    // read container
+    const uint32_t* off;      // KIND_CSR: row offsets [rows + 1]
+    const uint32_t* src;      // composite source per entry (nullptr for :IgnoreFrom)
+    const uint8_t* st;        // SoA state columns per entry: column c at st + c * st_cap * word
+    const uint32_t* cnt;      // KIND_COUNT: edges per row; KIND_FLAG: 0/1 per row
+    uint32_t rows;            // rows of the read container
+    uint32_t st_cap;          // column stride of `st` (entries)
+    // write container (append log) of the running apply
+    uint32_t* log_to;         // composite row per appended edge
+    uint32_t* log_from;
+    uint8_t* log_st;          // SoA columns, stride log_cap
+    uint32_t* wcnt;           // KIND_COUNT / KIND_FLAG write container (rows_w entries)
+    uint32_t log_cap;
+    uint32_t rows_w;
+    uint32_t size, word, ncols;
+    int32_t target;           // :SingleType target type id, else 0
+    uint8_t hints, kind, readable, writeable;
+};
+struct RasterView {
+    const uint32_t* cells;    // composite index of the cell agent at each position (column-major)
+    int32_t ndims;
+    int32_t type;             // agent type of the cells
+    int64_t dims[MAX_RASTER_DIMS];
+};
+struct DeviceSim {
+    AgentView agents[MAX_AGENT_TYPES + 1];   // index = type id (1-based)
+    EdgeView edges[MAX_EDGE_TYPES];
+    RasterView rasters[MAX_RASTERS];
+    uint32_t base[MAX_AGENT_TYPES + 2];      // composite base per type id; base[ntypes + 1] = total
+    uint32_t n_agent_types, n_edge_types, n_rasters;
+    uint32_t rank;
+    uint32_t check;                           // asserts_enabled && check_readable
+    uint32_t* error;                          // device word, OR of DevError bits
+    uint64_t seed;
+    alignas(16) uint8_t params[MAX_PARAM_BYTES];
+};
+
+// per-launch arguments of one transition kernel
+struct LaunchArgs {
+    const DeviceSim* ds;
+    int mode;                 // Mode
+    int type;                 // called agent type id
+    uint32_t n;               // slots to visit (= nslots_r of the type)
+    int in_read, in_write;    // C in read / C in write
+    int with_edge;            // -1 or edge type: only agents with an edge of this type are called
+    uint32_t* ecount[MAX_EDGE_WRITES];    // COUNT: per-agent add_edge counts; EMIT: exclusive offsets into the log
+    uint32_t ebase[MAX_EDGE_WRITES];      // EMIT: log position where this call's appends start
+    uint32_t* acount[MAX_AGENT_WRITES];   // COUNT: per-agent add_agent counts; EMIT: exclusive offsets
+    uint32_t abase[MAX_AGENT_WRITES];     // EMIT: births of that type by earlier calls of this apply
+    unsigned long long* stats;            // [0] edges read
+    cudaStream_t stream;
+};
+
+// host-side descriptor of a compiled transition (one per (name, agent type))
+struct TransitionInfo {
+    const char* name;
+    const char* agent_type;
+    uint32_t state_size;
+    int cooperative;
+    int n_edge_writes, edge_writes[MAX_EDGE_WRITES];
+    int n_agent_writes, agent_writes[MAX_AGENT_WRITES];
+    cudaError_t (*launch)(const LaunchArgs&);
+};
+// exported by libvahana_b200.so; model libraries call it from static initialisers
+extern "C" int vb_register_transition(const TransitionInfo* info);
+
+#if defined(__CUDACC__)
+// ---- SoA word access ---------------------------------------------------------------------------------
+template <int W> struct WordT;
+template <> struct WordT<1> { typedef uint8_t type; };
+template <> struct WordT<2> { typedef uint16_t type; };
+template <> struct WordT<4> { typedef uint32_t type; };
+template <> struct WordT<8> { typedef uint64_t type; };
+template <> struct WordT<16> { typedef uint4 type; };
+template <int S> struct SoaWord { static constexpr int value = (S % 16 == 0) ? 16 : (S % 8 == 0) ? 8 : (S % 4 == 0) ? 4 : (S % 2 == 0) ? 2 : 1; };
+
+template <class T>
+__device__ __forceinline__ T soa_load(const uint8_t* __restrict__ cols, uint32_t stride, uint32_t i) {
+    constexpr int W = SoaWord<sizeof(T)>::value;
+    constexpr int NC = sizeof(T) / W;
+    typedef typename WordT<W>::type Word;
+    union { T t; Word w[NC]; } u;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) u.w[c] = reinterpret_cast<const Word*>(cols + (size_t)c * stride * W)[i];
+    return u.t;
+}
+template <class T>
+__device__ __forceinline__ void soa_store(uint8_t* __restrict__ cols, uint32_t stride, uint32_t i, const T& v) {
+    constexpr int W = SoaWord<sizeof(T)>::value;
+    constexpr int NC = sizeof(T) / W;
+    typedef typename WordT<W>::type Word;
+    union U { T t; Word w[NC]; __device__ U() {} } u;
+    u.t = v;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) reinterpret_cast<Word*>(cols + (size_t)c * stride * W)[i] = u.w[c];
+}
+// bytes [off, off + sizeof(F)) of a record stored in columns of `word` bytes
+template <class F>
+__device__ __forceinline__ F soa_load_field(const uint8_t* __restrict__ cols, uint32_t stride, uint32_t word, uint32_t i, uint32_t off) {
+    F out;
+    uint8_t* o = reinterpret_cast<uint8_t*>(&out);
+#pragma unroll
+    for (uint32_t b = 0; b < sizeof(F); ++b) {
+        const uint32_t p = off + b, c = p / word;
+        o[b] = cols[(size_t)c * stride * word + (size_t)i * word + (p - c * word)];
+    }
+    return out;
+}
+
+// ---- the CUDA context -----------------------------------------------------------------------------------
+// GROUP lanes cooperate on one agent: 1 (thread per agent) or 32 (warp per agent).
+template <class F, int MODE, int GROUP>
+class Ctx {
+  public:
+    const DeviceSim& ds;
+    const LaunchArgs& la;
+    uint32_t slot;       // slot of the called agent
+    uint32_t lane_;
+    uint32_t ecnt[F::EdgeWrites::size + 1];
+    uint32_t acnt[F::AgentWrites::size + 1];
+    unsigned long long edges_read = 0;
+
+    __device__ Ctx(const DeviceSim& d, const LaunchArgs& l, uint32_t s, uint32_t lane) : ds(d), la(l), slot(s), lane_(lane) {
+#pragma unroll
+        for (int i = 0; i <= F::EdgeWrites::size; ++i) ecnt[i] = 0;
+#pragma unroll
+        for (int i = 0; i <= F::AgentWrites::size; ++i) acnt[i] = 0;
+    }
+    __device__ __forceinline__ void fail(uint32_t code) const { atomicOr(ds.error, code); }
+
+    template <class P> __device__ __forceinline__ const P& param() const { return *reinterpret_cast<const P*>(ds.params); }
+    __device__ __forceinline__ double uniform(int k) const { return Philox::uniform(ds.seed, slot, (uint64_t)k); }
+    __device__ __forceinline__ int lanes() const { return GROUP; }
+    __device__ __forceinline__ int lane() const { return (int)lane_; }
+    __device__ __forceinline__ bool leader() const { return lane_ == 0; }
+    template <class T> __device__ __forceinline__ T sum(T v) const {
+        if (GROUP == 32) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        }
+        return v;
+    }
+    template <class T> __device__ __forceinline__ T max(T v) const {
+        if (GROUP == 32) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { T x = __shfl_xor_sync(0xffffffffu, v, o); v = x > v ? x : v; }
+        }
+        return v;
+    }
+    template <class T> __device__ __forceinline__ T min(T v) const {
+        if (GROUP == 32) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { T x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+        }
+        return v;
+    }
+
+    // -- id <-> composite --
+    __device__ __forceinline__ bool comp_of(AgentID id, uint32_t& comp) const {
+        const uint32_t t = type_nr(id);
+        const uint64_t nr = agent_nr(id);
+        if (t < 1 || t > ds.n_agent_types || nr < 1 || nr > ds.agents[t].cap) return false;
+        comp = ds.base[t] + (uint32_t)(nr - 1);
+        return true;
+    }
+    __device__ __forceinline__ AgentID id_of(uint32_t comp) const {
+        uint32_t t = 1;
+        while (t < ds.n_agent_types && comp >= ds.base[t + 1]) ++t;
+        return agent_id(t, ds.rank, (uint64_t)(comp - ds.base[t]) + 1);
+    }
+    // row of target `id` in the read container of edge type e; false = no container entry
+    __device__ __forceinline__ bool row_of(const EdgeView& ev, AgentID id, uint32_t& row) const {
+        const uint32_t t = type_nr(id);
+        const uint64_t nr = agent_nr(id);
+        if (t < 1 || t > ds.n_agent_types || nr < 1) { fail(DERR_BAD_ID); return false; }
+        if (ev.target) {
+            if ((int)t != ev.target) { if (ds.check) fail(DERR_SINGLETYPE_MISMATCH); return false; }
+            row = (uint32_t)(nr - 1);
+        } else {
+            if (nr > ds.agents[t].cap) return false;
+            row = ds.base[t] + (uint32_t)(nr - 1);
+        }
+        return row < ev.rows;
+    }
+    __device__ __forceinline__ const EdgeView& rview(int e) const {
+        const EdgeView& ev = ds.edges[e];
+        if (ds.check && !ev.readable) fail(DERR_EDGE_NOT_READABLE);   // EdgeMethods.jl:310-316,362-368
+        return ev;
+    }
+
+    // -- read accessors --
+    __device__ __forceinline__ long long num_edges(int e, AgentID id) {
+        const EdgeView& ev = rview(e);
+        if (ev.hints & EDGE_SINGLE_EDGE) { fail(DERR_ACCESSOR_UNAVAILABLE); return 0; }
+        uint32_t row;
+        if (!row_of(ev, id, row)) return 0;
+        if (ev.kind != KIND_CSR) return ev.cnt[row];
+        return (long long)(ev.off[row + 1] - ev.off[row]);
+    }
+    __device__ __forceinline__ bool has_edge(int e, AgentID id) {
+        const EdgeView& ev = rview(e);
+        if ((ev.hints & EDGE_SINGLE_EDGE) && ev.target && ev.kind == KIND_CSR) { fail(DERR_ACCESSOR_UNAVAILABLE); return false; }
+        uint32_t row;
+        if (!row_of(ev, id, row)) return false;
+        if (ev.kind != KIND_CSR) return ev.cnt[row] != 0;
+        return ev.off[row + 1] != ev.off[row];
+    }
+    template <class Fn> __device__ __forceinline__ void for_each_neighbor(int e, AgentID id, Fn&& fn) {
+        const EdgeView& ev = rview(e);
+        if (ev.hints & EDGE_IGNORE_FROM) { fail(DERR_ACCESSOR_UNAVAILABLE); return; }
+        uint32_t row;
+        if (!row_of(ev, id, row)) return;
+        const uint32_t b = ev.off[row], en = ev.off[row + 1];
+        for (uint32_t k = b + lane_; k < en; k += GROUP) fn(id_of(ev.src[k]));
+        if (lane_ == 0) edges_read += en - b;
+    }
+    __device__ __forceinline__ AgentID neighbor_at(int e, AgentID id, long long k) {
+        const EdgeView& ev = rview(e);
+        if (ev.hints & EDGE_IGNORE_FROM) { fail(DERR_ACCESSOR_UNAVAILABLE); return 0; }
+        uint32_t row;
+        if (!row_of(ev, id, row) || k < 0 || (uint32_t)k >= ev.off[row + 1] - ev.off[row]) { fail(DERR_INDEX); return 0; }
+        return id_of(ev.src[ev.off[row] + (uint32_t)k]);
+    }
+    template <class S, class Fn> __device__ __forceinline__ void for_each_edge(int e, AgentID id, Fn&& fn) {
+        const EdgeView& ev = rview(e);
+        if (ev.hints & (EDGE_IGNORE_FROM | EDGE_STATELESS)) { fail(DERR_ACCESSOR_UNAVAILABLE); return; }
+        uint32_t row;
+        if (!row_of(ev, id, row)) return;
+        const uint32_t b = ev.off[row], en = ev.off[row + 1];
+        for (uint32_t k = b + lane_; k < en; k += GROUP) fn(id_of(ev.src[k]), soa_load<S>(ev.st, ev.st_cap, k));
+        if (lane_ == 0) edges_read += en - b;
+    }
+    template <class S, class Fn> __device__ __forceinline__ void for_each_edgestate(int e, AgentID id, Fn&& fn) {
+        const EdgeView& ev = rview(e);
+        if (ev.hints & EDGE_STATELESS) { fail(DERR_ACCESSOR_UNAVAILABLE); return; }
+        uint32_t row;
+        if (!row_of(ev, id, row)) return;
+        const uint32_t b = ev.off[row], en = ev.off[row + 1];
+        for (uint32_t k = b + lane_; k < en; k += GROUP) fn(soa_load<S>(ev.st, ev.st_cap, k));
+        if (lane_ == 0) edges_read += en - b;
+    }
+    __device__ __forceinline__ bool agent_slot(int type, AgentID id, uint32_t& s) const {
+        const AgentView& av = ds.agents[type];
+        if (ds.check) {
+            if ((int)type_nr(id) != type) { fail(DERR_AGENT_TYPE_MISMATCH); return false; }   // AgentMethods.jl:92-94
+            if (!av.readable) fail(DERR_AGENT_NOT_READABLE);                                   // :96-101
+        }
+        const uint64_t nr = agent_nr(id);
+        if (nr < 1 || nr > av.nslots_r) { fail(DERR_BAD_ID); return false; }
+        s = (uint32_t)(nr - 1);
+        if (ds.check && av.died_r && av.died_r[s]) fail(DERR_AGENT_DIED);                      // :106-110
+        return true;
+    }
+    template <class A> __device__ __forceinline__ A agentstate(int type, AgentID id) {
+        uint32_t s;
+        if (!agent_slot(type, id, s)) return A{};
+        const AgentView& av = ds.agents[type];
+        return soa_load<A>(av.state_r, av.cap, s);
+    }
+    template <class Fd> __device__ __forceinline__ Fd agentfield(int type, AgentID id, int off) {
+        uint32_t s;
+        if (!agent_slot(type, id, s)) return Fd{};
+        const AgentView& av = ds.agents[type];
+        return soa_load_field<Fd>(av.state_r, av.cap, av.word, s, (uint32_t)off);
+    }
+    // neighborstates: column -> slot directly (no id round trip): the hot gather of the read phase
+    template <class A, class Fn> __device__ __forceinline__ void for_each_neighborstate(int e, int type, AgentID id, Fn&& fn) {
+        const EdgeView& ev = rview(e);
+        if (ev.hints & EDGE_IGNORE_FROM) { fail(DERR_ACCESSOR_UNAVAILABLE); return; }
+        const AgentView& av = ds.agents[type];
+        if (ds.check && !av.readable) fail(DERR_AGENT_NOT_READABLE);
+        uint32_t row;
+        if (!row_of(ev, id, row)) return;
+        const uint32_t b = ev.off[row], en = ev.off[row + 1];
+        const uint32_t tb = ds.base[type];
+        const uint32_t* __restrict__ src = ev.src;
+        const uint8_t* __restrict__ st = av.state_r;
+        const uint32_t cap = av.cap;
+        uint32_t k = b + lane_;
+        // two independent gathers in flight per lane
+        for (; k + GROUP < en; k += 2 * GROUP) {
+            const uint32_t s0 = src[k] - tb, s1 = src[k + GROUP] - tb;
+            if (ds.check && (s0 >= av.nslots_r || s1 >= av.nslots_r)) { fail(DERR_AGENT_TYPE_MISMATCH); continue; }
+            const A a0 = soa_load<A>(st, cap, s0);
+            const A a1 = soa_load<A>(st, cap, s1);
+            fn(a0);
+            fn(a1);
+        }
+        if (k < en) {
+            const uint32_t s0 = src[k] - tb;
+            if (ds.check && s0 >= av.nslots_r) { fail(DERR_AGENT_TYPE_MISMATCH); return; }
+            fn(soa_load<A>(st, cap, s0));
+        }
+        if (lane_ == 0) edges_read += en - b;
+    }
+
+    // -- write side --
+    template <class S> __device__ __forceinline__ void add_edge_impl(int e, AgentID from, AgentID to, const S* st) {
+        if (lane_ != 0) return;
+        const int w = F::EdgeWrites::find(e);
+        if (w < 0) { fail(DERR_EDGE_NOT_DECLARED); return; }
+        const EdgeView& ev = ds.edges[e];
+        if (MODE == MODE_COUNT) { ecnt[w] += 1; return; }
+        uint32_t trow, fcomp = 0;
+        const uint32_t tt = type_nr(to);
+        const uint64_t tnr = agent_nr(to);
+        if (tt < 1 || tt > ds.n_agent_types || tnr < 1 || tnr > ds.agents[tt].cap) { fail(DERR_BAD_ID); return; }
+        if (ev.target) {
+            if ((int)tt != ev.target) { fail(DERR_SINGLETYPE_MISMATCH); return; }
+            trow = (uint32_t)(tnr - 1);
+        } else {
+            trow = ds.base[tt] + (uint32_t)(tnr - 1);
+        }
+        if (!(ev.hints & EDGE_IGNORE_FROM) && !comp_of(from, fcomp)) { fail(DERR_BAD_ID); return; }
+        if (ev.kind == KIND_COUNT) { atomicAdd(&ev.wcnt[trow], 1u); ecnt[w] += 1; return; }   // count[to] += 1
+        if (ev.kind == KIND_FLAG) { ev.wcnt[trow] = 1u; ecnt[w] += 1; return; }
+        const uint32_t pos = la.ebase[w] + la.ecount[w][slot] + ecnt[w];
+        ecnt[w] += 1;
+        ev.log_to[pos] = trow;
+        if (ev.log_from) ev.log_from[pos] = fcomp;
+        if (st && ev.log_st) soa_store<S>(ev.log_st, ev.log_cap, pos, *st);
+    }
+    struct NoState {};
+    __device__ __forceinline__ void add_edge(int e, AgentID from, AgentID to) { add_edge_impl<NoState>(e, from, to, nullptr); }
+    template <class S> __device__ __forceinline__ void add_edge(int e, AgentID from, AgentID to, const S& st) { add_edge_impl<S>(e, from, to, &st); }
+
+    template <class A> __device__ __forceinline__ AgentID add_agent(int type, const A& a) {
+        const int w = F::AgentWrites::find(type);
+        if (w < 0) { fail(DERR_EDGE_NOT_DECLARED); return 0; }
+        if (MODE == MODE_COUNT) { if (lane_ == 0) acnt[w] += 1; return agent_id((uint32_t)type, ds.rank, 1); }
+        const AgentView& av = ds.agents[type];
+        // _get_next_id (AgentMethods.jl:37-63): j-th birth of the apply takes reuse[end - j], then fresh slots
+        const uint32_t j = la.abase[w] + la.acount[w][slot] + acnt[w];
+        acnt[w] += 1;
+        const uint32_t s = j < av.n_reuse ? av.reuse[av.n_reuse - 1 - j] : av.next0 + (j - av.n_reuse);
+        if (lane_ == 0) {
+            uint8_t* dst = (av.independent && s < av.nslots_r) ? av.state_r : av.state_w;   // AgentMethods.jl:79-87
+            if (sizeof(A) > 0 && av.size) soa_store<A>(dst, av.cap, s, a);
+            if (av.died_w) av.died_w[s] = 0;
+        }
+        return agent_id((uint32_t)type, ds.rank, (uint64_t)s + 1);
+    }
+
+    // -- raster --
+    __device__ __forceinline__ AgentID cellid(int r, const Pos& p) const {
+        const RasterView& rv = ds.rasters[r];
+        size_t idx = 0, stride = 1;
+        for (int k = 0; k < rv.ndims; ++k) {
+            if (p.v[k] < 1 || p.v[k] > rv.dims[k]) { fail(DERR_RASTER_POS); return 0; }
+            idx += (size_t)(p.v[k] - 1) * stride;
+            stride *= (size_t)rv.dims[k];
+        }
+        return id_of(rv.cells[idx]);
+    }
+    // move_to! for stateless edge types (Raster.jl:437-477); stencil enumeration as _stencil_core :82-96
+    __device__ void move_to(int r, AgentID id, const Pos& p, int e_from, int e_to, double distance = 0, int metric = CHEBYSHEV,
+                            bool periodic = true, bool only_surrounding = false) {
+        const RasterView& rv = ds.rasters[r];
+        if (!only_surrounding) {
+            const AgentID cell = cellid(r, p);
+            if (cell) {
+                if (e_from >= 0) add_edge(e_from, cell, id);
+                if (e_to >= 0) add_edge(e_to, id, cell);
+            }
+        }
+        if (distance >= 1) {
+            const long long d = (long long)floor(distance);
+            long long o[MAX_RASTER_DIMS];
+            for (int k = 0; k < rv.ndims; ++k) o[k] = -d;
+            while (true) {
+                bool zero = true;
+                double n2 = 0;
+                long long n1 = 0;
+                for (int k = 0; k < rv.ndims; ++k) { zero &= o[k] == 0; n2 += (double)(o[k] * o[k]); n1 += o[k] < 0 ? -o[k] : o[k]; }
+                bool keep = !zero;
+                if (keep && metric == EUCLIDEAN) keep = sqrt(n2) <= distance;
+                if (keep && metric == MANHATTEN) keep = (double)n1 <= distance;
+                if (keep) {
+                    Pos q;
+                    bool oob = false;
+                    for (int k = 0; k < rv.ndims; ++k) {
+                        long long v = p.v[k] + o[k];
+                        if (v < 1 || v > rv.dims[k]) { oob = true; long long m = (v - 1) % rv.dims[k]; if (m < 0) m += rv.dims[k]; v = m + 1; }
+                        q.v[k] = v;
+                    }
+                    if (!oob || periodic) {
+                        const AgentID cell = cellid(r, q);
+                        if (e_from >= 0) add_edge(e_from, cell, id);
+                        if (e_to >= 0) add_edge(e_to, id, cell);
+                    }
+                }
+                int k = 0;
+                while (k < rv.ndims && ++o[k] > d) { o[k] = -d; ++k; }
+                if (k == rv.ndims) break;
+            }
+        }
+    }
+};
+
+// ---- the transition kernel: the per-agent loop of transition_with(out)_read! + transition_with_write!
+//      (src/AgentMethods.jl:159-245) with GROUP lanes per agent -----------------------------------------
+template <class F, int MODE, int GROUP>
+__global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__ LaunchArgs la) {
+    typedef typename F::State State;
+    const DeviceSim& ds = *la.ds;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t idx = gtid / GROUP;
+    const uint32_t lane = gtid % GROUP;
+    if (idx >= la.n) return;
+    const AgentView& av = ds.agents[la.type];
+    bool skip = av.died_r && av.died_r[idx];                           // jump over died agents (:199-203)
+    if (!skip && la.with_edge >= 0) {                                  // with_edge: only targets of that edge type (:209-229)
+        const EdgeView& we = ds.edges[la.with_edge];
+        const uint32_t row = ds.base[la.type] + idx;
+        skip = !(row < we.rows && (we.kind == KIND_CSR ? we.off[row + 1] != we.off[row] : we.cnt[row] != 0));
+    }
+    if (skip) {
+        if (lane == 0) {
+            if (MODE == MODE_COUNT) {
+#pragma unroll
+                for (int i = 0; i < F::EdgeWrites::size; ++i) la.ecount[i][idx] = 0;
+#pragma unroll
+                for (int i = 0; i < F::AgentWrites::size; ++i) la.acount[i][idx] = 0;
+            }
+        }
+        return;
+    }
+    State self;
+    if (la.in_read && av.size) self = soa_load<State>(av.state_r, av.cap, idx);
+    else memset(&self, 0, sizeof(State));                              // Val(T) form (:232-245)
+    Ctx<F, MODE, GROUP> ctx(ds, la, idx, lane);
+    const AgentID id = agent_id((uint32_t)la.type, ds.rank, (uint64_t)idx + 1);
+    const bool alive = F()(ctx, self, id);
+    if (lane != 0) return;
+    if (MODE == MODE_COUNT) {
+#pragma unroll
+        for (int i = 0; i < F::EdgeWrites::size; ++i) la.ecount[i][idx] = ctx.ecnt[i];
+#pragma unroll
+        for (int i = 0; i < F::AgentWrites::size; ++i) la.acount[i][idx] = ctx.acnt[i];
+        return;
+    }
+    if (la.in_write) {                                                 // transition_with_write! (:159-181)
+        if (alive) {   // died_w was set to died_r by the engine before the launch, so a living agent's flag is already 0
+            if (av.size) soa_store<State>(av.independent ? av.state_r : av.state_w, av.cap, idx, self);
+        } else if (av.immortal) {
+            atomicOr(ds.error, (uint32_t)DERR_IMMORTAL_DIED);
+        } else {
+            av.died_w[idx] = 1;
+        }
+    }
+    if (ctx.edges_read) atomicAdd(la.stats, ctx.edges_read);
+}
+
+template <class F>
+cudaError_t launch_transition(const LaunchArgs& la) {
+    constexpr int GROUP = F::kCooperative ? 32 : 1;
+    const unsigned threads = 256;
+    const unsigned long long total = (unsigned long long)la.n * GROUP;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    if (blocks == 0) return cudaSuccess;
+    switch (la.mode) {
+        case MODE_DIRECT: transition_kernel<F, MODE_DIRECT, GROUP><<<blocks, threads, 0, la.stream>>>(la); break;
+        case MODE_COUNT: transition_kernel<F, MODE_COUNT, GROUP><<<blocks, threads, 0, la.stream>>>(la); break;
+        case MODE_EMIT: transition_kernel<F, MODE_EMIT, GROUP><<<blocks, threads, 0, la.stream>>>(la); break;
+    }
+    return cudaGetLastError();
+}
+
+template <class F>
+TransitionInfo make_transition_info(const char* name, const char* agent_type) {
+    TransitionInfo ti{};
+    ti.name = name;
+    ti.agent_type = agent_type;
+    ti.state_size = (uint32_t)sizeof(typename F::State);
+    ti.cooperative = F::kCooperative;
+    ti.n_edge_writes = F::EdgeWrites::size;
+    for (int i = 0; i < F::EdgeWrites::size; ++i) ti.edge_writes[i] = F::EdgeWrites::at(i);
+    ti.n_agent_writes = F::AgentWrites::size;
+    for (int i = 0; i < F::AgentWrites::size; ++i) ti.agent_writes[i] = F::AgentWrites::at(i);
+    ti.launch = &launch_transition<F>;
+    return ti;
+}
+
+#define VB_CAT2(a, b) a##b
+#define VB_CAT(a, b) VB_CAT2(a, b)
+// Registers Functor as the transition `tname` for agents of type `atype` (a string: the registered name).
+#define VB_REGISTER_TRANSITION(tname, atype, ...)                                              \
+    static const int VB_CAT(vb_reg_, __COUNTER__) = [] {                                       \
+        static const vb::TransitionInfo ti = vb::make_transition_info<__VA_ARGS__>(tname, atype); \
+        return vb_register_transition(&ti);                                                    \
+    }();
+#endif  // __CUDACC__
+
+}  // namespace vb

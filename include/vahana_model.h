@@ -101,6 +101,26 @@ VB_HD uint32_t soa_word(uint32_t size) {
     return w;
 }
 
+// Compile-time list of type ids: a transition declares the edge / agent types it appends to.
+template <int... Is> struct IntList {
+    static constexpr int size = sizeof...(Is);
+    static VB_HD int at(int i) {
+        const int v[sizeof...(Is) + 1] = {Is..., -1};
+        return v[i];
+    }
+    static VB_HD int find(int x) {
+        const int v[sizeof...(Is) + 1] = {Is..., -1};
+        for (int i = 0; i < (int)sizeof...(Is); ++i) if (v[i] == x) return i;
+        return -1;
+    }
+};
+// Defaults every transition functor inherits (see include/vahana_device.cuh).
+struct TransitionBase {
+    static constexpr bool kCooperative = false;   // true: all lanes of a warp run the functor for one agent
+    using EdgeWrites = IntList<>;                 // edge types the functor calls add_edge on
+    using AgentWrites = IntList<>;                // agent types the functor calls add_agent on
+};
+
 // Raster position (up to 4 dimensions, 1-based like CartesianIndex).
 enum : int { MAX_RASTER_DIMS = 4 };
 struct Pos {

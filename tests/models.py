@@ -49,3 +49,27 @@ def createsim(backend):
     ids = add_example_network(sim)
     sim.finish_init()
     return (sim,) + ids
+
+
+def hk_model():
+    """docs/examples/hegselmann.jl:27-45"""
+    t = vh.ModelTypes()
+    t.register_agenttype("HKAgent", [("opinion", "f8")])
+    t.register_edgetype("Knows")
+    t.register_param("eps", 0.02)
+    return vh.create_model(t, "Hegselmann-Krause")
+
+
+def hk_sim(backend, n, edges_uv, opinions, eps=0.02):
+    """add_graph! + one self loop per agent (hegselmann.jl:85-95)"""
+    sim = vh.create_simulation(hk_model(), params={"eps": eps}, backend=backend)
+    ids = vh.add_graph(sim, edges_uv, n, "HKAgent", np.asarray(opinions, dtype="f8").view([("opinion", "f8")]), "Knows")
+    sim.add_edges(ids, ids, "Knows")
+    sim.finish_init()
+    return sim, ids
+
+
+def ba_graph(n, m, seed):
+    import networkx as nx
+    g = nx.barabasi_albert_graph(n, m, seed=seed)
+    return np.array(list(g.edges()), dtype=np.int64)

@@ -1,0 +1,1923 @@
+// engine.cu — the B200 execution engine behind include/vahana_b200.h.
+//
+// Host-side phase logic of apply! (src/Simulation.jl:720-821) and finish_write!
+// (src/AgentMethods.jl:300-439, src/EdgeMethods.jl:639-684) driving hand-written sm_100a kernels:
+//   read phase / write phase   transition_kernel<F,...> (include/vahana_device.cuh), count -> scan -> emit
+//   finish_write! (edges)      stable radix sort on target row + CSR build / merge (primitives.cuh)
+//   finish_write! (agents)     buffer swap, died flags, ordered reuse-stack append, dead-agent edge purge
+//   mapreduce                  block reduction kernels
+// There is no CPU fallback: every state-touching entry point needs the CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/vahana_b200.h"
+#include "../../../include/vahana_device.cuh"
+#include "primitives.cuh"
+
+using vb::AgentID;
+using vbp::nblk;
+
+// ------------------------------------------------------------------------------------------------------
+namespace {
+
+struct AssertionError : std::runtime_error { explicit AssertionError(const std::string& m) : std::runtime_error(m) {} };
+struct ArgError : std::runtime_error { explicit ArgError(const std::string& m) : std::runtime_error(m) {} };
+struct CudaError : std::runtime_error { explicit CudaError(const std::string& m) : std::runtime_error(m) {} };
+
+thread_local std::string g_err;
+int g_device = -1;
+cudaStream_t g_stream = nullptr;
+unsigned long long g_launches = 0;   // kernels of ours launched (bench reports the per-step count)
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+#define LAUNCH_CHECK()                 \
+    do {                               \
+        ++g_launches;                  \
+        CK(cudaGetLastError());        \
+    } while (0)
+
+void require_device() {
+    if (g_device < 0) throw CudaError("vahana_b200: vb_init() has not been called or no CUDA device is available (no CPU fallback)");
+}
+
+// ---- caching device allocator: finish_write! ping-pongs buffers of a few recurring sizes every apply ----
+struct Pool {
+    std::multimap<size_t, void*> free_;
+    std::unordered_map<void*, size_t> size_;
+    static size_t round(size_t b) {
+        size_t g = 256;
+        if (b > (1u << 20)) g = 1u << 20;
+        return ((b + g - 1) / g) * g;
+    }
+    void* alloc(size_t bytes) {
+        if (bytes == 0) bytes = 256;
+        const size_t r = round(bytes);
+        auto it = free_.lower_bound(r);
+        if (it != free_.end() && it->first <= r + r / 4) {
+            void* p = it->second;
+            free_.erase(it);
+            return p;
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, r);
+        if (e != cudaSuccess) {
+            release_all();
+            e = cudaMalloc(&p, r);
+            if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(r) + "): " + cudaGetErrorString(e));
+        }
+        size_[p] = r;
+        return p;
+    }
+    void free(void* p) {
+        if (!p) return;
+        auto it = size_.find(p);
+        if (it == size_.end()) return;
+        free_.insert({it->second, p});
+    }
+    void release_all() {
+        for (auto& kv : free_) { cudaFree(kv.second); size_.erase(kv.second); }
+        free_.clear();
+    }
+};
+Pool g_pool;
+
+template <class T> T* dalloc(size_t n) { return (T*)g_pool.alloc(n * sizeof(T)); }
+inline void dfree(void* p) { g_pool.free(p); }
+
+std::map<std::pair<std::string, std::string>, const vb::TransitionInfo*>& registry() {
+    static std::map<std::pair<std::string, std::string>, const vb::TransitionInfo*> r;
+    return r;
+}
+
+// ---- engine-side kernels -------------------------------------------------------------------------------
+// raw (AgentID) adds -> composite append log.  Validation as in the reference's add_edge! (ids must
+// name an existing slot of a registered type; :SingleType target must match).
+struct TranslateArgs {
+    const uint64_t* to; const uint64_t* from; uint64_t n;
+    uint32_t* log_to; uint32_t* log_from; uint64_t pos0;
+    uint32_t base[vb::MAX_AGENT_TYPES + 2]; uint32_t nslots[vb::MAX_AGENT_TYPES + 1];
+    uint32_t ntypes; int32_t target; int ignore_from; uint32_t* error;
+};
+__global__ void translate_edges_kernel(const TranslateArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint64_t to = a.to[i];
+    const uint32_t tt = vb::type_nr(to);
+    const uint64_t tnr = vb::agent_nr(to);
+    uint32_t row = 0;
+    if (tt < 1 || tt > a.ntypes || tnr < 1 || tnr > a.nslots[tt]) { atomicOr(a.error, (uint32_t)vb::DERR_BAD_ID); }
+    else if (a.target) { if ((int)tt != a.target) atomicOr(a.error, (uint32_t)vb::DERR_SINGLETYPE_MISMATCH); row = (uint32_t)(tnr - 1); }
+    else row = a.base[tt] + (uint32_t)(tnr - 1);
+    a.log_to[a.pos0 + i] = row;
+    if (!a.ignore_from) {
+        const uint64_t fr = a.from[i];
+        const uint32_t ft = vb::type_nr(fr);
+        const uint64_t fnr = vb::agent_nr(fr);
+        uint32_t c = 0;
+        if (ft < 1 || ft > a.ntypes || fnr < 1 || fnr > a.nslots[ft]) atomicOr(a.error, (uint32_t)vb::DERR_BAD_ID);
+        else c = a.base[ft] + (uint32_t)(fnr - 1);
+        a.log_from[a.pos0 + i] = c;
+    }
+}
+__global__ void count_adds_kernel(const uint32_t* __restrict__ rows, uint64_t n, uint32_t* __restrict__ cnt, int flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag) cnt[rows[i]] = 1u; else atomicAdd(&cnt[rows[i]], 1u);
+}
+// keep only the last entry of every run of equal keys (:SingleEdge "overwrite the slot", EdgeMethods.jl:441-445);
+// flags a run whose entries differ (second add with another value asserts for Dict containers, :267-293)
+__global__ void last_of_run_flags_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == n - 1 || keys[i + 1] != keys[i]) ? 1u : 0u;
+}
+__global__ void single_edge_conflict_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ from, const uint8_t* __restrict__ st,
+                                            uint32_t st_stride, uint32_t word, uint32_t ncols, uint32_t n, uint32_t* conflict) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n || keys[i] != keys[i + 1]) return;
+    bool diff = from && from[i] != from[i + 1];
+    for (uint32_t c = 0; st && c < ncols && !diff; ++c)
+        for (uint32_t b = 0; b < word; ++b)
+            if (st[(size_t)c * st_stride * word + (size_t)i * word + b] != st[(size_t)c * st_stride * word + (size_t)(i + 1) * word + b]) { diff = true; break; }
+    if (diff) *conflict = 1u;
+}
+__global__ void compact_u32_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t n,
+                                   uint32_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = in[i];
+}
+__global__ void compact_soa_kernel(const uint8_t* __restrict__ in, uint32_t istride, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos,
+                                   uint32_t n, uint8_t* __restrict__ out, uint32_t ostride, uint32_t word, uint32_t ncols) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n * ncols) return;
+    const uint32_t i = (uint32_t)(t % n), c = (uint32_t)(t / n);
+    if (!flag[i]) return;
+    for (uint32_t b = 0; b < word; ++b) out[(size_t)c * ostride * word + (size_t)pos[i] * word + b] = in[(size_t)c * istride * word + (size_t)i * word + b];
+}
+__global__ void gather_soa_kernel(const uint8_t* __restrict__ in, uint32_t istride, const uint32_t* __restrict__ perm, uint32_t n, uint8_t* __restrict__ out,
+                                  uint32_t ostride, uint32_t word, uint32_t ncols) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n * ncols) return;
+    const uint32_t i = (uint32_t)(t % n), c = (uint32_t)(t / n);
+    const uint32_t s = perm[i];
+    for (uint32_t b = 0; b < word; ++b) out[(size_t)c * ostride * word + (size_t)i * word + b] = in[(size_t)c * istride * word + (size_t)s * word + b];
+}
+// merge an existing CSR (old) with newly sorted edges (new, run offsets noff): row r of the result is
+// old row r followed by the new entries of r — push! order (EdgeMethods.jl:495-496).  single_edge: a new
+// entry replaces the old one.
+struct MergeArgs {
+    const uint32_t* ooff; const uint32_t* osrc; const uint8_t* ost; uint32_t ostride; uint32_t orows;
+    const uint32_t* noff; const uint32_t* nsrc; const uint8_t* nst; uint32_t nstride;
+    const uint32_t* off; uint32_t* src; uint8_t* st; uint32_t stride;
+    uint32_t rows; uint32_t word, ncols; int single_edge;
+};
+__global__ void merge_counts_kernel(const uint32_t* __restrict__ ooff, uint32_t orows, const uint32_t* __restrict__ ncnt, uint32_t rows, int single_edge,
+                                    uint32_t* __restrict__ cnt) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > rows) return;
+    if (r == rows) { cnt[r] = 0; return; }
+    const uint32_t o = r < orows ? ooff[r + 1] - ooff[r] : 0;
+    const uint32_t nn = ncnt[r];
+    cnt[r] = single_edge ? (nn ? 1u : o) : o + nn;
+}
+__global__ void merge_copy_kernel(const MergeArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.rows) return;
+    uint32_t d = a.off[r];
+    const uint32_t nb = a.noff[r], ne = a.noff[r + 1];
+    if (!(a.single_edge && ne > nb) && r < a.orows) {
+        for (uint32_t k = a.ooff[r]; k < a.ooff[r + 1]; ++k, ++d) {
+            if (a.src) a.src[d] = a.osrc[k];
+            for (uint32_t c = 0; a.st && c < a.ncols; ++c)
+                for (uint32_t b = 0; b < a.word; ++b)
+                    a.st[(size_t)c * a.stride * a.word + (size_t)d * a.word + b] = a.ost[(size_t)c * a.ostride * a.word + (size_t)k * a.word + b];
+        }
+    }
+    for (uint32_t k = a.single_edge ? (ne > nb ? ne - 1 : ne) : nb; k < ne; ++k, ++d) {
+        if (a.src) a.src[d] = a.nsrc[k];
+        for (uint32_t c = 0; a.st && c < a.ncols; ++c)
+            for (uint32_t b = 0; b < a.word; ++b)
+                a.st[(size_t)c * a.stride * a.word + (size_t)d * a.word + b] = a.nst[(size_t)c * a.nstride * a.word + (size_t)k * a.word + b];
+    }
+}
+// dead-agent edge purge (src/AgentMethods.jl:314-358, src/EdgeMethods.jl:606-631,897-920): drop rows whose
+// target died this apply and entries whose source died; `dead` is indexed by composite agent index.
+struct PurgeArgs {
+    const uint32_t* off; const uint32_t* src; const uint8_t* st; uint32_t stride; uint32_t rows;
+    const uint8_t* dead; uint32_t row_base;   // composite index of row 0 (SingleType: base[target], else 0)
+    int check_src;
+    uint32_t* cnt;                            // out: kept entries per row [rows + 1]
+    const uint32_t* noff; uint32_t* nsrc; uint8_t* nst; uint32_t nstride; uint32_t word, ncols;
+};
+__global__ void purge_count_kernel(const PurgeArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > a.rows) return;
+    if (r == a.rows) { a.cnt[r] = 0; return; }
+    uint32_t keep = 0;
+    if (!a.dead[a.row_base + r]) {
+        if (!a.check_src) keep = a.off[r + 1] - a.off[r];
+        else for (uint32_t k = a.off[r]; k < a.off[r + 1]; ++k) keep += a.dead[a.src[k]] ? 0u : 1u;
+    }
+    a.cnt[r] = keep;
+}
+__global__ void purge_copy_kernel(const PurgeArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.rows || a.dead[a.row_base + r]) return;
+    uint32_t d = a.noff[r];
+    for (uint32_t k = a.off[r]; k < a.off[r + 1]; ++k) {
+        if (a.check_src && a.dead[a.src[k]]) continue;
+        if (a.nsrc) a.nsrc[d] = a.src[k];
+        for (uint32_t c = 0; a.nst && c < a.ncols; ++c)
+            for (uint32_t b = 0; b < a.word; ++b)
+                a.nst[(size_t)c * a.nstride * a.word + (size_t)d * a.word + b] = a.st[(size_t)c * a.stride * a.word + (size_t)k * a.word + b];
+        ++d;
+    }
+}
+__global__ void purge_rows_cnt_kernel(uint32_t* __restrict__ cnt, uint32_t rows, const uint8_t* __restrict__ dead, uint32_t row_base) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows && dead[row_base + r]) cnt[r] = 0;
+}
+__global__ void mark_dead_kernel(const uint32_t* __restrict__ flag, uint32_t n, uint8_t* __restrict__ dead, uint32_t base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) dead[base + i] = 1;
+}
+// composite index rebase after an agent type's capacity grew (bases of later types shift)
+struct RebaseArgs { uint32_t old_base[vb::MAX_AGENT_TYPES + 2]; uint32_t new_base[vb::MAX_AGENT_TYPES + 2]; uint32_t ntypes; };
+__global__ void rebase_values_kernel(uint32_t* __restrict__ v, uint64_t n, const RebaseArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = v[i];
+    uint32_t t = 1;
+    while (t < a.ntypes && c >= a.old_base[t + 1]) ++t;
+    v[i] = c - a.old_base[t] + a.new_base[t];
+}
+__global__ void rebase_rows_kernel(const uint32_t* __restrict__ ooff, uint32_t orows, uint32_t* __restrict__ noff, uint32_t nrows, const RebaseArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > nrows) return;
+    if (r == nrows) { noff[r] = ooff[orows]; return; }
+    uint32_t t = 1;
+    while (t < a.ntypes && r >= a.new_base[t + 1]) ++t;
+    const uint32_t slot = (uint32_t)r - a.new_base[t];
+    const uint32_t ocap = a.old_base[t + 1] - a.old_base[t];
+    // rows that did not exist before point at the end of their type's old segment (empty row)
+    noff[r] = slot < ocap ? ooff[a.old_base[t] + slot] : ooff[a.old_base[t + 1]];
+}
+__global__ void rebase_cnt_kernel(const uint32_t* __restrict__ ocnt, uint32_t orows, uint32_t* __restrict__ ncnt, uint32_t nrows, const RebaseArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    uint32_t t = 1;
+    while (t < a.ntypes && r >= a.new_base[t + 1]) ++t;
+    const uint32_t slot = (uint32_t)r - a.new_base[t];
+    const uint32_t ocap = a.old_base[t + 1] - a.old_base[t];
+    ncnt[r] = (slot < ocap && a.old_base[t] + slot < orows) ? ocnt[a.old_base[t] + slot] : 0;
+}
+__global__ void comp_to_id_kernel(const uint32_t* __restrict__ comp, uint64_t n, uint64_t* __restrict__ ids, const RebaseArgs a, uint32_t rank) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = comp[i];
+    uint32_t t = 1;
+    while (t < a.ntypes && c >= a.old_base[t + 1]) ++t;
+    ids[i] = vb::agent_id(t, rank, (uint64_t)(c - a.old_base[t]) + 1);
+}
+__global__ void raster_cells_kernel(const uint64_t* __restrict__ ids, uint64_t n, uint32_t* __restrict__ cells, const RebaseArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cells[i] = a.new_base[vb::type_nr(ids[i])] + (uint32_t)(vb::agent_nr(ids[i]) - 1);
+}
+
+// mapreduce (src/AgentMethods.jl:533-565, src/EdgeMethods.jl:972-994): map = field at byte offset (optionally
+// compared with a constant, or the constant 1), fold with op.  Integer results are exact and order free;
+// floating point uses a fixed reduction tree (deterministic run to run, within 1e-12 relative of the
+// reference's left fold — tests state the tolerance).
+struct MapArgs {
+    const uint8_t* cols; uint64_t stride; uint32_t word; uint64_t n; const uint8_t* died;
+    int offset; int dt; int has_cmp; long long cmp; int op;
+};
+template <bool FLOAT> struct Acc { typedef long long T; };
+template <> struct Acc<true> { typedef double T; };
+template <bool FLOAT>
+__device__ __forceinline__ typename Acc<FLOAT>::T mr_identity(int op) {
+    typedef typename Acc<FLOAT>::T T;
+    switch (op) {
+        case vb::OP_PROD: return (T)1;
+        case vb::OP_MIN: return FLOAT ? (T)INFINITY : (T)INT64_MAX;
+        case vb::OP_MAX: return FLOAT ? (T)-INFINITY : (T)(-INT64_MAX - 1);
+        case vb::OP_AND: return (T)-1;
+        default: return (T)0;
+    }
+}
+template <bool FLOAT>
+__device__ __forceinline__ typename Acc<FLOAT>::T mr_fold(typename Acc<FLOAT>::T a, typename Acc<FLOAT>::T b, int op) {
+    typedef typename Acc<FLOAT>::T T;
+    switch (op) {
+        case vb::OP_SUM: return FLOAT ? a + b : (T)((unsigned long long)a + (unsigned long long)b);
+        case vb::OP_PROD: return FLOAT ? a * b : (T)((unsigned long long)a * (unsigned long long)b);
+        case vb::OP_MIN: return a < b ? a : b;
+        case vb::OP_MAX: return a > b ? a : b;
+        case vb::OP_AND: return (T)((long long)a & (long long)b);
+        default: return (T)((long long)a | (long long)b);
+    }
+}
+template <bool FLOAT>
+__device__ __forceinline__ typename Acc<FLOAT>::T mr_load(const MapArgs& a, uint64_t i) {
+    typedef typename Acc<FLOAT>::T T;
+    if (a.dt < 0) return (T)1;
+    long long iv = 0;
+    double fv = 0;
+    bool isf = false;
+    const uint32_t w = a.word;
+    switch (a.dt) {
+        case vb::DT_I64: iv = vb::soa_load_field<long long>(a.cols, (uint32_t)a.stride, w, (uint32_t)i, a.offset); break;
+        case vb::DT_F64: fv = vb::soa_load_field<double>(a.cols, (uint32_t)a.stride, w, (uint32_t)i, a.offset); isf = true; break;
+        case vb::DT_I32: iv = vb::soa_load_field<int>(a.cols, (uint32_t)a.stride, w, (uint32_t)i, a.offset); break;
+        case vb::DT_F32: fv = vb::soa_load_field<float>(a.cols, (uint32_t)a.stride, w, (uint32_t)i, a.offset); isf = true; break;
+        default: iv = vb::soa_load_field<uint8_t>(a.cols, (uint32_t)a.stride, w, (uint32_t)i, a.offset); break;
+    }
+    if (a.has_cmp) { iv = isf ? (fv == (double)a.cmp) : (iv == a.cmp); isf = false; }
+    return isf ? (T)fv : (T)iv;
+}
+template <bool FLOAT>
+__global__ void __launch_bounds__(256) mapreduce_kernel(const MapArgs a, typename Acc<FLOAT>::T* __restrict__ partial) {
+    typedef typename Acc<FLOAT>::T T;
+    __shared__ T sm[8];
+    T acc = mr_identity<FLOAT>(a.op);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (a.died && a.died[i]) continue;
+        acc = mr_fold<FLOAT>(mr_load<FLOAT>(a, i), acc, a.op);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = mr_fold<FLOAT>(acc, __shfl_xor_sync(0xffffffffu, acc, o), a.op);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T v = threadIdx.x < 8 ? sm[threadIdx.x] : mr_identity<FLOAT>(a.op);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v = mr_fold<FLOAT>(v, __shfl_xor_sync(0xffffffffu, v, o), a.op);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+template <bool FLOAT>
+__global__ void __launch_bounds__(256) mapreduce_final_kernel(const typename Acc<FLOAT>::T* __restrict__ partial, uint32_t n, int op,
+                                                            typename Acc<FLOAT>::T* __restrict__ out) {
+    typedef typename Acc<FLOAT>::T T;
+    __shared__ T sm[8];
+    T acc = mr_identity<FLOAT>(op);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) acc = mr_fold<FLOAT>(partial[i], acc, op);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = mr_fold<FLOAT>(acc, __shfl_xor_sync(0xffffffffu, acc, o), op);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T v = sm[0];
+        for (int i = 1; i < 8; ++i) v = mr_fold<FLOAT>(v, sm[i], op);
+        *out = v;
+    }
+}
+__global__ void field_out_kernel(const uint8_t* __restrict__ cols, uint32_t stride, uint32_t word, const uint32_t* __restrict__ cells, uint32_t cbase,
+                                 uint64_t n, int offset, uint32_t fsize, uint8_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = cells[i] - cbase;
+    for (uint32_t b = 0; b < fsize; ++b) {
+        const uint32_t p = offset + b, c = p / word;
+        out[i * fsize + b] = cols[(size_t)c * stride * word + (size_t)s * word + (p - c * word)];
+    }
+}
+__global__ void raster_num_edges_kernel(const uint32_t* __restrict__ cells, uint64_t n, const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
+                                        uint32_t rows, uint32_t row_shift, long long* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = cells[i] - row_shift;
+    out[i] = r < rows ? (off ? (long long)(off[r + 1] - off[r]) : (long long)cnt[r]) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+struct AgentStore {
+    std::string name;
+    uint32_t size = 0, hints = 0, word = 0, ncols = 0;
+    bool immortal = false, independent = false, stateless = false;
+    uint32_t cap = 0;
+    uint8_t* state[2] = {nullptr, nullptr};
+    uint8_t* died[2] = {nullptr, nullptr};
+    int cur = 0;                 // state[cur] / died[cur] is the read buffer
+    uint32_t* reuse = nullptr;
+    uint32_t reuse_cap = 0, n_reuse = 0;
+    uint32_t nslots = 0;         // length(read.state) == length(write.state) between applies
+    uint64_t nextid = 1;
+    bool write_stale = false;    // the write buffer does not hold the current states (after a swap)
+    bool writeable = false, prepared = false;
+    int64_t last_change = 0;
+    uint32_t births = 0;         // births of the running apply
+    uint8_t* rstate() const { return state[cur]; }
+    uint8_t* wstate() const { return independent ? state[cur] : state[cur ^ 1]; }
+    uint8_t* rdied() const { return died[cur]; }
+    uint8_t* wdied() const { return died[cur ^ 1]; }
+};
+
+struct RawChunk { uint64_t* to = nullptr; uint64_t* from = nullptr; uint8_t* st = nullptr; uint64_t n = 0; };
+
+struct EdgeStore {
+    std::string name;
+    uint32_t size = 0, hints = 0, word = 0, ncols = 0;
+    int32_t target = 0;
+    uint64_t size_hint = 0;
+    bool stateless = false, ignorefrom = false, singleedge = false, singletype = false;
+    uint8_t kind = vb::KIND_CSR;
+    // read container
+    uint32_t* off = nullptr; uint32_t rows = 0;
+    uint32_t* src = nullptr; uint8_t* st = nullptr; uint32_t nnz = 0, st_cap = 0;
+    uint32_t* cnt = nullptr;
+    // write container of the running apply
+    uint32_t* log_to = nullptr; uint32_t* log_from = nullptr; uint8_t* log_st = nullptr;
+    uint32_t log_n = 0, log_cap = 0;
+    uint32_t* wcnt = nullptr; uint32_t rows_w = 0;
+    // raw adds from the host API (AgentIDs, AoS states) awaiting translation, in call order
+    std::vector<uint64_t> h_to, h_from; std::vector<uint8_t> h_st;
+    std::vector<RawChunk> chunks;
+    uint64_t raw_n = 0;
+    // :SingleEdge double-add detection at add time for host adds (EdgeMethods.jl:267-293)
+    std::unordered_map<uint64_t, std::pair<uint64_t, std::vector<uint8_t>>> single_seen;
+    bool readable = false, writeable = false, add_existing = false;
+    int64_t last_change = 0;
+    bool has_src() const { return !ignorefrom; }
+    bool has_state() const { return !stateless && size > 0; }
+};
+
+struct RasterStore {
+    std::string name;
+    std::vector<int64_t> dims;
+    int type = 0;
+    std::vector<uint64_t> ids;    // host copy (column-major)
+    uint32_t* cells = nullptr;    // device composite indices (rebuilt when bases change)
+};
+
+}  // namespace
+
+struct vb_sim {
+    std::string name;
+    std::vector<AgentStore> agents;   // index = type id - 1
+    std::vector<EdgeStore> edges;
+    std::vector<RasterStore> rasters;
+    std::vector<uint8_t> params;
+    bool initialized = false, intransition = false;
+    int64_t num_transitions = 0;
+    bool asserts_enabled = true, check_readable = true;
+    bool all_immortal = true;
+    uint32_t rank = 0;
+    uint32_t base[vb::MAX_AGENT_TYPES + 2] = {0};
+    vb::DeviceSim* d_ds = nullptr;
+    uint32_t* d_error = nullptr;
+    uint32_t* d_scalars = nullptr;          // small device scratch for totals
+    unsigned long long* d_stats = nullptr;
+    // stats of the last apply
+    double ms_rw = 0, ms_fin = 0;
+    uint64_t st_edges_read = 0, st_edges_appended = 0, st_agents_called = 0, st_launches = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+
+    AgentStore& A(int t) { if (t < 1 || t > (int)agents.size()) throw ArgError("unknown agent type id"); return agents[t - 1]; }
+    EdgeStore& E(int e) { if (e < 0 || e >= (int)edges.size()) throw ArgError("unknown edge type index"); return edges[e]; }
+    void mayassert(bool c, const char* m) const { if (asserts_enabled && !c) throw AssertionError(m); }
+    uint32_t total_slots() const { return base[agents.size() + 1]; }
+    uint32_t rows_of(const EdgeStore& e) const { return e.singletype ? agents[e.target - 1].cap : base[agents.size() + 1]; }
+    uint32_t row_base_of(const EdgeStore& e) const { return e.singletype ? base[e.target] : 0; }
+
+    ~vb_sim();
+    void compute_bases(uint32_t* out) const;
+    void ensure_agent_cap(int t, uint64_t need);
+    void rebase(const uint32_t* old_base);
+    void upload_view(uint64_t seed);
+    void check_device_error(const char* where);
+    void flush_raw(int e);
+    void merge_pending(int e);
+    void merge_all_pending() { for (size_t e = 0; e < edges.size(); ++e) merge_pending((int)e); }
+    void ensure_log(EdgeStore& es, uint64_t need);
+    void build_container(int e, bool add_existing);
+    void purge_dead(const uint8_t* dead);
+    uint64_t edge_total(int e, bool write);
+};
+
+namespace {
+
+void free_agent(AgentStore& a) {
+    dfree(a.state[0]); if (a.state[1] != a.state[0]) dfree(a.state[1]);
+    dfree(a.died[0]); dfree(a.died[1]); dfree(a.reuse);
+    a.state[0] = a.state[1] = a.died[0] = a.died[1] = nullptr; a.reuse = nullptr;
+}
+void free_edge_read(EdgeStore& e) {
+    dfree(e.off); dfree(e.src); dfree(e.st); dfree(e.cnt);
+    e.off = e.src = e.cnt = nullptr; e.st = nullptr; e.nnz = e.st_cap = 0; e.rows = 0;
+}
+void free_edge_log(EdgeStore& e) {
+    dfree(e.log_to); dfree(e.log_from); dfree(e.log_st); dfree(e.wcnt);
+    e.log_to = e.log_from = e.wcnt = nullptr; e.log_st = nullptr; e.log_n = e.log_cap = 0; e.rows_w = 0;
+}
+void free_chunks(EdgeStore& e) {
+    for (auto& c : e.chunks) { dfree(c.to); dfree(c.from); dfree(c.st); }
+    e.chunks.clear();
+}
+
+}  // namespace
+
+vb_sim::~vb_sim() {
+    for (auto& a : agents) free_agent(a);
+    for (auto& e : edges) { free_edge_read(e); free_edge_log(e); free_chunks(e); }
+    for (auto& r : rasters) dfree(r.cells);
+    dfree(d_ds); dfree(d_error); dfree(d_scalars); dfree(d_stats);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+}
+
+void vb_sim::compute_bases(uint32_t* out) const {
+    uint64_t run = 0;
+    out[0] = 0;
+    for (size_t t = 1; t <= agents.size(); ++t) { out[t] = (uint32_t)run; run += agents[t - 1].cap; }
+    if (run >= 0xffffffffull) throw ArgError("more than 2^32-1 agent slots on one rank are not supported by the 32-bit composite index");
+    out[agents.size() + 1] = (uint32_t)run;
+}
+
+// grow the buffers of agent type t to hold `need` slots; composite bases of later types shift (rebase)
+void vb_sim::ensure_agent_cap(int t, uint64_t need) {
+    AgentStore& a = A(t);
+    if (need <= a.cap) return;
+    uint64_t ncap = std::max<uint64_t>(need, (uint64_t)a.cap + a.cap / 2);
+    ncap = (ncap + 255) / 256 * 256;
+    if (ncap >= 0xffffffffull) throw ArgError("agent type too large for 32-bit slots");
+    uint32_t old_base[vb::MAX_AGENT_TYPES + 2];
+    std::memcpy(old_base, base, sizeof(old_base));
+    const bool had = a.cap > 0;
+    const int nb = a.independent ? 1 : 2;
+    if (a.size) {
+        for (int b = 0; b < nb; ++b) {
+            uint8_t* n = (uint8_t*)g_pool.alloc(ncap * a.size);
+            if (had) {
+                vbp::soa_copy_kernel<<<nblk((uint64_t)a.cap * a.size), 256, 0, g_stream>>>(a.state[b], a.cap, n, ncap, a.cap, a.ncols, a.word, 0, 0);
+                LAUNCH_CHECK();
+            }
+            dfree(a.state[b]);
+            a.state[b] = n;
+        }
+        if (a.independent) a.state[1] = a.state[0];
+    }
+    if (!a.immortal) {
+        for (int b = 0; b < 2; ++b) {
+            uint8_t* n = (uint8_t*)g_pool.alloc(ncap);
+            CK(cudaMemsetAsync(n, 0, ncap, g_stream));
+            if (had) CK(cudaMemcpyAsync(n, a.died[b], a.cap, cudaMemcpyDeviceToDevice, g_stream));
+            dfree(a.died[b]);
+            a.died[b] = n;
+        }
+        uint32_t* r = dalloc<uint32_t>(ncap);
+        if (a.n_reuse) CK(cudaMemcpyAsync(r, a.reuse, (size_t)a.n_reuse * 4, cudaMemcpyDeviceToDevice, g_stream));
+        dfree(a.reuse);
+        a.reuse = r;
+        a.reuse_cap = (uint32_t)ncap;
+    }
+    a.cap = (uint32_t)ncap;
+    compute_bases(base);
+    rebase(old_base);
+}
+
+// after capacities changed: remap every stored composite index (CSR columns, rows of containers that are
+// keyed by all agent types, append logs, raster cell tables)
+void vb_sim::rebase(const uint32_t* old_base) {
+    RebaseArgs ra;
+    std::memcpy(ra.old_base, old_base, sizeof(ra.old_base));
+    std::memcpy(ra.new_base, base, sizeof(ra.new_base));
+    ra.ntypes = (uint32_t)agents.size();
+    bool same = true;
+    for (size_t t = 0; t <= agents.size() + 1; ++t) same &= ra.old_base[t] == ra.new_base[t];
+    for (auto& e : edges) {
+        if (!same && e.src && e.nnz) { rebase_values_kernel<<<nblk(e.nnz), 256, 0, g_stream>>>(e.src, e.nnz, ra); LAUNCH_CHECK(); }
+        if (!same && e.log_from && e.log_n) { rebase_values_kernel<<<nblk(e.log_n), 256, 0, g_stream>>>(e.log_from, e.log_n, ra); LAUNCH_CHECK(); }
+        const uint32_t nrows = rows_of(e);
+        if (!e.singletype) {
+            if (!same && e.log_to && e.log_n) { rebase_values_kernel<<<nblk(e.log_n), 256, 0, g_stream>>>(e.log_to, e.log_n, ra); LAUNCH_CHECK(); }
+            if (e.off && nrows != e.rows) {
+                uint32_t* noff = dalloc<uint32_t>((size_t)nrows + 1);
+                rebase_rows_kernel<<<nblk((uint64_t)nrows + 1), 256, 0, g_stream>>>(e.off, e.rows, noff, nrows, ra); LAUNCH_CHECK();
+                dfree(e.off); e.off = noff; e.rows = nrows;
+            }
+            if (e.cnt && nrows != e.rows) {
+                uint32_t* nc = dalloc<uint32_t>((size_t)nrows + 1);
+                rebase_cnt_kernel<<<nblk(nrows), 256, 0, g_stream>>>(e.cnt, e.rows, nc, nrows, ra); LAUNCH_CHECK();
+                dfree(e.cnt); e.cnt = nc; e.rows = nrows;
+            }
+            if (e.wcnt && nrows != e.rows_w) {
+                uint32_t* nc = dalloc<uint32_t>((size_t)nrows + 1);
+                rebase_cnt_kernel<<<nblk(nrows), 256, 0, g_stream>>>(e.wcnt, e.rows_w, nc, nrows, ra); LAUNCH_CHECK();
+                dfree(e.wcnt); e.wcnt = nc; e.rows_w = nrows;
+            }
+        } else {
+            // rows are the slots of the target type only: extend with empty rows
+            if (e.off && nrows > e.rows) {
+                uint32_t* noff = dalloc<uint32_t>((size_t)nrows + 1);
+                CK(cudaMemcpyAsync(noff, e.off, ((size_t)e.rows + 1) * 4, cudaMemcpyDeviceToDevice, g_stream));
+                vbp::fill_u32_kernel<<<nblk(nrows - e.rows), 256, 0, g_stream>>>(noff + e.rows + 1, nrows - e.rows, e.nnz); LAUNCH_CHECK();
+                dfree(e.off); e.off = noff; e.rows = nrows;
+            }
+            if (e.cnt && nrows > e.rows) {
+                uint32_t* nc = dalloc<uint32_t>((size_t)nrows + 1);
+                CK(cudaMemsetAsync(nc, 0, ((size_t)nrows + 1) * 4, g_stream));
+                CK(cudaMemcpyAsync(nc, e.cnt, (size_t)e.rows * 4, cudaMemcpyDeviceToDevice, g_stream));
+                dfree(e.cnt); e.cnt = nc; e.rows = nrows;
+            }
+            if (e.wcnt && nrows > e.rows_w) {
+                uint32_t* nc = dalloc<uint32_t>((size_t)nrows + 1);
+                CK(cudaMemsetAsync(nc, 0, ((size_t)nrows + 1) * 4, g_stream));
+                CK(cudaMemcpyAsync(nc, e.wcnt, (size_t)e.rows_w * 4, cudaMemcpyDeviceToDevice, g_stream));
+                dfree(e.wcnt); e.wcnt = nc; e.rows_w = nrows;
+            }
+        }
+    }
+    for (auto& r : rasters) {
+        if (!r.cells) r.cells = dalloc<uint32_t>(r.ids.size());
+        uint64_t* tmp = dalloc<uint64_t>(r.ids.size());
+        CK(cudaMemcpyAsync(tmp, r.ids.data(), r.ids.size() * 8, cudaMemcpyHostToDevice, g_stream));
+        raster_cells_kernel<<<nblk(r.ids.size()), 256, 0, g_stream>>>(tmp, r.ids.size(), r.cells, ra); LAUNCH_CHECK();
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(tmp);
+    }
+}
+
+void vb_sim::upload_view(uint64_t seed) {
+    static thread_local vb::DeviceSim h;
+    std::memset(&h, 0, sizeof(h));
+    for (size_t t = 1; t <= agents.size(); ++t) {
+        const AgentStore& a = agents[t - 1];
+        vb::AgentView& v = h.agents[t];
+        v.state_r = a.rstate(); v.state_w = a.wstate();
+        v.died_r = a.immortal ? nullptr : a.rdied(); v.died_w = a.immortal ? nullptr : a.wdied();
+        v.reuse = a.reuse; v.cap = a.cap; v.nslots_r = a.nslots;
+        v.n_reuse = a.n_reuse; v.next0 = (uint32_t)(a.nextid - 1);
+        v.size = a.size; v.word = a.word ? a.word : 1; v.ncols = a.ncols;
+        v.immortal = a.immortal; v.independent = a.independent; v.readable = a.prepared; v.writeable = a.writeable;
+    }
+    for (size_t i = 0; i < edges.size(); ++i) {
+        const EdgeStore& e = edges[i];
+        vb::EdgeView& v = h.edges[i];
+        v.off = e.off; v.src = e.src; v.st = e.st; v.cnt = e.cnt; v.rows = e.rows; v.st_cap = e.st_cap;
+        v.log_to = e.log_to; v.log_from = e.log_from; v.log_st = e.log_st; v.wcnt = e.wcnt; v.log_cap = e.log_cap; v.rows_w = e.rows_w;
+        v.size = e.size; v.word = e.word ? e.word : 1; v.ncols = e.ncols; v.target = e.singletype ? e.target : 0;
+        v.hints = (uint8_t)e.hints; v.kind = e.kind; v.readable = e.readable; v.writeable = e.writeable;
+    }
+    for (size_t i = 0; i < rasters.size(); ++i) {
+        vb::RasterView& v = h.rasters[i];
+        v.cells = rasters[i].cells; v.ndims = (int)rasters[i].dims.size(); v.type = rasters[i].type;
+        for (size_t k = 0; k < rasters[i].dims.size(); ++k) v.dims[k] = rasters[i].dims[k];
+    }
+    std::memcpy(h.base, base, sizeof(h.base));
+    h.n_agent_types = (uint32_t)agents.size(); h.n_edge_types = (uint32_t)edges.size(); h.n_rasters = (uint32_t)rasters.size();
+    h.rank = rank; h.check = asserts_enabled && check_readable; h.error = d_error; h.seed = seed;
+    if (!params.empty()) std::memcpy(h.params, params.data(), params.size());
+    CK(cudaMemcpyAsync(d_ds, &h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));   // `h` is reused by the next upload
+}
+
+void vb_sim::check_device_error(const char* where) {
+    uint32_t err = 0;
+    CK(cudaMemcpyAsync(&err, d_error, 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    if (!err) return;
+    CK(cudaMemsetAsync(d_error, 0, 4, g_stream));
+    std::string m = std::string(where) + ":";
+    if (err & vb::DERR_EDGE_NOT_READABLE) m += " an edge type was accessed that is not in the `read` argument;";
+    if (err & vb::DERR_AGENT_NOT_READABLE) m += " an agent type was accessed that is not in the `read` argument;";
+    if (err & vb::DERR_AGENT_TYPE_MISMATCH) m += " the id of an agent does not match the given type;";
+    if (err & vb::DERR_AGENT_DIED) m += " agentstate was requested for an agent that has been removed;";
+    if (err & vb::DERR_IMMORTAL_DIED) m += " `nothing` was returned for an :Immortal agent;";
+    if (err & vb::DERR_ACCESSOR_UNAVAILABLE) m += " an accessor was used that is not defined for the edge type's hint combination;";
+    if (err & vb::DERR_BAD_ID) m += " an agent id does not name an existing agent;";
+    if (err & vb::DERR_EDGE_NOT_DECLARED) m += " add_edge/add_agent on a type the transition did not declare in EdgeWrites/AgentWrites;";
+    if (err & vb::DERR_SINGLETYPE_MISMATCH) m += " :SingleType edge used with an agent of another type;";
+    if (err & vb::DERR_RASTER_POS) m += " raster position out of range;";
+    if (err & vb::DERR_INDEX) m += " neighbour index out of range;";
+    throw AssertionError(m);
+}
+
+void vb_sim::ensure_log(EdgeStore& es, uint64_t need) {
+    if (need <= es.log_cap) return;
+    if (need >= 0xffffffffull) throw ArgError("more than 2^32-1 edges of one type on one rank are not supported");
+    uint64_t ncap = std::max<uint64_t>(need, (uint64_t)es.log_cap + es.log_cap / 2);
+    ncap = (ncap + 1023) / 1024 * 1024;
+    uint32_t* nt = dalloc<uint32_t>(ncap);
+    if (es.log_n) CK(cudaMemcpyAsync(nt, es.log_to, (size_t)es.log_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+    dfree(es.log_to); es.log_to = nt;
+    if (es.has_src()) {
+        uint32_t* nf = dalloc<uint32_t>(ncap);
+        if (es.log_n) CK(cudaMemcpyAsync(nf, es.log_from, (size_t)es.log_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+        dfree(es.log_from); es.log_from = nf;
+    }
+    if (es.has_state()) {
+        uint8_t* ns = (uint8_t*)g_pool.alloc(ncap * es.size);
+        if (es.log_n) { vbp::soa_copy_kernel<<<nblk((uint64_t)es.log_n * es.size), 256, 0, g_stream>>>(es.log_st, es.log_cap, ns, ncap, es.log_n, es.ncols, es.word, 0, 0); LAUNCH_CHECK(); }
+        dfree(es.log_st); es.log_st = ns;
+    }
+    es.log_cap = (uint32_t)ncap;
+}
+
+// host-staged raw adds -> one device chunk
+void vb_sim::flush_raw(int ei) {
+    EdgeStore& e = E(ei);
+    const uint64_t n = e.h_to.size();
+    if (!n) return;
+    RawChunk c;
+    c.n = n;
+    c.to = dalloc<uint64_t>(n);
+    CK(cudaMemcpyAsync(c.to, e.h_to.data(), n * 8, cudaMemcpyHostToDevice, g_stream));
+    if (e.has_src()) { c.from = dalloc<uint64_t>(n); CK(cudaMemcpyAsync(c.from, e.h_from.data(), n * 8, cudaMemcpyHostToDevice, g_stream)); }
+    if (e.has_state()) { c.st = (uint8_t*)g_pool.alloc(n * e.size); CK(cudaMemcpyAsync(c.st, e.h_st.data(), n * e.size, cudaMemcpyHostToDevice, g_stream)); }
+    CK(cudaStreamSynchronize(g_stream));
+    e.h_to.clear(); e.h_from.clear(); e.h_st.clear();
+    e.chunks.push_back(c);
+}
+
+// translate all raw chunks into the append log and fold them into the container as an add_existing write:
+// this is what makes add_edge! outside of transitions (init phase; test hacks after finish_init!) visible.
+void vb_sim::merge_pending(int ei) {
+    EdgeStore& e = E(ei);
+    flush_raw(ei);
+    if (e.chunks.empty()) return;
+    uint64_t total = 0;
+    for (auto& c : e.chunks) total += c.n;
+    const uint32_t rows = rows_of(e);
+    if (e.kind == vb::KIND_CSR) ensure_log(e, e.log_n + total);
+    else if (!e.wcnt) {
+        e.wcnt = dalloc<uint32_t>((size_t)rows + 1); e.rows_w = rows;
+        CK(cudaMemsetAsync(e.wcnt, 0, ((size_t)rows + 1) * 4, g_stream));
+        if (e.cnt) CK(cudaMemcpyAsync(e.wcnt, e.cnt, (size_t)std::min(rows, e.rows) * 4, cudaMemcpyDeviceToDevice, g_stream));
+    }
+    uint32_t* tmp_rows = e.kind == vb::KIND_CSR ? nullptr : dalloc<uint32_t>(total);
+    uint64_t pos = e.kind == vb::KIND_CSR ? e.log_n : 0;
+    for (auto& c : e.chunks) {
+        TranslateArgs ta{};
+        ta.to = c.to; ta.from = c.from; ta.n = c.n;
+        ta.log_to = e.kind == vb::KIND_CSR ? e.log_to : tmp_rows; ta.log_from = e.log_from; ta.pos0 = pos;
+        std::memcpy(ta.base, base, sizeof(ta.base));
+        for (size_t t = 1; t <= agents.size(); ++t) ta.nslots[t] = (uint32_t)std::max<uint64_t>(agents[t - 1].nslots, agents[t - 1].nextid - 1);
+        ta.ntypes = (uint32_t)agents.size(); ta.target = e.singletype ? e.target : 0; ta.ignore_from = !e.has_src() || e.kind != vb::KIND_CSR; ta.error = d_error;
+        translate_edges_kernel<<<nblk(c.n), 256, 0, g_stream>>>(ta); LAUNCH_CHECK();
+        if (e.kind == vb::KIND_CSR && e.has_state()) {
+            vbp::aos_to_soa_kernel<<<nblk(c.n * e.ncols), 256, 0, g_stream>>>(c.st, e.log_st, e.log_cap, pos, c.n, e.size, e.word); LAUNCH_CHECK();
+        }
+        pos += c.n;
+    }
+    check_device_error("add_edge!");
+    if (e.kind == vb::KIND_CSR) {
+        e.log_n = (uint32_t)pos;
+        build_container(ei, true);
+    } else {
+        count_adds_kernel<<<nblk(total), 256, 0, g_stream>>>(tmp_rows, total, e.wcnt, e.kind == vb::KIND_FLAG); LAUNCH_CHECK();
+        dfree(tmp_rows);
+        dfree(e.cnt); e.cnt = e.wcnt; e.rows = e.rows_w; e.wcnt = nullptr; e.rows_w = 0;
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    free_chunks(e);
+    e.raw_n = 0;
+}
+
+// finish_write! for one edge type: sorted append log (+ the existing container when add_existing) -> new
+// read container.  Per-target order = append order (stable sort), old entries first.
+void vb_sim::build_container(int ei, bool add_existing) {
+    EdgeStore& e = E(ei);
+    const uint32_t rows = rows_of(e);
+    if (e.kind != vb::KIND_CSR) {   // count / flag containers were written in place by the transition
+        if (!e.wcnt) { e.wcnt = dalloc<uint32_t>((size_t)rows + 1); e.rows_w = rows; CK(cudaMemsetAsync(e.wcnt, 0, ((size_t)rows + 1) * 4, g_stream)); }
+        dfree(e.cnt); e.cnt = e.wcnt; e.rows = e.rows_w; e.wcnt = nullptr; e.rows_w = 0;
+        return;
+    }
+    uint32_t n = e.log_n;
+    const bool have_old = add_existing && e.off && e.nnz > 0;
+    // --- sort the log by target row (stable) ---
+    uint32_t* skey = e.log_to; uint32_t* sfrom = e.log_from; uint8_t* sst = e.log_st; const uint32_t sstride = e.log_cap;
+    if (n > 1) {
+        const int bits = vbp::bits_for(rows);
+        const bool direct = e.has_state() && e.ncols == 1 && (e.word == 4 || e.word == 8);
+        const bool via_perm = e.has_state() && !direct;
+        // buffer set A = the log itself, set B = scratch of the same capacity; the sort ping-pongs between them
+        uint32_t* kA = e.log_to; uint32_t* kB = dalloc<uint32_t>(e.log_cap);
+        uint32_t* fA = e.log_from; uint32_t* fB = e.has_src() ? dalloc<uint32_t>(e.log_cap) : nullptr;
+        void* pA = nullptr; void* pB = nullptr; int p2b = 0;
+        if (direct) { p2b = (int)e.word; pA = e.log_st; pB = g_pool.alloc((size_t)e.log_cap * e.word); }
+        else if (via_perm) {
+            p2b = 4; pA = dalloc<uint32_t>(e.log_cap); pB = dalloc<uint32_t>(e.log_cap);
+            vbp::iota_u32_kernel<<<nblk(n), 256, 0, g_stream>>>((uint32_t*)pA, n); LAUNCH_CHECK();
+        }
+        uint32_t* scratch = dalloc<uint32_t>(vbp::rs_scratch_words(n));
+        g_launches += (unsigned long long)((bits + 7) / 8) * 5;
+        const int res = vbp::radix_sort(kA, kB, fA, fB, pA, pB, p2b, n, bits, scratch, g_stream);
+        CK(cudaGetLastError());
+        dfree(scratch);
+        if (res == 1) { std::swap(kA, kB); std::swap(fA, fB); std::swap(pA, pB); }   // A now holds the sorted data
+        e.log_to = kA; e.log_from = fA;
+        dfree(kB); dfree(fB);
+        if (direct) { e.log_st = (uint8_t*)pA; dfree(pB); }
+        else if (via_perm) {   // gather the state columns through the sort permutation
+            uint8_t* g = (uint8_t*)g_pool.alloc((size_t)e.log_cap * e.size);
+            gather_soa_kernel<<<nblk((uint64_t)n * e.ncols), 256, 0, g_stream>>>(e.log_st, e.log_cap, (const uint32_t*)pA, n, g, e.log_cap, e.word, e.ncols); LAUNCH_CHECK();
+            dfree(e.log_st); e.log_st = g;
+            dfree(pA); dfree(pB);
+        }
+        skey = e.log_to; sfrom = e.log_from; sst = e.log_st;
+    }
+    // --- :SingleEdge: the last add to a target wins; two different values for one target assert (Dict containers) ---
+    if (e.singleedge && n > 1) {
+        if (!e.singletype && asserts_enabled) {
+            CK(cudaMemsetAsync(d_scalars, 0, 4, g_stream));
+            single_edge_conflict_kernel<<<nblk(n), 256, 0, g_stream>>>(skey, sfrom, e.has_state() ? sst : nullptr, sstride, e.word, e.ncols, n, d_scalars); LAUNCH_CHECK();
+            uint32_t conflict = 0;
+            CK(cudaMemcpyAsync(&conflict, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            if (conflict) { e.log_n = 0; throw AssertionError("An edge has already been added to this agent (the edge type has the :SingleEdge hint)"); }
+        }
+        uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
+        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+        last_of_run_flags_kernel<<<nblk(n), 256, 0, g_stream>>>(skey, n, flag); LAUNCH_CHECK();
+        vbp::exclusive_scan(flag, pos, n, d_scalars, scr, g_stream); g_launches += 3;
+        uint32_t kept = 0;
+        CK(cudaMemcpyAsync(&kept, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (kept != n) {
+            uint32_t* nk = dalloc<uint32_t>(e.log_cap);
+            compact_u32_kernel<<<nblk(n), 256, 0, g_stream>>>(skey, flag, pos, n, nk); LAUNCH_CHECK();
+            dfree(e.log_to); e.log_to = nk; skey = nk;
+            if (e.has_src()) {
+                uint32_t* nf = dalloc<uint32_t>(e.log_cap);
+                compact_u32_kernel<<<nblk(n), 256, 0, g_stream>>>(sfrom, flag, pos, n, nf); LAUNCH_CHECK();
+                dfree(e.log_from); e.log_from = nf; sfrom = nf;
+            }
+            if (e.has_state()) {
+                uint8_t* ns = (uint8_t*)g_pool.alloc((size_t)e.log_cap * e.size);
+                compact_soa_kernel<<<nblk((uint64_t)n * e.ncols), 256, 0, g_stream>>>(sst, sstride, flag, pos, n, ns, e.log_cap, e.word, e.ncols); LAUNCH_CHECK();
+                dfree(e.log_st); e.log_st = ns; sst = ns;
+            }
+            n = kept; e.log_n = kept;
+        }
+        dfree(flag); dfree(pos); dfree(scr);
+    }
+    // --- row counts of the new entries -> offsets ---
+    uint32_t* ncnt = dalloc<uint32_t>((size_t)rows + 2);
+    CK(cudaMemsetAsync(ncnt, 0, ((size_t)rows + 2) * 4, g_stream));
+    if (n) { vbp::csr_run_counts_kernel<<<nblk(n), 256, 0, g_stream>>>(skey, n, ncnt); LAUNCH_CHECK(); }
+    uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words((uint64_t)rows + 1));
+    if (!have_old) {
+        uint32_t* off = dalloc<uint32_t>((size_t)rows + 2);
+        vbp::exclusive_scan(ncnt, off, (uint64_t)rows + 1, nullptr, scr, g_stream); g_launches += 3;
+        CK(cudaGetLastError());
+        free_edge_read(e);
+        e.off = off; e.rows = rows; e.nnz = n;
+        e.src = e.log_from; e.st = e.log_st; e.st_cap = e.log_cap;       // the sorted log becomes the container
+        e.log_from = nullptr; e.log_st = nullptr;
+        dfree(e.log_to); e.log_to = nullptr; e.log_n = 0; e.log_cap = 0;
+    } else {
+        uint32_t* noff = dalloc<uint32_t>((size_t)rows + 2);
+        vbp::exclusive_scan(ncnt, noff, (uint64_t)rows + 1, nullptr, scr, g_stream); g_launches += 3;   // run offsets of the new entries
+        uint32_t* cnt = dalloc<uint32_t>((size_t)rows + 2);
+        merge_counts_kernel<<<nblk((uint64_t)rows + 1), 256, 0, g_stream>>>(e.off, e.rows, ncnt, rows, e.singleedge, cnt); LAUNCH_CHECK();
+        uint32_t* off = dalloc<uint32_t>((size_t)rows + 2);
+        vbp::exclusive_scan(cnt, off, (uint64_t)rows + 1, d_scalars, scr, g_stream); g_launches += 3;
+        uint32_t total = 0;
+        CK(cudaMemcpyAsync(&total, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        const uint32_t cap = std::max<uint32_t>(total, 1);
+        MergeArgs ma{};
+        ma.ooff = e.off; ma.osrc = e.src; ma.ost = e.st; ma.ostride = e.st_cap; ma.orows = e.rows;
+        ma.noff = noff; ma.nsrc = sfrom; ma.nst = sst; ma.nstride = sstride;
+        ma.off = off; ma.src = e.has_src() ? dalloc<uint32_t>(cap) : nullptr; ma.st = e.has_state() ? (uint8_t*)g_pool.alloc((size_t)cap * e.size) : nullptr;
+        ma.stride = cap; ma.rows = rows; ma.word = e.word; ma.ncols = e.ncols; ma.single_edge = e.singleedge;
+        merge_copy_kernel<<<nblk(rows), 256, 0, g_stream>>>(ma); LAUNCH_CHECK();
+        free_edge_read(e);
+        e.off = off; e.rows = rows; e.nnz = total; e.src = ma.src; e.st = ma.st; e.st_cap = cap;
+        dfree(noff); dfree(cnt);
+        free_edge_log(e);
+    }
+    dfree(ncnt); dfree(scr);
+}
+
+// purge edges of agents that died in this apply from every edge type's container
+void vb_sim::purge_dead(const uint8_t* dead) {
+    for (auto& e : edges) {
+        const uint32_t rb = row_base_of(e);
+        if (e.kind != vb::KIND_CSR) {
+            if (e.cnt && e.rows) { purge_rows_cnt_kernel<<<nblk(e.rows), 256, 0, g_stream>>>(e.cnt, e.rows, dead, rb); LAUNCH_CHECK(); }
+            continue;
+        }
+        if (!e.off || !e.nnz) continue;
+        PurgeArgs pa{};
+        pa.off = e.off; pa.src = e.src; pa.st = e.st; pa.stride = e.st_cap; pa.rows = e.rows; pa.dead = dead; pa.row_base = rb;
+        pa.check_src = e.has_src() && !all_immortal;
+        pa.cnt = dalloc<uint32_t>((size_t)e.rows + 2);
+        purge_count_kernel<<<nblk((uint64_t)e.rows + 1), 256, 0, g_stream>>>(pa); LAUNCH_CHECK();
+        uint32_t* noff = dalloc<uint32_t>((size_t)e.rows + 2);
+        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words((uint64_t)e.rows + 1));
+        vbp::exclusive_scan(pa.cnt, noff, (uint64_t)e.rows + 1, d_scalars, scr, g_stream); g_launches += 3;
+        uint32_t total = 0;
+        CK(cudaMemcpyAsync(&total, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (total != e.nnz) {
+            const uint32_t cap = std::max<uint32_t>(total, 1);
+            pa.noff = noff; pa.nsrc = e.has_src() ? dalloc<uint32_t>(cap) : nullptr;
+            pa.nst = e.has_state() ? (uint8_t*)g_pool.alloc((size_t)cap * e.size) : nullptr;
+            pa.nstride = cap; pa.word = e.word; pa.ncols = e.ncols;
+            purge_copy_kernel<<<nblk(e.rows), 256, 0, g_stream>>>(pa); LAUNCH_CHECK();
+            dfree(e.off); dfree(e.src); dfree(e.st);
+            e.off = noff; e.src = pa.nsrc; e.st = pa.nst; e.st_cap = cap; e.nnz = total;
+            e.last_change = num_transitions;
+            noff = nullptr;
+        }
+        dfree(pa.cnt); dfree(noff); dfree(scr);
+    }
+}
+
+uint64_t vb_sim::edge_total(int ei, bool write) {
+    EdgeStore& e = E(ei);
+    // before finish_init! everything lives in the write container = raw adds (Edge.jl:376-380)
+    if (!initialized) {
+        if (!write) return 0;
+        if (e.singleedge && e.chunks.empty()) {   // one slot per target: count distinct targets
+            std::vector<uint64_t> t = e.h_to;
+            std::sort(t.begin(), t.end());
+            return (uint64_t)(std::unique(t.begin(), t.end()) - t.begin());
+        }
+        return e.raw_n;
+    }
+    merge_pending(ei);
+    if (e.kind == vb::KIND_CSR) return e.nnz;
+    if (!e.cnt || !e.rows) return 0;
+    // sum of the per-row counts
+    MapArgs ma{};
+    ma.cols = (const uint8_t*)e.cnt; ma.stride = e.rows; ma.word = 4; ma.n = e.rows; ma.died = nullptr; ma.offset = 0; ma.dt = vb::DT_I32; ma.op = vb::OP_SUM;
+    long long* part = dalloc<long long>(1024 + 1);
+    const unsigned nb = std::min<unsigned>(1024, nblk(e.rows));
+    mapreduce_kernel<false><<<nb, 256, 0, g_stream>>>(ma, part); LAUNCH_CHECK();
+    mapreduce_final_kernel<false><<<1, 256, 0, g_stream>>>(part, nb, vb::OP_SUM, part + 1024); LAUNCH_CHECK();
+    long long r = 0;
+    CK(cudaMemcpyAsync(&r, part + 1024, 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(part);
+    return (uint64_t)r;
+}
+
+// ------------------------------------------------------------------------------------------------------
+namespace {
+
+template <class F>
+int guard(F&& f) {
+    try { f(); return VB_OK; }
+    catch (const AssertionError& e) { g_err = e.what(); return VB_ERR_ASSERT; }
+    catch (const ArgError& e) { g_err = e.what(); return VB_ERR_ARG; }
+    catch (const CudaError& e) { g_err = e.what(); return VB_ERR_CUDA; }
+    catch (const std::exception& e) { g_err = e.what(); return VB_ERR_STATE; }
+}
+bool contains(const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+
+void finish_write_agent(vb_sim& s, int t, std::vector<uint32_t*>& died_flags, std::vector<uint32_t>& died_n) {
+    AgentStore& a = s.A(t);
+    // births of this apply: pops from the reuse stack first, then fresh slots (AgentMethods.jl:37-63)
+    const uint32_t pops = std::min(a.births, a.n_reuse);
+    const uint32_t fresh = a.births - pops;
+    const uint32_t n_before = a.nslots;
+    a.n_reuse -= pops;
+    a.nextid += fresh;
+    a.nslots = (uint32_t)std::max<uint64_t>(a.nslots, a.nextid - 1);
+    a.births = 0;
+    if (!a.immortal && n_before > 0 && s.initialized) {
+        // agents that died in this apply, in ascending slot order, are appended to read.reuseable (:171,:430)
+        uint32_t* flag = dalloc<uint32_t>(n_before); uint32_t* pos = dalloc<uint32_t>(n_before);
+        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n_before));
+        vbp::newly_died_flags_kernel<<<nblk(n_before), 256, 0, g_stream>>>(a.rdied(), a.wdied(), n_before, flag); LAUNCH_CHECK();
+        vbp::exclusive_scan(flag, pos, n_before, s.d_scalars, scr, g_stream); g_launches += 3;
+        uint32_t nd = 0;
+        CK(cudaMemcpyAsync(&nd, s.d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (nd) {
+            vbp::compact_indices_kernel<<<nblk(n_before), 256, 0, g_stream>>>(flag, pos, n_before, a.reuse + a.n_reuse); LAUNCH_CHECK();
+            a.n_reuse += nd;
+            died_flags[t] = flag; died_n[t] = n_before;
+            flag = nullptr;
+        }
+        dfree(flag); dfree(pos); dfree(scr);
+    }
+    a.cur ^= 1;   // read := write by swapping the double buffers (:Independent types share one state buffer)
+    a.write_stale = true;
+    a.last_change = s.num_transitions;
+    a.writeable = false;
+}
+
+void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call, const std::vector<int>& read, const std::vector<int>& write,
+              const std::vector<int>& add_existing, int with_edge, uint64_t seed) {
+    require_device();
+    if (!s.initialized) throw AssertionError("You must call finish_init! before apply!");
+    if (with_edge >= 0 && s.E(with_edge).singletype) throw AssertionError("The `with_edge` keyword can only be used for edgetypes without the :SingleType hint");
+    for (int c : call) if (contains(add_existing, c)) throw AssertionError("a `call` type can not be element of `add_existing`");
+    for (int ae : add_existing) if (!contains(write, ae)) throw AssertionError("type is in `add_existing` but not in `write`");
+    std::vector<const vb::TransitionInfo*> tis;
+    for (int c : call) {
+        if (c >= vb::EDGE_REF) throw ArgError("`call` must list agent types");
+        AgentStore& a = s.A(c);
+        auto it = registry().find({tname, a.name});
+        if (it == registry().end()) throw ArgError("transition '" + tname + "' is not registered for agent type " + a.name);
+        const vb::TransitionInfo* ti = it->second;
+        if (a.size && ti->state_size != a.size) throw ArgError("transition '" + tname + "': sizeof(State) does not match the registered size of " + a.name);
+        for (int i = 0; i < ti->n_edge_writes; ++i)   // _can_add: EdgeMethods.jl:258-265
+            if (s.asserts_enabled && s.check_readable && !contains(write, vb::EDGE_REF + ti->edge_writes[i]))
+                throw AssertionError("edge type " + s.E(ti->edge_writes[i]).name + " must be in the `write` argument of the transition function");
+        for (int i = 0; i < ti->n_agent_writes; ++i)  // add_agent!: AgentMethods.jl:71-77
+            if (s.asserts_enabled && !contains(write, ti->agent_writes[i]))
+                throw AssertionError("agent type " + s.A(ti->agent_writes[i]).name + " must be in the `write` argument of the transition function");
+        tis.push_back(ti);
+    }
+    s.merge_all_pending();
+    const unsigned long long launches0 = g_launches;
+    s.intransition = true;
+    struct Reset {
+        vb_sim& s; const std::vector<int>& read;
+        ~Reset() {
+            s.intransition = false;
+            for (int r : read) { if (r >= vb::EDGE_REF) s.edges[r - vb::EDGE_REF].readable = false; else s.agents[r - 1].prepared = false; }
+            for (auto& a : s.agents) { a.writeable = false; a.births = 0; }
+            for (auto& e : s.edges) e.writeable = false;
+        }
+    } reset{s, read};
+    for (int r : read) { if (r >= vb::EDGE_REF) s.E(r - vb::EDGE_REF).readable = true; else s.A(r).prepared = true; }
+
+    // ---- prepare_write! ----
+    for (int w : write) {
+        const bool ae = contains(call, w) || contains(add_existing, w);
+        if (w < vb::EDGE_REF) {                                                // AgentMethods.jl:271-298
+            AgentStore& a = s.A(w);
+            if (a.immortal && !ae) throw AssertionError("an :Immortal type in `write` must also be in `add_existing` (or `call`)");
+            if (!ae) { a.nslots = 0; a.nextid = 1; a.n_reuse = 0; }
+            a.writeable = true;
+            a.births = 0;
+            if (a.nslots) {
+                if (!a.immortal) CK(cudaMemcpyAsync(a.wdied(), a.rdied(), a.nslots, cudaMemcpyDeviceToDevice, g_stream));
+                const bool full_call = contains(call, w) && with_edge < 0;
+                if (!a.independent && a.size && a.write_stale && !full_call) {
+                    CK(cudaMemcpyAsync(a.wstate(), a.rstate(), (size_t)a.cap * a.size, cudaMemcpyDeviceToDevice, g_stream));
+                }
+            }
+        } else {                                                               // EdgeMethods.jl:639-663
+            EdgeStore& e = s.E(w - vb::EDGE_REF);
+            e.writeable = true;
+            e.add_existing = contains(add_existing, w);
+            e.log_n = 0;
+            if (e.kind != vb::KIND_CSR) {
+                const uint32_t rows = s.rows_of(e);
+                dfree(e.wcnt);
+                e.wcnt = dalloc<uint32_t>((size_t)rows + 1); e.rows_w = rows;
+                CK(cudaMemsetAsync(e.wcnt, 0, ((size_t)rows + 1) * 4, g_stream));
+                if (e.add_existing && e.cnt) CK(cudaMemcpyAsync(e.wcnt, e.cnt, (size_t)std::min(rows, e.rows) * 4, cudaMemcpyDeviceToDevice, g_stream));
+            }
+        }
+    }
+    CK(cudaMemsetAsync(s.d_stats, 0, 8, g_stream));
+    CK(cudaEventRecord(s.ev[0], g_stream));
+    s.st_agents_called = 0;
+    uint64_t appended = 0;
+
+    // ---- the transition loop over `call` (Simulation.jl:774-788) ----
+    for (size_t ci = 0; ci < call.size(); ++ci) {
+        const int C = call[ci];
+        const vb::TransitionInfo* ti = tis[ci];
+        AgentStore& a = s.A(C);
+        const uint32_t n = a.nslots;
+        if (n == 0) continue;
+        s.st_agents_called += n;
+        vb::LaunchArgs la{};
+        la.ds = s.d_ds; la.type = C; la.n = n; la.in_read = contains(read, C); la.in_write = contains(write, C);
+        la.with_edge = with_edge; la.stats = s.d_stats; la.stream = g_stream;
+        const int nw = ti->n_edge_writes + ti->n_agent_writes;
+        std::vector<uint32_t*> tmp;
+        if (nw > 0) {
+            // count pass -> exclusive scans -> totals
+            uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+            tmp.push_back(scr);
+            for (int i = 0; i < ti->n_edge_writes; ++i) { la.ecount[i] = dalloc<uint32_t>(n); tmp.push_back(la.ecount[i]); }
+            for (int i = 0; i < ti->n_agent_writes; ++i) { la.acount[i] = dalloc<uint32_t>(n); tmp.push_back(la.acount[i]); }
+            s.upload_view(seed);
+            la.mode = vb::MODE_COUNT;
+            CK(ti->launch(la)); ++g_launches;
+            for (int i = 0; i < ti->n_edge_writes; ++i) { vbp::exclusive_scan(la.ecount[i], la.ecount[i], n, s.d_scalars + i, scr, g_stream); g_launches += 3; }
+            for (int i = 0; i < ti->n_agent_writes; ++i) { vbp::exclusive_scan(la.acount[i], la.acount[i], n, s.d_scalars + vb::MAX_EDGE_WRITES + i, scr, g_stream); g_launches += 3; }
+            uint32_t totals[vb::MAX_EDGE_WRITES + vb::MAX_AGENT_WRITES] = {0};
+            CK(cudaMemcpyAsync(totals, s.d_scalars, sizeof(totals), cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            s.check_device_error("apply! (count pass)");
+            // births: make room (may shift composite bases -> rebase), then logs
+            for (int i = 0; i < ti->n_agent_writes; ++i) {
+                AgentStore& b = s.A(ti->agent_writes[i]);
+                la.abase[i] = b.births;
+                const uint32_t total_births = b.births + totals[vb::MAX_EDGE_WRITES + i];
+                const uint32_t pops = std::min(total_births, b.n_reuse);
+                s.ensure_agent_cap(ti->agent_writes[i], (b.nextid - 1) + (total_births - pops));
+            }
+            for (int i = 0; i < ti->n_edge_writes; ++i) {
+                EdgeStore& e = s.E(ti->edge_writes[i]);
+                la.ebase[i] = e.log_n;
+                if (e.kind == vb::KIND_CSR) s.ensure_log(e, (uint64_t)e.log_n + totals[i]);
+                if (e.kind != vb::KIND_CSR && s.rows_of(e) != e.rows_w) throw CudaError("internal: count container not sized");
+            }
+            s.upload_view(seed);
+            la.mode = vb::MODE_EMIT;
+            CK(ti->launch(la)); ++g_launches;
+            for (int i = 0; i < ti->n_edge_writes; ++i) { EdgeStore& e = s.E(ti->edge_writes[i]); if (e.kind == vb::KIND_CSR) e.log_n += totals[i]; appended += totals[i]; }
+            for (int i = 0; i < ti->n_agent_writes; ++i) s.A(ti->agent_writes[i]).births += totals[vb::MAX_EDGE_WRITES + i];
+        } else {
+            s.upload_view(seed);
+            la.mode = vb::MODE_DIRECT;
+            CK(ti->launch(la)); ++g_launches;
+        }
+        CK(cudaStreamSynchronize(g_stream));
+        for (auto p : tmp) dfree(p);
+    }
+    CK(cudaEventRecord(s.ev[1], g_stream));
+    s.check_device_error("apply!");
+
+    // ---- finish_write! agents (Simulation.jl:807), then edges (:809), then the dead-agent purge ----
+    std::vector<uint32_t*> died_flags(s.agents.size() + 1, nullptr);
+    std::vector<uint32_t> died_n(s.agents.size() + 1, 0);
+    for (int w : write) if (w < vb::EDGE_REF) finish_write_agent(s, w, died_flags, died_n);
+    for (int w : write) if (w >= vb::EDGE_REF) {
+        EdgeStore& e = s.E(w - vb::EDGE_REF);
+        s.build_container(w - vb::EDGE_REF, e.add_existing);
+        e.last_change = s.num_transitions;
+        e.writeable = false;
+    }
+    bool any_dead = false;
+    for (auto p : died_flags) any_dead |= p != nullptr;
+    if (any_dead) {
+        const uint32_t tot = s.total_slots();
+        uint8_t* dead = (uint8_t*)g_pool.alloc((size_t)tot + 1);
+        CK(cudaMemsetAsync(dead, 0, (size_t)tot + 1, g_stream));
+        for (size_t t = 1; t <= s.agents.size(); ++t)
+            if (died_flags[t]) { mark_dead_kernel<<<nblk(died_n[t]), 256, 0, g_stream>>>(died_flags[t], died_n[t], dead, s.base[t]); LAUNCH_CHECK(); }
+        s.purge_dead(dead);
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(dead);
+        for (auto p : died_flags) dfree(p);
+    }
+    CK(cudaEventRecord(s.ev[2], g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    float m0 = 0, m1 = 0;
+    cudaEventElapsedTime(&m0, s.ev[0], s.ev[1]);
+    cudaEventElapsedTime(&m1, s.ev[1], s.ev[2]);
+    s.ms_rw = m0; s.ms_fin = m1;
+    unsigned long long er = 0;
+    CK(cudaMemcpy(&er, s.d_stats, 8, cudaMemcpyDeviceToHost));
+    s.st_edges_read = er; s.st_edges_appended = appended; s.st_launches = g_launches - launches0;
+    s.num_transitions += 1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int vb_register_transition(const vb::TransitionInfo* info) {
+    registry()[{info->name, info->agent_type}] = info;
+    return 0;
+}
+
+const char* vb_last_error(void) { return g_err.c_str(); }
+const char* vb_backend(void) { return "cuda-sm100a"; }
+
+int vb_init(int device) {
+    return guard([&] {
+        if (g_device >= 0) return;
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) throw CudaError("vahana_b200: no CUDA device available (this engine has no CPU fallback)");
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+        g_device = device;
+    });
+}
+int vb_shutdown(void) {
+    return guard([&] {
+        if (g_device < 0) return;
+        g_pool.release_all();
+        cudaStreamDestroy(g_stream);
+        g_stream = nullptr;
+        g_device = -1;
+    });
+}
+int vb_comm_unique_id(uint8_t id_out[128]) { std::memset(id_out, 0, 128); return VB_OK; }
+int vb_comm_init(int, int nranks, const uint8_t*) {
+    if (nranks != 1) { g_err = "multi-GPU communicator is not initialised in this build"; return VB_ERR_STATE; }
+    return VB_OK;
+}
+int vb_comm_rank(int* r, int* n) { *r = 0; *n = 1; return VB_OK; }
+
+int vb_sim_create(const vb_model_desc* m, const void* params, vb_sim** out) {
+    return guard([&] {
+        require_device();
+        if (m->n_agent_types > vb::MAX_AGENT_TYPES) throw ArgError("more agent types than this build supports (MAX_AGENT_TYPES)");
+        if (m->n_edge_types > vb::MAX_EDGE_TYPES) throw ArgError("more edge types than this build supports (MAX_EDGE_TYPES)");
+        if (m->param_size > vb::MAX_PARAM_BYTES) throw ArgError("parameter struct too large (MAX_PARAM_BYTES)");
+        auto s = std::make_unique<vb_sim>();
+        s->name = m->name;
+        for (uint32_t i = 0; i < m->n_agent_types; ++i) {
+            AgentStore a;
+            a.name = m->agent_types[i].name; a.size = m->agent_types[i].size; a.hints = m->agent_types[i].hints;
+            a.word = vb::soa_word(a.size); a.ncols = a.size ? a.size / a.word : 0;
+            a.immortal = a.hints & vb::AGENT_IMMORTAL; a.independent = a.hints & vb::AGENT_INDEPENDENT; a.stateless = a.size == 0;
+            if (!a.immortal) s->all_immortal = false;
+            s->agents.push_back(a);
+        }
+        for (uint32_t i = 0; i < m->n_edge_types; ++i) {
+            EdgeStore e;
+            const vb_edgetype_desc& d = m->edge_types[i];
+            e.name = d.name; e.size = d.size; e.hints = d.hints; e.target = d.target_type; e.size_hint = d.size_hint;
+            e.stateless = (d.hints & vb::EDGE_STATELESS) || d.size == 0; e.ignorefrom = d.hints & vb::EDGE_IGNORE_FROM;
+            e.singleedge = d.hints & vb::EDGE_SINGLE_EDGE; e.singletype = d.hints & vb::EDGE_SINGLE_TYPE;
+            if (e.singletype && (e.target < 1 || e.target > (int)m->n_agent_types)) throw AssertionError(":SingleType needs the target keyword");
+            if (e.singletype && e.singleedge && !((d.hints & vb::EDGE_STATELESS) && e.ignorefrom))
+                throw AssertionError(":SingleEdge and :SingleType can only be combined with :Stateless and :IgnoreFrom");
+            const bool S = d.hints & vb::EDGE_STATELESS;
+            e.stateless = S;
+            e.kind = (S && e.ignorefrom) ? (e.singleedge ? vb::KIND_FLAG : vb::KIND_COUNT) : vb::KIND_CSR;
+            e.word = vb::soa_word(S ? 0 : e.size); e.ncols = (!S && e.size) ? e.size / e.word : 0;
+            s->edges.push_back(std::move(e));
+        }
+        if (m->param_size) s->params.assign((const uint8_t*)params, (const uint8_t*)params + m->param_size);
+        s->d_ds = (vb::DeviceSim*)g_pool.alloc(sizeof(vb::DeviceSim));
+        s->d_error = dalloc<uint32_t>(1);
+        s->d_scalars = dalloc<uint32_t>(64);
+        s->d_stats = dalloc<unsigned long long>(4);
+        CK(cudaMemsetAsync(s->d_error, 0, 4, g_stream));
+        CK(cudaMemsetAsync(s->d_stats, 0, 32, g_stream));
+        for (auto& e : s->ev) CK(cudaEventCreate(&e));
+        s->compute_bases(s->base);
+        *out = s.release();
+    });
+}
+
+int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulation.jl:500-510
+    return guard([&] {
+        require_device();
+        vb_sim& o = const_cast<vb_sim&>(*src);
+        if (o.initialized) o.merge_all_pending();
+        auto s = std::make_unique<vb_sim>();
+        s->name = o.name; s->params = o.params; s->initialized = o.initialized; s->num_transitions = o.num_transitions;
+        s->asserts_enabled = o.asserts_enabled; s->check_readable = o.check_readable; s->all_immortal = o.all_immortal; s->rank = o.rank;
+        std::memcpy(s->base, o.base, sizeof(o.base));
+        auto dup = [&](const void* p, size_t bytes) -> void* {
+            if (!p) return nullptr;
+            void* q = g_pool.alloc(bytes);
+            CK(cudaMemcpyAsync(q, p, bytes, cudaMemcpyDeviceToDevice, g_stream));
+            return q;
+        };
+        for (auto& a : o.agents) {
+            AgentStore b = a;
+            if (a.size && a.cap) { b.state[0] = (uint8_t*)dup(a.state[0], (size_t)a.cap * a.size); b.state[1] = a.independent ? b.state[0] : (uint8_t*)dup(a.state[1], (size_t)a.cap * a.size); }
+            if (!a.immortal && a.cap) { b.died[0] = (uint8_t*)dup(a.died[0], a.cap); b.died[1] = (uint8_t*)dup(a.died[1], a.cap); b.reuse = (uint32_t*)dup(a.reuse, (size_t)a.reuse_cap * 4); }
+            s->agents.push_back(b);
+        }
+        for (auto& e : o.edges) {
+            EdgeStore f = e;
+            f.chunks.clear();
+            f.off = (uint32_t*)dup(e.off, ((size_t)e.rows + 2) * 4);
+            f.src = (uint32_t*)dup(e.src, (size_t)std::max<uint32_t>(e.st_cap, e.nnz) * 4);
+            f.st = (uint8_t*)dup(e.st, (size_t)e.st_cap * e.size);
+            f.cnt = (uint32_t*)dup(e.cnt, ((size_t)e.rows + 1) * 4);
+            f.log_to = f.log_from = f.wcnt = nullptr; f.log_st = nullptr; f.log_n = f.log_cap = 0; f.rows_w = 0;
+            for (auto& c : e.chunks) {
+                RawChunk d; d.n = c.n;
+                d.to = (uint64_t*)dup(c.to, c.n * 8); d.from = (uint64_t*)dup(c.from, c.n * 8); d.st = (uint8_t*)dup(c.st, c.n * e.size);
+                f.chunks.push_back(d);
+            }
+            s->edges.push_back(std::move(f));
+        }
+        for (auto& r : o.rasters) { RasterStore q = r; q.cells = (uint32_t*)dup(r.cells, r.ids.size() * 4); s->rasters.push_back(q); }
+        s->d_ds = (vb::DeviceSim*)g_pool.alloc(sizeof(vb::DeviceSim));
+        s->d_error = dalloc<uint32_t>(1);
+        s->d_scalars = dalloc<uint32_t>(64);
+        s->d_stats = dalloc<unsigned long long>(4);
+        CK(cudaMemsetAsync(s->d_error, 0, 4, g_stream));
+        for (auto& e : s->ev) CK(cudaEventCreate(&e));
+        CK(cudaStreamSynchronize(g_stream));
+        *out = s.release();
+    });
+}
+int vb_sim_destroy(vb_sim* s) { delete s; return VB_OK; }
+
+int vb_set_param(vb_sim* s, const void* p, uint32_t size) {
+    return guard([&] {
+        if (s->initialized) throw AssertionError("set_param! can only be called before finish_init!");
+        if (size > vb::MAX_PARAM_BYTES) throw ArgError("parameter struct too large");
+        s->params.assign((const uint8_t*)p, (const uint8_t*)p + size);
+    });
+}
+int vb_set_config(vb_sim* s, int asserts, int check_readable) { s->asserts_enabled = asserts; s->check_readable = check_readable; return VB_OK; }
+int vb_disable_transition_checks(vb_sim* s, int disable) { s->intransition = disable; s->check_readable = !disable; return VB_OK; }
+
+int vb_add_agents(vb_sim* s, int type, const void* states, uint64_t n, vb_agent_id* ids_out) {
+    return guard([&] {   // add_agent!: AgentMethods.jl:65-89 (outside of transitions: init phase)
+        require_device();
+        AgentStore& a = s->A(type);
+        s->mayassert(!s->initialized || s->intransition, "add_agent! only in the initialization phase or within a transition");
+        s->mayassert(!s->initialized || a.writeable, "agent type must be in the `write` argument");
+        if (n == 0) return;
+        const uint64_t first = a.nextid;   // init phase: no reuse (nothing has died yet)
+        s->ensure_agent_cap(type, first - 1 + n);
+        if (a.size) {
+            uint8_t* tmp = (uint8_t*)g_pool.alloc(n * a.size);
+            CK(cudaMemcpyAsync(tmp, states, n * a.size, cudaMemcpyHostToDevice, g_stream));
+            vbp::aos_to_soa_kernel<<<nblk(n * a.ncols), 256, 0, g_stream>>>(tmp, a.wstate(), a.cap, first - 1, n, a.size, a.word); LAUNCH_CHECK();
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(tmp);
+        }
+        a.nextid += n;
+        for (uint64_t i = 0; i < n && ids_out; ++i) ids_out[i] = vb::agent_id((uint32_t)type, s->rank, first + i);
+    });
+}
+
+int vb_add_edges(vb_sim* s, int ei, const vb_agent_id* from, const vb_agent_id* to, const void* states, uint64_t n) {
+    return guard([&] {   // add_edge!: EdgeMethods.jl:388-523 (outside of transitions)
+        require_device();
+        EdgeStore& e = s->E(ei);
+        s->mayassert(!s->initialized || s->intransition, "add_edge! only in the initialization phase or within a transition");
+        s->mayassert(!s->check_readable || !s->initialized || e.writeable, "edge type must be in the `write` argument");
+        cudaPointerAttributes pa{};
+        const bool dev = cudaPointerGetAttributes(&pa, to) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+        cudaGetLastError();
+        if (dev) {   // bulk ingest straight from device memory
+            s->flush_raw(ei);
+            RawChunk c; c.n = n;
+            c.to = dalloc<uint64_t>(n); CK(cudaMemcpyAsync(c.to, to, n * 8, cudaMemcpyDeviceToDevice, g_stream));
+            if (e.has_src()) { c.from = dalloc<uint64_t>(n); CK(cudaMemcpyAsync(c.from, from, n * 8, cudaMemcpyDeviceToDevice, g_stream)); }
+            if (e.has_state()) { c.st = (uint8_t*)g_pool.alloc(n * e.size); CK(cudaMemcpyAsync(c.st, states, n * e.size, cudaMemcpyDeviceToDevice, g_stream)); }
+            CK(cudaStreamSynchronize(g_stream));
+            e.chunks.push_back(c); e.raw_n += n;
+            return;
+        }
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t t = to[i], f = from ? from[i] : 0;
+            if (s->asserts_enabled) {   // ids must name existing agents (the reference dereferences them)
+                const uint32_t tt = vb::type_nr(t);
+                if (tt < 1 || tt > s->agents.size() || vb::agent_nr(t) < 1 || vb::agent_nr(t) >= s->agents[tt - 1].nextid) throw AssertionError("add_edge!: invalid target id");
+                if (e.singletype && (int)tt != e.target) throw AssertionError("add_edge!: the :SingleType hint is set and the target has another type");
+                if (e.has_src()) {
+                    const uint32_t ft = vb::type_nr(f);
+                    if (ft < 1 || ft > s->agents.size() || vb::agent_nr(f) < 1 || vb::agent_nr(f) >= s->agents[ft - 1].nextid) throw AssertionError("add_edge!: invalid source id");
+                }
+            }
+            const uint8_t* st = (e.has_state() && states) ? (const uint8_t*)states + i * e.size : nullptr;
+            if (e.singleedge && !e.singletype && !(e.stateless && e.ignorefrom) && s->asserts_enabled) {   // _can_add: :267-293
+                auto it = e.single_seen.find(t);
+                if (it != e.single_seen.end()) {
+                    bool same = (!e.has_src() || it->second.first == f) && (!st || std::memcmp(it->second.second.data(), st, e.size) == 0);
+                    if (!same) throw AssertionError("An edge has already been added to this agent (the edge type has the :SingleEdge hint)");
+                } else {
+                    e.single_seen[t] = {f, st ? std::vector<uint8_t>(st, st + e.size) : std::vector<uint8_t>()};
+                }
+            }
+            e.h_to.push_back(t);
+            if (e.has_src()) e.h_from.push_back(f);
+            if (e.has_state()) { if (!st) throw ArgError("edge type has a state"); e.h_st.insert(e.h_st.end(), st, st + e.size); }
+        }
+        e.raw_n += n;
+        if (e.h_to.size() >= (1u << 22)) s->flush_raw(ei);
+    });
+}
+int vb_remove_edges(vb_sim*, int, vb_agent_id, vb_agent_id) { g_err = "remove_edges! outside of transitions is not implemented yet"; return VB_ERR_STATE; }
+
+int vb_add_raster(vb_sim* s, const char* name, int ndims, const int64_t* dims, int type, const void* states, vb_agent_id* ids_out) {
+    return guard([&] {   // add_raster!: Raster.jl:32-54
+        if (s->initialized) throw AssertionError("add_raster! can be only called before finish_init!");
+        if (ndims < 1 || ndims > vb::MAX_RASTER_DIMS) throw ArgError("rasters with 1..4 dimensions are supported");
+        if (s->rasters.size() >= vb::MAX_RASTERS) throw ArgError("too many rasters (MAX_RASTERS)");
+        RasterStore r;
+        r.name = name; r.dims.assign(dims, dims + ndims); r.type = type;
+        uint64_t n = 1;
+        for (int i = 0; i < ndims; ++i) n *= (uint64_t)dims[i];
+        r.ids.resize(n);
+        int rc = vb_add_agents(s, type, states, n, r.ids.data());
+        if (rc != VB_OK) throw AssertionError(g_err);
+        if (ids_out) std::memcpy(ids_out, r.ids.data(), n * 8);
+        s->rasters.push_back(std::move(r));
+        uint32_t ob[vb::MAX_AGENT_TYPES + 2];
+        std::memcpy(ob, s->base, sizeof(ob));
+        s->rebase(ob);   // builds the device cell table
+    });
+}
+
+namespace {
+// host-side stencil enumeration for the init-phase helpers (Raster.jl:82-110)
+std::vector<std::vector<int64_t>> stencil(int metric, int n, double distance) {
+    int64_t d = (int64_t)std::floor(distance);
+    std::vector<std::vector<int64_t>> out;
+    if (d < 0) return out;
+    std::vector<int64_t> cur(n, -d);
+    while (true) {
+        bool zero = true; double n2 = 0; int64_t n1 = 0;
+        for (int i = 0; i < n; ++i) { zero &= cur[i] == 0; n2 += (double)(cur[i] * cur[i]); n1 += std::llabs(cur[i]); }
+        bool keep = !zero;
+        if (keep && metric == vb::EUCLIDEAN) keep = std::sqrt(n2) <= distance;
+        if (keep && metric == vb::MANHATTEN) keep = (double)n1 <= distance;
+        if (keep) out.push_back(cur);
+        int i = 0;
+        while (i < n && ++cur[i] > d) { cur[i] = -d; ++i; }
+        if (i == n) break;
+    }
+    return out;
+}
+bool checkpos(std::vector<int64_t>& pos, const std::vector<int64_t>& dims, bool periodic) {   // Raster.jl:479-499
+    bool oob = false;
+    for (size_t i = 0; i < dims.size(); ++i)
+        if (pos[i] < 1 || pos[i] > dims[i]) { oob = true; int64_t m = (pos[i] - 1) % dims[i]; if (m < 0) m += dims[i]; pos[i] = m + 1; }
+    return !oob || periodic;
+}
+size_t linear_index(const std::vector<int64_t>& pos, const std::vector<int64_t>& dims) {
+    size_t idx = 0, stride = 1;
+    for (size_t i = 0; i < dims.size(); ++i) { idx += (size_t)(pos[i] - 1) * stride; stride *= (size_t)dims[i]; }
+    return idx;
+}
+RasterStore& find_raster(vb_sim* s, const char* name) {
+    for (auto& r : s->rasters) if (r.name == name) return r;
+    throw ArgError(std::string("unknown raster ") + name);
+}
+}  // namespace
+
+int vb_connect_raster_neighbors(vb_sim* s, const char* name, int ei, double distance, int metric, int periodic, const void* st) {
+    return guard([&] {   // Raster.jl:139-167: for org in cells (column-major), for s in stencil: org -> shifted
+        RasterStore& r = find_raster(s, name);
+        EdgeStore& e = s->E(ei);
+        auto sten = stencil(metric, (int)r.dims.size(), distance);
+        const size_t n = r.ids.size();
+        std::vector<uint64_t> from, to;
+        from.reserve(std::min<size_t>(n * sten.size(), (size_t)1 << 24)); to.reserve(from.capacity());
+        std::vector<uint8_t> sts;
+        std::vector<int64_t> org(r.dims.size(), 1), sh(r.dims.size());
+        auto flush = [&] {
+            if (to.empty()) return;
+            if (e.has_state()) { sts.resize(to.size() * e.size); for (size_t i = 0; i < to.size(); ++i) std::memcpy(&sts[i * e.size], st, e.size); }
+            int rc = vb_add_edges(s, ei, from.data(), to.data(), e.has_state() ? sts.data() : nullptr, to.size());
+            if (rc != VB_OK) throw AssertionError(g_err);
+            from.clear(); to.clear();
+        };
+        for (size_t i = 0; i < n; ++i) {
+            for (auto& o : sten) {
+                for (size_t k = 0; k < org.size(); ++k) sh[k] = org[k] + o[k];
+                if (checkpos(sh, r.dims, periodic)) { from.push_back(r.ids[i]); to.push_back(r.ids[linear_index(sh, r.dims)]); }
+            }
+            if (to.size() >= ((size_t)1 << 24)) flush();
+            size_t k = 0;
+            while (k < org.size() && ++org[k] > r.dims[k]) { org[k] = 1; ++k; }
+        }
+        flush();
+    });
+}
+int vb_move_to(vb_sim* s, const char* name, vb_agent_id id, const int64_t* posv, int e_from, const void* s_from, int e_to, const void* s_to,
+               double distance, int metric, int periodic, int only_surrounding) {
+    return guard([&] {   // Raster.jl:437-477
+        RasterStore& r = find_raster(s, name);
+        std::vector<int64_t> pos(posv, posv + r.dims.size());
+        auto add = [&](int ei, uint64_t f, uint64_t t, const void* st) {
+            int rc = vb_add_edges(s, ei, &f, &t, st, 1);
+            if (rc != VB_OK) throw AssertionError(g_err);
+        };
+        if (!only_surrounding) {
+            for (size_t k = 0; k < pos.size(); ++k) if (pos[k] < 1 || pos[k] > r.dims[k]) throw AssertionError("move_to!: position outside the raster");
+            const uint64_t cell = r.ids[linear_index(pos, r.dims)];
+            if (e_from >= 0) add(e_from, cell, id, s_from);
+            if (e_to >= 0) add(e_to, id, cell, s_to);
+        }
+        if (distance >= 1) {
+            std::vector<int64_t> sh(pos.size());
+            for (auto& o : stencil(metric, (int)r.dims.size(), distance)) {
+                for (size_t k = 0; k < pos.size(); ++k) sh[k] = pos[k] + o[k];
+                if (!checkpos(sh, r.dims, periodic)) continue;
+                const uint64_t cell = r.ids[linear_index(sh, r.dims)];
+                if (e_from >= 0) add(e_from, cell, id, s_from);
+                if (e_to >= 0) add(e_to, id, cell, s_to);
+            }
+        }
+    });
+}
+int vb_cellid(vb_sim* s, const char* name, const int64_t* posv, vb_agent_id* out) {
+    return guard([&] {
+        RasterStore& r = find_raster(s, name);
+        std::vector<int64_t> pos(posv, posv + r.dims.size());
+        for (size_t k = 0; k < pos.size(); ++k) if (pos[k] < 1 || pos[k] > r.dims[k]) throw AssertionError("cellid: position outside the raster");
+        *out = r.ids[linear_index(pos, r.dims)];
+    });
+}
+
+int vb_finish_init(vb_sim* s) {
+    return guard([&] {   // Simulation.jl:403-476 (single rank): finish_write! all agent types, then all edge types
+        require_device();
+        if (s->initialized) throw AssertionError("You can not call finish_init! twice for the same simulation");
+        for (auto& a : s->agents) {   // read := write
+            a.nslots = (uint32_t)(a.nextid - 1);
+            a.cur ^= 1;
+            a.write_stale = true;
+            if (!a.immortal && a.cap) CK(cudaMemsetAsync(a.rdied(), 0, a.cap, g_stream));
+        }
+        s->initialized = true;
+        s->merge_all_pending();
+        for (auto& e : s->edges) {   // every container exists after init, even if empty
+            if (e.kind == vb::KIND_CSR && !e.off) { e.log_n = 0; s->build_container((int)(&e - &s->edges[0]), false); }
+            if (e.kind != vb::KIND_CSR && !e.cnt) s->build_container((int)(&e - &s->edges[0]), false);
+            e.single_seen.clear();
+        }
+        CK(cudaStreamSynchronize(g_stream));
+        s->num_transitions = 1;
+    });
+}
+
+int vb_apply(vb_sim* s, const char* transition, const int* call, int ncall, const int* read, int nread, const int* write, int nwrite,
+             const int* add_existing, int nadd, int with_edge, uint64_t seed) {
+    return guard([&] {
+        do_apply(*s, transition, std::vector<int>(call, call + ncall), std::vector<int>(read, read + nread), std::vector<int>(write, write + nwrite),
+                 std::vector<int>(add_existing, add_existing + nadd), with_edge, seed);
+    });
+}
+int vb_has_transition(const char* t, const char* a) { return registry().count({t, a}) ? 1 : 0; }
+int vb_load_model_library(const char* path) {
+    void* h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_err = std::string("dlopen: ") + dlerror(); return VB_ERR_NOTFOUND; }
+    return VB_OK;
+}
+
+int vb_num_agents(vb_sim* s, int type, uint64_t* n_out) {
+    return guard([&] {   // Agent.jl:324-343
+        require_device();
+        AgentStore& a = s->A(type);
+        if (a.immortal) { *n_out = a.nextid - 1; return; }
+        const uint32_t n = s->initialized ? a.nslots : (uint32_t)(a.nextid - 1);
+        if (!n) { *n_out = 0; return; }
+        if (!s->initialized) { *n_out = n; return; }
+        MapArgs ma{};
+        ma.cols = nullptr; ma.n = n; ma.died = a.rdied(); ma.dt = -1; ma.op = vb::OP_SUM; ma.word = 1;
+        long long* part = dalloc<long long>(1024 + 1);
+        const unsigned nb = std::min<unsigned>(1024, nblk(n));
+        mapreduce_kernel<false><<<nb, 256, 0, g_stream>>>(ma, part); LAUNCH_CHECK();
+        mapreduce_final_kernel<false><<<1, 256, 0, g_stream>>>(part, nb, vb::OP_SUM, part + 1024); LAUNCH_CHECK();
+        long long r = 0;
+        CK(cudaMemcpyAsync(&r, part + 1024, 8, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(part);
+        *n_out = (uint64_t)r;
+    });
+}
+
+int vb_all_agents(vb_sim* s, int type, void* states_out, vb_agent_id* ids_out, uint64_t cap, uint64_t* n_out) {
+    return guard([&] {   // Agent.jl:234-313: live slots in ascending nr
+        require_device();
+        AgentStore& a = s->A(type);
+        const uint32_t n = s->initialized ? a.nslots : (uint32_t)(a.nextid - 1);
+        const uint8_t* state = s->initialized ? a.rstate() : a.wstate();
+        const uint8_t* died = (a.immortal || !s->initialized) ? nullptr : a.rdied();
+        if (!n) { *n_out = 0; return; }
+        uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n); uint32_t* idx = dalloc<uint32_t>(n);
+        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+        vbp::alive_flags_kernel<<<nblk(n), 256, 0, g_stream>>>(died, n, flag); LAUNCH_CHECK();
+        vbp::exclusive_scan(flag, pos, n, s->d_scalars, scr, g_stream);
+        uint32_t live = 0;
+        CK(cudaMemcpyAsync(&live, s->d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        *n_out = live;
+        if (live && cap >= live) {
+            vbp::compact_indices_kernel<<<nblk(n), 256, 0, g_stream>>>(flag, pos, n, idx); LAUNCH_CHECK();
+            if (states_out && a.size) {
+                uint8_t* tmp = (uint8_t*)g_pool.alloc((size_t)live * a.size);
+                vbp::soa_gather_aos_kernel<<<nblk((uint64_t)live * a.ncols), 256, 0, g_stream>>>(state, tmp, a.cap, idx, live, a.size, a.word); LAUNCH_CHECK();
+                CK(cudaMemcpyAsync(states_out, tmp, (size_t)live * a.size, cudaMemcpyDeviceToHost, g_stream));
+                CK(cudaStreamSynchronize(g_stream));
+                dfree(tmp);
+            }
+            if (ids_out) {
+                std::vector<uint32_t> h(live);
+                CK(cudaMemcpyAsync(h.data(), idx, (size_t)live * 4, cudaMemcpyDeviceToHost, g_stream));
+                CK(cudaStreamSynchronize(g_stream));
+                for (uint32_t i = 0; i < live; ++i) ids_out[i] = vb::agent_id((uint32_t)type, s->rank, (uint64_t)h[i] + 1);
+            }
+        }
+        dfree(flag); dfree(pos); dfree(idx); dfree(scr);
+    });
+}
+
+int vb_agentstate(vb_sim* s, vb_agent_id id, int type, void* out) {
+    return guard([&] {   // AgentMethods.jl:91-124
+        require_device();
+        AgentStore& a = s->A(type);
+        s->mayassert((int)vb::type_nr(id) == type, "The id of the agent does not match the given type");
+        s->mayassert(a.prepared || !s->check_readable, "agent type must be in the `read` argument of the transition function");
+        const uint64_t nr = vb::agent_nr(id);
+        if (nr < 1 || nr > a.nslots) throw AssertionError("agentstate: agent does not exist");
+        if (!a.immortal) {
+            uint8_t d = 0;
+            CK(cudaMemcpyAsync(&d, a.rdied() + (nr - 1), 1, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            s->mayassert(!d, "agentstate was requested for an agent that has been removed");
+        }
+        if (!a.size) return;
+        uint8_t* tmp = (uint8_t*)g_pool.alloc(a.size);
+        vbp::soa_to_aos_kernel<<<1, 64, 0, g_stream>>>(a.rstate(), tmp, a.cap, nr - 1, 1, a.size, a.word); LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(out, tmp, a.size, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(tmp);
+    });
+}
+
+int vb_num_edges_total(vb_sim* s, int e, int write, uint64_t* n_out) {
+    return guard([&] { require_device(); *n_out = s->edge_total(e, write != 0); });
+}
+
+namespace {
+// fetch row `to` of edge type e to the host: ids (AgentIDs) and AoS states; returns count or -1 (`nothing`)
+int64_t fetch_row(vb_sim* s, EdgeStore& e, vb_agent_id to, std::vector<uint64_t>* from, std::vector<uint8_t>* st, bool count_only) {
+    const uint32_t tt = vb::type_nr(to);
+    const uint64_t nr = vb::agent_nr(to);
+    if (tt < 1 || tt > s->agents.size() || nr < 1) throw AssertionError("invalid agent id");
+    if (e.singletype) s->mayassert((int)tt == e.target, "The :SingleType hint is set and the agent has another type");
+    if (e.singletype && (int)tt != e.target) return -1;
+    if (nr > s->agents[tt - 1].cap) return -1;
+    const uint32_t row = e.singletype ? (uint32_t)(nr - 1) : s->base[tt] + (uint32_t)(nr - 1);
+    if (row >= e.rows) return -1;
+    if (e.kind != vb::KIND_CSR) {
+        uint32_t c = 0;
+        CK(cudaMemcpyAsync(&c, e.cnt + row, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        return c ? (int64_t)c : -1;
+    }
+    uint32_t o[2];
+    CK(cudaMemcpyAsync(o, e.off + row, 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    const uint32_t n = o[1] - o[0];
+    if (!n) return -1;
+    if (count_only) return n;
+    if (from && e.has_src()) {
+        std::vector<uint32_t> c(n);
+        CK(cudaMemcpyAsync(c.data(), e.src + o[0], (size_t)n * 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        from->resize(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t t = 1;
+            while (t < s->agents.size() && c[i] >= s->base[t + 1]) ++t;
+            (*from)[i] = vb::agent_id(t, s->rank, (uint64_t)(c[i] - s->base[t]) + 1);
+        }
+    }
+    if (st && e.has_state()) {
+        uint8_t* tmp = (uint8_t*)g_pool.alloc((size_t)n * e.size);
+        vbp::soa_to_aos_kernel<<<nblk((uint64_t)n * e.ncols), 256, 0, g_stream>>>(e.st, tmp, e.st_cap, o[0], n, e.size, e.word); LAUNCH_CHECK();
+        st->resize((size_t)n * e.size);
+        CK(cudaMemcpyAsync(st->data(), tmp, (size_t)n * e.size, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(tmp);
+    }
+    return n;
+}
+void avail(bool ok, const char* what) { if (!ok) throw AssertionError(std::string(what) + " is not defined for this hint combination"); }
+}  // namespace
+
+int vb_edges_of(vb_sim* s, int ei, vb_agent_id to, int what, vb_agent_id* from_out, void* states_out, uint64_t cap, int64_t* n_out) {
+    return guard([&] {   // EdgeMethods.jl:699-892
+        require_device();
+        EdgeStore& e = s->E(ei);
+        const bool S = e.stateless, I = e.ignorefrom, E1 = e.singleedge, T = e.singletype;
+        switch (what) {
+            case VB_ACC_EDGES: avail(!S && !I, "edges"); break;
+            case VB_ACC_NEIGHBORIDS: avail(!I, "neighborids"); break;
+            case VB_ACC_NEIGHBORIDS_ITER: avail(!I && !E1, "neighborids_iter"); break;
+            case VB_ACC_EDGESTATES: avail(!S, "edgestates"); break;
+            case VB_ACC_EDGESTATES_ITER: avail(!S && !E1, "edgestates_iter"); break;
+            case VB_ACC_NUM_EDGES: avail(!E1, "num_edges"); break;
+            case VB_ACC_HAS_EDGE: avail(!(E1 && T && !(S && I)), "has_edge"); break;
+            default: throw ArgError("bad accessor");
+        }
+        s->mayassert(e.readable || !s->check_readable, "edge type is not in the `read` argument of apply!");
+        s->merge_pending(ei);
+        const bool count_only = what == VB_ACC_NUM_EDGES || what == VB_ACC_HAS_EDGE || (S && I);
+        std::vector<uint64_t> from; std::vector<uint8_t> st;
+        const int64_t n = fetch_row(s, e, to, &from, &st, count_only || cap == 0);
+        if (what == VB_ACC_NUM_EDGES || what == VB_ACC_HAS_EDGE) { *n_out = n < 0 ? 0 : n; return; }
+        *n_out = n;
+        if (n <= 0 || count_only || cap == 0) return;
+        for (int64_t i = 0; i < n && (uint64_t)i < cap; ++i) {
+            if (from_out && !I) from_out[i] = from[i];
+            if (states_out && e.has_state()) std::memcpy((uint8_t*)states_out + i * e.size, &st[i * e.size], e.size);
+        }
+    });
+}
+
+int vb_export_csr(vb_sim* s, int ei, int target_type, uint64_t* offsets, uint64_t nrows, vb_agent_id* from_out, void* states_out, uint64_t cap) {
+    return guard([&] {
+        require_device();
+        EdgeStore& e = s->E(ei);
+        s->merge_pending(ei);
+        const uint32_t rb = e.singletype ? 0 : s->base[target_type];
+        if (e.singletype && target_type != e.target) { for (uint64_t r = 0; r <= nrows; ++r) offsets[r] = 0; return; }
+        std::vector<uint32_t> off(nrows + 1, 0);
+        if (e.kind != vb::KIND_CSR) {
+            std::vector<uint32_t> c(nrows, 0);
+            const uint64_t avail_rows = rb < e.rows ? std::min<uint64_t>(nrows, e.rows - rb) : 0;
+            if (avail_rows && e.cnt) { CK(cudaMemcpyAsync(c.data(), e.cnt + rb, avail_rows * 4, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream)); }
+            uint64_t run = 0;
+            for (uint64_t r = 0; r < nrows; ++r) { offsets[r] = run; run += c[r]; }
+            offsets[nrows] = run;
+            return;
+        }
+        const uint64_t avail_rows = (e.off && rb < e.rows) ? std::min<uint64_t>(nrows, e.rows - rb) : 0;
+        if (avail_rows) { CK(cudaMemcpyAsync(off.data(), e.off + rb, (avail_rows + 1) * 4, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream)); }
+        const uint32_t o0 = avail_rows ? off[0] : 0;
+        for (uint64_t r = 0; r <= nrows; ++r) offsets[r] = r <= avail_rows ? off[r] - o0 : off[avail_rows] - o0;
+        const uint64_t n = avail_rows ? off[avail_rows] - o0 : 0;
+        if (!n || cap < n) return;
+        if (from_out && e.has_src()) {
+            uint64_t* ids = dalloc<uint64_t>(n);
+            RebaseArgs ra; std::memcpy(ra.old_base, s->base, sizeof(ra.old_base)); std::memcpy(ra.new_base, s->base, sizeof(ra.new_base)); ra.ntypes = (uint32_t)s->agents.size();
+            comp_to_id_kernel<<<nblk(n), 256, 0, g_stream>>>(e.src + o0, n, ids, ra, s->rank); LAUNCH_CHECK();
+            CK(cudaMemcpyAsync(from_out, ids, n * 8, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(ids);
+        }
+        if (states_out && e.has_state()) {
+            uint8_t* tmp = (uint8_t*)g_pool.alloc(n * e.size);
+            vbp::soa_to_aos_kernel<<<nblk(n * e.ncols), 256, 0, g_stream>>>(e.st, tmp, e.st_cap, o0, n, e.size, e.word); LAUNCH_CHECK();
+            CK(cudaMemcpyAsync(states_out, tmp, n * e.size, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(tmp);
+        }
+    });
+}
+
+int vb_all_edges(vb_sim* s, int ei, vb_agent_id* to_out, vb_agent_id* from_out, void* states_out, uint64_t cap, uint64_t* n_out) {
+    return guard([&] {   // EdgeMethods.jl:1005-1027; emitted in ascending target id order
+        require_device();
+        EdgeStore& e = s->E(ei);
+        if (!s->initialized) throw AssertionError("all_edges before finish_init! is not supported by the CUDA engine");
+        s->merge_pending(ei);
+        uint64_t n = 0;
+        for (size_t t = 1; t <= s->agents.size(); ++t) {
+            if (e.singletype && (int)t != e.target) continue;
+            const uint64_t nrows = s->agents[t - 1].cap;
+            if (!nrows) continue;
+            std::vector<uint64_t> off(nrows + 1);
+            int rc = vb_export_csr(s, ei, (int)t, off.data(), nrows, nullptr, nullptr, 0);
+            if (rc != VB_OK) throw AssertionError(g_err);
+            const uint64_t m = off[nrows];
+            if (m && n + m <= cap) {
+                rc = vb_export_csr(s, ei, (int)t, off.data(), nrows, from_out ? from_out + n : nullptr, states_out ? (uint8_t*)states_out + n * e.size : nullptr, m);
+                if (rc != VB_OK) throw AssertionError(g_err);
+                if (to_out) for (uint64_t r = 0; r < nrows; ++r) for (uint64_t k = off[r]; k < off[r + 1]; ++k) to_out[n + k] = vb::agent_id((uint32_t)t, s->rank, r + 1);
+            }
+            n += m;
+        }
+        *n_out = n;
+    });
+}
+
+int vb_mapreduce(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64_t cmp, int op, int result_dt, const void* init, void* out) {
+    return guard([&] {
+        require_device();
+        if (s->intransition) throw AssertionError("You can not call mapreduce inside of a transition function.");
+        MapArgs ma{};
+        ma.offset = offset; ma.dt = dt; ma.has_cmp = has_cmp; ma.cmp = cmp; ma.op = op;
+        if (type_ref < vb::EDGE_REF) {
+            AgentStore& a = s->A(type_ref);
+            ma.cols = a.rstate(); ma.stride = a.cap; ma.word = a.word ? a.word : 1; ma.n = a.nextid - 1; ma.died = a.immortal ? nullptr : a.rdied();
+            if (ma.n > a.nslots) ma.n = a.nslots;
+        } else {
+            EdgeStore& e = s->E(type_ref - vb::EDGE_REF);
+            if (e.stateless) throw AssertionError("mapreduce is not defined for :Stateless edge types");
+            s->merge_pending(type_ref - vb::EDGE_REF);
+            ma.cols = e.st; ma.stride = e.st_cap; ma.word = e.word; ma.n = e.nnz; ma.died = nullptr;
+        }
+        const bool isf = result_dt == vb::DT_F64 || result_dt == vb::DT_F32;
+        const bool isb = result_dt == vb::DT_BOOL;
+        if (isf && (op == vb::OP_AND || op == vb::OP_OR)) throw AssertionError("& and | are only supported for integer and boolean types");
+        const unsigned nb = std::max<unsigned>(1, std::min<unsigned>(1024, nblk(ma.n)));
+        double fres = 0; long long ires = 0;
+        if (isf) {
+            double* part = dalloc<double>(1024 + 1);
+            mapreduce_kernel<true><<<nb, 256, 0, g_stream>>>(ma, part); LAUNCH_CHECK();
+            mapreduce_final_kernel<true><<<1, 256, 0, g_stream>>>(part, nb, op, part + 1024); LAUNCH_CHECK();
+            CK(cudaMemcpyAsync(&fres, part + 1024, 8, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(part);
+        } else {
+            long long* part = dalloc<long long>(1024 + 1);
+            mapreduce_kernel<false><<<nb, 256, 0, g_stream>>>(ma, part); LAUNCH_CHECK();
+            mapreduce_final_kernel<false><<<1, 256, 0, g_stream>>>(part, nb, op, part + 1024); LAUNCH_CHECK();
+            CK(cudaMemcpyAsync(&ires, part + 1024, 8, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(part);
+        }
+        // fold in the reference's start value: `init` or the identity of val4empty (Helpers.jl:44-81)
+        auto fold_i = [&](long long a, long long b) -> long long {
+            switch (op) {
+                case vb::OP_SUM: return (long long)((unsigned long long)a + (unsigned long long)b);
+                case vb::OP_PROD: return (long long)((unsigned long long)a * (unsigned long long)b);
+                case vb::OP_MIN: return std::min(a, b);
+                case vb::OP_MAX: return std::max(a, b);
+                case vb::OP_AND: return a & b;
+                default: return a | b;
+            }
+        };
+        auto fold_f = [&](double a, double b) -> double {
+            switch (op) {
+                case vb::OP_SUM: return a + b;
+                case vb::OP_PROD: return a * b;
+                case vb::OP_MIN: return std::fmin(a, b);
+                default: return std::fmax(a, b);
+            }
+        };
+        if (isf) {
+            double start;
+            if (init) { if (result_dt == vb::DT_F64) std::memcpy(&start, init, 8); else { float f; std::memcpy(&f, init, 4); start = f; } }
+            else start = op == vb::OP_PROD ? 1.0 : op == vb::OP_MIN ? INFINITY : op == vb::OP_MAX ? -INFINITY : 0.0;
+            const double r = ma.n ? fold_f(fres, start) : start;
+            if (result_dt == vb::DT_F64) std::memcpy(out, &r, 8); else { float f = (float)r; std::memcpy(out, &f, 4); }
+        } else {
+            long long start;
+            if (init) {
+                switch (result_dt) {
+                    case vb::DT_I64: std::memcpy(&start, init, 8); break;
+                    case vb::DT_I32: { int v; std::memcpy(&v, init, 4); start = v; break; }
+                    default: start = *(const uint8_t*)init; break;
+                }
+            } else {
+                switch (op) {
+                    case vb::OP_PROD: start = 1; break;
+                    case vb::OP_MAX: start = isb ? -1 : -INT64_MAX; break;
+                    case vb::OP_MIN: start = isb ? 1 : INT64_MAX; break;
+                    case vb::OP_AND: start = isb ? 1 : INT64_MAX; break;
+                    default: start = 0; break;
+                }
+            }
+            const long long r = fold_i(ires, start);
+            switch (result_dt) {
+                case vb::DT_I64: std::memcpy(out, &r, 8); break;
+                case vb::DT_I32: { int v = (int)r; std::memcpy(out, &v, 4); break; }
+                case vb::DT_BOOL: { uint8_t v = r != 0; std::memcpy(out, &v, 1); break; }
+                default: { uint8_t v = (uint8_t)r; std::memcpy(out, &v, 1); break; }
+            }
+        }
+    });
+}
+
+namespace { size_t dt_size(int dt) { return (dt == VB_DT_I64 || dt == VB_DT_F64) ? 8 : (dt == VB_DT_I32 || dt == VB_DT_F32) ? 4 : 1; } }
+
+int vb_rastervalues(vb_sim* s, const char* name, int offset, int dt, void* out) {
+    return guard([&] {   // Raster.jl:282-387
+        require_device();
+        if (!s->initialized) throw AssertionError("rastervalues can be only called after finish_init!");
+        RasterStore& r = find_raster(s, name);
+        AgentStore& a = s->A(r.type);
+        const size_t w = dt_size(dt), n = r.ids.size();
+        uint8_t* tmp = (uint8_t*)g_pool.alloc(n * w);
+        field_out_kernel<<<nblk(n), 256, 0, g_stream>>>(a.rstate(), a.cap, a.word, r.cells, s->base[r.type], n, offset, (uint32_t)w, tmp); LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(out, tmp, n * w, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(tmp);
+    });
+}
+int vb_calc_raster_num_edges(vb_sim* s, const char* name, int ei, int64_t* out) {
+    return guard([&] {   // Raster.jl:206-236 with f = id -> num_edges(sim, id, E)
+        require_device();
+        if (!s->initialized) throw AssertionError("calc_raster can be only called after finish_init!");
+        RasterStore& r = find_raster(s, name);
+        EdgeStore& e = s->E(ei);
+        avail(!e.singleedge, "num_edges");
+        s->merge_pending(ei);
+        const size_t n = r.ids.size();
+        long long* tmp = dalloc<long long>(n);
+        const uint32_t shift = e.singletype ? s->base[e.target] : 0;
+        if (e.singletype && e.target != r.type) { std::memset(out, 0, n * 8); dfree(tmp); return; }
+        raster_num_edges_kernel<<<nblk(n), 256, 0, g_stream>>>(r.cells, n, e.kind == vb::KIND_CSR ? e.off : nullptr, e.cnt, e.rows, shift, tmp); LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(tmp);
+    });
+}
+int vb_raster_info(vb_sim* s, const char* name, int* ndims, int64_t* dims, vb_agent_id* ids) {
+    return guard([&] {
+        RasterStore& r = find_raster(s, name);
+        *ndims = (int)r.dims.size();
+        if (dims) for (size_t i = 0; i < r.dims.size(); ++i) dims[i] = r.dims[i];
+        if (ids) std::memcpy(ids, r.ids.data(), r.ids.size() * 8);
+    });
+}
+int vb_num_transitions(vb_sim* s, int64_t* n) { *n = s->num_transitions; return VB_OK; }
+int vb_last_apply_stats(vb_sim* s, double* ms_rw, double* ms_fin, uint64_t* er, uint64_t* ea, uint64_t* ac, uint64_t* kl) {
+    if (ms_rw) *ms_rw = s->ms_rw; if (ms_fin) *ms_fin = s->ms_fin;
+    if (er) *er = s->st_edges_read; if (ea) *ea = s->st_edges_appended; if (ac) *ac = s->st_agents_called; if (kl) *kl = s->st_launches;
+    return VB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+// primitives.cuh — device building blocks of finish_write! and the count->scan->emit write phase:
+// exclusive scan, stable LSD radix sort (8-bit digits) with payload, CSR offset construction,
+// AoS<->SoA transposition, stream compaction of flags.  All hand-written for sm_100a; every kernel is
+// HBM-bound (no tensor-core work on this path).
+//
+// Replaces, on device, what the reference does with Dict/Vector containers on the host:
+//   per-target push! order        src/EdgeMethods.jl:495-496,518-519   -> stable sort on target row
+//   Dict{AgentID,Vector} lookup   src/EdgeMethods.jl:303-371            -> CSR offsets
+//   reuseable slot list           src/AgentMethods.jl:171,430           -> ordered compaction of died flags
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vbp {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t x = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += x;
+    }
+    return v;
+}
+// exclusive scan of one value per thread across a 256-thread block; returns the block total in `total`
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t& total) {
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t inc = warp_incl_scan(v, lane);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
+        s = warp_incl_scan(s, lane);
+        if (lane < SCAN_THREADS / 32) wsum[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t woff = w ? wsum[w - 1] : 0;
+    total = wsum[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return woff + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ bsum) {
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const uint64_t k = base + (uint64_t)i * SCAN_THREADS + threadIdx.x;
+        if (k < n) s += in[k];
+    }
+    uint32_t total;
+    block_excl_scan(s, total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+// in-place exclusive scan of up to SCAN_TILE values by one block; writes the grand total to *total (if non-null)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ total_out) {
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const uint32_t k = threadIdx.x * SCAN_ITEMS + i;
+        v[i] = k < n ? data[k] : 0;
+        s += v[i];
+    }
+    uint32_t total;
+    uint32_t ex = block_excl_scan(s, total);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const uint32_t k = threadIdx.x * SCAN_ITEMS + i;
+        if (k < n) data[k] = ex;
+        ex += v[i];
+    }
+    if (total_out && threadIdx.x == 0) *total_out = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n,
+                                                                    const uint32_t* __restrict__ boff) {
+    // thread t owns items [t*ITEMS, t*ITEMS+ITEMS) of the tile (blocked), so the per-thread scan is sequential
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
+    uint32_t total;
+    uint32_t ex = block_excl_scan(s, total) + boff[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+}
+__global__ void scan_total_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ out, uint64_t n, uint32_t* total) {
+    *total = n ? out[n - 1] + in[n - 1] : 0;
+}
+
+// scratch needed by exclusive_scan for n elements (in uint32 words)
+inline uint64_t scan_scratch_words(uint64_t n) {
+    uint64_t words = 0;
+    while (n > SCAN_TILE) { n = (n + SCAN_TILE - 1) / SCAN_TILE; words += n; }
+    return words + 1;
+}
+// out[i] = sum(in[0..i)); in and out may alias only if identical.  `total` (device, optional) receives the sum.
+inline void exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total, uint32_t* scratch, cudaStream_t st) {
+    if (n == 0) { if (total) cudaMemsetAsync(total, 0, 4, st); return; }
+    if (n <= SCAN_TILE) {
+        if (in != out) cudaMemcpyAsync(out, in, n * 4, cudaMemcpyDeviceToDevice, st);
+        scan_single_kernel<<<1, SCAN_THREADS, 0, st>>>(out, (uint32_t)n, total);
+        return;
+    }
+    const uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, scratch);
+    exclusive_scan(scratch, scratch, nb, total, scratch + nb, st);
+    scan_downsweep_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, scratch);
+}
+
+// ---- stable LSD radix sort, 8-bit digits, u32 keys, up to two payload arrays (4 B and 4/8 B) -----------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;                         // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 4096 keys per block
+constexpr int RS_SEG = RS_TILE / RS_WARPS;           // contiguous keys per warp
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t* __restrict__ hist,
+                                                           uint32_t nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint64_t k = base + (uint64_t)i * RS_THREADS + threadIdx.x;
+        if (k < n) atomicAdd(&h[(keys[k] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+template <class P1, class P2>   // payload word types; use uint8_t-sized tag `NoPayload` for absent
+struct RsArgs {
+    const uint32_t* kin; uint32_t* kout;
+    const P1* p1in; P1* p1out;
+    const P2* p2in; P2* p2out;
+    uint64_t n; int shift; const uint32_t* hist; uint32_t nblocks;
+};
+struct NoPayload { uint8_t x; };
+
+template <class P1, class P2, bool HAS1, bool HAS2>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const RsArgs<P1, P2> a) {
+    __shared__ uint32_t wh[RS_WARPS][256];
+    __shared__ uint32_t dstart[256];
+    __shared__ uint32_t gbase[256];
+    __shared__ __align__(16) uint8_t stage[RS_TILE * 8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t tile0 = (uint64_t)blockIdx.x * RS_TILE;
+    const uint32_t count = (uint32_t)((a.n - tile0) < (uint64_t)RS_TILE ? (a.n - tile0) : (uint64_t)RS_TILE);
+    uint32_t key[RS_ITEMS], pos[RS_ITEMS];
+    // phase 1: per-warp stable ranks (warp w owns the contiguous segment [w*RS_SEG, (w+1)*RS_SEG) of the tile)
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t li = w * RS_SEG + r * 32 + lane;
+        const bool valid = li < count;
+        key[r] = valid ? a.kin[tile0 + li] : 0xffffffffu;
+        const uint32_t d = valid ? ((key[r] >> a.shift) & 255u) : 256u;
+        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(m) - 1;
+        uint32_t prev = 0;
+        if (valid && lane == leader) prev = wh[w][d];
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        if (valid && lane == leader) wh[w][d] = prev + __popc(m);
+        __syncwarp();
+        pos[r] = prev + __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    // phase 2: exclusive prefix over warps per digit, digit starts inside the tile, global bases
+    {
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) { const uint32_t t = wh[ww][d]; wh[ww][d] = run; run += t; }
+        uint32_t total;
+        const uint32_t ex = block_excl_scan(run, total);
+        dstart[d] = ex;
+        gbase[d] = a.hist[(uint64_t)d * a.nblocks + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t li = w * RS_SEG + r * 32 + lane;
+        if (li < count) { const uint32_t d = (key[r] >> a.shift) & 255u; pos[r] += dstart[d] + wh[w][d]; }
+    }
+    // phase 3: stage keys in tile-sorted order, then write each digit run coalesced
+    uint32_t* skey = reinterpret_cast<uint32_t*>(stage);
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t li = w * RS_SEG + r * 32 + lane;
+        if (li < count) skey[pos[r]] = key[r];
+    }
+    __syncthreads();
+    // destination of sorted tile element i (kept in registers for the payload rounds)
+    uint32_t dst[RS_ITEMS];   // positions < n < 2^32 (CSR positions are 32-bit)
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t i = r * RS_THREADS + threadIdx.x;
+        if (i < count) {
+            const uint32_t k = skey[i];
+            const uint32_t d = (k >> a.shift) & 255u;
+            dst[r] = gbase[d] + (i - dstart[d]);
+            a.kout[dst[r]] = k;
+        }
+    }
+    if (HAS1) {
+        __syncthreads();
+        P1* s1 = reinterpret_cast<P1*>(stage);
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r) {
+            const uint32_t li = w * RS_SEG + r * 32 + lane;
+            if (li < count) s1[pos[r]] = a.p1in[tile0 + li];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r) {
+            const uint32_t i = r * RS_THREADS + threadIdx.x;
+            if (i < count) a.p1out[dst[r]] = s1[i];
+        }
+    }
+    if (HAS2) {
+        __syncthreads();
+        P2* s2 = reinterpret_cast<P2*>(stage);
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r) {
+            const uint32_t li = w * RS_SEG + r * 32 + lane;
+            if (li < count) s2[pos[r]] = a.p2in[tile0 + li];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r) {
+            const uint32_t i = r * RS_THREADS + threadIdx.x;
+            if (i < count) a.p2out[dst[r]] = s2[i];
+        }
+    }
+}
+
+inline uint64_t rs_scratch_words(uint64_t n) {
+    const uint64_t nb = (n + RS_TILE - 1) / RS_TILE;
+    return nb * 256 + scan_scratch_words(nb * 256) + 16;
+}
+inline int bits_for(uint64_t maxkey_plus1) {
+    int b = 1;
+    while (b < 32 && (1ull << b) < maxkey_plus1) ++b;
+    return b;
+}
+
+// One sort = ceil(bits/8) passes ping-ponging between (k0,p10,p20) and (k1,p11,p21); returns which buffer
+// set holds the result (0 or 1).  p2 word size: 0 (none), 4 or 8 bytes.  p1 (4 B) may be null.
+inline int radix_sort(uint32_t* k0, uint32_t* k1, uint32_t* p10, uint32_t* p11, void* p20, void* p21, int p2_bytes, uint64_t n, int bits,
+                      uint32_t* scratch, cudaStream_t st) {
+    if (n == 0) return 0;
+    const uint32_t nb = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    uint32_t* hist = scratch;
+    uint32_t* sscr = scratch + (uint64_t)nb * 256;
+    int cur = 0;
+    for (int shift = 0; shift < bits; shift += 8) {
+        uint32_t* kin = cur ? k1 : k0; uint32_t* kout = cur ? k0 : k1;
+        uint32_t* p1in = cur ? p11 : p10; uint32_t* p1out = cur ? p10 : p11;
+        void* p2in = cur ? p21 : p20; void* p2out = cur ? p20 : p21;
+        rs_hist_kernel<<<nb, RS_THREADS, 0, st>>>(kin, n, shift, hist, nb);
+        exclusive_scan(hist, hist, (uint64_t)nb * 256, nullptr, sscr, st);
+        const bool h1 = p10 != nullptr;
+        if (p2_bytes == 8) {
+            RsArgs<uint32_t, uint64_t> a{kin, kout, p1in, p1out, (const uint64_t*)p2in, (uint64_t*)p2out, n, shift, hist, nb};
+            if (h1) rs_scatter_kernel<uint32_t, uint64_t, true, true><<<nb, RS_THREADS, 0, st>>>(a);
+            else rs_scatter_kernel<uint32_t, uint64_t, false, true><<<nb, RS_THREADS, 0, st>>>(a);
+        } else if (p2_bytes == 4) {
+            RsArgs<uint32_t, uint32_t> a{kin, kout, p1in, p1out, (const uint32_t*)p2in, (uint32_t*)p2out, n, shift, hist, nb};
+            if (h1) rs_scatter_kernel<uint32_t, uint32_t, true, true><<<nb, RS_THREADS, 0, st>>>(a);
+            else rs_scatter_kernel<uint32_t, uint32_t, false, true><<<nb, RS_THREADS, 0, st>>>(a);
+        } else {
+            RsArgs<uint32_t, NoPayload> a{kin, kout, p1in, p1out, nullptr, nullptr, n, shift, hist, nb};
+            if (h1) rs_scatter_kernel<uint32_t, NoPayload, true, false><<<nb, RS_THREADS, 0, st>>>(a);
+            else rs_scatter_kernel<uint32_t, NoPayload, false, false><<<nb, RS_THREADS, 0, st>>>(a);
+        }
+        cur ^= 1;
+    }
+    return cur;
+}
+
+// ---- CSR row counts from sorted row keys: cnt[r] += (#entries with key r).  Two atomics per non-empty row
+//      (run start subtracts its index, run end adds index+1), no per-entry atomics; an exclusive scan of cnt
+//      gives the offsets.  cnt must be zero (or hold the counts of an existing CSR being merged). ------------
+__global__ void csr_run_counts_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ cnt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    if (i == 0 || keys[i - 1] != k) atomicSub(&cnt[k], (uint32_t)i);
+    if (i == n - 1 || keys[i + 1] != k) atomicAdd(&cnt[k], (uint32_t)i + 1u);
+}
+__global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void iota_u32_kernel(uint32_t* p, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+// row lengths -> counts (for merging an existing CSR with newly sorted edges)
+__global__ void row_counts_kernel(const uint32_t* __restrict__ off, uint32_t rows, uint32_t* __restrict__ cnt) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) cnt[r] = off[r + 1] - off[r];
+}
+
+// ---- AoS (host records) <-> SoA word columns ------------------------------------------------------------------
+// dst column c of record slot0+i at cols + c*stride*word + (slot0+i)*word
+__global__ void aos_to_soa_kernel(const uint8_t* __restrict__ aos, uint8_t* __restrict__ cols, uint64_t stride, uint64_t slot0, uint64_t n,
+                                  uint32_t size, uint32_t word) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ncols = size / word;
+    if (t >= n * ncols) return;
+    const uint64_t i = t / ncols;
+    const uint32_t c = (uint32_t)(t % ncols);
+    const uint8_t* s = aos + i * size + (uint64_t)c * word;
+    uint8_t* d = cols + (uint64_t)c * stride * word + (slot0 + i) * word;
+    for (uint32_t b = 0; b < word; ++b) d[b] = s[b];
+}
+__global__ void soa_to_aos_kernel(const uint8_t* __restrict__ cols, uint8_t* __restrict__ aos, uint64_t stride, uint64_t slot0, uint64_t n,
+                                  uint32_t size, uint32_t word) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ncols = size / word;
+    if (t >= n * ncols) return;
+    const uint64_t i = t / ncols;
+    const uint32_t c = (uint32_t)(t % ncols);
+    uint8_t* d = aos + i * size + (uint64_t)c * word;
+    const uint8_t* s = cols + (uint64_t)c * stride * word + (slot0 + i) * word;
+    for (uint32_t b = 0; b < word; ++b) d[b] = s[b];
+}
+// gather records through an index list (compacted read-out): aos[i] = record idx[i]
+__global__ void soa_gather_aos_kernel(const uint8_t* __restrict__ cols, uint8_t* __restrict__ aos, uint64_t stride, const uint32_t* __restrict__ idx,
+                                      uint64_t n, uint32_t size, uint32_t word) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ncols = size / word;
+    if (t >= n * ncols) return;
+    const uint64_t i = t / ncols;
+    const uint32_t c = (uint32_t)(t % ncols);
+    uint8_t* d = aos + i * size + (uint64_t)c * word;
+    const uint8_t* s = cols + (uint64_t)c * stride * word + (uint64_t)idx[i] * word;
+    for (uint32_t b = 0; b < word; ++b) d[b] = s[b];
+}
+// column-wise copy between two SoA buffers with different strides (capacity growth, log -> CSR moves)
+__global__ void soa_copy_kernel(const uint8_t* __restrict__ src, uint64_t sstride, uint8_t* __restrict__ dst, uint64_t dstride, uint64_t n,
+                                uint32_t ncols, uint32_t word, uint64_t soff, uint64_t doff) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = n * word;
+    if (t >= per * ncols) return;
+    const uint32_t c = (uint32_t)(t / per);
+    const uint64_t b = t % per;
+    dst[(uint64_t)c * dstride * word + doff * word + b] = src[(uint64_t)c * sstride * word + soff * word + b];
+}
+
+// ---- flags -> ordered index list (newly died slots appended to the reuse stack in ascending order) ------------
+// flag[i] = died_w[i] && !died_r[i] for i < n_r (slots beyond the read length cannot die this step)
+__global__ void newly_died_flags_kernel(const uint8_t* __restrict__ died_r, const uint8_t* __restrict__ died_w, uint32_t n, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (died_w[i] && !died_r[i]) ? 1u : 0u;
+}
+__global__ void alive_flags_kernel(const uint8_t* __restrict__ died, uint32_t n, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = died ? (died[i] ? 0u : 1u) : 1u;
+}
+__global__ void compact_indices_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t n, uint32_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = (uint32_t)i;
+}
+
+inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace vbp

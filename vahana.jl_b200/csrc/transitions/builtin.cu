@@ -1,0 +1,9 @@
+// builtin.cu — compiles every built-in single-source transition (transitions/*.h) into CUDA launchers and
+// registers them with the engine under (name, agent type).  Model authors build the same way: include
+// vahana_device.cuh, define functors, VB_REGISTER_TRANSITION(...), link or vb_load_model_library() the result.
+#include "../../../include/vahana_device.cuh"
+#include "all.h"
+
+#define VB_TRANSITION(tname, atype, ...) VB_REGISTER_TRANSITION(tname, atype, __VA_ARGS__)
+#include "registry.inc"
+#undef VB_TRANSITION

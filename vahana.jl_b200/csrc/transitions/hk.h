@@ -18,7 +18,7 @@ enum : int { E_KNOWS = 0 };             // edge types in registration order (str
 //   accepted = filter(o -> abs(o - agent.opinion) < ϵ, opinions);  HKAgent(mean(accepted))
 // The neighbour walk is cooperative: each lane of the agent's group folds a strided share of the
 // row, ctx.sum() combines the lanes (group of 1 in the oracle => strict left-to-right order).
-struct Step {
+struct Step : vb::TransitionBase {
     using State = HKAgent;
     static constexpr bool kCooperative = true;
     template <class Ctx>

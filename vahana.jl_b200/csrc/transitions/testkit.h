@@ -13,25 +13,25 @@ struct FooBool { int64_t foo; bool b; };     // ADefault (test/core.jl:14-17)
 struct EFoo { int64_t foo; };                // ESDict / EdgeD... (test/core.jl:24, test/edges.jl:15-30)
 
 // do state,_,_ -> nothing   (test/core.jl:144-146,150-152)
-template <class S> struct KillAll {
+template <class S> struct KillAll : vb::TransitionBase {
     using State = S;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx&, S&, vb::AgentID) const { return false; }
 };
 // identity / no-op closures (test/core.jl:101-103 on rank 0, test/edges.jl:349-350,377-378)
-template <class S> struct Identity {
+template <class S> struct Identity : vb::TransitionBase {
     using State = S;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx&, S&, vb::AgentID) const { return true; }
 };
 // state.foo < 6 ? state : nothing   (test/core.jl:223-229)
-struct KeepFooLt6 {
+struct KeepFooLt6 : vb::TransitionBase {
     using State = Foo;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx&, Foo& s, vb::AgentID) const { return s.foo < 6; }
 };
 // state.foo % 2 == 0 ? state : nothing   (test/core.jl:256-258)
-struct KeepEvenFoo {
+struct KeepEvenFoo : vb::TransitionBase {
     using State = Foo;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx&, Foo& s, vb::AgentID) const { return s.foo % 2 == 0; }
@@ -39,7 +39,7 @@ struct KeepEvenFoo {
 // create_sum_state_neighbors(edgetype): sum of n.foo over neighborstates_flexible (test/core.jl:71-83).
 // `foo` is the first field of every agent type of the model, so the flexible lookup is a field read
 // at offset 0 of whatever type the neighbour id carries.
-template <int E> struct SumStateNeighbors {
+template <int E> struct SumStateNeighbors : vb::TransitionBase {
     using State = Foo;
     static constexpr bool kCooperative = true;
     template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& self, vb::AgentID id) const {
@@ -52,27 +52,28 @@ template <int E> struct SumStateNeighbors {
     }
 };
 // ADefault(state.foo, false)   (test/core.jl:425-427)
-struct SetBoolFalse {
+struct SetBoolFalse : vb::TransitionBase {
     using State = FooBool;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx&, FooBool& s, vb::AgentID) const { s.b = false; return true; }
 };
 // ADefault(state.foo, mod(id, 2) == 1)   (test/core.jl:433-435)
-struct SetBoolIdOdd {
+struct SetBoolIdOdd : vb::TransitionBase {
     using State = FooBool;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx&, FooBool& s, vb::AgentID id) const { s.b = (id % 2) == 1; return true; }
 };
 // @test num_edges(sim, id, ET) == n  inside the closure (test/edges.jl:338-346): the count is
 // stored in the agent so the host can assert on it.
-template <int E> struct StoreNumEdges {
+template <int E> struct StoreNumEdges : vb::TransitionBase {
     using State = Foo;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& s, vb::AgentID id) const { s.foo = ctx.num_edges(E, id); return true; }
 };
 // add_edges!(sim, id, edges(sim, id, ET))   (test/edges.jl:357-359,367-369)
-template <int E> struct ReaddEdges {
+template <int E> struct ReaddEdges : vb::TransitionBase {
     using State = Foo;
+    using EdgeWrites = vb::IntList<E>;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
         ctx.template for_each_edge<EFoo>(E, id, [&](vb::AgentID from, const EFoo& st) { ctx.add_edge(E, from, id, st); });
@@ -80,8 +81,9 @@ template <int E> struct ReaddEdges {
     }
 };
 // add_edge!(sim, id, id, t())  (test/edges.jl:253-266): used for the read/write permission checks
-template <int E, bool kStateful> struct AddSelfLoop {
+template <int E, bool kStateful> struct AddSelfLoop : vb::TransitionBase {
     using State = Foo;
+    using EdgeWrites = vb::IntList<E>;
     static constexpr bool kCooperative = false;
     template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
         if (kStateful) ctx.add_edge(E, id, id, EFoo{0});
