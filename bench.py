@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py — edges/s per apply! of the Hegselmann–Krause transition on the synthetic power-law graph
+(BASELINE.json config 4: 100M agents / ~2B edges), one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this engine (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle restatement)
+
+Prints ONE JSON line (rank 0).  Keys: see the task contract; `roofline` is for the dominant kernel
+(transition_kernel<hk::Step>), `cpu_baseline` is the oracle timed on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+SEED_GRAPH, SEED_OPINION = 4, 5
+C_PARETO, DMAX = 6.8333, 1_000_000       # mean in-degree ~ 20 (+1 self loop)
+EPS = 0.02
+ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "libvahana_oracle.so")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_oracle_sim(vh, n):
+    """The reference's CPU algorithm (oracle restatement) on an n-agent sample of the same workload."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    from models import hk_model
+    ob = vh.load_backend(ORACLE_LIB)
+    ne = C.c_uint64()
+    ob.lib.vbw_hk_powerlaw_host(C.c_uint64(n), 1, C.c_uint64(SEED_GRAPH), C.c_uint64(SEED_OPINION), C.c_double(C_PARETO), C.c_uint32(DMAX),
+                                None, None, None, C.byref(ne))
+    fr = np.zeros(ne.value, dtype=np.uint64)
+    to = np.zeros(ne.value, dtype=np.uint64)
+    op = np.zeros(n, dtype=np.float64)
+    ob.lib.vbw_hk_powerlaw_host(C.c_uint64(n), 1, C.c_uint64(SEED_GRAPH), C.c_uint64(SEED_OPINION), C.c_double(C_PARETO), C.c_uint32(DMAX),
+                                fr.ctypes.data_as(C.c_void_p), to.ctypes.data_as(C.c_void_p), op.ctypes.data_as(C.c_void_p), C.byref(ne))
+    sim = vh.create_simulation(hk_model(), params={"eps": EPS}, backend=ob)
+    sim.add_agents("HKAgent", op.view([("opinion", "f8")]))
+    sim.add_edges(fr, to, "Knows")
+    sim.finish_init()
+    return sim, int(ne.value)
+
+
+def time_oracle(vh, n, steps, warmup):
+    sim, ne = build_oracle_sim(vh, n)
+    for _ in range(warmup):
+        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+    dt = time.perf_counter() - t0
+    return ne * steps / dt, dt / steps * 1e3, ne
+
+
+def run_reference(args):
+    import vahana_b200 as vh
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_agents
+    eps_, ms, ne = time_oracle(vh, n, args.steps, args.warmup)
+    sample = f"{n} agents / {ne} edges of the config-4 generator (1/{int(args.agents // n)} scale; the Dict-of-Vector containers of the full graph do not fit host RAM)"
+    line = {
+        "impl": "reference", "metric": "edges/sec per apply! (Hegselmann-Krause read+write phase)", "value": eps_, "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "hk-powerlaw (BASELINE config 4)", "agents": int(args.agents), "eps": EPS, "note": "oracle restatement of the reference's CPU apply!, not Julia (Julia/MPI are not installed in this image)"},
+        "cpu_baseline": {"value": eps_, "unit": "edges/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": eps_, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    import vahana_b200 as vh
+    from models import hk_model
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    be = vh.default_backend()
+    be.init(local)
+    be.set_stream(torch.cuda.current_stream().cuda_stream)
+    lib = be.lib
+    lib.vb_device_view_bytes.restype = C.c_uint64
+
+    # ---- build the workload on device (per rank: the same graph is built by every rank when world > 1:
+    #      replicas until the sharded halo path lands; see DESIGN.md "multi-GPU") ----
+    n = int(args.agents)
+    t_build = time.perf_counter()
+    sim = vh.create_simulation(hk_model(), params={"eps": EPS}, backend=be, device=local)
+    ne = C.c_uint64()
+    be.check(lib.vbw_hk_powerlaw_build(sim.h, 1, 0, C.c_uint64(n), C.c_uint64(SEED_GRAPH), C.c_uint64(SEED_OPINION), C.c_double(C_PARETO),
+                                       C.c_uint32(DMAX), C.c_uint64(1 << 22), C.byref(ne)))
+    sim.finish_init()
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+    E = int(ne.value)
+
+    def step():
+        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # ---- device-timed K steps ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, launches, edges_read = 0.0, 0, 0
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+        st = sim.last_apply_stats()
+        kernel_ms += st["ms_kernel"]
+        launches += st["kernel_launches"]
+        edges_read += st["edges_read"]
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end to end through the public API: apply! + a host-visible metric every step ----
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    metric = 0.0
+    for _ in range(args.steps):
+        step()
+        metric = sim.mapreduce("opinion", "+", "HKAgent")     # device reduction, 8 B device->host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    view_bytes = int(lib.vb_device_view_bytes())
+
+    if rank != 0:
+        return
+    assert edges_read == E * args.steps, (edges_read, E)
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes of the read+write phase: 12 B/edge (4 B column + 8 B source state) +
+    # 20 B/agent (4 B row offset + 8 B own state + 8 B new state)
+    alg_bytes = 12.0 * E + 20.0 * n
+    k_ms = kernel_ms / args.steps
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "hk_step_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    cpu_eps, cpu_ms, cpu_ne = time_oracle(vh, args.cpu_agents, 3, 1) if not args.no_cpu else (None, None, None)
+    value = E * args.steps * world / (ms_total * 1e-3) if world == 1 else E * args.steps * world / (ms_total * 1e-3)
+    line = {
+        "metric": "edges/sec per apply! (Hegselmann-Krause read+write phase)", "value": value, "unit": "edges/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "hk-powerlaw-100M (BASELINE config 4)", "agents": n, "edges": E, "eps": EPS,
+                   "parallelism": f"{world} GPU" + (" (independent replicas of the full graph)" if world > 1 else ""),
+                   "l2": "inputs larger than L2 (source states 0.8 GB, CSR columns %.1f GB); no flush needed" % (4.0 * E / 1e9),
+                   "agent_updates_per_s": n * args.steps * world / (ms_total * 1e-3), "build_s": t_build, "opinion_sum": metric},
+        "roofline": {"bound": "hbm", "kernel": "transition_kernel<hk::Step, DIRECT, warp-per-agent>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "frac_of_8TBs_spec": achieved / 8000.0},
+        "cpu_baseline": None if cpu_eps is None else {
+            "value": cpu_eps, "unit": "edges/s", "cores": 1, "kind": "port",
+            "sample": f"{args.cpu_agents} agents / {cpu_ne} edges of the same generator, 3 applies (oracle restatement, not Julia)"},
+        "e2e": {"value": E * args.steps / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": view_bytes, "d2h_bytes_per_step": 8 + 4,
+                "note": "apply! + mapreduce(opinion,+) through the Python/ctypes API per step; agent state stays resident on device as it stays resident in the reference's process"},
+        "gpu_launches": launches, "clocks": clk,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--agents", type=float, default=1e8)
+    ap.add_argument("--cpu-agents", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

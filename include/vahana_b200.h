@@ -70,6 +70,7 @@ const char* vb_last_error(void);
 const char* vb_backend(void);                 /* "cuda-sm100a" (product) or "oracle-cpu" (tests only) */
 int vb_init(int device);                      /* mpiinit analogue, src/MPIinit.jl:21: rank <-> GPU */
 int vb_shutdown(void);
+int vb_set_stream(void* cuda_stream);         /* run on the caller's CUDA stream (cudaStream_t) instead of the engine's own */
 /* multi-GPU: one process per GPU; the 128-byte NCCL unique id is created on rank 0 and
  * handed to the other ranks by the host launcher (torch.distributed store / MPI / file). */
 int vb_comm_unique_id(uint8_t id_out[128]);
@@ -145,6 +146,8 @@ int vb_export_csr(vb_sim* sim, int etype, int target_type, uint64_t* offsets_out
                   vb_agent_id* from_out, void* states_out, uint64_t cap);
 int vb_last_apply_stats(vb_sim* sim, double* ms_read_write, double* ms_finish, uint64_t* edges_read,
                         uint64_t* edges_appended, uint64_t* agents_called, uint64_t* kernel_launches);
+uint64_t vb_device_view_bytes(void);               /* bytes of the simulation view uploaded host->device per transition launch */
+int vb_last_kernel_ms(vb_sim* sim, double* ms_out); /* CUDA-event time of the transition kernels of the last apply */
 
 #ifdef __cplusplus
 }

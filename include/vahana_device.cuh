@@ -106,7 +106,7 @@ struct DeviceSim {
 
 // per-launch arguments of one transition kernel
 struct LaunchArgs {
-    const DeviceSim* ds;
+    const DeviceSim* ds;      // HOST pointer: the launcher copies the view into the kernel's parameter block
     int mode;                 // Mode
     int type;                 // called agent type id
     uint32_t n;               // slots to visit (= nslots_r of the type)
@@ -116,8 +116,19 @@ struct LaunchArgs {
     uint32_t ebase[MAX_EDGE_WRITES];      // EMIT: log position where this call's appends start
     uint32_t* acount[MAX_AGENT_WRITES];   // COUNT: per-agent add_agent counts; EMIT: exclusive offsets
     uint32_t abase[MAX_AGENT_WRITES];     // EMIT: births of that type by earlier calls of this apply
-    unsigned long long* stats;            // [0] edges read
+    unsigned long long* stats;            // 1024 counters, 4 words apart: edges read (summed by the host)
+    // degree binning of cooperative, write-free transitions (DESIGN.md "read phase"):
+    int group;                            // lanes per agent: 0 = default (32 cooperative / 1 otherwise), 8, 32 or 256
+    int primary_edge;                     // edge type whose row length classifies an agent (-1 = none)
+    uint32_t heavy_min;                   // group < 256: skip agents with >= heavy_min edges (they run in the block pass)
+    const uint32_t* rows;                 // group == 256: list of agent slots to run (one block each)
     cudaStream_t stream;
+};
+// what the kernel actually receives: launch arguments + the whole simulation view, by value in the
+// parameter block (constant bank): no separate upload, no pointer chase to reach a container.
+struct KernelArgs {
+    LaunchArgs la;
+    DeviceSim ds;
 };
 
 // host-side descriptor of a compiled transition (one per (name, agent type))
@@ -128,6 +139,7 @@ struct TransitionInfo {
     int cooperative;
     int n_edge_writes, edge_writes[MAX_EDGE_WRITES];
     int n_agent_writes, agent_writes[MAX_AGENT_WRITES];
+    int primary_edge;         // F::kPrimaryEdge (-1 = none): enables degree binning of the read phase
     cudaError_t (*launch)(const LaunchArgs&);
 };
 // exported by libvahana_b200.so; model libraries call it from static initialisers
@@ -151,6 +163,29 @@ __device__ __forceinline__ T soa_load(const uint8_t* __restrict__ cols, uint32_t
     union { T t; Word w[NC]; } u;
 #pragma unroll
     for (int c = 0; c < NC; ++c) u.w[c] = reinterpret_cast<const Word*>(cols + (size_t)c * stride * W)[i];
+    return u.t;
+}
+// random gather of one record: bypass L1 allocation and ask L2 for 64 B instead of the default 128 B per miss
+// (profiles/microbench/gather.cu: 114 B -> 60 B of DRAM traffic per random 8 B load on B200)
+template <int W> __device__ __forceinline__ typename WordT<W>::type ld_gather_word(const void* p) { return *reinterpret_cast<const typename WordT<W>::type*>(p); }
+template <> __device__ __forceinline__ uint64_t ld_gather_word<8>(const void* p) {
+    uint64_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+template <> __device__ __forceinline__ uint32_t ld_gather_word<4>(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.b32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+template <class T>
+__device__ __forceinline__ T soa_gather(const uint8_t* __restrict__ cols, uint32_t stride, uint32_t i) {
+    constexpr int W = SoaWord<sizeof(T)>::value;
+    constexpr int NC = sizeof(T) / W;
+    typedef typename WordT<W>::type Word;
+    union { T t; Word w[NC]; } u;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) u.w[c] = ld_gather_word<W>(cols + (size_t)c * stride * W + (size_t)i * W);
     return u.t;
 }
 template <class T>
@@ -202,27 +237,34 @@ class Ctx {
     __device__ __forceinline__ int lanes() const { return GROUP; }
     __device__ __forceinline__ int lane() const { return (int)lane_; }
     __device__ __forceinline__ bool leader() const { return lane_ == 0; }
-    template <class T> __device__ __forceinline__ T sum(T v) const {
-        if (GROUP == 32) {
+    // group reductions: sub-warp / warp groups shuffle (exited lanes of other groups are not named by a
+    // non-exited thread's butterfly partners: groups are aligned powers of two), block groups go through smem
+    struct OpSum { template <class T> __device__ __forceinline__ T operator()(T a, T b) const { return a + b; } };
+    struct OpMax { template <class T> __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; } };
+    struct OpMin { template <class T> __device__ __forceinline__ T operator()(T a, T b) const { return a < b ? a : b; } };
+    template <class T, class Op> __device__ __forceinline__ T reduce(T v, Op op) const {
+        if (GROUP == 1) return v;
+        constexpr int W = GROUP < 32 ? GROUP : 32;
+        // all lanes of one group run the functor in lock step, so the group's own lanes are a safe shuffle mask
+        const unsigned mask = GROUP >= 32 ? 0xffffffffu : (((1u << W) - 1u) << ((threadIdx.x & 31u) / W * W));
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        for (int o = W / 2; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(mask, v, o));
+        if (GROUP > 32) {
+            __shared__ unsigned long long red[GROUP > 32 ? GROUP / 32 : 1];
+            static_assert(sizeof(T) <= 8, "block reduction of values up to 8 bytes");
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { unsigned long long u = 0; memcpy(&u, &v, sizeof(T)); red[threadIdx.x >> 5] = u; }
+            __syncthreads();
+            T r; { unsigned long long u = red[0]; memcpy(&r, &u, sizeof(T)); }
+#pragma unroll
+            for (int i = 1; i < GROUP / 32; ++i) { T x; unsigned long long u = red[i]; memcpy(&x, &u, sizeof(T)); r = op(r, x); }
+            v = r;
         }
         return v;
     }
-    template <class T> __device__ __forceinline__ T max(T v) const {
-        if (GROUP == 32) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { T x = __shfl_xor_sync(0xffffffffu, v, o); v = x > v ? x : v; }
-        }
-        return v;
-    }
-    template <class T> __device__ __forceinline__ T min(T v) const {
-        if (GROUP == 32) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { T x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
-        }
-        return v;
-    }
+    template <class T> __device__ __forceinline__ T sum(T v) const { return reduce(v, OpSum()); }
+    template <class T> __device__ __forceinline__ T max(T v) const { return reduce(v, OpMax()); }
+    template <class T> __device__ __forceinline__ T min(T v) const { return reduce(v, OpMin()); }
 
     // -- id <-> composite --
     __device__ __forceinline__ bool comp_of(AgentID id, uint32_t& comp) const {
@@ -340,25 +382,27 @@ class Ctx {
         if (ds.check && !av.readable) fail(DERR_AGENT_NOT_READABLE);
         uint32_t row;
         if (!row_of(ev, id, row)) return;
-        const uint32_t b = ev.off[row], en = ev.off[row + 1];
+        const uint32_t b = __ldcs(ev.off + row), en = __ldcs(ev.off + row + 1);   // CSR is streamed once: evict-first
         const uint32_t tb = ds.base[type];
         const uint32_t* __restrict__ src = ev.src;
         const uint8_t* __restrict__ st = av.state_r;
-        const uint32_t cap = av.cap;
+        const uint32_t cap = av.cap, nsl = av.nslots_r;
         uint32_t k = b + lane_;
-        // two independent gathers in flight per lane
-        for (; k + GROUP < en; k += 2 * GROUP) {
-            const uint32_t s0 = src[k] - tb, s1 = src[k + GROUP] - tb;
-            if (ds.check && (s0 >= av.nslots_r || s1 >= av.nslots_r)) { fail(DERR_AGENT_TYPE_MISMATCH); continue; }
-            const A a0 = soa_load<A>(st, cap, s0);
-            const A a1 = soa_load<A>(st, cap, s1);
-            fn(a0);
-            fn(a1);
+        // four independent gathers in flight per lane; the unsigned compare also rejects sources of another type
+        for (; k + 3 * GROUP < en; k += 4 * GROUP) {
+            const uint32_t s0 = __ldcs(src + k) - tb, s1 = __ldcs(src + k + GROUP) - tb;
+            const uint32_t s2 = __ldcs(src + k + 2 * GROUP) - tb, s3 = __ldcs(src + k + 3 * GROUP) - tb;
+            if ((s0 >= nsl) | (s1 >= nsl) | (s2 >= nsl) | (s3 >= nsl)) { fail(DERR_AGENT_TYPE_MISMATCH); continue; }
+            const A a0 = soa_gather<A>(st, cap, s0);
+            const A a1 = soa_gather<A>(st, cap, s1);
+            const A a2 = soa_gather<A>(st, cap, s2);
+            const A a3 = soa_gather<A>(st, cap, s3);
+            fn(a0); fn(a1); fn(a2); fn(a3);
         }
-        if (k < en) {
-            const uint32_t s0 = src[k] - tb;
-            if (ds.check && s0 >= av.nslots_r) { fail(DERR_AGENT_TYPE_MISMATCH); return; }
-            fn(soa_load<A>(st, cap, s0));
+        for (; k < en; k += GROUP) {
+            const uint32_t s0 = __ldcs(src + k) - tb;
+            if (s0 >= nsl) { fail(DERR_AGENT_TYPE_MISMATCH); continue; }
+            fn(soa_gather<A>(st, cap, s0));
         }
         if (lane_ == 0) edges_read += en - b;
     }
@@ -469,13 +513,20 @@ class Ctx {
 // ---- the transition kernel: the per-agent loop of transition_with(out)_read! + transition_with_write!
 //      (src/AgentMethods.jl:159-245) with GROUP lanes per agent -----------------------------------------
 template <class F, int MODE, int GROUP>
-__global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__ LaunchArgs la) {
+__global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__ KernelArgs ka) {
     typedef typename F::State State;
-    const DeviceSim& ds = *la.ds;
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t idx = gtid / GROUP;
-    const uint32_t lane = gtid % GROUP;
-    if (idx >= la.n) return;
+    const LaunchArgs& la = ka.la;
+    const DeviceSim& ds = ka.ds;
+    uint32_t idx, lane;
+    if (GROUP == 256) {                                                // block per agent: heavy rows of the binned read phase
+        idx = la.rows[blockIdx.x];
+        lane = threadIdx.x;
+    } else {
+        const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (gtid / GROUP >= la.n) return;
+        idx = (uint32_t)(gtid / GROUP);
+        lane = (uint32_t)(gtid % GROUP);
+    }
     const AgentView& av = ds.agents[la.type];
     bool skip = av.died_r && av.died_r[idx];                           // jump over died agents (:199-203)
     if (!skip && la.with_edge >= 0) {                                  // with_edge: only targets of that edge type (:209-229)
@@ -483,14 +534,17 @@ __global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__
         const uint32_t row = ds.base[la.type] + idx;
         skip = !(row < we.rows && (we.kind == KIND_CSR ? we.off[row + 1] != we.off[row] : we.cnt[row] != 0));
     }
+    if (GROUP < 256 && !skip && la.heavy_min) {                        // heavy rows are handled by the block pass
+        const EdgeView& pe = ds.edges[la.primary_edge];
+        const uint32_t row = (pe.target ? 0u : ds.base[la.type]) + idx;
+        if (row < pe.rows && pe.off[row + 1] - pe.off[row] >= la.heavy_min) return;
+    }
     if (skip) {
-        if (lane == 0) {
-            if (MODE == MODE_COUNT) {
+        if (lane == 0 && MODE == MODE_COUNT) {
 #pragma unroll
-                for (int i = 0; i < F::EdgeWrites::size; ++i) la.ecount[i][idx] = 0;
+            for (int i = 0; i < F::EdgeWrites::size; ++i) la.ecount[i][idx] = 0;
 #pragma unroll
-                for (int i = 0; i < F::AgentWrites::size; ++i) la.acount[i][idx] = 0;
-            }
+            for (int i = 0; i < F::AgentWrites::size; ++i) la.acount[i][idx] = 0;
         }
         return;
     }
@@ -517,22 +571,51 @@ __global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__
             av.died_w[idx] = 1;
         }
     }
-    if (ctx.edges_read) atomicAdd(la.stats, ctx.edges_read);
+    // statistics: spread over 1024 counters (32 B apart) so the L2 atomic units never serialise on one address
+    if (ctx.edges_read) atomicAdd(la.stats + ((blockIdx.x & 1023u) << 2), ctx.edges_read);
 }
 
+template <class F, int MODE, int GROUP>
+cudaError_t launch_one(const KernelArgs& ka) {
+    const LaunchArgs& la = ka.la;
+    const unsigned threads = 256;
+    unsigned blocks;
+    if (GROUP == 256) blocks = la.n;   // la.n = number of listed rows
+    else blocks = (unsigned)(((unsigned long long)la.n * GROUP + threads - 1) / threads);
+    if (blocks == 0) return cudaSuccess;
+    transition_kernel<F, MODE, GROUP><<<blocks, threads, 0, la.stream>>>(ka);
+    return cudaGetLastError();
+}
+
+template <class F, bool COOP> struct LaunchSelect;
+template <class F> struct LaunchSelect<F, false> {   // thread per agent: exact sequential semantics inside the functor
+    static cudaError_t run(const KernelArgs& ka) {
+        switch (ka.la.mode) {
+            case MODE_COUNT: return launch_one<F, MODE_COUNT, 1>(ka);
+            case MODE_EMIT: return launch_one<F, MODE_EMIT, 1>(ka);
+            default: return launch_one<F, MODE_DIRECT, 1>(ka);
+        }
+    }
+};
+template <class F> struct LaunchSelect<F, true> {    // cooperative: 8 / 32 / 256 lanes per agent
+    static cudaError_t run(const KernelArgs& ka) {
+        switch (ka.la.mode) {
+            case MODE_COUNT: return launch_one<F, MODE_COUNT, 32>(ka);
+            case MODE_EMIT: return launch_one<F, MODE_EMIT, 32>(ka);
+            default:
+                if (ka.la.group == 8) return launch_one<F, MODE_DIRECT, 8>(ka);
+                if (ka.la.group == 256) return launch_one<F, MODE_DIRECT, 256>(ka);
+                return launch_one<F, MODE_DIRECT, 32>(ka);
+        }
+    }
+};
 template <class F>
 cudaError_t launch_transition(const LaunchArgs& la) {
-    constexpr int GROUP = F::kCooperative ? 32 : 1;
-    const unsigned threads = 256;
-    const unsigned long long total = (unsigned long long)la.n * GROUP;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    if (blocks == 0) return cudaSuccess;
-    switch (la.mode) {
-        case MODE_DIRECT: transition_kernel<F, MODE_DIRECT, GROUP><<<blocks, threads, 0, la.stream>>>(la); break;
-        case MODE_COUNT: transition_kernel<F, MODE_COUNT, GROUP><<<blocks, threads, 0, la.stream>>>(la); break;
-        case MODE_EMIT: transition_kernel<F, MODE_EMIT, GROUP><<<blocks, threads, 0, la.stream>>>(la); break;
-    }
-    return cudaGetLastError();
+    static thread_local KernelArgs ka;
+    ka.la = la;
+    ka.ds = *la.ds;
+    ka.la.ds = nullptr;
+    return LaunchSelect<F, F::kCooperative>::run(ka);
 }
 
 template <class F>
@@ -546,6 +629,7 @@ TransitionInfo make_transition_info(const char* name, const char* agent_type) {
     for (int i = 0; i < F::EdgeWrites::size; ++i) ti.edge_writes[i] = F::EdgeWrites::at(i);
     ti.n_agent_writes = F::AgentWrites::size;
     for (int i = 0; i < F::AgentWrites::size; ++i) ti.agent_writes[i] = F::AgentWrites::at(i);
+    ti.primary_edge = F::kPrimaryEdge;
     ti.launch = &launch_transition<F>;
     return ti;
 }

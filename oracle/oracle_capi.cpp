@@ -27,6 +27,9 @@ const char* vb_last_error(void) { return g_err.c_str(); }
 const char* vb_backend(void) { return "oracle-cpu"; }
 int vb_init(int) { return VB_OK; }
 int vb_shutdown(void) { return VB_OK; }
+int vb_set_stream(void*) { return VB_OK; }
+uint64_t vb_device_view_bytes(void) { return 0; }
+int vb_last_kernel_ms(vb_sim*, double* ms) { *ms = 0; return VB_OK; }
 int vb_comm_unique_id(uint8_t id_out[128]) { std::memset(id_out, 0, 128); return VB_OK; }
 int vb_comm_init(int, int nranks, const uint8_t*) { if (nranks != 1) { g_err = "oracle C-ABI is single rank"; return VB_ERR_ARG; } return VB_OK; }
 int vb_comm_rank(int* r, int* n) { *r = 0; *n = 1; return VB_OK; }

@@ -62,3 +62,55 @@ def test_hk_gpu_vs_oracle(oracle, cuda, n, m):
     assert st["edges_read"] == 2 * len(uv) + n
     assert st["agents_called"] == n
     assert st["kernel_launches"] >= 1
+
+
+def _powerlaw_host(backend_lib, n, c=6.8333, dmax=1000000):
+    import ctypes as C
+    ne = C.c_uint64()
+    backend_lib.vbw_hk_powerlaw_host(C.c_uint64(n), 1, C.c_uint64(4), C.c_uint64(5), C.c_double(c), C.c_uint32(dmax), None, None, None, C.byref(ne))
+    fr = np.zeros(ne.value, dtype=np.uint64)
+    to = np.zeros(ne.value, dtype=np.uint64)
+    op = np.zeros(n, dtype=np.float64)
+    backend_lib.vbw_hk_powerlaw_host(C.c_uint64(n), 1, C.c_uint64(4), C.c_uint64(5), C.c_double(c), C.c_uint32(dmax),
+                                     fr.ctypes.data_as(C.c_void_p), to.ctypes.data_as(C.c_void_p), op.ctypes.data_as(C.c_void_p), C.byref(ne))
+    return fr, to, op
+
+
+def test_powerlaw_generator_host(oracle):
+    fr, to, op = _powerlaw_host(oracle.lib, 50000)
+    n = 50000
+    deg = np.bincount((to & ((1 << 36) - 1)).astype(np.int64) - 1, minlength=n)
+    assert deg.min() >= 7 and 18 < deg.mean() < 24          # Pareto(1.5) with c = 6.83, +1 self loop
+    assert np.all(np.diff(to.astype(np.int64)) >= 0)        # grouped by target, ascending
+    assert 0 <= op.min() and op.max() < 1
+    src = (fr & ((1 << 36) - 1)).astype(np.int64) - 1
+    assert np.median(src) < 0.3 * n                         # hub skew: floor(N u^2)
+
+
+@pytest.mark.gpu
+def test_powerlaw_device_generator_matches_host_and_oracle(oracle, cuda):
+    """The device generator used by bench.py builds the same CSR as the host generator fed through the oracle,
+    and one HK step on it matches the oracle (config 4 at 1/1000 scale)."""
+    import ctypes as C
+    from models import hk_model
+    n = 100000
+    fr, to, op = _powerlaw_host(oracle.lib, n)
+    o = vh.create_simulation(hk_model(), backend=oracle)
+    o.add_agents("HKAgent", op.view([("opinion", "f8")]))
+    o.add_edges(fr, to, "Knows")
+    o.finish_init()
+    g = vh.create_simulation(hk_model(), backend=cuda)
+    ne = C.c_uint64()
+    cuda.check(cuda.lib.vbw_hk_powerlaw_build(g.h, 1, 0, C.c_uint64(n), C.c_uint64(4), C.c_uint64(5), C.c_double(6.8333), C.c_uint32(1000000),
+                                              C.c_uint64(30000), C.byref(ne)))
+    g.finish_init()
+    assert ne.value == len(to) == g.num_edges("Knows") == o.num_edges("Knows")
+    goff, gfrom, _ = g.export_csr("Knows", "HKAgent", n)
+    ooff, ofrom, _ = o.export_csr("Knows", "HKAgent", n)
+    assert np.array_equal(goff, ooff) and np.array_equal(gfrom, ofrom)
+    np.testing.assert_array_equal(g.all_agents("HKAgent")["opinion"], op)
+    for _ in range(3):
+        g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        np.testing.assert_allclose(g.all_agents("HKAgent")["opinion"], o.all_agents("HKAgent")["opinion"], rtol=RTOL)
+    assert abs(g.mapreduce("opinion", "+", "HKAgent") - o.mapreduce("opinion", "+", "HKAgent")) < 1e-12 * n

@@ -103,7 +103,7 @@ ABI_SYMBOLS = [
     "vb_cellid", "vb_finish_init", "vb_apply", "vb_has_transition", "vb_load_model_library", "vb_num_agents",
     "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce",
     "vb_rastervalues", "vb_calc_raster_num_edges", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
-    "vb_last_apply_stats",
+    "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes",
 ]
 
 
@@ -136,6 +136,10 @@ class Backend:
         if not self._initialized:
             self.check(self.lib.vb_init(C.c_int(device)))
             self._initialized = True
+
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run all engine work on the given cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self.check(self.lib.vb_set_stream(C.c_void_p(cuda_stream)))
 
 
 _default_backend: Optional[Backend] = None
@@ -387,6 +391,15 @@ class Simulation:
                                         C.c_uint64(n), ids.ctypes.data_as(C.c_void_p)))
         return ids
 
+    def add_agents_device(self, type_name: str, dev_ptr: int, n: int) -> None:
+        """Bulk add from a device buffer of n AoS records (no ids returned: slots first..first+n-1 in order)."""
+        self._ck(self.lib.vb_add_agents(self.h, C.c_int(self._aid[type_name]), C.c_void_p(dev_ptr), C.c_uint64(n), None))
+
+    def add_edges_device(self, edge_name: str, from_ptr: int, to_ptr: int, n: int, states_ptr: int = 0) -> None:
+        """Bulk add from device buffers of AgentIDs (uint64) in call order."""
+        self._ck(self.lib.vb_add_edges(self.h, C.c_int(self._eid[edge_name]), C.c_void_p(from_ptr), C.c_void_p(to_ptr),
+                                       C.c_void_p(states_ptr) if states_ptr else None, C.c_uint64(n)))
+
     def add_agent(self, type_name: str, state=None) -> int:
         dt = self._adt(type_name)
         if dt is None:
@@ -502,8 +515,10 @@ class Simulation:
         a, b = C.c_double(), C.c_double()
         er, ea, ac, kl = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self.lib.vb_last_apply_stats(self.h, C.byref(a), C.byref(b), C.byref(er), C.byref(ea), C.byref(ac), C.byref(kl)))
-        return {"ms_read_write": a.value, "ms_finish": b.value, "edges_read": er.value, "edges_appended": ea.value,
-                "agents_called": ac.value, "kernel_launches": kl.value}
+        k = C.c_double()
+        self._ck(self.lib.vb_last_kernel_ms(self.h, C.byref(k)))
+        return {"ms_read_write": a.value, "ms_finish": b.value, "ms_kernel": k.value, "edges_read": er.value,
+                "edges_appended": ea.value, "agents_called": ac.value, "kernel_launches": kl.value}
 
     # -- agent queries --
     def num_agents(self, type_name: str) -> int:

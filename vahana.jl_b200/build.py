@@ -8,14 +8,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(CSRC, "build")
 OUT = os.path.join(OUT_DIR, "libvahana_b200.so")
-SOURCES = [os.path.join(CSRC, "engine", "engine.cu"), os.path.join(CSRC, "transitions", "builtin.cu")]
+SOURCES = [os.path.join(CSRC, "engine", "engine.cu"), os.path.join(CSRC, "transitions", "builtin.cu"),
+           os.path.join(CSRC, "workloads", "generators.cu")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 
 def _deps():
     deps = list(SOURCES)
-    for root in (os.path.join(CSRC, "engine"), os.path.join(CSRC, "transitions"), os.path.join(HERE, "..", "include")):
+    for root in (os.path.join(CSRC, "engine"), os.path.join(CSRC, "transitions"), os.path.join(CSRC, "workloads"),
+                 os.path.join(HERE, "..", "include")):
         for f in os.listdir(root):
             if f.endswith((".h", ".cuh", ".inc", ".cu")):
                 deps.append(os.path.join(root, f))

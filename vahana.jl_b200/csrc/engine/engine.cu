@@ -251,6 +251,12 @@ __global__ void purge_rows_cnt_kernel(uint32_t* __restrict__ cnt, uint32_t rows,
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < rows && dead[row_base + r]) cnt[r] = 0;
 }
+__global__ void heavy_flags_kernel(const uint32_t* __restrict__ off, uint32_t row0, uint32_t n, uint32_t rows, uint32_t heavy_min, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = row0 + (uint32_t)i;
+    flag[i] = (r < rows && off[r + 1] - off[r] >= heavy_min) ? 1u : 0u;
+}
 __global__ void mark_dead_kernel(const uint32_t* __restrict__ flag, uint32_t n, uint8_t* __restrict__ dead, uint32_t base) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) dead[base + i] = 1;
@@ -453,6 +459,8 @@ struct EdgeStore {
     std::unordered_map<uint64_t, std::pair<uint64_t, std::vector<uint8_t>>> single_seen;
     bool readable = false, writeable = false, add_existing = false;
     int64_t last_change = 0;
+    // degree-binning cache: slots of agent type `heavy_type` whose row has >= HEAVY_MIN entries
+    uint32_t* heavy_rows = nullptr; uint32_t heavy_n = 0; int heavy_type = 0; uint64_t heavy_version = ~0ull; uint64_t version = 0;
     bool has_src() const { return !ignorefrom; }
     bool has_state() const { return !stateless && size > 0; }
 };
@@ -479,7 +487,7 @@ struct vb_sim {
     bool all_immortal = true;
     uint32_t rank = 0;
     uint32_t base[vb::MAX_AGENT_TYPES + 2] = {0};
-    vb::DeviceSim* d_ds = nullptr;
+    vb::DeviceSim h_ds;                       // host copy of the view; passed by value in every transition launch
     uint32_t* d_error = nullptr;
     uint32_t* d_scalars = nullptr;          // small device scratch for totals
     unsigned long long* d_stats = nullptr;
@@ -487,6 +495,8 @@ struct vb_sim {
     double ms_rw = 0, ms_fin = 0;
     uint64_t st_edges_read = 0, st_edges_appended = 0, st_agents_called = 0, st_launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t evk[2] = {nullptr, nullptr};   // around the transition kernels themselves
+    double ms_kernel = 0;
 
     AgentStore& A(int t) { if (t < 1 || t > (int)agents.size()) throw ArgError("unknown agent type id"); return agents[t - 1]; }
     EdgeStore& E(int e) { if (e < 0 || e >= (int)edges.size()) throw ArgError("unknown edge type index"); return edges[e]; }
@@ -518,6 +528,7 @@ void free_agent(AgentStore& a) {
     a.state[0] = a.state[1] = a.died[0] = a.died[1] = nullptr; a.reuse = nullptr;
 }
 void free_edge_read(EdgeStore& e) {
+    ++e.version;
     dfree(e.off); dfree(e.src); dfree(e.st); dfree(e.cnt);
     e.off = e.src = e.cnt = nullptr; e.st = nullptr; e.nnz = e.st_cap = 0; e.rows = 0;
 }
@@ -536,8 +547,9 @@ vb_sim::~vb_sim() {
     for (auto& a : agents) free_agent(a);
     for (auto& e : edges) { free_edge_read(e); free_edge_log(e); free_chunks(e); }
     for (auto& r : rasters) dfree(r.cells);
-    dfree(d_ds); dfree(d_error); dfree(d_scalars); dfree(d_stats);
+    dfree(d_error); dfree(d_scalars); dfree(d_stats);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : evk) if (e) cudaEventDestroy(e);
 }
 
 void vb_sim::compute_bases(uint32_t* out) const {
@@ -653,7 +665,7 @@ void vb_sim::rebase(const uint32_t* old_base) {
 }
 
 void vb_sim::upload_view(uint64_t seed) {
-    static thread_local vb::DeviceSim h;
+    vb::DeviceSim& h = h_ds;
     std::memset(&h, 0, sizeof(h));
     for (size_t t = 1; t <= agents.size(); ++t) {
         const AgentStore& a = agents[t - 1];
@@ -682,8 +694,6 @@ void vb_sim::upload_view(uint64_t seed) {
     h.n_agent_types = (uint32_t)agents.size(); h.n_edge_types = (uint32_t)edges.size(); h.n_rasters = (uint32_t)rasters.size();
     h.rank = rank; h.check = asserts_enabled && check_readable; h.error = d_error; h.seed = seed;
     if (!params.empty()) std::memcpy(h.params, params.data(), params.size());
-    CK(cudaMemcpyAsync(d_ds, &h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
-    CK(cudaStreamSynchronize(g_stream));   // `h` is reused by the next upload
 }
 
 void vb_sim::check_device_error(const char* where) {
@@ -932,7 +942,7 @@ void vb_sim::purge_dead(const uint8_t* dead) {
             pa.nst = e.has_state() ? (uint8_t*)g_pool.alloc((size_t)cap * e.size) : nullptr;
             pa.nstride = cap; pa.word = e.word; pa.ncols = e.ncols;
             purge_copy_kernel<<<nblk(e.rows), 256, 0, g_stream>>>(pa); LAUNCH_CHECK();
-            dfree(e.off); dfree(e.src); dfree(e.st);
+            dfree(e.off); dfree(e.src); dfree(e.st); ++e.version;
             e.off = noff; e.src = pa.nsrc; e.st = pa.nst; e.st_cap = cap; e.nnz = total;
             e.last_change = num_transitions;
             noff = nullptr;
@@ -1083,9 +1093,10 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             }
         }
     }
-    CK(cudaMemsetAsync(s.d_stats, 0, 8, g_stream));
+    CK(cudaMemsetAsync(s.d_stats, 0, 4096 * 8, g_stream));
     CK(cudaEventRecord(s.ev[0], g_stream));
     s.st_agents_called = 0;
+    s.ms_kernel = 0;
     uint64_t appended = 0;
 
     // ---- the transition loop over `call` (Simulation.jl:774-788) ----
@@ -1097,7 +1108,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         if (n == 0) continue;
         s.st_agents_called += n;
         vb::LaunchArgs la{};
-        la.ds = s.d_ds; la.type = C; la.n = n; la.in_read = contains(read, C); la.in_write = contains(write, C);
+        la.ds = &s.h_ds; la.type = C; la.n = n; la.in_read = contains(read, C); la.in_write = contains(write, C);
         la.with_edge = with_edge; la.stats = s.d_stats; la.stream = g_stream;
         const int nw = ti->n_edge_writes + ti->n_agent_writes;
         std::vector<uint32_t*> tmp;
@@ -1132,15 +1143,68 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             }
             s.upload_view(seed);
             la.mode = vb::MODE_EMIT;
+            CK(cudaEventRecord(s.evk[0], g_stream));
             CK(ti->launch(la)); ++g_launches;
+            CK(cudaEventRecord(s.evk[1], g_stream));
             for (int i = 0; i < ti->n_edge_writes; ++i) { EdgeStore& e = s.E(ti->edge_writes[i]); if (e.kind == vb::KIND_CSR) e.log_n += totals[i]; appended += totals[i]; }
             for (int i = 0; i < ti->n_agent_writes; ++i) s.A(ti->agent_writes[i]).births += totals[vb::MAX_EDGE_WRITES + i];
         } else {
-            s.upload_view(seed);
             la.mode = vb::MODE_DIRECT;
+            la.primary_edge = -1; la.heavy_min = 0; la.group = 0; la.rows = nullptr;
+            uint32_t heavy_n = 0; const uint32_t* heavy_rows = nullptr;
+            if (ti->cooperative && ti->primary_edge >= 0 && with_edge < 0) {
+                // degree binning (north_star: sub-warp / warp per agent, block per agent for rows >= 1024 entries)
+                EdgeStore& pe = s.E(ti->primary_edge);
+                if (pe.kind == vb::KIND_CSR && pe.off && (!pe.singletype || pe.target == C)) {
+                    constexpr uint32_t HEAVY_MIN = 1024;
+                    if (pe.heavy_version != pe.version || pe.heavy_type != C) {
+                        dfree(pe.heavy_rows); pe.heavy_rows = nullptr; pe.heavy_n = 0;
+                        uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
+                        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+                        heavy_flags_kernel<<<nblk(n), 256, 0, g_stream>>>(pe.off, pe.singletype ? 0u : s.base[C], n, pe.rows, HEAVY_MIN, flag); LAUNCH_CHECK();
+                        vbp::exclusive_scan(flag, pos, n, s.d_scalars, scr, g_stream); g_launches += 3;
+                        uint32_t hn = 0;
+                        CK(cudaMemcpyAsync(&hn, s.d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+                        CK(cudaStreamSynchronize(g_stream));
+                        if (hn) {
+                            pe.heavy_rows = dalloc<uint32_t>(hn);
+                            vbp::compact_indices_kernel<<<nblk(n), 256, 0, g_stream>>>(flag, pos, n, pe.heavy_rows); LAUNCH_CHECK();
+                        }
+                        pe.heavy_n = hn; pe.heavy_type = C; pe.heavy_version = pe.version;
+                        CK(cudaStreamSynchronize(g_stream));
+                        dfree(flag); dfree(pos); dfree(scr);
+                    }
+                    heavy_n = pe.heavy_n; heavy_rows = pe.heavy_rows;
+                    la.primary_edge = ti->primary_edge; la.heavy_min = HEAVY_MIN;
+                    const double avg = (double)pe.nnz / std::max<uint32_t>(1, n);
+                    la.group = avg < 48.0 ? 8 : 32;
+                }
+            }
+            s.upload_view(seed);
+            // optional experiment: keep the head of the called type's read state resident in L2 (VB_L2_PERSIST_MB)
+            static const int persist_mb = getenv("VB_L2_PERSIST_MB") ? atoi(getenv("VB_L2_PERSIST_MB")) : 0;
+            if (persist_mb > 0 && a.size) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20);
+                cudaStreamAttrValue av{};
+                av.accessPolicyWindow.base_ptr = a.rstate();
+                av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)a.cap * a.size, (size_t)persist_mb << 20);
+                av.accessPolicyWindow.hitRatio = 1.0f;
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(g_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+                cudaGetLastError();
+            }
+            CK(cudaEventRecord(s.evk[0], g_stream));
             CK(ti->launch(la)); ++g_launches;
+            if (heavy_n) {
+                vb::LaunchArgs lh = la;
+                lh.group = 256; lh.rows = heavy_rows; lh.n = heavy_n; lh.heavy_min = 0;
+                CK(ti->launch(lh)); ++g_launches;
+            }
+            CK(cudaEventRecord(s.evk[1], g_stream));
         }
         CK(cudaStreamSynchronize(g_stream));
+        { float mk = 0; cudaEventElapsedTime(&mk, s.evk[0], s.evk[1]); s.ms_kernel += mk; }
         for (auto p : tmp) dfree(p);
     }
     CK(cudaEventRecord(s.ev[1], g_stream));
@@ -1176,7 +1240,12 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     cudaEventElapsedTime(&m1, s.ev[1], s.ev[2]);
     s.ms_rw = m0; s.ms_fin = m1;
     unsigned long long er = 0;
-    CK(cudaMemcpy(&er, s.d_stats, 8, cudaMemcpyDeviceToHost));
+    {
+        static thread_local std::vector<unsigned long long> hs(4096);
+        CK(cudaMemcpyAsync(hs.data(), s.d_stats, 4096 * 8, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        for (int i = 0; i < 1024; ++i) er += hs[(size_t)i * 4];
+    }
     s.st_edges_read = er; s.st_edges_appended = appended; s.st_launches = g_launches - launches0;
     s.num_transitions += 1;
 }
@@ -1212,6 +1281,13 @@ int vb_shutdown(void) {
         cudaStreamDestroy(g_stream);
         g_stream = nullptr;
         g_device = -1;
+    });
+}
+int vb_set_stream(void* stream) {   // run all engine work on the caller's stream (e.g. torch's current stream)
+    return guard([&] {
+        require_device();
+        CK(cudaStreamSynchronize(g_stream));
+        g_stream = (cudaStream_t)stream;
     });
 }
 int vb_comm_unique_id(uint8_t id_out[128]) { std::memset(id_out, 0, 128); return VB_OK; }
@@ -1253,13 +1329,13 @@ int vb_sim_create(const vb_model_desc* m, const void* params, vb_sim** out) {
             s->edges.push_back(std::move(e));
         }
         if (m->param_size) s->params.assign((const uint8_t*)params, (const uint8_t*)params + m->param_size);
-        s->d_ds = (vb::DeviceSim*)g_pool.alloc(sizeof(vb::DeviceSim));
         s->d_error = dalloc<uint32_t>(1);
         s->d_scalars = dalloc<uint32_t>(64);
-        s->d_stats = dalloc<unsigned long long>(4);
+        s->d_stats = dalloc<unsigned long long>(4096);
         CK(cudaMemsetAsync(s->d_error, 0, 4, g_stream));
-        CK(cudaMemsetAsync(s->d_stats, 0, 32, g_stream));
+        CK(cudaMemsetAsync(s->d_stats, 0, 4096 * 8, g_stream));
         for (auto& e : s->ev) CK(cudaEventCreate(&e));
+        for (auto& e : s->evk) CK(cudaEventCreate(&e));
         s->compute_bases(s->base);
         *out = s.release();
     });
@@ -1302,12 +1378,12 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
             s->edges.push_back(std::move(f));
         }
         for (auto& r : o.rasters) { RasterStore q = r; q.cells = (uint32_t*)dup(r.cells, r.ids.size() * 4); s->rasters.push_back(q); }
-        s->d_ds = (vb::DeviceSim*)g_pool.alloc(sizeof(vb::DeviceSim));
         s->d_error = dalloc<uint32_t>(1);
         s->d_scalars = dalloc<uint32_t>(64);
-        s->d_stats = dalloc<unsigned long long>(4);
+        s->d_stats = dalloc<unsigned long long>(4096);
         CK(cudaMemsetAsync(s->d_error, 0, 4, g_stream));
         for (auto& e : s->ev) CK(cudaEventCreate(&e));
+        for (auto& e : s->evk) CK(cudaEventCreate(&e));
         CK(cudaStreamSynchronize(g_stream));
         *out = s.release();
     });
@@ -1334,14 +1410,17 @@ int vb_add_agents(vb_sim* s, int type, const void* states, uint64_t n, vb_agent_
         const uint64_t first = a.nextid;   // init phase: no reuse (nothing has died yet)
         s->ensure_agent_cap(type, first - 1 + n);
         if (a.size) {
-            uint8_t* tmp = (uint8_t*)g_pool.alloc(n * a.size);
-            CK(cudaMemcpyAsync(tmp, states, n * a.size, cudaMemcpyHostToDevice, g_stream));
+            cudaPointerAttributes pa{};
+            const bool dev = cudaPointerGetAttributes(&pa, states) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+            cudaGetLastError();
+            uint8_t* tmp = dev ? (uint8_t*)states : (uint8_t*)g_pool.alloc(n * a.size);
+            if (!dev) CK(cudaMemcpyAsync(tmp, states, n * a.size, cudaMemcpyHostToDevice, g_stream));
             vbp::aos_to_soa_kernel<<<nblk(n * a.ncols), 256, 0, g_stream>>>(tmp, a.wstate(), a.cap, first - 1, n, a.size, a.word); LAUNCH_CHECK();
             CK(cudaStreamSynchronize(g_stream));
-            dfree(tmp);
+            if (!dev) dfree(tmp);
         }
         a.nextid += n;
-        for (uint64_t i = 0; i < n && ids_out; ++i) ids_out[i] = vb::agent_id((uint32_t)type, s->rank, first + i);
+        for (uint64_t i = 0; i < n && ids_out; ++i) ids_out[i] = vb::agent_id((uint32_t)type, s->rank, first + i);   // ids_out may be NULL for bulk adds
     });
 }
 
@@ -1919,5 +1998,7 @@ int vb_last_apply_stats(vb_sim* s, double* ms_rw, double* ms_fin, uint64_t* er, 
     if (er) *er = s->st_edges_read; if (ea) *ea = s->st_edges_appended; if (ac) *ac = s->st_agents_called; if (kl) *kl = s->st_launches;
     return VB_OK;
 }
+int vb_last_kernel_ms(vb_sim* s, double* ms) { *ms = s->ms_kernel; return VB_OK; }
+uint64_t vb_device_view_bytes(void) { return sizeof(vb::DeviceSim); }   // host->device bytes uploaded per transition launch
 
 }  // extern "C"

@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t& total)
     return woff + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ bsum) {
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ bsum) {
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
     uint32_t s = 0;
 #pragma unroll
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_
     if (threadIdx.x == 0) bsum[blockIdx.x] = total;
 }
 // in-place exclusive scan of up to SCAN_TILE values by one block; writes the grand total to *total (if non-null)
-__global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ total_out) {
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ total_out) {
     uint32_t v[SCAN_ITEMS], s = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(uint32_t* __r
     }
     if (total_out && threadIdx.x == 0) *total_out = total;
 }
-__global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n,
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n,
                                                                     const uint32_t* __restrict__ boff) {
     // thread t owns items [t*ITEMS, t*ITEMS+ITEMS) of the tile (blocked), so the per-thread scan is sequential
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep_kernel(const uint
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
 }
-__global__ void scan_total_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ out, uint64_t n, uint32_t* total) {
+static __global__ void scan_total_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ out, uint64_t n, uint32_t* total) {
     *total = n ? out[n - 1] + in[n - 1] : 0;
 }
 
@@ -118,7 +118,7 @@ constexpr int RS_ITEMS = 16;                         // keys per thread
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 4096 keys per block
 constexpr int RS_SEG = RS_TILE / RS_WARPS;           // contiguous keys per warp
 
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t* __restrict__ hist,
+static __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t* __restrict__ hist,
                                                            uint32_t nblocks) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
@@ -143,7 +143,7 @@ struct RsArgs {
 struct NoPayload { uint8_t x; };
 
 template <class P1, class P2, bool HAS1, bool HAS2>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const RsArgs<P1, P2> a) {
+static __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const RsArgs<P1, P2> a) {
     __shared__ uint32_t wh[RS_WARPS][256];
     __shared__ uint32_t dstart[256];
     __shared__ uint32_t gbase[256];
@@ -287,30 +287,30 @@ inline int radix_sort(uint32_t* k0, uint32_t* k1, uint32_t* p10, uint32_t* p11, 
 // ---- CSR row counts from sorted row keys: cnt[r] += (#entries with key r).  Two atomics per non-empty row
 //      (run start subtracts its index, run end adds index+1), no per-entry atomics; an exclusive scan of cnt
 //      gives the offsets.  cnt must be zero (or hold the counts of an existing CSR being merged). ------------
-__global__ void csr_run_counts_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ cnt) {
+static __global__ void csr_run_counts_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ cnt) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t k = keys[i];
     if (i == 0 || keys[i - 1] != k) atomicSub(&cnt[k], (uint32_t)i);
     if (i == n - 1 || keys[i + 1] != k) atomicAdd(&cnt[k], (uint32_t)i + 1u);
 }
-__global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
+static __global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-__global__ void iota_u32_kernel(uint32_t* p, uint64_t n) {
+static __global__ void iota_u32_kernel(uint32_t* p, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = (uint32_t)i;
 }
 // row lengths -> counts (for merging an existing CSR with newly sorted edges)
-__global__ void row_counts_kernel(const uint32_t* __restrict__ off, uint32_t rows, uint32_t* __restrict__ cnt) {
+static __global__ void row_counts_kernel(const uint32_t* __restrict__ off, uint32_t rows, uint32_t* __restrict__ cnt) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < rows) cnt[r] = off[r + 1] - off[r];
 }
 
 // ---- AoS (host records) <-> SoA word columns ------------------------------------------------------------------
 // dst column c of record slot0+i at cols + c*stride*word + (slot0+i)*word
-__global__ void aos_to_soa_kernel(const uint8_t* __restrict__ aos, uint8_t* __restrict__ cols, uint64_t stride, uint64_t slot0, uint64_t n,
+static __global__ void aos_to_soa_kernel(const uint8_t* __restrict__ aos, uint8_t* __restrict__ cols, uint64_t stride, uint64_t slot0, uint64_t n,
                                   uint32_t size, uint32_t word) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ncols = size / word;
@@ -321,7 +321,7 @@ __global__ void aos_to_soa_kernel(const uint8_t* __restrict__ aos, uint8_t* __re
     uint8_t* d = cols + (uint64_t)c * stride * word + (slot0 + i) * word;
     for (uint32_t b = 0; b < word; ++b) d[b] = s[b];
 }
-__global__ void soa_to_aos_kernel(const uint8_t* __restrict__ cols, uint8_t* __restrict__ aos, uint64_t stride, uint64_t slot0, uint64_t n,
+static __global__ void soa_to_aos_kernel(const uint8_t* __restrict__ cols, uint8_t* __restrict__ aos, uint64_t stride, uint64_t slot0, uint64_t n,
                                   uint32_t size, uint32_t word) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ncols = size / word;
@@ -333,7 +333,7 @@ __global__ void soa_to_aos_kernel(const uint8_t* __restrict__ cols, uint8_t* __r
     for (uint32_t b = 0; b < word; ++b) d[b] = s[b];
 }
 // gather records through an index list (compacted read-out): aos[i] = record idx[i]
-__global__ void soa_gather_aos_kernel(const uint8_t* __restrict__ cols, uint8_t* __restrict__ aos, uint64_t stride, const uint32_t* __restrict__ idx,
+static __global__ void soa_gather_aos_kernel(const uint8_t* __restrict__ cols, uint8_t* __restrict__ aos, uint64_t stride, const uint32_t* __restrict__ idx,
                                       uint64_t n, uint32_t size, uint32_t word) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ncols = size / word;
@@ -345,7 +345,7 @@ __global__ void soa_gather_aos_kernel(const uint8_t* __restrict__ cols, uint8_t*
     for (uint32_t b = 0; b < word; ++b) d[b] = s[b];
 }
 // column-wise copy between two SoA buffers with different strides (capacity growth, log -> CSR moves)
-__global__ void soa_copy_kernel(const uint8_t* __restrict__ src, uint64_t sstride, uint8_t* __restrict__ dst, uint64_t dstride, uint64_t n,
+static __global__ void soa_copy_kernel(const uint8_t* __restrict__ src, uint64_t sstride, uint8_t* __restrict__ dst, uint64_t dstride, uint64_t n,
                                 uint32_t ncols, uint32_t word, uint64_t soff, uint64_t doff) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t per = n * word;
@@ -357,15 +357,15 @@ __global__ void soa_copy_kernel(const uint8_t* __restrict__ src, uint64_t sstrid
 
 // ---- flags -> ordered index list (newly died slots appended to the reuse stack in ascending order) ------------
 // flag[i] = died_w[i] && !died_r[i] for i < n_r (slots beyond the read length cannot die this step)
-__global__ void newly_died_flags_kernel(const uint8_t* __restrict__ died_r, const uint8_t* __restrict__ died_w, uint32_t n, uint32_t* __restrict__ flag) {
+static __global__ void newly_died_flags_kernel(const uint8_t* __restrict__ died_r, const uint8_t* __restrict__ died_w, uint32_t n, uint32_t* __restrict__ flag) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = (died_w[i] && !died_r[i]) ? 1u : 0u;
 }
-__global__ void alive_flags_kernel(const uint8_t* __restrict__ died, uint32_t n, uint32_t* __restrict__ flag) {
+static __global__ void alive_flags_kernel(const uint8_t* __restrict__ died, uint32_t n, uint32_t* __restrict__ flag) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = died ? (died[i] ? 0u : 1u) : 1u;
 }
-__global__ void compact_indices_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t n, uint32_t* __restrict__ out) {
+static __global__ void compact_indices_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint32_t n, uint32_t* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) out[pos[i]] = (uint32_t)i;
 }

@@ -21,6 +21,7 @@ enum : int { E_KNOWS = 0 };             // edge types in registration order (str
 struct Step : vb::TransitionBase {
     using State = HKAgent;
     static constexpr bool kCooperative = true;
+    static constexpr int kPrimaryEdge = E_KNOWS;
     template <class Ctx>
     VB_HD bool operator()(Ctx& ctx, HKAgent& self, vb::AgentID id) const {
         const double eps = ctx.template param<Params>().eps;
