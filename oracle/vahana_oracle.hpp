@@ -227,7 +227,11 @@ inline std::unique_ptr<Sim> create_sim(const std::string& name, const std::vecto
         if (f.singletype && f.singleedge && !(f.stateless && f.ignorefrom))
             throw AssertionError(":SingleEdge and :SingleType can only be combined with :Stateless and :IgnoreFrom");
         f.read = std::make_shared<EdgeContainer>();
-        f.write = f.read;   // before init everything goes to `write`; read aliases it after finish_write!
+        f.write = std::make_shared<EdgeContainer>();   // before init everything goes to `write`; read aliases it after finish_write!
+        if (f.singletype && d.size_hint) {   // init_field! after construction (EdgeMethods.jl:198-239, Simulation.jl create_simulation)
+            f.write->vec.resize(d.size_hint);
+            f.write->assigned.assign(d.size_hint, f.bits_container() ? 1 : 0);
+        }
         s->edges.push_back(std::move(f));
     }
     if (psize) s->params.assign((const uint8_t*)params, (const uint8_t*)params + psize);
@@ -944,12 +948,13 @@ inline std::unique_ptr<Sim> copy_sim(const Sim& s) {   // copy_simulation: Simul
 #define VO_CAT2(a, b) a##b
 #define VO_CAT(a, b) VO_CAT2(a, b)
 // Registers Functor (a single-source transition from vahana.jl_b200/csrc/transitions) with the oracle.
-#define VO_REGISTER_TRANSITION(tname, agenttype_name, Functor)                                                 \
+#define VO_REGISTER_TRANSITION(tname, agenttype_name, ...)                                                     \
     static const bool VO_CAT(vo_reg_, __COUNTER__) = [] {                                                      \
         vo::Registry::get().fns[{tname, agenttype_name}] = [](vo::Ctx& ctx, void* st, vb::AgentID id) -> bool { \
-            typename Functor::State local;                                                                     \
+            using VoFunctor = __VA_ARGS__;                                                                     \
+            typename VoFunctor::State local;                                                                   \
             std::memcpy((void*)&local, st, sizeof(local));                                                     \
-            bool alive = Functor()(ctx, local, id);                                                            \
+            bool alive = VoFunctor()(ctx, local, id);                                                          \
             std::memcpy(st, (void*)&local, sizeof(local));                                                     \
             return alive;                                                                                      \
         };                                                                                                     \

@@ -73,3 +73,92 @@ def ba_graph(n, m, seed):
     import networkx as nx
     g = nx.barabasi_albert_graph(n, m, seed=seed)
     return np.array(list(g.edges()), dtype=np.int64)
+
+
+# ---- test/edges.jl:13-63 ----
+EDGE_TYPES = ["EdgeD", "EdgeS", "EdgeE", "EdgeT", "EdgeI", "EdgeSE", "EdgeST", "EdgeSI", "EdgeEI", "EdgeTI", "EdgeSEI", "EdgeSTI",
+              "EdgeSETI", "EdgeTs", "EdgeTsI", "EdgeSTs", "EdgeSTsI", "EdgeSETsI"]
+STATELESS_EDGE_TYPES = ["EdgeS", "EdgeSE", "EdgeST", "EdgeSI", "EdgeSEI", "EdgeSTI", "EdgeSETI", "EdgeSTs", "EdgeSTsI", "EdgeSETsI"]
+STATEFUL_EDGE_TYPES = ["EdgeD", "EdgeE", "EdgeT", "EdgeI", "EdgeEI", "EdgeTI", "EdgeTs", "EdgeTsI"]
+
+
+def hashint(name, hint):
+    return hint in name[4:]
+
+
+def edges_model():
+    t = vh.ModelTypes()
+    t.register_agenttype("Agent", FOO)
+    t.register_agenttype("AgentB", FOO)
+    hintmap = {"S": "Stateless", "E": "SingleEdge", "T": "SingleType", "I": "IgnoreFrom"}
+    for name in EDGE_TYPES:
+        code = name[4:]
+        hints = [hintmap[c] for c in code if c in hintmap]
+        kw = {}
+        if "T" in code:
+            kw["target"] = "Agent"
+        if "s" in code:
+            kw["size"] = 10
+        t.register_edgetype(name, None if "S" in code else FOO, *hints, **kw)
+    return vh.create_model(t, "Test Edges")
+
+
+def remove_agents_model():
+    """test/remove_agents.jl:13-20"""
+    t = vh.ModelTypes()
+    t.register_agenttype("DAgent", [("idx", "i8")])
+    t.register_agenttype("DAgentRemove")
+    t.register_edgetype("DEdge")
+    t.register_edgetype("DEdgeState", [("state", "i8")])
+    t.register_edgetype("DSingleEdge", None, "SingleEdge")
+    t.register_edgetype("DEdgeST", None, "SingleType", target="DAgent")
+    return vh.create_model(t, "remove_agents")
+
+
+def addexisting_model(compute_hints=(), constructed_hints=()):
+    """test/addexisting.jl:88-110 (detect_stateless(true) is active in that file)"""
+    old = vh.config.detect_stateless
+    vh.detect_stateless(True)
+    try:
+        t = vh.ModelTypes()
+        t.register_agenttype("ComputeAgent", None, *compute_hints)
+        t.register_agenttype("ConstructedAgent", None, *constructed_hints)
+        t.register_edgetype("Connection")
+    finally:
+        vh.detect_stateless(old)
+    return vh.create_model(t, "Test add_existing")
+
+
+def independent_model():
+    """test/independent.jl:24-30"""
+    t = vh.ModelTypes()
+    t.register_agenttype("AIndependent", FOO, "Independent")
+    t.register_agenttype("ANotIndependent", FOO)
+    t.register_agenttype("AIndependentImmortal", FOO, "Independent")
+    t.register_edgetype("AFooEdge", FOO)
+    t.register_edgetype("AEdge")
+    return vh.create_model(t, "Test Independent")
+
+
+def graph_model():
+    """test/graphs.jl:11-14"""
+    t = vh.ModelTypes()
+    t.register_agenttype("GraphA", [("id", "i8"), ("sum_ids_neighbors", "i8")])
+    t.register_edgetype("GraphE")
+    return vh.create_model(t, "Test Graph")
+
+
+GRIDA = [("pos", "i8", (2,)), ("active", "?")]
+GRID3D = [("pos", "i8", (3,)), ("active", "?")]
+
+
+def raster_model():
+    """test/raster.jl:22-29"""
+    t = vh.ModelTypes()
+    t.register_agenttype("GridA", GRIDA)
+    t.register_agenttype("Grid3D", GRID3D)
+    t.register_edgetype("GridE")
+    t.register_agenttype("Position", [("ids_sum", "i8")])
+    t.register_agenttype("MovingAgent", [("value", "i8")])
+    t.register_edgetype("OnPosition")
+    return vh.create_model(t, "Raster_Test")

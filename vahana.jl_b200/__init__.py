@@ -692,7 +692,19 @@ class Simulation:
         dims = self.raster_info(name)
         dt = self._adt(type_name)
         fdt, off = dt.fields[field][0], dt.fields[field][1]
-        out = np.zeros(int(np.prod(dims)), dtype=fdt)
+        n = int(np.prod(dims))
+        if fdt.subdtype is not None:   # tuple-valued field (e.g. pos::Tuple{Int64,Int64}): one pass per component
+            base, shape = fdt.subdtype
+            k = int(np.prod(shape))
+            out = np.zeros((n, k), dtype=base)
+            for j in range(k):
+                col = np.zeros(n, dtype=base)
+                self._ck(self.lib.vb_rastervalues(self.h, name.encode(), C.c_int(off + j * base.itemsize), C.c_int(_DT[base]),
+                                                  col.ctypes.data_as(C.c_void_p)))
+                out[:, j] = col
+            return out.reshape(dims + tuple(shape), order="F") if len(shape) == 0 else \
+                np.stack([out[:, j].reshape(dims, order="F") for j in range(k)], axis=-1)
+        out = np.zeros(n, dtype=fdt)
         self._ck(self.lib.vb_rastervalues(self.h, name.encode(), C.c_int(off), C.c_int(_DT[fdt]), out.ctypes.data_as(C.c_void_p)))
         return out.reshape(dims, order="F")
 

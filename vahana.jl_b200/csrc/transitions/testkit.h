@@ -92,4 +92,110 @@ template <int E, bool kStateful> struct AddSelfLoop : vb::TransitionBase {
     }
 };
 
+// has_edge(sim, id, t) inside a closure: the read-permission check of test/edges.jl:268-272
+template <int E> struct TouchEdge : vb::TransitionBase {
+    using State = Foo;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const { (void)ctx.has_edge(E, id); return true; }
+};
+
+// ---- test/remove_agents.jl ----
+struct Empty {};
+struct Idx { int64_t idx; };
+// num_edges(sim, id, E) == 0 ? nothing : state   (test/remove_agents.jl:52-58)
+template <int E> struct DieIfNoEdges : vb::TransitionBase {
+    using State = Idx;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Idx&, vb::AgentID id) const { return ctx.num_edges(E, id) != 0; }
+};
+
+// ---- test/addexisting.jl: ComputeAgent = 1, ConstructedAgent = 2, Connection = 0 ----
+struct ConstructAndConnect : vb::TransitionBase {   // :47-50
+    using State = Empty;
+    using EdgeWrites = vb::IntList<0>;
+    using AgentWrites = vb::IntList<2>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Empty&, vb::AgentID id) const {
+        const vb::AgentID c = ctx.add_agent(2, Empty{});
+        ctx.add_edge(0, c, id);
+        return true;
+    }
+};
+
+// ---- test/independent.jl: agent types 1..3 (Foo), AFooEdge = 0 {foo}, AEdge = 1 ----
+template <int K> struct IndepStep : vb::TransitionBase {   // :63-75, :113-125
+    using State = Foo;
+    using EdgeWrites = vb::IntList<0>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& s, vb::AgentID id) const {
+        if (s.foo == K) return false;
+        const EFoo st{s.foo};
+        ctx.for_each_neighbor(1, id, [&](vb::AgentID nid) {
+            ctx.add_edge(0, nid, id, st);
+            ctx.add_edge(0, id, nid, st);
+        });
+        return true;
+    }
+};
+template <int T> struct IndepSpawn : vb::TransitionBase {   // :164-176
+    using State = Foo;
+    using EdgeWrites = vb::IntList<0>;
+    using AgentWrites = vb::IntList<T>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& s, vb::AgentID id) const {
+        vb::AgentID nid = ctx.add_agent(T, Foo{s.foo + 10});
+        ctx.add_edge(0, nid, id, EFoo{(int64_t)nid});
+        ctx.add_edge(0, id, nid, EFoo{(int64_t)nid});
+        nid = ctx.add_agent(T, Foo{s.foo + 20});
+        ctx.add_edge(0, nid, id, EFoo{(int64_t)nid});
+        ctx.add_edge(0, id, nid, EFoo{(int64_t)nid});
+        return true;
+    }
+};
+
+// ---- test/graphs.jl: GraphA = 1 {id, sum_ids_neighbors}, GraphE = 0 ----
+struct GraphA { int64_t id; int64_t sum_ids_neighbors; };
+struct SumIds : vb::TransitionBase {   // :19-23
+    using State = GraphA;
+    static constexpr bool kCooperative = true;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, GraphA& a, vb::AgentID id) const {
+        int64_t s = 0;
+        ctx.for_each_neighbor(0, id, [&](vb::AgentID from) { s += ctx.template agentfield<int64_t>((int)vb::type_nr(from), from, 0); });
+        a.sum_ids_neighbors = ctx.sum(s);
+        return true;
+    }
+};
+
+// ---- test/raster.jl: GridA = 1, Grid3D = 2, Position = 3, MovingAgent = 4; GridE = 0, OnPosition = 1 ----
+struct GridA { int64_t pos[2]; bool active; };
+struct Grid3D { int64_t pos[3]; bool active; };
+struct Position { int64_t ids_sum; };
+struct MovingAgent { int64_t value; };
+// a.active || any(neighbour.active)   (:25-28, :107-110)
+template <class G, int T> struct Diffuse : vb::TransitionBase {
+    using State = G;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, G& a, vb::AgentID id) const {
+        bool any = a.active;
+        ctx.template for_each_neighborstate<G>(0, T, id, [&](const G& n) { any = any || n.active; });
+        a.active = any;
+        return true;
+    }
+};
+struct SumOnPos : vb::TransitionBase {   // :243-250 (Val{Position} form)
+    using State = Position;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Position& p, vb::AgentID id) const {
+        int64_t s = 0;
+        ctx.for_each_neighbor(1, id, [&](vb::AgentID from) { s += ctx.template agentfield<int64_t>((int)vb::type_nr(from), from, 0); });
+        p.ids_sum = s;
+        return true;
+    }
+};
+struct ValueOnPos : vb::TransitionBase {   // :251-255 (Val{MovingAgent} form)
+    using State = MovingAgent;
+    using EdgeWrites = vb::IntList<1>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, MovingAgent& m, vb::AgentID id) const {
+        const vb::AgentID first = ctx.neighbor_at(1, id, 0);
+        const int64_t value = ctx.template agentfield<int64_t>((int)vb::type_nr(first), first, 0);
+        vb::Pos p{{value, value, 0, 0}};
+        ctx.move_to(0, id, p, 1, 1);
+        m.value = value;
+        return true;
+    }
+};
+
 }  // namespace testkit
