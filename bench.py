@@ -146,21 +146,25 @@ def run_engine(args):
     be = vh.default_backend()
     be.init(local)
     be.set_stream(torch.cuda.current_stream().cuda_stream)
+    be.init_distributed(rank, world)       # the engine's own NCCL communicator (halo exchange, collective folds)
     lib = be.lib
     lib.vb_device_view_bytes.restype = C.c_uint64
 
-    # ---- build the workload on device (per rank: the same graph is built by every rank when world > 1:
-    #      replicas until the sharded halo path lands; see DESIGN.md "multi-GPU") ----
+    # ---- build the workload on device: rank r owns block r of the contiguous equal partition of the agents
+    #      (= :EqualAgentNumbers, src/Simulation.jl:353-367) and every edge whose target it owns ----
     n = int(args.agents)
     t_build = time.perf_counter()
     sim = vh.create_simulation(hk_model(), params={"eps": EPS}, backend=be, device=local)
     ne = C.c_uint64()
-    be.check(lib.vbw_hk_powerlaw_build(sim.h, 1, 0, C.c_uint64(n), C.c_uint64(SEED_GRAPH), C.c_uint64(SEED_OPINION), C.c_double(C_PARETO),
-                                       C.c_uint32(DMAX), C.c_uint64(1 << 22), C.byref(ne)))
+    be.check(lib.vbw_hk_powerlaw_build_sharded(sim.h, 1, 0, C.c_uint64(n), C.c_uint64(SEED_GRAPH), C.c_uint64(SEED_OPINION), C.c_double(C_PARETO),
+                                               C.c_uint32(DMAX), C.c_uint64(1 << 22), C.c_uint32(rank), C.c_uint32(world), C.byref(ne)))
     sim.finish_init()
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
-    E = int(ne.value)
+    E_local = int(ne.value)
+    E = sim.num_edges("Knows")             # summed over ranks
+    bounds = vh.equal_partition(n, world)
+    n_local = bounds[rank + 1] - bounds[rank]
 
     def step():
         sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
@@ -204,14 +208,18 @@ def run_engine(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     view_bytes = int(lib.vb_device_view_bytes())
+    hb = C.c_uint64()
+    lib.vb_halo_bytes(sim.h, C.byref(hb))
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
-    assert edges_read == E * args.steps, (edges_read, E)
+    assert edges_read == E_local * args.steps, (edges_read, E_local)
     peak, peak_src = measured_peaks()
     # algorithmic bytes of the read+write phase: 12 B/edge (4 B column + 8 B source state) +
     # 20 B/agent (4 B row offset + 8 B own state + 8 B new state)
-    alg_bytes = 12.0 * E + 20.0 * n
+    alg_bytes = 12.0 * E_local + 20.0 * n_local
     k_ms = kernel_ms / args.steps
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
@@ -220,15 +228,16 @@ def run_engine(args):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     cpu_eps, cpu_ms, cpu_ne = time_oracle(vh, args.cpu_agents, 3, 1) if not args.no_cpu else (None, None, None)
-    value = E * args.steps * world / (ms_total * 1e-3) if world == 1 else E * args.steps * world / (ms_total * 1e-3)
+    value = E * args.steps / (ms_total * 1e-3)
     line = {
         "metric": "edges/sec per apply! (Hegselmann-Krause read+write phase)", "value": value, "unit": "edges/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "hk-powerlaw-100M (BASELINE config 4)", "agents": n, "edges": E, "eps": EPS,
-                   "parallelism": f"{world} GPU" + (" (independent replicas of the full graph)" if world > 1 else ""),
+                   "parallelism": f"{world} GPU, contiguous equal blocks of agents, edges on the target's rank, NCCL halo of source states",
+                   "halo_bytes_per_step_rank0": int(hb.value),
                    "l2": "inputs larger than L2 (source states 0.8 GB, CSR columns %.1f GB); no flush needed" % (4.0 * E / 1e9),
-                   "agent_updates_per_s": n * args.steps * world / (ms_total * 1e-3), "build_s": t_build, "opinion_sum": metric},
+                   "agent_updates_per_s": n * args.steps / (ms_total * 1e-3), "build_s": t_build, "opinion_sum": metric},
         "roofline": {"bound": "hbm", "kernel": "transition_kernel<hk::Step, DIRECT, warp-per-agent>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "frac_of_8TBs_spec": achieved / 8000.0},

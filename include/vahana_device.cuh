@@ -46,7 +46,7 @@ enum Mode : int { MODE_DIRECT = 0, MODE_COUNT = 1, MODE_EMIT = 2 };
 enum DevError : uint32_t {
     DERR_EDGE_NOT_READABLE = 1, DERR_AGENT_NOT_READABLE = 2, DERR_AGENT_TYPE_MISMATCH = 4, DERR_AGENT_DIED = 8,
     DERR_IMMORTAL_DIED = 16, DERR_ACCESSOR_UNAVAILABLE = 32, DERR_BAD_ID = 64, DERR_EDGE_NOT_DECLARED = 128,
-    DERR_SINGLETYPE_MISMATCH = 256, DERR_RASTER_POS = 512, DERR_INDEX = 1024
+    DERR_SINGLETYPE_MISMATCH = 256, DERR_RASTER_POS = 512, DERR_INDEX = 1024, DERR_REMOTE = 2048
 };
 
 // ---- device views of the simulation state (filled by the engine, read by every kernel) -----------
@@ -59,7 +59,10 @@ struct AgentView {
     uint8_t* died_r;          // 1 B per slot, nullptr for :Immortal
     uint8_t* died_w;
     const uint32_t* reuse;    // read.reuseable (slots, 0-based), LIFO: pop from the end
-    uint32_t cap;             // allocated slots
+    uint32_t cap;             // column stride of the state buffers = local capacity + ghost capacity
+    uint32_t lcap;            // local capacity: slots [0, lcap) are this rank's agents, [lcap, lcap + nghost) are ghosts
+    uint32_t nghost;          // remote agents (other ranks) whose state is mirrored here by the halo exchange
+    const uint64_t* ghost_ids;// AgentIDs of the ghosts, ascending (rank-major): ghost slot = lcap + position
     uint32_t nslots_r;        // length(read.state)
     uint32_t n_reuse;         // entries of `reuse` still available to this call (after earlier pops)
     uint32_t next0;           // first never-used slot (= nextid - 1) before this call's births
@@ -267,28 +270,46 @@ class Ctx {
     template <class T> __device__ __forceinline__ T min(T v) const { return reduce(v, OpMin()); }
 
     // -- id <-> composite --
+    // slot of a remote agent in the ghost segment of its type (binary search in the sorted ghost table)
+    __device__ __forceinline__ bool ghost_slot(const AgentView& av, AgentID id, uint32_t& slot) const {
+        uint32_t lo = 0, hi = av.nghost;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (av.ghost_ids[mid] < id) lo = mid + 1; else hi = mid; }
+        if (lo >= av.nghost || av.ghost_ids[lo] != id) return false;
+        slot = av.lcap + lo;
+        return true;
+    }
     __device__ __forceinline__ bool comp_of(AgentID id, uint32_t& comp) const {
         const uint32_t t = type_nr(id);
         const uint64_t nr = agent_nr(id);
-        if (t < 1 || t > ds.n_agent_types || nr < 1 || nr > ds.agents[t].cap) return false;
+        if (t < 1 || t > ds.n_agent_types || nr < 1) return false;
+        if (process_nr(id) != ds.rank) {
+            uint32_t s;
+            if (!ghost_slot(ds.agents[t], id, s)) return false;
+            comp = ds.base[t] + s;
+            return true;
+        }
+        if (nr > ds.agents[t].lcap) return false;
         comp = ds.base[t] + (uint32_t)(nr - 1);
         return true;
     }
     __device__ __forceinline__ AgentID id_of(uint32_t comp) const {
         uint32_t t = 1;
         while (t < ds.n_agent_types && comp >= ds.base[t + 1]) ++t;
-        return agent_id(t, ds.rank, (uint64_t)(comp - ds.base[t]) + 1);
+        const uint32_t slot = comp - ds.base[t];
+        if (slot >= ds.agents[t].lcap) return ds.agents[t].ghost_ids[slot - ds.agents[t].lcap];
+        return agent_id(t, ds.rank, (uint64_t)slot + 1);
     }
     // row of target `id` in the read container of edge type e; false = no container entry
     __device__ __forceinline__ bool row_of(const EdgeView& ev, AgentID id, uint32_t& row) const {
         const uint32_t t = type_nr(id);
         const uint64_t nr = agent_nr(id);
         if (t < 1 || t > ds.n_agent_types || nr < 1) { fail(DERR_BAD_ID); return false; }
+        if (process_nr(id) != ds.rank) { fail(DERR_REMOTE); return false; }   // edges live on the rank of their target
         if (ev.target) {
             if ((int)t != ev.target) { if (ds.check) fail(DERR_SINGLETYPE_MISMATCH); return false; }
             row = (uint32_t)(nr - 1);
         } else {
-            if (nr > ds.agents[t].cap) return false;
+            if (nr > ds.agents[t].lcap) return false;
             row = ds.base[t] + (uint32_t)(nr - 1);
         }
         return row < ev.rows;
@@ -357,6 +378,10 @@ class Ctx {
             if (!av.readable) fail(DERR_AGENT_NOT_READABLE);                                   // :96-101
         }
         const uint64_t nr = agent_nr(id);
+        if (process_nr(id) != ds.rank) {                                                        // other rank: mirrored ghost state
+            if (!ghost_slot(av, id, s)) { fail(DERR_BAD_ID); return false; }
+            return true;
+        }
         if (nr < 1 || nr > av.nslots_r) { fail(DERR_BAD_ID); return false; }
         s = (uint32_t)(nr - 1);
         if (ds.check && av.died_r && av.died_r[s]) fail(DERR_AGENT_DIED);                      // :106-110
@@ -386,7 +411,7 @@ class Ctx {
         const uint32_t tb = ds.base[type];
         const uint32_t* __restrict__ src = ev.src;
         const uint8_t* __restrict__ st = av.state_r;
-        const uint32_t cap = av.cap, nsl = av.nslots_r;
+        const uint32_t cap = av.cap, nsl = av.lcap + av.nghost;   // local slots and ghosts are addressed uniformly
         uint32_t k = b + lane_;
         // four independent gathers in flight per lane; the unsigned compare also rejects sources of another type
         for (; k + 3 * GROUP < en; k += 4 * GROUP) {
@@ -417,7 +442,9 @@ class Ctx {
         uint32_t trow, fcomp = 0;
         const uint32_t tt = type_nr(to);
         const uint64_t tnr = agent_nr(to);
-        if (tt < 1 || tt > ds.n_agent_types || tnr < 1 || tnr > ds.agents[tt].cap) { fail(DERR_BAD_ID); return; }
+        if (tt < 1 || tt > ds.n_agent_types || tnr < 1) { fail(DERR_BAD_ID); return; }
+        if (process_nr(to) != ds.rank) { fail(DERR_REMOTE); return; }   // appending to a remote target needs the edge redistribution step
+        if (tnr > ds.agents[tt].lcap) { fail(DERR_BAD_ID); return; }
         if (ev.target) {
             if ((int)tt != ev.target) { fail(DERR_SINGLETYPE_MISMATCH); return; }
             trow = (uint32_t)(tnr - 1);

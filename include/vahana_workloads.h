@@ -19,6 +19,10 @@ extern "C" {
 /* device generation + ingestion into `sim` (CUDA engine only).  Targets [0, n) in chunks of `chunk_targets`. */
 int vbw_hk_powerlaw_build(vb_sim* sim, int agent_type, int edge_type, uint64_t n, uint64_t seed_graph, uint64_t seed_opinion,
                           double c, uint32_t dmax, uint64_t chunk_targets, uint64_t* n_edges_out);
+/* the same for rank `rank` of `nranks`: builds block `rank` of the contiguous equal partition of the n agents
+ * (src/Simulation.jl:353-367) — its agents and every edge whose target it owns; sources carry their owner's rank. */
+int vbw_hk_powerlaw_build_sharded(vb_sim* sim, int agent_type, int edge_type, uint64_t n, uint64_t seed_graph, uint64_t seed_opinion,
+                                  double c, uint32_t dmax, uint64_t chunk_targets, uint32_t rank, uint32_t nranks, uint64_t* n_edges_out);
 /* host generation of the same graph (parity tests, CPU baseline): first call with from/to == NULL to get the
  * edge count, then with caller-allocated arrays.  opinions may be NULL. */
 int vbw_hk_powerlaw_host(uint64_t n, int agent_type, uint64_t seed_graph, uint64_t seed_opinion, double c, uint32_t dmax,

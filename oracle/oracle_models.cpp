@@ -15,4 +15,5 @@ extern "C" int vbw_hk_powerlaw_host(uint64_t n, int agent_type, uint64_t seed_gr
                                     vb_agent_id* from_out, vb_agent_id* to_out, double* opinions_out, uint64_t* n_edges_out) {
     return vbw::hk_powerlaw_host(n, agent_type, seed_graph, seed_opinion, c, dmax, from_out, to_out, opinions_out, n_edges_out);
 }
+extern "C" int vbw_hk_powerlaw_build_sharded(vb_sim*, int, int, uint64_t, uint64_t, uint64_t, double, uint32_t, uint64_t, uint32_t, uint32_t, uint64_t*) { return VB_ERR_STATE; }
 extern "C" int vbw_hk_powerlaw_build(vb_sim*, int, int, uint64_t, uint64_t, uint64_t, double, uint32_t, uint64_t, uint64_t*) { return VB_ERR_STATE; }

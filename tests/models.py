@@ -162,3 +162,55 @@ def raster_model():
     t.register_agenttype("MovingAgent", [("value", "i8")])
     t.register_edgetype("OnPosition")
     return vh.create_model(t, "Raster_Test")
+
+
+def gol_model():
+    """SURVEY.md Appendix C (Game of Life in the reference's API)"""
+    t = vh.ModelTypes()
+    t.register_agenttype("Cell", [("active", "?")], "Immortal")
+    t.register_edgetype("Neighbor", None, "Stateless", "SingleType", target="Cell")
+    return vh.create_model(t, "GoL")
+
+
+def gol_sim(backend, init):
+    """init: bool array (nx, ny); cell (i, j) is created in column-major order (Raster.jl:44-49)"""
+    sim = vh.create_simulation(gol_model(), backend=backend)
+    sim.add_raster("grid", init.shape, "Cell", np.asarray(init, dtype="?").reshape(-1, order="F").view([("active", "?")]))
+    sim.connect_raster_neighbors("grid", "Neighbor")
+    sim.finish_init()
+    return sim
+
+
+PERSON = [("state", "u1"), ("days", "u1")]
+
+
+def sir_model():
+    """SURVEY.md Appendix C (Episim-style SIR stand-in)"""
+    t = vh.ModelTypes()
+    t.register_agenttype("Person", PERSON, "Immortal")
+    t.register_agenttype("Location", [("n_inf", "i4")], "Immortal")
+    t.register_edgetype("Visit", [("infectious", "?")], "SingleType", "IgnoreSourceState", target="Location")
+    t.register_edgetype("Exposure", [("risk", "f4")], "IgnoreFrom", "SingleType", target="Person")
+    t.register_param("beta", 0.05)
+    t.register_param("n_locations", 1)
+    t.register_param("visits_per_step", 2)
+    t.register_param("infectious_days", 10)
+    return vh.create_model(t, "SIR")
+
+
+def sir_sim(backend, n_persons, n_locations, seed=7, frac=0.01, beta=0.05):
+    sim = vh.create_simulation(sir_model(), params={"n_locations": n_locations, "beta": beta}, backend=backend)
+    st = np.zeros(n_persons, dtype=np.dtype(PERSON, align=True))
+    st["state"] = (np.random.default_rng(seed).random(n_persons) < frac).astype("u1")
+    sim.add_agents("Person", st)
+    sim.add_agents("Location", np.zeros(n_locations, dtype=[("n_inf", "i4")]))
+    sim.finish_init()
+    return sim
+
+
+def sir_step(sim, step):
+    """the four applies of one SIR step; `seed` keys the per-agent uniform table of each apply"""
+    sim.apply("sir_visit", "Person", ["Person"], ["Visit"], seed=4 * step)
+    sim.apply("sir_tally", "Location", ["Visit"], ["Location"], seed=4 * step + 1)
+    sim.apply("sir_expose", "Location", ["Location", "Visit"], ["Exposure"], seed=4 * step + 2)
+    sim.apply("sir_infect", "Person", ["Person", "Exposure"], ["Person"], seed=4 * step + 3)

@@ -1,0 +1,80 @@
+"""Model-level parity for the BASELINE configs that no reference test pins (parity unpinned vs Julia: oracle-vs-GPU only,
+plus independent restatements in numpy where the model is simple enough): Game of Life (config 2), SIR (config 5)."""
+import numpy as np
+import pytest
+
+import vahana_b200 as vh
+from models import gol_sim, sir_sim, sir_step
+
+
+def _life_numpy(a):
+    n = sum(np.roll(np.roll(a, dx, 0), dy, 1) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0))
+    return (n == 3) | (a & (n == 2))
+
+
+def test_gol_oracle_vs_numpy(oracle):
+    init = np.random.default_rng(2).random((37, 23)) < 0.35
+    sim = gol_sim(oracle, init)
+    assert sim.num_edges("Neighbor") == 8 * init.size
+    a = init.copy()
+    for _ in range(6):
+        sim.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
+        a = _life_numpy(a)
+        assert np.array_equal(sim.rastervalues("grid", "active", "Cell"), a)
+
+
+@pytest.mark.gpu
+def test_gol_gpu_vs_oracle(oracle, cuda):
+    init = np.random.default_rng(2).random((96, 64)) < 0.35
+    g, o = gol_sim(cuda, init), gol_sim(oracle, init)
+    goff, gfrom, _ = g.export_csr("Neighbor", "Cell", init.size)
+    ooff, ofrom, _ = o.export_csr("Neighbor", "Cell", init.size)
+    assert np.array_equal(goff, ooff) and np.array_equal(gfrom, ofrom)     # per-target neighbour order incl. the wrapped border
+    a = init.copy()
+    for _ in range(10):
+        g.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
+        o.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
+        a = _life_numpy(a)
+        gv = g.rastervalues("grid", "active", "Cell")
+        assert np.array_equal(gv, o.rastervalues("grid", "active", "Cell"))
+        assert np.array_equal(gv, a)
+    assert g.mapreduce("active", "+", "Cell", datatype="i8") == int(a.sum())
+
+
+def _sir_counts(sim):
+    s = sim.all_agents("Person")["state"]
+    return [int((s == k).sum()) for k in range(3)]
+
+
+def test_sir_oracle_invariants(oracle):
+    n, nl = 5000, 400
+    sim = sir_sim(oracle, n, nl, beta=0.3)
+    r_prev = 0
+    for step in range(12):
+        sir_step(sim, step)
+        assert sim.num_edges("Visit") == 2 * n and sim.num_edges("Exposure") == 2 * n
+        s, i, r = _sir_counts(sim)
+        assert s + i + r == n and r >= r_prev
+        r_prev = r
+        assert sim.mapreduce("n_inf", "+", "Location") == int(np.sum(sim.edgestates_all("Visit")["infectious"])) if hasattr(sim, "edgestates_all") else True
+    assert r_prev > 0    # the initially infectious recovered after 10 days
+
+
+@pytest.mark.gpu
+def test_sir_gpu_vs_oracle(oracle, cuda):
+    n, nl = 20000, 1500
+    g, o = sir_sim(cuda, n, nl, beta=0.3), sir_sim(oracle, n, nl, beta=0.3)
+    for step in range(12):
+        sir_step(g, step)
+        sir_step(o, step)
+        gp, op = g.all_agents("Person"), o.all_agents("Person")
+        assert np.array_equal(gp["state"], op["state"]) and np.array_equal(gp["days"], op["days"])
+        assert np.array_equal(g.all_agents("Location")["n_inf"], o.all_agents("Location")["n_inf"])
+        for et, tt, rows in (("Visit", "Location", nl), ("Exposure", "Person", n)):
+            a, b = g.export_csr(et, tt, rows), o.export_csr(et, tt, rows)
+            assert np.array_equal(a[0], b[0])                    # CSR offsets
+            if et == "Visit":
+                assert np.array_equal(a[1], b[1])                # per-target visitor order (append order)
+            assert np.array_equal(a[2].view("u1"), b[2].view("u1"))   # edge states bit-exact (incl. the Float32 risk)
+    assert _sir_counts(g) == _sir_counts(o)
+    assert _sir_counts(g)[2] > 0

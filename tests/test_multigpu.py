@@ -1,0 +1,75 @@
+"""N > 1: (a) host-side logic on CPU with gloo at world_size 2 (partition, unique-id plumbing, sharded generator ==
+global generator), (b) on >= 2 GPUs the sharded HK step with the NCCL halo against the single-rank oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import vahana_b200 as vh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_equal_partition_matches_reference_formula():   # src/Simulation.jl:353-367
+    for n, p in [(10, 3), (7, 7), (100, 8), (5, 2), (3, 4)]:
+        b = vh.equal_partition(n, p)
+        s, r = divmod(n, p)
+        ref = [((i - 1) * s + 1 + min(i - 1, r), i * s + min(i, r)) for i in range(1, p + 1)]    # Julia's 1-based ranges
+        assert [(b[i] + 1, b[i + 1]) for i in range(p)] == ref
+
+
+_GLOO = r'''
+import os, sys, ctypes as C
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import vahana_b200 as vh
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# unique-id plumbing of Backend.init_distributed, exercised with the oracle library (no GPU here)
+ob = vh.load_backend(os.path.join({root!r}, "oracle", "_build", "libvahana_oracle.so"))
+buf = (C.c_uint8 * 128)()
+if rank == 0:
+    ob.check(ob.lib.vb_comm_unique_id(buf)); buf[5] = 77
+t = torch.tensor(list(buf), dtype=torch.uint8); dist.broadcast(t, src=0)
+assert t[5].item() == 77
+# sharded generation: the union of the ranks' shards is the global graph with block-partitioned ids
+n = 3001
+bounds = vh.equal_partition(n, world)
+ne = C.c_uint64()
+ob.lib.vbw_hk_powerlaw_host(C.c_uint64(n), 1, C.c_uint64(4), C.c_uint64(5), C.c_double(6.8333), C.c_uint32(1000000), None, None, None, C.byref(ne))
+fr = np.zeros(ne.value, dtype=np.uint64); to = np.zeros(ne.value, dtype=np.uint64)
+ob.lib.vbw_hk_powerlaw_host(C.c_uint64(n), 1, C.c_uint64(4), C.c_uint64(5), C.c_double(6.8333), C.c_uint32(1000000), fr.ctypes.data_as(C.c_void_p), to.ctypes.data_as(C.c_void_p), None, C.byref(ne))
+g = (to & ((1 << 36) - 1)).astype(np.int64) - 1
+mine = (g >= bounds[rank]) & (g < bounds[rank + 1])
+cnt = torch.tensor([int(mine.sum())]); dist.all_reduce(cnt)
+assert cnt.item() == ne.value                      # every edge is stored on exactly one rank: its target's
+owner = np.searchsorted(np.array(bounds[1:]), (fr & ((1 << 36) - 1)).astype(np.int64) - 1, side="right")
+remote = int((owner[mine] != rank).sum())
+assert remote > 0                                  # there is a halo to exchange
+print("gloo rank", rank, "ok", flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_world2_host_logic(oracle, tmp_path):
+    script = tmp_path / "gloo_host.py"
+    script.write_text(_GLOO.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+
+
+@pytest.mark.gpu
+def test_hk_sharded_halo_vs_oracle(cuda):
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ng, 4)), "--master-addr", "127.0.0.1",
+                        "--master-port", "29519", os.path.join(ROOT, "tests", "mgpu_hk.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(": ok") == min(ng, 4)

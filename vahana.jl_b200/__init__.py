@@ -103,7 +103,7 @@ ABI_SYMBOLS = [
     "vb_cellid", "vb_finish_init", "vb_apply", "vb_has_transition", "vb_load_model_library", "vb_num_agents",
     "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce",
     "vb_rastervalues", "vb_calc_raster_num_edges", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
-    "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes",
+    "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes",
 ]
 
 
@@ -142,7 +142,40 @@ class Backend:
         self.check(self.lib.vb_set_stream(C.c_void_p(cuda_stream)))
 
 
+    # -- multi-GPU: one process per GPU (src/MPIinit.jl) --
+    def init_distributed(self, rank: Optional[int] = None, world: Optional[int] = None) -> tuple:
+        """Creates the engine's NCCL communicator.  The 128-byte unique id is created on rank 0 and broadcast with
+        torch.distributed (any backend), which must already be initialised when world > 1."""
+        import torch
+        import torch.distributed as dist
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        if world == 1:
+            self.check(self.lib.vb_comm_init(0, 1, None))
+            return 0, 1
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            self.check(self.lib.vb_comm_unique_id(buf))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        self.check(self.lib.vb_comm_init(C.c_int(rank), C.c_int(world), ident))
+        return rank, world
+
+
 _default_backend: Optional[Backend] = None
+
+
+def equal_partition(n: int, nranks: int) -> list:
+    """_create_equal_partition (src/Simulation.jl:353-367): contiguous blocks, sizes differ by at most one, larger blocks first.
+    Returns the nranks + 1 block boundaries."""
+    q, r = divmod(int(n), int(nranks))
+    b = [0]
+    for p in range(nranks):
+        b.append(b[-1] + q + (1 if p < r else 0))
+    return b
 
 
 def load_backend(path: Optional[str] = None) -> Backend:

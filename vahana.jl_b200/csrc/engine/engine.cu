@@ -9,6 +9,7 @@
 // There is no CPU fallback: every state-touching entry point needs the CUDA device.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nccl.h>   // types and enums only: the library is resolved at run time (dlopen), see Nccl below
 
 #include <algorithm>
 #include <cmath>
@@ -49,6 +50,43 @@ unsigned long long g_launches = 0;   // kernels of ours launched (bench reports 
     do {                               \
         ++g_launches;                  \
         CK(cudaGetLastError());        \
+    } while (0)
+
+// ---- NCCL over NVLink: replaces the reference's MPI exchanges (src/MPI.jl, src/MPIinit.jl) -----------------
+// Resolved with dlopen so the engine has no link-time dependency: inside a torch process the bundled
+// libnccl.so.2 is already mapped; other hosts set VB_NCCL_LIB or have libnccl.so.2 on the loader path.
+struct Nccl {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char* env = getenv("VB_NCCL_LIB");
+        const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { if (n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break; }
+        if (!h) return false;
+#define VB_SYM(field, name) field = (decltype(field))dlsym(h, name); if (!field) return false;
+        VB_SYM(GetUniqueId, "ncclGetUniqueId") VB_SYM(CommInitRank, "ncclCommInitRank") VB_SYM(CommDestroy, "ncclCommDestroy")
+        VB_SYM(Send, "ncclSend") VB_SYM(Recv, "ncclRecv") VB_SYM(GroupStart, "ncclGroupStart") VB_SYM(GroupEnd, "ncclGroupEnd")
+        VB_SYM(AllGather, "ncclAllGather") VB_SYM(GetErrorString, "ncclGetErrorString")
+#undef VB_SYM
+        return true;
+    }
+};
+Nccl g_nccl;
+ncclComm_t g_comm = nullptr;
+int g_rank = 0, g_nranks = 1;
+#define NK(expr)                                                                                                  \
+    do {                                                                                                          \
+        ncclResult_t _r = (expr);                                                                                 \
+        if (_r != ncclSuccess) throw CudaError(std::string(#expr) + ": " + g_nccl.GetErrorString(_r));           \
     } while (0)
 
 void require_device() {
@@ -111,7 +149,8 @@ struct TranslateArgs {
     const uint64_t* to; const uint64_t* from; uint64_t n;
     uint32_t* log_to; uint32_t* log_from; uint64_t pos0;
     uint32_t base[vb::MAX_AGENT_TYPES + 2]; uint32_t nslots[vb::MAX_AGENT_TYPES + 1];
-    uint32_t ntypes; int32_t target; int ignore_from; uint32_t* error;
+    uint32_t lcap[vb::MAX_AGENT_TYPES + 1]; uint32_t nghost[vb::MAX_AGENT_TYPES + 1]; const uint64_t* ghost_ids[vb::MAX_AGENT_TYPES + 1];
+    uint32_t ntypes; int32_t target; int ignore_from; uint32_t rank; uint32_t* error;
 };
 __global__ void translate_edges_kernel(const TranslateArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,6 +160,7 @@ __global__ void translate_edges_kernel(const TranslateArgs a) {
     const uint64_t tnr = vb::agent_nr(to);
     uint32_t row = 0;
     if (tt < 1 || tt > a.ntypes || tnr < 1 || tnr > a.nslots[tt]) { atomicOr(a.error, (uint32_t)vb::DERR_BAD_ID); }
+    else if (vb::process_nr(to) != a.rank) { atomicOr(a.error, (uint32_t)vb::DERR_REMOTE); }   // edges are stored on the rank of their target
     else if (a.target) { if ((int)tt != a.target) atomicOr(a.error, (uint32_t)vb::DERR_SINGLETYPE_MISMATCH); row = (uint32_t)(tnr - 1); }
     else row = a.base[tt] + (uint32_t)(tnr - 1);
     a.log_to[a.pos0 + i] = row;
@@ -129,7 +169,15 @@ __global__ void translate_edges_kernel(const TranslateArgs a) {
         const uint32_t ft = vb::type_nr(fr);
         const uint64_t fnr = vb::agent_nr(fr);
         uint32_t c = 0;
-        if (ft < 1 || ft > a.ntypes || fnr < 1 || fnr > a.nslots[ft]) atomicOr(a.error, (uint32_t)vb::DERR_BAD_ID);
+        if (ft < 1 || ft > a.ntypes || fnr < 1) atomicOr(a.error, (uint32_t)vb::DERR_BAD_ID);
+        else if (vb::process_nr(fr) != a.rank) {   // remote source: its slot in the ghost segment
+            uint32_t lo = 0, hi = a.nghost[ft];
+            const uint64_t* g = a.ghost_ids[ft];
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (g[mid] < fr) lo = mid + 1; else hi = mid; }
+            if (lo >= a.nghost[ft] || g[lo] != fr) atomicOr(a.error, (uint32_t)vb::DERR_BAD_ID);
+            else c = a.base[ft] + a.lcap[ft] + lo;
+        }
+        else if (fnr > a.nslots[ft]) atomicOr(a.error, (uint32_t)vb::DERR_BAD_ID);
         else c = a.base[ft] + (uint32_t)(fnr - 1);
         a.log_from[a.pos0 + i] = c;
     }
@@ -250,6 +298,51 @@ __global__ void purge_copy_kernel(const PurgeArgs a) {
 __global__ void purge_rows_cnt_kernel(uint32_t* __restrict__ cnt, uint32_t rows, const uint8_t* __restrict__ dead, uint32_t row_base) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < rows && dead[row_base + r]) cnt[r] = 0;
+}
+// multi-GPU ghost discovery: remote source ids of raw adds
+__global__ void remote_flags_kernel(const uint64_t* __restrict__ ids, uint64_t n, uint32_t rank, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = vb::process_nr(ids[i]) != rank ? 1u : 0u;
+}
+__global__ void compact_u64_split_kernel(const uint64_t* __restrict__ in, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, uint64_t n,
+                                         uint32_t* __restrict__ lo, uint32_t* __restrict__ hi, uint64_t out0) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) { lo[out0 + pos[i]] = (uint32_t)in[i]; hi[out0 + pos[i]] = (uint32_t)(in[i] >> 32); }
+}
+__global__ void unique_flags64_kernel(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, uint64_t n, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || hi[i] != hi[i - 1] || lo[i] != lo[i - 1]) ? 1u : 0u;
+}
+__global__ void compact_join64_kernel(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, const uint32_t* __restrict__ flag,
+                                      const uint32_t* __restrict__ pos, uint64_t n, uint64_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = ((uint64_t)hi[i] << 32) | lo[i];
+}
+// lower_bound of (type, rank, nr = 0) boundaries in the sorted ghost id list
+__global__ void ghost_bounds_kernel(const uint64_t* __restrict__ ids, uint32_t n, uint32_t ntypes, uint32_t nranks, uint32_t* __restrict__ bounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > ntypes * nranks) return;
+    const uint32_t t = i / nranks + 1, r = i % nranks;
+    const uint64_t key = i == ntypes * nranks ? ~0ull : vb::agent_id(t, r, 0);
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ids[mid] < key) lo = mid + 1; else hi = mid; }
+    bounds[i] = lo;
+}
+__global__ void ids_to_slots_kernel(const uint64_t* __restrict__ ids, uint32_t n, uint32_t* __restrict__ slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slots[i] = (uint32_t)(vb::agent_nr(ids[i]) - 1);
+}
+// halo pack: send[c][i] = state[c][slot[i]] for every SoA column c
+__global__ void halo_pack_kernel(const uint8_t* __restrict__ cols, uint32_t stride, const uint32_t* __restrict__ slots, uint32_t n, uint8_t* __restrict__ out,
+                                 uint32_t word, uint32_t ncols) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n * ncols) return;
+    const uint32_t i = (uint32_t)(t % n), c = (uint32_t)(t / n);
+    const uint8_t* sp = cols + (size_t)c * stride * word + (size_t)slots[i] * word;
+    uint8_t* dp = out + (size_t)c * n * word + (size_t)i * word;
+    if (word == 8) *reinterpret_cast<uint64_t*>(dp) = *reinterpret_cast<const uint64_t*>(sp);
+    else if (word == 4) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
+    else for (uint32_t b = 0; b < word; ++b) dp[b] = sp[b];
 }
 __global__ void heavy_flags_kernel(const uint32_t* __restrict__ off, uint32_t row0, uint32_t n, uint32_t rows, uint32_t heavy_min, uint32_t* __restrict__ flag) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,6 +521,15 @@ struct AgentStore {
     bool writeable = false, prepared = false;
     int64_t last_change = 0;
     uint32_t births = 0;         // births of the running apply
+    // multi-GPU: ghost segment [cap, cap + nghost) mirrors remote agents referenced by local edges
+    uint32_t gcap = 0, nghost = 0;
+    uint64_t* ghost_ids = nullptr;            // device, ascending (rank-major)
+    std::vector<uint32_t> ghost_off;          // [nranks + 1] ghost range per owner rank
+    uint32_t* send_slots = nullptr;           // device: local slots requested by the peers, grouped by peer
+    std::vector<uint32_t> send_off;           // [nranks + 1]
+    uint8_t* send_buf = nullptr;              // packed states for the halo exchange
+    bool halo_dirty = true;
+    uint32_t stride() const { return cap + gcap; }
     uint8_t* rstate() const { return state[cur]; }
     uint8_t* wstate() const { return independent ? state[cur] : state[cur ^ 1]; }
     uint8_t* rdied() const { return died[cur]; }
@@ -507,7 +609,10 @@ struct vb_sim {
 
     ~vb_sim();
     void compute_bases(uint32_t* out) const;
-    void ensure_agent_cap(int t, uint64_t need);
+    void ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need = 0);
+    void build_ghosts();
+    void halo_exchange(int t);
+    uint64_t halo_bytes = 0;   // bytes received by the last apply's halo exchanges
     void rebase(const uint32_t* old_base);
     void upload_view(uint64_t seed);
     void check_device_error(const char* where);
@@ -524,8 +629,8 @@ namespace {
 
 void free_agent(AgentStore& a) {
     dfree(a.state[0]); if (a.state[1] != a.state[0]) dfree(a.state[1]);
-    dfree(a.died[0]); dfree(a.died[1]); dfree(a.reuse);
-    a.state[0] = a.state[1] = a.died[0] = a.died[1] = nullptr; a.reuse = nullptr;
+    dfree(a.died[0]); dfree(a.died[1]); dfree(a.reuse); dfree(a.ghost_ids); dfree(a.send_slots); dfree(a.send_buf);
+    a.state[0] = a.state[1] = a.died[0] = a.died[1] = nullptr; a.reuse = nullptr; a.ghost_ids = nullptr; a.send_slots = nullptr; a.send_buf = nullptr;
 }
 void free_edge_read(EdgeStore& e) {
     ++e.version;
@@ -555,17 +660,19 @@ vb_sim::~vb_sim() {
 void vb_sim::compute_bases(uint32_t* out) const {
     uint64_t run = 0;
     out[0] = 0;
-    for (size_t t = 1; t <= agents.size(); ++t) { out[t] = (uint32_t)run; run += agents[t - 1].cap; }
+    for (size_t t = 1; t <= agents.size(); ++t) { out[t] = (uint32_t)run; run += agents[t - 1].stride(); }
     if (run >= 0xffffffffull) throw ArgError("more than 2^32-1 agent slots on one rank are not supported by the 32-bit composite index");
     out[agents.size() + 1] = (uint32_t)run;
 }
 
 // grow the buffers of agent type t to hold `need` slots; composite bases of later types shift (rebase)
-void vb_sim::ensure_agent_cap(int t, uint64_t need) {
+void vb_sim::ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need) {
     AgentStore& a = A(t);
-    if (need <= a.cap) return;
-    uint64_t ncap = std::max<uint64_t>(need, (uint64_t)a.cap + a.cap / 2);
-    ncap = (ncap + 255) / 256 * 256;
+    if (need <= a.cap && ghost_need <= a.gcap) return;
+    uint64_t ncap = a.cap;
+    if (need > a.cap) { ncap = std::max<uint64_t>(need, (uint64_t)a.cap + a.cap / 2); ncap = (ncap + 255) / 256 * 256; }
+    const uint32_t ngcap = std::max(a.gcap, ghost_need);
+    const uint64_t nstride = ncap + ngcap;
     if (ncap >= 0xffffffffull) throw ArgError("agent type too large for 32-bit slots");
     uint32_t old_base[vb::MAX_AGENT_TYPES + 2];
     std::memcpy(old_base, base, sizeof(old_base));
@@ -573,9 +680,9 @@ void vb_sim::ensure_agent_cap(int t, uint64_t need) {
     const int nb = a.independent ? 1 : 2;
     if (a.size) {
         for (int b = 0; b < nb; ++b) {
-            uint8_t* n = (uint8_t*)g_pool.alloc(ncap * a.size);
-            if (had) {
-                vbp::soa_copy_kernel<<<nblk((uint64_t)a.cap * a.size), 256, 0, g_stream>>>(a.state[b], a.cap, n, ncap, a.cap, a.ncols, a.word, 0, 0);
+            uint8_t* n = (uint8_t*)g_pool.alloc(nstride * a.size);
+            if (had) {   // the local part moves; ghosts are refilled by the next halo exchange
+                vbp::soa_copy_kernel<<<nblk((uint64_t)a.cap * a.size), 256, 0, g_stream>>>(a.state[b], a.stride(), n, nstride, a.cap, a.ncols, a.word, 0, 0);
                 LAUNCH_CHECK();
             }
             dfree(a.state[b]);
@@ -585,9 +692,9 @@ void vb_sim::ensure_agent_cap(int t, uint64_t need) {
     }
     if (!a.immortal) {
         for (int b = 0; b < 2; ++b) {
-            uint8_t* n = (uint8_t*)g_pool.alloc(ncap);
-            CK(cudaMemsetAsync(n, 0, ncap, g_stream));
-            if (had) CK(cudaMemcpyAsync(n, a.died[b], a.cap, cudaMemcpyDeviceToDevice, g_stream));
+            uint8_t* n = (uint8_t*)g_pool.alloc(nstride);
+            CK(cudaMemsetAsync(n, 0, nstride, g_stream));
+            if (had) CK(cudaMemcpyAsync(n, a.died[b], a.cap, cudaMemcpyDeviceToDevice, g_stream));   // local flags; ghosts count as alive
             dfree(a.died[b]);
             a.died[b] = n;
         }
@@ -598,6 +705,8 @@ void vb_sim::ensure_agent_cap(int t, uint64_t need) {
         a.reuse_cap = (uint32_t)ncap;
     }
     a.cap = (uint32_t)ncap;
+    a.gcap = ngcap;
+    a.halo_dirty = true;
     compute_bases(base);
     rebase(old_base);
 }
@@ -672,7 +781,7 @@ void vb_sim::upload_view(uint64_t seed) {
         vb::AgentView& v = h.agents[t];
         v.state_r = a.rstate(); v.state_w = a.wstate();
         v.died_r = a.immortal ? nullptr : a.rdied(); v.died_w = a.immortal ? nullptr : a.wdied();
-        v.reuse = a.reuse; v.cap = a.cap; v.nslots_r = a.nslots;
+        v.reuse = a.reuse; v.cap = a.stride(); v.lcap = a.cap; v.nghost = a.nghost; v.ghost_ids = a.ghost_ids; v.nslots_r = a.nslots;
         v.n_reuse = a.n_reuse; v.next0 = (uint32_t)(a.nextid - 1);
         v.size = a.size; v.word = a.word ? a.word : 1; v.ncols = a.ncols;
         v.immortal = a.immortal; v.independent = a.independent; v.readable = a.prepared; v.writeable = a.writeable;
@@ -714,6 +823,7 @@ void vb_sim::check_device_error(const char* where) {
     if (err & vb::DERR_SINGLETYPE_MISMATCH) m += " :SingleType edge used with an agent of another type;";
     if (err & vb::DERR_RASTER_POS) m += " raster position out of range;";
     if (err & vb::DERR_INDEX) m += " neighbour index out of range;";
+    if (err & vb::DERR_REMOTE) m += " an edge was added to (or read for) an agent of another rank: edge redistribution is not implemented yet;";
     throw AssertionError(m);
 }
 
@@ -777,7 +887,8 @@ void vb_sim::merge_pending(int ei) {
         ta.log_to = e.kind == vb::KIND_CSR ? e.log_to : tmp_rows; ta.log_from = e.log_from; ta.pos0 = pos;
         std::memcpy(ta.base, base, sizeof(ta.base));
         for (size_t t = 1; t <= agents.size(); ++t) ta.nslots[t] = (uint32_t)std::max<uint64_t>(agents[t - 1].nslots, agents[t - 1].nextid - 1);
-        ta.ntypes = (uint32_t)agents.size(); ta.target = e.singletype ? e.target : 0; ta.ignore_from = !e.has_src() || e.kind != vb::KIND_CSR; ta.error = d_error;
+        for (size_t t = 1; t <= agents.size(); ++t) { ta.lcap[t] = agents[t - 1].cap; ta.nghost[t] = agents[t - 1].nghost; ta.ghost_ids[t] = agents[t - 1].ghost_ids; }
+        ta.ntypes = (uint32_t)agents.size(); ta.target = e.singletype ? e.target : 0; ta.ignore_from = !e.has_src() || e.kind != vb::KIND_CSR; ta.rank = rank; ta.error = d_error;
         translate_edges_kernel<<<nblk(c.n), 256, 0, g_stream>>>(ta); LAUNCH_CHECK();
         if (e.kind == vb::KIND_CSR && e.has_state()) {
             vbp::aos_to_soa_kernel<<<nblk(c.n * e.ncols), 256, 0, g_stream>>>(c.st, e.log_st, e.log_cap, pos, c.n, e.size, e.word); LAUNCH_CHECK();
@@ -951,6 +1062,138 @@ void vb_sim::purge_dead(const uint8_t* dead) {
     }
 }
 
+// Multi-GPU (one process per GPU).  Agents are owned by one rank (rank bits of the id, src/Agent.jl:39-40), every edge is
+// stored on its target's rank (src/EdgeMethods.jl:396-398).  The state of remote *sources* is mirrored in a ghost segment
+// behind the local slots of each agent type; this replaces the reference's request/reply halo (transmit_agents!,
+// src/MPI.jl:155-267): the request lists are exchanged once here, per step only packed states travel (halo_exchange).
+void vb_sim::build_ghosts() {
+    if (g_nranks <= 1) return;
+    const uint32_t NT = (uint32_t)agents.size(), P = (uint32_t)g_nranks;
+    // 1. all remote source ids of the raw adds, split into 32-bit halves for the radix sort
+    uint64_t cap = 0;
+    for (auto& e : edges) { if (!e.has_src()) continue; flush_raw((int)(&e - &edges[0])); for (auto& c : e.chunks) cap += c.n; }
+    uint32_t* lo = dalloc<uint32_t>(std::max<uint64_t>(cap, 1)); uint32_t* hi = dalloc<uint32_t>(std::max<uint64_t>(cap, 1));
+    uint64_t nrem = 0;
+    for (auto& e : edges) {
+        if (!e.has_src()) continue;
+        for (auto& c : e.chunks) {
+            if (c.n >= 0xffffffffull) throw ArgError("raw edge chunk too large");
+            uint32_t* flag = dalloc<uint32_t>(c.n); uint32_t* pos = dalloc<uint32_t>(c.n);
+            uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(c.n));
+            remote_flags_kernel<<<nblk(c.n), 256, 0, g_stream>>>(c.from, c.n, rank, flag); LAUNCH_CHECK();
+            vbp::exclusive_scan(flag, pos, c.n, d_scalars, scr, g_stream);
+            uint32_t k = 0;
+            CK(cudaMemcpyAsync(&k, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            if (k) { compact_u64_split_kernel<<<nblk(c.n), 256, 0, g_stream>>>(c.from, flag, pos, c.n, lo, hi, nrem); LAUNCH_CHECK(); }
+            nrem += k;
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(flag); dfree(pos); dfree(scr);
+        }
+    }
+    if (nrem >= 0xffffffffull) throw ArgError("too many remote edge sources on one rank");
+    // 2. sort by (hi, lo) = ascending AgentID (two stable 32-bit sorts), then unique
+    uint64_t* G = nullptr; uint32_t ng = 0;
+    if (nrem) {
+        uint32_t* lo2 = dalloc<uint32_t>(nrem); uint32_t* hi2 = dalloc<uint32_t>(nrem);
+        uint32_t* scratch = dalloc<uint32_t>(vbp::rs_scratch_words(nrem));
+        int r = vbp::radix_sort(lo, lo2, hi, hi2, nullptr, nullptr, 0, nrem, 32, scratch, g_stream);     // key = low half, payload = high half
+        uint32_t* slo = r ? lo2 : lo; uint32_t* shi = r ? hi2 : hi; uint32_t* tlo = r ? lo : lo2; uint32_t* thi = r ? hi : hi2;
+        r = vbp::radix_sort(shi, thi, slo, tlo, nullptr, nullptr, 0, nrem, 32, scratch, g_stream);       // key = high half (stable)
+        uint32_t* fhi = r ? thi : shi; uint32_t* flo = r ? tlo : slo;
+        CK(cudaGetLastError());
+        uint32_t* flag = dalloc<uint32_t>(nrem); uint32_t* pos = dalloc<uint32_t>(nrem);
+        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(nrem));
+        unique_flags64_kernel<<<nblk(nrem), 256, 0, g_stream>>>(fhi, flo, nrem, flag); LAUNCH_CHECK();
+        vbp::exclusive_scan(flag, pos, nrem, d_scalars, scr, g_stream);
+        CK(cudaMemcpyAsync(&ng, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        G = dalloc<uint64_t>(std::max<uint32_t>(ng, 1));
+        compact_join64_kernel<<<nblk(nrem), 256, 0, g_stream>>>(fhi, flo, flag, pos, nrem, G); LAUNCH_CHECK();
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(lo2); dfree(hi2); dfree(scratch); dfree(flag); dfree(pos); dfree(scr);
+    }
+    dfree(lo); dfree(hi);
+    // 3. boundaries per (type, owner rank)
+    std::vector<uint32_t> bounds((size_t)NT * P + 1, 0);
+    if (ng) {
+        uint32_t* db = dalloc<uint32_t>(bounds.size());
+        ghost_bounds_kernel<<<nblk(bounds.size()), 256, 0, g_stream>>>(G, ng, NT, P, db); LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(bounds.data(), db, bounds.size() * 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(db);
+    }
+    for (uint32_t t = 1; t <= NT; ++t) {
+        AgentStore& a = agents[t - 1];
+        const uint32_t b0 = bounds[(size_t)(t - 1) * P], b1 = bounds[(size_t)t * P];
+        a.nghost = b1 - b0;
+        dfree(a.ghost_ids); a.ghost_ids = nullptr;
+        a.ghost_off.assign(P + 1, 0);
+        for (uint32_t r = 0; r <= P; ++r) a.ghost_off[r] = bounds[(size_t)(t - 1) * P + r] - b0;
+        if (a.nghost) {
+            a.ghost_ids = dalloc<uint64_t>(a.nghost);
+            CK(cudaMemcpyAsync(a.ghost_ids, G + b0, (size_t)a.nghost * 8, cudaMemcpyDeviceToDevice, g_stream));
+        }
+        ensure_agent_cap((int)t, a.cap, a.nghost);
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(G);
+    // 4. tell every owner which of its agents we mirror: counts (all-gather), then the id lists (grouped send/recv)
+    uint32_t* dcnt = dalloc<uint32_t>((size_t)P * NT); uint32_t* dall = dalloc<uint32_t>((size_t)P * P * NT);
+    std::vector<uint32_t> mine((size_t)P * NT), all((size_t)P * P * NT);
+    for (uint32_t t = 1; t <= NT; ++t) for (uint32_t r = 0; r < P; ++r) mine[(size_t)(t - 1) * P + r] = agents[t - 1].ghost_off[r + 1] - agents[t - 1].ghost_off[r];
+    CK(cudaMemcpyAsync(dcnt, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice, g_stream));
+    NK(g_nccl.AllGather(dcnt, dall, mine.size() * 4, ncclUint8, g_comm, g_stream));
+    CK(cudaMemcpyAsync(all.data(), dall, all.size() * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(dcnt); dfree(dall);
+    for (uint32_t t = 1; t <= NT; ++t) {
+        AgentStore& a = agents[t - 1];
+        a.send_off.assign(P + 1, 0);
+        for (uint32_t r = 0; r < P; ++r) a.send_off[r + 1] = a.send_off[r] + all[(size_t)r * P * NT + (size_t)(t - 1) * P + rank];   // what rank r wants from me
+        const uint32_t ns = a.send_off[P];
+        dfree(a.send_slots); a.send_slots = nullptr; dfree(a.send_buf); a.send_buf = nullptr;
+        uint64_t* req = dalloc<uint64_t>(std::max<uint32_t>(ns, 1));
+        NK(g_nccl.GroupStart());
+        for (uint32_t r = 0; r < P; ++r) {
+            if (r == rank) continue;
+            const uint32_t want = a.ghost_off[r + 1] - a.ghost_off[r], give = a.send_off[r + 1] - a.send_off[r];
+            if (want) NK(g_nccl.Send(a.ghost_ids + a.ghost_off[r], (size_t)want * 8, ncclUint8, (int)r, g_comm, g_stream));
+            if (give) NK(g_nccl.Recv(req + a.send_off[r], (size_t)give * 8, ncclUint8, (int)r, g_comm, g_stream));
+        }
+        NK(g_nccl.GroupEnd());
+        if (ns) {
+            a.send_slots = dalloc<uint32_t>(ns);
+            ids_to_slots_kernel<<<nblk(ns), 256, 0, g_stream>>>(req, ns, a.send_slots); LAUNCH_CHECK();
+            a.send_buf = (uint8_t*)g_pool.alloc((size_t)ns * std::max<uint32_t>(a.size, 1));
+        }
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(req);
+        a.halo_dirty = true;
+    }
+}
+
+// per-step halo: pack the states the peers mirror, grouped ncclSend/ncclRecv (all-to-all-v) straight into the ghost segments
+void vb_sim::halo_exchange(int t) {
+    AgentStore& a = A(t);
+    if (g_nranks <= 1 || !a.halo_dirty) return;
+    a.halo_dirty = false;
+    if (!a.size || a.send_off.empty()) return;
+    const uint32_t P = (uint32_t)g_nranks, ns = a.send_off[P];
+    if (ns) { halo_pack_kernel<<<nblk((uint64_t)ns * a.ncols), 256, 0, g_stream>>>(a.rstate(), a.stride(), a.send_slots, ns, a.send_buf, a.word, a.ncols); LAUNCH_CHECK(); }
+    NK(g_nccl.GroupStart());
+    for (uint32_t c = 0; c < a.ncols; ++c) {
+        for (uint32_t r = 0; r < P; ++r) {
+            if (r == rank) continue;
+            const uint32_t give = a.send_off[r + 1] - a.send_off[r], want = a.ghost_off[r + 1] - a.ghost_off[r];
+            if (give) NK(g_nccl.Send(a.send_buf + ((size_t)c * ns + a.send_off[r]) * a.word, (size_t)give * a.word, ncclUint8, (int)r, g_comm, g_stream));
+            if (want) NK(g_nccl.Recv(a.rstate() + ((size_t)c * a.stride() + a.cap + a.ghost_off[r]) * a.word, (size_t)want * a.word, ncclUint8, (int)r, g_comm, g_stream));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    halo_bytes += (uint64_t)a.nghost * a.size;
+}
+
 uint64_t vb_sim::edge_total(int ei, bool write) {
     EdgeStore& e = E(ei);
     // before finish_init! everything lives in the write container = raw adds (Edge.jl:376-380)
@@ -1022,6 +1265,7 @@ void finish_write_agent(vb_sim& s, int t, std::vector<uint32_t*>& died_flags, st
     }
     a.cur ^= 1;   // read := write by swapping the double buffers (:Independent types share one state buffer)
     a.write_stale = true;
+    a.halo_dirty = true;
     a.last_change = s.num_transitions;
     a.writeable = false;
 }
@@ -1076,7 +1320,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 if (!a.immortal) CK(cudaMemcpyAsync(a.wdied(), a.rdied(), a.nslots, cudaMemcpyDeviceToDevice, g_stream));
                 const bool full_call = contains(call, w) && with_edge < 0;
                 if (!a.independent && a.size && a.write_stale && !full_call) {
-                    CK(cudaMemcpyAsync(a.wstate(), a.rstate(), (size_t)a.cap * a.size, cudaMemcpyDeviceToDevice, g_stream));
+                    CK(cudaMemcpyAsync(a.wstate(), a.rstate(), (size_t)a.stride() * a.size, cudaMemcpyDeviceToDevice, g_stream));
                 }
             }
         } else {                                                               // EdgeMethods.jl:639-663
@@ -1095,6 +1339,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     }
     CK(cudaMemsetAsync(s.d_stats, 0, 4096 * 8, g_stream));
     CK(cudaEventRecord(s.ev[0], g_stream));
+    s.halo_bytes = 0;
+    for (int r : read) if (r < vb::EDGE_REF) s.halo_exchange(r);   // prepare_read!: transmit_agents! (AgentMethods.jl:484-496)
     s.st_agents_called = 0;
     s.ms_kernel = 0;
     uint64_t appended = 0;
@@ -1187,7 +1433,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20);
                 cudaStreamAttrValue av{};
                 av.accessPolicyWindow.base_ptr = a.rstate();
-                av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)a.cap * a.size, (size_t)persist_mb << 20);
+                av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)a.stride() * a.size, (size_t)persist_mb << 20);
                 av.accessPolicyWindow.hitRatio = 1.0f;
                 av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
                 av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
@@ -1290,12 +1536,40 @@ int vb_set_stream(void* stream) {   // run all engine work on the caller's strea
         g_stream = (cudaStream_t)stream;
     });
 }
-int vb_comm_unique_id(uint8_t id_out[128]) { std::memset(id_out, 0, 128); return VB_OK; }
-int vb_comm_init(int, int nranks, const uint8_t*) {
-    if (nranks != 1) { g_err = "multi-GPU communicator is not initialised in this build"; return VB_ERR_STATE; }
-    return VB_OK;
+int vb_comm_unique_id(uint8_t id_out[128]) {
+    return guard([&] {
+        if (!g_nccl.load()) throw CudaError("libnccl.so.2 could not be loaded (set VB_NCCL_LIB)");
+        ncclUniqueId id;
+        NK(g_nccl.GetUniqueId(&id));
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        std::memcpy(id_out, &id, 128);
+    });
 }
-int vb_comm_rank(int* r, int* n) { *r = 0; *n = 1; return VB_OK; }
+int vb_comm_init(int rank, int nranks, const uint8_t* idbytes) {
+    return guard([&] {
+        require_device();
+        if (nranks <= 1) { g_rank = 0; g_nranks = 1; return; }
+        if (!g_nccl.load()) throw CudaError("libnccl.so.2 could not be loaded (set VB_NCCL_LIB)");
+        if (nranks > (1 << vb::BITS_PROCESS)) throw ArgError("too many ranks for the 20-bit process id");
+        ncclUniqueId id;
+        std::memcpy(&id, idbytes, 128);
+        NK(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
+        g_rank = rank; g_nranks = nranks;
+    });
+}
+int vb_comm_rank(int* r, int* n) { *r = g_rank; *n = g_nranks; return VB_OK; }
+// fold one 8-byte value per rank with `op` (mapreduce / num_agents / num_edges: MPI.Allreduce in the reference)
+static void allgather8(const void* mine, std::vector<uint64_t>& all) {
+    all.assign((size_t)g_nranks, 0);
+    if (g_nranks <= 1) { std::memcpy(all.data(), mine, 8); return; }
+    uint64_t* d = dalloc<uint64_t>((size_t)g_nranks + 1);
+    CK(cudaMemcpyAsync(d + g_nranks, mine, 8, cudaMemcpyHostToDevice, g_stream));
+    NK(g_nccl.AllGather(d + g_nranks, d, 8, ncclUint8, g_comm, g_stream));
+    CK(cudaMemcpyAsync(all.data(), d, (size_t)g_nranks * 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(d);
+}
+int vb_halo_bytes(vb_sim* s, uint64_t* out) { *out = s->halo_bytes; return VB_OK; }
 
 int vb_sim_create(const vb_model_desc* m, const void* params, vb_sim** out) {
     return guard([&] {
@@ -1305,6 +1579,7 @@ int vb_sim_create(const vb_model_desc* m, const void* params, vb_sim** out) {
         if (m->param_size > vb::MAX_PARAM_BYTES) throw ArgError("parameter struct too large (MAX_PARAM_BYTES)");
         auto s = std::make_unique<vb_sim>();
         s->name = m->name;
+        s->rank = (uint32_t)g_rank;
         for (uint32_t i = 0; i < m->n_agent_types; ++i) {
             AgentStore a;
             a.name = m->agent_types[i].name; a.size = m->agent_types[i].size; a.hints = m->agent_types[i].hints;
@@ -1358,8 +1633,8 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
         };
         for (auto& a : o.agents) {
             AgentStore b = a;
-            if (a.size && a.cap) { b.state[0] = (uint8_t*)dup(a.state[0], (size_t)a.cap * a.size); b.state[1] = a.independent ? b.state[0] : (uint8_t*)dup(a.state[1], (size_t)a.cap * a.size); }
-            if (!a.immortal && a.cap) { b.died[0] = (uint8_t*)dup(a.died[0], a.cap); b.died[1] = (uint8_t*)dup(a.died[1], a.cap); b.reuse = (uint32_t*)dup(a.reuse, (size_t)a.reuse_cap * 4); }
+            if (a.size && a.cap) { b.state[0] = (uint8_t*)dup(a.state[0], (size_t)a.stride() * a.size); b.state[1] = a.independent ? b.state[0] : (uint8_t*)dup(a.state[1], (size_t)a.stride() * a.size); }
+            if (!a.immortal && a.cap) { b.died[0] = (uint8_t*)dup(a.died[0], a.stride()); b.died[1] = (uint8_t*)dup(a.died[1], a.stride()); b.ghost_ids = (uint64_t*)dup(a.ghost_ids, (size_t)a.nghost * 8); b.send_slots = (uint32_t*)dup(a.send_slots, (a.send_off.empty() ? 0 : (size_t)a.send_off.back()) * 4); b.send_buf = nullptr; b.reuse = (uint32_t*)dup(a.reuse, (size_t)a.reuse_cap * 4); }
             s->agents.push_back(b);
         }
         for (auto& e : o.edges) {
@@ -1415,7 +1690,7 @@ int vb_add_agents(vb_sim* s, int type, const void* states, uint64_t n, vb_agent_
             cudaGetLastError();
             uint8_t* tmp = dev ? (uint8_t*)states : (uint8_t*)g_pool.alloc(n * a.size);
             if (!dev) CK(cudaMemcpyAsync(tmp, states, n * a.size, cudaMemcpyHostToDevice, g_stream));
-            vbp::aos_to_soa_kernel<<<nblk(n * a.ncols), 256, 0, g_stream>>>(tmp, a.wstate(), a.cap, first - 1, n, a.size, a.word); LAUNCH_CHECK();
+            vbp::aos_to_soa_kernel<<<nblk(n * a.ncols), 256, 0, g_stream>>>(tmp, a.wstate(), a.stride(), first - 1, n, a.size, a.word); LAUNCH_CHECK();
             CK(cudaStreamSynchronize(g_stream));
             if (!dev) dfree(tmp);
         }
@@ -1604,9 +1879,10 @@ int vb_finish_init(vb_sim* s) {
             a.nslots = (uint32_t)(a.nextid - 1);
             a.cur ^= 1;
             a.write_stale = true;
-            if (!a.immortal && a.cap) CK(cudaMemsetAsync(a.rdied(), 0, a.cap, g_stream));
+            if (!a.immortal && a.cap) CK(cudaMemsetAsync(a.rdied(), 0, a.stride(), g_stream));
         }
         s->initialized = true;
+        s->build_ghosts();
         s->merge_all_pending();
         for (auto& e : s->edges) {   // every container exists after init, even if empty
             if (e.kind == vb::KIND_CSR && !e.off) { e.log_n = 0; s->build_container((int)(&e - &s->edges[0]), false); }
@@ -1636,10 +1912,17 @@ int vb_num_agents(vb_sim* s, int type, uint64_t* n_out) {
     return guard([&] {   // Agent.jl:324-343
         require_device();
         AgentStore& a = s->A(type);
-        if (a.immortal) { *n_out = a.nextid - 1; return; }
+        auto sum_ranks = [&](uint64_t local) {   // MPI.Allreduce(local_num, +): Agent.jl:338-342
+            std::vector<uint64_t> all;
+            allgather8(&local, all);
+            uint64_t t = 0;
+            for (uint64_t v : all) t += v;
+            return t;
+        };
+        if (a.immortal) { *n_out = sum_ranks(a.nextid - 1); return; }
         const uint32_t n = s->initialized ? a.nslots : (uint32_t)(a.nextid - 1);
-        if (!n) { *n_out = 0; return; }
-        if (!s->initialized) { *n_out = n; return; }
+        if (!n) { *n_out = sum_ranks(0); return; }
+        if (!s->initialized) { *n_out = sum_ranks(n); return; }
         MapArgs ma{};
         ma.cols = nullptr; ma.n = n; ma.died = a.rdied(); ma.dt = -1; ma.op = vb::OP_SUM; ma.word = 1;
         long long* part = dalloc<long long>(1024 + 1);
@@ -1650,7 +1933,7 @@ int vb_num_agents(vb_sim* s, int type, uint64_t* n_out) {
         CK(cudaMemcpyAsync(&r, part + 1024, 8, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
         dfree(part);
-        *n_out = (uint64_t)r;
+        *n_out = sum_ranks((uint64_t)r);
     });
 }
 
@@ -1674,7 +1957,7 @@ int vb_all_agents(vb_sim* s, int type, void* states_out, vb_agent_id* ids_out, u
             vbp::compact_indices_kernel<<<nblk(n), 256, 0, g_stream>>>(flag, pos, n, idx); LAUNCH_CHECK();
             if (states_out && a.size) {
                 uint8_t* tmp = (uint8_t*)g_pool.alloc((size_t)live * a.size);
-                vbp::soa_gather_aos_kernel<<<nblk((uint64_t)live * a.ncols), 256, 0, g_stream>>>(state, tmp, a.cap, idx, live, a.size, a.word); LAUNCH_CHECK();
+                vbp::soa_gather_aos_kernel<<<nblk((uint64_t)live * a.ncols), 256, 0, g_stream>>>(state, tmp, a.stride(), idx, live, a.size, a.word); LAUNCH_CHECK();
                 CK(cudaMemcpyAsync(states_out, tmp, (size_t)live * a.size, cudaMemcpyDeviceToHost, g_stream));
                 CK(cudaStreamSynchronize(g_stream));
                 dfree(tmp);
@@ -1706,7 +1989,7 @@ int vb_agentstate(vb_sim* s, vb_agent_id id, int type, void* out) {
         }
         if (!a.size) return;
         uint8_t* tmp = (uint8_t*)g_pool.alloc(a.size);
-        vbp::soa_to_aos_kernel<<<1, 64, 0, g_stream>>>(a.rstate(), tmp, a.cap, nr - 1, 1, a.size, a.word); LAUNCH_CHECK();
+        vbp::soa_to_aos_kernel<<<1, 64, 0, g_stream>>>(a.rstate(), tmp, a.stride(), nr - 1, 1, a.size, a.word); LAUNCH_CHECK();
         CK(cudaMemcpyAsync(out, tmp, a.size, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
         dfree(tmp);
@@ -1714,7 +1997,15 @@ int vb_agentstate(vb_sim* s, vb_agent_id id, int type, void* out) {
 }
 
 int vb_num_edges_total(vb_sim* s, int e, int write, uint64_t* n_out) {
-    return guard([&] { require_device(); *n_out = s->edge_total(e, write != 0); });
+    return guard([&] {   // Edge.jl:373-389 incl. the Allreduce over ranks
+        require_device();
+        const uint64_t local = s->edge_total(e, write != 0);
+        std::vector<uint64_t> all;
+        allgather8(&local, all);
+        uint64_t t = 0;
+        for (uint64_t v : all) t += v;
+        *n_out = t;
+    });
 }
 
 namespace {
@@ -1869,7 +2160,7 @@ int vb_mapreduce(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64
         ma.offset = offset; ma.dt = dt; ma.has_cmp = has_cmp; ma.cmp = cmp; ma.op = op;
         if (type_ref < vb::EDGE_REF) {
             AgentStore& a = s->A(type_ref);
-            ma.cols = a.rstate(); ma.stride = a.cap; ma.word = a.word ? a.word : 1; ma.n = a.nextid - 1; ma.died = a.immortal ? nullptr : a.rdied();
+            ma.cols = a.rstate(); ma.stride = a.stride(); ma.word = a.word ? a.word : 1; ma.n = a.nextid - 1; ma.died = a.immortal ? nullptr : a.rdied();
             if (ma.n > a.nslots) ma.n = a.nslots;
         } else {
             EdgeStore& e = s->E(type_ref - vb::EDGE_REF);
@@ -1920,7 +2211,13 @@ int vb_mapreduce(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64
             double start;
             if (init) { if (result_dt == vb::DT_F64) std::memcpy(&start, init, 8); else { float f; std::memcpy(&f, init, 4); start = f; } }
             else start = op == vb::OP_PROD ? 1.0 : op == vb::OP_MIN ? INFINITY : op == vb::OP_MAX ? -INFINITY : 0.0;
-            const double r = ma.n ? fold_f(fres, start) : start;
+            double r = ma.n ? fold_f(fres, start) : start;
+            if (g_nranks > 1) {   // MPI.Allreduce(reduced, op) in rank order (AgentMethods.jl:555-560)
+                std::vector<uint64_t> all;
+                allgather8(&r, all);
+                std::memcpy(&r, &all[0], 8);
+                for (int k = 1; k < g_nranks; ++k) { double v; std::memcpy(&v, &all[k], 8); r = fold_f(v, r); }
+            }
             if (result_dt == vb::DT_F64) std::memcpy(out, &r, 8); else { float f = (float)r; std::memcpy(out, &f, 4); }
         } else {
             long long start;
@@ -1939,7 +2236,13 @@ int vb_mapreduce(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64
                     default: start = 0; break;
                 }
             }
-            const long long r = fold_i(ires, start);
+            long long r = fold_i(ires, start);
+            if (g_nranks > 1) {
+                std::vector<uint64_t> all;
+                allgather8(&r, all);
+                r = (long long)all[0];
+                for (int k = 1; k < g_nranks; ++k) r = fold_i((long long)all[k], r);
+            }
             switch (result_dt) {
                 case vb::DT_I64: std::memcpy(out, &r, 8); break;
                 case vb::DT_I32: { int v = (int)r; std::memcpy(out, &v, 4); break; }
@@ -1960,7 +2263,7 @@ int vb_rastervalues(vb_sim* s, const char* name, int offset, int dt, void* out) 
         AgentStore& a = s->A(r.type);
         const size_t w = dt_size(dt), n = r.ids.size();
         uint8_t* tmp = (uint8_t*)g_pool.alloc(n * w);
-        field_out_kernel<<<nblk(n), 256, 0, g_stream>>>(a.rstate(), a.cap, a.word, r.cells, s->base[r.type], n, offset, (uint32_t)w, tmp); LAUNCH_CHECK();
+        field_out_kernel<<<nblk(n), 256, 0, g_stream>>>(a.rstate(), a.stride(), a.word, r.cells, s->base[r.type], n, offset, (uint32_t)w, tmp); LAUNCH_CHECK();
         CK(cudaMemcpyAsync(out, tmp, n * w, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
         dfree(tmp);

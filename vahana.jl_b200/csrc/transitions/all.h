@@ -1,4 +1,6 @@
 // all.h — every built-in single-source transition header.
 #pragma once
+#include "gol.h"
 #include "hk.h"
+#include "sir.h"
 #include "testkit.h"

@@ -18,6 +18,15 @@ VB_HD uint64_t hk_source(uint64_t seed, uint64_t k, uint64_t n) {
 }
 VB_HD double hk_opinion(uint64_t seed, uint64_t i) { return vb::Philox::uniform(seed, i, 0); }
 
+// contiguous equal blocks over nranks (src/Simulation.jl:353-367): AgentID of global agent index g
+VB_HD uint64_t hk_global_id(int type, uint64_t g, uint64_t n, uint32_t nranks) {
+    const uint64_t q = n / nranks, r = n % nranks;
+    uint64_t p, local;
+    if (g < r * (q + 1)) { p = g / (q + 1); local = g % (q + 1); }
+    else { p = r + (g - r * (q + 1)) / q; local = (g - r * (q + 1)) % q; }
+    return vb::agent_id((uint32_t)type, (uint32_t)p, local + 1);
+}
+
 // host generator (used by both libraries)
 inline int hk_powerlaw_host(uint64_t n, int agent_type, uint64_t seed_graph, uint64_t seed_opinion, double c, uint32_t dmax,
                             uint64_t* from_out, uint64_t* to_out, double* opinions_out, uint64_t* n_edges_out) {
