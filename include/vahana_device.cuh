@@ -40,7 +40,7 @@
 namespace vb {
 
 enum : int { MAX_AGENT_TYPES = 16, MAX_EDGE_TYPES = 32, MAX_RASTERS = 4, MAX_PARAM_BYTES = 512 };
-enum : int { MAX_EDGE_WRITES = 6, MAX_AGENT_WRITES = 3 };
+enum : int { MAX_EDGE_WRITES = 6, MAX_AGENT_WRITES = 3, MAX_EDGE_REMOVES = 3 };
 enum EdgeKind : uint8_t { KIND_CSR = 0, KIND_COUNT = 1, KIND_FLAG = 2 };
 enum Mode : int { MODE_DIRECT = 0, MODE_COUNT = 1, MODE_EMIT = 2 };
 enum DevError : uint32_t {
@@ -84,6 +84,8 @@ struct EdgeView {
     uint32_t* wcnt;           // KIND_COUNT / KIND_FLAG write container (rows_w entries)
     uint32_t log_cap;
     uint32_t rows_w;
+    // remove_edges! records of the running apply: (row, source composite or 0xffffffff = all, append position at call time)
+    uint32_t* rm_row; uint32_t* rm_from; uint32_t* rm_mark;
     uint32_t size, word, ncols;
     int32_t target;           // :SingleType target type id, else 0
     uint8_t hints, kind, readable, writeable;
@@ -119,6 +121,9 @@ struct LaunchArgs {
     uint32_t ebase[MAX_EDGE_WRITES];      // EMIT: log position where this call's appends start
     uint32_t* acount[MAX_AGENT_WRITES];   // COUNT: per-agent add_agent counts; EMIT: exclusive offsets
     uint32_t abase[MAX_AGENT_WRITES];     // EMIT: births of that type by earlier calls of this apply
+    uint32_t* rcount[MAX_EDGE_REMOVES];   // COUNT: per-agent remove_edges counts; EMIT: exclusive offsets into the remove log
+    uint32_t rbase[MAX_EDGE_REMOVES];     // EMIT: remove-log position where this call's records start
+    uint32_t rmark[MAX_EDGE_REMOVES];     // EMIT: append-log length of that edge type before this call (for functors that only remove)
     unsigned long long* stats;            // 1024 counters, 4 words apart: edges read (summed by the host)
     // degree binning of cooperative, write-free transitions (DESIGN.md "read phase"):
     int group;                            // lanes per agent: 0 = default (32 cooperative / 1 otherwise), 8, 32 or 256
@@ -142,6 +147,7 @@ struct TransitionInfo {
     int cooperative;
     int n_edge_writes, edge_writes[MAX_EDGE_WRITES];
     int n_agent_writes, agent_writes[MAX_AGENT_WRITES];
+    int n_edge_removes, edge_removes[MAX_EDGE_REMOVES];
     int primary_edge;         // F::kPrimaryEdge (-1 = none): enables degree binning of the read phase
     cudaError_t (*launch)(const LaunchArgs&);
 };
@@ -225,6 +231,7 @@ class Ctx {
     uint32_t lane_;
     uint32_t ecnt[F::EdgeWrites::size + 1];
     uint32_t acnt[F::AgentWrites::size + 1];
+    uint32_t rcnt[F::EdgeRemoves::size + 1];
     unsigned long long edges_read = 0;
 
     __device__ Ctx(const DeviceSim& d, const LaunchArgs& l, uint32_t s, uint32_t lane) : ds(d), la(l), slot(s), lane_(lane) {
@@ -232,6 +239,8 @@ class Ctx {
         for (int i = 0; i <= F::EdgeWrites::size; ++i) ecnt[i] = 0;
 #pragma unroll
         for (int i = 0; i <= F::AgentWrites::size; ++i) acnt[i] = 0;
+#pragma unroll
+        for (int i = 0; i <= F::EdgeRemoves::size; ++i) rcnt[i] = 0;
     }
     __device__ __forceinline__ void fail(uint32_t code) const { atomicOr(ds.error, code); }
 
@@ -452,8 +461,11 @@ class Ctx {
             trow = ds.base[tt] + (uint32_t)(tnr - 1);
         }
         if (!(ev.hints & EDGE_IGNORE_FROM) && !comp_of(from, fcomp)) { fail(DERR_BAD_ID); return; }
-        if (ev.kind == KIND_COUNT) { atomicAdd(&ev.wcnt[trow], 1u); ecnt[w] += 1; return; }   // count[to] += 1
-        if (ev.kind == KIND_FLAG) { ev.wcnt[trow] = 1u; ecnt[w] += 1; return; }
+        if (ev.kind != KIND_CSR && !ev.log_to) {                                               // order-free fast path
+            if (ev.kind == KIND_COUNT) atomicAdd(&ev.wcnt[trow], 1u); else ev.wcnt[trow] = 1u;   // count[to] += 1 / true
+            ecnt[w] += 1;
+            return;
+        }
         const uint32_t pos = la.ebase[w] + la.ecount[w][slot] + ecnt[w];
         ecnt[w] += 1;
         ev.log_to[pos] = trow;
@@ -480,6 +492,32 @@ class Ctx {
         }
         return agent_id((uint32_t)type, ds.rank, (uint64_t)s + 1);
     }
+
+    // remove_edges!(sim, to, T) / remove_edges!(sim, from, to, T)  (EdgeMethods.jl:527-599).  A record removes what is in the
+    // write container at the moment of the call: the existing entries and the appends that precede it in call order.
+    __device__ __forceinline__ void remove_edges_impl(int e, bool has_from, AgentID from, AgentID to) {
+        if (lane_ != 0) return;
+        const int r = F::EdgeRemoves::find(e);
+        if (r < 0) { fail(DERR_EDGE_NOT_DECLARED); return; }
+        if (MODE == MODE_COUNT) { rcnt[r] += 1; return; }
+        const EdgeView& ev = ds.edges[e];
+        if (has_from && (ev.hints & EDGE_IGNORE_FROM)) { fail(DERR_ACCESSOR_UNAVAILABLE); return; }   // :592-598
+        const uint32_t pos = la.rbase[r] + la.rcount[r][slot] + rcnt[r];
+        rcnt[r] += 1;
+        uint32_t row = 0xffffffffu, fcomp = 0xffffffffu;
+        const uint32_t tt = type_nr(to);
+        const uint64_t tnr = agent_nr(to);
+        if (process_nr(to) != ds.rank) fail(DERR_REMOTE);
+        else if (tt >= 1 && tt <= ds.n_agent_types && tnr >= 1 && tnr <= ds.agents[tt].lcap && (!ev.target || (int)tt == ev.target))
+            row = (ev.target ? 0u : ds.base[tt]) + (uint32_t)(tnr - 1);
+        if (has_from && !comp_of(from, fcomp)) row = 0xffffffffu;       // an id that names nobody matches no entry
+        const int w = F::EdgeWrites::find(e);
+        ev.rm_row[pos] = row;
+        ev.rm_from[pos] = has_from ? fcomp : 0xffffffffu;
+        ev.rm_mark[pos] = w >= 0 ? la.ebase[w] + la.ecount[w][slot] + ecnt[w] : la.rmark[r];
+    }
+    __device__ __forceinline__ void remove_edges(int e, AgentID to) { remove_edges_impl(e, false, 0, to); }
+    __device__ __forceinline__ void remove_edges(int e, AgentID from, AgentID to) { remove_edges_impl(e, true, from, to); }
 
     // -- raster --
     __device__ __forceinline__ AgentID cellid(int r, const Pos& p) const {
@@ -572,6 +610,8 @@ __global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__
             for (int i = 0; i < F::EdgeWrites::size; ++i) la.ecount[i][idx] = 0;
 #pragma unroll
             for (int i = 0; i < F::AgentWrites::size; ++i) la.acount[i][idx] = 0;
+#pragma unroll
+            for (int i = 0; i < F::EdgeRemoves::size; ++i) la.rcount[i][idx] = 0;
         }
         return;
     }
@@ -587,6 +627,8 @@ __global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__
         for (int i = 0; i < F::EdgeWrites::size; ++i) la.ecount[i][idx] = ctx.ecnt[i];
 #pragma unroll
         for (int i = 0; i < F::AgentWrites::size; ++i) la.acount[i][idx] = ctx.acnt[i];
+#pragma unroll
+        for (int i = 0; i < F::EdgeRemoves::size; ++i) la.rcount[i][idx] = ctx.rcnt[i];
         return;
     }
     if (la.in_write) {                                                 // transition_with_write! (:159-181)
@@ -656,6 +698,8 @@ TransitionInfo make_transition_info(const char* name, const char* agent_type) {
     for (int i = 0; i < F::EdgeWrites::size; ++i) ti.edge_writes[i] = F::EdgeWrites::at(i);
     ti.n_agent_writes = F::AgentWrites::size;
     for (int i = 0; i < F::AgentWrites::size; ++i) ti.agent_writes[i] = F::AgentWrites::at(i);
+    ti.n_edge_removes = F::EdgeRemoves::size;
+    for (int i = 0; i < F::EdgeRemoves::size; ++i) ti.edge_removes[i] = F::EdgeRemoves::at(i);
     ti.primary_edge = F::kPrimaryEdge;
     ti.launch = &launch_transition<F>;
     return ti;

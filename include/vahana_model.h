@@ -119,6 +119,7 @@ struct TransitionBase {
     static constexpr bool kCooperative = false;   // true: all lanes of a warp run the functor for one agent
     using EdgeWrites = IntList<>;                 // edge types the functor calls add_edge on
     using AgentWrites = IntList<>;                // agent types the functor calls add_agent on
+    using EdgeRemoves = IntList<>;                // edge types the functor calls remove_edges on
     static constexpr int kPrimaryEdge = -1;       // cooperative functors: the edge type whose row the functor walks;
                                                   // lets the engine bin agents by degree (sub-warp / warp / block per agent)
 };

@@ -262,6 +262,41 @@ __global__ void merge_copy_kernel(const MergeArgs a) {
                 a.st[(size_t)c * a.stride * a.word + (size_t)d * a.word + b] = a.nst[(size_t)c * a.nstride * a.word + (size_t)k * a.word + b];
     }
 }
+// remove_edges! (src/EdgeMethods.jl:527-599) applied at finish_write!: a record (row, from|ALL, P) deletes the existing entries of
+// the row (matching `from`) and the appended ones at log positions < P, i.e. what was in the write container when it was called.
+__global__ void rm_cut_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ from, const uint32_t* __restrict__ mark, uint32_t n,
+                              uint32_t* __restrict__ cutA, uint32_t* __restrict__ pairflag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool valid = row[i] != 0xffffffffu;
+    if (valid && from[i] == 0xffffffffu) atomicMax(&cutA[row[i]], mark[i] + 1u);
+    pairflag[i] = (valid && from[i] != 0xffffffffu) ? 1u : 0u;
+}
+struct RmArgs {
+    const uint32_t* cutA;                                           // per row: 0 = no remove_edges!(to), else max P + 1
+    const uint32_t* poff; const uint32_t* pfrom; const uint32_t* pmark;   // (from,to) records grouped by row (nullptr if none)
+};
+__device__ __forceinline__ bool rm_hits(const RmArgs& a, uint32_t row, uint32_t from, bool has_from, long long p) {
+    const uint32_t c = a.cutA[row];
+    if (c && p + 1 < (long long)c) return true;
+    if (a.poff && has_from)
+        for (uint32_t k = a.poff[row]; k < a.poff[row + 1]; ++k)
+            if (a.pfrom[k] == from && p < (long long)a.pmark[k]) return true;
+    return false;
+}
+__global__ void rm_filter_log_kernel(const uint32_t* __restrict__ to, const uint32_t* __restrict__ from, uint32_t n, const RmArgs a, uint32_t* __restrict__ keep) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = rm_hits(a, to[i], from ? from[i] : 0u, from != nullptr, (long long)i) ? 0u : 1u;
+}
+__global__ void rm_filter_old_count_kernel(const uint32_t* __restrict__ off, const uint32_t* __restrict__ src, uint32_t rows, const RmArgs a,
+                                           uint32_t* __restrict__ cnt) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > rows) return;
+    if (r == rows) { cnt[r] = 0; return; }
+    uint32_t keep = 0;
+    for (uint32_t k = off[r]; k < off[r + 1]; ++k) keep += rm_hits(a, (uint32_t)r, src ? src[k] : 0u, src != nullptr, -1) ? 0u : 1u;
+    cnt[r] = keep;
+}
 // dead-agent edge purge (src/AgentMethods.jl:314-358, src/EdgeMethods.jl:606-631,897-920): drop rows whose
 // target died this apply and entries whose source died; `dead` is indexed by composite agent index.
 struct PurgeArgs {
@@ -294,6 +329,23 @@ __global__ void purge_copy_kernel(const PurgeArgs a) {
                 a.nst[(size_t)c * a.nstride * a.word + (size_t)d * a.word + b] = a.st[(size_t)c * a.stride * a.word + (size_t)k * a.word + b];
         ++d;
     }
+}
+__global__ void rm_filter_old_copy_kernel(const PurgeArgs a, const RmArgs rm) {   // PurgeArgs reused: off/src/st -> noff/nsrc/nst
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.rows) return;
+    uint32_t d = a.noff[r];
+    for (uint32_t k = a.off[r]; k < a.off[r + 1]; ++k) {
+        if (rm_hits(rm, (uint32_t)r, a.src ? a.src[k] : 0u, a.src != nullptr, -1)) continue;
+        if (a.nsrc) a.nsrc[d] = a.src[k];
+        for (uint32_t c = 0; a.nst && c < a.ncols; ++c)
+            for (uint32_t b = 0; b < a.word; ++b)
+                a.nst[(size_t)c * a.nstride * a.word + (size_t)d * a.word + b] = a.st[(size_t)c * a.stride * a.word + (size_t)k * a.word + b];
+        ++d;
+    }
+}
+__global__ void rm_zero_rows_kernel(uint32_t* __restrict__ cnt, uint32_t rows, const uint32_t* __restrict__ cutA) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows && cutA[r]) cnt[r] = 0;
 }
 __global__ void purge_rows_cnt_kernel(uint32_t* __restrict__ cnt, uint32_t rows, const uint8_t* __restrict__ dead, uint32_t row_base) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,6 +605,9 @@ struct EdgeStore {
     uint32_t* log_to = nullptr; uint32_t* log_from = nullptr; uint8_t* log_st = nullptr;
     uint32_t log_n = 0, log_cap = 0;
     uint32_t* wcnt = nullptr; uint32_t rows_w = 0;
+    // remove_edges! records of the running apply
+    uint32_t* rm_row = nullptr; uint32_t* rm_from = nullptr; uint32_t* rm_mark = nullptr; uint32_t rm_n = 0, rm_cap = 0;
+    bool ordered_log = false;   // count/flag container whose appends must be ordered this apply (a transition removes edges of it)
     // raw adds from the host API (AgentIDs, AoS states) awaiting translation, in call order
     std::vector<uint64_t> h_to, h_from; std::vector<uint8_t> h_st;
     std::vector<RawChunk> chunks;
@@ -621,6 +676,7 @@ struct vb_sim {
     void merge_all_pending() { for (size_t e = 0; e < edges.size(); ++e) merge_pending((int)e); }
     void ensure_log(EdgeStore& es, uint64_t need);
     void build_container(int e, bool add_existing);
+    void apply_removes(int e);
     void purge_dead(const uint8_t* dead);
     uint64_t edge_total(int e, bool write);
 };
@@ -638,8 +694,9 @@ void free_edge_read(EdgeStore& e) {
     e.off = e.src = e.cnt = nullptr; e.st = nullptr; e.nnz = e.st_cap = 0; e.rows = 0;
 }
 void free_edge_log(EdgeStore& e) {
-    dfree(e.log_to); dfree(e.log_from); dfree(e.log_st); dfree(e.wcnt);
+    dfree(e.log_to); dfree(e.log_from); dfree(e.log_st); dfree(e.wcnt); dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark);
     e.log_to = e.log_from = e.wcnt = nullptr; e.log_st = nullptr; e.log_n = e.log_cap = 0; e.rows_w = 0;
+    e.rm_row = e.rm_from = e.rm_mark = nullptr; e.rm_n = e.rm_cap = 0;
 }
 void free_chunks(EdgeStore& e) {
     for (auto& c : e.chunks) { dfree(c.to); dfree(c.from); dfree(c.st); }
@@ -791,6 +848,7 @@ void vb_sim::upload_view(uint64_t seed) {
         vb::EdgeView& v = h.edges[i];
         v.off = e.off; v.src = e.src; v.st = e.st; v.cnt = e.cnt; v.rows = e.rows; v.st_cap = e.st_cap;
         v.log_to = e.log_to; v.log_from = e.log_from; v.log_st = e.log_st; v.wcnt = e.wcnt; v.log_cap = e.log_cap; v.rows_w = e.rows_w;
+        v.rm_row = e.rm_row; v.rm_from = e.rm_from; v.rm_mark = e.rm_mark;
         v.size = e.size; v.word = e.word ? e.word : 1; v.ncols = e.ncols; v.target = e.singletype ? e.target : 0;
         v.hints = (uint8_t)e.hints; v.kind = e.kind; v.readable = e.readable; v.writeable = e.writeable;
     }
@@ -909,12 +967,113 @@ void vb_sim::merge_pending(int ei) {
     e.raw_n = 0;
 }
 
+// remove_edges! records -> filter the append log and the existing container (which is being merged: removes require add_existing)
+void vb_sim::apply_removes(int ei) {
+    EdgeStore& e = E(ei);
+    const uint32_t nrec = e.rm_n;
+    if (!nrec) return;
+    e.rm_n = 0;
+    const uint32_t rows = rows_of(e);
+    uint32_t* cutA = dalloc<uint32_t>((size_t)rows + 2);
+    CK(cudaMemsetAsync(cutA, 0, ((size_t)rows + 2) * 4, g_stream));
+    uint32_t* pflag = dalloc<uint32_t>(nrec); uint32_t* ppos = dalloc<uint32_t>(nrec);
+    uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(std::max<uint64_t>(nrec, (uint64_t)rows + 1)));
+    rm_cut_kernel<<<nblk(nrec), 256, 0, g_stream>>>(e.rm_row, e.rm_from, e.rm_mark, nrec, cutA, pflag); LAUNCH_CHECK();
+    vbp::exclusive_scan(pflag, ppos, nrec, d_scalars, scr, g_stream); g_launches += 3;
+    uint32_t npair = 0;
+    CK(cudaMemcpyAsync(&npair, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    RmArgs rm{cutA, nullptr, nullptr, nullptr};
+    uint32_t *prow = nullptr, *pfrom = nullptr, *pmark = nullptr, *poff = nullptr, *t0 = nullptr, *t1 = nullptr, *t2 = nullptr;
+    if (npair) {   // group the (from,to) records by row: stable sort on the row, payloads from + mark
+        prow = dalloc<uint32_t>(npair); pfrom = dalloc<uint32_t>(npair); pmark = dalloc<uint32_t>(npair);
+        t0 = dalloc<uint32_t>(npair); t1 = dalloc<uint32_t>(npair); t2 = dalloc<uint32_t>(npair);
+        compact_u32_kernel<<<nblk(nrec), 256, 0, g_stream>>>(e.rm_row, pflag, ppos, nrec, prow); LAUNCH_CHECK();
+        compact_u32_kernel<<<nblk(nrec), 256, 0, g_stream>>>(e.rm_from, pflag, ppos, nrec, pfrom); LAUNCH_CHECK();
+        compact_u32_kernel<<<nblk(nrec), 256, 0, g_stream>>>(e.rm_mark, pflag, ppos, nrec, pmark); LAUNCH_CHECK();
+        uint32_t* sscr = dalloc<uint32_t>(vbp::rs_scratch_words(npair));
+        const int res = vbp::radix_sort(prow, t0, pfrom, t1, pmark, t2, 4, npair, vbp::bits_for(rows), sscr, g_stream);
+        CK(cudaGetLastError());
+        dfree(sscr);
+        if (res) { std::swap(prow, t0); std::swap(pfrom, t1); std::swap(pmark, t2); }
+        uint32_t* pc = dalloc<uint32_t>((size_t)rows + 2);
+        CK(cudaMemsetAsync(pc, 0, ((size_t)rows + 2) * 4, g_stream));
+        vbp::csr_run_counts_kernel<<<nblk(npair), 256, 0, g_stream>>>(prow, npair, pc); LAUNCH_CHECK();
+        poff = dalloc<uint32_t>((size_t)rows + 2);
+        vbp::exclusive_scan(pc, poff, (uint64_t)rows + 1, nullptr, scr, g_stream); g_launches += 3;
+        dfree(pc);
+        rm.poff = poff; rm.pfrom = pfrom; rm.pmark = pmark;
+    }
+    // --- the append log ---
+    if (e.log_n) {
+        const uint32_t n = e.log_n;
+        uint32_t* keep = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
+        uint32_t* scr2 = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+        rm_filter_log_kernel<<<nblk(n), 256, 0, g_stream>>>(e.log_to, e.has_src() ? e.log_from : nullptr, n, rm, keep); LAUNCH_CHECK();
+        vbp::exclusive_scan(keep, pos, n, d_scalars, scr2, g_stream); g_launches += 3;
+        uint32_t kept = 0;
+        CK(cudaMemcpyAsync(&kept, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (kept != n) {
+            uint32_t* nt = dalloc<uint32_t>(e.log_cap);
+            compact_u32_kernel<<<nblk(n), 256, 0, g_stream>>>(e.log_to, keep, pos, n, nt); LAUNCH_CHECK();
+            dfree(e.log_to); e.log_to = nt;
+            if (e.has_src() && e.log_from) {
+                uint32_t* nf = dalloc<uint32_t>(e.log_cap);
+                compact_u32_kernel<<<nblk(n), 256, 0, g_stream>>>(e.log_from, keep, pos, n, nf); LAUNCH_CHECK();
+                dfree(e.log_from); e.log_from = nf;
+            }
+            if (e.has_state() && e.log_st) {
+                uint8_t* ns = (uint8_t*)g_pool.alloc((size_t)e.log_cap * e.size);
+                compact_soa_kernel<<<nblk((uint64_t)n * e.ncols), 256, 0, g_stream>>>(e.log_st, e.log_cap, keep, pos, n, ns, e.log_cap, e.word, e.ncols); LAUNCH_CHECK();
+                dfree(e.log_st); e.log_st = ns;
+            }
+            e.log_n = kept;
+        }
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(keep); dfree(pos); dfree(scr2);
+    }
+    // --- the existing container ---
+    if (e.kind != vb::KIND_CSR) {
+        if (e.wcnt) { rm_zero_rows_kernel<<<nblk(std::min(rows, e.rows_w)), 256, 0, g_stream>>>(e.wcnt, std::min(rows, e.rows_w), cutA); LAUNCH_CHECK(); }
+    } else if (e.off && e.nnz) {
+        PurgeArgs pa{};
+        pa.off = e.off; pa.src = e.src; pa.st = e.st; pa.stride = e.st_cap; pa.rows = e.rows;
+        uint32_t* cnt = dalloc<uint32_t>((size_t)e.rows + 2);
+        rm_filter_old_count_kernel<<<nblk((uint64_t)e.rows + 1), 256, 0, g_stream>>>(e.off, e.src, e.rows, rm, cnt); LAUNCH_CHECK();
+        uint32_t* noff = dalloc<uint32_t>((size_t)e.rows + 2);
+        vbp::exclusive_scan(cnt, noff, (uint64_t)e.rows + 1, d_scalars, scr, g_stream); g_launches += 3;
+        uint32_t total = 0;
+        CK(cudaMemcpyAsync(&total, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (total != e.nnz) {
+            const uint32_t cap = std::max<uint32_t>(total, 1);
+            pa.noff = noff; pa.nsrc = e.has_src() ? dalloc<uint32_t>(cap) : nullptr;
+            pa.nst = e.has_state() ? (uint8_t*)g_pool.alloc((size_t)cap * e.size) : nullptr;
+            pa.nstride = cap; pa.word = e.word; pa.ncols = e.ncols;
+            rm_filter_old_copy_kernel<<<nblk(e.rows), 256, 0, g_stream>>>(pa, rm); LAUNCH_CHECK();
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(e.off); dfree(e.src); dfree(e.st); ++e.version;
+            e.off = noff; e.src = pa.nsrc; e.st = pa.nst; e.st_cap = cap; e.nnz = total;
+            noff = nullptr;
+        }
+        dfree(cnt); dfree(noff);
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(cutA); dfree(pflag); dfree(ppos); dfree(scr); dfree(prow); dfree(pfrom); dfree(pmark); dfree(poff); dfree(t0); dfree(t1); dfree(t2);
+}
+
 // finish_write! for one edge type: sorted append log (+ the existing container when add_existing) -> new
 // read container.  Per-target order = append order (stable sort), old entries first.
 void vb_sim::build_container(int ei, bool add_existing) {
     EdgeStore& e = E(ei);
     const uint32_t rows = rows_of(e);
+    apply_removes(ei);
     if (e.kind != vb::KIND_CSR) {   // count / flag containers were written in place by the transition
+        if (e.wcnt && e.log_to && e.log_n) {   // ordered path (an apply with remove_edges!): the surviving appends are counted now
+            count_adds_kernel<<<nblk(e.log_n), 256, 0, g_stream>>>(e.log_to, e.log_n, e.wcnt, e.kind == vb::KIND_FLAG); LAUNCH_CHECK();
+        }
+        dfree(e.log_to); e.log_to = nullptr; e.log_n = 0; e.log_cap = 0;
         if (!e.wcnt) { e.wcnt = dalloc<uint32_t>((size_t)rows + 1); e.rows_w = rows; CK(cudaMemsetAsync(e.wcnt, 0, ((size_t)rows + 1) * 4, g_stream)); }
         dfree(e.cnt); e.cnt = e.wcnt; e.rows = e.rows_w; e.wcnt = nullptr; e.rows_w = 0;
         return;
@@ -1288,6 +1447,13 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         for (int i = 0; i < ti->n_edge_writes; ++i)   // _can_add: EdgeMethods.jl:258-265
             if (s.asserts_enabled && s.check_readable && !contains(write, vb::EDGE_REF + ti->edge_writes[i]))
                 throw AssertionError("edge type " + s.E(ti->edge_writes[i]).name + " must be in the `write` argument of the transition function");
+        for (int i = 0; i < ti->n_edge_removes; ++i) {   // _can_remove_edges: EdgeMethods.jl:101-121
+            const int er = vb::EDGE_REF + ti->edge_removes[i];
+            if (s.asserts_enabled && s.check_readable && !contains(write, er))
+                throw AssertionError("Edge of " + s.E(ti->edge_removes[i]).name + " can not removed, as it is not in the `write` argument of the transition function");
+            if (s.asserts_enabled && s.check_readable && !contains(add_existing, er))
+                throw AssertionError(s.E(ti->edge_removes[i]).name + " must be in the `add_existing` keyword of the transition function");
+        }
         for (int i = 0; i < ti->n_agent_writes; ++i)  // add_agent!: AgentMethods.jl:71-77
             if (s.asserts_enabled && !contains(write, ti->agent_writes[i]))
                 throw AssertionError("agent type " + s.A(ti->agent_writes[i]).name + " must be in the `write` argument of the transition function");
@@ -1327,7 +1493,9 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             EdgeStore& e = s.E(w - vb::EDGE_REF);
             e.writeable = true;
             e.add_existing = contains(add_existing, w);
-            e.log_n = 0;
+            e.log_n = 0; e.rm_n = 0;
+            e.ordered_log = false;
+            for (auto* ti : tis) for (int i = 0; i < ti->n_edge_removes; ++i) if (ti->edge_removes[i] == w - vb::EDGE_REF) e.ordered_log = e.kind != vb::KIND_CSR;
             if (e.kind != vb::KIND_CSR) {
                 const uint32_t rows = s.rows_of(e);
                 dfree(e.wcnt);
@@ -1356,7 +1524,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         vb::LaunchArgs la{};
         la.ds = &s.h_ds; la.type = C; la.n = n; la.in_read = contains(read, C); la.in_write = contains(write, C);
         la.with_edge = with_edge; la.stats = s.d_stats; la.stream = g_stream;
-        const int nw = ti->n_edge_writes + ti->n_agent_writes;
+        const int nw = ti->n_edge_writes + ti->n_agent_writes + ti->n_edge_removes;
         std::vector<uint32_t*> tmp;
         if (nw > 0) {
             // count pass -> exclusive scans -> totals
@@ -1364,12 +1532,15 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             tmp.push_back(scr);
             for (int i = 0; i < ti->n_edge_writes; ++i) { la.ecount[i] = dalloc<uint32_t>(n); tmp.push_back(la.ecount[i]); }
             for (int i = 0; i < ti->n_agent_writes; ++i) { la.acount[i] = dalloc<uint32_t>(n); tmp.push_back(la.acount[i]); }
+            for (int i = 0; i < ti->n_edge_removes; ++i) { la.rcount[i] = dalloc<uint32_t>(n); tmp.push_back(la.rcount[i]); }
             s.upload_view(seed);
             la.mode = vb::MODE_COUNT;
             CK(ti->launch(la)); ++g_launches;
             for (int i = 0; i < ti->n_edge_writes; ++i) { vbp::exclusive_scan(la.ecount[i], la.ecount[i], n, s.d_scalars + i, scr, g_stream); g_launches += 3; }
             for (int i = 0; i < ti->n_agent_writes; ++i) { vbp::exclusive_scan(la.acount[i], la.acount[i], n, s.d_scalars + vb::MAX_EDGE_WRITES + i, scr, g_stream); g_launches += 3; }
-            uint32_t totals[vb::MAX_EDGE_WRITES + vb::MAX_AGENT_WRITES] = {0};
+            constexpr int RM0 = vb::MAX_EDGE_WRITES + vb::MAX_AGENT_WRITES;
+            for (int i = 0; i < ti->n_edge_removes; ++i) { vbp::exclusive_scan(la.rcount[i], la.rcount[i], n, s.d_scalars + RM0 + i, scr, g_stream); g_launches += 3; }
+            uint32_t totals[vb::MAX_EDGE_WRITES + vb::MAX_AGENT_WRITES + vb::MAX_EDGE_REMOVES] = {0};
             CK(cudaMemcpyAsync(totals, s.d_scalars, sizeof(totals), cudaMemcpyDeviceToHost, g_stream));
             CK(cudaStreamSynchronize(g_stream));
             s.check_device_error("apply! (count pass)");
@@ -1384,15 +1555,32 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             for (int i = 0; i < ti->n_edge_writes; ++i) {
                 EdgeStore& e = s.E(ti->edge_writes[i]);
                 la.ebase[i] = e.log_n;
-                if (e.kind == vb::KIND_CSR) s.ensure_log(e, (uint64_t)e.log_n + totals[i]);
+                if (e.kind == vb::KIND_CSR || e.ordered_log) s.ensure_log(e, (uint64_t)e.log_n + totals[i] + 1);
                 if (e.kind != vb::KIND_CSR && s.rows_of(e) != e.rows_w) throw CudaError("internal: count container not sized");
+            }
+            for (int i = 0; i < ti->n_edge_removes; ++i) {
+                EdgeStore& e = s.E(ti->edge_removes[i]);
+                la.rbase[i] = e.rm_n; la.rmark[i] = e.log_n;
+                const uint64_t need = (uint64_t)e.rm_n + totals[RM0 + i];
+                if (need > e.rm_cap) {
+                    const uint32_t ncap = (uint32_t)std::max<uint64_t>(need, (uint64_t)e.rm_cap * 2 + 1024);
+                    uint32_t* nr = dalloc<uint32_t>(ncap); uint32_t* nf = dalloc<uint32_t>(ncap); uint32_t* nm = dalloc<uint32_t>(ncap);
+                    if (e.rm_n) {
+                        CK(cudaMemcpyAsync(nr, e.rm_row, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+                        CK(cudaMemcpyAsync(nf, e.rm_from, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+                        CK(cudaMemcpyAsync(nm, e.rm_mark, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+                    }
+                    dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark);
+                    e.rm_row = nr; e.rm_from = nf; e.rm_mark = nm; e.rm_cap = ncap;
+                }
             }
             s.upload_view(seed);
             la.mode = vb::MODE_EMIT;
             CK(cudaEventRecord(s.evk[0], g_stream));
             CK(ti->launch(la)); ++g_launches;
             CK(cudaEventRecord(s.evk[1], g_stream));
-            for (int i = 0; i < ti->n_edge_writes; ++i) { EdgeStore& e = s.E(ti->edge_writes[i]); if (e.kind == vb::KIND_CSR) e.log_n += totals[i]; appended += totals[i]; }
+            for (int i = 0; i < ti->n_edge_writes; ++i) { EdgeStore& e = s.E(ti->edge_writes[i]); if (e.kind == vb::KIND_CSR || e.ordered_log) e.log_n += totals[i]; appended += totals[i]; }
+            for (int i = 0; i < ti->n_edge_removes; ++i) s.E(ti->edge_removes[i]).rm_n += totals[RM0 + i];
             for (int i = 0; i < ti->n_agent_writes; ++i) s.A(ti->agent_writes[i]).births += totals[vb::MAX_EDGE_WRITES + i];
         } else {
             la.mode = vb::MODE_DIRECT;
@@ -1645,6 +1833,7 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
             f.st = (uint8_t*)dup(e.st, (size_t)e.st_cap * e.size);
             f.cnt = (uint32_t*)dup(e.cnt, ((size_t)e.rows + 1) * 4);
             f.log_to = f.log_from = f.wcnt = nullptr; f.log_st = nullptr; f.log_n = f.log_cap = 0; f.rows_w = 0;
+            f.rm_row = f.rm_from = f.rm_mark = nullptr; f.rm_n = f.rm_cap = 0; f.heavy_rows = nullptr; f.heavy_n = 0; f.heavy_version = ~0ull;
             for (auto& c : e.chunks) {
                 RawChunk d; d.n = c.n;
                 d.to = (uint64_t*)dup(c.to, c.n * 8); d.from = (uint64_t*)dup(c.from, c.n * 8); d.st = (uint8_t*)dup(c.st, c.n * e.size);
@@ -1747,7 +1936,56 @@ int vb_add_edges(vb_sim* s, int ei, const vb_agent_id* from, const vb_agent_id* 
         if (e.h_to.size() >= (1u << 22)) s->flush_raw(ei);
     });
 }
-int vb_remove_edges(vb_sim*, int, vb_agent_id, vb_agent_id) { g_err = "remove_edges! outside of transitions is not implemented yet"; return VB_ERR_STATE; }
+int vb_remove_edges(vb_sim* s, int ei, vb_agent_id from, vb_agent_id to) {
+    return guard([&] {   // remove_edges! outside of transitions (init phase, or with the transition checks disabled): EdgeMethods.jl:527-599
+        require_device();
+        EdgeStore& e = s->E(ei);
+        s->mayassert(!s->initialized || s->intransition, "remove_edges! only in the initialization phase or within a transition");
+        if (from && e.ignorefrom) throw AssertionError("remove_edges! with a source agent is not defined for edgetypes with the :IgnoreFrom hint");
+        if (!s->initialized) {   // the adds are still staged on the host as AgentIDs: filter them in place
+            if (!e.chunks.empty()) throw ArgError("remove_edges! before finish_init! after a device-side bulk add is not supported");
+            size_t w = 0;
+            for (size_t i = 0; i < e.h_to.size(); ++i) {
+                const bool hit = e.h_to[i] == to && (!from || (e.has_src() && e.h_from[i] == from));
+                if (hit) continue;
+                e.h_to[w] = e.h_to[i];
+                if (e.has_src()) e.h_from[w] = e.h_from[i];
+                if (e.has_state()) std::memmove(&e.h_st[w * e.size], &e.h_st[i * e.size], e.size);
+                ++w;
+            }
+            e.raw_n -= e.h_to.size() - w;
+            e.h_to.resize(w); if (e.has_src()) e.h_from.resize(w); if (e.has_state()) e.h_st.resize(w * e.size);
+            e.single_seen.erase(to);
+            return;
+        }
+        s->merge_pending(ei);
+        const uint32_t tt = vb::type_nr(to);
+        const uint64_t tnr = vb::agent_nr(to);
+        if (tt < 1 || tt > s->agents.size() || tnr < 1 || tnr > s->agents[tt - 1].cap) return;
+        if (e.singletype && (int)tt != e.target) return;
+        uint32_t rec[3] = {(e.singletype ? 0u : s->base[tt]) + (uint32_t)(tnr - 1), 0xffffffffu, 0u};
+        if (from) {
+            const uint32_t ft = vb::type_nr(from);
+            const uint64_t fnr = vb::agent_nr(from);
+            if (ft < 1 || ft > s->agents.size() || fnr < 1 || fnr > s->agents[ft - 1].cap) return;
+            rec[1] = s->base[ft] + (uint32_t)(fnr - 1);
+        }
+        dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark);
+        e.rm_row = dalloc<uint32_t>(1); e.rm_from = dalloc<uint32_t>(1); e.rm_mark = dalloc<uint32_t>(1); e.rm_cap = 1; e.rm_n = 1;
+        CK(cudaMemcpyAsync(e.rm_row, &rec[0], 4, cudaMemcpyHostToDevice, g_stream));
+        CK(cudaMemcpyAsync(e.rm_from, &rec[1], 4, cudaMemcpyHostToDevice, g_stream));
+        CK(cudaMemcpyAsync(e.rm_mark, &rec[2], 4, cudaMemcpyHostToDevice, g_stream));
+        e.log_n = 0;
+        if (e.kind != vb::KIND_CSR && !e.wcnt) {
+            const uint32_t rows = s->rows_of(e);
+            e.wcnt = dalloc<uint32_t>((size_t)rows + 1); e.rows_w = rows;
+            CK(cudaMemsetAsync(e.wcnt, 0, ((size_t)rows + 1) * 4, g_stream));
+            if (e.cnt) CK(cudaMemcpyAsync(e.wcnt, e.cnt, (size_t)std::min(rows, e.rows) * 4, cudaMemcpyDeviceToDevice, g_stream));
+        }
+        s->build_container(ei, true);
+        CK(cudaStreamSynchronize(g_stream));
+    });
+}
 
 int vb_add_raster(vb_sim* s, const char* name, int ndims, const int64_t* dims, int type, const void* states, vb_agent_id* ids_out) {
     return guard([&] {   // add_raster!: Raster.jl:32-54

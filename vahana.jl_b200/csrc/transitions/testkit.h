@@ -98,6 +98,59 @@ template <int E> struct TouchEdge : vb::TransitionBase {
     template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const { (void)ctx.has_edge(E, id); return true; }
 };
 
+// ---- remove_edges! inside transitions (test/mpi/test_edgetypes.jl:295-449, single process) ----
+template <int E> struct RemoveOwnIfEven : vb::TransitionBase {          // :311-317
+    using State = Foo;
+    using EdgeRemoves = vb::IntList<E>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& s, vb::AgentID id) const { if (s.foo % 2 == 0) ctx.remove_edges(E, id); return true; }
+};
+template <int E> struct RemoveNeighborsIfEven : vb::TransitionBase {    // :323-330
+    using State = Foo;
+    using EdgeRemoves = vb::IntList<E>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& s, vb::AgentID id) const {
+        if (s.foo % 2 == 0) ctx.remove_edges(E, ctx.neighbor_at(E, id, 0));
+        return true;
+    }
+};
+template <int E, bool kStateful> struct RemoveAndReadd : vb::TransitionBase {   // :337-346: remove + add of the same edge keeps it
+    using State = Foo;
+    using EdgeRemoves = vb::IntList<E>;
+    using EdgeWrites = vb::IntList<E>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
+        const vb::AgentID from = ctx.neighbor_at(E, id, 0);
+        ctx.remove_edges(E, from, id);
+        if (kStateful) ctx.add_edge(E, from, id, EFoo{0}); else ctx.add_edge(E, from, id);
+        return true;
+    }
+};
+template <int E, bool kSingle> struct RemoveFirstTwoFrom : vb::TransitionBase {   // :385-392
+    using State = Foo;
+    using EdgeRemoves = vb::IntList<E>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
+        ctx.remove_edges(E, ctx.neighbor_at(E, id, 0), id);
+        if (!kSingle) ctx.remove_edges(E, ctx.neighbor_at(E, id, 1), id);
+        return true;
+    }
+};
+template <int E> struct RemoveToRandomNeighborIfEven : vb::TransitionBase {   // :399-406: remove_edges!(sim, id, nid, ET), nid = rand(neighborids)
+    using State = Foo;
+    using EdgeRemoves = vb::IntList<E>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo& s, vb::AgentID id) const {
+        if (s.foo % 2 == 0) {
+            const long long n = ctx.num_edges(E, id);
+            long long k = (long long)(ctx.uniform(0) * (double)n);
+            if (k >= n) k = n - 1;
+            ctx.remove_edges(E, id, ctx.neighbor_at(E, id, k));
+        }
+        return true;
+    }
+};
+template <int E> struct RemoveFromZero : vb::TransitionBase {            // :428-430
+    using State = Foo;
+    using EdgeRemoves = vb::IntList<E>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const { ctx.remove_edges(E, (vb::AgentID)0, id); return true; }
+};
+
 // ---- test/remove_agents.jl ----
 struct Empty {};
 struct Idx { int64_t idx; };
