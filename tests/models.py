@@ -214,3 +214,71 @@ def sir_step(sim, step):
     sim.apply("sir_tally", "Location", ["Visit"], ["Location"], seed=4 * step + 1)
     sim.apply("sir_expose", "Location", ["Location", "Visit"], ["Exposure"], seed=4 * step + 2)
     sim.apply("sir_infect", "Person", ["Person", "Exposure"], ["Person"], seed=4 * step + 3)
+
+
+ANIMAL = [("energy", "i8"), ("pos", "i8", (2,))]
+PPCELL = [("pos", "i8", (2,)), ("countdown", "i8")]
+PP_EDGES = ["Position{Predator}", "Position{Prey}", "View{Predator}", "View{Prey}", "VisiblePrey", "Die", "Eat"]
+
+
+def pp_model():
+    """docs/examples/predator.jl:50-183 (detect_stateless(true): all seven edge types become :Stateless)"""
+    old = vh.config.detect_stateless
+    vh.detect_stateless(True)
+    try:
+        t = vh.ModelTypes()
+        t.register_agenttype("Predator", ANIMAL)
+        t.register_agenttype("Prey", ANIMAL)
+        t.register_agenttype("Cell", PPCELL)
+        for e in PP_EDGES:
+            t.register_edgetype(e)
+    finally:
+        vh.detect_stateless(old)
+    t.register_param("restart", 5)
+    for sp in ("pred", "prey"):
+        t.register_param(f"{sp}_gain", 5)
+        t.register_param(f"{sp}_loss", 1)
+        t.register_param(f"{sp}_thres", 5)
+        t.register_param(f"{sp}_prob", 20)
+    return vh.create_model(t, "Predator Prey")
+
+
+def pp_sim(backend, dims=(100, 100), nprey=2000, npred=500, seed=3):
+    """init as in predator.jl:185-229 with numpy's generator in place of Julia's"""
+    rng = np.random.default_rng(seed)
+    sim = vh.create_simulation(pp_model(), backend=backend)
+    n = dims[0] * dims[1]
+    cells = np.zeros(n, dtype=np.dtype(PPCELL, align=True))
+    ii, jj = np.meshgrid(np.arange(1, dims[0] + 1), np.arange(1, dims[1] + 1), indexing="ij")
+    cells["pos"][:, 0] = ii.reshape(-1, order="F")
+    cells["pos"][:, 1] = jj.reshape(-1, order="F")
+    cells["countdown"] = np.where(rng.random(n) < 0.5, 0, rng.integers(1, 6, n))
+    sim.add_raster("raster", dims, "Cell", cells)
+    for species, count in (("Prey", nprey), ("Predator", npred)):
+        for _ in range(count):
+            pos = (int(rng.integers(1, dims[0] + 1)), int(rng.integers(1, dims[1] + 1)))
+            aid = sim.add_agent(species, (int(rng.integers(1, 11)), pos))
+            sim.move_to("raster", aid, pos, None, f"Position{{{species}}}")
+            sim.move_to("raster", aid, pos, f"View{{{species}}}", f"View{{{species}}}", distance=1, metric="manhatten")
+    sim.finish_init()
+    return sim
+
+
+def pp_step(sim, step):
+    """step!(sim), predator.jl:437-469: six applies; `seed` keys each apply's uniform table"""
+    s = 6 * step
+    sim.apply("pp_move", ["Prey"], ["Prey", "View{Prey}", "Cell"], ["Prey", "View{Prey}", "Position{Prey}"], seed=s)
+    sim.apply("pp_find_prey", ["Cell"], ["Position{Prey}", "View{Predator}"], ["VisiblePrey"], seed=s + 1)
+    sim.apply("pp_move", ["Predator"], ["Predator", "View{Predator}", "Cell", "Prey", "VisiblePrey"],
+              ["Predator", "View{Predator}", "Position{Predator}"], seed=s + 2)
+    sim.apply("pp_grow_food", "Cell", "Cell", "Cell", seed=s + 3)
+    sim.apply("pp_try_eat", ["Cell"], ["Cell", "Position{Predator}", "Position{Prey}"], ["Cell", "Die", "Eat"], seed=s + 4)
+    keep = ["Position{Predator}", "Position{Prey}", "View{Predator}", "View{Prey}"]
+    sim.apply("pp_try_reproduce", ["Predator", "Prey"], ["Predator", "Prey", "Die", "Eat"], ["Predator", "Prey"] + keep, add_existing=keep, seed=s + 5)
+
+
+def pp_globals(sim):
+    """update_globals, predator.jl:402-417"""
+    return {"predator_pop": sim.mapreduce(None, "+", "Predator", init=0), "prey_pop": sim.mapreduce(None, "+", "Prey", init=0),
+            "cells_with_food": sim.mapreduce("countdown", "+", "Cell", equals=0),
+            "predator_energy": sim.mapreduce("energy", "+", "Predator", init=0), "prey_energy": sim.mapreduce("energy", "+", "Prey", init=0)}

@@ -78,3 +78,53 @@ def test_sir_gpu_vs_oracle(oracle, cuda):
             assert np.array_equal(a[2].view("u1"), b[2].view("u1"))   # edge states bit-exact (incl. the Float32 risk)
     assert _sir_counts(g) == _sir_counts(o)
     assert _sir_counts(g)[2] > 0
+
+
+# ---- predator / prey (BASELINE config 3) ----
+from models import pp_sim, pp_step, pp_globals, PP_EDGES  # noqa: E402
+
+
+def _pp_state(sim, ncells):
+    out = {"globals": pp_globals(sim)}
+    for T in ("Predator", "Prey", "Cell"):
+        a = sim.all_agents(T)
+        out[T] = (a.tobytes(), [vh.agent_nr(x) for x in sim.all_agentids(T)])
+    return out
+
+
+def test_pp_oracle_invariants(oracle):
+    sim = pp_sim(oracle, (30, 30), 180, 45)
+    g0 = pp_globals(sim)
+    assert g0["prey_pop"] == 180 and g0["predator_pop"] == 45
+    assert sim.num_edges("Position{Prey}") == 180 and sim.num_edges("View{Prey}") == 180 * 10
+    pops = []
+    for step in range(15):
+        pp_step(sim, step)
+        g = pp_globals(sim)
+        # every living animal stands on exactly one cell and sees / is seen by five
+        assert sim.num_edges("Position{Prey}") == g["prey_pop"] and sim.num_edges("Position{Predator}") == g["predator_pop"]
+        assert sim.num_edges("View{Prey}") == 10 * g["prey_pop"] and sim.num_edges("View{Predator}") == 10 * g["predator_pop"]
+        assert sim.num_edges("Die") <= sim.num_edges("Eat")
+        pops.append((g["prey_pop"], g["predator_pop"]))
+    assert len(set(pops)) > 5          # the populations move
+
+
+@pytest.mark.gpu
+def test_pp_gpu_vs_oracle(oracle, cuda):
+    """all-integer model with births, deaths, slot reuse, seven edge types rebuilt / merged every step: bit-exact"""
+    dims = (40, 40)
+    g, o = pp_sim(cuda, dims, 320, 80), pp_sim(oracle, dims, 320, 80)
+    for step in range(12):
+        pp_step(g, step)
+        pp_step(o, step)
+        gs, os_ = _pp_state(g, dims[0] * dims[1]), _pp_state(o, dims[0] * dims[1])
+        assert gs["globals"] == os_["globals"], (step, gs["globals"], os_["globals"])
+        for T in ("Predator", "Prey", "Cell"):
+            assert gs[T] == os_[T], (step, T)
+        for e in PP_EDGES:
+            assert g.num_edges(e) == o.num_edges(e), (step, e)
+    for e, tt in (("View{Prey}", "Prey"), ("View{Prey}", "Cell"), ("Position{Predator}", "Cell"), ("Eat", "Predator")):
+        rows = max(o.num_agents(tt) * 4, 64)
+        a, b = g.export_csr(e, tt, rows), o.export_csr(e, tt, rows)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), e     # row order = insertion order, ids incl. reused slots
+    assert gs["globals"]["prey_pop"] > 0

@@ -2,5 +2,6 @@
 #pragma once
 #include "gol.h"
 #include "hk.h"
+#include "predator.h"
 #include "sir.h"
 #include "testkit.h"
