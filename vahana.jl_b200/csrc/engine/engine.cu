@@ -2333,14 +2333,15 @@ int vb_export_csr(vb_sim* s, int ei, int target_type, uint64_t* offsets, uint64_
         std::vector<uint32_t> off(nrows + 1, 0);
         if (e.kind != vb::KIND_CSR) {
             std::vector<uint32_t> c(nrows, 0);
-            const uint64_t avail_rows = rb < e.rows ? std::min<uint64_t>(nrows, e.rows - rb) : 0;
+            const uint64_t avail_rows = rb < e.rows ? std::min<uint64_t>(std::min<uint64_t>(nrows, s->A(target_type).cap), e.rows - rb) : 0;
             if (avail_rows && e.cnt) { CK(cudaMemcpyAsync(c.data(), e.cnt + rb, avail_rows * 4, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream)); }
             uint64_t run = 0;
             for (uint64_t r = 0; r < nrows; ++r) { offsets[r] = run; run += c[r]; }
             offsets[nrows] = run;
             return;
         }
-        const uint64_t avail_rows = (e.off && rb < e.rows) ? std::min<uint64_t>(nrows, e.rows - rb) : 0;
+        const uint64_t type_rows = s->A(target_type).cap;   // rows of this target type only (the composite row space continues with the next type)
+        const uint64_t avail_rows = (e.off && rb < e.rows) ? std::min<uint64_t>(std::min<uint64_t>(nrows, type_rows), e.rows - rb) : 0;
         if (avail_rows) { CK(cudaMemcpyAsync(off.data(), e.off + rb, (avail_rows + 1) * 4, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream)); }
         const uint32_t o0 = avail_rows ? off[0] : 0;
         for (uint64_t r = 0; r <= nrows; ++r) offsets[r] = r <= avail_rows ? off[r] - o0 : off[avail_rows] - o0;
