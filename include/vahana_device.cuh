@@ -41,7 +41,8 @@ namespace vb {
 
 enum : int { MAX_AGENT_TYPES = 16, MAX_EDGE_TYPES = 32, MAX_RASTERS = 4, MAX_PARAM_BYTES = 512 };
 enum : int { MAX_EDGE_WRITES = 6, MAX_AGENT_WRITES = 3, MAX_EDGE_REMOVES = 3 };
-enum EdgeKind : uint8_t { KIND_CSR = 0, KIND_COUNT = 1, KIND_FLAG = 2 };
+enum EdgeKind : uint8_t { KIND_CSR = 0, KIND_COUNT = 1, KIND_FLAG = 2, KIND_STENCIL = 3 };
+enum : int { MAX_IMPLICIT_STENCIL = 32 };
 enum Mode : int { MODE_DIRECT = 0, MODE_COUNT = 1, MODE_EMIT = 2 };
 enum DevError : uint32_t {
     DERR_EDGE_NOT_READABLE = 1, DERR_AGENT_NOT_READABLE = 2, DERR_AGENT_TYPE_MISMATCH = 4, DERR_AGENT_DIED = 8,
@@ -89,6 +90,12 @@ struct EdgeView {
     uint32_t size, word, ncols;
     int32_t target;           // :SingleType target type id, else 0
     uint8_t hints, kind, readable, writeable;
+    // KIND_STENCIL: the edges of connect_raster_neighbors! (src/Raster.jl:139-167) kept implicit: row c holds the cells
+    // c - s (wrapped or clipped) for every stencil offset s, ordered by (source linear index, s) = the reference's insertion order
+    const int8_t* st_off;     // [st_n][MAX_RASTER_DIMS] stencil offsets in _stencil_core order (src/Raster.jl:82-96)
+    int32_t st_n, st_raster;
+    uint32_t st_slot0;        // slot of raster cell 0 (cells occupy consecutive slots)
+    uint8_t st_periodic, st_reach;
 };
 struct RasterView {
     const uint32_t* cells;    // composite index of the cell agent at each position (column-major)
@@ -329,10 +336,68 @@ class Ctx {
         return ev;
     }
 
+    // -- implicit raster stencil (KIND_STENCIL) --
+    __device__ __forceinline__ bool stencil_cell(const EdgeView& ev, AgentID id, uint32_t& lin) const {
+        const RasterView& rv = ds.rasters[ev.st_raster];
+        if ((int)type_nr(id) != rv.type || process_nr(id) != ds.rank) return false;
+        const uint64_t slot = agent_nr(id) - 1;
+        uint64_t ncells = 1;
+        for (int k = 0; k < rv.ndims; ++k) ncells *= (uint64_t)rv.dims[k];
+        if (slot < ev.st_slot0 || slot - ev.st_slot0 >= ncells) return false;
+        lin = (uint32_t)(slot - ev.st_slot0);
+        return true;
+    }
+    // calls fn(source cell linear index) for the entries first, first + step, ... of row `lin`
+    template <class Fn> __device__ __forceinline__ uint32_t stencil_row(const EdgeView& ev, uint32_t lin, uint32_t first, uint32_t step, Fn&& fn) const {
+        const RasterView& rv = ds.rasters[ev.st_raster];
+        long long pos[MAX_RASTER_DIMS], stride[MAX_RASTER_DIMS];
+        bool interior = true;
+        {
+            uint32_t rest = lin; long long st = 1;
+            for (int k = 0; k < rv.ndims; ++k) {
+                pos[k] = rest % (uint32_t)rv.dims[k]; rest /= (uint32_t)rv.dims[k];
+                stride[k] = st; st *= rv.dims[k];
+                interior &= pos[k] >= ev.st_reach && pos[k] + ev.st_reach < rv.dims[k];
+            }
+        }
+        if (interior) {   // no wrap, no clip: walking the stencil backwards yields ascending source indices
+            uint32_t j = 0;
+            for (int si = ev.st_n - 1; si >= 0; --si, ++j) {
+                if (j % step != first % step || j < first) continue;
+                long long l = 0;
+                for (int k = 0; k < rv.ndims; ++k) l += (pos[k] - ev.st_off[si * MAX_RASTER_DIMS + k]) * stride[k];
+                fn((uint32_t)l);
+            }
+            return (uint32_t)ev.st_n;
+        }
+        unsigned long long key[MAX_IMPLICIT_STENCIL];
+        uint32_t n = 0;
+        for (int si = 0; si < ev.st_n; ++si) {
+            long long l = 0; bool ok = true;
+            for (int k = 0; k < rv.ndims; ++k) {
+                long long v = pos[k] - ev.st_off[si * MAX_RASTER_DIMS + k];
+                if (v < 0 || v >= rv.dims[k]) { if (!ev.st_periodic) { ok = false; break; } v %= rv.dims[k]; if (v < 0) v += rv.dims[k]; }
+                l += v * stride[k];
+            }
+            if (!ok) continue;
+            const unsigned long long kk = ((unsigned long long)l << 6) | (unsigned)si;
+            uint32_t j = n++;
+            while (j > 0 && key[j - 1] > kk) { key[j] = key[j - 1]; --j; }   // insertion sort: (source index, stencil position)
+            key[j] = kk;
+        }
+        for (uint32_t j = first; j < n; j += step) fn((uint32_t)(key[j] >> 6));
+        return n;
+    }
+
     // -- read accessors --
     __device__ __forceinline__ long long num_edges(int e, AgentID id) {
         const EdgeView& ev = rview(e);
         if (ev.hints & EDGE_SINGLE_EDGE) { fail(DERR_ACCESSOR_UNAVAILABLE); return 0; }
+        if (ev.kind == KIND_STENCIL) {
+            uint32_t lin;
+            if (!stencil_cell(ev, id, lin)) return 0;
+            return (long long)stencil_row(ev, lin, 0xffffffffu, 1, [](uint32_t) {});
+        }
         uint32_t row;
         if (!row_of(ev, id, row)) return 0;
         if (ev.kind != KIND_CSR) return ev.cnt[row];
@@ -341,6 +406,7 @@ class Ctx {
     __device__ __forceinline__ bool has_edge(int e, AgentID id) {
         const EdgeView& ev = rview(e);
         if ((ev.hints & EDGE_SINGLE_EDGE) && ev.target && ev.kind == KIND_CSR) { fail(DERR_ACCESSOR_UNAVAILABLE); return false; }
+        if (ev.kind == KIND_STENCIL) return num_edges(e, id) > 0;
         uint32_t row;
         if (!row_of(ev, id, row)) return false;
         if (ev.kind != KIND_CSR) return ev.cnt[row] != 0;
@@ -349,6 +415,14 @@ class Ctx {
     template <class Fn> __device__ __forceinline__ void for_each_neighbor(int e, AgentID id, Fn&& fn) {
         const EdgeView& ev = rview(e);
         if (ev.hints & EDGE_IGNORE_FROM) { fail(DERR_ACCESSOR_UNAVAILABLE); return; }
+        if (ev.kind == KIND_STENCIL) {
+            uint32_t lin;
+            if (!stencil_cell(ev, id, lin)) return;
+            const uint32_t t = (uint32_t)ds.rasters[ev.st_raster].type;
+            const uint32_t n = stencil_row(ev, lin, lane_, GROUP, [&](uint32_t src) { fn(agent_id(t, ds.rank, (uint64_t)ev.st_slot0 + src + 1)); });
+            if (lane_ == 0) edges_read += n;
+            return;
+        }
         uint32_t row;
         if (!row_of(ev, id, row)) return;
         const uint32_t b = ev.off[row], en = ev.off[row + 1];
@@ -358,6 +432,16 @@ class Ctx {
     __device__ __forceinline__ AgentID neighbor_at(int e, AgentID id, long long k) {
         const EdgeView& ev = rview(e);
         if (ev.hints & EDGE_IGNORE_FROM) { fail(DERR_ACCESSOR_UNAVAILABLE); return 0; }
+        if (ev.kind == KIND_STENCIL) {
+            uint32_t lin; AgentID out = 0;
+            if (stencil_cell(ev, id, lin) && k >= 0) {
+                const uint32_t t = (uint32_t)ds.rasters[ev.st_raster].type;
+                uint32_t j = 0;
+                stencil_row(ev, lin, 0, 1, [&](uint32_t src) { if ((long long)j++ == k) out = agent_id(t, ds.rank, (uint64_t)ev.st_slot0 + src + 1); });
+            }
+            if (!out) fail(DERR_INDEX);
+            return out;
+        }
         uint32_t row;
         if (!row_of(ev, id, row) || k < 0 || (uint32_t)k >= ev.off[row + 1] - ev.off[row]) { fail(DERR_INDEX); return 0; }
         return id_of(ev.src[ev.off[row] + (uint32_t)k]);
@@ -414,6 +498,16 @@ class Ctx {
         if (ev.hints & EDGE_IGNORE_FROM) { fail(DERR_ACCESSOR_UNAVAILABLE); return; }
         const AgentView& av = ds.agents[type];
         if (ds.check && !av.readable) fail(DERR_AGENT_NOT_READABLE);
+        if (ev.kind == KIND_STENCIL) {   // grid stencil: neighbour cells are adjacent slots, the loads of a warp coalesce / hit L1
+            uint32_t lin;
+            if (!stencil_cell(ev, id, lin)) return;
+            if (type != ds.rasters[ev.st_raster].type) { fail(DERR_AGENT_TYPE_MISMATCH); return; }
+            const uint8_t* __restrict__ stp = av.state_r;
+            const uint32_t capp = av.cap, s0 = ev.st_slot0;
+            const uint32_t n = stencil_row(ev, lin, lane_, GROUP, [&](uint32_t src) { fn(soa_load<A>(stp, capp, s0 + src)); });
+            if (lane_ == 0) edges_read += n;
+            return;
+        }
         uint32_t row;
         if (!row_of(ev, id, row)) return;
         const uint32_t b = __ldcs(ev.off + row), en = __ldcs(ev.off + row + 1);   // CSR is streamed once: evict-first
@@ -672,6 +766,7 @@ template <class F> struct LaunchSelect<F, true> {    // cooperative: 8 / 32 / 25
             case MODE_COUNT: return launch_one<F, MODE_COUNT, 32>(ka);
             case MODE_EMIT: return launch_one<F, MODE_EMIT, 32>(ka);
             default:
+                if (ka.la.group == 1) return launch_one<F, MODE_DIRECT, 1>(ka);
                 if (ka.la.group == 8) return launch_one<F, MODE_DIRECT, 8>(ka);
                 if (ka.la.group == 256) return launch_one<F, MODE_DIRECT, 256>(ka);
                 return launch_one<F, MODE_DIRECT, 32>(ka);

@@ -93,3 +93,34 @@ def test_move_to_dist(backend):  # test/raster.jl:305-345: 25 / 13 / 21, 4-D 81 
     assert sim.num_edges(p1, "OnPosition") == 81
     assert sim.num_edges(p2, "OnPosition") == 9
     sim.disable_transition_checks(False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,kw", [((9, 7), dict()), ((9, 7), dict(periodic=False)), ((5, 4), dict(distance=2)),
+                                      ((12, 10), dict(distance=2, metric="manhatten", periodic=False)), ((3, 3), dict())])
+def test_implicit_stencil_row_order_matches_oracle(oracle, cuda, dims, kw):
+    """The CUDA engine keeps connect_raster_neighbors! edges implicit (grid-stencil path); rows must still list the sources in
+    the reference's insertion order, including wrapped borders, clipped borders and the duplicates of tiny periodic rasters."""
+    sims = []
+    for be in (cuda, oracle):
+        sim = vh.create_simulation(raster_model(), backend=be)
+        sim.add_raster("grid", dims, "GridA", lambda p: (p, False))
+        sim.connect_raster_neighbors("grid", "GridE", **kw)
+        sim.finish_init()
+        sims.append(sim)
+    g, o = sims
+    n = dims[0] * dims[1]
+    assert g.num_edges("GridE") == o.num_edges("GridE")
+    a, b = g.export_csr("GridE", "GridA", n), o.export_csr("GridE", "GridA", n)          # host-side enumeration
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for sim in sims:                                                                       # device-side enumeration
+        sim.apply("grid_probe", "GridA", ["GridA", "GridE"], "GridA")
+    assert np.array_equal(g.all_agents("GridA")["pos"], o.all_agents("GridA")["pos"])
+    ids = g.all_agentids("GridA")
+    g.disable_transition_checks(True); o.disable_transition_checks(True)
+    for i in (0, n // 2, n - 1):
+        assert g.neighborids(int(ids[i]), "GridE") == o.neighborids(int(ids[i]), "GridE")
+    # an explicit add turns the implicit container into ordinary rows, in the same order
+    g.add_edge(int(ids[0]), int(ids[1]), "GridE"); o.add_edge(int(ids[0]), int(ids[1]), "GridE")
+    a, b = g.export_csr("GridE", "GridA", n), o.export_csr("GridE", "GridA", n)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

@@ -216,6 +216,17 @@ __global__ void compact_soa_kernel(const uint8_t* __restrict__ in, uint32_t istr
     if (!flag[i]) return;
     for (uint32_t b = 0; b < word; ++b) out[(size_t)c * ostride * word + (size_t)pos[i] * word + b] = in[(size_t)c * istride * word + (size_t)i * word + b];
 }
+// 1- and 2-byte edge states ride through the sort as a 32-bit payload (cheaper than a permutation + random gather)
+__global__ void widen_state_kernel(const uint8_t* __restrict__ in, uint32_t n, uint32_t word, uint32_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = word == 1 ? (uint32_t)in[i] : (uint32_t)reinterpret_cast<const uint16_t*>(in)[i];
+}
+__global__ void narrow_state_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t word, uint8_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (word == 1) out[i] = (uint8_t)in[i]; else reinterpret_cast<uint16_t*>(out)[i] = (uint16_t)in[i];
+}
 __global__ void gather_soa_kernel(const uint8_t* __restrict__ in, uint32_t istride, const uint32_t* __restrict__ perm, uint32_t n, uint8_t* __restrict__ out,
                                   uint32_t ostride, uint32_t word, uint32_t ncols) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -607,6 +618,9 @@ struct EdgeStore {
     uint32_t* wcnt = nullptr; uint32_t rows_w = 0;
     // remove_edges! records of the running apply
     uint32_t* rm_row = nullptr; uint32_t* rm_from = nullptr; uint32_t* rm_mark = nullptr; uint32_t rm_n = 0, rm_cap = 0;
+    // connect_raster_neighbors! kept implicit (KIND_STENCIL on device) until something needs explicit rows
+    bool implicit_stencil = false; int st_raster = -1; int st_metric = 0; double st_distance = 0; bool st_periodic = true;
+    std::vector<int8_t> st_off_host; int8_t* st_off = nullptr; int st_n = 0; int st_reach = 0; uint32_t st_slot0 = 0;
     bool ordered_log = false;   // count/flag container whose appends must be ordered this apply (a transition removes edges of it)
     // raw adds from the host API (AgentIDs, AoS states) awaiting translation, in call order
     std::vector<uint64_t> h_to, h_from; std::vector<uint8_t> h_st;
@@ -677,6 +691,10 @@ struct vb_sim {
     void ensure_log(EdgeStore& es, uint64_t need);
     void build_container(int e, bool add_existing);
     void apply_removes(int e);
+    void materialize_stencil(int e);
+    void emit_raster_edges(int e, int raster, double distance, int metric, bool periodic, const void* st);
+    std::vector<uint32_t> stencil_row_host(const EdgeStore& e, uint64_t lin) const;
+    uint64_t stencil_total(const EdgeStore& e) const;
     void purge_dead(const uint8_t* dead);
     uint64_t edge_total(int e, bool write);
 };
@@ -707,7 +725,7 @@ void free_chunks(EdgeStore& e) {
 
 vb_sim::~vb_sim() {
     for (auto& a : agents) free_agent(a);
-    for (auto& e : edges) { free_edge_read(e); free_edge_log(e); free_chunks(e); }
+    for (auto& e : edges) { free_edge_read(e); free_edge_log(e); free_chunks(e); dfree(e.st_off); dfree(e.heavy_rows); }
     for (auto& r : rasters) dfree(r.cells);
     dfree(d_error); dfree(d_scalars); dfree(d_stats);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -850,7 +868,9 @@ void vb_sim::upload_view(uint64_t seed) {
         v.log_to = e.log_to; v.log_from = e.log_from; v.log_st = e.log_st; v.wcnt = e.wcnt; v.log_cap = e.log_cap; v.rows_w = e.rows_w;
         v.rm_row = e.rm_row; v.rm_from = e.rm_from; v.rm_mark = e.rm_mark;
         v.size = e.size; v.word = e.word ? e.word : 1; v.ncols = e.ncols; v.target = e.singletype ? e.target : 0;
-        v.hints = (uint8_t)e.hints; v.kind = e.kind; v.readable = e.readable; v.writeable = e.writeable;
+        v.hints = (uint8_t)e.hints; v.kind = e.implicit_stencil ? (uint8_t)vb::KIND_STENCIL : e.kind; v.readable = e.readable; v.writeable = e.writeable;
+        v.st_off = e.st_off; v.st_n = e.st_n; v.st_raster = e.st_raster; v.st_slot0 = e.st_slot0; v.st_periodic = e.st_periodic; v.st_reach = (uint8_t)e.st_reach;
+        if (e.implicit_stencil) v.rows = 0xffffffffu;
     }
     for (size_t i = 0; i < rasters.size(); ++i) {
         vb::RasterView& v = h.rasters[i];
@@ -1085,12 +1105,17 @@ void vb_sim::build_container(int ei, bool add_existing) {
     if (n > 1) {
         const int bits = vbp::bits_for(rows);
         const bool direct = e.has_state() && e.ncols == 1 && (e.word == 4 || e.word == 8);
-        const bool via_perm = e.has_state() && !direct;
+        const bool widened = e.has_state() && e.ncols == 1 && (e.word == 1 || e.word == 2);
+        const bool via_perm = e.has_state() && !direct && !widened;
         // buffer set A = the log itself, set B = scratch of the same capacity; the sort ping-pongs between them
         uint32_t* kA = e.log_to; uint32_t* kB = dalloc<uint32_t>(e.log_cap);
         uint32_t* fA = e.log_from; uint32_t* fB = e.has_src() ? dalloc<uint32_t>(e.log_cap) : nullptr;
         void* pA = nullptr; void* pB = nullptr; int p2b = 0;
         if (direct) { p2b = (int)e.word; pA = e.log_st; pB = g_pool.alloc((size_t)e.log_cap * e.word); }
+        else if (widened) {
+            p2b = 4; pA = dalloc<uint32_t>(e.log_cap); pB = dalloc<uint32_t>(e.log_cap);
+            widen_state_kernel<<<nblk(n), 256, 0, g_stream>>>(e.log_st, n, e.word, (uint32_t*)pA); LAUNCH_CHECK();
+        }
         else if (via_perm) {
             p2b = 4; pA = dalloc<uint32_t>(e.log_cap); pB = dalloc<uint32_t>(e.log_cap);
             vbp::iota_u32_kernel<<<nblk(n), 256, 0, g_stream>>>((uint32_t*)pA, n); LAUNCH_CHECK();
@@ -1104,6 +1129,10 @@ void vb_sim::build_container(int ei, bool add_existing) {
         e.log_to = kA; e.log_from = fA;
         dfree(kB); dfree(fB);
         if (direct) { e.log_st = (uint8_t*)pA; dfree(pB); }
+        else if (widened) {
+            narrow_state_kernel<<<nblk(n), 256, 0, g_stream>>>((const uint32_t*)pA, n, e.word, e.log_st); LAUNCH_CHECK();
+            dfree(pA); dfree(pB);
+        }
         else if (via_perm) {   // gather the state columns through the sort permutation
             uint8_t* g = (uint8_t*)g_pool.alloc((size_t)e.log_cap * e.size);
             gather_soa_kernel<<<nblk((uint64_t)n * e.ncols), 256, 0, g_stream>>>(e.log_st, e.log_cap, (const uint32_t*)pA, n, g, e.log_cap, e.word, e.ncols); LAUNCH_CHECK();
@@ -1353,8 +1382,53 @@ void vb_sim::halo_exchange(int t) {
     halo_bytes += (uint64_t)a.nghost * a.size;
 }
 
+// rows of an implicit raster stencil, enumerated exactly like Ctx::stencil_row on the device
+std::vector<uint32_t> vb_sim::stencil_row_host(const EdgeStore& e, uint64_t lin) const {
+    const RasterStore& r = rasters[e.st_raster];
+    const int nd = (int)r.dims.size();
+    std::vector<int64_t> pos(nd), stride(nd);
+    uint64_t rest = lin; int64_t st = 1;
+    for (int k = 0; k < nd; ++k) { pos[k] = (int64_t)(rest % (uint64_t)r.dims[k]); rest /= (uint64_t)r.dims[k]; stride[k] = st; st *= r.dims[k]; }
+    std::vector<std::pair<uint64_t, int>> keys;
+    for (int si = 0; si < e.st_n; ++si) {
+        int64_t l = 0; bool ok = true;
+        for (int k = 0; k < nd; ++k) {
+            int64_t v = pos[k] - e.st_off_host[(size_t)si * vb::MAX_RASTER_DIMS + k];
+            if (v < 0 || v >= r.dims[k]) { if (!e.st_periodic) { ok = false; break; } v %= r.dims[k]; if (v < 0) v += r.dims[k]; }
+            l += v * stride[k];
+        }
+        if (ok) keys.push_back({(uint64_t)l, si});
+    }
+    std::sort(keys.begin(), keys.end());
+    std::vector<uint32_t> out;
+    for (auto& k : keys) out.push_back((uint32_t)k.first);
+    return out;
+}
+uint64_t vb_sim::stencil_total(const EdgeStore& e) const {
+    const RasterStore& r = rasters[e.st_raster];
+    uint64_t total = 0;
+    for (int si = 0; si < e.st_n; ++si) {
+        uint64_t c = 1;
+        for (size_t k = 0; k < r.dims.size(); ++k) {
+            const int64_t o = std::llabs((long long)e.st_off_host[(size_t)si * vb::MAX_RASTER_DIMS + k]);
+            c *= e.st_periodic ? (uint64_t)r.dims[k] : (uint64_t)std::max<int64_t>(0, r.dims[k] - o);
+        }
+        total += c;
+    }
+    return total;
+}
+void vb_sim::materialize_stencil(int ei) {
+    EdgeStore& e = E(ei);
+    if (!e.implicit_stencil) return;
+    e.implicit_stencil = false;
+    dfree(e.st_off); e.st_off = nullptr;
+    emit_raster_edges(ei, e.st_raster, e.st_distance, e.st_metric, e.st_periodic, nullptr);
+    if (initialized) merge_pending(ei);
+}
+
 uint64_t vb_sim::edge_total(int ei, bool write) {
     EdgeStore& e = E(ei);
+    if (e.implicit_stencil) return (initialized || write) ? stencil_total(e) : 0;
     // before finish_init! everything lives in the write container = raw adds (Edge.jl:376-380)
     if (!initialized) {
         if (!write) return 0;
@@ -1459,6 +1533,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 throw AssertionError("agent type " + s.A(ti->agent_writes[i]).name + " must be in the `write` argument of the transition function");
         tis.push_back(ti);
     }
+    for (int w : write) if (w >= vb::EDGE_REF) s.materialize_stencil(w - vb::EDGE_REF);
+    if (with_edge >= 0) s.materialize_stencil(with_edge);
     s.merge_all_pending();
     const unsigned long long launches0 = g_launches;
     s.intransition = true;
@@ -1589,7 +1665,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             if (ti->cooperative && ti->primary_edge >= 0 && with_edge < 0) {
                 // degree binning (north_star: sub-warp / warp per agent, block per agent for rows >= 1024 entries)
                 EdgeStore& pe = s.E(ti->primary_edge);
-                if (pe.kind == vb::KIND_CSR && pe.off && (!pe.singletype || pe.target == C)) {
+                if (pe.implicit_stencil) la.group = 1;   // grid stencil: a thread per cell, neighbour loads of a warp are adjacent
+                else if (pe.kind == vb::KIND_CSR && pe.off && (!pe.singletype || pe.target == C)) {
                     constexpr uint32_t HEAVY_MIN = 1024;
                     if (pe.heavy_version != pe.version || pe.heavy_type != C) {
                         dfree(pe.heavy_rows); pe.heavy_rows = nullptr; pe.heavy_n = 0;
@@ -1657,6 +1734,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     bool any_dead = false;
     for (auto p : died_flags) any_dead |= p != nullptr;
     if (any_dead) {
+        for (size_t e = 0; e < s.edges.size(); ++e) s.materialize_stencil((int)e);
         const uint32_t tot = s.total_slots();
         uint8_t* dead = (uint8_t*)g_pool.alloc((size_t)tot + 1);
         CK(cudaMemsetAsync(dead, 0, (size_t)tot + 1, g_stream));
@@ -1833,6 +1911,7 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
             f.st = (uint8_t*)dup(e.st, (size_t)e.st_cap * e.size);
             f.cnt = (uint32_t*)dup(e.cnt, ((size_t)e.rows + 1) * 4);
             f.log_to = f.log_from = f.wcnt = nullptr; f.log_st = nullptr; f.log_n = f.log_cap = 0; f.rows_w = 0;
+            f.st_off = (int8_t*)dup(e.st_off, e.st_off_host.size());
             f.rm_row = f.rm_from = f.rm_mark = nullptr; f.rm_n = f.rm_cap = 0; f.heavy_rows = nullptr; f.heavy_n = 0; f.heavy_version = ~0ull;
             for (auto& c : e.chunks) {
                 RawChunk d; d.n = c.n;
@@ -1894,6 +1973,7 @@ int vb_add_edges(vb_sim* s, int ei, const vb_agent_id* from, const vb_agent_id* 
         EdgeStore& e = s->E(ei);
         s->mayassert(!s->initialized || s->intransition, "add_edge! only in the initialization phase or within a transition");
         s->mayassert(!s->check_readable || !s->initialized || e.writeable, "edge type must be in the `write` argument");
+        if (e.implicit_stencil) s->materialize_stencil(ei);
         cudaPointerAttributes pa{};
         const bool dev = cudaPointerGetAttributes(&pa, to) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
         cudaGetLastError();
@@ -1942,6 +2022,7 @@ int vb_remove_edges(vb_sim* s, int ei, vb_agent_id from, vb_agent_id to) {
         EdgeStore& e = s->E(ei);
         s->mayassert(!s->initialized || s->intransition, "remove_edges! only in the initialization phase or within a transition");
         if (from && e.ignorefrom) throw AssertionError("remove_edges! with a source agent is not defined for edgetypes with the :IgnoreFrom hint");
+        s->materialize_stencil(ei);
         if (!s->initialized) {   // the adds are still staged on the host as AgentIDs: filter them in place
             if (!e.chunks.empty()) throw ArgError("remove_edges! before finish_init! after a device-side bulk add is not supported");
             size_t w = 0;
@@ -2044,33 +2125,62 @@ RasterStore& find_raster(vb_sim* s, const char* name) {
 }
 }  // namespace
 
+}  // extern "C" (re-opened below)
+// explicit generation of the raster edges (Raster.jl:139-167): for org in cells (column-major), for s in stencil: org -> shifted
+void vb_sim::emit_raster_edges(int ei, int raster, double distance, int metric, bool periodic, const void* st) {
+    RasterStore& r = rasters[raster];
+    EdgeStore& e = E(ei);
+    auto sten = stencil(metric, (int)r.dims.size(), distance);
+    const size_t n = r.ids.size();
+    std::vector<uint64_t> from, to;
+    from.reserve(std::min<size_t>(n * sten.size(), (size_t)1 << 24)); to.reserve(from.capacity());
+    std::vector<uint8_t> sts;
+    std::vector<int64_t> org(r.dims.size(), 1), sh(r.dims.size());
+    auto flush = [&] {
+        if (to.empty()) return;
+        if (e.has_state()) { sts.resize(to.size() * e.size); for (size_t i = 0; i < to.size(); ++i) std::memcpy(&sts[i * e.size], st, e.size); }
+        int rc = vb_add_edges(this, ei, from.data(), to.data(), e.has_state() ? sts.data() : nullptr, to.size());
+        if (rc != VB_OK) throw AssertionError(g_err);
+        from.clear(); to.clear();
+    };
+    for (size_t i = 0; i < n; ++i) {
+        for (auto& o : sten) {
+            for (size_t k = 0; k < org.size(); ++k) sh[k] = org[k] + o[k];
+            if (checkpos(sh, r.dims, periodic)) { from.push_back(r.ids[i]); to.push_back(r.ids[linear_index(sh, r.dims)]); }
+        }
+        if (to.size() >= ((size_t)1 << 24)) flush();
+        size_t k = 0;
+        while (k < org.size() && ++org[k] > r.dims[k]) { org[k] = 1; ++k; }
+    }
+    flush();
+}
+extern "C" {
 int vb_connect_raster_neighbors(vb_sim* s, const char* name, int ei, double distance, int metric, int periodic, const void* st) {
-    return guard([&] {   // Raster.jl:139-167: for org in cells (column-major), for s in stencil: org -> shifted
+    return guard([&] {
         RasterStore& r = find_raster(s, name);
         EdgeStore& e = s->E(ei);
+        const int ri = (int)(&r - &s->rasters[0]);
         auto sten = stencil(metric, (int)r.dims.size(), distance);
-        const size_t n = r.ids.size();
-        std::vector<uint64_t> from, to;
-        from.reserve(std::min<size_t>(n * sten.size(), (size_t)1 << 24)); to.reserve(from.capacity());
-        std::vector<uint8_t> sts;
-        std::vector<int64_t> org(r.dims.size(), 1), sh(r.dims.size());
-        auto flush = [&] {
-            if (to.empty()) return;
-            if (e.has_state()) { sts.resize(to.size() * e.size); for (size_t i = 0; i < to.size(); ++i) std::memcpy(&sts[i * e.size], st, e.size); }
-            int rc = vb_add_edges(s, ei, from.data(), to.data(), e.has_state() ? sts.data() : nullptr, to.size());
-            if (rc != VB_OK) throw AssertionError(g_err);
-            from.clear(); to.clear();
-        };
-        for (size_t i = 0; i < n; ++i) {
-            for (auto& o : sten) {
-                for (size_t k = 0; k < org.size(); ++k) sh[k] = org[k] + o[k];
-                if (checkpos(sh, r.dims, periodic)) { from.push_back(r.ids[i]); to.push_back(r.ids[linear_index(sh, r.dims)]); }
+        // Grid-stencil fast path (K7): if these are the only edges of a stateless CSR edge type over consecutively stored cells,
+        // keep them implicit — no 8N-edge list, no sort; the read phase enumerates neighbours arithmetically.
+        bool contiguous = !r.ids.empty();
+        for (size_t i = 1; i < r.ids.size() && contiguous; ++i) contiguous = r.ids[i] == r.ids[0] + i;
+        const bool eligible = !getenv("VB_NO_IMPLICIT_STENCIL") && !s->initialized && e.kind == vb::KIND_CSR && !e.has_state() && !e.singleedge &&
+                              !e.ignorefrom && e.raw_n == 0 && !e.implicit_stencil && contiguous && !sten.empty() &&
+                              sten.size() <= vb::MAX_IMPLICIT_STENCIL && (!e.singletype || e.target == r.type) && r.ids.size() < 0xffffffffull;
+        if (!eligible) { s->materialize_stencil(ei); s->emit_raster_edges(ei, ri, distance, metric, periodic != 0, st); return; }
+        e.implicit_stencil = true; e.st_raster = ri; e.st_metric = metric; e.st_distance = distance; e.st_periodic = periodic != 0;
+        e.st_n = (int)sten.size(); e.st_reach = 0; e.st_slot0 = (uint32_t)(vb::agent_nr(r.ids[0]) - 1);
+        e.st_off_host.assign(sten.size() * vb::MAX_RASTER_DIMS, 0);
+        for (size_t i = 0; i < sten.size(); ++i)
+            for (size_t k = 0; k < sten[i].size(); ++k) {
+                e.st_off_host[i * vb::MAX_RASTER_DIMS + k] = (int8_t)sten[i][k];
+                e.st_reach = std::max<int>(e.st_reach, (int)std::llabs(sten[i][k]));
             }
-            if (to.size() >= ((size_t)1 << 24)) flush();
-            size_t k = 0;
-            while (k < org.size() && ++org[k] > r.dims[k]) { org[k] = 1; ++k; }
-        }
-        flush();
+        dfree(e.st_off);
+        e.st_off = (int8_t*)g_pool.alloc(e.st_off_host.size());
+        CK(cudaMemcpyAsync(e.st_off, e.st_off_host.data(), e.st_off_host.size(), cudaMemcpyHostToDevice, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
     });
 }
 int vb_move_to(vb_sim* s, const char* name, vb_agent_id id, const int64_t* posv, int e_from, const void* s_from, int e_to, const void* s_to,
@@ -2123,7 +2233,7 @@ int vb_finish_init(vb_sim* s) {
         s->build_ghosts();
         s->merge_all_pending();
         for (auto& e : s->edges) {   // every container exists after init, even if empty
-            if (e.kind == vb::KIND_CSR && !e.off) { e.log_n = 0; s->build_container((int)(&e - &s->edges[0]), false); }
+            if (e.kind == vb::KIND_CSR && !e.off && !e.implicit_stencil) { e.log_n = 0; s->build_container((int)(&e - &s->edges[0]), false); }
             if (e.kind != vb::KIND_CSR && !e.cnt) s->build_container((int)(&e - &s->edges[0]), false);
             e.single_seen.clear();
         }
@@ -2253,6 +2363,14 @@ int64_t fetch_row(vb_sim* s, EdgeStore& e, vb_agent_id to, std::vector<uint64_t>
     const uint64_t nr = vb::agent_nr(to);
     if (tt < 1 || tt > s->agents.size() || nr < 1) throw AssertionError("invalid agent id");
     if (e.singletype) s->mayassert((int)tt == e.target, "The :SingleType hint is set and the agent has another type");
+    if (e.implicit_stencil) {
+        const RasterStore& r = s->rasters[e.st_raster];
+        if ((int)tt != r.type || nr - 1 < e.st_slot0 || nr - 1 - e.st_slot0 >= r.ids.size()) return -1;
+        auto row = s->stencil_row_host(e, nr - 1 - e.st_slot0);
+        if (row.empty()) return -1;
+        if (from && !count_only) { from->resize(row.size()); for (size_t i = 0; i < row.size(); ++i) (*from)[i] = r.ids[row[i]]; }
+        return (int64_t)row.size();
+    }
     if (e.singletype && (int)tt != e.target) return -1;
     if (nr > s->agents[tt - 1].cap) return -1;
     const uint32_t row = e.singletype ? (uint32_t)(nr - 1) : s->base[tt] + (uint32_t)(nr - 1);
@@ -2330,6 +2448,18 @@ int vb_export_csr(vb_sim* s, int ei, int target_type, uint64_t* offsets, uint64_
         s->merge_pending(ei);
         const uint32_t rb = e.singletype ? 0 : s->base[target_type];
         if (e.singletype && target_type != e.target) { for (uint64_t r = 0; r <= nrows; ++r) offsets[r] = 0; return; }
+        if (e.implicit_stencil) {
+            const RasterStore& r = s->rasters[e.st_raster];
+            uint64_t n = 0;
+            for (uint64_t row = 0; row < nrows; ++row) {
+                offsets[row] = n;
+                if (target_type != r.type || row < e.st_slot0 || row - e.st_slot0 >= r.ids.size()) continue;
+                auto src = s->stencil_row_host(e, row - e.st_slot0);
+                for (uint32_t c : src) { if (from_out && n < cap) from_out[n] = r.ids[c]; ++n; }
+            }
+            offsets[nrows] = n;
+            return;
+        }
         std::vector<uint32_t> off(nrows + 1, 0);
         if (e.kind != vb::KIND_CSR) {
             std::vector<uint32_t> c(nrows, 0);
@@ -2517,6 +2647,14 @@ int vb_calc_raster_num_edges(vb_sim* s, const char* name, int ei, int64_t* out) 
         avail(!e.singleedge, "num_edges");
         s->merge_pending(ei);
         const size_t n = r.ids.size();
+        if (e.implicit_stencil) {
+            for (size_t i = 0; i < n; ++i) {
+                const uint64_t slot = vb::agent_nr(r.ids[i]) - 1;
+                const RasterStore& er = s->rasters[e.st_raster];
+                out[i] = (r.type == er.type && slot >= e.st_slot0 && slot - e.st_slot0 < er.ids.size()) ? (int64_t)s->stencil_row_host(e, slot - e.st_slot0).size() : 0;
+            }
+            return;
+        }
         long long* tmp = dalloc<long long>(n);
         const uint32_t shift = e.singletype ? s->base[e.target] : 0;
         if (e.singletype && e.target != r.type) { std::memset(out, 0, n * 8); dfree(tmp); return; }

@@ -114,52 +114,71 @@ inline void exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32
 // ---- stable LSD radix sort, 8-bit digits, u32 keys, up to two payload arrays (4 B and 4/8 B) -----------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                         // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 4096 keys per block
+constexpr int RS_ITEMS = 8;                          // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 2048 keys per block
 constexpr int RS_SEG = RS_TILE / RS_WARPS;           // contiguous keys per warp
 
 static __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t* __restrict__ hist,
-                                                           uint32_t nblocks) {
+                                                                  uint32_t nblocks) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
     const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
+#pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const uint64_t k = base + (uint64_t)i * RS_THREADS + threadIdx.x;
-        if (k < n) atomicAdd(&h[(keys[k] >> shift) & 255u], 1u);
+        if (k < n) atomicAdd(&h[(__ldcs(keys + k) >> shift) & 255u], 1u);
     }
     __syncthreads();
     hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-template <class P1, class P2>   // payload word types; use uint8_t-sized tag `NoPayload` for absent
+struct NoPayload { uint8_t x; };
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ uint64_t ld_stream(const uint64_t* p) { return (uint64_t)__ldcs(reinterpret_cast<const unsigned long long*>(p)); }
+__device__ __forceinline__ NoPayload ld_stream(const NoPayload* p) { return *p; }
+
+template <class P1, class P2>   // payload word types; NoPayload for absent
 struct RsArgs {
     const uint32_t* kin; uint32_t* kout;
     const P1* p1in; P1* p1out;
     const P2* p2in; P2* p2out;
     uint64_t n; int shift; const uint32_t* hist; uint32_t nblocks;
 };
-struct NoPayload { uint8_t x; };
-
+// One pass of the stable LSD sort for one tile: all loads are issued up front, ranks come from warp-private digit
+// counters (match.any), key and payloads are staged together in shared memory in tile-sorted order and written out
+// as coalesced digit runs.  4 blocks per SM (<= 64 registers, 45 KB smem).
 template <class P1, class P2, bool HAS1, bool HAS2>
-static __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const RsArgs<P1, P2> a) {
+static __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const RsArgs<P1, P2> a) {
     __shared__ uint32_t wh[RS_WARPS][256];
     __shared__ uint32_t dstart[256];
     __shared__ uint32_t gbase[256];
-    __shared__ __align__(16) uint8_t stage[RS_TILE * 8];
+    __shared__ uint32_t skey[RS_TILE];
+    __shared__ P1 sp1[HAS1 ? RS_TILE : 1];
+    __shared__ P2 sp2[HAS2 ? RS_TILE : 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
-    __syncthreads();
     const uint64_t tile0 = (uint64_t)blockIdx.x * RS_TILE;
     const uint32_t count = (uint32_t)((a.n - tile0) < (uint64_t)RS_TILE ? (a.n - tile0) : (uint64_t)RS_TILE);
-    uint32_t key[RS_ITEMS], pos[RS_ITEMS];
-    // phase 1: per-warp stable ranks (warp w owns the contiguous segment [w*RS_SEG, (w+1)*RS_SEG) of the tile)
+    uint32_t key[RS_ITEMS];
+    P1 v1[HAS1 ? RS_ITEMS : 1];
+    P2 v2[HAS2 ? RS_ITEMS : 1];
+    // warp w owns the contiguous segment [w*RS_SEG, (w+1)*RS_SEG) of the tile; round r covers 32 consecutive keys
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const uint32_t li = w * RS_SEG + r * 32 + lane;
         const bool valid = li < count;
-        key[r] = valid ? a.kin[tile0 + li] : 0xffffffffu;
+        key[r] = valid ? __ldcs(a.kin + tile0 + li) : 0xffffffffu;
+        if (HAS1) v1[r] = valid ? ld_stream(a.p1in + tile0 + li) : P1();
+        if (HAS2) v2[r] = valid ? ld_stream(a.p2in + tile0 + li) : P2();
+    }
+    __syncthreads();
+    // phase 1: stable rank of every key among the keys of its digit inside the warp segment
+    uint32_t pos[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t li = w * RS_SEG + r * 32 + lane;
+        const bool valid = li < count;
         const uint32_t d = valid ? ((key[r] >> a.shift) & 255u) : 256u;
         const uint32_t m = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(m) - 1;
@@ -183,59 +202,30 @@ static __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const RsA
         gbase[d] = a.hist[(uint64_t)d * a.nblocks + blockIdx.x];
     }
     __syncthreads();
+    // phase 3: stage key + payloads in tile-sorted order
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const uint32_t li = w * RS_SEG + r * 32 + lane;
-        if (li < count) { const uint32_t d = (key[r] >> a.shift) & 255u; pos[r] += dstart[d] + wh[w][d]; }
-    }
-    // phase 3: stage keys in tile-sorted order, then write each digit run coalesced
-    uint32_t* skey = reinterpret_cast<uint32_t*>(stage);
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
-        const uint32_t li = w * RS_SEG + r * 32 + lane;
-        if (li < count) skey[pos[r]] = key[r];
+        if (li < count) {
+            const uint32_t d = (key[r] >> a.shift) & 255u;
+            const uint32_t p = pos[r] + dstart[d] + wh[w][d];
+            skey[p] = key[r];
+            if (HAS1) sp1[p] = v1[r];
+            if (HAS2) sp2[p] = v2[r];
+        }
     }
     __syncthreads();
-    // destination of sorted tile element i (kept in registers for the payload rounds)
-    uint32_t dst[RS_ITEMS];   // positions < n < 2^32 (CSR positions are 32-bit)
+    // phase 4: element i of the sorted tile goes to gbase[digit] + (i - dstart[digit]): consecutive threads write consecutive addresses
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const uint32_t i = r * RS_THREADS + threadIdx.x;
         if (i < count) {
             const uint32_t k = skey[i];
             const uint32_t d = (k >> a.shift) & 255u;
-            dst[r] = gbase[d] + (i - dstart[d]);
-            a.kout[dst[r]] = k;
-        }
-    }
-    if (HAS1) {
-        __syncthreads();
-        P1* s1 = reinterpret_cast<P1*>(stage);
-#pragma unroll
-        for (int r = 0; r < RS_ITEMS; ++r) {
-            const uint32_t li = w * RS_SEG + r * 32 + lane;
-            if (li < count) s1[pos[r]] = a.p1in[tile0 + li];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < RS_ITEMS; ++r) {
-            const uint32_t i = r * RS_THREADS + threadIdx.x;
-            if (i < count) a.p1out[dst[r]] = s1[i];
-        }
-    }
-    if (HAS2) {
-        __syncthreads();
-        P2* s2 = reinterpret_cast<P2*>(stage);
-#pragma unroll
-        for (int r = 0; r < RS_ITEMS; ++r) {
-            const uint32_t li = w * RS_SEG + r * 32 + lane;
-            if (li < count) s2[pos[r]] = a.p2in[tile0 + li];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < RS_ITEMS; ++r) {
-            const uint32_t i = r * RS_THREADS + threadIdx.x;
-            if (i < count) a.p2out[dst[r]] = s2[i];
+            const uint32_t dst = gbase[d] + (i - dstart[d]);
+            a.kout[dst] = k;
+            if (HAS1) a.p1out[dst] = sp1[i];
+            if (HAS2) a.p2out[dst] = sp2[i];
         }
     }
 }

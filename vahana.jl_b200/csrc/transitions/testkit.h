@@ -229,6 +229,19 @@ template <class G, int T> struct Diffuse : vb::TransitionBase {
         return true;
     }
 };
+// probes the per-target row order of a raster edge type: pos := (nr of the k-th neighbour, row length), k = (x + y) mod length
+struct GridProbe : vb::TransitionBase {
+    using State = GridA;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, GridA& a, vb::AgentID id) const {
+        const int64_t n = ctx.num_edges(0, id);
+        if (n > 0) {
+            const vb::AgentID nb = ctx.neighbor_at(0, id, (a.pos[0] + a.pos[1]) % n);
+            a.pos[0] = (int64_t)vb::agent_nr(nb);
+        }
+        a.pos[1] = n;
+        return true;
+    }
+};
 struct SumOnPos : vb::TransitionBase {   // :243-250 (Val{Position} form)
     using State = Position;
     template <class Ctx> VB_HD bool operator()(Ctx& ctx, Position& p, vb::AgentID id) const {
