@@ -76,6 +76,7 @@ int vb_set_stream(void* cuda_stream);         /* run on the caller's CUDA stream
 int vb_comm_unique_id(uint8_t id_out[128]);
 int vb_comm_init(int rank, int nranks, const uint8_t id[128]);
 int vb_comm_rank(int* rank_out, int* nranks_out);
+int vb_set_uniform_offset(vb_sim* sim, int type, uint64_t offset); /* global row of this rank's first agent in the per-agent uniform table */
 int vb_halo_bytes(vb_sim* sim, uint64_t* bytes_out); /* bytes this rank received in the halo exchanges of the last apply */
 
 /* ---- lifecycle: create_simulation / copy_simulation / finish_simulation!

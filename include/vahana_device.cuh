@@ -69,6 +69,7 @@ struct AgentView {
     uint32_t next0;           // first never-used slot (= nextid - 1) before this call's births
     uint32_t size, word, ncols;
     uint8_t immortal, independent, readable, writeable;
+    uint64_t uoffset;         // row offset of this rank's agents in the global per-agent uniform table (multi-GPU)
 };
 struct EdgeView {
     // read container
@@ -85,6 +86,9 @@ struct EdgeView {
     uint32_t* wcnt;           // KIND_COUNT / KIND_FLAG write container (rows_w entries)
     uint32_t log_cap;
     uint32_t rows_w;
+    // multi-GPU: appended edges whose target lives on another rank (or whose source is a remote agent this rank does not mirror
+    // yet) travel as AgentIDs: the `storage` of the reference (src/EdgeMethods.jl:396-398), exchanged after the transition
+    uint64_t* rlog_to; uint64_t* rlog_from; uint8_t* rlog_st; uint32_t* rlog_dst; uint32_t rlog_cap;
     // remove_edges! records of the running apply: (row, source composite or 0xffffffff = all, append position at call time)
     uint32_t* rm_row; uint32_t* rm_from; uint32_t* rm_mark;
     uint32_t size, word, ncols;
@@ -109,7 +113,7 @@ struct DeviceSim {
     RasterView rasters[MAX_RASTERS];
     uint32_t base[MAX_AGENT_TYPES + 2];      // composite base per type id; base[ntypes + 1] = total
     uint32_t n_agent_types, n_edge_types, n_rasters;
-    uint32_t rank;
+    uint32_t rank, nranks;
     uint32_t check;                           // asserts_enabled && check_readable
     uint32_t* error;                          // device word, OR of DevError bits
     uint64_t seed;
@@ -126,6 +130,8 @@ struct LaunchArgs {
     int with_edge;            // -1 or edge type: only agents with an edge of this type are called
     uint32_t* ecount[MAX_EDGE_WRITES];    // COUNT: per-agent add_edge counts; EMIT: exclusive offsets into the log
     uint32_t ebase[MAX_EDGE_WRITES];      // EMIT: log position where this call's appends start
+    uint32_t* ercount[MAX_EDGE_WRITES];   // multi-GPU: the same for edges that leave the rank (nullptr on one rank)
+    uint32_t erbase[MAX_EDGE_WRITES];
     uint32_t* acount[MAX_AGENT_WRITES];   // COUNT: per-agent add_agent counts; EMIT: exclusive offsets
     uint32_t abase[MAX_AGENT_WRITES];     // EMIT: births of that type by earlier calls of this apply
     uint32_t* rcount[MAX_EDGE_REMOVES];   // COUNT: per-agent remove_edges counts; EMIT: exclusive offsets into the remove log
@@ -237,13 +243,14 @@ class Ctx {
     uint32_t slot;       // slot of the called agent
     uint32_t lane_;
     uint32_t ecnt[F::EdgeWrites::size + 1];
+    uint32_t ercnt[F::EdgeWrites::size + 1];   // appended edges that leave the rank
     uint32_t acnt[F::AgentWrites::size + 1];
     uint32_t rcnt[F::EdgeRemoves::size + 1];
     unsigned long long edges_read = 0;
 
     __device__ Ctx(const DeviceSim& d, const LaunchArgs& l, uint32_t s, uint32_t lane) : ds(d), la(l), slot(s), lane_(lane) {
 #pragma unroll
-        for (int i = 0; i <= F::EdgeWrites::size; ++i) ecnt[i] = 0;
+        for (int i = 0; i <= F::EdgeWrites::size; ++i) { ecnt[i] = 0; ercnt[i] = 0; }
 #pragma unroll
         for (int i = 0; i <= F::AgentWrites::size; ++i) acnt[i] = 0;
 #pragma unroll
@@ -252,7 +259,7 @@ class Ctx {
     __device__ __forceinline__ void fail(uint32_t code) const { atomicOr(ds.error, code); }
 
     template <class P> __device__ __forceinline__ const P& param() const { return *reinterpret_cast<const P*>(ds.params); }
-    __device__ __forceinline__ double uniform(int k) const { return Philox::uniform(ds.seed, slot, (uint64_t)k); }
+    __device__ __forceinline__ double uniform(int k) const { return Philox::uniform(ds.seed, ds.agents[la.type].uoffset + slot, (uint64_t)k); }
     __device__ __forceinline__ int lanes() const { return GROUP; }
     __device__ __forceinline__ int lane() const { return (int)lane_; }
     __device__ __forceinline__ bool leader() const { return lane_ == 0; }
@@ -541,12 +548,28 @@ class Ctx {
         const int w = F::EdgeWrites::find(e);
         if (w < 0) { fail(DERR_EDGE_NOT_DECLARED); return; }
         const EdgeView& ev = ds.edges[e];
-        if (MODE == MODE_COUNT) { ecnt[w] += 1; return; }
         uint32_t trow, fcomp = 0;
         const uint32_t tt = type_nr(to);
         const uint64_t tnr = agent_nr(to);
+        if (ds.nranks > 1) {
+            // the edge travels as AgentIDs if its target lives on another rank, or if its source is a remote agent that is not
+            // mirrored here yet (the receiver — possibly this rank — registers the ghost before translating)
+            const bool away = process_nr(to) != ds.rank ||
+                              (!(ev.hints & EDGE_IGNORE_FROM) && process_nr(from) != ds.rank && !comp_of(from, fcomp));
+            if (away) {
+                if (MODE == MODE_COUNT) { ercnt[w] += 1; return; }
+                const uint32_t pos = la.erbase[w] + la.ercount[w][slot] + ercnt[w];
+                ercnt[w] += 1;
+                ev.rlog_to[pos] = to;
+                if (ev.rlog_from) ev.rlog_from[pos] = from;
+                ev.rlog_dst[pos] = process_nr(to);
+                if (st && ev.rlog_st) soa_store<S>(ev.rlog_st, ev.rlog_cap, pos, *st);
+                return;
+            }
+        }
+        if (MODE == MODE_COUNT) { ecnt[w] += 1; return; }
         if (tt < 1 || tt > ds.n_agent_types || tnr < 1) { fail(DERR_BAD_ID); return; }
-        if (process_nr(to) != ds.rank) { fail(DERR_REMOTE); return; }   // appending to a remote target needs the edge redistribution step
+        if (process_nr(to) != ds.rank) { fail(DERR_REMOTE); return; }
         if (tnr > ds.agents[tt].lcap) { fail(DERR_BAD_ID); return; }
         if (ev.target) {
             if ((int)tt != ev.target) { fail(DERR_SINGLETYPE_MISMATCH); return; }
@@ -701,7 +724,7 @@ __global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__
     if (skip) {
         if (lane == 0 && MODE == MODE_COUNT) {
 #pragma unroll
-            for (int i = 0; i < F::EdgeWrites::size; ++i) la.ecount[i][idx] = 0;
+            for (int i = 0; i < F::EdgeWrites::size; ++i) { la.ecount[i][idx] = 0; if (la.ercount[i]) la.ercount[i][idx] = 0; }
 #pragma unroll
             for (int i = 0; i < F::AgentWrites::size; ++i) la.acount[i][idx] = 0;
 #pragma unroll
@@ -718,7 +741,7 @@ __global__ void __launch_bounds__(256) transition_kernel(const __grid_constant__
     if (lane != 0) return;
     if (MODE == MODE_COUNT) {
 #pragma unroll
-        for (int i = 0; i < F::EdgeWrites::size; ++i) la.ecount[i][idx] = ctx.ecnt[i];
+        for (int i = 0; i < F::EdgeWrites::size; ++i) { la.ecount[i][idx] = ctx.ecnt[i]; if (la.ercount[i]) la.ercount[i][idx] = ctx.ercnt[i]; }
 #pragma unroll
         for (int i = 0; i < F::AgentWrites::size; ++i) la.acount[i][idx] = ctx.acnt[i];
 #pragma unroll

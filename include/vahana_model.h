@@ -101,6 +101,16 @@ VB_HD uint32_t soa_word(uint32_t size) {
     return w;
 }
 
+// AgentID of the g-th agent (0-based, global) of a type whose n agents are spread over nranks in contiguous equal blocks
+// (_create_equal_partition, src/Simulation.jl:353-367): larger blocks first, nr counts from 1 inside the owner's block.
+VB_HD AgentID block_partition_id(uint32_t type, uint64_t g, uint64_t n, uint32_t nranks) {
+    const uint64_t q = n / nranks, r = n % nranks;
+    uint64_t p, local;
+    if (g < r * (q + 1)) { p = g / (q + 1); local = g % (q + 1); }
+    else { p = r + (g - r * (q + 1)) / q; local = (g - r * (q + 1)) % q; }
+    return agent_id(type, (uint32_t)p, local + 1);
+}
+
 // Compile-time list of type ids: a transition declares the edge / agent types it appends to.
 template <int... Is> struct IntList {
     static constexpr int size = sizeof...(Is);

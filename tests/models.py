@@ -195,6 +195,7 @@ def sir_model():
     t.register_param("n_locations", 1)
     t.register_param("visits_per_step", 2)
     t.register_param("infectious_days", 10)
+    t.register_param("n_ranks", 1)
     return vh.create_model(t, "SIR")
 
 

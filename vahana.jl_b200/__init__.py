@@ -103,7 +103,7 @@ ABI_SYMBOLS = [
     "vb_cellid", "vb_finish_init", "vb_apply", "vb_has_transition", "vb_load_model_library", "vb_num_agents",
     "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce",
     "vb_rastervalues", "vb_calc_raster_num_edges", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
-    "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes",
+    "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes", "vb_set_uniform_offset",
 ]
 
 
@@ -390,6 +390,10 @@ class Simulation:
         self._params[name] = value
         self._ck(self.lib.vb_set_param(self.h, self._params.tobytes(), C.c_uint32(self._params.nbytes)))
         return self
+
+    def set_uniform_offset(self, type_name: str, offset: int):
+        """multi-GPU: global index of this rank's first agent of the type (keys ctx.uniform like a single-rank run)"""
+        self._ck(self.lib.vb_set_uniform_offset(self.h, C.c_int(self._aid[type_name]), C.c_uint64(int(offset))))
 
     def disable_transition_checks(self, disable: bool):
         self._ck(self.lib.vb_disable_transition_checks(self.h, C.c_int(int(disable))))

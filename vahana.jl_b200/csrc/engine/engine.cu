@@ -89,6 +89,8 @@ int g_rank = 0, g_nranks = 1;
         if (_r != ncclSuccess) throw CudaError(std::string(#expr) + ": " + g_nccl.GetErrorString(_r));           \
     } while (0)
 
+void allgather8_host(const void* mine, std::vector<uint64_t>& all);
+
 void require_device() {
     if (g_device < 0) throw CudaError("vahana_b200: vb_init() has not been called or no CUDA device is available (no CPU fallback)");
 }
@@ -407,6 +409,20 @@ __global__ void halo_pack_kernel(const uint8_t* __restrict__ cols, uint32_t stri
     else if (word == 4) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
     else for (uint32_t b = 0; b < word; ++b) dp[b] = sp[b];
 }
+__global__ void gather_u64_kernel(const uint64_t* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t n, uint64_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+__global__ void gather_soa_to_aos_kernel(const uint8_t* __restrict__ cols, uint32_t stride, const uint32_t* __restrict__ perm, uint32_t n, uint8_t* __restrict__ aos,
+                                         uint32_t size, uint32_t word) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ncols = size / word;
+    if (t >= (uint64_t)n * ncols) return;
+    const uint32_t i = (uint32_t)(t / ncols), c = (uint32_t)(t % ncols);
+    const uint8_t* sp = cols + (size_t)c * stride * word + (size_t)perm[i] * word;
+    uint8_t* dp = aos + (size_t)i * size + (size_t)c * word;
+    for (uint32_t b = 0; b < word; ++b) dp[b] = sp[b];
+}
 __global__ void heavy_flags_kernel(const uint32_t* __restrict__ off, uint32_t row0, uint32_t n, uint32_t rows, uint32_t heavy_min, uint32_t* __restrict__ flag) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -418,14 +434,38 @@ __global__ void mark_dead_kernel(const uint32_t* __restrict__ flag, uint32_t n, 
     if (i < n && flag[i]) dead[base + i] = 1;
 }
 // composite index rebase after an agent type's capacity grew (bases of later types shift)
-struct RebaseArgs { uint32_t old_base[vb::MAX_AGENT_TYPES + 2]; uint32_t new_base[vb::MAX_AGENT_TYPES + 2]; uint32_t ntypes; };
+struct RebaseArgs {
+    uint32_t old_base[vb::MAX_AGENT_TYPES + 2]; uint32_t new_base[vb::MAX_AGENT_TYPES + 2]; uint32_t ntypes;
+    // ghost slots sit behind the local capacity: they move when the local capacity grows and are renumbered (remap) when
+    // the sorted ghost table of a type gains entries
+    uint32_t old_lcap[vb::MAX_AGENT_TYPES + 1]; uint32_t new_lcap[vb::MAX_AGENT_TYPES + 1]; const uint32_t* remap[vb::MAX_AGENT_TYPES + 1];
+};
 __global__ void rebase_values_kernel(uint32_t* __restrict__ v, uint64_t n, const RebaseArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = v[i];
     uint32_t t = 1;
     while (t < a.ntypes && c >= a.old_base[t + 1]) ++t;
-    v[i] = c - a.old_base[t] + a.new_base[t];
+    uint32_t slot = c - a.old_base[t];
+    if (slot >= a.old_lcap[t]) {
+        uint32_t g = slot - a.old_lcap[t];
+        if (a.remap[t]) g = a.remap[t][g];
+        slot = a.new_lcap[t] + g;
+    }
+    v[i] = a.new_base[t] + slot;
+}
+__global__ void ghost_remap_kernel(const uint64_t* __restrict__ old_ids, uint32_t n_old, const uint64_t* __restrict__ new_ids, uint32_t n_new,
+                                   uint32_t* __restrict__ remap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_old) return;
+    const uint64_t id = old_ids[i];
+    uint32_t lo = 0, hi = n_new;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (new_ids[mid] < id) lo = mid + 1; else hi = mid; }
+    remap[i] = lo;
+}
+__global__ void split64_kernel(const uint64_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ lo, uint32_t* __restrict__ hi, uint64_t out0) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { lo[out0 + i] = (uint32_t)in[i]; hi[out0 + i] = (uint32_t)(in[i] >> 32); }
 }
 __global__ void rebase_rows_kernel(const uint32_t* __restrict__ ooff, uint32_t orows, uint32_t* __restrict__ noff, uint32_t nrows, const RebaseArgs a) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -584,6 +624,7 @@ struct AgentStore {
     bool writeable = false, prepared = false;
     int64_t last_change = 0;
     uint32_t births = 0;         // births of the running apply
+    uint64_t uoffset = 0;        // offset of this rank's block in the global per-agent uniform table
     // multi-GPU: ghost segment [cap, cap + nghost) mirrors remote agents referenced by local edges
     uint32_t gcap = 0, nghost = 0;
     uint64_t* ghost_ids = nullptr;            // device, ascending (rank-major)
@@ -621,6 +662,8 @@ struct EdgeStore {
     // connect_raster_neighbors! kept implicit (KIND_STENCIL on device) until something needs explicit rows
     bool implicit_stencil = false; int st_raster = -1; int st_metric = 0; double st_distance = 0; bool st_periodic = true;
     std::vector<int8_t> st_off_host; int8_t* st_off = nullptr; int st_n = 0; int st_reach = 0; uint32_t st_slot0 = 0;
+    // multi-GPU: appended edges that leave the rank (AgentIDs), exchanged by transmit_edges
+    uint64_t* rlog_to = nullptr; uint64_t* rlog_from = nullptr; uint8_t* rlog_st = nullptr; uint32_t* rlog_dst = nullptr; uint32_t rlog_n = 0, rlog_cap = 0;
     bool ordered_log = false;   // count/flag container whose appends must be ordered this apply (a transition removes edges of it)
     // raw adds from the host API (AgentIDs, AoS states) awaiting translation, in call order
     std::vector<uint64_t> h_to, h_from; std::vector<uint8_t> h_st;
@@ -678,11 +721,13 @@ struct vb_sim {
 
     ~vb_sim();
     void compute_bases(uint32_t* out) const;
-    void ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need = 0);
-    void build_ghosts();
+    void ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need = 0, bool do_rebase = true);
+    void build_ghosts(const uint64_t* const* extra = nullptr, const uint64_t* extra_n = nullptr, int n_extra = 0);
     void halo_exchange(int t);
     uint64_t halo_bytes = 0;   // bytes received by the last apply's halo exchanges
-    void rebase(const uint32_t* old_base);
+    void rebase(const uint32_t* old_base, const uint32_t* old_lcap = nullptr, const uint32_t* const* remap = nullptr);
+    void exchange_ghost_requests();
+    void transmit_edges(int e);
     void upload_view(uint64_t seed);
     void check_device_error(const char* where);
     void flush_raw(int e);
@@ -715,6 +760,8 @@ void free_edge_log(EdgeStore& e) {
     dfree(e.log_to); dfree(e.log_from); dfree(e.log_st); dfree(e.wcnt); dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark);
     e.log_to = e.log_from = e.wcnt = nullptr; e.log_st = nullptr; e.log_n = e.log_cap = 0; e.rows_w = 0;
     e.rm_row = e.rm_from = e.rm_mark = nullptr; e.rm_n = e.rm_cap = 0;
+    dfree(e.rlog_to); dfree(e.rlog_from); dfree(e.rlog_st); dfree(e.rlog_dst);
+    e.rlog_to = e.rlog_from = nullptr; e.rlog_st = nullptr; e.rlog_dst = nullptr; e.rlog_n = e.rlog_cap = 0;
 }
 void free_chunks(EdgeStore& e) {
     for (auto& c : e.chunks) { dfree(c.to); dfree(c.from); dfree(c.st); }
@@ -741,7 +788,7 @@ void vb_sim::compute_bases(uint32_t* out) const {
 }
 
 // grow the buffers of agent type t to hold `need` slots; composite bases of later types shift (rebase)
-void vb_sim::ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need) {
+void vb_sim::ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need, bool do_rebase) {
     AgentStore& a = A(t);
     if (need <= a.cap && ghost_need <= a.gcap) return;
     uint64_t ncap = a.cap;
@@ -779,22 +826,30 @@ void vb_sim::ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need) {
         a.reuse = r;
         a.reuse_cap = (uint32_t)ncap;
     }
+    uint32_t old_lcap[vb::MAX_AGENT_TYPES + 1] = {0};
+    for (size_t k = 1; k <= agents.size(); ++k) old_lcap[k] = agents[k - 1].cap;
     a.cap = (uint32_t)ncap;
     a.gcap = ngcap;
     a.halo_dirty = true;
     compute_bases(base);
-    rebase(old_base);
+    if (do_rebase) rebase(old_base, old_lcap);
 }
 
 // after capacities changed: remap every stored composite index (CSR columns, rows of containers that are
 // keyed by all agent types, append logs, raster cell tables)
-void vb_sim::rebase(const uint32_t* old_base) {
-    RebaseArgs ra;
+void vb_sim::rebase(const uint32_t* old_base, const uint32_t* old_lcap, const uint32_t* const* remap) {
+    RebaseArgs ra{};
     std::memcpy(ra.old_base, old_base, sizeof(ra.old_base));
     std::memcpy(ra.new_base, base, sizeof(ra.new_base));
     ra.ntypes = (uint32_t)agents.size();
     bool same = true;
     for (size_t t = 0; t <= agents.size() + 1; ++t) same &= ra.old_base[t] == ra.new_base[t];
+    for (size_t t = 1; t <= agents.size(); ++t) {
+        ra.new_lcap[t] = agents[t - 1].cap;
+        ra.old_lcap[t] = old_lcap ? old_lcap[t] : agents[t - 1].cap;
+        ra.remap[t] = remap ? remap[t] : nullptr;
+        same &= ra.old_lcap[t] == ra.new_lcap[t] && !ra.remap[t];
+    }
     for (auto& e : edges) {
         if (!same && e.src && e.nnz) { rebase_values_kernel<<<nblk(e.nnz), 256, 0, g_stream>>>(e.src, e.nnz, ra); LAUNCH_CHECK(); }
         if (!same && e.log_from && e.log_n) { rebase_values_kernel<<<nblk(e.log_n), 256, 0, g_stream>>>(e.log_from, e.log_n, ra); LAUNCH_CHECK(); }
@@ -858,7 +913,7 @@ void vb_sim::upload_view(uint64_t seed) {
         v.died_r = a.immortal ? nullptr : a.rdied(); v.died_w = a.immortal ? nullptr : a.wdied();
         v.reuse = a.reuse; v.cap = a.stride(); v.lcap = a.cap; v.nghost = a.nghost; v.ghost_ids = a.ghost_ids; v.nslots_r = a.nslots;
         v.n_reuse = a.n_reuse; v.next0 = (uint32_t)(a.nextid - 1);
-        v.size = a.size; v.word = a.word ? a.word : 1; v.ncols = a.ncols;
+        v.size = a.size; v.word = a.word ? a.word : 1; v.ncols = a.ncols; v.uoffset = a.uoffset;
         v.immortal = a.immortal; v.independent = a.independent; v.readable = a.prepared; v.writeable = a.writeable;
     }
     for (size_t i = 0; i < edges.size(); ++i) {
@@ -867,6 +922,7 @@ void vb_sim::upload_view(uint64_t seed) {
         v.off = e.off; v.src = e.src; v.st = e.st; v.cnt = e.cnt; v.rows = e.rows; v.st_cap = e.st_cap;
         v.log_to = e.log_to; v.log_from = e.log_from; v.log_st = e.log_st; v.wcnt = e.wcnt; v.log_cap = e.log_cap; v.rows_w = e.rows_w;
         v.rm_row = e.rm_row; v.rm_from = e.rm_from; v.rm_mark = e.rm_mark;
+        v.rlog_to = e.rlog_to; v.rlog_from = e.rlog_from; v.rlog_st = e.rlog_st; v.rlog_dst = e.rlog_dst; v.rlog_cap = e.rlog_cap;
         v.size = e.size; v.word = e.word ? e.word : 1; v.ncols = e.ncols; v.target = e.singletype ? e.target : 0;
         v.hints = (uint8_t)e.hints; v.kind = e.implicit_stencil ? (uint8_t)vb::KIND_STENCIL : e.kind; v.readable = e.readable; v.writeable = e.writeable;
         v.st_off = e.st_off; v.st_n = e.st_n; v.st_raster = e.st_raster; v.st_slot0 = e.st_slot0; v.st_periodic = e.st_periodic; v.st_reach = (uint8_t)e.st_reach;
@@ -879,7 +935,7 @@ void vb_sim::upload_view(uint64_t seed) {
     }
     std::memcpy(h.base, base, sizeof(h.base));
     h.n_agent_types = (uint32_t)agents.size(); h.n_edge_types = (uint32_t)edges.size(); h.n_rasters = (uint32_t)rasters.size();
-    h.rank = rank; h.check = asserts_enabled && check_readable; h.error = d_error; h.seed = seed;
+    h.rank = rank; h.nranks = (uint32_t)g_nranks; h.check = asserts_enabled && check_readable; h.error = d_error; h.seed = seed;
     if (!params.empty()) std::memcpy(h.params, params.data(), params.size());
 }
 
@@ -1254,31 +1310,36 @@ void vb_sim::purge_dead(const uint8_t* dead) {
 // stored on its target's rank (src/EdgeMethods.jl:396-398).  The state of remote *sources* is mirrored in a ghost segment
 // behind the local slots of each agent type; this replaces the reference's request/reply halo (transmit_agents!,
 // src/MPI.jl:155-267): the request lists are exchanged once here, per step only packed states travel (halo_exchange).
-void vb_sim::build_ghosts() {
+void vb_sim::build_ghosts(const uint64_t* const* extra, const uint64_t* extra_n, int n_extra) {
     if (g_nranks <= 1) return;
     const uint32_t NT = (uint32_t)agents.size(), P = (uint32_t)g_nranks;
-    // 1. all remote source ids of the raw adds, split into 32-bit halves for the radix sort
+    // 1. candidate ids: remote sources of the raw adds + the caller's id arrays (edges received from other ranks) + the
+    //    ghosts already mirrored; split into 32-bit halves for the radix sort
     uint64_t cap = 0;
     for (auto& e : edges) { if (!e.has_src()) continue; flush_raw((int)(&e - &edges[0])); for (auto& c : e.chunks) cap += c.n; }
+    for (int i = 0; i < n_extra; ++i) cap += extra_n[i];
+    for (auto& a : agents) cap += a.nghost;
     uint32_t* lo = dalloc<uint32_t>(std::max<uint64_t>(cap, 1)); uint32_t* hi = dalloc<uint32_t>(std::max<uint64_t>(cap, 1));
     uint64_t nrem = 0;
-    for (auto& e : edges) {
-        if (!e.has_src()) continue;
-        for (auto& c : e.chunks) {
-            if (c.n >= 0xffffffffull) throw ArgError("raw edge chunk too large");
-            uint32_t* flag = dalloc<uint32_t>(c.n); uint32_t* pos = dalloc<uint32_t>(c.n);
-            uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(c.n));
-            remote_flags_kernel<<<nblk(c.n), 256, 0, g_stream>>>(c.from, c.n, rank, flag); LAUNCH_CHECK();
-            vbp::exclusive_scan(flag, pos, c.n, d_scalars, scr, g_stream);
-            uint32_t k = 0;
-            CK(cudaMemcpyAsync(&k, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
-            CK(cudaStreamSynchronize(g_stream));
-            if (k) { compact_u64_split_kernel<<<nblk(c.n), 256, 0, g_stream>>>(c.from, flag, pos, c.n, lo, hi, nrem); LAUNCH_CHECK(); }
-            nrem += k;
-            CK(cudaStreamSynchronize(g_stream));
-            dfree(flag); dfree(pos); dfree(scr);
-        }
-    }
+    auto add_filtered = [&](const uint64_t* ids, uint64_t n) {
+        if (!n) return;
+        if (n >= 0xffffffffull) throw ArgError("id chunk too large");
+        uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
+        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+        remote_flags_kernel<<<nblk(n), 256, 0, g_stream>>>(ids, n, rank, flag); LAUNCH_CHECK();
+        vbp::exclusive_scan(flag, pos, n, d_scalars, scr, g_stream);
+        uint32_t k = 0;
+        CK(cudaMemcpyAsync(&k, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (k) { compact_u64_split_kernel<<<nblk(n), 256, 0, g_stream>>>(ids, flag, pos, n, lo, hi, nrem); LAUNCH_CHECK(); }
+        nrem += k;
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(flag); dfree(pos); dfree(scr);
+    };
+    for (auto& e : edges) { if (!e.has_src()) continue; for (auto& c : e.chunks) add_filtered(c.from, c.n); }
+    for (int i = 0; i < n_extra; ++i) add_filtered(extra[i], extra_n[i]);
+    for (auto& a : agents)
+        if (a.nghost) { split64_kernel<<<nblk(a.nghost), 256, 0, g_stream>>>(a.ghost_ids, a.nghost, lo, hi, nrem); LAUNCH_CHECK(); nrem += a.nghost; }
     if (nrem >= 0xffffffffull) throw ArgError("too many remote edge sources on one rank");
     // 2. sort by (hi, lo) = ascending AgentID (two stable 32-bit sorts), then unique
     uint64_t* G = nullptr; uint32_t ng = 0;
@@ -1302,7 +1363,7 @@ void vb_sim::build_ghosts() {
         dfree(lo2); dfree(hi2); dfree(scratch); dfree(flag); dfree(pos); dfree(scr);
     }
     dfree(lo); dfree(hi);
-    // 3. boundaries per (type, owner rank)
+    // 3. boundaries per (type, owner rank); remap of the previous ghost numbering
     std::vector<uint32_t> bounds((size_t)NT * P + 1, 0);
     if (ng) {
         uint32_t* db = dalloc<uint32_t>(bounds.size());
@@ -1311,22 +1372,50 @@ void vb_sim::build_ghosts() {
         CK(cudaStreamSynchronize(g_stream));
         dfree(db);
     }
+    uint32_t old_base[vb::MAX_AGENT_TYPES + 2]; uint32_t old_lcap[vb::MAX_AGENT_TYPES + 1] = {0};
+    const uint32_t* remap[vb::MAX_AGENT_TYPES + 1] = {nullptr};
+    std::memcpy(old_base, base, sizeof(old_base));
+    bool changed = false;
     for (uint32_t t = 1; t <= NT; ++t) {
         AgentStore& a = agents[t - 1];
+        old_lcap[t] = a.cap;
         const uint32_t b0 = bounds[(size_t)(t - 1) * P], b1 = bounds[(size_t)t * P];
-        a.nghost = b1 - b0;
-        dfree(a.ghost_ids); a.ghost_ids = nullptr;
+        const uint32_t nn = b1 - b0;
+        if (nn != a.nghost) {
+            changed = true;
+            uint64_t* ng_ids = dalloc<uint64_t>(std::max<uint32_t>(nn, 1));
+            if (nn) CK(cudaMemcpyAsync(ng_ids, G + b0, (size_t)nn * 8, cudaMemcpyDeviceToDevice, g_stream));
+            if (a.nghost) {
+                uint32_t* rm = dalloc<uint32_t>(a.nghost);
+                ghost_remap_kernel<<<nblk(a.nghost), 256, 0, g_stream>>>(a.ghost_ids, a.nghost, ng_ids, nn, rm); LAUNCH_CHECK();
+                remap[t] = rm;
+            }
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(a.ghost_ids);
+            a.ghost_ids = ng_ids;
+            a.nghost = nn;
+        }
         a.ghost_off.assign(P + 1, 0);
         for (uint32_t r = 0; r <= P; ++r) a.ghost_off[r] = bounds[(size_t)(t - 1) * P + r] - b0;
-        if (a.nghost) {
-            a.ghost_ids = dalloc<uint64_t>(a.nghost);
-            CK(cudaMemcpyAsync(a.ghost_ids, G + b0, (size_t)a.nghost * 8, cudaMemcpyDeviceToDevice, g_stream));
-        }
-        ensure_agent_cap((int)t, a.cap, a.nghost);
+        ensure_agent_cap((int)t, a.cap, a.nghost + a.nghost / 4, false);   // some headroom: the table only grows
     }
+    compute_bases(base);
+    rebase(old_base, old_lcap, remap);
     CK(cudaStreamSynchronize(g_stream));
+    for (uint32_t t = 1; t <= NT; ++t) dfree((void*)remap[t]);
     dfree(G);
-    // 4. tell every owner which of its agents we mirror: counts (all-gather), then the id lists (grouped send/recv)
+    // 4. all ranks agree whether anybody's tables changed; if so the request lists are exchanged again
+    uint64_t mine = changed ? 1 : 0;
+    std::vector<uint64_t> all;
+    allgather8_host(&mine, all);
+    bool any = false;
+    for (uint64_t v : all) any |= v != 0;
+    if (any || agents[0].send_off.empty()) exchange_ghost_requests();
+}
+
+// tell every owner which of its agents this rank mirrors: counts (all-gather), then the id lists (grouped send/recv)
+void vb_sim::exchange_ghost_requests() {
+    const uint32_t NT = (uint32_t)agents.size(), P = (uint32_t)g_nranks;
     uint32_t* dcnt = dalloc<uint32_t>((size_t)P * NT); uint32_t* dall = dalloc<uint32_t>((size_t)P * P * NT);
     std::vector<uint32_t> mine((size_t)P * NT), all((size_t)P * P * NT);
     for (uint32_t t = 1; t <= NT; ++t) for (uint32_t r = 0; r < P; ++r) mine[(size_t)(t - 1) * P + r] = agents[t - 1].ghost_off[r + 1] - agents[t - 1].ghost_off[r];
@@ -1359,6 +1448,107 @@ void vb_sim::build_ghosts() {
         dfree(req);
         a.halo_dirty = true;
     }
+}
+
+// transmit_edges! (src/EdgeMethods.jl:686-689, edges_alltoall! src/MPI.jl:353-430): the appended edges that belong to another rank are
+// bucketed by destination (stable: each rank's batch keeps its call order), exchanged with grouped ncclSend/ncclRecv (all-to-all-v)
+// and appended behind the local adds in source-rank order (A-15).  Collective: every rank calls it for every written edge type.
+void vb_sim::transmit_edges(int ei) {
+    EdgeStore& e = E(ei);
+    const uint32_t P = (uint32_t)g_nranks, n = e.rlog_n;
+    e.rlog_n = 0;
+    std::vector<uint32_t> scnt(P + 1, 0);
+    uint64_t* sto = nullptr; uint64_t* sfrom = nullptr; uint8_t* sst = nullptr;
+    if (n) {
+        uint32_t* perm = dalloc<uint32_t>(n); uint32_t* k1 = dalloc<uint32_t>(n); uint32_t* p1 = dalloc<uint32_t>(n);
+        vbp::iota_u32_kernel<<<nblk(n), 256, 0, g_stream>>>(perm, n); LAUNCH_CHECK();
+        uint32_t* scratch = dalloc<uint32_t>(vbp::rs_scratch_words(n));
+        const int res = vbp::radix_sort(e.rlog_dst, k1, perm, p1, nullptr, nullptr, 0, n, vbp::bits_for(P), scratch, g_stream);
+        CK(cudaGetLastError());
+        dfree(scratch);
+        const uint32_t* sdst = res ? k1 : e.rlog_dst; const uint32_t* sperm = res ? p1 : perm;
+        uint32_t* dc = dalloc<uint32_t>(P + 2);
+        CK(cudaMemsetAsync(dc, 0, (P + 2) * 4, g_stream));
+        vbp::csr_run_counts_kernel<<<nblk(n), 256, 0, g_stream>>>(sdst, n, dc); LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(scnt.data(), dc, P * 4, cudaMemcpyDeviceToHost, g_stream));
+        sto = dalloc<uint64_t>(n);
+        gather_u64_kernel<<<nblk(n), 256, 0, g_stream>>>(e.rlog_to, sperm, n, sto); LAUNCH_CHECK();
+        if (e.has_src()) { sfrom = dalloc<uint64_t>(n); gather_u64_kernel<<<nblk(n), 256, 0, g_stream>>>(e.rlog_from, sperm, n, sfrom); LAUNCH_CHECK(); }
+        if (e.has_state()) {
+            sst = (uint8_t*)g_pool.alloc((size_t)n * e.size);
+            gather_soa_to_aos_kernel<<<nblk((uint64_t)n * e.ncols), 256, 0, g_stream>>>(e.rlog_st, e.rlog_cap, sperm, n, sst, e.size, e.word); LAUNCH_CHECK();
+        }
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(perm); dfree(k1); dfree(p1); dfree(dc);
+    }
+    // counts: everybody learns the whole P x P matrix
+    uint32_t* dcnt = dalloc<uint32_t>(P); uint32_t* dall = dalloc<uint32_t>((size_t)P * P);
+    std::vector<uint32_t> all((size_t)P * P);
+    CK(cudaMemcpyAsync(dcnt, scnt.data(), P * 4, cudaMemcpyHostToDevice, g_stream));
+    NK(g_nccl.AllGather(dcnt, dall, (size_t)P * 4, ncclUint8, g_comm, g_stream));
+    CK(cudaMemcpyAsync(all.data(), dall, all.size() * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(dcnt); dfree(dall);
+    std::vector<uint32_t> soff(P + 1, 0), roff(P + 1, 0);
+    for (uint32_t r = 0; r < P; ++r) { soff[r + 1] = soff[r] + scnt[r]; roff[r + 1] = roff[r] + all[(size_t)r * P + rank]; }
+    const uint32_t nrecv = roff[P];
+    uint64_t* rto = dalloc<uint64_t>(std::max<uint32_t>(nrecv, 1));
+    uint64_t* rfrom = e.has_src() ? dalloc<uint64_t>(std::max<uint32_t>(nrecv, 1)) : nullptr;
+    uint8_t* rst = e.has_state() ? (uint8_t*)g_pool.alloc((size_t)std::max<uint32_t>(nrecv, 1) * e.size) : nullptr;
+    NK(g_nccl.GroupStart());
+    for (uint32_t r = 0; r < P; ++r) {
+        const uint32_t give = scnt[r], want = roff[r + 1] - roff[r];
+        if (r == rank) continue;
+        if (give) {
+            NK(g_nccl.Send(sto + soff[r], (size_t)give * 8, ncclUint8, (int)r, g_comm, g_stream));
+            if (sfrom) NK(g_nccl.Send(sfrom + soff[r], (size_t)give * 8, ncclUint8, (int)r, g_comm, g_stream));
+            if (sst) NK(g_nccl.Send(sst + (size_t)soff[r] * e.size, (size_t)give * e.size, ncclUint8, (int)r, g_comm, g_stream));
+        }
+        if (want) {
+            NK(g_nccl.Recv(rto + roff[r], (size_t)want * 8, ncclUint8, (int)r, g_comm, g_stream));
+            if (rfrom) NK(g_nccl.Recv(rfrom + roff[r], (size_t)want * 8, ncclUint8, (int)r, g_comm, g_stream));
+            if (rst) NK(g_nccl.Recv(rst + (size_t)roff[r] * e.size, (size_t)want * e.size, ncclUint8, (int)r, g_comm, g_stream));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    if (scnt[rank]) {   // edges kept on this rank because their source was not mirrored yet
+        CK(cudaMemcpyAsync(rto + roff[rank], sto + soff[rank], (size_t)scnt[rank] * 8, cudaMemcpyDeviceToDevice, g_stream));
+        if (rfrom) CK(cudaMemcpyAsync(rfrom + roff[rank], sfrom + soff[rank], (size_t)scnt[rank] * 8, cudaMemcpyDeviceToDevice, g_stream));
+        if (rst) CK(cudaMemcpyAsync(rst + (size_t)roff[rank] * e.size, sst + (size_t)soff[rank] * e.size, (size_t)scnt[rank] * e.size, cudaMemcpyDeviceToDevice, g_stream));
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(sto); dfree(sfrom); dfree(sst);
+    halo_bytes += (uint64_t)nrecv * (8 + (e.has_src() ? 8 : 0) + (e.has_state() ? e.size : 0));
+    // the sources of the received edges that live on other ranks become ghosts (collective)
+    const uint64_t* extra[1] = {rfrom};
+    const uint64_t extra_n[1] = {rfrom ? nrecv : 0u};
+    build_ghosts(extra, extra_n, 1);
+    // translate and append behind the local adds
+    if (nrecv) {
+        uint32_t* tmp_rows = nullptr;
+        if (e.kind == vb::KIND_CSR || e.ordered_log) ensure_log(e, (uint64_t)e.log_n + nrecv);
+        else tmp_rows = dalloc<uint32_t>(nrecv);
+        TranslateArgs ta{};
+        ta.to = rto; ta.from = rfrom; ta.n = nrecv;
+        ta.log_to = tmp_rows ? tmp_rows : e.log_to; ta.log_from = e.log_from; ta.pos0 = tmp_rows ? 0 : e.log_n;
+        std::memcpy(ta.base, base, sizeof(ta.base));
+        for (size_t t = 1; t <= agents.size(); ++t) {
+            ta.nslots[t] = (uint32_t)std::max<uint64_t>(agents[t - 1].nslots, agents[t - 1].nextid - 1 + agents[t - 1].births);
+            ta.lcap[t] = agents[t - 1].cap; ta.nghost[t] = agents[t - 1].nghost; ta.ghost_ids[t] = agents[t - 1].ghost_ids;
+        }
+        ta.ntypes = (uint32_t)agents.size(); ta.target = e.singletype ? e.target : 0; ta.ignore_from = !e.has_src() || e.kind != vb::KIND_CSR; ta.rank = rank; ta.error = d_error;
+        translate_edges_kernel<<<nblk(nrecv), 256, 0, g_stream>>>(ta); LAUNCH_CHECK();
+        if (tmp_rows) {
+            count_adds_kernel<<<nblk(nrecv), 256, 0, g_stream>>>(tmp_rows, nrecv, e.wcnt, e.kind == vb::KIND_FLAG); LAUNCH_CHECK();
+        } else {
+            if (e.kind == vb::KIND_CSR && e.has_state()) { vbp::aos_to_soa_kernel<<<nblk((uint64_t)nrecv * e.ncols), 256, 0, g_stream>>>(rst, e.log_st, e.log_cap, e.log_n, nrecv, e.size, e.word); LAUNCH_CHECK(); }
+            e.log_n += nrecv;
+        }
+        check_device_error("transmit_edges!");
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(tmp_rows);
+    }
+    dfree(rto); dfree(rfrom); dfree(rst);
 }
 
 // per-step halo: pack the states the peers mirror, grouped ncclSend/ncclRecv (all-to-all-v) straight into the ghost segments
@@ -1569,7 +1759,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             EdgeStore& e = s.E(w - vb::EDGE_REF);
             e.writeable = true;
             e.add_existing = contains(add_existing, w);
-            e.log_n = 0; e.rm_n = 0;
+            e.log_n = 0; e.rm_n = 0; e.rlog_n = 0;
             e.ordered_log = false;
             for (auto* ti : tis) for (int i = 0; i < ti->n_edge_removes; ++i) if (ti->edge_removes[i] == w - vb::EDGE_REF) e.ordered_log = e.kind != vb::KIND_CSR;
             if (e.kind != vb::KIND_CSR) {
@@ -1609,6 +1799,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             for (int i = 0; i < ti->n_edge_writes; ++i) { la.ecount[i] = dalloc<uint32_t>(n); tmp.push_back(la.ecount[i]); }
             for (int i = 0; i < ti->n_agent_writes; ++i) { la.acount[i] = dalloc<uint32_t>(n); tmp.push_back(la.acount[i]); }
             for (int i = 0; i < ti->n_edge_removes; ++i) { la.rcount[i] = dalloc<uint32_t>(n); tmp.push_back(la.rcount[i]); }
+            if (g_nranks > 1) for (int i = 0; i < ti->n_edge_writes; ++i) { la.ercount[i] = dalloc<uint32_t>(n); tmp.push_back(la.ercount[i]); }
             s.upload_view(seed);
             la.mode = vb::MODE_COUNT;
             CK(ti->launch(la)); ++g_launches;
@@ -1616,7 +1807,9 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             for (int i = 0; i < ti->n_agent_writes; ++i) { vbp::exclusive_scan(la.acount[i], la.acount[i], n, s.d_scalars + vb::MAX_EDGE_WRITES + i, scr, g_stream); g_launches += 3; }
             constexpr int RM0 = vb::MAX_EDGE_WRITES + vb::MAX_AGENT_WRITES;
             for (int i = 0; i < ti->n_edge_removes; ++i) { vbp::exclusive_scan(la.rcount[i], la.rcount[i], n, s.d_scalars + RM0 + i, scr, g_stream); g_launches += 3; }
-            uint32_t totals[vb::MAX_EDGE_WRITES + vb::MAX_AGENT_WRITES + vb::MAX_EDGE_REMOVES] = {0};
+            constexpr int ER0 = RM0 + vb::MAX_EDGE_REMOVES;
+            if (g_nranks > 1) for (int i = 0; i < ti->n_edge_writes; ++i) { vbp::exclusive_scan(la.ercount[i], la.ercount[i], n, s.d_scalars + ER0 + i, scr, g_stream); g_launches += 3; }
+            uint32_t totals[vb::MAX_EDGE_WRITES + vb::MAX_AGENT_WRITES + vb::MAX_EDGE_REMOVES + vb::MAX_EDGE_WRITES] = {0};
             CK(cudaMemcpyAsync(totals, s.d_scalars, sizeof(totals), cudaMemcpyDeviceToHost, g_stream));
             CK(cudaStreamSynchronize(g_stream));
             s.check_device_error("apply! (count pass)");
@@ -1633,6 +1826,24 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 la.ebase[i] = e.log_n;
                 if (e.kind == vb::KIND_CSR || e.ordered_log) s.ensure_log(e, (uint64_t)e.log_n + totals[i] + 1);
                 if (e.kind != vb::KIND_CSR && s.rows_of(e) != e.rows_w) throw CudaError("internal: count container not sized");
+            }
+            if (g_nranks > 1) for (int i = 0; i < ti->n_edge_writes; ++i) {   // edges that leave the rank
+                EdgeStore& e = s.E(ti->edge_writes[i]);
+                la.erbase[i] = e.rlog_n;
+                const uint64_t need = (uint64_t)e.rlog_n + totals[ER0 + i];
+                if (need > e.rlog_cap) {
+                    const uint32_t ncap = (uint32_t)std::max<uint64_t>(need, (uint64_t)e.rlog_cap * 2 + 1024);
+                    uint64_t* nt = dalloc<uint64_t>(ncap); uint64_t* nf = e.has_src() ? dalloc<uint64_t>(ncap) : nullptr;
+                    uint32_t* nd = dalloc<uint32_t>(ncap); uint8_t* ns = e.has_state() ? (uint8_t*)g_pool.alloc((size_t)ncap * e.size) : nullptr;
+                    if (e.rlog_n) {
+                        CK(cudaMemcpyAsync(nt, e.rlog_to, (size_t)e.rlog_n * 8, cudaMemcpyDeviceToDevice, g_stream));
+                        if (nf) CK(cudaMemcpyAsync(nf, e.rlog_from, (size_t)e.rlog_n * 8, cudaMemcpyDeviceToDevice, g_stream));
+                        CK(cudaMemcpyAsync(nd, e.rlog_dst, (size_t)e.rlog_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+                        if (ns) { vbp::soa_copy_kernel<<<nblk((uint64_t)e.rlog_n * e.size), 256, 0, g_stream>>>(e.rlog_st, e.rlog_cap, ns, ncap, e.rlog_n, e.ncols, e.word, 0, 0); LAUNCH_CHECK(); }
+                    }
+                    dfree(e.rlog_to); dfree(e.rlog_from); dfree(e.rlog_dst); dfree(e.rlog_st);
+                    e.rlog_to = nt; e.rlog_from = nf; e.rlog_dst = nd; e.rlog_st = ns; e.rlog_cap = ncap;
+                }
             }
             for (int i = 0; i < ti->n_edge_removes; ++i) {
                 EdgeStore& e = s.E(ti->edge_removes[i]);
@@ -1657,6 +1868,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             CK(cudaEventRecord(s.evk[1], g_stream));
             for (int i = 0; i < ti->n_edge_writes; ++i) { EdgeStore& e = s.E(ti->edge_writes[i]); if (e.kind == vb::KIND_CSR || e.ordered_log) e.log_n += totals[i]; appended += totals[i]; }
             for (int i = 0; i < ti->n_edge_removes; ++i) s.E(ti->edge_removes[i]).rm_n += totals[RM0 + i];
+            if (g_nranks > 1) for (int i = 0; i < ti->n_edge_writes; ++i) { s.E(ti->edge_writes[i]).rlog_n += totals[ER0 + i]; appended += totals[ER0 + i]; }
             for (int i = 0; i < ti->n_agent_writes; ++i) s.A(ti->agent_writes[i]).births += totals[vb::MAX_EDGE_WRITES + i];
         } else {
             la.mode = vb::MODE_DIRECT;
@@ -1720,6 +1932,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     }
     CK(cudaEventRecord(s.ev[1], g_stream));
     s.check_device_error("apply!");
+    if (g_nranks > 1)   // transmit_edges! for every writable edge type (Simulation.jl:800), collective
+        for (int w : write) if (w >= vb::EDGE_REF) s.transmit_edges(w - vb::EDGE_REF);
 
     // ---- finish_write! agents (Simulation.jl:807), then edges (:809), then the dead-agent purge ----
     std::vector<uint32_t*> died_flags(s.agents.size() + 1, nullptr);
@@ -1825,7 +2039,10 @@ int vb_comm_init(int rank, int nranks, const uint8_t* idbytes) {
 }
 int vb_comm_rank(int* r, int* n) { *r = g_rank; *n = g_nranks; return VB_OK; }
 // fold one 8-byte value per rank with `op` (mapreduce / num_agents / num_edges: MPI.Allreduce in the reference)
-static void allgather8(const void* mine, std::vector<uint64_t>& all) {
+static void allgather8(const void* mine, std::vector<uint64_t>& all) { allgather8_host(mine, all); }
+}  // extern "C"
+namespace {
+void allgather8_host(const void* mine, std::vector<uint64_t>& all) {
     all.assign((size_t)g_nranks, 0);
     if (g_nranks <= 1) { std::memcpy(all.data(), mine, 8); return; }
     uint64_t* d = dalloc<uint64_t>((size_t)g_nranks + 1);
@@ -1835,7 +2052,10 @@ static void allgather8(const void* mine, std::vector<uint64_t>& all) {
     CK(cudaStreamSynchronize(g_stream));
     dfree(d);
 }
+}  // namespace
+extern "C" {
 int vb_halo_bytes(vb_sim* s, uint64_t* out) { *out = s->halo_bytes; return VB_OK; }
+int vb_set_uniform_offset(vb_sim* s, int type, uint64_t offset) { return guard([&] { s->A(type).uoffset = offset; }); }
 
 int vb_sim_create(const vb_model_desc* m, const void* params, vb_sim** out) {
     return guard([&] {
@@ -1912,6 +2132,7 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
             f.cnt = (uint32_t*)dup(e.cnt, ((size_t)e.rows + 1) * 4);
             f.log_to = f.log_from = f.wcnt = nullptr; f.log_st = nullptr; f.log_n = f.log_cap = 0; f.rows_w = 0;
             f.st_off = (int8_t*)dup(e.st_off, e.st_off_host.size());
+            f.rlog_to = f.rlog_from = nullptr; f.rlog_st = nullptr; f.rlog_dst = nullptr; f.rlog_n = f.rlog_cap = 0;
             f.rm_row = f.rm_from = f.rm_mark = nullptr; f.rm_n = f.rm_cap = 0; f.heavy_rows = nullptr; f.heavy_n = 0; f.heavy_version = ~0ull;
             for (auto& c : e.chunks) {
                 RawChunk d; d.n = c.n;

@@ -19,7 +19,7 @@ struct Person { uint8_t state; uint8_t days; };
 struct Location { int32_t n_inf; };
 struct Visit { bool infectious; };
 struct Exposure { float risk; };
-struct Params { double beta; int64_t n_locations; int64_t visits_per_step; int64_t infectious_days; };
+struct Params { double beta; int64_t n_locations; int64_t visits_per_step; int64_t infectious_days; int64_t n_ranks; };
 enum : int { T_PERSON = 1, T_LOCATION = 2 };
 enum : int { E_VISIT = 0, E_EXPOSURE = 1 };
 
@@ -33,7 +33,8 @@ struct DoVisit : vb::TransitionBase {
         for (int k = 0; k < (int)pr.visits_per_step; ++k) {
             int64_t loc = (int64_t)(ctx.uniform(k) * (double)pr.n_locations);
             if (loc >= pr.n_locations) loc = pr.n_locations - 1;
-            ctx.add_edge(E_VISIT, id, vb::agent_id(T_LOCATION, 0, (uint64_t)loc + 1), v);
+            // locations are spread over the ranks in contiguous equal blocks (one rank: rank 0, nr = loc + 1)
+            ctx.add_edge(E_VISIT, id, vb::block_partition_id(T_LOCATION, (uint64_t)loc, (uint64_t)pr.n_locations, (uint32_t)(pr.n_ranks > 0 ? pr.n_ranks : 1)), v);
         }
         return true;
     }
