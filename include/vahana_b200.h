@@ -90,6 +90,7 @@ int vb_disable_transition_checks(vb_sim* sim, int disable);                /* sr
 
 /* ---- init phase (bulk): add_agent(s)!, add_edge(s)!, rasters, finish_init! ----------- */
 int vb_add_agents(vb_sim* sim, int type, const void* states, uint64_t n, vb_agent_id* ids_out); /* AgentMethods.jl:65 */
+int vb_add_agent_per_process(vb_sim* sim, int type, const void* state, vb_agent_id* id_out);    /* Agent.jl:363-388 */
 int vb_add_edges(vb_sim* sim, int etype, const vb_agent_id* from, const vb_agent_id* to, const void* states,
                  uint64_t n);                                                                    /* EdgeMethods.jl:388-523 */
 int vb_remove_edges(vb_sim* sim, int etype, vb_agent_id from /*0 = all*/, vb_agent_id to);      /* EdgeMethods.jl:527-599 */

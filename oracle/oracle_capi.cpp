@@ -72,6 +72,19 @@ int vb_add_agents(vb_sim* sim, int type, const void* states, uint64_t n, vb_agen
         }
     });
 }
+int vb_add_agent_per_process(vb_sim* sim, int type, const void* state, vb_agent_id* id_out) {
+    return guard([&] {   // Agent.jl:363-388
+        vo::Sim& s = *sim->s;
+        if (!s.initialized) throw vo::AssertionError("add_agent_per_process! can only be called after finish_init!");
+        if (s.intransition) throw vo::AssertionError("add_agent_per_process! cannot be called within a transition function");
+        vo::prepare_write_agent(s, type, true);
+        s.intransition = true;
+        vb_agent_id id = vo::add_agent(s, type, state);
+        s.intransition = false;
+        vo::finish_write_agent(s, type);
+        if (id_out) *id_out = id;
+    });
+}
 int vb_add_edges(vb_sim* sim, int e, const vb_agent_id* from, const vb_agent_id* to, const void* states, uint64_t n) {
     return guard([&] {
         const uint32_t sz = sim->s->E(e).desc.size;

@@ -189,3 +189,21 @@ def test_mapreduce(backend):  # test/core.jl:396-440
     sim.apply("set_bool_id_odd", ["ADefault"], ["ADefault"], ["ADefault"])
     assert sim.mapreduce("bool", "&", "ADefault") is False
     assert sim.mapreduce("bool", "|", "ADefault") is True
+
+
+def test_add_agent_per_process(backend):  # test/core.jl:442-466
+    sim = vh.create_simulation(core_model(), backend=backend)
+    for i in range(1, 11):
+        sim.add_agent("AMortal", i)
+    sim.finish_init()
+    new_id = sim.add_agent_per_process("AMortal", 100)
+    assert sim.num_agents("AMortal") == 10 + 1          # + mpi.size
+    assert vh.agent_nr(new_id) == 11
+    sim.disable_transition_checks(True)
+    assert sim.agentstate(new_id, "AMortal")["foo"] == 100
+    sim.disable_transition_checks(False)
+    sim.apply("keep_even_foo", "AMortal", "AMortal", "AMortal")      # 2,4,6,8,10,100 survive
+    assert sim.num_agents("AMortal") == 6
+    again = sim.add_agent_per_process("AMortal", 7)                   # reuses the most recently freed slot
+    assert vh.agent_nr(again) == 9
+    assert sorted(sim.all_agents("AMortal")["foo"].tolist()) == [2, 4, 6, 7, 8, 10, 100]

@@ -85,3 +85,15 @@ def test_sir_sharded_edge_redistribution_vs_oracle(cuda):
                         "--master-port", "29521", os.path.join(ROOT, "tests", "mgpu_sir.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(": ok") == min(ng, 4)
+
+
+@pytest.mark.gpu
+def test_dead_agent_purge_across_ranks(cuda):
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ng, 4)), "--master-addr", "127.0.0.1",
+                        "--master-port", "29523", os.path.join(ROOT, "tests", "mgpu_purge.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(": ok") == min(ng, 4)

@@ -103,7 +103,7 @@ ABI_SYMBOLS = [
     "vb_cellid", "vb_finish_init", "vb_apply", "vb_has_transition", "vb_load_model_library", "vb_num_agents",
     "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce",
     "vb_rastervalues", "vb_calc_raster_num_edges", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
-    "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes", "vb_set_uniform_offset",
+    "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes", "vb_set_uniform_offset", "vb_add_agent_per_process",
 ]
 
 
@@ -436,6 +436,17 @@ class Simulation:
         """Bulk add from device buffers of AgentIDs (uint64) in call order."""
         self._ck(self.lib.vb_add_edges(self.h, C.c_int(self._eid[edge_name]), C.c_void_p(from_ptr), C.c_void_p(to_ptr),
                                        C.c_void_p(states_ptr) if states_ptr else None, C.c_uint64(n)))
+
+    def add_agent_per_process(self, type_name: str, state=None) -> int:
+        """add_agent_per_process!(sim, agent) (src/Agent.jl:363-388): one agent on every rank, outside of transitions"""
+        dt = self._adt(type_name)
+        buf = None
+        if dt is not None:
+            buf = np.array([state if isinstance(state, (tuple, np.void)) else (state,)], dtype=dt)
+        out = C.c_uint64()
+        self._ck(self.lib.vb_add_agent_per_process(self.h, C.c_int(self._aid[type_name]), buf.ctypes.data_as(C.c_void_p) if buf is not None else None,
+                                                   C.byref(out)))
+        return out.value
 
     def add_agent(self, type_name: str, state=None) -> int:
         dt = self._adt(type_name)

@@ -409,6 +409,26 @@ __global__ void halo_pack_kernel(const uint8_t* __restrict__ cols, uint32_t stri
     else if (word == 4) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
     else for (uint32_t b = 0; b < word; ++b) dp[b] = sp[b];
 }
+// died-agent ids of the other ranks (C7: join(aids), src/AgentMethods.jl:338): mark the ghosts that mirror them
+struct MarkDeadArgs {
+    const uint64_t* ids; uint32_t n; uint8_t* dead; uint32_t rank; uint32_t ntypes;
+    uint32_t base[vb::MAX_AGENT_TYPES + 2]; uint32_t lcap[vb::MAX_AGENT_TYPES + 1]; uint32_t nghost[vb::MAX_AGENT_TYPES + 1]; const uint64_t* ghost_ids[vb::MAX_AGENT_TYPES + 1];
+};
+__global__ void mark_remote_dead_kernel(const MarkDeadArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint64_t id = a.ids[i];
+    const uint32_t t = vb::type_nr(id);
+    if (id == 0 || t < 1 || t > a.ntypes || vb::process_nr(id) == a.rank) return;
+    const uint64_t* g = a.ghost_ids[t];
+    uint32_t lo = 0, hi = a.nghost[t];
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (g[mid] < id) lo = mid + 1; else hi = mid; }
+    if (lo < a.nghost[t] && g[lo] == id) a.dead[a.base[t] + a.lcap[t] + lo] = 1;
+}
+__global__ void slots_to_ids_kernel(const uint32_t* __restrict__ slots, uint32_t n, uint32_t type, uint32_t rank, uint64_t* __restrict__ ids) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = vb::agent_id(type, rank, (uint64_t)slots[i] + 1);
+}
 __global__ void gather_u64_kernel(const uint64_t* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t n, uint64_t* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[perm[i]];
@@ -1659,7 +1679,7 @@ int guard(F&& f) {
 }
 bool contains(const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }
 
-void finish_write_agent(vb_sim& s, int t, std::vector<uint32_t*>& died_flags, std::vector<uint32_t>& died_n) {
+void finish_write_agent(vb_sim& s, int t, std::vector<uint32_t*>& died_flags, std::vector<uint32_t>& died_n, std::vector<uint32_t>& died_cnt) {
     AgentStore& a = s.A(t);
     // births of this apply: pops from the reuse stack first, then fresh slots (AgentMethods.jl:37-63)
     const uint32_t pops = std::min(a.births, a.n_reuse);
@@ -1681,7 +1701,7 @@ void finish_write_agent(vb_sim& s, int t, std::vector<uint32_t*>& died_flags, st
         if (nd) {
             vbp::compact_indices_kernel<<<nblk(n_before), 256, 0, g_stream>>>(flag, pos, n_before, a.reuse + a.n_reuse); LAUNCH_CHECK();
             a.n_reuse += nd;
-            died_flags[t] = flag; died_n[t] = n_before;
+            died_flags[t] = flag; died_n[t] = n_before; died_cnt[t] = nd;
             flag = nullptr;
         }
         dfree(flag); dfree(pos); dfree(scr);
@@ -1938,7 +1958,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     // ---- finish_write! agents (Simulation.jl:807), then edges (:809), then the dead-agent purge ----
     std::vector<uint32_t*> died_flags(s.agents.size() + 1, nullptr);
     std::vector<uint32_t> died_n(s.agents.size() + 1, 0);
-    for (int w : write) if (w < vb::EDGE_REF) finish_write_agent(s, w, died_flags, died_n);
+    std::vector<uint32_t> died_cnt(s.agents.size() + 1, 0);
+    for (int w : write) if (w < vb::EDGE_REF) finish_write_agent(s, w, died_flags, died_n, died_cnt);
     for (int w : write) if (w >= vb::EDGE_REF) {
         EdgeStore& e = s.E(w - vb::EDGE_REF);
         s.build_container(w - vb::EDGE_REF, e.add_existing);
@@ -1947,6 +1968,36 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     }
     bool any_dead = false;
     for (auto p : died_flags) any_dead |= p != nullptr;
+    // multi-GPU (C7): the ids of the agents that died on the other ranks, so that edges *from* them are purged here too.
+    // Collective whenever a mortal type is written (the same decision on every rank).
+    uint64_t* remote_died = nullptr; uint32_t remote_died_n = 0;
+    bool mortal_written = false;
+    for (int w : write) if (w < vb::EDGE_REF && !s.A(w).immortal) mortal_written = true;
+    if (g_nranks > 1 && mortal_written) {
+        uint64_t mine = 0;
+        for (size_t t = 1; t <= s.agents.size(); ++t) mine += died_cnt[t];
+        std::vector<uint64_t> all;
+        allgather8_host(&mine, all);
+        uint64_t mx = 0;
+        for (uint64_t v : all) mx = std::max(mx, v);
+        if (mx) {
+            uint64_t* sendb = dalloc<uint64_t>(mx);
+            CK(cudaMemsetAsync(sendb, 0, mx * 8, g_stream));
+            uint64_t o = 0;
+            for (size_t t = 1; t <= s.agents.size(); ++t) {
+                if (!died_cnt[t]) continue;
+                AgentStore& a = s.agents[t - 1];   // this apply's deaths are the top died_cnt entries of the reuse stack
+                slots_to_ids_kernel<<<nblk(died_cnt[t]), 256, 0, g_stream>>>(a.reuse + (a.n_reuse - died_cnt[t]), died_cnt[t], (uint32_t)t, s.rank, sendb + o); LAUNCH_CHECK();
+                o += died_cnt[t];
+            }
+            remote_died_n = (uint32_t)(mx * g_nranks);
+            remote_died = dalloc<uint64_t>(remote_died_n);
+            NK(g_nccl.AllGather(sendb, remote_died, mx * 8, ncclUint8, g_comm, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(sendb);
+            any_dead = true;
+        }
+    }
     if (any_dead) {
         for (size_t e = 0; e < s.edges.size(); ++e) s.materialize_stencil((int)e);
         const uint32_t tot = s.total_slots();
@@ -1954,9 +2005,16 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         CK(cudaMemsetAsync(dead, 0, (size_t)tot + 1, g_stream));
         for (size_t t = 1; t <= s.agents.size(); ++t)
             if (died_flags[t]) { mark_dead_kernel<<<nblk(died_n[t]), 256, 0, g_stream>>>(died_flags[t], died_n[t], dead, s.base[t]); LAUNCH_CHECK(); }
+        if (remote_died) {
+            MarkDeadArgs md{};
+            md.ids = remote_died; md.n = remote_died_n; md.dead = dead; md.rank = s.rank; md.ntypes = (uint32_t)s.agents.size();
+            std::memcpy(md.base, s.base, sizeof(md.base));
+            for (size_t t = 1; t <= s.agents.size(); ++t) { md.lcap[t] = s.agents[t - 1].cap; md.nghost[t] = s.agents[t - 1].nghost; md.ghost_ids[t] = s.agents[t - 1].ghost_ids; }
+            mark_remote_dead_kernel<<<nblk(remote_died_n), 256, 0, g_stream>>>(md); LAUNCH_CHECK();
+        }
         s.purge_dead(dead);
         CK(cudaStreamSynchronize(g_stream));
-        dfree(dead);
+        dfree(dead); dfree(remote_died);
         for (auto p : died_flags) dfree(p);
     }
     CK(cudaEventRecord(s.ev[2], g_stream));
@@ -2185,6 +2243,37 @@ int vb_add_agents(vb_sim* s, int type, const void* states, uint64_t n, vb_agent_
         }
         a.nextid += n;
         for (uint64_t i = 0; i < n && ids_out; ++i) ids_out[i] = vb::agent_id((uint32_t)type, s->rank, first + i);   // ids_out may be NULL for bulk adds
+    });
+}
+
+int vb_add_agent_per_process(vb_sim* s, int type, const void* state, vb_agent_id* id_out) {
+    return guard([&] {   // add_agent_per_process!: Agent.jl:363-388 = prepare_write!(add_existing) + add_agent! + finish_write!
+        require_device();
+        if (!s->initialized) throw AssertionError("add_agent_per_process! can only be called after finish_init!");
+        if (s->intransition) throw AssertionError("add_agent_per_process! cannot be called within a transition function");
+        AgentStore& a = s->A(type);
+        uint32_t slot;
+        if (!a.immortal && a.n_reuse) {   // _get_next_id: pop the most recently freed slot
+            CK(cudaMemcpyAsync(&slot, a.reuse + (a.n_reuse - 1), 4, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            a.n_reuse -= 1;
+        } else {
+            slot = (uint32_t)(a.nextid - 1);
+            s->ensure_agent_cap(type, a.nextid);
+            a.nextid += 1;
+        }
+        a.nslots = (uint32_t)std::max<uint64_t>(a.nslots, a.nextid - 1);
+        if (a.size) {   // read := write afterwards, so the state goes to both buffers
+            uint8_t* tmp = (uint8_t*)g_pool.alloc(a.size);
+            CK(cudaMemcpyAsync(tmp, state, a.size, cudaMemcpyHostToDevice, g_stream));
+            for (int b = 0; b < (a.independent ? 1 : 2); ++b) { vbp::aos_to_soa_kernel<<<1, 64, 0, g_stream>>>(tmp, a.state[b], a.stride(), slot, 1, a.size, a.word); LAUNCH_CHECK(); }
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(tmp);
+        }
+        if (!a.immortal) { CK(cudaMemsetAsync(a.died[0] + slot, 0, 1, g_stream)); CK(cudaMemsetAsync(a.died[1] + slot, 0, 1, g_stream)); }
+        a.halo_dirty = true;
+        a.last_change = s->num_transitions;
+        if (id_out) *id_out = vb::agent_id((uint32_t)type, s->rank, (uint64_t)slot + 1);
     });
 }
 
