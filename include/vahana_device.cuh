@@ -96,7 +96,7 @@ struct EdgeView {
     uint8_t hints, kind, readable, writeable;
     // KIND_STENCIL: the edges of connect_raster_neighbors! (src/Raster.jl:139-167) kept implicit: row c holds the cells
     // c - s (wrapped or clipped) for every stencil offset s, ordered by (source linear index, s) = the reference's insertion order
-    const int8_t* st_off;     // [st_n][MAX_RASTER_DIMS] stencil offsets in _stencil_core order (src/Raster.jl:82-96)
+    int32_t st_tab;           // index into DeviceSim::stencils: offsets in _stencil_core order (src/Raster.jl:82-96)
     int32_t st_n, st_raster;
     uint32_t st_slot0;        // slot of raster cell 0 (cells occupy consecutive slots)
     uint8_t st_periodic, st_reach;
@@ -107,10 +107,15 @@ struct RasterView {
     int32_t type;             // agent type of the cells
     int64_t dims[MAX_RASTER_DIMS];
 };
+struct StencilTab {                           // lives in the kernel parameter block (constant bank)
+    int32_t lin[MAX_IMPLICIT_STENCIL];        // linear offset of each stencil entry (sum of off[k] * stride[k])
+    int8_t off[MAX_IMPLICIT_STENCIL][MAX_RASTER_DIMS];
+};
 struct DeviceSim {
     AgentView agents[MAX_AGENT_TYPES + 1];   // index = type id (1-based)
     EdgeView edges[MAX_EDGE_TYPES];
     RasterView rasters[MAX_RASTERS];
+    StencilTab stencils[MAX_RASTERS];
     uint32_t base[MAX_AGENT_TYPES + 2];      // composite base per type id; base[ntypes + 1] = total
     uint32_t n_agent_types, n_edge_types, n_rasters;
     uint32_t rank, nranks;
@@ -357,6 +362,7 @@ class Ctx {
     // calls fn(source cell linear index) for the entries first, first + step, ... of row `lin`
     template <class Fn> __device__ __forceinline__ uint32_t stencil_row(const EdgeView& ev, uint32_t lin, uint32_t first, uint32_t step, Fn&& fn) const {
         const RasterView& rv = ds.rasters[ev.st_raster];
+        const StencilTab& tab = ds.stencils[ev.st_tab];
         long long pos[MAX_RASTER_DIMS], stride[MAX_RASTER_DIMS];
         bool interior = true;
         {
@@ -371,9 +377,7 @@ class Ctx {
             uint32_t j = 0;
             for (int si = ev.st_n - 1; si >= 0; --si, ++j) {
                 if (j % step != first % step || j < first) continue;
-                long long l = 0;
-                for (int k = 0; k < rv.ndims; ++k) l += (pos[k] - ev.st_off[si * MAX_RASTER_DIMS + k]) * stride[k];
-                fn((uint32_t)l);
+                fn((uint32_t)((int32_t)lin - tab.lin[si]));
             }
             return (uint32_t)ev.st_n;
         }
@@ -382,7 +386,7 @@ class Ctx {
         for (int si = 0; si < ev.st_n; ++si) {
             long long l = 0; bool ok = true;
             for (int k = 0; k < rv.ndims; ++k) {
-                long long v = pos[k] - ev.st_off[si * MAX_RASTER_DIMS + k];
+                long long v = pos[k] - tab.off[si][k];
                 if (v < 0 || v >= rv.dims[k]) { if (!ev.st_periodic) { ok = false; break; } v %= rv.dims[k]; if (v < 0) v += rv.dims[k]; }
                 l += v * stride[k];
             }

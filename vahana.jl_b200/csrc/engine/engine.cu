@@ -727,6 +727,7 @@ struct vb_sim {
     unsigned long long* d_stats = nullptr;
     // stats of the last apply
     double ms_rw = 0, ms_fin = 0;
+    bool stats_pending = false;
     uint64_t st_edges_read = 0, st_edges_appended = 0, st_agents_called = 0, st_launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t evk[2] = {nullptr, nullptr};   // around the transition kernels themselves
@@ -936,6 +937,7 @@ void vb_sim::upload_view(uint64_t seed) {
         v.size = a.size; v.word = a.word ? a.word : 1; v.ncols = a.ncols; v.uoffset = a.uoffset;
         v.immortal = a.immortal; v.independent = a.independent; v.readable = a.prepared; v.writeable = a.writeable;
     }
+    int n_tab = 0;
     for (size_t i = 0; i < edges.size(); ++i) {
         const EdgeStore& e = edges[i];
         vb::EdgeView& v = h.edges[i];
@@ -945,8 +947,21 @@ void vb_sim::upload_view(uint64_t seed) {
         v.rlog_to = e.rlog_to; v.rlog_from = e.rlog_from; v.rlog_st = e.rlog_st; v.rlog_dst = e.rlog_dst; v.rlog_cap = e.rlog_cap;
         v.size = e.size; v.word = e.word ? e.word : 1; v.ncols = e.ncols; v.target = e.singletype ? e.target : 0;
         v.hints = (uint8_t)e.hints; v.kind = e.implicit_stencil ? (uint8_t)vb::KIND_STENCIL : e.kind; v.readable = e.readable; v.writeable = e.writeable;
-        v.st_off = e.st_off; v.st_n = e.st_n; v.st_raster = e.st_raster; v.st_slot0 = e.st_slot0; v.st_periodic = e.st_periodic; v.st_reach = (uint8_t)e.st_reach;
-        if (e.implicit_stencil) v.rows = 0xffffffffu;
+        v.st_tab = 0; v.st_n = e.st_n; v.st_raster = e.st_raster; v.st_slot0 = e.st_slot0; v.st_periodic = e.st_periodic; v.st_reach = (uint8_t)e.st_reach;
+        if (e.implicit_stencil) {
+            v.rows = 0xffffffffu;
+            v.st_tab = n_tab;
+            vb::StencilTab& tb = h.stencils[n_tab++];
+            const RasterStore& r = rasters[e.st_raster];
+            for (int si = 0; si < e.st_n; ++si) {
+                long long lin = 0, stride = 1;
+                for (size_t k = 0; k < r.dims.size(); ++k) {
+                    tb.off[si][k] = e.st_off_host[(size_t)si * vb::MAX_RASTER_DIMS + k];
+                    lin += (long long)tb.off[si][k] * stride; stride *= r.dims[k];
+                }
+                tb.lin[si] = (int32_t)lin;
+            }
+        }
     }
     for (size_t i = 0; i < rasters.size(); ++i) {
         vb::RasterView& v = h.rasters[i];
@@ -2023,13 +2038,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     cudaEventElapsedTime(&m0, s.ev[0], s.ev[1]);
     cudaEventElapsedTime(&m1, s.ev[1], s.ev[2]);
     s.ms_rw = m0; s.ms_fin = m1;
-    unsigned long long er = 0;
-    {
-        static thread_local std::vector<unsigned long long> hs(4096);
-        CK(cudaMemcpyAsync(hs.data(), s.d_stats, 4096 * 8, cudaMemcpyDeviceToHost, g_stream));
-        CK(cudaStreamSynchronize(g_stream));
-        for (int i = 0; i < 1024; ++i) er += hs[(size_t)i * 4];
-    }
+    s.stats_pending = true;   // the 1024 spread counters are fetched lazily by vb_last_apply_stats
+    const unsigned long long er = 0;
     s.st_edges_read = er; s.st_edges_appended = appended; s.st_launches = g_launches - launches0;
     s.num_transitions += 1;
 }
@@ -2477,7 +2487,8 @@ int vb_connect_raster_neighbors(vb_sim* s, const char* name, int ei, double dist
         for (size_t i = 1; i < r.ids.size() && contiguous; ++i) contiguous = r.ids[i] == r.ids[0] + i;
         const bool eligible = !getenv("VB_NO_IMPLICIT_STENCIL") && !s->initialized && e.kind == vb::KIND_CSR && !e.has_state() && !e.singleedge &&
                               !e.ignorefrom && e.raw_n == 0 && !e.implicit_stencil && contiguous && !sten.empty() &&
-                              sten.size() <= vb::MAX_IMPLICIT_STENCIL && (!e.singletype || e.target == r.type) && r.ids.size() < 0xffffffffull;
+                              sten.size() <= vb::MAX_IMPLICIT_STENCIL && (!e.singletype || e.target == r.type) && r.ids.size() < 0x7fffffffull &&
+                              std::count_if(s->edges.begin(), s->edges.end(), [](const EdgeStore& x) { return x.implicit_stencil; }) < vb::MAX_RASTERS;
         if (!eligible) { s->materialize_stencil(ei); s->emit_raster_edges(ei, ri, distance, metric, periodic != 0, st); return; }
         e.implicit_stencil = true; e.st_raster = ri; e.st_metric = metric; e.st_distance = distance; e.st_periodic = periodic != 0;
         e.st_n = (int)sten.size(); e.st_reach = 0; e.st_slot0 = (uint32_t)(vb::agent_nr(r.ids[0]) - 1);
@@ -2984,6 +2995,15 @@ int vb_raster_info(vb_sim* s, const char* name, int* ndims, int64_t* dims, vb_ag
 }
 int vb_num_transitions(vb_sim* s, int64_t* n) { *n = s->num_transitions; return VB_OK; }
 int vb_last_apply_stats(vb_sim* s, double* ms_rw, double* ms_fin, uint64_t* er, uint64_t* ea, uint64_t* ac, uint64_t* kl) {
+    if (s->stats_pending) {
+        s->stats_pending = false;
+        std::vector<unsigned long long> hs(4096);
+        if (cudaMemcpyAsync(hs.data(), s->d_stats, 4096 * 8, cudaMemcpyDeviceToHost, g_stream) == cudaSuccess && cudaStreamSynchronize(g_stream) == cudaSuccess) {
+            unsigned long long t = 0;
+            for (int i = 0; i < 1024; ++i) t += hs[(size_t)i * 4];
+            s->st_edges_read = t;
+        }
+    }
     if (ms_rw) *ms_rw = s->ms_rw; if (ms_fin) *ms_fin = s->ms_fin;
     if (er) *er = s->st_edges_read; if (ea) *ea = s->st_edges_appended; if (ac) *ac = s->st_agents_called; if (kl) *kl = s->st_launches;
     return VB_OK;
