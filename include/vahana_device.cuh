@@ -106,6 +106,9 @@ struct RasterView {
     int32_t ndims;
     int32_t type;             // agent type of the cells
     int64_t dims[MAX_RASTER_DIMS];
+    uint32_t dim32[MAX_RASTER_DIMS];    // dims / column-major strides as 32-bit values (unused dimensions: 1 / 0), and the cell count
+    uint32_t stride32[MAX_RASTER_DIMS];
+    uint32_t ncells;
 };
 struct StencilTab {                           // lives in the kernel parameter block (constant bank)
     int32_t lin[MAX_IMPLICIT_STENCIL];        // linear offset of each stencil entry (sum of off[k] * stride[k])
@@ -353,24 +356,25 @@ class Ctx {
         const RasterView& rv = ds.rasters[ev.st_raster];
         if ((int)type_nr(id) != rv.type || process_nr(id) != ds.rank) return false;
         const uint64_t slot = agent_nr(id) - 1;
-        uint64_t ncells = 1;
-        for (int k = 0; k < rv.ndims; ++k) ncells *= (uint64_t)rv.dims[k];
-        if (slot < ev.st_slot0 || slot - ev.st_slot0 >= ncells) return false;
+        if (slot < ev.st_slot0 || slot - ev.st_slot0 >= rv.ncells) return false;
         lin = (uint32_t)(slot - ev.st_slot0);
         return true;
     }
-    // calls fn(source cell linear index) for the entries first, first + step, ... of row `lin`
+    // calls fn(source cell linear index) for the entries first, first + step, ... of row `lin`; returns the row length
     template <class Fn> __device__ __forceinline__ uint32_t stencil_row(const EdgeView& ev, uint32_t lin, uint32_t first, uint32_t step, Fn&& fn) const {
         const RasterView& rv = ds.rasters[ev.st_raster];
         const StencilTab& tab = ds.stencils[ev.st_tab];
-        long long pos[MAX_RASTER_DIMS], stride[MAX_RASTER_DIMS];
+        int32_t pos[MAX_RASTER_DIMS];
         bool interior = true;
         {
-            uint32_t rest = lin; long long st = 1;
-            for (int k = 0; k < rv.ndims; ++k) {
-                pos[k] = rest % (uint32_t)rv.dims[k]; rest /= (uint32_t)rv.dims[k];
-                stride[k] = st; st *= rv.dims[k];
-                interior &= pos[k] >= ev.st_reach && pos[k] + ev.st_reach < rv.dims[k];
+            uint32_t rest = lin;
+#pragma unroll
+            for (int k = 0; k < MAX_RASTER_DIMS; ++k) {     // unused dimensions have extent 1: pos = 0, never "interior"-relevant
+                const uint32_t d = rv.dim32[k];
+                if (k < rv.ndims) {
+                    pos[k] = (int32_t)(rest % d); rest /= d;
+                    interior &= pos[k] >= (int32_t)ev.st_reach && pos[k] + (int32_t)ev.st_reach < (int32_t)d;
+                } else pos[k] = 0;
             }
         }
         if (interior) {   // no wrap, no clip: walking the stencil backwards yields ascending source indices
@@ -384,11 +388,14 @@ class Ctx {
         unsigned long long key[MAX_IMPLICIT_STENCIL];
         uint32_t n = 0;
         for (int si = 0; si < ev.st_n; ++si) {
-            long long l = 0; bool ok = true;
-            for (int k = 0; k < rv.ndims; ++k) {
-                long long v = pos[k] - tab.off[si][k];
-                if (v < 0 || v >= rv.dims[k]) { if (!ev.st_periodic) { ok = false; break; } v %= rv.dims[k]; if (v < 0) v += rv.dims[k]; }
-                l += v * stride[k];
+            uint32_t l = 0; bool ok = true;
+#pragma unroll
+            for (int k = 0; k < MAX_RASTER_DIMS; ++k) {
+                if (k >= rv.ndims) break;
+                int32_t v = pos[k] - tab.off[si][k];
+                const int32_t d = (int32_t)rv.dim32[k];
+                if (v < 0 || v >= d) { if (!ev.st_periodic) { ok = false; break; } v %= d; if (v < 0) v += d; }
+                l += (uint32_t)v * rv.stride32[k];
             }
             if (!ok) continue;
             const unsigned long long kk = ((unsigned long long)l << 6) | (unsigned)si;

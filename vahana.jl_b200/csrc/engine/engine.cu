@@ -12,6 +12,7 @@
 #include <nccl.h>   // types and enums only: the library is resolved at run time (dlopen), see Nccl below
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -91,6 +92,21 @@ int g_rank = 0, g_nranks = 1;
 
 void allgather8_host(const void* mine, std::vector<uint64_t>& all);
 
+// VB_TRACE=1: per-phase host wall times of apply! on stderr (the analogue of the reference's <Begin>/<End> duration log, src/Logging.jl:30-73)
+struct Trace {
+    bool on = getenv("VB_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0;
+    void begin() { if (on) { cudaStreamSynchronize(g_stream); t0 = std::chrono::steady_clock::now(); } }
+    void end(const char* what, const std::string& detail = "") {
+        if (!on) return;
+        cudaStreamSynchronize(g_stream);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[vb trace] %-28s %-24s %9.3f ms\n", what, detail.c_str(), ms);
+        t0 = std::chrono::steady_clock::now();
+    }
+};
+Trace g_trace;
+
 void require_device() {
     if (g_device < 0) throw CudaError("vahana_b200: vb_init() has not been called or no CUDA device is available (no CPU fallback)");
 }
@@ -99,16 +115,19 @@ void require_device() {
 struct Pool {
     std::multimap<size_t, void*> free_;
     std::unordered_map<void*, size_t> size_;
+    // size classes: four per octave above 1 MB (<= 25 % slack), so the slowly growing buffers of a growing population keep
+    // hitting cached blocks instead of calling cudaMalloc every step
     static size_t round(size_t b) {
-        size_t g = 256;
-        if (b > (1u << 20)) g = 1u << 20;
+        if (b <= (1u << 20)) return ((b + 255) / 256) * 256;
+        int lg = 63 - __builtin_clzll((unsigned long long)b);
+        const size_t g = (size_t)1 << (lg - 2);
         return ((b + g - 1) / g) * g;
     }
     void* alloc(size_t bytes) {
         if (bytes == 0) bytes = 256;
         const size_t r = round(bytes);
         auto it = free_.lower_bound(r);
-        if (it != free_.end() && it->first <= r + r / 4) {
+        if (it != free_.end() && it->first <= r + r / 2) {
             void* p = it->second;
             free_.erase(it);
             return p;
@@ -966,7 +985,10 @@ void vb_sim::upload_view(uint64_t seed) {
     for (size_t i = 0; i < rasters.size(); ++i) {
         vb::RasterView& v = h.rasters[i];
         v.cells = rasters[i].cells; v.ndims = (int)rasters[i].dims.size(); v.type = rasters[i].type;
-        for (size_t k = 0; k < rasters[i].dims.size(); ++k) v.dims[k] = rasters[i].dims[k];
+        uint64_t st = 1;
+        for (int k = 0; k < vb::MAX_RASTER_DIMS; ++k) { v.dim32[k] = 1; v.stride32[k] = 0; }
+        for (size_t k = 0; k < rasters[i].dims.size(); ++k) { v.dims[k] = rasters[i].dims[k]; v.dim32[k] = (uint32_t)rasters[i].dims[k]; v.stride32[k] = (uint32_t)st; st *= (uint64_t)rasters[i].dims[k]; }
+        v.ncells = (uint32_t)std::min<uint64_t>(st, 0xffffffffull);
     }
     std::memcpy(h.base, base, sizeof(h.base));
     h.n_agent_types = (uint32_t)agents.size(); h.n_edge_types = (uint32_t)edges.size(); h.n_rasters = (uint32_t)rasters.size();
@@ -1761,6 +1783,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     for (int w : write) if (w >= vb::EDGE_REF) s.materialize_stencil(w - vb::EDGE_REF);
     if (with_edge >= 0) s.materialize_stencil(with_edge);
     s.merge_all_pending();
+    g_trace.begin();
     const unsigned long long launches0 = g_launches;
     s.intransition = true;
     struct Reset {
@@ -1806,6 +1829,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             }
         }
     }
+    g_trace.end("prepare_write!", tname);
     CK(cudaMemsetAsync(s.d_stats, 0, 4096 * 8, g_stream));
     CK(cudaEventRecord(s.ev[0], g_stream));
     s.halo_bytes = 0;
@@ -1966,6 +1990,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         for (auto p : tmp) dfree(p);
     }
     CK(cudaEventRecord(s.ev[1], g_stream));
+    g_trace.end("transition loop", tname);
     s.check_device_error("apply!");
     if (g_nranks > 1)   // transmit_edges! for every writable edge type (Simulation.jl:800), collective
         for (int w : write) if (w >= vb::EDGE_REF) s.transmit_edges(w - vb::EDGE_REF);
@@ -1974,12 +1999,14 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     std::vector<uint32_t*> died_flags(s.agents.size() + 1, nullptr);
     std::vector<uint32_t> died_n(s.agents.size() + 1, 0);
     std::vector<uint32_t> died_cnt(s.agents.size() + 1, 0);
-    for (int w : write) if (w < vb::EDGE_REF) finish_write_agent(s, w, died_flags, died_n, died_cnt);
+    g_trace.end("transmit_edges!", tname);
+    for (int w : write) if (w < vb::EDGE_REF) { finish_write_agent(s, w, died_flags, died_n, died_cnt); g_trace.end("finish_write! agents", s.A(w).name); }
     for (int w : write) if (w >= vb::EDGE_REF) {
         EdgeStore& e = s.E(w - vb::EDGE_REF);
         s.build_container(w - vb::EDGE_REF, e.add_existing);
         e.last_change = s.num_transitions;
         e.writeable = false;
+        g_trace.end("finish_write! edges", e.name);
     }
     bool any_dead = false;
     for (auto p : died_flags) any_dead |= p != nullptr;
@@ -2030,6 +2057,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         s.purge_dead(dead);
         CK(cudaStreamSynchronize(g_stream));
         dfree(dead); dfree(remote_died);
+        g_trace.end("purge dead agents' edges", tname);
         for (auto p : died_flags) dfree(p);
     }
     CK(cudaEventRecord(s.ev[2], g_stream));
