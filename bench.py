@@ -212,8 +212,8 @@ def run_engine(args):
     lib.vb_halo_bytes(sim.h, C.byref(hb))
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist.barrier()
+        dist.destroy_process_group()
         return
     assert edges_read == E_local * args.steps, (edges_read, E_local)
     peak, peak_src = measured_peaks()
@@ -227,7 +227,7 @@ def run_engine(args):
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    cpu_eps, cpu_ms, cpu_ne = time_oracle(vh, args.cpu_agents, 3, 1) if not args.no_cpu else (None, None, None)
+    cpu_eps, cpu_ms, cpu_ne = time_oracle(vh, args.cpu_agents, 3, 1) if (not args.no_cpu and world == 1) else (None, None, None)
     value = E * args.steps / (ms_total * 1e-3)
     line = {
         "metric": "edges/sec per apply! (Hegselmann-Krause read+write phase)", "value": value, "unit": "edges/s",
@@ -248,8 +248,9 @@ def run_engine(args):
                 "note": "apply! + mapreduce(opinion,+) through the Python/ctypes API per step; agent state stays resident on device as it stays resident in the reference's process"},
         "gpu_launches": launches, "clocks": clk,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

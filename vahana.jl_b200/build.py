@@ -9,6 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(CSRC, "build")
 OUT = os.path.join(OUT_DIR, "libvahana_b200.so")
 SOURCES = [os.path.join(CSRC, "engine", "engine.cu"), os.path.join(CSRC, "transitions", "builtin.cu"),
+           os.path.join(CSRC, "transitions", "builtin_tests.cu"),
            os.path.join(CSRC, "workloads", "generators.cu")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -26,10 +27,11 @@ def _deps():
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
-    objs = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+    newest = max(os.path.getmtime(d) for d in _deps())
+
+    def compile_one(src):
         obj = os.path.join(OUT_DIR, os.path.basename(src) + ".o")
-        newest = max(os.path.getmtime(d) for d in _deps())
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
             cmd = ["nvcc", *FLAGS, "-c", src, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -40,7 +42,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
             if verbose:
                 print(r.stderr[-2000:])
-        objs.append(obj)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=4) as ex:     # the translation units compile concurrently
+        objs = list(ex.map(compile_one, SOURCES))
     if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs, "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
