@@ -151,6 +151,12 @@ int vb_last_apply_stats(vb_sim* sim, double* ms_read_write, double* ms_finish, u
                         uint64_t* edges_appended, uint64_t* agents_called, uint64_t* kernel_launches);
 uint64_t vb_device_view_bytes(void);               /* bytes of the simulation view uploaded host->device per transition launch */
 int vb_last_kernel_ms(vb_sim* sim, double* ms_out); /* CUDA-event time of the transition kernels of the last apply */
+/* Policy of the source-blocked read phase of reduce transitions (include/vahana_model.h, vb::ReduceTransition): block size in MB of
+   source states (0 disables), activation threshold in MB of the source type's state array, eager = build at first sight instead of
+   waiting for a container that survived one apply.  Negative values keep the defaults (VB_BLOCK_MB / VB_BLOCK_MIN_MB / VB_BLOCK_EAGER). */
+int vb_set_read_blocking(vb_sim* sim, double block_mb, double min_mb, int eager);
+/* Source blocks swept by the read phase of the last apply (0 = direct path): which kernel shape ran (read phase). */
+int vb_last_apply_blocks(vb_sim* sim, uint32_t* nblocks_out);
 
 #ifdef __cplusplus
 }

@@ -132,6 +132,38 @@ struct TransitionBase {
     using EdgeRemoves = IntList<>;                // edge types the functor calls remove_edges on
     static constexpr int kPrimaryEdge = -1;       // cooperative functors: the edge type whose row the functor walks;
                                                   // lets the engine bin agents by degree (sub-warp / warp / block per agent)
+    static constexpr bool kReduce = false;        // true for vb::ReduceTransition functors (init / fold / merge / finish)
+};
+
+// A *reduce transition*: the common shape "fold the states of my in-neighbours, then update myself"
+// (neighborstates + reduce in the reference's models, e.g. docs/examples/hegselmann.jl:134-144) split into its parts, so that
+// the engine is free to choose how the row is walked: lanes of a group with a strided share each (direct path), or one sweep per
+// L2-sized block of the source-state array with the accumulator parked in HBM between sweeps (source-blocked path).
+//
+//     struct Step : vb::ReduceTransition<Step> {
+//         using State = HKAgent;  using Source = HKAgent;           // called agent / neighbour state
+//         struct Acc { double sum; uint32_t n; };                    // trivially copyable accumulator
+//         static constexpr int kAccBytes = 12;                       // leading bytes of Acc that carry information
+//         static constexpr int kPrimaryEdge = E_KNOWS, kSourceType = T_HKAGENT;
+//         template <class Ctx> VB_HD void init(const Ctx&, const State& self, Acc& a) const;          // a = identity of merge
+//         template <class Ctx> VB_HD void fold(const Ctx&, const State& self, const Source& nb, Acc& a) const;
+//         VB_HD void merge(Acc& a, const Acc& b) const;              // commutative, associative up to rounding
+//         template <class Ctx> VB_HD bool finish(const Ctx&, State& self, vb::AgentID id, const Acc& a) const;   // false = die
+//     };
+//
+// The oracle folds the row strictly left to right (one lane); the GPU paths combine partial accumulators with merge().
+template <class D> struct ReduceTransition : TransitionBase {
+    static constexpr bool kCooperative = true;
+    static constexpr bool kReduce = true;
+    template <class Ctx, class S> VB_HD bool operator()(Ctx& ctx, S& self, AgentID id) const {
+        const D& d = static_cast<const D&>(*this);
+        typename D::Acc a;
+        d.init(ctx, self, a);
+        ctx.template for_each_neighborstate<typename D::Source>(D::kPrimaryEdge, D::kSourceType, id,
+                                                                [&](const typename D::Source& nb) { d.fold(ctx, self, nb, a); });
+        a = ctx.reduce_acc(a, [&](typename D::Acc& x, const typename D::Acc& y) { d.merge(x, y); });
+        return d.finish(ctx, self, id, a);
+    }
 };
 
 // Raster position (up to 4 dimensions, 1-based like CartesianIndex).

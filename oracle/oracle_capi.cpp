@@ -307,5 +307,7 @@ int vb_last_apply_stats(vb_sim* sim, double* ms_rw, double* ms_fin, uint64_t* er
     if (kl) *kl = 0;
     return VB_OK;
 }
+int vb_set_read_blocking(vb_sim*, double, double, int) { return VB_OK; }   // the oracle walks every row left to right
+int vb_last_apply_blocks(vb_sim*, uint32_t* nb) { if (nb) *nb = 0; return VB_OK; }
 
 }  // extern "C"

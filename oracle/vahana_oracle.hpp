@@ -673,6 +673,7 @@ class Ctx {
     template <class T> T sum(T v) const { return v; }
     template <class T> T max(T v) const { return v; }
     template <class T> T min(T v) const { return v; }
+    template <class A, class M> A reduce_acc(const A& a, M&&) const { return a; }   // vb::ReduceTransition: one lane, nothing to merge
 
     static void avail(bool ok, const char* what) { if (!ok) throw AssertionError(std::string(what) + " is not defined for this hint combination"); }
 

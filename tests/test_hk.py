@@ -114,3 +114,50 @@ def test_powerlaw_device_generator_matches_host_and_oracle(oracle, cuda):
         o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
         np.testing.assert_allclose(g.all_agents("HKAgent")["opinion"], o.all_agents("HKAgent")["opinion"], rtol=RTOL)
     assert abs(g.mapreduce("opinion", "+", "HKAgent") - o.mapreduce("opinion", "+", "HKAgent")) < 1e-12 * n
+
+
+# ---- source-blocked read phase (vb::ReduceTransition) -------------------------------------------------------
+# The sweep per source block adds the blocks' partial sums in block order instead of row order: same tolerance as above.
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,block_mb", [(300, 3, 0.0005), (20000, 8, 0.02), (20000, 8, 0.081), (50001, 5, 0.05)])
+def test_hk_blocked_read_phase_vs_oracle(oracle, cuda, n, m, block_mb):
+    uv = ba_graph(n, m, 1)
+    op0 = np.random.default_rng(1).random(n)
+    g, _ = hk_sim(cuda, n, uv, op0)
+    o, _ = hk_sim(oracle, n, uv, op0)
+    g.set_read_blocking(block_mb, 0.0, 1)              # tiny blocks, no size threshold, build at first sight
+    min_nb = min(int(np.ceil(n * 8 / (block_mb * 1e6))), 64)      # blocks cover the type's capacity (>= n slots)
+    for step in range(4):
+        g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        st = g.last_apply_stats()
+        assert 2 <= min_nb <= st["source_blocks"] <= 64, st
+        assert st["edges_read"] == 2 * len(uv) + n
+        np.testing.assert_allclose(_opinions(g), _opinions(o), rtol=RTOL, atol=0)
+
+
+@pytest.mark.gpu
+def test_hk_blocked_matches_direct_on_hub_graph(oracle, cuda):
+    """Power-law rows up to the block-per-agent class (>= 1024 entries) next to blocked sweeps: the heavy rows are
+    finished by the direct pass, every other row by the last sweep; the default policy waits for the second apply."""
+    import ctypes as C
+    from models import hk_model
+    n = 200000
+    sims = []
+    for blocked in (False, True):
+        g = vh.create_simulation(hk_model(), backend=cuda)
+        ne = C.c_uint64()
+        cuda.check(cuda.lib.vbw_hk_powerlaw_build(g.h, 1, 0, C.c_uint64(n), C.c_uint64(4), C.c_uint64(5), C.c_double(6.8333), C.c_uint32(1000000),
+                                                  C.c_uint64(30000), C.byref(ne)))
+        g.finish_init()
+        g.set_read_blocking(0.2 if blocked else 0.0, 0.0, 0)
+        sims.append(g)
+    d, b = sims
+    for step in range(4):
+        d.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        b.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        assert d.last_apply_stats()["source_blocks"] == 0
+        nb = b.last_apply_stats()["source_blocks"]
+        assert nb == (0 if step == 0 else 8), nb           # first apply: direct (the container has not been seen twice yet)
+        assert b.last_apply_stats()["edges_read"] == d.last_apply_stats()["edges_read"] == ne.value
+        np.testing.assert_allclose(_opinions(b), _opinions(d), rtol=RTOL, atol=0)

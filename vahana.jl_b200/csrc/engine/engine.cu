@@ -468,6 +468,51 @@ __global__ void heavy_flags_kernel(const uint32_t* __restrict__ off, uint32_t ro
     const uint32_t r = row0 + (uint32_t)i;
     flag[i] = (r < rows && off[r + 1] - off[r] >= heavy_min) ? 1u : 0u;
 }
+
+// ---- source-blocked view of a CSR (reduce transitions): count -> scan -> fill, one thread per called row ----------------------
+// Rows with >= heavy_min entries stay with the block-per-agent pass and contribute nothing here.
+__global__ void blk_heavy_bits_kernel(const uint32_t* __restrict__ off, uint32_t row0, uint32_t n, uint32_t rows, uint32_t heavy_min, uint32_t* __restrict__ bits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = row0 + (uint32_t)i;
+    const bool heavy = i < n && r < rows && off[r + 1] - off[r] >= heavy_min;
+    const unsigned b = __ballot_sync(0xffffffffu, heavy);
+    if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = b;
+}
+struct BlkBuildArgs {
+    const uint32_t* off; const uint32_t* src; uint32_t row0, n, rows, heavy_min;
+    uint32_t tb, nsl;            // composite base and slot count (local + ghosts) of the source type
+    uint32_t bsize, nb, rpad;
+    uint32_t* boff; uint32_t* bsrc; uint32_t* error;
+};
+__global__ void blk_count_kernel(const BlkBuildArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint32_t r = a.row0 + (uint32_t)i;
+    if (r >= a.rows) return;
+    const uint32_t b0 = a.off[r], b1 = a.off[r + 1];
+    if (b1 - b0 >= a.heavy_min) return;
+    for (uint32_t k = b0; k < b1; ++k) {
+        const uint32_t s = a.src[k] - a.tb;
+        if (s >= a.nsl) { atomicOr(a.error, 1u); continue; }     // a source of another agent type
+        a.boff[(size_t)(s / a.bsize) * a.rpad + i] += 1;          // one thread per row: no atomics
+    }
+}
+__global__ void blk_fill_kernel(const BlkBuildArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint32_t r = a.row0 + (uint32_t)i;
+    if (r >= a.rows) return;
+    const uint32_t b0 = a.off[r], b1 = a.off[r + 1];
+    if (b1 - b0 >= a.heavy_min) return;
+    uint16_t cur[64];                                             // entries of this row already placed, per block (row < heavy_min <= 65535)
+    for (uint32_t b = 0; b < a.nb; ++b) cur[b] = 0;
+    for (uint32_t k = b0; k < b1; ++k) {
+        const uint32_t s = a.src[k] - a.tb;
+        if (s >= a.nsl) continue;
+        const uint32_t b = s / a.bsize;
+        a.bsrc[a.boff[(size_t)b * a.rpad + i] + cur[b]++] = s;    // row order is kept inside every block
+    }
+}
 __global__ void mark_dead_kernel(const uint32_t* __restrict__ flag, uint32_t n, uint8_t* __restrict__ dead, uint32_t base) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) dead[base + i] = 1;
@@ -713,7 +758,18 @@ struct EdgeStore {
     bool readable = false, writeable = false, add_existing = false;
     int64_t last_change = 0;
     // degree-binning cache: slots of agent type `heavy_type` whose row has >= HEAVY_MIN entries
-    uint32_t* heavy_rows = nullptr; uint32_t heavy_n = 0; int heavy_type = 0; uint64_t heavy_version = ~0ull; uint64_t version = 0;
+    uint32_t* heavy_rows = nullptr; uint32_t heavy_n = 0; int heavy_type = 0; uint32_t heavy_min = 0; uint64_t heavy_version = ~0ull; uint64_t version = 0;
+    // source-blocked view of the CSR columns for reduce transitions (include/vahana_device.cuh): per block b of the
+    // source type's slots an offset array boff + b * rpad ([n + 1] positions into bsrc) and the rows' sources inside that block
+    struct Blocked {
+        uint32_t* boff = nullptr; uint32_t* bsrc = nullptr; uint32_t* heavy_bits = nullptr; uint8_t* acc = nullptr;
+        uint32_t nb = 0, bsize = 0, rpad = 0, n = 0, acc_bytes = 0, heavy_min = 0;
+        std::vector<uint32_t> bstart;                 // position in bsrc where each block's entries start (nb + 1 values)
+        int called = 0, source = 0;
+        uint64_t version = ~0ull, epoch = ~0ull;      // container version / sim layout epoch the view was built for
+        uint64_t seen_version = ~0ull; uint32_t seen = 0;   // how many applies found the same container (static network => worth building)
+        bool refused = false;                          // the build found a source of another type: stay on the direct path
+    } blk;
     bool has_src() const { return !ignorefrom; }
     bool has_state() const { return !stateless && size > 0; }
 };
@@ -765,6 +821,10 @@ struct vb_sim {
     void build_ghosts(const uint64_t* const* extra = nullptr, const uint64_t* extra_n = nullptr, int n_extra = 0);
     void halo_exchange(int t);
     uint64_t halo_bytes = 0;   // bytes received by the last apply's halo exchanges
+    double blk_block_mb = -1, blk_min_mb = -1; int blk_eager = -1;   // vb_set_read_blocking (negative = environment / default)
+    uint32_t last_blocked_nb = 0;   // source blocks swept by the last apply's read phase (0 = direct path)
+    uint64_t layout_epoch = 0; // bumped whenever stored composite indices are renumbered (rebase): invalidates blocked views
+    bool ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min);
     void rebase(const uint32_t* old_base, const uint32_t* old_lcap = nullptr, const uint32_t* const* remap = nullptr);
     void exchange_ghost_requests();
     void transmit_edges(int e);
@@ -791,8 +851,13 @@ void free_agent(AgentStore& a) {
     dfree(a.died[0]); dfree(a.died[1]); dfree(a.reuse); dfree(a.ghost_ids); dfree(a.send_slots); dfree(a.send_buf);
     a.state[0] = a.state[1] = a.died[0] = a.died[1] = nullptr; a.reuse = nullptr; a.ghost_ids = nullptr; a.send_slots = nullptr; a.send_buf = nullptr;
 }
+void free_blocked(EdgeStore& e) {
+    dfree(e.blk.boff); dfree(e.blk.bsrc); dfree(e.blk.heavy_bits); dfree(e.blk.acc);
+    e.blk = EdgeStore::Blocked{};
+}
 void free_edge_read(EdgeStore& e) {
     ++e.version;
+    if (e.blk.boff) free_blocked(e);
     dfree(e.off); dfree(e.src); dfree(e.st); dfree(e.cnt);
     e.off = e.src = e.cnt = nullptr; e.st = nullptr; e.nnz = e.st_cap = 0; e.rows = 0;
 }
@@ -812,7 +877,7 @@ void free_chunks(EdgeStore& e) {
 
 vb_sim::~vb_sim() {
     for (auto& a : agents) free_agent(a);
-    for (auto& e : edges) { free_edge_read(e); free_edge_log(e); free_chunks(e); dfree(e.st_off); dfree(e.heavy_rows); }
+    for (auto& e : edges) { free_edge_read(e); free_edge_log(e); free_chunks(e); dfree(e.st_off); dfree(e.heavy_rows); free_blocked(e); }
     for (auto& r : rasters) dfree(r.cells);
     dfree(d_error); dfree(d_scalars); dfree(d_stats);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -890,6 +955,7 @@ void vb_sim::rebase(const uint32_t* old_base, const uint32_t* old_lcap, const ui
         ra.remap[t] = remap ? remap[t] : nullptr;
         same &= ra.old_lcap[t] == ra.new_lcap[t] && !ra.remap[t];
     }
+    if (!same) ++layout_epoch;
     for (auto& e : edges) {
         if (!same && e.src && e.nnz) { rebase_values_kernel<<<nblk(e.nnz), 256, 0, g_stream>>>(e.src, e.nnz, ra); LAUNCH_CHECK(); }
         if (!same && e.log_from && e.log_n) { rebase_values_kernel<<<nblk(e.log_n), 256, 0, g_stream>>>(e.log_from, e.log_n, ra); LAUNCH_CHECK(); }
@@ -1609,6 +1675,88 @@ void vb_sim::transmit_edges(int ei) {
 }
 
 // per-step halo: pack the states the peers mirror, grouped ncclSend/ncclRecv (all-to-all-v) straight into the ghost segments
+
+// Source-blocked view of edge type `ei` for the reduce transition `ti` called on agent type C (n slots).  Returns true when the view
+// is ready.  Policy: only for gather-bound shapes (the source type's state array is several times the L2 set-aside) and only once
+// the same container has been seen by two applies (a network rebuilt every step never amortises the build).
+// VB_BLOCK=0 disables, VB_BLOCK_MB sets the block size (default 60 MB of source states), VB_BLOCK_MIN_MB the activation threshold
+// (default 192 MB), VB_BLOCK_EAGER=1 builds at first sight (tests).
+bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min) {
+    static const bool enabled = !(getenv("VB_BLOCK") && atoi(getenv("VB_BLOCK")) == 0);
+    static const double env_block_mb = getenv("VB_BLOCK_MB") ? atof(getenv("VB_BLOCK_MB")) : 60.0;
+    static const double env_min_mb = getenv("VB_BLOCK_MIN_MB") ? atof(getenv("VB_BLOCK_MIN_MB")) : 192.0;
+    static const bool env_eager = getenv("VB_BLOCK_EAGER") && atoi(getenv("VB_BLOCK_EAGER")) != 0;
+    const double block_mb = blk_block_mb > 0 ? blk_block_mb : env_block_mb;       // vb_set_read_blocking overrides the environment
+    const double min_mb = blk_min_mb >= 0 ? blk_min_mb : env_min_mb;
+    const bool eager = blk_eager >= 0 ? blk_eager != 0 : env_eager;
+    if (!enabled || blk_block_mb == 0 || !ti->reduce || !ti->launch_blocked) return false;
+    EdgeStore& pe = E(ei);
+    AgentStore& src = A(ti->source_type);
+    AgentStore& a = A(C);
+    if (pe.kind != vb::KIND_CSR || !pe.off || !pe.src || pe.implicit_stencil || !pe.nnz) return false;
+    if (pe.singletype && pe.target != C) return false;
+    if (!src.size || src.size != ti->source_size) return false;
+    if (a.independent && ti->source_type == C) return false;          // in-place states: a later sweep would read updated sources
+    const uint32_t nsl = src.cap + src.nghost;
+    if ((double)nsl * src.size < min_mb * 1e6) return false;
+    uint32_t bsize = (uint32_t)std::max<double>(1.0, block_mb * 1e6 / src.size);
+    uint32_t nb = (nsl + bsize - 1) / bsize;
+    if (nb > 64) { bsize = (nsl + 63) / 64; nb = (nsl + bsize - 1) / bsize; }
+    if (nb < 2) return false;
+    EdgeStore::Blocked& k = pe.blk;
+    if (k.boff && k.version == pe.version && k.epoch == layout_epoch && k.called == C && k.source == ti->source_type && k.n == n &&
+        k.acc_bytes == ti->acc_bytes && k.bsize == bsize && k.heavy_min == heavy_min)
+        return true;
+    if (k.seen_version != pe.version) { k.seen_version = pe.version; k.seen = 1; k.refused = false; }
+    else if (k.seen < 0xffffffffu) ++k.seen;
+    if (k.refused || (!eager && k.seen < 2)) return false;
+    const uint64_t rpad = ((uint64_t)n + 1 + 3) & ~3ull;
+    if (rpad * nb >= 0xfffffff0ull) return false;
+    {   // drop a stale view, keep the bookkeeping
+        const uint64_t sv = k.seen_version; const uint32_t sn = k.seen;
+        free_blocked(pe);
+        k.seen_version = sv; k.seen = sn;
+    }
+    g_trace.begin();
+    try {
+        const uint64_t total = rpad * nb;
+        k.boff = dalloc<uint32_t>(total + 4);
+        CK(cudaMemsetAsync(k.boff, 0, (total + 4) * 4, g_stream));
+        CK(cudaMemsetAsync(d_scalars, 0, 8, g_stream));
+        BlkBuildArgs ba{};
+        ba.off = pe.off; ba.src = pe.src; ba.row0 = pe.singletype ? 0u : base[C]; ba.n = n; ba.rows = pe.rows; ba.heavy_min = heavy_min;
+        ba.tb = base[ti->source_type]; ba.nsl = nsl; ba.bsize = bsize; ba.nb = nb; ba.rpad = (uint32_t)rpad;
+        ba.boff = k.boff; ba.bsrc = nullptr; ba.error = d_scalars + 1;
+        blk_count_kernel<<<nblk(n), 256, 0, g_stream>>>(ba); LAUNCH_CHECK();
+        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(total + 1));
+        vbp::exclusive_scan(k.boff, k.boff, total + 1, d_scalars, scr, g_stream); g_launches += 3;
+        uint32_t res[2] = {0, 0};
+        CK(cudaMemcpyAsync(res, d_scalars, 8, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(scr);
+        if (res[1]) { free_blocked(pe); k.seen_version = pe.version; k.seen = 2; k.refused = true; return false; }
+        k.bstart.assign(nb + 1, res[0]);
+        for (uint32_t b = 0; b < nb; ++b) CK(cudaMemcpyAsync(&k.bstart[b], k.boff + (size_t)b * rpad, 4, cudaMemcpyDeviceToHost, g_stream));
+        k.bsrc = dalloc<uint32_t>((uint64_t)res[0] + 64);
+        ba.bsrc = k.bsrc;
+        blk_fill_kernel<<<nblk(n), 256, 0, g_stream>>>(ba); LAUNCH_CHECK();
+        k.heavy_bits = dalloc<uint32_t>(((uint64_t)n + 31) / 32 + 1);
+        blk_heavy_bits_kernel<<<nblk(n), 256, 0, g_stream>>>(pe.off, ba.row0, n, pe.rows, heavy_min, k.heavy_bits); LAUNCH_CHECK();
+        k.acc = (uint8_t*)g_pool.alloc((size_t)rpad * ti->acc_bytes);
+        CK(cudaStreamSynchronize(g_stream));
+    } catch (...) {
+        free_blocked(pe);
+        k.seen_version = pe.version; k.seen = 2; k.refused = true;     // e.g. out of memory: stay on the direct path
+        cudaGetLastError();
+        return false;
+    }
+    k.heavy_min = heavy_min;
+    k.nb = nb; k.bsize = bsize; k.rpad = (uint32_t)rpad; k.n = n; k.acc_bytes = ti->acc_bytes; k.called = C; k.source = ti->source_type;
+    k.version = pe.version; k.epoch = layout_epoch;
+    g_trace.end("build source-blocked view", pe.name);
+    return true;
+}
+
 void vb_sim::halo_exchange(int t) {
     AgentStore& a = A(t);
     if (g_nranks <= 1 || !a.halo_dirty) return;
@@ -1834,6 +1982,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     CK(cudaEventRecord(s.ev[0], g_stream));
     s.halo_bytes = 0;
     for (int r : read) if (r < vb::EDGE_REF) s.halo_exchange(r);   // prepare_read!: transmit_agents! (AgentMethods.jl:484-496)
+    if (g_nranks > 1) g_trace.end("halo exchange", tname);
     s.st_agents_called = 0;
     s.ms_kernel = 0;
     uint64_t appended = 0;
@@ -1933,13 +2082,19 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             la.mode = vb::MODE_DIRECT;
             la.primary_edge = -1; la.heavy_min = 0; la.group = 0; la.rows = nullptr;
             uint32_t heavy_n = 0; const uint32_t* heavy_rows = nullptr;
+            bool blocked = false;
             if (ti->cooperative && ti->primary_edge >= 0 && with_edge < 0) {
                 // degree binning (north_star: sub-warp / warp per agent, block per agent for rows >= 1024 entries)
                 EdgeStore& pe = s.E(ti->primary_edge);
                 if (pe.implicit_stencil) la.group = 1;   // grid stencil: a thread per cell, neighbour loads of a warp are adjacent
                 else if (pe.kind == vb::KIND_CSR && pe.off && (!pe.singletype || pe.target == C)) {
-                    constexpr uint32_t HEAVY_MIN = 1024;
-                    if (pe.heavy_version != pe.version || pe.heavy_type != C) {
+                    // Reduce transitions over a static network whose source states dwarf L2 sweep the rows once per L2-sized
+                    // source block; only hub rows of >= 16384 entries are left to the block-per-agent pass there (the sweeps fold
+                    // long rows warp-cooperatively), the direct path hands over rows of >= 1024 entries.
+                    constexpr uint32_t HEAVY_DIRECT = 1024, HEAVY_BLOCKED = 16384;
+                    blocked = ti->reduce && s.ensure_blocked(ti->primary_edge, ti, C, n, HEAVY_BLOCKED);
+                    const uint32_t HEAVY_MIN = blocked ? HEAVY_BLOCKED : HEAVY_DIRECT;
+                    if (pe.heavy_version != pe.version || pe.heavy_type != C || pe.heavy_min != HEAVY_MIN) {
                         dfree(pe.heavy_rows); pe.heavy_rows = nullptr; pe.heavy_n = 0;
                         uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
                         uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
@@ -1952,7 +2107,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                             pe.heavy_rows = dalloc<uint32_t>(hn);
                             vbp::compact_indices_kernel<<<nblk(n), 256, 0, g_stream>>>(flag, pos, n, pe.heavy_rows); LAUNCH_CHECK();
                         }
-                        pe.heavy_n = hn; pe.heavy_type = C; pe.heavy_version = pe.version;
+                        pe.heavy_n = hn; pe.heavy_type = C; pe.heavy_version = pe.version; pe.heavy_min = HEAVY_MIN;
                         CK(cudaStreamSynchronize(g_stream));
                         dfree(flag); dfree(pos); dfree(scr);
                     }
@@ -1962,6 +2117,41 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                     la.group = avg < 48.0 ? 8 : 32;
                 }
             }
+            if (blocked) {
+                EdgeStore& pe = s.E(ti->primary_edge);
+                const EdgeStore::Blocked& k = pe.blk;
+                uint32_t swept = 0;
+                static int n_sm = [] { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, g_device); return v; }();
+                static const int l2_mb = getenv("VB_BLOCK_L2_MB") ? atoi(getenv("VB_BLOCK_L2_MB")) : 64;
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)l2_mb << 20);   // room for the evict_last source block
+                cudaGetLastError();
+                s.upload_view(seed);
+                CK(cudaEventRecord(s.evk[0], g_stream));
+                vb::LaunchArgs lb = la;
+                lb.blk_src = k.bsrc; lb.blk_acc = k.acc; lb.blk_stride = k.rpad; lb.blk_heavy = heavy_n ? k.heavy_bits : nullptr;
+                lb.blk_ctas = n_sm * ti->blocked_ctas_per_sm();
+                // sweeps over blocks that hold no entry (capacity beyond the agents in use) are skipped; the first sweep that runs
+                // initialises the accumulators, the last one runs finish()
+                std::vector<uint32_t> todo;
+                for (uint32_t b = 0; b < k.nb; ++b) if (k.bstart[b + 1] > k.bstart[b]) todo.push_back(b);
+                while (todo.size() < 2) { uint32_t b = 0; while (std::find(todo.begin(), todo.end(), b) != todo.end()) ++b; todo.push_back(b); std::sort(todo.begin(), todo.end()); }
+                for (size_t i = 0; i < todo.size(); ++i) {
+                    lb.blk_off = k.boff + (size_t)todo[i] * k.rpad; lb.blk_first = i == 0; lb.blk_last = i + 1 == todo.size();
+                    CK(ti->launch_blocked(lb)); ++g_launches;
+                }
+                swept = (uint32_t)todo.size();
+                if (heavy_n) {
+                    vb::LaunchArgs lh = la;
+                    lh.group = 256; lh.rows = heavy_rows; lh.n = heavy_n; lh.heavy_min = 0;
+                    CK(ti->launch(lh)); ++g_launches;
+                }
+                CK(cudaEventRecord(s.evk[1], g_stream));
+                CK(cudaStreamSynchronize(g_stream));
+                cudaCtxResetPersistingL2Cache();
+                cudaGetLastError();
+                s.last_blocked_nb = swept;
+            } else {
+            s.last_blocked_nb = 0;
             s.upload_view(seed);
             // Gather-bound read phases (state array far larger than L2): keep the head of the gathered type's state resident in
             // L2 for the duration of the launch.  Power-law / preferential-attachment graphs number their hubs first, so the head
@@ -1996,6 +2186,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 cudaStreamSetAttribute(g_stream, cudaStreamAttributeAccessPolicyWindow, &av);
                 cudaCtxResetPersistingL2Cache();
                 cudaGetLastError();
+            }
             }
         }
         CK(cudaStreamSynchronize(g_stream));
@@ -2243,6 +2434,7 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
             f.st_off = (int8_t*)dup(e.st_off, e.st_off_host.size());
             f.rlog_to = f.rlog_from = nullptr; f.rlog_st = nullptr; f.rlog_dst = nullptr; f.rlog_n = f.rlog_cap = 0;
             f.rm_row = f.rm_from = f.rm_mark = nullptr; f.rm_n = f.rm_cap = 0; f.heavy_rows = nullptr; f.heavy_n = 0; f.heavy_version = ~0ull;
+            f.blk = EdgeStore::Blocked{};
             for (auto& c : e.chunks) {
                 RawChunk d; d.n = c.n;
                 d.to = (uint64_t*)dup(c.to, c.n * 8); d.from = (uint64_t*)dup(c.from, c.n * 8); d.st = (uint8_t*)dup(c.st, c.n * e.size);
@@ -3050,6 +3242,11 @@ int vb_last_apply_stats(vb_sim* s, double* ms_rw, double* ms_fin, uint64_t* er, 
     return VB_OK;
 }
 int vb_last_kernel_ms(vb_sim* s, double* ms) { *ms = s->ms_kernel; return VB_OK; }
+int vb_set_read_blocking(vb_sim* s, double block_mb, double min_mb, int eager) {
+    s->blk_block_mb = block_mb; s->blk_min_mb = min_mb; s->blk_eager = eager;
+    return VB_OK;
+}
+int vb_last_apply_blocks(vb_sim* s, uint32_t* nb) { if (nb) *nb = s->last_blocked_nb; return VB_OK; }
 uint64_t vb_device_view_bytes(void) { return sizeof(vb::DeviceSim); }   // host->device bytes uploaded per transition launch
 
 }  // extern "C"

@@ -16,24 +16,22 @@ enum : int { E_KNOWS = 0 };             // edge types in registration order (str
 // step(agent, id, sim): hegselmann.jl:134-144
 //   opinions = map(a -> a.opinion, neighborstates(sim, id, Knows, HKAgent))
 //   accepted = filter(o -> abs(o - agent.opinion) < ϵ, opinions);  HKAgent(mean(accepted))
-// The neighbour walk is cooperative: each lane of the agent's group folds a strided share of the
-// row, ctx.sum() combines the lanes (group of 1 in the oracle => strict left-to-right order).
-struct Step : vb::TransitionBase {
+// Written as a reduce transition (include/vahana_model.h): fold = the filter + running sum, finish = the mean.  The oracle folds
+// the row left to right like the reference's `filter`/`mean`; the GPU combines per-lane or per-source-block partial sums.
+struct Step : vb::ReduceTransition<Step> {
     using State = HKAgent;
-    static constexpr bool kCooperative = true;
+    using Source = HKAgent;
+    struct Acc { double sum; uint32_t n; };
+    static constexpr int kAccBytes = 12;
     static constexpr int kPrimaryEdge = E_KNOWS;
-    template <class Ctx>
-    VB_HD bool operator()(Ctx& ctx, HKAgent& self, vb::AgentID id) const {
-        const double eps = ctx.template param<Params>().eps;
-        const double own = self.opinion;
-        double acc = 0.0;
-        long long n = 0;
-        ctx.template for_each_neighborstate<HKAgent>(E_KNOWS, T_HKAGENT, id, [&](const HKAgent& nb) {
-            if (fabs(nb.opinion - own) < eps) { acc += nb.opinion; n += 1; }
-        });
-        acc = ctx.sum(acc);
-        n = ctx.sum(n);
-        self.opinion = acc / (double)n;   // mean(accepted): NaN for an empty set, as in Julia
+    static constexpr int kSourceType = T_HKAGENT;
+    template <class Ctx> VB_HD void init(const Ctx&, const HKAgent&, Acc& a) const { a.sum = 0.0; a.n = 0; }
+    template <class Ctx> VB_HD void fold(const Ctx& ctx, const HKAgent& self, const HKAgent& nb, Acc& a) const {
+        if (fabs(nb.opinion - self.opinion) < ctx.template param<Params>().eps) { a.sum += nb.opinion; a.n += 1; }
+    }
+    VB_HD void merge(Acc& a, const Acc& b) const { a.sum += b.sum; a.n += b.n; }
+    template <class Ctx> VB_HD bool finish(const Ctx&, HKAgent& self, vb::AgentID, const Acc& a) const {
+        self.opinion = a.sum / (double)a.n;   // mean(accepted): NaN for an empty set, as in Julia
         return true;
     }
 };
