@@ -158,7 +158,9 @@ struct LaunchArgs {
     uint32_t blk_stride;
     int blk_first, blk_last;              // first sweep initialises the accumulators, last sweep runs finish()
     const uint32_t* blk_heavy;            // bitmap of rows left to the block-per-agent pass (>= heavy_min entries), or nullptr
-    int blk_ctas;                         // grid size (persistent warps)
+    uint32_t blk_ahead;                   // CTAs of look-ahead of the L2 prefetch (about one residency wave), 0 = off
+    const uint32_t* blk_rows;             // middle sweeps: ascending list of the rows that own an entry in this block (else nullptr:
+    uint32_t blk_nrows;                   //   all n rows are swept); rows outside the list keep their parked accumulator untouched
     cudaStream_t stream;
 };
 // what the kernel actually receives: launch arguments + the whole simulation view, by value in the
@@ -185,7 +187,6 @@ struct TransitionInfo {
     uint32_t source_size;     // sizeof(F::Source)
     uint32_t acc_bytes;       // F::kAccBytes: bytes of the accumulator parked per row between sweeps
     cudaError_t (*launch_blocked)(const LaunchArgs&);
-    int (*blocked_ctas_per_sm)();   // resident CTAs per SM of the blocked kernel (occupancy query, for the persistent grid)
 };
 // exported by libvahana_b200.so; model libraries call it from static initialisers
 extern "C" int vb_register_transition(const TransitionInfo* info);
@@ -868,18 +869,12 @@ cudaError_t launch_transition(const LaunchArgs& la) {
 // and sweeps the called rows once per block: all gathers of a sweep hit L2 (~280 G/s), the accumulator (F::Acc, kAccBytes per
 // row) is parked in HBM between sweeps and finish() runs in the last one (profiles/microbench/blocked.cu: 37 ms -> 16 ms).
 //
-// Kernel shape: persistent warps, an item = R consecutive rows.  Every stream of an item (offsets, own state, accumulator,
-// source indices) is copied into the warp's shared-memory ring with cp.async two items ahead, so ~5 KB per warp are always
-// in flight without holding registers (a sweep is otherwise bound by the dependent chain offsets -> indices -> gather);
-// the staged indices are gathered edge-parallel (CH/32 independent L2 hits per lane), then each lane folds its rows.
+// Kernel shape (profiles/microbench/blocked.cu compares five): a warp owns 32 consecutive rows, 2048 threads per SM.  The rows'
+// entries inside the block are contiguous, so the warp gathers them edge-parallel (coalesced index loads, independent L2 hits,
+// no divergence however skewed the degrees are) into shared memory and every lane folds its own row's part from there.
+// Software-pipelined persistent variants (register-, cp.async- and TMA-staged) issue 2-3x the instructions per row and end up
+// issue-bound at the same or a worse time.
 namespace blk {
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-template <int W> __device__ __forceinline__ void cp_async(void* dst, const void* src) {
-    static_assert(W == 4 || W == 8 || W == 16, "cp.async moves 4, 8 or 16 bytes");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(dst)), "l"(src), "n"(W) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // gather with an L2 evict_last policy: the sweep's source block stays resident while the streams pass through
 template <int W> __device__ __forceinline__ typename WordT<W>::type ld_keep_word(const void* p, uint64_t) { return *reinterpret_cast<const typename WordT<W>::type*>(p); }
 template <> __device__ __forceinline__ uint64_t ld_keep_word<8>(const void* p, uint64_t pol) {
@@ -897,213 +892,153 @@ template <class T> __device__ __forceinline__ T gather_keep(const uint8_t* __res
     for (int c = 0; c < NC; ++c) u.w[c] = ld_keep_word<W>(cols + (size_t)c * stride * W + (size_t)i * W, pol);
     return u.t;
 }
+// pull a byte range into L2 (one 128 B line per participating thread and round)
+__device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes, uint32_t tid, uint32_t nthreads) {
+    const char* b = reinterpret_cast<const char*>(p);
+    const size_t first = (size_t)(reinterpret_cast<uintptr_t>(b) & 127u);
+    for (size_t o = (size_t)tid * 128; o < bytes + first; o += (size_t)nthreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b - first + o));
+}
+// streaming (evict-first) column access for the per-row streams
+template <class T> __device__ __forceinline__ T soa_load_cs(const uint8_t* __restrict__ cols, uint32_t stride, uint32_t i) {
+    constexpr int W = SoaWord<sizeof(T)>::value;
+    constexpr int NC = sizeof(T) / W;
+    typedef typename WordT<W>::type Word;
+    union U { T t; Word w[NC]; __device__ U() {} } u;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) u.w[c] = __ldcs(reinterpret_cast<const Word*>(cols + (size_t)c * stride * W) + i);
+    return u.t;
+}
 }  // namespace blk
 
 template <class F> struct BlockedCfg {
     typedef typename F::State State;
     typedef typename F::Source Source;
     typedef typename F::Acc Acc;
-    static constexpr int R = 32;            // rows per item (R / 32 per lane)
-    static constexpr int CH = 128;          // source indices staged per item (CH / 32 gathers in flight per lane)
-    static constexpr int COOP_MIN = 48;     // a row with at least this many entries inside one chunk is folded by the whole warp
-    static constexpr int NA = 5, NB = 3;    // ring depths: offsets are fetched 4 items ahead, everything else 2 items ahead
-    static constexpr int WARPS = 8;
-    static constexpr int SW = SoaWord<sizeof(State)>::value, SC = sizeof(State) / SW;
-    static constexpr int AW = SoaWord<F::kAccBytes>::value, AC = F::kAccBytes / AW;
-    static_assert(SW >= 4 && AW >= 4, "blocked sweeps need state / accumulator words of at least 4 bytes (cp.async)");
-    static_assert(F::kAccBytes <= (int)sizeof(Acc), "kAccBytes exceeds sizeof(Acc)");
-    struct StageA { uint32_t off[R + 4]; };
-    struct StageB {
-        alignas(16) uint8_t state[SC * R * SW];
-        alignas(16) uint8_t acc[AC * R * AW];
-        alignas(16) uint32_t src[CH];
-    };
-    struct WarpSmem {
-        StageA a[NA];
-        StageB b[NB];
-        alignas(16) uint8_t val[CH * sizeof(Source)];
-    };
-    static constexpr size_t kSmem = sizeof(WarpSmem) * WARPS;
+    static constexpr int CHK = 128;         // entries a warp gathers per round (CHK / 32 independent L2 hits per lane)
+    // the accumulator is parked as word columns: an 8-byte column for every full 8 bytes, then 4-byte columns
+    static_assert(F::kAccBytes % 4 == 0 && F::kAccBytes <= (int)sizeof(Acc), "kAccBytes: a multiple of 4, at most sizeof(Acc)");
+    static_assert(sizeof(Acc) % 4 == 0 && sizeof(State) % 4 == 0, "state and accumulator sizes must be multiples of 4 bytes");
+    static constexpr int A8 = F::kAccBytes / 8, A4 = (F::kAccBytes % 8) / 4;
+    static __device__ __forceinline__ void acc_load(const uint8_t* __restrict__ base, uint32_t stride, uint32_t i, Acc& a) {
+        union U { Acc t; uint32_t w[sizeof(Acc) / 4]; __device__ U() {} } u;
+#pragma unroll
+        for (int c = 0; c < (int)(sizeof(Acc) / 4); ++c) u.w[c] = 0;
+#pragma unroll
+        for (int c = 0; c < A8; ++c) {
+            const uint64_t v = __ldcs(reinterpret_cast<const uint64_t*>(base + (size_t)c * stride * 8) + i);
+            u.w[2 * c] = (uint32_t)v; u.w[2 * c + 1] = (uint32_t)(v >> 32);
+        }
+#pragma unroll
+        for (int c = 0; c < A4; ++c) u.w[2 * A8 + c] = __ldcs(reinterpret_cast<const uint32_t*>(base + (size_t)A8 * stride * 8 + (size_t)c * stride * 4) + i);
+        a = u.t;
+    }
+    static __device__ __forceinline__ void acc_store(uint8_t* __restrict__ base, uint32_t stride, uint32_t i, const Acc& a) {
+        union U { Acc t; uint32_t w[sizeof(Acc) / 4]; __device__ U() {} } u;
+        u.t = a;
+#pragma unroll
+        for (int c = 0; c < A8; ++c) __stcs(reinterpret_cast<uint64_t*>(base + (size_t)c * stride * 8) + i, (uint64_t)u.w[2 * c] | ((uint64_t)u.w[2 * c + 1] << 32));
+#pragma unroll
+        for (int c = 0; c < A4; ++c) __stcs(reinterpret_cast<uint32_t*>(base + (size_t)A8 * stride * 8 + (size_t)c * stride * 4) + i, u.w[2 * A8 + c]);
+    }
 };
 
 template <class F, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(256, 4) reduce_blocked_kernel(const __grid_constant__ KernelArgs ka) {
+__global__ void __launch_bounds__(256, 6) reduce_blocked_kernel(const __grid_constant__ KernelArgs ka) {
     typedef BlockedCfg<F> C;
     typedef typename C::State State;
     typedef typename C::Source Source;
     typedef typename C::Acc Acc;
-    constexpr int R = C::R, CH = C::CH, NA = C::NA, NB = C::NB;
-    extern __shared__ __align__(16) uint8_t blk_smem[];
+    constexpr int CHK = C::CHK;
+    __shared__ __align__(16) uint8_t val_raw[8][CHK * sizeof(Source)];
     const LaunchArgs& la = ka.la;
     const DeviceSim& ds = ka.ds;
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    typename C::WarpSmem& sm = reinterpret_cast<typename C::WarpSmem*>(blk_smem)[wib];
-    const uint32_t W = gridDim.x * C::WARPS, w = blockIdx.x * C::WARPS + wib;
-    const uint32_t n = la.n, nitems = (n + R - 1) / R;
+    const uint32_t lane = threadIdx.x & 31;
+    Source* val = reinterpret_cast<Source*>(val_raw[threadIdx.x >> 5]);
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool listed = !FIRST && !LAST && la.blk_rows != nullptr;         // sweep only the rows that own an entry in this block
+    const uint32_t nwork = listed ? la.blk_nrows : la.n;
+    const uint32_t idx = listed ? (gtid < nwork ? __ldcs(la.blk_rows + gtid) : la.n) : (uint32_t)gtid;
     const AgentView& av = ds.agents[la.type];
     const AgentView& sv = ds.agents[F::kSourceType];
-    const uint8_t* __restrict__ own_st = av.state_r;
     const uint8_t* __restrict__ src_st = sv.state_r;
-    const uint32_t own_cap = av.cap, src_cap = sv.cap;
-    const uint32_t* __restrict__ goff = la.blk_off;
+    const uint32_t src_cap = sv.cap;
     const uint32_t* __restrict__ gsrc = la.blk_src;
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    Source* val = reinterpret_cast<Source*>(sm.val);
-    unsigned long long edges_read = 0;
-
-    auto issueA = [&](uint32_t k) {                       // offsets of the warp's k-th item
-        const uint64_t item = (uint64_t)w + (uint64_t)k * W;
-        if (item >= nitems) return;
-        const uint32_t r0 = (uint32_t)item * R;
-        uint32_t* dst = sm.a[k % NA].off;
-        for (uint32_t i = lane; i <= (uint32_t)R; i += 32) if (r0 + i <= n) blk::cp_async<4>(dst + i, goff + r0 + i);
-    };
-    auto issueB = [&](uint32_t k) {                       // own states, accumulators and source indices (needs A(k) in smem)
-        const uint64_t item = (uint64_t)w + (uint64_t)k * W;
-        if (item >= nitems) return;
-        const uint32_t r0 = (uint32_t)item * R, nr = n - r0 < (uint32_t)R ? n - r0 : (uint32_t)R;
-        const uint32_t* soff = sm.a[k % NA].off;
-        typename C::StageB& B = sm.b[k % NB];
-        const uint32_t e0 = soff[0];
-        uint32_t m = soff[nr] - e0; if (m > (uint32_t)CH) m = CH;
+    // Latency: a row's work is the dependent chain offsets -> indices -> gather, two DRAM round trips before the first L2 hit.
+    // Every CTA therefore pulls the streams of the CTA that will run `blk_ahead` CTAs later (about one residency wave) into L2:
+    // its offsets, own states and parked accumulators now, its index range at the end (once the two bounding offsets arrived).
+    const uint32_t pc = blockIdx.x + la.blk_ahead;
+    uint32_t pa = 0, pb = 0;
+    if (la.blk_ahead && pc < gridDim.x && !listed) {
+        const uint32_t r0 = pc * 256u, nr = la.n - r0 < 256u ? la.n - r0 : 256u;
+        if (threadIdx.x == 0) { pa = __ldg(la.blk_off + r0); pb = __ldg(la.blk_off + r0 + nr); }
+        blk::prefetch_l2(la.blk_off + r0, (size_t)(nr + 1) * 4, threadIdx.x, 256);
+        constexpr int SW = SoaWord<sizeof(State)>::value, SC = sizeof(State) / SW;
 #pragma unroll
-        for (int j = 0; j < CH / 32; ++j) { const uint32_t i = lane + 32 * j; if (i < m) blk::cp_async<4>(B.src + i, gsrc + e0 + i); }
+        for (int c = 0; c < SC; ++c) blk::prefetch_l2(av.state_r + ((size_t)c * av.cap + r0) * SW, (size_t)nr * SW, threadIdx.x, 256);
+        if (!FIRST) {
 #pragma unroll
-        for (int q = 0; q < R / 32; ++q) {
-            const uint32_t r = lane + 32 * q;
-            if (r < nr) {
+            for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, threadIdx.x, 256);
 #pragma unroll
-                for (int c = 0; c < C::SC; ++c) blk::cp_async<C::SW>(B.state + (c * R + r) * C::SW, own_st + ((size_t)c * own_cap + r0 + r) * C::SW);
-                if (!FIRST) {
-#pragma unroll
-                    for (int c = 0; c < C::AC; ++c) blk::cp_async<C::AW>(B.acc + (c * R + r) * C::AW, la.blk_acc + ((size_t)c * la.blk_stride + r0 + r) * C::AW);
-                }
-            }
+            for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, threadIdx.x, 256);
         }
-    };
-
-    // prologue: G(-2) = {A(2), B(0)}, G(-1) = {A(3), B(1)}; iteration k issues G(k) = {A(k+4), B(k+2)} and needs G(k-2)
-    issueA(0); issueA(1); blk::cp_commit(); blk::cp_wait<0>(); __syncwarp();
-    issueA(2); issueB(0); blk::cp_commit();
-    issueA(3); issueB(1); blk::cp_commit();
-    for (uint32_t k = 0;; ++k) {
-        const uint64_t item = (uint64_t)w + (uint64_t)k * W;
-        if (item >= nitems) break;
-        blk::cp_wait<1>();
+    }
+    // no early exit: the 32 rows of a warp are walked together.  Their entries are contiguous: [lo of lane 0, hi of lane 31)
+    // (with a row list the listed rows' entries are still contiguous: the rows in between own none)
+    const uint32_t row = gtid < nwork ? idx : la.n;                        // rows past the end: an empty range at the very end
+    uint32_t lo = __ldcs(la.blk_off + row), hi = gtid < nwork ? __ldcs(la.blk_off + row + 1) : lo;
+    const bool act = gtid < nwork && !(av.died_r && av.died_r[idx]);       // jump over died agents (AgentMethods.jl:199-203)
+    const F f{};
+    Ctx<F, MODE_DIRECT, 1> ctx(ds, la, idx, 0);
+    State self;
+    Acc acc;
+    if (act) {
+        self = blk::soa_load_cs<State>(av.state_r, av.cap, idx);
+        if (FIRST) f.init(ctx, self, acc); else C::acc_load(la.blk_acc, la.blk_stride, idx, acc);
+    } else {
+        memset(&self, 0, sizeof(State));
+        memset(&acc, 0, sizeof(Acc));
+    }
+    const uint32_t e0 = __shfl_sync(0xffffffffu, lo, 0), e1 = __shfl_sync(0xffffffffu, hi, 31);
+    const uint32_t len = hi - lo;
+    if (!act) hi = lo;                                                    // a died agent's entries are gathered but never folded
+    // the warp's entries in chunks of CHK: edge-parallel (coalesced index loads, CHK / 32 independent L2 hits per lane) into
+    // shared memory, then every lane folds the part of its own row that lies in the chunk
+    for (uint32_t base = e0; base < e1; base += CHK) {
+        Source v[CHK / 32];
+        uint32_t six[CHK / 32];
+#pragma unroll
+        for (int j = 0; j < CHK / 32; ++j) { const uint32_t x = base + lane + 32 * j; if (x < e1) six[j] = __ldcs(gsrc + x); }
+#pragma unroll
+        for (int j = 0; j < CHK / 32; ++j) { const uint32_t x = base + lane + 32 * j; if (x < e1) v[j] = blk::gather_keep<Source>(src_st, src_cap, six[j], pol); }
+#pragma unroll
+        for (int j = 0; j < CHK / 32; ++j) { const uint32_t x = base + lane + 32 * j; if (x < e1) val[lane + 32 * j] = v[j]; }
         __syncwarp();
-        issueA(k + 4); issueB(k + 2); blk::cp_commit();
-
-        const uint32_t r0 = (uint32_t)item * R, nr = n - r0 < (uint32_t)R ? n - r0 : (uint32_t)R;
-        const uint32_t* soff = sm.a[k % NA].off;
-        const typename C::StageB& B = sm.b[k % NB];
-        const uint32_t e0 = soff[0], etot = soff[nr] - e0;
-        if (lane == 0) edges_read += etot;
-        // this lane's rows: own state, accumulator (parked since the previous sweep) and entry range relative to e0
-        constexpr int Q = R / 32;
-        State self[Q]; Acc acc[Q]; uint32_t lo[Q], hi[Q]; bool act[Q];
-        const F f{};
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const uint32_t r = lane + 32 * q;
-            act[q] = r < nr && !(av.died_r && av.died_r[r0 + r]);      // jump over died agents (AgentMethods.jl:199-203)
-            lo[q] = hi[q] = 0;
-            if (!act[q]) continue;
-            {
-                typedef typename WordT<C::SW>::type Word;
-                union U { State t; Word wd[C::SC]; __device__ U() {} } u;
-#pragma unroll
-                for (int c = 0; c < C::SC; ++c) u.wd[c] = *reinterpret_cast<const Word*>(B.state + (c * R + r) * C::SW);
-                self[q] = u.t;
-            }
-            if (FIRST) { Ctx<F, MODE_DIRECT, 1> ctx(ds, la, r0 + r, 0); f.init(ctx, self[q], acc[q]); }
-            else {
-                typedef typename WordT<C::AW>::type Word;
-                constexpr int NW = (int)((sizeof(Acc) + C::AW - 1) / C::AW);
-                union U { Acc t; Word wd[NW]; __device__ U() {} } u;
-#pragma unroll
-                for (int c = 0; c < NW; ++c) u.wd[c] = Word{};
-#pragma unroll
-                for (int c = 0; c < C::AC; ++c) u.wd[c] = *reinterpret_cast<const Word*>(B.acc + (c * R + r) * C::AW);
-                acc[q] = u.t;
-            }
-            lo[q] = soff[r] - e0; hi[q] = soff[r + 1] - e0;
-        }
-        // the item's entries in chunks of CH: edge-parallel gather (CH / 32 independent L2 hits per lane) into shared memory,
-        // then every lane folds the part of its rows' ranges that lies in the chunk.  The first chunk's indices were staged.
-        for (uint32_t base = 0; base < etot; base += CH) {
-            const uint32_t mm = etot - base < (uint32_t)CH ? etot - base : (uint32_t)CH;
-            {
-                Source v[CH / 32];
-                uint32_t six[CH / 32];
-#pragma unroll
-                for (int j = 0; j < CH / 32; ++j) { const uint32_t i = lane + 32 * j; if (i < mm) six[j] = base ? __ldcs(gsrc + e0 + base + i) : B.src[i]; }
-#pragma unroll
-                for (int j = 0; j < CH / 32; ++j) { const uint32_t i = lane + 32 * j; if (i < mm) v[j] = blk::gather_keep<Source>(src_st, src_cap, six[j], pol); }
-#pragma unroll
-                for (int j = 0; j < CH / 32; ++j) { const uint32_t i = lane + 32 * j; if (i < mm) val[i] = v[j]; }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const uint32_t b = lo[q] > base ? lo[q] : base, e = hi[q] < base + mm ? hi[q] : base + mm;
-                const uint32_t len = act[q] && e > b ? e - b : 0u;
-                // long ranges (hub rows): all lanes fold a strided share into a private accumulator, merge() combines them
-                unsigned coop = __ballot_sync(0xffffffffu, len >= (uint32_t)C::COOP_MIN);
-                while (coop) {
-                    const int owner = __ffs(coop) - 1;
-                    coop &= coop - 1;
-                    const uint32_t bb = __shfl_sync(0xffffffffu, b, owner), ee = __shfl_sync(0xffffffffu, e, owner);
-                    State oself;
-                    {
-                        union U { State t; uint32_t w[sizeof(State) / 4]; __device__ U() {} } in, out;
-                        in.t = self[q];
-#pragma unroll
-                        for (int i = 0; i < (int)(sizeof(State) / 4); ++i) out.w[i] = __shfl_sync(0xffffffffu, in.w[i], owner);
-                        oself = out.t;
-                    }
-                    Ctx<F, MODE_DIRECT, 1> octx(ds, la, r0 + owner + 32 * q, 0);
-                    Acc part;
-                    f.init(octx, oself, part);
-                    for (uint32_t x = bb + lane; x < ee; x += 32) f.fold(octx, oself, val[x - base], part);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { const Acc other = Ctx<F, MODE_DIRECT, 32>::shfl_xor_struct(0xffffffffu, part, o); f.merge(part, other); }
-                    if ((int)lane == owner) f.merge(acc[q], part);
-                }
-                if (len && len < (uint32_t)C::COOP_MIN) {
-                    Ctx<F, MODE_DIRECT, 1> ctx(ds, la, r0 + lane + 32 * q, 0);
-                    for (uint32_t x = b; x < e; ++x) f.fold(ctx, self[q], val[x - base], acc[q]);
-                }
-            }
-            __syncwarp();
-        }
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            if (!act[q]) continue;
-            const uint32_t idx = r0 + lane + 32 * q;
-            if (!LAST) {
-                typedef typename WordT<C::AW>::type Word;
-                constexpr int NW = (int)((sizeof(Acc) + C::AW - 1) / C::AW);
-                union U { Acc t; Word wd[NW]; __device__ U() {} } u;
-                u.t = acc[q];
-#pragma unroll
-                for (int c = 0; c < C::AC; ++c) __stcs(reinterpret_cast<Word*>(la.blk_acc + ((size_t)c * la.blk_stride + idx) * C::AW), u.wd[c]);
-            } else {
-                if (la.blk_heavy && ((la.blk_heavy[idx >> 5] >> (idx & 31)) & 1u)) continue;   // done by the block-per-agent pass
-                Ctx<F, MODE_DIRECT, 1> ctx(ds, la, idx, 0);
-                const AgentID id = agent_id((uint32_t)la.type, ds.rank, (uint64_t)idx + 1);
-                const bool alive = f.finish(ctx, self[q], id, acc[q]);
-                if (la.in_write) {                                         // transition_with_write! (AgentMethods.jl:159-181)
-                    if (alive) { if (av.size) soa_store<State>(av.independent ? av.state_r : av.state_w, av.cap, idx, self[q]); }
-                    else if (av.immortal) atomicOr(ds.error, (uint32_t)DERR_IMMORTAL_DIED);
-                    else av.died_w[idx] = 1;
-                }
-            }
-        }
+        const uint32_t b = lo > base ? lo : base, e = hi < base + CHK ? hi : base + CHK;
+        for (uint32_t x = b; x < e; ++x) f.fold(ctx, self, val[x - base], acc);
         __syncwarp();
     }
-    blk::cp_wait<0>();
-    if (edges_read) atomicAdd(la.stats + ((blockIdx.x & 1023u) << 2), edges_read);
+    if (threadIdx.x < 32 && la.blk_ahead && pc < gridDim.x && !listed) {              // warp 0: the index range of the CTA `blk_ahead` later
+        pa = __shfl_sync(0xffffffffu, pa, 0); pb = __shfl_sync(0xffffffffu, pb, 0);
+        blk::prefetch_l2(gsrc + pa, (size_t)(pb - pa) * 4, lane, 32);
+    }
+    {
+        const unsigned total = __reduce_add_sync(0xffffffffu, act ? len : 0u);
+        if (lane == 0 && total) atomicAdd(la.stats + ((blockIdx.x & 1023u) << 2), (unsigned long long)total);
+    }
+    if (!act) return;
+    if (!LAST) C::acc_store(la.blk_acc, la.blk_stride, idx, acc);
+    else if (!(la.blk_heavy && ((la.blk_heavy[idx >> 5] >> (idx & 31)) & 1u))) {   // heavy rows: done by the block-per-agent pass
+        const AgentID id = agent_id((uint32_t)la.type, ds.rank, (uint64_t)idx + 1);
+        const bool alive = f.finish(ctx, self, id, acc);
+        if (la.in_write) {                                                 // transition_with_write! (AgentMethods.jl:159-181)
+            if (alive) { if (av.size) soa_store<State>(av.independent ? av.state_r : av.state_w, av.cap, idx, self); }
+            else if (av.immortal) atomicOr(ds.error, (uint32_t)DERR_IMMORTAL_DIED);
+            else av.died_w[idx] = 1;
+        }
+    }
 }
 
 template <class F>
@@ -1112,27 +1047,25 @@ cudaError_t launch_blocked(const LaunchArgs& la) {
     ka.la = la;
     ka.ds = *la.ds;
     ka.la.ds = nullptr;
-    constexpr size_t smem = BlockedCfg<F>::kSmem;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(reduce_blocked_kernel<F, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(reduce_blocked_kernel<F, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(reduce_blocked_kernel<F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+    if (la.n == 0) return cudaSuccess;
+    const bool listed = !la.blk_first && !la.blk_last && la.blk_rows != nullptr;
+    if (listed && la.blk_nrows == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)(((unsigned long long)(listed ? la.blk_nrows : la.n) + 255) / 256);
+    static int wave = 0;                                                // resident CTAs of this kernel on the whole device
+    if (!wave) {
+        int dev = 0, sms = 148, per_sm = 6;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_blocked_kernel<F, false, false>, 256, 0);
+        wave = sms * (per_sm > 0 ? per_sm : 1);
+        if (getenv("VB_BLOCK_AHEAD")) wave = atoi(getenv("VB_BLOCK_AHEAD"));
     }
-    const unsigned grid = (unsigned)(la.blk_ctas > 0 ? la.blk_ctas : 148);
+    ka.la.blk_ahead = (uint32_t)wave;
     if (la.blk_first && la.blk_last) return cudaErrorInvalidValue;      // a single block is the direct path's job
-    if (la.blk_first) reduce_blocked_kernel<F, true, false><<<grid, 256, smem, la.stream>>>(ka);
-    else if (la.blk_last) reduce_blocked_kernel<F, false, true><<<grid, 256, smem, la.stream>>>(ka);
-    else reduce_blocked_kernel<F, false, false><<<grid, 256, smem, la.stream>>>(ka);
+    if (la.blk_first) reduce_blocked_kernel<F, true, false><<<grid, 256, 0, la.stream>>>(ka);
+    else if (la.blk_last) reduce_blocked_kernel<F, false, true><<<grid, 256, 0, la.stream>>>(ka);
+    else reduce_blocked_kernel<F, false, false><<<grid, 256, 0, la.stream>>>(ka);
     return cudaGetLastError();
-}
-template <class F>
-int blocked_ctas_per_sm() {
-    int nb = 0;
-    cudaFuncSetAttribute(reduce_blocked_kernel<F, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BlockedCfg<F>::kSmem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, reduce_blocked_kernel<F, false, false>, 256, BlockedCfg<F>::kSmem) != cudaSuccess) { cudaGetLastError(); return 1; }
-    return nb > 0 ? nb : 1;
 }
 
 template <class F>
@@ -1156,7 +1089,6 @@ TransitionInfo make_transition_info(const char* name, const char* agent_type) {
         ti.source_size = (uint32_t)sizeof(typename F::Source);
         ti.acc_bytes = (uint32_t)F::kAccBytes;
         ti.launch_blocked = &launch_blocked<F>;
-        ti.blocked_ctas_per_sm = &blocked_ctas_per_sm<F>;
     }
     return ti;
 }

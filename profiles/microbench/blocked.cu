@@ -37,38 +37,49 @@ __global__ void window_gather(const double* __restrict__ a, uint64_t window, uin
     if (acc == 12345.678) out[0] = acc;
 }
 
-// graph: row t has `deg` random sources + itself
-__global__ void fill_direct(uint32_t* src, uint64_t n, uint32_t deg) {
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n * (deg + 1)) return;
-    const uint64_t t = e / (deg + 1), k = e % (deg + 1);
-    src[e] = k == deg ? (uint32_t)t : source_of(e, n);
+// graph: row t has deg(t) random sources + itself; deg = `deg` (uniform) or a Pareto(1.5) draw with mean ~20 capped at 16383 (powerlaw)
+__global__ void fill_degrees(uint32_t* d, uint64_t n, uint32_t deg, int powerlaw) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n) return;
+    if (t == n) { d[t] = 0; return; }
+    if (!powerlaw) { d[t] = deg + 1; return; }
+    const double u = (double)(mix(t ^ 0x9e3779b97f4a7c15ull) >> 11) * (1.0 / 9007199254740992.0);
+    const double x = 6.8333 * pow(1.0 - u, -2.0 / 3.0);
+    d[t] = (x >= 16383.0 ? 16383u : (uint32_t)x) + 1;
 }
-__global__ void count_blocks(const uint32_t* __restrict__ src, uint64_t n, uint32_t deg, uint32_t bsize, uint32_t nb, uint32_t* cnt /*[nb][n+1]*/) {
+__global__ void fill_direct(uint32_t* src, const uint32_t* __restrict__ roff, uint64_t n) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    for (uint32_t k = 0; k <= deg; ++k) { const uint32_t b = src[t * (deg + 1) + k] / bsize; cnt[(uint64_t)b * (n + 4) + t] += 1; }
+    const uint32_t b = roff[t], e = roff[t + 1];
+    for (uint32_t k = b; k + 1 < e; ++k) src[k] = source_of(k, n);
+    src[e - 1] = (uint32_t)t;
 }
-__global__ void fill_blocks(const uint32_t* __restrict__ src, uint64_t n, uint32_t deg, uint32_t bsize, uint32_t nb, const uint32_t* off, const uint64_t* base, uint32_t* bsrc) {
+__global__ void count_blocks(const uint32_t* __restrict__ src, const uint32_t* __restrict__ roff, uint64_t n, uint32_t bsize, uint32_t nb, uint32_t* cnt /*[nb][n+4]*/) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    for (uint32_t k = roff[t]; k < roff[t + 1]; ++k) { const uint32_t b = src[k] / bsize; cnt[(uint64_t)b * (n + 4) + t] += 1; }
+}
+__global__ void fill_blocks(const uint32_t* __restrict__ src, const uint32_t* __restrict__ roff, uint64_t n, uint32_t bsize, uint32_t nb, const uint32_t* off, const uint64_t* base, uint32_t* bsrc) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     uint32_t fill[64];
     for (uint32_t b = 0; b < nb; ++b) fill[b] = 0;
-    for (uint32_t k = 0; k <= deg; ++k) {
-        const uint32_t s = src[t * (deg + 1) + k], b = s / bsize;
+    for (uint32_t k = roff[t]; k < roff[t + 1]; ++k) {
+        const uint32_t s = src[k], b = s / bsize;
         bsrc[base[b] + off[(uint64_t)b * (n + 4) + t] + fill[b]++] = s;
     }
 }
 
 // (2) direct: 8 lanes per target
-__global__ void direct_step(const uint32_t* __restrict__ src, const double* __restrict__ state, double* __restrict__ out, uint64_t n, uint32_t deg, double eps) {
+__global__ void direct_step(const uint32_t* __restrict__ src, const uint32_t* __restrict__ roff, const double* __restrict__ state, double* __restrict__ out, uint64_t n, double eps) {
     const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const uint32_t lane = threadIdx.x & 7;
     if (g >= n) return;
     const double own = state[g];
     double s = 0; uint32_t c = 0;
-    for (uint32_t k = lane; k <= deg; k += 8) {
-        const double v = ld_gather(state + __ldcs(src + g * (deg + 1) + k));
+    const uint32_t rb = roff[g], re = roff[g + 1];
+    for (uint32_t k = rb + lane; k < re; k += 8) {
+        const double v = ld_gather(state + __ldcs(src + k));
         if (fabs(v - own) < eps) { s += v; c += 1; }
     }
     for (int o = 4; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
@@ -495,7 +506,12 @@ int main(int argc, char** argv) {
     setvbuf(stdout, nullptr, _IONBF, 0);
     const uint64_t n = argc > 1 ? strtoull(argv[1], 0, 10) : 100000000ull;
     const uint32_t deg = argc > 2 ? atoi(argv[2]) : 20;
-    const uint64_t E = n * (deg + 1);
+    const int powerlaw = getenv("POWERLAW") != nullptr;
+    uint32_t* roff; CK(cudaMalloc(&roff, (n + 1) * 4));
+    fill_degrees<<<(unsigned)((n + 256) / 256), 256>>>(roff, n, deg, powerlaw);
+    { void* t = nullptr; size_t tz = 0; cub::DeviceScan::ExclusiveSum(t, tz, roff, roff, (int)(n + 1)); CK(cudaMalloc(&t, tz)); cub::DeviceScan::ExclusiveSum(t, tz, roff, roff, (int)(n + 1)); CK(cudaFree(t)); }
+    uint32_t E32; CK(cudaMemcpy(&E32, roff + n, 4, cudaMemcpyDeviceToHost));
+    const uint64_t E = E32;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float ms;
     {
@@ -525,12 +541,12 @@ int main(int argc, char** argv) {
         printf("window %4llu MB: %8.3f ms  %7.1f Ggather/s\n", (unsigned long long)mb, ms, (double)threads * per / ms / 1e6);
     }
 
-    fill_direct<<<(unsigned)((E + 255) / 256), 256>>>(src, n, deg);
+    fill_direct<<<(unsigned)((n + 255) / 256), 256>>>(src, roff, n);
     CK(cudaDeviceSynchronize());
     printf("== direct (8 lanes per target), n=%llu E=%llu ==\n", (unsigned long long)n, (unsigned long long)E);
     for (int r = 0; r < 3; ++r) {
         CK(cudaEventRecord(e0));
-        direct_step<<<(unsigned)((n * 8 + 255) / 256), 256>>>(src, state, out, n, deg, 0.02);
+        direct_step<<<(unsigned)((n * 8 + 255) / 256), 256>>>(src, roff, state, out, n, 0.02);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         CK(cudaEventElapsedTime(&ms, e0, e1));
     }
@@ -543,7 +559,7 @@ int main(int argc, char** argv) {
         uint32_t* off; uint64_t* base;
         CK(cudaMalloc(&off, (uint64_t)nb * (n + 4) * 4)); CK(cudaMalloc(&base, nb * 8));
         CK(cudaMemset(off, 0, (uint64_t)nb * (n + 4) * 4));
-        count_blocks<<<(unsigned)((n + 255) / 256), 256>>>(src, n, deg, bsize, nb, off);
+        count_blocks<<<(unsigned)((n + 255) / 256), 256>>>(src, roff, n, bsize, nb, off);
         void* tmp = nullptr; size_t tmpsz = 0;
         cub::DeviceScan::ExclusiveSum(tmp, tmpsz, off, off, (int)(n + 4));
         CK(cudaMalloc(&tmp, tmpsz));
@@ -554,7 +570,7 @@ int main(int argc, char** argv) {
             hbase[b + 1] = hbase[b] + tot;
         }
         CK(cudaMemcpy(base, hbase.data(), nb * 8, cudaMemcpyHostToDevice));
-        fill_blocks<<<(unsigned)((n + 255) / 256), 256>>>(src, n, deg, bsize, nb, off, base, bsrc);
+        fill_blocks<<<(unsigned)((n + 255) / 256), 256>>>(src, roff, n, bsize, nb, off, base, bsrc);
         CK(cudaDeviceSynchronize());
         float best = 1e9f;
         for (int r = 0; r < 3; ++r) {
@@ -589,6 +605,7 @@ int main(int argc, char** argv) {
         }
         printf("blocked nb=%2u (block %6.1f MB, edges in block 0: %5.1f%%): %8.3f ms  %7.2f Gedges/s\n", nb, bsize * 8.0 / 1e6,
                100.0 * hbase[1] / E, best, (double)E / best / 1e6);
+        if (getenv("QUICK")) { CK(cudaFree(off)); CK(cudaFree(base)); CK(cudaFree(tmp)); continue; }
         float b2;
         run_pass_t<512, 2048, 2>(nb, off, bsrc, hbase, state, sum, cnt, out, n, e0, e1, 3);
         run_pass_t<512, 2048, 3>(nb, off, bsrc, hbase, state, sum, cnt, out, n, e0, e1, 2);

@@ -484,6 +484,10 @@ struct BlkBuildArgs {
     uint32_t bsize, nb, rpad;
     uint32_t* boff; uint32_t* bsrc; uint32_t* error;
 };
+__global__ void blk_active_flags_kernel(const uint32_t* __restrict__ boff, uint32_t n, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = boff[i + 1] > boff[i] ? 1u : 0u;
+}
 __global__ void blk_count_kernel(const BlkBuildArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -765,6 +769,8 @@ struct EdgeStore {
         uint32_t* boff = nullptr; uint32_t* bsrc = nullptr; uint32_t* heavy_bits = nullptr; uint8_t* acc = nullptr;
         uint32_t nb = 0, bsize = 0, rpad = 0, n = 0, acc_bytes = 0, heavy_min = 0;
         std::vector<uint32_t> bstart;                 // position in bsrc where each block's entries start (nb + 1 values)
+        std::vector<uint32_t*> arows;                 // per block: ascending list of the rows that own an entry in it
+        std::vector<uint32_t> acount;
         int called = 0, source = 0;
         uint64_t version = ~0ull, epoch = ~0ull;      // container version / sim layout epoch the view was built for
         uint64_t seen_version = ~0ull; uint32_t seen = 0;   // how many applies found the same container (static network => worth building)
@@ -852,6 +858,7 @@ void free_agent(AgentStore& a) {
     a.state[0] = a.state[1] = a.died[0] = a.died[1] = nullptr; a.reuse = nullptr; a.ghost_ids = nullptr; a.send_slots = nullptr; a.send_buf = nullptr;
 }
 void free_blocked(EdgeStore& e) {
+    for (auto p : e.blk.arows) dfree(p);
     dfree(e.blk.boff); dfree(e.blk.bsrc); dfree(e.blk.heavy_bits); dfree(e.blk.acc);
     e.blk = EdgeStore::Blocked{};
 }
@@ -1679,11 +1686,11 @@ void vb_sim::transmit_edges(int ei) {
 // Source-blocked view of edge type `ei` for the reduce transition `ti` called on agent type C (n slots).  Returns true when the view
 // is ready.  Policy: only for gather-bound shapes (the source type's state array is several times the L2 set-aside) and only once
 // the same container has been seen by two applies (a network rebuilt every step never amortises the build).
-// VB_BLOCK=0 disables, VB_BLOCK_MB sets the block size (default 60 MB of source states), VB_BLOCK_MIN_MB the activation threshold
+// VB_BLOCK=0 disables, VB_BLOCK_MB sets the block size (default 88 MB of source states), VB_BLOCK_MIN_MB the activation threshold
 // (default 192 MB), VB_BLOCK_EAGER=1 builds at first sight (tests).
 bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min) {
     static const bool enabled = !(getenv("VB_BLOCK") && atoi(getenv("VB_BLOCK")) == 0);
-    static const double env_block_mb = getenv("VB_BLOCK_MB") ? atof(getenv("VB_BLOCK_MB")) : 60.0;
+    static const double env_block_mb = getenv("VB_BLOCK_MB") ? atof(getenv("VB_BLOCK_MB")) : 88.0;
     static const double env_min_mb = getenv("VB_BLOCK_MIN_MB") ? atof(getenv("VB_BLOCK_MIN_MB")) : 192.0;
     static const bool env_eager = getenv("VB_BLOCK_EAGER") && atoi(getenv("VB_BLOCK_EAGER")) != 0;
     const double block_mb = blk_block_mb > 0 ? blk_block_mb : env_block_mb;       // vb_set_read_blocking overrides the environment
@@ -1744,6 +1751,27 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
         blk_heavy_bits_kernel<<<nblk(n), 256, 0, g_stream>>>(pe.off, ba.row0, n, pe.rows, heavy_min, k.heavy_bits); LAUNCH_CHECK();
         k.acc = (uint8_t*)g_pool.alloc((size_t)rpad * ti->acc_bytes);
         CK(cudaStreamSynchronize(g_stream));
+        // per block the list of rows that own an entry in it: the middle sweeps visit only those
+        k.arows.assign(nb, nullptr); k.acount.assign(nb, 0);
+        {
+            uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
+            uint32_t* scr2 = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+            for (uint32_t b = 0; b < nb; ++b) {
+                if (k.bstart[b + 1] == k.bstart[b]) continue;
+                blk_active_flags_kernel<<<nblk(n), 256, 0, g_stream>>>(k.boff + (size_t)b * rpad, n, flag); LAUNCH_CHECK();
+                vbp::exclusive_scan(flag, pos, n, d_scalars, scr2, g_stream); g_launches += 3;
+                uint32_t cnt = 0;
+                CK(cudaMemcpyAsync(&cnt, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+                CK(cudaStreamSynchronize(g_stream));
+                k.acount[b] = cnt;
+                if (cnt && (double)cnt < 0.75 * n) {     // a list only pays off when a good part of the rows can be skipped
+                    k.arows[b] = dalloc<uint32_t>(cnt);
+                    vbp::compact_indices_kernel<<<nblk(n), 256, 0, g_stream>>>(flag, pos, n, k.arows[b]); LAUNCH_CHECK();
+                }
+            }
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(flag); dfree(pos); dfree(scr2);
+        }
     } catch (...) {
         free_blocked(pe);
         k.seen_version = pe.version; k.seen = 2; k.refused = true;     // e.g. out of memory: stay on the direct path
@@ -2121,7 +2149,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 EdgeStore& pe = s.E(ti->primary_edge);
                 const EdgeStore::Blocked& k = pe.blk;
                 uint32_t swept = 0;
-                static int n_sm = [] { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, g_device); return v; }();
+                static const bool use_lists = !(getenv("VB_BLOCK_LISTS") && atoi(getenv("VB_BLOCK_LISTS")) == 0);
                 static const int l2_mb = getenv("VB_BLOCK_L2_MB") ? atoi(getenv("VB_BLOCK_L2_MB")) : 64;
                 cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)l2_mb << 20);   // room for the evict_last source block
                 cudaGetLastError();
@@ -2129,22 +2157,31 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 CK(cudaEventRecord(s.evk[0], g_stream));
                 vb::LaunchArgs lb = la;
                 lb.blk_src = k.bsrc; lb.blk_acc = k.acc; lb.blk_stride = k.rpad; lb.blk_heavy = heavy_n ? k.heavy_bits : nullptr;
-                lb.blk_ctas = n_sm * ti->blocked_ctas_per_sm();
                 // sweeps over blocks that hold no entry (capacity beyond the agents in use) are skipped; the first sweep that runs
                 // initialises the accumulators, the last one runs finish()
                 std::vector<uint32_t> todo;
                 for (uint32_t b = 0; b < k.nb; ++b) if (k.bstart[b + 1] > k.bstart[b]) todo.push_back(b);
                 while (todo.size() < 2) { uint32_t b = 0; while (std::find(todo.begin(), todo.end(), b) != todo.end()) ++b; todo.push_back(b); std::sort(todo.begin(), todo.end()); }
+                // the hub rows left to the block-per-agent pass (a handful of CTAs with long dependent chains) run beside the sweeps
+                // on a second stream: they read the same read buffer and write rows the last sweep skips
+                static cudaStream_t side = nullptr;
+                static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+                if (heavy_n) {
+                    if (!side) { CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming)); }
+                    CK(cudaEventRecord(ev_fork, g_stream));
+                    CK(cudaStreamWaitEvent(side, ev_fork, 0));
+                    vb::LaunchArgs lh = la;
+                    lh.group = 256; lh.rows = heavy_rows; lh.n = heavy_n; lh.heavy_min = 0; lh.stream = side;
+                    CK(ti->launch(lh)); ++g_launches;
+                    CK(cudaEventRecord(ev_join, side));
+                }
                 for (size_t i = 0; i < todo.size(); ++i) {
                     lb.blk_off = k.boff + (size_t)todo[i] * k.rpad; lb.blk_first = i == 0; lb.blk_last = i + 1 == todo.size();
+                    lb.blk_rows = use_lists ? k.arows[todo[i]] : nullptr; lb.blk_nrows = k.acount[todo[i]];
                     CK(ti->launch_blocked(lb)); ++g_launches;
                 }
                 swept = (uint32_t)todo.size();
-                if (heavy_n) {
-                    vb::LaunchArgs lh = la;
-                    lh.group = 256; lh.rows = heavy_rows; lh.n = heavy_n; lh.heavy_min = 0;
-                    CK(ti->launch(lh)); ++g_launches;
-                }
+                if (heavy_n) CK(cudaStreamWaitEvent(g_stream, ev_join, 0));
                 CK(cudaEventRecord(s.evk[1], g_stream));
                 CK(cudaStreamSynchronize(g_stream));
                 cudaCtxResetPersistingL2Cache();
