@@ -161,6 +161,7 @@ struct LaunchArgs {
     uint32_t blk_ahead;                   // CTAs of look-ahead of the L2 prefetch (about one residency wave), 0 = off
     const uint32_t* blk_rows;             // middle sweeps: ascending list of the rows that own an entry in this block (else nullptr:
     uint32_t blk_nrows;                   //   all n rows are swept); rows outside the list keep their parked accumulator untouched
+    const uint32_t* blk_roff;             // with a row list: [blk_nrows + 1] entry positions of the listed rows (their entries are contiguous)
     cudaStream_t stream;
 };
 // what the kernel actually receives: launch arguments + the whole simulation view, by value in the
@@ -911,6 +912,9 @@ template <class T> __device__ __forceinline__ T soa_load_cs(const uint8_t* __res
 }
 }  // namespace blk
 
+#ifndef VB_BLK_MINCTAS
+#define VB_BLK_MINCTAS 6
+#endif
 template <class F> struct BlockedCfg {
     typedef typename F::State State;
     typedef typename F::Source Source;
@@ -944,7 +948,7 @@ template <class F> struct BlockedCfg {
 };
 
 template <class F, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(256, 6) reduce_blocked_kernel(const __grid_constant__ KernelArgs ka) {
+__global__ void __launch_bounds__(256, VB_BLK_MINCTAS) reduce_blocked_kernel(const __grid_constant__ KernelArgs ka) {
     typedef BlockedCfg<F> C;
     typedef typename C::State State;
     typedef typename C::Source Source;
@@ -971,24 +975,35 @@ __global__ void __launch_bounds__(256, 6) reduce_blocked_kernel(const __grid_con
     // its offsets, own states and parked accumulators now, its index range at the end (once the two bounding offsets arrived).
     const uint32_t pc = blockIdx.x + la.blk_ahead;
     uint32_t pa = 0, pb = 0;
-    if (la.blk_ahead && pc < gridDim.x && !listed) {
-        const uint32_t r0 = pc * 256u, nr = la.n - r0 < 256u ? la.n - r0 : 256u;
-        if (threadIdx.x == 0) { pa = __ldg(la.blk_off + r0); pb = __ldg(la.blk_off + r0 + nr); }
-        blk::prefetch_l2(la.blk_off + r0, (size_t)(nr + 1) * 4, threadIdx.x, 256);
-        constexpr int SW = SoaWord<sizeof(State)>::value, SC = sizeof(State) / SW;
+    const bool ahead = la.blk_ahead && pc < gridDim.x;
+    if (ahead) {
+        const uint32_t r0 = pc * 256u, nr = nwork - r0 < 256u ? nwork - r0 : 256u;
+        const uint32_t* __restrict__ offs = listed ? la.blk_roff : la.blk_off;
+        if (threadIdx.x == 0) { pa = __ldg(offs + r0); pb = __ldg(offs + r0 + nr); }
+        blk::prefetch_l2(offs + r0, (size_t)(nr + 1) * 4, threadIdx.x, 256);
+        if (listed) blk::prefetch_l2(la.blk_rows + r0, (size_t)nr * 4, threadIdx.x, 256);   // (own states / accumulators of listed rows are scattered)
+        else {
+            constexpr int SW = SoaWord<sizeof(State)>::value, SC = sizeof(State) / SW;
 #pragma unroll
-        for (int c = 0; c < SC; ++c) blk::prefetch_l2(av.state_r + ((size_t)c * av.cap + r0) * SW, (size_t)nr * SW, threadIdx.x, 256);
-        if (!FIRST) {
+            for (int c = 0; c < SC; ++c) blk::prefetch_l2(av.state_r + ((size_t)c * av.cap + r0) * SW, (size_t)nr * SW, threadIdx.x, 256);
+            if (!FIRST) {
 #pragma unroll
-            for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, threadIdx.x, 256);
+                for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, threadIdx.x, 256);
 #pragma unroll
-            for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, threadIdx.x, 256);
+                for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, threadIdx.x, 256);
+            }
         }
     }
     // no early exit: the 32 rows of a warp are walked together.  Their entries are contiguous: [lo of lane 0, hi of lane 31)
     // (with a row list the listed rows' entries are still contiguous: the rows in between own none)
-    const uint32_t row = gtid < nwork ? idx : la.n;                        // rows past the end: an empty range at the very end
-    uint32_t lo = __ldcs(la.blk_off + row), hi = gtid < nwork ? __ldcs(la.blk_off + row + 1) : lo;
+    uint32_t lo, hi;
+    if (listed) {
+        const uint32_t i = gtid < nwork ? (uint32_t)gtid : nwork;
+        lo = __ldcs(la.blk_roff + i); hi = gtid < nwork ? __ldcs(la.blk_roff + i + 1) : lo;
+    } else {
+        const uint32_t row = gtid < nwork ? idx : la.n;                    // rows past the end: an empty range at the very end
+        lo = __ldcs(la.blk_off + row); hi = gtid < nwork ? __ldcs(la.blk_off + row + 1) : lo;
+    }
     const bool act = gtid < nwork && !(av.died_r && av.died_r[idx]);       // jump over died agents (AgentMethods.jl:199-203)
     const F f{};
     Ctx<F, MODE_DIRECT, 1> ctx(ds, la, idx, 0);
@@ -1020,7 +1035,7 @@ __global__ void __launch_bounds__(256, 6) reduce_blocked_kernel(const __grid_con
         for (uint32_t x = b; x < e; ++x) f.fold(ctx, self, val[x - base], acc);
         __syncwarp();
     }
-    if (threadIdx.x < 32 && la.blk_ahead && pc < gridDim.x && !listed) {              // warp 0: the index range of the CTA `blk_ahead` later
+    if (threadIdx.x < 32 && ahead) {                                       // warp 0: the index range of the CTA `blk_ahead` later
         pa = __shfl_sync(0xffffffffu, pa, 0); pb = __shfl_sync(0xffffffffu, pb, 0);
         blk::prefetch_l2(gsrc + pa, (size_t)(pb - pa) * 4, lane, 32);
     }

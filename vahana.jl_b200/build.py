@@ -12,7 +12,7 @@ SOURCES = [os.path.join(CSRC, "engine", "engine.cu"), os.path.join(CSRC, "transi
            os.path.join(CSRC, "transitions", "builtin_tests.cu"),
            os.path.join(CSRC, "workloads", "generators.cu")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("VB_NVCC_EXTRA", "").split()   # e.g. -DVB_BLK_MINCTAS=8 for tuning runs
 
 
 def _deps():

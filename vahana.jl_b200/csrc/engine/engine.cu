@@ -488,6 +488,11 @@ __global__ void blk_active_flags_kernel(const uint32_t* __restrict__ boff, uint3
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = boff[i + 1] > boff[i] ? 1u : 0u;
 }
+__global__ void blk_listed_offsets_kernel(const uint32_t* __restrict__ boff, const uint32_t* __restrict__ rows, uint32_t cnt, uint32_t end, uint32_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) out[i] = boff[rows[i]];
+    else if (i == cnt) out[i] = end;
+}
 __global__ void blk_count_kernel(const BlkBuildArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -770,6 +775,7 @@ struct EdgeStore {
         uint32_t nb = 0, bsize = 0, rpad = 0, n = 0, acc_bytes = 0, heavy_min = 0;
         std::vector<uint32_t> bstart;                 // position in bsrc where each block's entries start (nb + 1 values)
         std::vector<uint32_t*> arows;                 // per block: ascending list of the rows that own an entry in it
+        std::vector<uint32_t*> aoff;                  //   and the positions of their entries ([acount + 1], contiguous in bsrc)
         std::vector<uint32_t> acount;
         int called = 0, source = 0;
         uint64_t version = ~0ull, epoch = ~0ull;      // container version / sim layout epoch the view was built for
@@ -859,6 +865,7 @@ void free_agent(AgentStore& a) {
 }
 void free_blocked(EdgeStore& e) {
     for (auto p : e.blk.arows) dfree(p);
+    for (auto p : e.blk.aoff) dfree(p);
     dfree(e.blk.boff); dfree(e.blk.bsrc); dfree(e.blk.heavy_bits); dfree(e.blk.acc);
     e.blk = EdgeStore::Blocked{};
 }
@@ -1686,11 +1693,11 @@ void vb_sim::transmit_edges(int ei) {
 // Source-blocked view of edge type `ei` for the reduce transition `ti` called on agent type C (n slots).  Returns true when the view
 // is ready.  Policy: only for gather-bound shapes (the source type's state array is several times the L2 set-aside) and only once
 // the same container has been seen by two applies (a network rebuilt every step never amortises the build).
-// VB_BLOCK=0 disables, VB_BLOCK_MB sets the block size (default 88 MB of source states), VB_BLOCK_MIN_MB the activation threshold
+// VB_BLOCK=0 disables, VB_BLOCK_MB sets the block size (default 75 MB of source states), VB_BLOCK_MIN_MB the activation threshold
 // (default 192 MB), VB_BLOCK_EAGER=1 builds at first sight (tests).
 bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min) {
     static const bool enabled = !(getenv("VB_BLOCK") && atoi(getenv("VB_BLOCK")) == 0);
-    static const double env_block_mb = getenv("VB_BLOCK_MB") ? atof(getenv("VB_BLOCK_MB")) : 88.0;
+    static const double env_block_mb = getenv("VB_BLOCK_MB") ? atof(getenv("VB_BLOCK_MB")) : 75.0;
     static const double env_min_mb = getenv("VB_BLOCK_MIN_MB") ? atof(getenv("VB_BLOCK_MIN_MB")) : 192.0;
     static const bool env_eager = getenv("VB_BLOCK_EAGER") && atoi(getenv("VB_BLOCK_EAGER")) != 0;
     const double block_mb = blk_block_mb > 0 ? blk_block_mb : env_block_mb;       // vb_set_read_blocking overrides the environment
@@ -1752,7 +1759,7 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
         k.acc = (uint8_t*)g_pool.alloc((size_t)rpad * ti->acc_bytes);
         CK(cudaStreamSynchronize(g_stream));
         // per block the list of rows that own an entry in it: the middle sweeps visit only those
-        k.arows.assign(nb, nullptr); k.acount.assign(nb, 0);
+        k.arows.assign(nb, nullptr); k.aoff.assign(nb, nullptr); k.acount.assign(nb, 0);
         {
             uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
             uint32_t* scr2 = dalloc<uint32_t>(vbp::scan_scratch_words(n));
@@ -1767,6 +1774,8 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
                 if (cnt && (double)cnt < 0.75 * n) {     // a list only pays off when a good part of the rows can be skipped
                     k.arows[b] = dalloc<uint32_t>(cnt);
                     vbp::compact_indices_kernel<<<nblk(n), 256, 0, g_stream>>>(flag, pos, n, k.arows[b]); LAUNCH_CHECK();
+                    k.aoff[b] = dalloc<uint32_t>((uint64_t)cnt + 1);
+                    blk_listed_offsets_kernel<<<nblk((uint64_t)cnt + 1), 256, 0, g_stream>>>(k.boff + (size_t)b * rpad, k.arows[b], cnt, k.bstart[b + 1], k.aoff[b]); LAUNCH_CHECK();
                 }
             }
             CK(cudaStreamSynchronize(g_stream));
@@ -2177,7 +2186,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 }
                 for (size_t i = 0; i < todo.size(); ++i) {
                     lb.blk_off = k.boff + (size_t)todo[i] * k.rpad; lb.blk_first = i == 0; lb.blk_last = i + 1 == todo.size();
-                    lb.blk_rows = use_lists ? k.arows[todo[i]] : nullptr; lb.blk_nrows = k.acount[todo[i]];
+                    lb.blk_rows = use_lists ? k.arows[todo[i]] : nullptr; lb.blk_roff = k.aoff[todo[i]]; lb.blk_nrows = k.acount[todo[i]];
                     CK(ti->launch_blocked(lb)); ++g_launches;
                 }
                 swept = (uint32_t)todo.size();
