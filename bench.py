@@ -226,7 +226,7 @@ def run_engine(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "hk_step_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1 and n == 100_000_000:     # the ncu capture is of the 1-GPU, 100M-agent step
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     cpu_eps, cpu_ms, cpu_ne = time_oracle(vh, args.cpu_agents, 3, 1) if (not args.no_cpu and world == 1) else (None, None, None)

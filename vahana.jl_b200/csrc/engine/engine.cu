@@ -428,6 +428,26 @@ __global__ void halo_pack_kernel(const uint8_t* __restrict__ cols, uint32_t stri
     else if (word == 4) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
     else for (uint32_t b = 0; b < word; ++b) dp[b] = sp[b];
 }
+// halo push: the owner writes the requested states straight into the peers' ghost segments (peer memory over NVLink / NVSwitch):
+// pack and transfer are one kernel, the stores of a warp are contiguous in the peer's buffer (transmit_agents!, src/MPI.jl:155-267)
+struct HaloPushArgs {
+    const uint8_t* cols; uint32_t stride; const uint32_t* slots; uint32_t n, word, ncols, nranks;
+    uint32_t send_off[17];                    // [nranks + 1] (at most 16 ranks take this path)
+    uint8_t* remote[16]; uint32_t rstride[16]; uint32_t rghost0[16];
+};
+__global__ void halo_push_kernel(const HaloPushArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)a.n * a.ncols) return;
+    const uint32_t i = (uint32_t)(t % a.n), c = (uint32_t)(t / a.n);
+    uint32_t r = 0;
+    while (r + 1 < a.nranks && i >= a.send_off[r + 1]) ++r;
+    const uint8_t* sp = a.cols + (size_t)c * a.stride * a.word + (size_t)a.slots[i] * a.word;
+    uint8_t* dp = a.remote[r] + (size_t)c * a.rstride[r] * a.word + (size_t)(a.rghost0[r] + (i - a.send_off[r])) * a.word;
+    if (a.word == 8) *reinterpret_cast<uint64_t*>(dp) = *reinterpret_cast<const uint64_t*>(sp);
+    else if (a.word == 4) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
+    else if (a.word == 16) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
+    else for (uint32_t b = 0; b < a.word; ++b) dp[b] = sp[b];
+}
 // died-agent ids of the other ranks (C7: join(aids), src/AgentMethods.jl:338): mark the ghosts that mirror them
 struct MarkDeadArgs {
     const uint64_t* ids; uint32_t n; uint8_t* dead; uint32_t rank; uint32_t ntypes;
@@ -724,6 +744,14 @@ struct AgentStore {
     std::vector<uint32_t> ghost_off;          // [nranks + 1] ghost range per owner rank
     uint32_t* send_slots = nullptr;           // device: local slots requested by the peers, grouped by peer
     std::vector<uint32_t> send_off;           // [nranks + 1]
+    // peer-memory halo (one kernel packs and pushes over NVLink): the peers' state buffers mapped into this process
+    struct PeerMap {
+        std::vector<uint8_t*> base[2];        // [nranks] peer r's state[0] / state[1] (nullptr for this rank)
+        std::vector<uint32_t> stride, ghost0; // peer r's column stride; first ghost slot of MY agents in peer r's buffers
+        std::vector<void*> opened;            // cudaIpcOpenMemHandle results to close on refresh
+        uint64_t sig = 0;                     // layout signature the map was exchanged for (0 = never)
+        bool ok = false;
+    } peers;
     uint8_t* send_buf = nullptr;              // packed states for the halo exchange
     bool halo_dirty = true;
     uint32_t stride() const { return cap + gcap; }
@@ -832,6 +860,7 @@ struct vb_sim {
     void ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need = 0, bool do_rebase = true);
     void build_ghosts(const uint64_t* const* extra = nullptr, const uint64_t* extra_n = nullptr, int n_extra = 0);
     void halo_exchange(int t);
+    bool refresh_peer_map(int t);
     uint64_t halo_bytes = 0;   // bytes received by the last apply's halo exchanges
     double blk_block_mb = -1, blk_min_mb = -1; int blk_eager = -1;   // vb_set_read_blocking (negative = environment / default)
     uint32_t last_blocked_nb = 0;   // source blocks swept by the last apply's read phase (0 = direct path)
@@ -859,6 +888,9 @@ struct vb_sim {
 namespace {
 
 void free_agent(AgentStore& a) {
+    for (void* q : a.peers.opened) cudaIpcCloseMemHandle(q);
+    cudaGetLastError();
+    a.peers = AgentStore::PeerMap{};
     dfree(a.state[0]); if (a.state[1] != a.state[0]) dfree(a.state[1]);
     dfree(a.died[0]); dfree(a.died[1]); dfree(a.reuse); dfree(a.ghost_ids); dfree(a.send_slots); dfree(a.send_buf);
     a.state[0] = a.state[1] = a.died[0] = a.died[1] = nullptr; a.reuse = nullptr; a.ghost_ids = nullptr; a.send_slots = nullptr; a.send_buf = nullptr;
@@ -1794,12 +1826,95 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
     return true;
 }
 
+// stream-ordered barrier across the ranks: a collective completes on a rank only after every rank's stream has reached it
+static void stream_barrier() {
+    static uint64_t* buf = nullptr;
+    if (!buf) buf = dalloc<uint64_t>((size_t)g_nranks + 1);
+    NK(g_nccl.AllGather(buf + g_nranks, buf, 8, ncclUint8, g_comm, g_stream));
+}
+// (Re)maps the peers' state buffers of agent type t when any rank's layout changed (collective).  Returns false when the
+// peer-memory path is not available (more than 16 ranks, IPC refused): the caller falls back to ncclSend/ncclRecv.
+bool vb_sim::refresh_peer_map(int t) {
+    AgentStore& a = A(t);
+    static const bool enabled = !(getenv("VB_HALO_P2P") && atoi(getenv("VB_HALO_P2P")) == 0);
+    const uint32_t P = (uint32_t)g_nranks;
+    if (!enabled || P > 16) return false;
+    // layout signature of this rank: buffers, stride, ghost table
+    uint64_t sig = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((uint64_t)(uintptr_t)a.state[0]); mix((uint64_t)(uintptr_t)a.state[1]); mix(a.stride()); mix(a.cap); mix(a.nghost);
+    for (uint32_t r = 0; r <= P; ++r) mix(a.ghost_off[r]);
+    if (sig == 0) sig = 1;
+    uint64_t changed = (a.peers.sig != sig) ? 1 : 0;
+    std::vector<uint64_t> all;
+    allgather8_host(&changed, all);
+    bool any = false;
+    for (uint64_t v : all) any |= v != 0;
+    if (!any) return a.peers.ok;
+    // exchange {ipc handles of both buffers, stride, cap, ghost_off[]}
+    struct Desc { cudaIpcMemHandle_t h[2]; uint32_t same, stride, cap, pad; uint32_t ghost_off[17]; uint32_t pad2; };
+    static_assert(sizeof(Desc) % 8 == 0, "descriptor is exchanged in 8-byte units");
+    Desc mine{};
+    bool ok = true;
+    for (int b = 0; b < 2; ++b) {
+        if (b == 1 && a.state[1] == a.state[0]) { mine.same = 1; mine.h[1] = mine.h[0]; continue; }
+        if (cudaIpcGetMemHandle(&mine.h[b], a.state[b]) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    }
+    mine.stride = a.stride(); mine.cap = a.cap; mine.pad = ok ? 1u : 0u;
+    for (uint32_t r = 0; r <= P; ++r) mine.ghost_off[r] = a.ghost_off[r];
+    uint8_t* dsend = (uint8_t*)g_pool.alloc(sizeof(Desc)); uint8_t* drecv = (uint8_t*)g_pool.alloc(sizeof(Desc) * P);
+    CK(cudaMemcpyAsync(dsend, &mine, sizeof(Desc), cudaMemcpyHostToDevice, g_stream));
+    NK(g_nccl.AllGather(dsend, drecv, sizeof(Desc), ncclUint8, g_comm, g_stream));
+    std::vector<Desc> descs(P);
+    CK(cudaMemcpyAsync(descs.data(), drecv, sizeof(Desc) * P, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(dsend); dfree(drecv);
+    for (void* q : a.peers.opened) cudaIpcCloseMemHandle(q);
+    cudaGetLastError();
+    a.peers.opened.clear();
+    a.peers.base[0].assign(P, nullptr); a.peers.base[1].assign(P, nullptr); a.peers.stride.assign(P, 0); a.peers.ghost0.assign(P, 0);
+    for (uint32_t r = 0; r < P; ++r) ok &= descs[r].pad == 1u;
+    for (uint32_t r = 0; r < P && ok; ++r) {
+        if (r == rank) continue;
+        for (int b = 0; b < 2; ++b) {
+            if (b == 1 && descs[r].same) { a.peers.base[1][r] = a.peers.base[0][r]; continue; }
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, descs[r].h[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            a.peers.opened.push_back(q);
+            a.peers.base[b][r] = (uint8_t*)q;
+        }
+        a.peers.stride[r] = descs[r].stride;
+        a.peers.ghost0[r] = descs[r].cap + descs[r].ghost_off[rank];     // my agents' slots in peer r's ghost segment
+    }
+    // every rank must take the same path
+    uint64_t good = ok ? 1 : 0;
+    allgather8_host(&good, all);
+    for (uint64_t v : all) ok &= v != 0;
+    a.peers.ok = ok;
+    a.peers.sig = sig;
+    return ok;
+}
+
 void vb_sim::halo_exchange(int t) {
     AgentStore& a = A(t);
     if (g_nranks <= 1 || !a.halo_dirty) return;
     a.halo_dirty = false;
     if (!a.size || a.send_off.empty()) return;
     const uint32_t P = (uint32_t)g_nranks, ns = a.send_off[P];
+    if (refresh_peer_map(t)) {
+        // peer-memory path: barrier (no peer still reads last step's ghosts) -> pack + push in one kernel -> barrier (all pushes landed)
+        stream_barrier();
+        if (ns) {
+            HaloPushArgs h{};
+            h.cols = a.rstate(); h.stride = a.stride(); h.slots = a.send_slots; h.n = ns; h.word = a.word; h.ncols = a.ncols; h.nranks = P;
+            for (uint32_t r = 0; r <= P; ++r) h.send_off[r] = a.send_off[r];
+            for (uint32_t r = 0; r < P; ++r) { h.remote[r] = a.peers.base[a.cur][r]; h.rstride[r] = a.peers.stride[r]; h.rghost0[r] = a.peers.ghost0[r]; }
+            halo_push_kernel<<<nblk((uint64_t)ns * a.ncols), 256, 0, g_stream>>>(h); LAUNCH_CHECK();
+        }
+        stream_barrier();
+        halo_bytes += (uint64_t)a.nghost * a.size;
+        return;
+    }
     if (ns) { halo_pack_kernel<<<nblk((uint64_t)ns * a.ncols), 256, 0, g_stream>>>(a.rstate(), a.stride(), a.send_slots, ns, a.send_buf, a.word, a.ncols); LAUNCH_CHECK(); }
     NK(g_nccl.GroupStart());
     for (uint32_t c = 0; c < a.ncols; ++c) {
@@ -2465,6 +2580,7 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
         };
         for (auto& a : o.agents) {
             AgentStore b = a;
+            b.peers = AgentStore::PeerMap{};      // the copy maps its peers on its first halo exchange
             if (a.size && a.cap) { b.state[0] = (uint8_t*)dup(a.state[0], (size_t)a.stride() * a.size); b.state[1] = a.independent ? b.state[0] : (uint8_t*)dup(a.state[1], (size_t)a.stride() * a.size); }
             if (!a.immortal && a.cap) { b.died[0] = (uint8_t*)dup(a.died[0], a.stride()); b.died[1] = (uint8_t*)dup(a.died[1], a.stride()); b.ghost_ids = (uint64_t*)dup(a.ghost_ids, (size_t)a.nghost * 8); b.send_slots = (uint32_t*)dup(a.send_slots, (a.send_off.empty() ? 0 : (size_t)a.send_off.back()) * 4); b.send_buf = nullptr; b.reuse = (uint32_t*)dup(a.reuse, (size_t)a.reuse_cap * 4); }
             s->agents.push_back(b);
