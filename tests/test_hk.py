@@ -161,3 +161,41 @@ def test_hk_blocked_matches_direct_on_hub_graph(oracle, cuda):
         assert nb == (0 if step == 0 else 8), nb           # first apply: direct (the container has not been seen twice yet)
         assert b.last_apply_stats()["edges_read"] == d.last_apply_stats()["edges_read"] == ne.value
         np.testing.assert_allclose(_opinions(b), _opinions(d), rtol=RTOL, atol=0)
+
+
+@pytest.mark.gpu
+def test_hk_full_size_blocked_vs_direct_properties(cuda):
+    """BASELINE config 4 at full size (1e8 agents, 2.1e9 edges): too large for the Dict-based oracle, so the two read-phase forms of
+    the engine check each other and the step is checked through size-independent properties of the update rule:
+    every new opinion is a mean of opinions within eps of the old one (|new - old| < eps, range never grows), every agent reads
+    exactly its row (edges_read == number of edges), and mapreduce(+) equals the sum of the downloaded states."""
+    import ctypes as C
+    import torch
+    from models import hk_model
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~90 GB of free device memory")
+    n, eps = 100_000_000, 0.02
+    sims = []
+    for blocked in (False, True):
+        g = vh.create_simulation(hk_model(), params={"eps": eps}, backend=cuda)
+        ne = C.c_uint64()
+        cuda.check(cuda.lib.vbw_hk_powerlaw_build(g.h, 1, 0, C.c_uint64(n), C.c_uint64(4), C.c_uint64(5), C.c_double(6.8333), C.c_uint32(1000000),
+                                                  C.c_uint64(1 << 22), C.byref(ne)))
+        g.finish_init()
+        g.set_read_blocking(-1.0 if blocked else 0.0, -1.0, 1 if blocked else 0)
+        sims.append(g)
+    d, b = sims
+    old = _opinions(d)
+    for step in range(2):
+        d.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        b.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        sd, sb = d.last_apply_stats(), b.last_apply_stats()
+        assert sd["source_blocks"] == 0 and sb["source_blocks"] >= 8
+        assert sd["edges_read"] == sb["edges_read"] == ne.value
+        od, ob = _opinions(d), _opinions(b)
+        np.testing.assert_allclose(ob, od, rtol=RTOL, atol=0)
+        assert np.all(np.abs(od - old) < eps)                       # a mean of values within eps of the old opinion
+        assert od.min() >= old.min() and od.max() <= old.max()      # the opinion range never grows
+        assert abs(d.mapreduce("opinion", "+", "HKAgent") - float(np.sum(od))) < 1e-9 * n
+        old = od
