@@ -112,6 +112,25 @@ def test_graphs(backend):  # test/graphs.jl:17-45
     assert sim.mapreduce("sum_ids_neighbors", "+", "GraphA") == sum(range(1, nagents + 1)) * (nagents - 1)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("nagents,block_mb", [(4, 0.000016), (300, 0.0004), (1500, 0.003)])
+def test_graphs_source_blocked(cuda, nagents, block_mb):
+    """test/graphs.jl:37-43 (complete graph, sum of neighbour ids == sum(1:n) * (n - 1)) with the read phase forced into per-source-block
+    sweeps: the reference's golden value, bit-exact (integer fold), with rows of up to n - 1 entries spread over many blocks."""
+    sim = vh.create_simulation(graph_model(), backend=cuda)
+    uv = np.array([(i, j) for i in range(nagents) for j in range(i + 1, nagents)])
+    states = np.array([(i, 0) for i in range(1, nagents + 1)], dtype=[("id", "i8"), ("sum_ids_neighbors", "i8")])
+    vh.add_graph(sim, uv, nagents, "GraphA", states, "GraphE")
+    sim.finish_init()
+    sim.set_read_blocking(block_mb, 0.0, 1)
+    for _ in range(2):
+        sim.apply("sumids", ["GraphA"], ["GraphA", "GraphE"], ["GraphA"])
+        assert sim.last_apply_stats()["source_blocks"] >= 2
+        assert sim.mapreduce("sum_ids_neighbors", "+", "GraphA") == sum(range(1, nagents + 1)) * (nagents - 1)
+        got = sim.all_agents("GraphA")
+        assert np.array_equal(got["sum_ids_neighbors"], sum(range(1, nagents + 1)) - got["id"])
+
+
 @pytest.mark.parametrize("ET", STATEFUL_EDGE_TYPES)
 def test_edges_aggregate(backend, ET):  # test/edgesiterator.jl:59-98
     sim = vh.create_simulation(edges_model(), backend=backend)

@@ -203,15 +203,19 @@ template <int T> struct IndepSpawn : vb::TransitionBase {   // :164-176
 
 // ---- test/graphs.jl: GraphA = 1 {id, sum_ids_neighbors}, GraphE = 0 ----
 struct GraphA { int64_t id; int64_t sum_ids_neighbors; };
-struct SumIds : vb::TransitionBase {   // :19-23
+// :19-23  `sum(map(a -> a.id, neighborstates(sim, id, GraphE, GraphA)))` as a reduce transition: integer sums are exact in any
+// association, so the source-blocked read phase must reproduce the reference's golden value bit for bit
+struct SumIds : vb::ReduceTransition<SumIds> {
     using State = GraphA;
-    static constexpr bool kCooperative = true;
-    template <class Ctx> VB_HD bool operator()(Ctx& ctx, GraphA& a, vb::AgentID id) const {
-        int64_t s = 0;
-        ctx.for_each_neighbor(0, id, [&](vb::AgentID from) { s += ctx.template agentfield<int64_t>((int)vb::type_nr(from), from, 0); });
-        a.sum_ids_neighbors = ctx.sum(s);
-        return true;
-    }
+    using Source = GraphA;
+    struct Acc { int64_t s; };
+    static constexpr int kAccBytes = 8;
+    static constexpr int kPrimaryEdge = 0;
+    static constexpr int kSourceType = 1;
+    template <class Ctx> VB_HD void init(const Ctx&, const GraphA&, Acc& a) const { a.s = 0; }
+    template <class Ctx> VB_HD void fold(const Ctx&, const GraphA&, const GraphA& nb, Acc& a) const { a.s += nb.id; }
+    VB_HD void merge(Acc& a, const Acc& b) const { a.s += b.s; }
+    template <class Ctx> VB_HD bool finish(const Ctx&, GraphA& self, vb::AgentID, const Acc& a) const { self.sum_ids_neighbors = a.s; return true; }
 };
 
 // ---- test/raster.jl: GridA = 1, Grid3D = 2, Position = 3, MovingAgent = 4; GridE = 0, OnPosition = 1 ----
