@@ -188,6 +188,7 @@ struct TransitionInfo {
     uint32_t source_size;     // sizeof(F::Source)
     uint32_t acc_bytes;       // F::kAccBytes: bytes of the accumulator parked per row between sweeps
     cudaError_t (*launch_blocked)(const LaunchArgs&);
+    cudaError_t (*launch_stencil)(const LaunchArgs&);   // reduce transition whose primary edge type is an implicit raster stencil
 };
 // exported by libvahana_b200.so; model libraries call it from static initialisers
 extern "C" int vb_register_transition(const TransitionInfo* info);
@@ -1056,6 +1057,97 @@ __global__ void __launch_bounds__(256, VB_BLK_MINCTAS) reduce_blocked_kernel(con
     }
 }
 
+
+// ---- reduce transition over an implicit raster stencil (KIND_STENCIL): the grid-stencil kernel -----------------------------------
+// A thread per cell.  The generic accessor path enumerates a row in the reference's insertion order (sorted keys for border cells,
+// strided shares for lane groups); a reduce transition does not depend on the order, so this kernel only decodes the position,
+// walks the stencil offsets and folds the neighbour cells' states (adjacent slots: the loads of a warp coalesce and hit L1).
+template <class F>
+__global__ void __launch_bounds__(256) reduce_stencil_kernel(const __grid_constant__ KernelArgs ka) {
+    typedef typename F::State State;
+    typedef typename F::Source Source;
+    typedef typename F::Acc Acc;
+    const LaunchArgs& la = ka.la;
+    const DeviceSim& ds = ka.ds;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t idx = (uint32_t)gtid;
+    const AgentView& av = ds.agents[la.type];
+    const bool act = gtid < la.n && !(av.died_r && av.died_r[idx]);
+    uint32_t nedges = 0;
+    if (act) {
+        const EdgeView& ev = ds.edges[F::kPrimaryEdge];
+        const RasterView& rv = ds.rasters[ev.st_raster];
+        const StencilTab& tab = ds.stencils[ev.st_tab];
+        const AgentView& sv = ds.agents[F::kSourceType];
+        if (ds.check && (!ev.readable || !sv.readable)) atomicOr(ds.error, (uint32_t)(!ev.readable ? DERR_EDGE_NOT_READABLE : DERR_AGENT_NOT_READABLE));
+        State self;
+        if (la.in_read && av.size) self = soa_load<State>(av.state_r, av.cap, idx);
+        else memset(&self, 0, sizeof(State));
+        Ctx<F, MODE_DIRECT, 1> ctx(ds, la, idx, 0);
+        const F f{};
+        Acc acc;
+        f.init(ctx, self, acc);
+        const uint32_t lin = idx - ev.st_slot0;
+        if (la.type == rv.type && idx >= ev.st_slot0 && lin < rv.ncells) {
+            if (F::kSourceType != rv.type) atomicOr(ds.error, (uint32_t)DERR_AGENT_TYPE_MISMATCH);
+            else {
+                const uint8_t* __restrict__ st = sv.state_r;
+                const uint32_t cap = sv.cap, s0 = ev.st_slot0;
+                int32_t pos[MAX_RASTER_DIMS];
+                bool interior = true;
+                uint32_t rest = lin;
+#pragma unroll
+                for (int k = 0; k < MAX_RASTER_DIMS; ++k) {
+                    if (k < rv.ndims) {
+                        const uint32_t d = rv.dim32[k];
+                        const uint32_t q = (d & (d - 1)) == 0 ? rest >> (31 - __clz(d)) : rest / d;    // power-of-two extents: a shift
+                        pos[k] = (int32_t)(rest - q * d); rest = q;
+                        interior &= pos[k] >= (int32_t)ev.st_reach && pos[k] + (int32_t)ev.st_reach < (int32_t)d;
+                    } else pos[k] = 0;
+                }
+                if (interior) {
+                    for (int si = 0; si < ev.st_n; ++si) f.fold(ctx, self, soa_load<Source>(st, cap, s0 + (uint32_t)((int32_t)lin - tab.lin[si])), acc);
+                    nedges = (uint32_t)ev.st_n;
+                } else {
+                    for (int si = 0; si < ev.st_n; ++si) {
+                        uint32_t l = 0; bool ok = true;
+#pragma unroll
+                        for (int k = 0; k < MAX_RASTER_DIMS; ++k) {
+                            if (k >= rv.ndims) break;
+                            int32_t v = pos[k] - tab.off[si][k];
+                            const int32_t d = (int32_t)rv.dim32[k];
+                            if (v < 0 || v >= d) { if (!ev.st_periodic) { ok = false; break; } v %= d; if (v < 0) v += d; }
+                            l += (uint32_t)v * rv.stride32[k];
+                        }
+                        if (!ok) continue;
+                        f.fold(ctx, self, soa_load<Source>(st, cap, s0 + l), acc);
+                        ++nedges;
+                    }
+                }
+            }
+        }
+        const AgentID id = agent_id((uint32_t)la.type, ds.rank, (uint64_t)idx + 1);
+        const bool alive = f.finish(ctx, self, id, acc);
+        if (la.in_write) {                                                 // transition_with_write! (AgentMethods.jl:159-181)
+            if (alive) { if (av.size) soa_store<State>(av.independent ? av.state_r : av.state_w, av.cap, idx, self); }
+            else if (av.immortal) atomicOr(ds.error, (uint32_t)DERR_IMMORTAL_DIED);
+            else av.died_w[idx] = 1;
+        }
+    }
+    const unsigned total = __reduce_add_sync(0xffffffffu, nedges);
+    if ((threadIdx.x & 31) == 0 && total) atomicAdd(la.stats + ((blockIdx.x & 1023u) << 2), (unsigned long long)total);
+}
+template <class F>
+cudaError_t launch_stencil(const LaunchArgs& la) {
+    static thread_local KernelArgs ka;
+    ka.la = la;
+    ka.ds = *la.ds;
+    ka.la.ds = nullptr;
+    if (la.n == 0) return cudaSuccess;
+    reduce_stencil_kernel<F><<<(unsigned)(((unsigned long long)la.n + 255) / 256), 256, 0, la.stream>>>(ka);
+    return cudaGetLastError();
+}
+
 template <class F>
 cudaError_t launch_blocked(const LaunchArgs& la) {
     static thread_local KernelArgs ka;
@@ -1103,7 +1195,9 @@ TransitionInfo make_transition_info(const char* name, const char* agent_type) {
         ti.source_type = F::kSourceType;
         ti.source_size = (uint32_t)sizeof(typename F::Source);
         ti.acc_bytes = (uint32_t)F::kAccBytes;
-        ti.launch_blocked = &launch_blocked<F>;
+        // the source-blocked sweeps park states / accumulators as 4- and 8-byte words
+        if constexpr (sizeof(typename F::State) % 4 == 0 && sizeof(typename F::Acc) % 4 == 0 && F::kAccBytes % 4 == 0) ti.launch_blocked = &launch_blocked<F>;
+        ti.launch_stencil = &launch_stencil<F>;
     }
     return ti;
 }

@@ -2242,11 +2242,11 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             la.mode = vb::MODE_DIRECT;
             la.primary_edge = -1; la.heavy_min = 0; la.group = 0; la.rows = nullptr;
             uint32_t heavy_n = 0; const uint32_t* heavy_rows = nullptr;
-            bool blocked = false;
+            bool blocked = false, stencil_reduce = false;
             if (ti->cooperative && ti->primary_edge >= 0 && with_edge < 0) {
                 // degree binning (north_star: sub-warp / warp per agent, block per agent for rows >= 1024 entries)
                 EdgeStore& pe = s.E(ti->primary_edge);
-                if (pe.implicit_stencil) la.group = 1;   // grid stencil: a thread per cell, neighbour loads of a warp are adjacent
+                if (pe.implicit_stencil) { la.group = 1; stencil_reduce = ti->reduce && ti->launch_stencil; }   // grid stencil: a thread per cell, neighbour loads of a warp are adjacent
                 else if (pe.kind == vb::KIND_CSR && pe.off && (!pe.singletype || pe.target == C)) {
                     // Reduce transitions over a static network whose source states dwarf L2 sweep the rows once per L2-sized
                     // source block; only hub rows of >= 16384 entries are left to the block-per-agent pass there (the sweeps fold
@@ -2342,7 +2342,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 cudaGetLastError();
             }
             CK(cudaEventRecord(s.evk[0], g_stream));
-            CK(ti->launch(la)); ++g_launches;
+            if (stencil_reduce) CK(ti->launch_stencil(la)); else CK(ti->launch(la));
+            ++g_launches;
             if (heavy_n) {
                 vb::LaunchArgs lh = la;
                 lh.group = 256; lh.rows = heavy_rows; lh.n = heavy_n; lh.heavy_min = 0;

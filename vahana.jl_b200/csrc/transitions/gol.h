@@ -15,16 +15,20 @@ struct Cell { bool active; };
 enum : int { T_CELL = 1 };
 enum : int { E_NEIGHBOR = 0 };
 
-struct Life : vb::TransitionBase {
+// A reduce transition (include/vahana_model.h): the count of active neighbours is an integer fold, exact in any order, so the
+// engine may walk the implicit stencil with its grid-stencil kernel instead of enumerating the row in insertion order.
+struct Life : vb::ReduceTransition<Life> {
     using State = Cell;
-    static constexpr bool kCooperative = true;
+    using Source = Cell;
+    struct Acc { int32_t n; };
+    static constexpr int kAccBytes = 4;
     static constexpr int kPrimaryEdge = E_NEIGHBOR;
-    template <class Ctx>
-    VB_HD bool operator()(Ctx& ctx, Cell& self, vb::AgentID id) const {
-        int n = 0;
-        ctx.template for_each_neighborstate<Cell>(E_NEIGHBOR, T_CELL, id, [&](const Cell& c) { n += c.active ? 1 : 0; });
-        n = ctx.sum(n);
-        self.active = (n == 3) || (self.active && n == 2);
+    static constexpr int kSourceType = T_CELL;
+    template <class Ctx> VB_HD void init(const Ctx&, const Cell&, Acc& a) const { a.n = 0; }
+    template <class Ctx> VB_HD void fold(const Ctx&, const Cell&, const Cell& c, Acc& a) const { a.n += c.active ? 1 : 0; }
+    VB_HD void merge(Acc& a, const Acc& b) const { a.n += b.n; }
+    template <class Ctx> VB_HD bool finish(const Ctx&, Cell& self, vb::AgentID, const Acc& a) const {
+        self.active = (a.n == 3) || (self.active && a.n == 2);
         return true;
     }
 };
