@@ -977,21 +977,21 @@ __global__ void __launch_bounds__(256, VB_BLK_MINCTAS) reduce_blocked_kernel(con
     const uint32_t pc = blockIdx.x + la.blk_ahead;
     uint32_t pa = 0, pb = 0;
     const bool ahead = la.blk_ahead && pc < gridDim.x;
-    if (ahead) {
+    if (ahead && threadIdx.x < 64) {                                       // two warps issue the prefetches (one line per thread and round)
         const uint32_t r0 = pc * 256u, nr = nwork - r0 < 256u ? nwork - r0 : 256u;
         const uint32_t* __restrict__ offs = listed ? la.blk_roff : la.blk_off;
         if (threadIdx.x == 0) { pa = __ldg(offs + r0); pb = __ldg(offs + r0 + nr); }
-        blk::prefetch_l2(offs + r0, (size_t)(nr + 1) * 4, threadIdx.x, 256);
-        if (listed) blk::prefetch_l2(la.blk_rows + r0, (size_t)nr * 4, threadIdx.x, 256);   // (own states / accumulators of listed rows are scattered)
+        blk::prefetch_l2(offs + r0, (size_t)(nr + 1) * 4, threadIdx.x, 64);
+        if (listed) blk::prefetch_l2(la.blk_rows + r0, (size_t)nr * 4, threadIdx.x, 64);   // (own states / accumulators of listed rows are scattered)
         else {
             constexpr int SW = SoaWord<sizeof(State)>::value, SC = sizeof(State) / SW;
 #pragma unroll
-            for (int c = 0; c < SC; ++c) blk::prefetch_l2(av.state_r + ((size_t)c * av.cap + r0) * SW, (size_t)nr * SW, threadIdx.x, 256);
+            for (int c = 0; c < SC; ++c) blk::prefetch_l2(av.state_r + ((size_t)c * av.cap + r0) * SW, (size_t)nr * SW, threadIdx.x, 64);
             if (!FIRST) {
 #pragma unroll
-                for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, threadIdx.x, 256);
+                for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, threadIdx.x, 64);
 #pragma unroll
-                for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, threadIdx.x, 256);
+                for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, threadIdx.x, 64);
             }
         }
     }
