@@ -199,3 +199,29 @@ def test_hk_full_size_blocked_vs_direct_properties(cuda):
         assert od.min() >= old.min() and od.max() <= old.max()      # the opinion range never grows
         assert abs(d.mapreduce("opinion", "+", "HKAgent") - float(np.sum(od))) < 1e-9 * n
         old = od
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blocked", [False, True])
+def test_hk_mortal_agents_blocked_vs_oracle(oracle, cuda, blocked):
+    """Deaths next to the sweeps: agents die (`finish` returns false), their edges are purged, the container changes and the
+    blocked view is rebuilt; died rows are skipped by every later sweep.  Ids, survivors and CSR bit-exact, opinions within RTOL."""
+    n, m, eps = 6000, 6, 0.02
+    uv = ba_graph(n, m, 3)
+    op0 = np.random.default_rng(7).random(n)
+    g, _ = hk_sim(cuda, n, uv, op0, eps)
+    o, _ = hk_sim(oracle, n, uv, op0, eps)
+    g.set_read_blocking(0.004 if blocked else 0.0, 0.0, 1)
+    for step in range(5):
+        name = "hk_step_or_die" if step % 2 == 0 else "hk_step"
+        g.apply(name, "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        o.apply(name, "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        assert (g.last_apply_stats()["source_blocks"] >= 2) == blocked
+        assert g.num_agents("HKAgent") == o.num_agents("HKAgent")
+        assert np.array_equal(g.all_agentids("HKAgent"), o.all_agentids("HKAgent"))
+        assert g.num_edges("Knows") == o.num_edges("Knows")
+        np.testing.assert_allclose(_opinions(g), _opinions(o), rtol=RTOL, atol=0)
+    assert g.num_agents("HKAgent") < n                     # somebody did die
+    goff, gfrom, _ = g.export_csr("Knows", "HKAgent", n)
+    ooff, ofrom, _ = o.export_csr("Knows", "HKAgent", n)
+    assert np.array_equal(goff, ooff) and np.array_equal(gfrom, ofrom)

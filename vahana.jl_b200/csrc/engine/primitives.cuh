@@ -134,6 +134,22 @@ static __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32
     hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
+// lanes of the warp holding the same 9-bit digit value (bit 8 = "no key"): nine ballots instead of match.any, whose cost on
+// sm_100 grows with the number of distinct values in the warp (profiles: the scatter pass was issue-bound at 84 % SM throughput)
+__device__ __forceinline__ uint32_t match_digit(uint32_t d) {
+#ifdef VB_SORT_MATCH_ANY
+    return __match_any_sync(0xffffffffu, d);
+#else
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+#endif
+}
 struct NoPayload { uint8_t x; };
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
 __device__ __forceinline__ uint64_t ld_stream(const uint64_t* p) { return (uint64_t)__ldcs(reinterpret_cast<const unsigned long long*>(p)); }
@@ -181,7 +197,7 @@ static __global__ void __launch_bounds__(RS_THREADS, 4) rs_scatter_kernel(const 
         const uint32_t li = w * RS_SEG + r * 32 + lane;
         const bool valid = li < count;
         const uint32_t d = valid ? ((key[r] >> a.shift) & 255u) : 256u;
-        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        const uint32_t m = match_digit(d);
         const int leader = __ffs(m) - 1;
         uint32_t prev = 0;
         if (valid && lane == leader) prev = wh[w][d];
@@ -302,7 +318,7 @@ static __global__ void __launch_bounds__(RS_THREADS, 4) os_pass_kernel(const OsA
         const uint32_t li = w * RS_SEG + r * 32 + lane;
         const bool valid = li < count;
         const uint32_t d = valid ? ((key[r] >> a.shift) & 255u) : 256u;
-        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        const uint32_t m = match_digit(d);
         const int leader = __ffs(m) - 1;
         uint32_t prev = 0;
         if (valid && lane == leader) prev = wh[w][d];

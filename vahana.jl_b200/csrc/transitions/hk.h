@@ -36,4 +36,23 @@ struct Step : vb::ReduceTransition<Step> {
     }
 };
 
+// Test variant with mortality (not in the reference's example): an agent whose accepted neighbourhood averages below `eps * 10`
+// returns `nothing`.  Exercises died rows, the dead-agent edge purge and the rebuild of the source-blocked view next to the sweeps.
+struct StepOrDie : vb::ReduceTransition<StepOrDie> {
+    using State = HKAgent;
+    using Source = HKAgent;
+    using Acc = Step::Acc;
+    static constexpr int kAccBytes = 12;
+    static constexpr int kPrimaryEdge = E_KNOWS;
+    static constexpr int kSourceType = T_HKAGENT;
+    template <class Ctx> VB_HD void init(const Ctx& c, const HKAgent& s, Acc& a) const { Step().init(c, s, a); }
+    template <class Ctx> VB_HD void fold(const Ctx& c, const HKAgent& s, const HKAgent& nb, Acc& a) const { Step().fold(c, s, nb, a); }
+    VB_HD void merge(Acc& a, const Acc& b) const { Step().merge(a, b); }
+    template <class Ctx> VB_HD bool finish(const Ctx& ctx, HKAgent& self, vb::AgentID, const Acc& a) const {
+        if (a.n == 0) return false;                          // every neighbour (and the self loop) is gone or out of range
+        self.opinion = a.sum / (double)a.n;
+        return self.opinion >= ctx.template param<Params>().eps * 10.0;
+    }
+};
+
 }  // namespace hk
