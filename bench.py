@@ -201,7 +201,7 @@ def run_engine(args):
     if world > 1:
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches, edges_read, sweeps = 0.0, 0, 0, 0
+    kernel_ms, launches, edges_read, sweeps, prefiltered = 0.0, 0, 0, 0, False
     ev0.record()
     for _ in range(args.steps):
         step()
@@ -210,6 +210,7 @@ def run_engine(args):
         launches += st["kernel_launches"]
         edges_read += st["edges_read"]
         sweeps = st["source_blocks"]
+        prefiltered = st["prefiltered"]
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -249,7 +250,9 @@ def run_engine(args):
     tp = os.path.join(ROOT, "profiles", "hk_step_traffic.json")
     if os.path.exists(tp) and world == 1 and n == 100_000_000:     # the ncu capture is of the 1-GPU, 100M-agent step
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        if bool(tj.get("prefiltered", False)) == bool(prefiltered):     # a capture of the other kernel shape says nothing about this one
+            traffic = tj.get("dram_bytes_per_launch")
     cpu_eps, cpu_ms, cpu_ne = time_oracle(vh, args.cpu_agents, 3, 1) if (not args.no_cpu and world == 1) else (None, None, None)
     value = E * args.steps / (ms_total * 1e-3)
     line = {
@@ -262,9 +265,11 @@ def run_engine(args):
                    "l2": "inputs larger than L2 (source states 0.8 GB, CSR columns %.1f GB); no flush needed" % (4.0 * E / 1e9),
                    "agent_updates_per_s": n * args.steps / (ms_total * 1e-3), "build_s": t_build, "opinion_sum": metric},
         "roofline": {"bound": "hbm",
-                     "kernel": ("reduce_blocked_kernel<hk::Step> x %d source-block sweeps + transition_kernel<hk::Step, DIRECT, 256> (hub rows)" % sweeps)
+                     "kernel": ("build_keys_kernel<hk::Step> + reduce_prefilter_kernel<hk::Step> x %d key-block sweeps + transition_kernel<hk::Step, DIRECT, 256> (hub rows)" % sweeps)
+                     if (sweeps and prefiltered) else
+                     ("reduce_blocked_kernel<hk::Step> x %d source-block sweeps + transition_kernel<hk::Step, DIRECT, 256> (hub rows)" % sweeps)
                      if sweeps else "transition_kernel<hk::Step, DIRECT, 8 lanes per agent> + <..., 256> (hub rows)",
-                     "launches_per_step": (sweeps + 1) if sweeps else 2, "achieved": achieved, "peak": peak,
+                     "launches_per_step": (sweeps + 1 + int(prefiltered)) if sweeps else 2, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "frac_of_8TBs_spec": achieved / 8000.0},
         "cpu_baseline": None if cpu_eps is None else {

@@ -157,6 +157,11 @@ int vb_last_kernel_ms(vb_sim* sim, double* ms_out); /* CUDA-event time of the tr
 int vb_set_read_blocking(vb_sim* sim, double block_mb, double min_mb, int eager);
 /* Source blocks swept by the read phase of the last apply (0 = direct path): which kernel shape ran (read phase). */
 int vb_last_apply_blocks(vb_sim* sim, uint32_t* nblocks_out);
+/* Prefiltered sweeps for reduce transitions that name a one-byte key of the neighbour state (kPrefilter, include/vahana_model.h):
+   1 = on, 0 = off, negative = default (on; VB_PREFILTER=0 turns it off).  Results do not depend on it.  The second call reports
+   whether the last apply's sweeps were prefiltered. */
+int vb_set_read_prefilter(vb_sim* sim, int on);
+int vb_last_apply_prefiltered(vb_sim* sim, int* on_out);
 
 #ifdef __cplusplus
 }

@@ -162,6 +162,9 @@ struct LaunchArgs {
     const uint32_t* blk_rows;             // middle sweeps: ascending list of the rows that own an entry in this block (else nullptr:
     uint32_t blk_nrows;                   //   all n rows are swept); rows outside the list keep their parked accumulator untouched
     const uint32_t* blk_roff;             // with a row list: [blk_nrows + 1] entry positions of the listed rows (their entries are contiguous)
+    uint8_t* blk_key;                     // prefilter (F::kPrefilter): one key byte per slot of the source type, written by launch_keys
+    uint32_t blk_nkeys;                   //   slots of the source type covered by blk_key (local + ghosts)
+    int blk_prefilter;                    //   sweeps gather keys and fetch the exact state only where may_accept() holds
     cudaStream_t stream;
 };
 // what the kernel actually receives: launch arguments + the whole simulation view, by value in the
@@ -189,6 +192,8 @@ struct TransitionInfo {
     uint32_t acc_bytes;       // F::kAccBytes: bytes of the accumulator parked per row between sweeps
     cudaError_t (*launch_blocked)(const LaunchArgs&);
     cudaError_t (*launch_stencil)(const LaunchArgs&);   // reduce transition whose primary edge type is an implicit raster stencil
+    int prefilter;            // F::kPrefilter: the functor names a one-byte key of the source state (include/vahana_model.h)
+    cudaError_t (*launch_keys)(const LaunchArgs&);      // fills blk_key[0 .. blk_nkeys) from the source type's read states
 };
 // exported by libvahana_b200.so; model libraries call it from static initialisers
 extern "C" int vb_register_transition(const TransitionInfo* info);
@@ -1058,6 +1063,184 @@ __global__ void __launch_bounds__(256, VB_BLK_MINCTAS) reduce_blocked_kernel(con
 }
 
 
+// ---- prefiltered sweep (F::kPrefilter, include/vahana_model.h) ----------------------------------------------------------------------
+// Same walk as reduce_blocked_kernel — a warp owns 32 consecutive (listed) rows and takes their contiguous entries edge-parallel in
+// chunks — but what is gathered for every entry is the one-byte KEY of the source (a column of 1 B per slot: the whole source type or
+// half of it fits the L2 set-aside where the 8 B states need eleven blocks).  Entries whose key may_accept() are queued in entry order
+// (ballot compaction; a shared counter per row); a flush fetches the exact states of the queue edge-parallel and every lane folds
+// the segment of its own row in entry order.  Everything else (parked accumulators, row lists, look-ahead prefetch, finish and the
+// write rules) is as in the unfiltered sweep.  Shape from profiles/microbench/prefilter.cu: chunk 64, 8 resident CTAs per SM.
+namespace blk {
+__device__ __forceinline__ uint32_t ld_key(const uint8_t* p, uint64_t pol) {
+    uint32_t r; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol)); return r;
+}
+}  // namespace blk
+template <class F> struct PrefilterStage {
+    static constexpr int CHK = 64, QCAP = CHK + 32;
+    uint32_t off[33];                   // entry positions of the warp's 32 rows (+ end)
+    uint32_t qcnt[32];                  // queued entries per row
+    typename F::Probe probe[32];
+    uint32_t qidx[QCAP];                // queued source slots, in entry order
+    typename F::Source qval[QCAP];      // their exact states
+};
+template <class F, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(256, 8) reduce_prefilter_kernel(const __grid_constant__ KernelArgs ka) {
+    typedef BlockedCfg<F> C;
+    typedef typename C::State State;
+    typedef typename C::Source Source;
+    typedef typename C::Acc Acc;
+    typedef PrefilterStage<F> Stage;
+    constexpr int CHK = Stage::CHK, QCAP = Stage::QCAP, U = CHK / 32;
+    __shared__ Stage stages[8];
+    const LaunchArgs& la = ka.la;
+    const DeviceSim& ds = ka.ds;
+    const uint32_t lane = threadIdx.x & 31;
+    Stage& sm = stages[threadIdx.x >> 5];
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool listed = !FIRST && !LAST && la.blk_rows != nullptr;
+    const uint32_t nwork = listed ? la.blk_nrows : la.n;
+    const uint32_t idx = listed ? (gtid < nwork ? __ldcs(la.blk_rows + gtid) : la.n) : (uint32_t)gtid;
+    const AgentView& av = ds.agents[la.type];
+    const AgentView& sv = ds.agents[F::kSourceType];
+    const uint8_t* __restrict__ src_st = sv.state_r;
+    const uint32_t src_cap = sv.cap;
+    const uint32_t* __restrict__ gsrc = la.blk_src;
+    const uint8_t* __restrict__ keys = la.blk_key;
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    // look-ahead prefetch of the streams of the CTA one residency wave later (see reduce_blocked_kernel)
+    const uint32_t pc = blockIdx.x + la.blk_ahead;
+    uint32_t pa = 0, pb = 0;
+    const bool ahead = la.blk_ahead && pc < gridDim.x;
+    if (ahead && threadIdx.x < 64) {
+        const uint32_t r0 = pc * 256u, nr = nwork - r0 < 256u ? nwork - r0 : 256u;
+        const uint32_t* __restrict__ offs = listed ? la.blk_roff : la.blk_off;
+        if (threadIdx.x == 0) { pa = __ldg(offs + r0); pb = __ldg(offs + r0 + nr); }
+        blk::prefetch_l2(offs + r0, (size_t)(nr + 1) * 4, threadIdx.x, 64);
+        if (listed) blk::prefetch_l2(la.blk_rows + r0, (size_t)nr * 4, threadIdx.x, 64);
+        else {
+            constexpr int SW = SoaWord<sizeof(State)>::value, SC = sizeof(State) / SW;
+#pragma unroll
+            for (int c = 0; c < SC; ++c) blk::prefetch_l2(av.state_r + ((size_t)c * av.cap + r0) * SW, (size_t)nr * SW, threadIdx.x, 64);
+            if (!FIRST) {
+#pragma unroll
+                for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, threadIdx.x, 64);
+#pragma unroll
+                for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, threadIdx.x, 64);
+            }
+        }
+    }
+    uint32_t lo, hi;
+    if (listed) {
+        const uint32_t i = gtid < nwork ? (uint32_t)gtid : nwork;
+        lo = __ldcs(la.blk_roff + i); hi = gtid < nwork ? __ldcs(la.blk_roff + i + 1) : lo;
+    } else {
+        const uint32_t row = gtid < nwork ? idx : la.n;
+        lo = __ldcs(la.blk_off + row); hi = gtid < nwork ? __ldcs(la.blk_off + row + 1) : lo;
+    }
+    const bool act = gtid < nwork && !(av.died_r && av.died_r[idx]);       // jump over died agents (AgentMethods.jl:199-203)
+    const F f{};
+    Ctx<F, MODE_DIRECT, 1> ctx(ds, la, idx, 0);
+    State self;
+    Acc acc;
+    if (act) {
+        self = blk::soa_load_cs<State>(av.state_r, av.cap, idx);
+        if (FIRST) f.init(ctx, self, acc); else C::acc_load(la.blk_acc, la.blk_stride, idx, acc);
+        sm.probe[lane] = f.probe(ctx, self);
+    } else {
+        memset(&self, 0, sizeof(State));
+        memset(&acc, 0, sizeof(Acc));
+    }
+    sm.off[lane] = lo;
+    if (lane == 31) sm.off[32] = hi;
+    sm.qcnt[lane] = 0;
+    const uint32_t alive = __ballot_sync(0xffffffffu, act);               // entries of died rows are never queued
+    __syncwarp();
+    const uint32_t e0 = sm.off[0], e1 = sm.off[32];
+    const uint32_t len = hi - lo;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t qn = 0;
+    for (uint32_t base = e0; base < e1; base += CHK) {
+        uint32_t six[U], ks[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const uint32_t x = base + lane + 32 * u; six[u] = x < e1 ? __ldcs(gsrc + x) : 0u; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const uint32_t x = base + lane + 32 * u; ks[u] = x < e1 ? blk::ld_key(keys + six[u], pol) : 0u; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t x = base + lane + 32 * u;
+            uint32_t r = 0;                                                // the row that owns entry x: the last one starting at or before it
+#pragma unroll
+            for (int st = 16; st; st >>= 1) if (sm.off[r + st] <= x) r += st;
+            const bool pass = x < e1 && ((alive >> r) & 1u) && f.may_accept(sm.probe[r], ks[u]);
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (pass) { sm.qidx[qn + __popc(m & lt)] = six[u]; atomicAdd(&sm.qcnt[r], 1u); }
+            qn += __popc(m);
+        }
+        __syncwarp();
+        if (qn > (uint32_t)(QCAP - CHK) || base + CHK >= e1) {             // flush: exact states edge-parallel, then the per-row folds
+            for (uint32_t i = lane; i < qn; i += 32) sm.qval[i] = soa_gather<Source>(src_st, src_cap, sm.qidx[i]);
+            __syncwarp();
+            const uint32_t mine = sm.qcnt[lane];
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+            const uint32_t start = incl - mine;
+            for (uint32_t j = 0; j < mine; ++j) f.fold(ctx, self, sm.qval[start + j], acc);
+            sm.qcnt[lane] = 0; qn = 0;
+            __syncwarp();
+        }
+    }
+    if (threadIdx.x < 32 && ahead) {
+        pa = __shfl_sync(0xffffffffu, pa, 0); pb = __shfl_sync(0xffffffffu, pb, 0);
+        blk::prefetch_l2(gsrc + pa, (size_t)(pb - pa) * 4, lane, 32);
+    }
+    {
+        const unsigned total = __reduce_add_sync(0xffffffffu, act ? len : 0u);
+        if (lane == 0 && total) atomicAdd(la.stats + ((blockIdx.x & 1023u) << 2), (unsigned long long)total);
+    }
+    if (!act) return;
+    if (!LAST) C::acc_store(la.blk_acc, la.blk_stride, idx, acc);
+    else if (!(la.blk_heavy && ((la.blk_heavy[idx >> 5] >> (idx & 31)) & 1u))) {   // heavy rows: done by the block-per-agent pass
+        const AgentID id = agent_id((uint32_t)la.type, ds.rank, (uint64_t)idx + 1);
+        const bool alive_after = f.finish(ctx, self, id, acc);
+        if (la.in_write) {                                                 // transition_with_write! (AgentMethods.jl:159-181)
+            if (alive_after) { if (av.size) soa_store<State>(av.independent ? av.state_r : av.state_w, av.cap, idx, self); }
+            else if (av.immortal) atomicOr(ds.error, (uint32_t)DERR_IMMORTAL_DIED);
+            else av.died_w[idx] = 1;
+        }
+    }
+}
+// key column of the source type: four slots per thread, one packed store
+template <class F>
+__global__ void __launch_bounds__(256) build_keys_kernel(const __grid_constant__ KernelArgs ka) {
+    typedef typename F::Source Source;
+    const LaunchArgs& la = ka.la;
+    const DeviceSim& ds = ka.ds;
+    const AgentView& sv = ds.agents[F::kSourceType];
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= la.blk_nkeys) return;
+    const F f{};
+    Ctx<F, MODE_DIRECT, 1> ctx(ds, la, (uint32_t)i0, 0);
+    if (i0 + 3 < la.blk_nkeys) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) packed |= (uint32_t)f.key(ctx, soa_load<Source>(sv.state_r, sv.cap, (uint32_t)i0 + j)) << (8 * j);
+        *reinterpret_cast<uint32_t*>(la.blk_key + i0) = packed;
+    } else
+        for (uint64_t i = i0; i < la.blk_nkeys; ++i) la.blk_key[i] = f.key(ctx, soa_load<Source>(sv.state_r, sv.cap, (uint32_t)i));
+}
+template <class F>
+cudaError_t launch_keys(const LaunchArgs& la) {
+    static thread_local KernelArgs ka;
+    ka.la = la;
+    ka.ds = *la.ds;
+    ka.la.ds = nullptr;
+    if (la.blk_nkeys == 0) return cudaSuccess;
+    build_keys_kernel<F><<<(unsigned)(((unsigned long long)la.blk_nkeys + 1023) / 1024), 256, 0, la.stream>>>(ka);
+    return cudaGetLastError();
+}
+
 // ---- reduce transition over an implicit raster stencil (KIND_STENCIL): the grid-stencil kernel -----------------------------------
 // A thread per cell.  The generic accessor path enumerates a row in the reference's insertion order (sorted keys for border cells,
 // strided shares for lane groups); a reduce transition does not depend on the order, so this kernel only decodes the position,
@@ -1168,6 +1351,26 @@ cudaError_t launch_blocked(const LaunchArgs& la) {
         if (getenv("VB_BLOCK_AHEAD")) wave = atoi(getenv("VB_BLOCK_AHEAD"));
     }
     ka.la.blk_ahead = (uint32_t)wave;
+    if constexpr (F::kPrefilter) {
+        if (la.blk_prefilter) {
+            if (!la.blk_key) return cudaErrorInvalidValue;
+            static int pwave = 0;
+            if (!pwave) {
+                int dev = 0, sms = 148, per_sm = 8;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_prefilter_kernel<F, false, false>, 256, 0);
+                pwave = sms * (per_sm > 0 ? per_sm : 1);
+                if (getenv("VB_BLOCK_AHEAD")) pwave = atoi(getenv("VB_BLOCK_AHEAD"));
+            }
+            ka.la.blk_ahead = (uint32_t)pwave;
+            if (la.blk_first && la.blk_last) reduce_prefilter_kernel<F, true, true><<<grid, 256, 0, la.stream>>>(ka);   // all keys in one block
+            else if (la.blk_first) reduce_prefilter_kernel<F, true, false><<<grid, 256, 0, la.stream>>>(ka);
+            else if (la.blk_last) reduce_prefilter_kernel<F, false, true><<<grid, 256, 0, la.stream>>>(ka);
+            else reduce_prefilter_kernel<F, false, false><<<grid, 256, 0, la.stream>>>(ka);
+            return cudaGetLastError();
+        }
+    }
     if (la.blk_first && la.blk_last) return cudaErrorInvalidValue;      // a single block is the direct path's job
     if (la.blk_first) reduce_blocked_kernel<F, true, false><<<grid, 256, 0, la.stream>>>(ka);
     else if (la.blk_last) reduce_blocked_kernel<F, false, true><<<grid, 256, 0, la.stream>>>(ka);
@@ -1198,6 +1401,10 @@ TransitionInfo make_transition_info(const char* name, const char* agent_type) {
         // the source-blocked sweeps park states / accumulators as 4- and 8-byte words
         if constexpr (sizeof(typename F::State) % 4 == 0 && sizeof(typename F::Acc) % 4 == 0 && F::kAccBytes % 4 == 0) ti.launch_blocked = &launch_blocked<F>;
         ti.launch_stencil = &launch_stencil<F>;
+        if constexpr (F::kPrefilter) {
+            static_assert(sizeof(typename F::Probe) % 4 == 0, "Probe: a multiple of 4 bytes");
+            if (ti.launch_blocked) { ti.prefilter = 1; ti.launch_keys = &launch_keys<F>; }
+        }
     }
     return ti;
 }

@@ -152,9 +152,21 @@ struct TransitionBase {
 //     };
 //
 // The oracle folds the row strictly left to right (one lane); the GPU paths combine partial accumulators with merge().
+//
+// Optional *prefilter* (kPrefilter = true) for selective folds — folds that leave the accumulator untouched for most neighbours,
+// like the bounded-confidence test of hegselmann.jl:139.  The functor names a one-byte key of a neighbour's state; the engine keeps
+// the keys of the source type in a column of their own (1 B per slot: L2-sized where the 8 B states are not), gathers the key of
+// every entry and fetches the full state only where may_accept() says the fold could change the accumulator:
+//         using Probe = ...;                                                              // what a row needs to judge a key (small, trivially copyable)
+//         template <class Ctx> VB_HD uint8_t key(const Ctx&, const Source& nb) const;
+//         template <class Ctx> VB_HD Probe probe(const Ctx&, const State& self) const;    // once per row
+//         VB_HD bool may_accept(const Probe&, uint32_t key) const;
+// Contract: may_accept(probe(self), key(nb)) == false  ==>  fold(self, nb, a) leaves a unchanged.  The decision itself is always
+// taken by fold() on the exact state, so results do not depend on the prefilter (tests/test_hk.py pins that, CPU and GPU).
 template <class D> struct ReduceTransition : TransitionBase {
     static constexpr bool kCooperative = true;
     static constexpr bool kReduce = true;
+    static constexpr bool kPrefilter = false;
     template <class Ctx, class S> VB_HD bool operator()(Ctx& ctx, S& self, AgentID id) const {
         const D& d = static_cast<const D&>(*this);
         typename D::Acc a;

@@ -116,24 +116,91 @@ def test_powerlaw_device_generator_matches_host_and_oracle(oracle, cuda):
     assert abs(g.mapreduce("opinion", "+", "HKAgent") - o.mapreduce("opinion", "+", "HKAgent")) < 1e-12 * n
 
 
+def test_hk_prefilter_contract_on_cpu(oracle):
+    """may_accept(probe(self), key(nb)) must hold whenever fold() accepts nb (include/vahana_model.h): random pairs, pairs at the
+    edge of the band, values on key boundaries, outside [0, 1], infinities and NaN; and the key must actually be selective."""
+    import ctypes as C
+    f = oracle.lib.vbt_hk_prefilter_violations
+    f.restype = C.c_uint64
+    rng = np.random.default_rng(3)
+    for eps in [0.0, 1e-9, 0.003, 1 / 256, 0.02, 0.25, 0.999, 1.0, 7.5, float("inf"), float("nan"), -0.1]:
+        m = 200000
+        a = rng.random(m)
+        b = rng.random(m)
+        if np.isfinite(eps) and eps > 0:
+            b[: m // 2] = a[: m // 2] + rng.choice([-1.0, 1.0], m // 2) * eps * (1 - rng.random(m // 2) * 1e-9)     # just inside the band
+            b[m // 4: m // 2] = np.nextafter(a[m // 4: m // 2] + eps, -np.inf)
+        g = rng.integers(-300, 600, m // 10) / 256.0                                   # key boundaries, beyond the clamp on both sides
+        a[-len(g):] = g
+        b[-len(g):] = g + rng.choice([-1.0, 0.0, 1.0], len(g)) * (eps if np.isfinite(eps) else 1.0) * 0.999999
+        special = np.array([0.0, -0.0, 1.0, 255 / 256, 1 - 2.0 ** -53, 2.0, -3.0, np.inf, -np.inf, np.nan, 1e300, -1e300, 5e-324])
+        a = np.concatenate([a, np.repeat(special, len(special))])
+        b = np.concatenate([b, np.tile(special, len(special))])
+        acc, kept = C.c_uint64(), C.c_uint64()
+        bad = f(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_uint64(len(a)), C.c_double(eps), C.byref(acc), C.byref(kept))
+        assert bad == 0, (eps, bad)
+        if eps == 0.02:
+            assert acc.value > 0
+    a = rng.random(1000000)
+    b = rng.random(1000000)
+    acc, kept = C.c_uint64(), C.c_uint64()
+    assert f(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_uint64(len(a)), C.c_double(0.02), C.byref(acc), C.byref(kept)) == 0
+    assert 0.035 < acc.value / len(a) < 0.045 and kept.value / len(a) < 0.055          # 4 % accepted, 5 % of the states fetched
+
+
 # ---- source-blocked read phase (vb::ReduceTransition, DESIGN.md §3) -------------------------------------------------------
 # The sweep per source block adds the blocks' partial sums in block order instead of row order: same tolerance as above.
+# With the prefilter (hk::Step names a one-byte key of the opinion, include/vahana_model.h) the sweeps gather keys and the blocks are
+# sized in key bytes (52 M slots for the default 75 MB): fewer sweeps, the same results.
+KEY_SLOTS_PER_MB = 52e6 / 75.0
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,m,block_mb", [(300, 3, 0.0005), (20000, 8, 0.02), (20000, 8, 0.081), (50001, 5, 0.05)])
-def test_hk_blocked_read_phase_vs_oracle(oracle, cuda, n, m, block_mb):
+@pytest.mark.parametrize("prefilter", [0, 1])
+@pytest.mark.parametrize("n,m,block_mb", [(300, 3, 0.0005), (20000, 8, 0.02), (20000, 8, 0.081), (50001, 5, 0.05), (20000, 8, 0.003)])
+def test_hk_blocked_read_phase_vs_oracle(oracle, cuda, n, m, block_mb, prefilter):
     uv = ba_graph(n, m, 1)
     op0 = np.random.default_rng(1).random(n)
     g, _ = hk_sim(cuda, n, uv, op0)
     o, _ = hk_sim(oracle, n, uv, op0)
     g.set_read_blocking(block_mb, 0.0, 1)              # tiny blocks, no size threshold, build at first sight
-    min_nb = min(int(np.ceil(n * 8 / (block_mb * 1e6))), 64)      # blocks cover the type's capacity (>= n slots)
+    g.set_read_prefilter(prefilter)
+    if prefilter:
+        min_nb = min(int(np.ceil(n / (block_mb * KEY_SLOTS_PER_MB))), 64)
+    else:
+        min_nb = min(int(np.ceil(n * 8 / (block_mb * 1e6))), 64)      # blocks cover the type's capacity (>= n slots)
+        assert min_nb >= 2
     for step in range(4):
         g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
         o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
         st = g.last_apply_stats()
-        assert 2 <= min_nb <= st["source_blocks"] <= 64, st
+        assert 1 <= min_nb <= st["source_blocks"] <= 64, st
+        assert st["prefiltered"] == bool(prefilter)
         assert st["edges_read"] == 2 * len(uv) + n
         np.testing.assert_allclose(_opinions(g), _opinions(o), rtol=RTOL, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("eps", [0.0, 0.003, 0.25, 0.7, 2.0])
+def test_hk_prefilter_band_edges_vs_oracle(oracle, cuda, eps):
+    """Acceptance band against the key grid: eps below one key step, eps wider than the clamp, opinions on key boundaries and at
+    the ends of [0, 1] — the prefilter may never drop a neighbour the exact test accepts (counts are part of the mean)."""
+    n = 4096
+    uv = ba_graph(n, 6, 5)
+    rng = np.random.default_rng(11)
+    op0 = rng.integers(0, 257, n) / 256.0                      # exactly on the key grid, 0.0 and 1.0 included
+    sel = np.arange(n) % 3 == 0                                # a third: just inside the acceptance band of a grid value
+    op0[sel] = np.clip(op0[sel] + rng.choice([-1.0, 1.0], int(sel.sum())) * eps * (1 - 2.0 ** -30), 0.0, 1.0)
+    op0[5::97] = rng.random(len(op0[5::97]))
+    g, _ = hk_sim(cuda, n, uv, op0, eps)
+    o, _ = hk_sim(oracle, n, uv, op0, eps)
+    g.set_read_blocking(0.004, 0.0, 1)
+    g.set_read_prefilter(1)
+    for step in range(3):
+        g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        assert g.last_apply_stats()["prefiltered"]
+        np.testing.assert_allclose(_opinions(g), _opinions(o), rtol=RTOL, atol=0, equal_nan=True)
 
 
 @pytest.mark.gpu
@@ -144,23 +211,27 @@ def test_hk_blocked_matches_direct_on_hub_graph(oracle, cuda):
     from models import hk_model
     n = 200000
     sims = []
-    for blocked in (False, True):
+    for blocked, prefilter in ((False, 0), (True, 0), (True, 1)):
         g = vh.create_simulation(hk_model(), backend=cuda)
         ne = C.c_uint64()
         cuda.check(cuda.lib.vbw_hk_powerlaw_build(g.h, 1, 0, C.c_uint64(n), C.c_uint64(4), C.c_uint64(5), C.c_double(6.8333), C.c_uint32(1000000),
                                                   C.c_uint64(30000), C.byref(ne)))
         g.finish_init()
         g.set_read_blocking(0.2 if blocked else 0.0, 0.0, 0)
+        g.set_read_prefilter(prefilter)
         sims.append(g)
-    d, b = sims
+    d, b, p = sims
     for step in range(4):
-        d.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-        b.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        for g in sims:
+            g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
         assert d.last_apply_stats()["source_blocks"] == 0
         nb = b.last_apply_stats()["source_blocks"]
         assert nb == (0 if step == 0 else 8), nb           # first apply: direct (the container has not been seen twice yet)
-        assert b.last_apply_stats()["edges_read"] == d.last_apply_stats()["edges_read"] == ne.value
+        sp = p.last_apply_stats()
+        assert sp["source_blocks"] == (0 if step == 0 else 2) and sp["prefiltered"] == (step > 0), sp     # 200000 slots / 138666 keys per block
+        assert b.last_apply_stats()["edges_read"] == d.last_apply_stats()["edges_read"] == sp["edges_read"] == ne.value
         np.testing.assert_allclose(_opinions(b), _opinions(d), rtol=RTOL, atol=0)
+        np.testing.assert_allclose(_opinions(p), _opinions(d), rtol=RTOL, atol=0)
 
 
 @pytest.mark.gpu
@@ -191,7 +262,7 @@ def test_hk_full_size_blocked_vs_direct_properties(cuda):
         d.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
         b.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
         sd, sb = d.last_apply_stats(), b.last_apply_stats()
-        assert sd["source_blocks"] == 0 and sb["source_blocks"] >= 8
+        assert sd["source_blocks"] == 0 and sb["source_blocks"] >= 2 and sb["prefiltered"]     # 1e8 slots = two blocks of keys
         assert sd["edges_read"] == sb["edges_read"] == ne.value
         od, ob = _opinions(d), _opinions(b)
         np.testing.assert_allclose(ob, od, rtol=RTOL, atol=0)
@@ -202,8 +273,8 @@ def test_hk_full_size_blocked_vs_direct_properties(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("blocked", [False, True])
-def test_hk_mortal_agents_blocked_vs_oracle(oracle, cuda, blocked):
+@pytest.mark.parametrize("blocked,prefilter", [(False, 0), (True, 0), (True, 1)])
+def test_hk_mortal_agents_blocked_vs_oracle(oracle, cuda, blocked, prefilter):
     """Deaths next to the sweeps: agents die (`finish` returns false), their edges are purged, the container changes and the
     blocked view is rebuilt; died rows are skipped by every later sweep.  Ids, survivors and CSR bit-exact, opinions within RTOL."""
     n, m, eps = 6000, 6, 0.02
@@ -212,11 +283,13 @@ def test_hk_mortal_agents_blocked_vs_oracle(oracle, cuda, blocked):
     g, _ = hk_sim(cuda, n, uv, op0, eps)
     o, _ = hk_sim(oracle, n, uv, op0, eps)
     g.set_read_blocking(0.004 if blocked else 0.0, 0.0, 1)
+    g.set_read_prefilter(prefilter)
     for step in range(5):
         name = "hk_step_or_die" if step % 2 == 0 else "hk_step"
         g.apply(name, "HKAgent", ["HKAgent", "Knows"], "HKAgent")
         o.apply(name, "HKAgent", ["HKAgent", "Knows"], "HKAgent")
         assert (g.last_apply_stats()["source_blocks"] >= 2) == blocked
+        assert g.last_apply_stats()["prefiltered"] == bool(prefilter)
         assert g.num_agents("HKAgent") == o.num_agents("HKAgent")
         assert np.array_equal(g.all_agentids("HKAgent"), o.all_agentids("HKAgent"))
         assert g.num_edges("Knows") == o.num_edges("Knows")

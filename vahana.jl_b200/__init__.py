@@ -104,7 +104,7 @@ ABI_SYMBOLS = [
     "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce",
     "vb_rastervalues", "vb_calc_raster_num_edges", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
     "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes", "vb_set_uniform_offset", "vb_add_agent_per_process",
-    "vb_last_apply_blocks", "vb_set_read_blocking",
+    "vb_last_apply_blocks", "vb_set_read_blocking", "vb_set_read_prefilter", "vb_last_apply_prefiltered",
 ]
 
 
@@ -564,6 +564,10 @@ class Simulation:
         """Policy of the source-blocked read phase (engine-specific tuning knob, no reference counterpart)."""
         self._ck(self.lib.vb_set_read_blocking(self.h, C.c_double(block_mb), C.c_double(min_mb), C.c_int(eager)))
 
+    def set_read_prefilter(self, on: int = -1) -> None:
+        """Prefiltered sweeps of reduce transitions with a key (engine-specific knob; results do not depend on it)."""
+        self._ck(self.lib.vb_set_read_prefilter(self.h, C.c_int(on)))
+
     def last_apply_stats(self) -> dict:
         a, b = C.c_double(), C.c_double()
         er, ea, ac, kl = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -572,8 +576,11 @@ class Simulation:
         self._ck(self.lib.vb_last_kernel_ms(self.h, C.byref(k)))
         nb = C.c_uint32()
         self._ck(self.lib.vb_last_apply_blocks(self.h, C.byref(nb)))
+        pf = C.c_int()
+        self._ck(self.lib.vb_last_apply_prefiltered(self.h, C.byref(pf)))
         return {"ms_read_write": a.value, "ms_finish": b.value, "ms_kernel": k.value, "edges_read": er.value,
-                "edges_appended": ea.value, "agents_called": ac.value, "kernel_launches": kl.value, "source_blocks": nb.value}
+                "edges_appended": ea.value, "agents_called": ac.value, "kernel_launches": kl.value, "source_blocks": nb.value,
+                "prefiltered": bool(pf.value)}
 
     # -- agent queries --
     def num_agents(self, type_name: str) -> int:

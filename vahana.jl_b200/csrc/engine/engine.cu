@@ -804,6 +804,7 @@ struct EdgeStore {
     // source type's slots an offset array boff + b * rpad ([n + 1] positions into bsrc) and the rows' sources inside that block
     struct Blocked {
         uint32_t* boff = nullptr; uint32_t* bsrc = nullptr; uint32_t* heavy_bits = nullptr; uint8_t* acc = nullptr;
+        uint8_t* key = nullptr; uint32_t key_n = 0;   // prefiltered sweeps: one key byte per slot of the source type (rebuilt by every apply)
         uint32_t nb = 0, bsize = 0, rpad = 0, n = 0, acc_bytes = 0, heavy_min = 0;
         std::vector<uint32_t> bstart;                 // position in bsrc where each block's entries start (nb + 1 values)
         std::vector<uint32_t*> arows;                 // per block: ascending list of the rows that own an entry in it
@@ -867,7 +868,10 @@ struct vb_sim {
     bool refresh_peer_map(int t);
     uint64_t halo_bytes = 0;   // bytes received by the last apply's halo exchanges
     double blk_block_mb = -1, blk_min_mb = -1; int blk_eager = -1;   // vb_set_read_blocking (negative = environment / default)
+    int blk_prefilter = -1;                                          // vb_set_read_prefilter (negative = environment / default)
+    bool prefilter_on(const vb::TransitionInfo* ti) const;
     uint32_t last_blocked_nb = 0;   // source blocks swept by the last apply's read phase (0 = direct path)
+    bool last_prefiltered = false;  // those sweeps gathered keys (prefilter) instead of states
     uint64_t layout_epoch = 0; // bumped whenever stored composite indices are renumbered (rebase): invalidates blocked views
     bool ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min);
     void rebase(const uint32_t* old_base, const uint32_t* old_lcap = nullptr, const uint32_t* const* remap = nullptr);
@@ -902,7 +906,7 @@ void free_agent(AgentStore& a) {
 void free_blocked(EdgeStore& e) {
     for (auto p : e.blk.arows) dfree(p);
     for (auto p : e.blk.aoff) dfree(p);
-    dfree(e.blk.boff); dfree(e.blk.bsrc); dfree(e.blk.heavy_bits); dfree(e.blk.acc);
+    dfree(e.blk.boff); dfree(e.blk.bsrc); dfree(e.blk.heavy_bits); dfree(e.blk.acc); dfree(e.blk.key);
     e.blk = EdgeStore::Blocked{};
 }
 void free_edge_read(EdgeStore& e) {
@@ -1731,7 +1735,16 @@ void vb_sim::transmit_edges(int ei) {
 // the same container has been seen by two applies (a network rebuilt every step never amortises the build).
 // VB_BLOCK=0 disables, VB_BLOCK_MB sets the block size (default 75 MB of source states), VB_BLOCK_MIN_MB the activation threshold
 // (default 192 MB), VB_BLOCK_EAGER=1 builds at first sight (tests).
+// Prefiltered sweeps (functors with kPrefilter, include/vahana_model.h) gather one key byte per entry instead of the state, so their
+// blocks are sized in key bytes: VB_KEY_BLOCK_MB (default 52 MB of keys = 52 M slots; profiles/r1_prefilter: 50 MB of keys hold the
+// L2 gather rate, 100 MB do not).  VB_PREFILTER=0 / vb_set_read_prefilter(sim, 0) keeps the unfiltered sweeps.
+bool vb_sim::prefilter_on(const vb::TransitionInfo* ti) const {
+    static const bool env_on = !(getenv("VB_PREFILTER") && atoi(getenv("VB_PREFILTER")) == 0);
+    return ti->prefilter && ti->launch_keys && (blk_prefilter >= 0 ? blk_prefilter != 0 : env_on);
+}
 bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min) {
+    static const double env_key_block_mb = getenv("VB_KEY_BLOCK_MB") ? atof(getenv("VB_KEY_BLOCK_MB")) : 52.0;
+    const bool pf = prefilter_on(ti);
     static const bool enabled = !(getenv("VB_BLOCK") && atoi(getenv("VB_BLOCK")) == 0);
     static const double env_block_mb = getenv("VB_BLOCK_MB") ? atof(getenv("VB_BLOCK_MB")) : 75.0;
     static const double env_min_mb = getenv("VB_BLOCK_MIN_MB") ? atof(getenv("VB_BLOCK_MIN_MB")) : 192.0;
@@ -1752,10 +1765,19 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
     uint32_t bsize = (uint32_t)std::max<double>(1.0, block_mb * 1e6 / src.size);
     uint32_t nb = (nsl + bsize - 1) / bsize;
     if (nb > 64) { bsize = (nsl + 63) / 64; nb = (nsl + bsize - 1) / bsize; }
-    if (nb < 2) return false;
+    if (nb < 2 && !pf) return false;
+    if (pf) {     // blocks of keys: as few and as even as the key budget allows (an explicit vb_set_read_blocking size scales 1 : sizeof(state))
+        const double key_slots = std::max(1.0, (blk_block_mb > 0 ? block_mb / 75.0 : 1.0) * env_key_block_mb * 1e6);
+        const uint32_t used = src.nghost ? nsl : std::max<uint32_t>(1u, std::min<uint32_t>(nsl, src.nslots));   // capacity beyond the slots in use holds no source
+        nb = (uint32_t)std::max<double>(1.0, std::ceil((double)used / key_slots));
+        if (nb > 64) nb = 64;
+        bsize = (used + nb - 1) / nb;
+        nb = (nsl + bsize - 1) / bsize;                // blocks still cover the capacity; the ones past `used` stay empty and are skipped
+        if (nb > 64) { bsize = (nsl + 63) / 64; nb = (nsl + bsize - 1) / bsize; }
+    }
     EdgeStore::Blocked& k = pe.blk;
     if (k.boff && k.version == pe.version && k.epoch == layout_epoch && k.called == C && k.source == ti->source_type && k.n == n &&
-        k.acc_bytes == ti->acc_bytes && k.bsize == bsize && k.heavy_min == heavy_min)
+        k.acc_bytes == ti->acc_bytes && k.bsize == bsize && k.heavy_min == heavy_min && (k.key != nullptr) == pf)
         return true;
     if (k.seen_version != pe.version) { k.seen_version = pe.version; k.seen = 1; k.refused = false; }
     else if (k.seen < 0xffffffffu) ++k.seen;
@@ -1793,6 +1815,7 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
         k.heavy_bits = dalloc<uint32_t>(((uint64_t)n + 31) / 32 + 1);
         blk_heavy_bits_kernel<<<nblk(n), 256, 0, g_stream>>>(pe.off, ba.row0, n, pe.rows, heavy_min, k.heavy_bits); LAUNCH_CHECK();
         k.acc = (uint8_t*)g_pool.alloc((size_t)rpad * ti->acc_bytes);
+        if (pf) { k.key_n = nsl; k.key = dalloc<uint8_t>((uint64_t)nsl + 64); }
         CK(cudaStreamSynchronize(g_stream));
         // per block the list of rows that own an entry in it: the middle sweeps visit only those
         k.arows.assign(nb, nullptr); k.aoff.assign(nb, nullptr); k.acount.assign(nb, 0);
@@ -2289,11 +2312,14 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 CK(cudaEventRecord(s.evk[0], g_stream));
                 vb::LaunchArgs lb = la;
                 lb.blk_src = k.bsrc; lb.blk_acc = k.acc; lb.blk_stride = k.rpad; lb.blk_heavy = heavy_n ? k.heavy_bits : nullptr;
+                const bool pf = k.key != nullptr && s.prefilter_on(ti);
+                lb.blk_key = pf ? k.key : nullptr; lb.blk_nkeys = pf ? k.key_n : 0; lb.blk_prefilter = pf ? 1 : 0;
+                if (pf) { CK(ti->launch_keys(lb)); ++g_launches; }          // keys of this step's read states (inside the timed region)
                 // sweeps over blocks that hold no entry (capacity beyond the agents in use) are skipped; the first sweep that runs
                 // initialises the accumulators, the last one runs finish()
                 std::vector<uint32_t> todo;
                 for (uint32_t b = 0; b < k.nb; ++b) if (k.bstart[b + 1] > k.bstart[b]) todo.push_back(b);
-                while (todo.size() < 2) { uint32_t b = 0; while (std::find(todo.begin(), todo.end(), b) != todo.end()) ++b; todo.push_back(b); std::sort(todo.begin(), todo.end()); }
+                while (todo.size() < (pf ? 1u : 2u)) { uint32_t b = 0; while (std::find(todo.begin(), todo.end(), b) != todo.end()) ++b; todo.push_back(b); std::sort(todo.begin(), todo.end()); }
                 // the hub rows left to the block-per-agent pass (a handful of CTAs with long dependent chains) run beside the sweeps
                 // on a second stream: they read the same read buffer and write rows the last sweep skips
                 static cudaStream_t side = nullptr;
@@ -2318,9 +2344,9 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 CK(cudaStreamSynchronize(g_stream));
                 cudaCtxResetPersistingL2Cache();
                 cudaGetLastError();
-                s.last_blocked_nb = swept;
+                s.last_blocked_nb = swept; s.last_prefiltered = pf;
             } else {
-            s.last_blocked_nb = 0;
+            s.last_blocked_nb = 0; s.last_prefiltered = false;
             s.upload_view(seed);
             // Gather-bound read phases (state array far larger than L2): keep the head of the gathered type's state resident in
             // L2 for the duration of the launch.  Power-law / preferential-attachment graphs number their hubs first, so the head
@@ -3413,6 +3439,8 @@ int vb_last_apply_stats(vb_sim* s, double* ms_rw, double* ms_fin, uint64_t* er, 
     return VB_OK;
 }
 int vb_last_kernel_ms(vb_sim* s, double* ms) { *ms = s->ms_kernel; return VB_OK; }
+int vb_set_read_prefilter(vb_sim* s, int on) { if (!s) return VB_ERR_ARG; s->blk_prefilter = on; return VB_OK; }
+int vb_last_apply_prefiltered(vb_sim* s, int* on) { if (on) *on = s->last_prefiltered ? 1 : 0; return VB_OK; }
 int vb_set_read_blocking(vb_sim* s, double block_mb, double min_mb, int eager) {
     s->blk_block_mb = block_mb; s->blk_min_mb = min_mb; s->blk_eager = eager;
     return VB_OK;
