@@ -1083,15 +1083,18 @@ template <class F> struct PrefilterStage {
     uint32_t qidx[QCAP];                // queued source slots, in entry order
     typename F::Source qval[QCAP];      // their exact states
 };
-template <class F, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(256, 8) reduce_prefilter_kernel(const __grid_constant__ KernelArgs ka) {
+// WPC = warps per CTA.  A CTA lives as long as its slowest warp, and a warp that meets a long power-law row is slow: small CTAs leave
+// fewer warps idle (profiles/r1_prefilter/prefilter_shapes2.txt: 11.65 / 10.86 / 10.59 ms with 8 / 4 / 2 warps per CTA).
+template <class F, bool FIRST, bool LAST, int WPC>
+__global__ void __launch_bounds__(32 * WPC, 64 / WPC) reduce_prefilter_kernel(const __grid_constant__ KernelArgs ka) {
+    constexpr uint32_t TPB = 32 * WPC, PFT = TPB < 64 ? TPB : 64;   // rows per CTA; threads that issue the look-ahead prefetches
     typedef BlockedCfg<F> C;
     typedef typename C::State State;
     typedef typename C::Source Source;
     typedef typename C::Acc Acc;
     typedef PrefilterStage<F> Stage;
     constexpr int CHK = Stage::CHK, QCAP = Stage::QCAP, U = CHK / 32;
-    __shared__ Stage stages[8];
+    __shared__ Stage stages[WPC];
     const LaunchArgs& la = ka.la;
     const DeviceSim& ds = ka.ds;
     const uint32_t lane = threadIdx.x & 31;
@@ -1112,21 +1115,21 @@ __global__ void __launch_bounds__(256, 8) reduce_prefilter_kernel(const __grid_c
     const uint32_t pc = blockIdx.x + la.blk_ahead;
     uint32_t pa = 0, pb = 0;
     const bool ahead = la.blk_ahead && pc < gridDim.x;
-    if (ahead && threadIdx.x < 64) {
-        const uint32_t r0 = pc * 256u, nr = nwork - r0 < 256u ? nwork - r0 : 256u;
+    if (ahead && threadIdx.x < PFT) {
+        const uint32_t r0 = pc * TPB, nr = nwork - r0 < TPB ? nwork - r0 : TPB;
         const uint32_t* __restrict__ offs = listed ? la.blk_roff : la.blk_off;
         if (threadIdx.x == 0) { pa = __ldg(offs + r0); pb = __ldg(offs + r0 + nr); }
-        blk::prefetch_l2(offs + r0, (size_t)(nr + 1) * 4, threadIdx.x, 64);
-        if (listed) blk::prefetch_l2(la.blk_rows + r0, (size_t)nr * 4, threadIdx.x, 64);
+        blk::prefetch_l2(offs + r0, (size_t)(nr + 1) * 4, threadIdx.x, PFT);
+        if (listed) blk::prefetch_l2(la.blk_rows + r0, (size_t)nr * 4, threadIdx.x, PFT);
         else {
             constexpr int SW = SoaWord<sizeof(State)>::value, SC = sizeof(State) / SW;
 #pragma unroll
-            for (int c = 0; c < SC; ++c) blk::prefetch_l2(av.state_r + ((size_t)c * av.cap + r0) * SW, (size_t)nr * SW, threadIdx.x, 64);
+            for (int c = 0; c < SC; ++c) blk::prefetch_l2(av.state_r + ((size_t)c * av.cap + r0) * SW, (size_t)nr * SW, threadIdx.x, PFT);
             if (!FIRST) {
 #pragma unroll
-                for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, threadIdx.x, 64);
+                for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, threadIdx.x, PFT);
 #pragma unroll
-                for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, threadIdx.x, 64);
+                for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, threadIdx.x, PFT);
             }
         }
     }
@@ -1331,6 +1334,31 @@ cudaError_t launch_stencil(const LaunchArgs& la) {
     return cudaGetLastError();
 }
 
+// default shape: 2 warps per CTA (parity-tested on the GPU with VB_PF_WARPS=2; 8 and 4 stay selectable through VB_PF_WARPS)
+#ifndef VB_PF_WARPS_DEFAULT
+#define VB_PF_WARPS_DEFAULT 2
+#endif
+template <class F, int WPC>
+cudaError_t launch_prefilter(KernelArgs& ka, unsigned long long work) {
+    const LaunchArgs& la = ka.la;
+    constexpr unsigned TPB = 32 * WPC;
+    static int pwave = 0;                                               // resident CTAs of this shape on the whole device
+    if (!pwave) {
+        int dev = 0, sms = 148, per_sm = 64 / WPC;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_prefilter_kernel<F, false, false, WPC>, (int)TPB, 0);
+        pwave = sms * (per_sm > 0 ? per_sm : 1);
+        if (getenv("VB_BLOCK_AHEAD")) pwave = atoi(getenv("VB_BLOCK_AHEAD"));
+    }
+    ka.la.blk_ahead = (uint32_t)pwave;
+    const unsigned grid = (unsigned)((work + TPB - 1) / TPB);
+    if (la.blk_first && la.blk_last) reduce_prefilter_kernel<F, true, true, WPC><<<grid, TPB, 0, la.stream>>>(ka);   // all keys in one block
+    else if (la.blk_first) reduce_prefilter_kernel<F, true, false, WPC><<<grid, TPB, 0, la.stream>>>(ka);
+    else if (la.blk_last) reduce_prefilter_kernel<F, false, true, WPC><<<grid, TPB, 0, la.stream>>>(ka);
+    else reduce_prefilter_kernel<F, false, false, WPC><<<grid, TPB, 0, la.stream>>>(ka);
+    return cudaGetLastError();
+}
 template <class F>
 cudaError_t launch_blocked(const LaunchArgs& la) {
     static thread_local KernelArgs ka;
@@ -1354,21 +1382,11 @@ cudaError_t launch_blocked(const LaunchArgs& la) {
     if constexpr (F::kPrefilter) {
         if (la.blk_prefilter) {
             if (!la.blk_key) return cudaErrorInvalidValue;
-            static int pwave = 0;
-            if (!pwave) {
-                int dev = 0, sms = 148, per_sm = 8;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_prefilter_kernel<F, false, false>, 256, 0);
-                pwave = sms * (per_sm > 0 ? per_sm : 1);
-                if (getenv("VB_BLOCK_AHEAD")) pwave = atoi(getenv("VB_BLOCK_AHEAD"));
-            }
-            ka.la.blk_ahead = (uint32_t)pwave;
-            if (la.blk_first && la.blk_last) reduce_prefilter_kernel<F, true, true><<<grid, 256, 0, la.stream>>>(ka);   // all keys in one block
-            else if (la.blk_first) reduce_prefilter_kernel<F, true, false><<<grid, 256, 0, la.stream>>>(ka);
-            else if (la.blk_last) reduce_prefilter_kernel<F, false, true><<<grid, 256, 0, la.stream>>>(ka);
-            else reduce_prefilter_kernel<F, false, false><<<grid, 256, 0, la.stream>>>(ka);
-            return cudaGetLastError();
+            static const int wpc = [] { const char* e = getenv("VB_PF_WARPS"); const int v = e ? atoi(e) : VB_PF_WARPS_DEFAULT; return v == 2 || v == 4 ? v : 8; }();
+            const unsigned long long work = listed ? la.blk_nrows : la.n;
+            if (wpc == 2) return launch_prefilter<F, 2>(ka, work);
+            if (wpc == 4) return launch_prefilter<F, 4>(ka, work);
+            return launch_prefilter<F, 8>(ka, work);
         }
     }
     if (la.blk_first && la.blk_last) return cudaErrorInvalidValue;      // a single block is the direct path's job

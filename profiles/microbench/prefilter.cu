@@ -249,12 +249,15 @@ int main(int argc, char** argv) {
         float ms; CK(cudaEventRecord(b.e0)); build_keys<<<(unsigned)((n / 4 + 256) / 256), 256>>>(state, key, n); CK(cudaEventRecord(b.e1)); CK(cudaEventSynchronize(b.e1));
         CK(cudaEventElapsedTime(&ms, b.e0, b.e1)); printf("build_keys: %.3f ms (%.1f MB of keys)\n", ms, n / 1e6);
     }
+    if (!getenv("SHAPES2")) {
     b.run("prefilter  4 lanes/row, keys L2 evict_last", [&] { prefilter_lanes<4, 0><<<(unsigned)((n * 4 + 255) / 256), 256>>>(src, roff, state, key, out, outc, n, eps, band); });
     b.run("prefilter  8 lanes/row, keys L2 evict_last", [&] { prefilter_lanes<8, 0><<<(unsigned)((n * 8 + 255) / 256), 256>>>(src, roff, state, key, out, outc, n, eps, band); });
     b.run("prefilter  8 lanes/row, keys L1+L2 evict_last", [&] { prefilter_lanes<8, 1><<<(unsigned)((n * 8 + 255) / 256), 256>>>(src, roff, state, key, out, outc, n, eps, band); });
     b.run("prefilter  8 lanes/row, keys plain ldg", [&] { prefilter_lanes<8, 2><<<(unsigned)((n * 8 + 255) / 256), 256>>>(src, roff, state, key, out, outc, n, eps, band); });
     b.run("prefilter 16 lanes/row, keys L2 evict_last", [&] { prefilter_lanes<16, 0><<<(unsigned)((n * 16 + 255) / 256), 256>>>(src, roff, state, key, out, outc, n, eps, band); });
+    }
     const unsigned wgrid = (unsigned)((n + 32 * WPB - 1) / (32 * WPB));
+    if (!getenv("SHAPES2")) {
     b.run("prefilter warp-staged, keys L2 evict_last", [&] { prefilter_warp<0><<<wgrid, 32 * WPB>>>(src, roff, state, key, out, outc, n, eps, band); });
     b.run("prefilter warp-staged, keys L1+L2 evict_last", [&] { prefilter_warp<1><<<wgrid, 32 * WPB>>>(src, roff, state, key, out, outc, n, eps, band); });
     b.run("prefilter warp-staged, keys plain ldg", [&] { prefilter_warp<2><<<wgrid, 32 * WPB>>>(src, roff, state, key, out, outc, n, eps, band); });
@@ -272,6 +275,7 @@ int main(int argc, char** argv) {
         printf("   (occupancy calculator: %d CTAs/SM)\n", nblk);
     }
     CK(cudaFuncSetAttribute(prefilter_warp<0>, cudaFuncAttributePreferredSharedMemoryCarveout, -1));
+    }
     // key-blocked: nb sweeps, each over the rows' entries whose source lies in block b (keys of one block = n / nb bytes)
     double* sum; uint32_t* cnt; CK(cudaMalloc(&sum, n * 8)); CK(cudaMalloc(&cnt, n * 4));
     uint32_t* bsrc; CK(cudaMalloc(&bsrc, E * 4 + 64));
@@ -311,11 +315,21 @@ int main(int argc, char** argv) {
                 last<<<g, 32 * wpb>>>(bsrc + hbase[1], off + (n + 4), state, key, out, outc, n, eps, band, sum, cnt, 0xffffffffu);
             });
         };
-        if (nb == 2) for (int co : {-1, 15, 25, 35, 50}) {
+        if (nb == 2 && !getenv("SHAPES2")) for (int co : {-1, 15, 25, 35, 50}) {
             shape(prefilter_warp<0, true, false, 128, 8>, prefilter_warp<0, false, true, 128, 8>, "chunk 128, 8 warps", 8, co);
             shape(prefilter_warp<0, true, false, 64, 8>, prefilter_warp<0, false, true, 64, 8>, "chunk  64, 8 warps", 8, co);
             shape(prefilter_warp<0, true, false, 256, 8>, prefilter_warp<0, false, true, 256, 8>, "chunk 256, 8 warps", 8, co);
             shape(prefilter_warp<0, true, false, 128, 4>, prefilter_warp<0, false, true, 128, 4>, "chunk 128, 4 warps", 4, co);
+        }
+        if (nb == 2 && getenv("SHAPES2")) {     // CTA size: a CTA lives as long as its slowest warp (power-law rows), so small CTAs idle less
+            shape(prefilter_warp<0, true, false, 64, 8>, prefilter_warp<0, false, true, 64, 8>, "chunk  64, 8 warps", 8, -1);
+            shape(prefilter_warp<0, true, false, 64, 4>, prefilter_warp<0, false, true, 64, 4>, "chunk  64, 4 warps", 4, -1);
+            shape(prefilter_warp<0, true, false, 64, 2>, prefilter_warp<0, false, true, 64, 2>, "chunk  64, 2 warps", 2, -1);
+            shape(prefilter_warp<0, true, false, 128, 4>, prefilter_warp<0, false, true, 128, 4>, "chunk 128, 4 warps", 4, -1);
+            shape(prefilter_warp<0, true, false, 128, 2>, prefilter_warp<0, false, true, 128, 2>, "chunk 128, 2 warps", 2, -1);
+            shape(prefilter_warp<0, true, false, 128, 1>, prefilter_warp<0, false, true, 128, 1>, "chunk 128, 1 warp ", 1, -1);
+            shape(prefilter_warp<0, true, false, 96, 4>, prefilter_warp<0, false, true, 96, 4>, "chunk  96, 4 warps", 4, -1);
+            shape(prefilter_warp<0, true, false, 96, 2>, prefilter_warp<0, false, true, 96, 2>, "chunk  96, 2 warps", 2, -1);
         }
         {   // per-sweep times
             std::vector<cudaEvent_t> ev(nb + 1); for (auto& e : ev) CK(cudaEventCreate(&e));
