@@ -1,0 +1,43 @@
+"""Replays /root/reference/test/globals.jl and /root/reference/test/parametric_types.jl (the two remaining single-process
+test files of the reference's runtests.jl that touch the path: host-side globals, G1; type parameters of agent / edge structs)."""
+import numpy as np
+
+import vahana_b200 as vh
+
+
+def test_globals(backend):  # test/globals.jl:1-17
+    types = vh.ModelTypes().register_agenttype("Agent", [("foo", "i8")])
+    model = vh.create_model(types, "globals")
+    sim = vh.create_simulation(model, None, {"foo": 0.0, "bar": []}, backend=backend)
+    sim.set_global("foo", 1.1)
+    sim.push_global("bar", 1)
+    sim.push_global("bar", 2)
+    assert sim.get_global("foo") == 1.1
+    assert sim.get_global("bar") == [1, 2]
+    sim.modify_global("foo", lambda v: v * 2)          # modify_global! = set_global!(f(get_global)), src/Global.jl:52-54
+    assert sim.get_global("foo") == 2.2
+    sim.finish_simulation()
+
+
+def test_parametric_types(backend):  # test/parametric_types.jl:1-38
+    # PAgent{Float64}, PAgent2 and PEdge{Float64}: a type parameter only fixes the field type, i.e. the registered layout
+    types = (vh.ModelTypes()
+             .register_agenttype("PAgent{Float64}", [("t", "f8")])
+             .register_agenttype("PAgent2", [("t", "f8")])
+             .register_edgetype("PEdge{Float64}", [("t", "f8")]))
+    sim = vh.create_simulation(vh.create_model(types, "parametric types"), backend=backend)
+    id1 = sim.add_agent("PAgent{Float64}", (1.0,))
+    id2 = sim.add_agent("PAgent2", (2.0,))
+    sim.add_edge(id1, id2, "PEdge{Float64}", (3.0,))
+    sim.finish_init()
+    sim.disable_transition_checks(True)
+    e = sim.edges(id2, "PEdge{Float64}")
+    assert e[0][0] == id1 and e[0][1]["t"] == 3.0                                   # first(edges(...)).state.t == 3.0
+    assert [s["t"] for s in sim.edgestates(id2, "PEdge{Float64}")] == [3.0]
+    assert [s["t"] for s in sim.neighborstates(id2, "PEdge{Float64}", "PAgent{Float64}")] == [1.0]
+    assert vh.type_nr(id1) == 1 and vh.type_nr(id2) == 2
+    # the identity transition of the test (`agent` returned unchanged) leaves both types as they were
+    sim.apply("identity", "PAgent2", ["PAgent{Float64}", "PAgent2", "PEdge{Float64}"], "PAgent2")
+    assert sim.all_agents("PAgent2")["t"].tolist() == [2.0]
+    assert sim.all_agents("PAgent{Float64}")["t"].tolist() == [1.0]
+    sim.finish_simulation()
