@@ -41,3 +41,21 @@ def test_parametric_types(backend):  # test/parametric_types.jl:1-38
     assert sim.all_agents("PAgent2")["t"].tolist() == [2.0]
     assert sim.all_agents("PAgent{Float64}")["t"].tolist() == [1.0]
     sim.finish_simulation()
+
+
+def test_julia_wrapper_binds_only_declared_symbols():
+    """The Julia `ccall` wrapper cannot run here (no Julia in the image); at least every symbol it binds must be
+    declared in include/vahana_b200.h and exported by the library, and the entry points of the hot path must all be bound."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "vahana.jl_b200", "julia", "VahanaB200.jl")).read()
+    header = open(os.path.join(root, "include", "vahana_b200.h")).read()
+    bound = set(re.findall(r"\(:(vb_\w+), LIB\)", src))
+    assert bound, "no ccall found"
+    for sym in bound:
+        assert re.search(r"\b%s\(" % sym, header), sym + " is not declared in include/vahana_b200.h"
+        assert sym in vh.ABI_SYMBOLS, sym
+    for sym in ["vb_sim_create", "vb_add_agents", "vb_add_edges", "vb_finish_init", "vb_apply", "vb_edges_of", "vb_mapreduce",
+                "vb_add_raster", "vb_connect_raster_neighbors", "vb_move_to", "vb_rastervalues", "vb_num_agents", "vb_all_agents"]:
+        assert sym in bound, sym
