@@ -59,3 +59,37 @@ def test_julia_wrapper_binds_only_declared_symbols():
     for sym in ["vb_sim_create", "vb_add_agents", "vb_add_edges", "vb_finish_init", "vb_apply", "vb_edges_of", "vb_mapreduce",
                 "vb_add_raster", "vb_connect_raster_neighbors", "vb_move_to", "vb_rastervalues", "vb_num_agents", "vb_all_agents"]:
         assert sym in bound, sym
+
+
+def _declared(header_path):
+    import re
+    txt = open(header_path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return set(re.findall(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(vbw?_\w+)\s*\(", txt, flags=re.M))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """The drop-in boundary: both libraries (the CUDA engine — loaded here without a GPU, no compute call — and the oracle behind the
+    same ABI) export every function include/vahana_b200.h and include/vahana_workloads.h declare; the Python mirror's ABI_SYMBOLS
+    list is exactly the header's set."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    core = _declared(os.path.join(root, "include", "vahana_b200.h"))
+    work = _declared(os.path.join(root, "include", "vahana_workloads.h"))
+    assert len(core) > 40 and "vb_apply" in core and "vb_register_transition" not in core
+    assert core == set(vh.ABI_SYMBOLS), (core ^ set(vh.ABI_SYMBOLS))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "oracle")], check=True)
+    libs = [os.path.join(root, "oracle", "_build", "libvahana_oracle.so")]
+    cuda_lib = os.path.join(root, "vahana.jl_b200", "csrc", "build", "libvahana_b200.so")
+    if not os.path.exists(cuda_lib):      # nvcc cross-compiles without a GPU (minutes); normally __graft_entry__.build() ran before
+        import sys
+        subprocess.run([sys.executable, os.path.join(root, "vahana.jl_b200", "build.py")], check=True)
+    libs.append(cuda_lib)
+    for path in libs:
+        lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        missing = [s for s in sorted(core | work) if not hasattr(lib, s)]
+        assert not missing, (path, missing)
+    lib.vb_backend.restype = C.c_char_p
+    assert lib.vb_backend() == b"cuda-sm100a"
