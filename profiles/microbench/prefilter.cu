@@ -109,8 +109,12 @@ __global__ void __launch_bounds__(256) prefilter_lanes(const uint32_t* __restric
 // gathers the exact states of the queue edge-parallel and every lane folds its own row's segment in entry order, i.e. in
 // exactly the order of the sequential reference fold.
 constexpr int WPB = 8;
-template <int QCAP> struct WarpStage { uint32_t off[33]; uint32_t qcnt[32]; uint32_t key[32]; uint32_t qidx[QCAP]; double qval[QCAP]; };
-template <int MODE, bool FIRST = true, bool LAST = true, int CHUNK = 128, int WPB = 8>
+template <int QCAP> struct WarpStage { uint32_t off[33]; uint32_t qcnt[32]; uint32_t key[32]; uint32_t nz[32]; uint32_t qidx[QCAP]; double qval[QCAP]; };
+// RF (row find) = 0: the row that owns an entry by a 5-step search of the 33 offsets in shared memory (5 dependent LDS per entry);
+// RF = 1: per 32-entry sub-chunk one REDUX builds the mask of positions where a non-empty row starts and one ballot counts the rows
+// started before it; an entry's row is then nz[started_before + popc(mask & lanes_le) - 1] with nz = the table of non-empty rows
+// (one LDS per entry).  Index arithmetic checked against brute force on the CPU (random rows incl. empty ones).
+template <int MODE, bool FIRST = true, bool LAST = true, int CHUNK = 128, int WPB = 8, int RF = 0>
 __global__ void __launch_bounds__(32 * WPB) prefilter_warp(const uint32_t* __restrict__ src, const uint32_t* __restrict__ roff, const double* __restrict__ state,
                                                            const uint8_t* __restrict__ key, double* __restrict__ out, uint32_t* __restrict__ outc, uint64_t n, double eps, int band,
                                                            double* __restrict__ sum = nullptr, uint32_t* __restrict__ cnt = nullptr, uint32_t head = 0xffffffffu) {
@@ -131,6 +135,13 @@ __global__ void __launch_bounds__(32 * WPB) prefilter_warp(const uint32_t* __res
     __syncwarp();
     const uint32_t e0 = sm.off[0], e1 = sm.off[32];
     const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t my_lo = sm.off[lane];
+    const bool nonempty = sm.off[lane + 1] > my_lo;
+    if (RF == 1) {
+        const uint32_t nzmask = __ballot_sync(0xffffffffu, nonempty);
+        if (nonempty) sm.nz[__popc(nzmask & lt)] = lane;
+        __syncwarp();
+    }
     double s = 0; uint32_t c = 0, qn = 0;
     if (!FIRST && lane < nr) { s = __ldcs(sum + r0 + lane); c = __ldcs(cnt + r0 + lane); }
     for (uint32_t base = e0; base < e1; base += CHUNK) {
@@ -143,8 +154,15 @@ __global__ void __launch_bounds__(32 * WPB) prefilter_warp(const uint32_t* __res
         for (int u = 0; u < U; ++u) {
             const uint32_t e = base + u * 32 + lane;
             uint32_t r = 0;
+            if (RF == 0) {
 #pragma unroll
-            for (int st = 16; st; st >>= 1) if (sm.off[r + st] <= e) r += st;
+                for (int st = 16; st; st >>= 1) if (sm.off[r + st] <= e) r += st;
+            } else {
+                const uint32_t x0 = base + u * 32, d = my_lo - x0;
+                const uint32_t before = __popc(__ballot_sync(0xffffffffu, nonempty && my_lo < x0));
+                const uint32_t starts = __reduce_or_sync(0xffffffffu, (nonempty && my_lo >= x0 && d < 32u) ? (1u << d) : 0u);
+                r = sm.nz[(before + __popc(starts & (lt | (1u << lane))) - 1u) & 31u];
+            }
             const bool pass = abs(ks[u] - (int)sm.key[r]) <= band;
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             if (pass) { sm.qidx[qn + __popc(m & lt)] = idx[u] | (r << 27); atomicAdd(&sm.qcnt[r], 1u); }
@@ -330,6 +348,11 @@ int main(int argc, char** argv) {
             shape(prefilter_warp<0, true, false, 128, 1>, prefilter_warp<0, false, true, 128, 1>, "chunk 128, 1 warp ", 1, -1);
             shape(prefilter_warp<0, true, false, 96, 4>, prefilter_warp<0, false, true, 96, 4>, "chunk  96, 4 warps", 4, -1);
             shape(prefilter_warp<0, true, false, 96, 2>, prefilter_warp<0, false, true, 96, 2>, "chunk  96, 2 warps", 2, -1);
+            // NOT RUN YET (added after the round's GPU budget was spent): mask / popc row find instead of the offset search
+            shape(prefilter_warp<0, true, false, 64, 2, 1>, prefilter_warp<0, false, true, 64, 2, 1>, "chunk  64, 2 warps, mask row find", 2, -1);
+            shape(prefilter_warp<0, true, false, 64, 4, 1>, prefilter_warp<0, false, true, 64, 4, 1>, "chunk  64, 4 warps, mask row find", 4, -1);
+            shape(prefilter_warp<0, true, false, 96, 2, 1>, prefilter_warp<0, false, true, 96, 2, 1>, "chunk  96, 2 warps, mask row find", 2, -1);
+            shape(prefilter_warp<0, true, false, 128, 4, 1>, prefilter_warp<0, false, true, 128, 4, 1>, "chunk 128, 4 warps, mask row find", 4, -1);
         }
         {   // per-sweep times
             std::vector<cudaEvent_t> ev(nb + 1); for (auto& e : ev) CK(cudaEventCreate(&e));
