@@ -117,7 +117,8 @@ template <int QCAP> struct WarpStage { uint32_t off[33]; uint32_t qcnt[32]; uint
 template <int MODE, bool FIRST = true, bool LAST = true, int CHUNK = 128, int WPB = 8, int RF = 0>
 __global__ void __launch_bounds__(32 * WPB) prefilter_warp(const uint32_t* __restrict__ src, const uint32_t* __restrict__ roff, const double* __restrict__ state,
                                                            const uint8_t* __restrict__ key, double* __restrict__ out, uint32_t* __restrict__ outc, uint64_t n, double eps, int band,
-                                                           double* __restrict__ sum = nullptr, uint32_t* __restrict__ cnt = nullptr, uint32_t head = 0xffffffffu) {
+                                                           double* __restrict__ sum = nullptr, uint32_t* __restrict__ cnt = nullptr, uint32_t head = 0xffffffffu,
+                                                           cudaTextureObject_t ktex = 0) {
     constexpr int QCAP = CHUNK + 32, U = CHUNK / 32;
     __shared__ WarpStage<QCAP> stage[WPB];
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -149,7 +150,10 @@ __global__ void __launch_bounds__(32 * WPB) prefilter_warp(const uint32_t* __res
 #pragma unroll
         for (int u = 0; u < U; ++u) { const uint32_t e = base + u * 32 + lane; idx[u] = e < e1 ? __ldcs(src + e) : 0xffffffffu; }
 #pragma unroll
-        for (int u = 0; u < U; ++u) ks[u] = idx[u] != 0xffffffffu ? (int)ld_key<(MODE == 3 ? 0 : MODE)>(key + idx[u], MODE == 3 && idx[u] >= head ? pol_first : pol_keep) : 100000;
+        for (int u = 0; u < U; ++u) {
+            if (MODE == 5) ks[u] = idx[u] != 0xffffffffu ? (int)tex1Dfetch<unsigned char>(ktex, (int)idx[u]) : 100000;     // texture path (NOT RUN YET)
+            else ks[u] = idx[u] != 0xffffffffu ? (int)ld_key<(MODE == 3 ? 0 : MODE)>(key + idx[u], MODE == 3 && idx[u] >= head ? pol_first : pol_keep) : 100000;
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t e = base + u * 32 + lane;
@@ -348,6 +352,20 @@ int main(int argc, char** argv) {
             shape(prefilter_warp<0, true, false, 128, 1>, prefilter_warp<0, false, true, 128, 1>, "chunk 128, 1 warp ", 1, -1);
             shape(prefilter_warp<0, true, false, 96, 4>, prefilter_warp<0, false, true, 96, 4>, "chunk  96, 4 warps", 4, -1);
             shape(prefilter_warp<0, true, false, 96, 2>, prefilter_warp<0, false, true, 96, 2>, "chunk  96, 2 warps", 2, -1);
+            {   // NOT RUN YET: keys through the texture path (linear texture over the key column; 2^27 texels at most)
+                cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = key; rd.res.linear.desc = cudaCreateChannelDesc<unsigned char>();
+                rd.res.linear.sizeInBytes = n;
+                cudaTextureDesc td = {}; td.readMode = cudaReadModeElementType;
+                cudaTextureObject_t ktex = 0;
+                if (cudaCreateTextureObject(&ktex, &rd, &td, nullptr) == cudaSuccess) {
+                    const unsigned g = (unsigned)((n + 63) / 64);
+                    b.run("   nb=2 chunk  64, 2 warps, keys via tex1Dfetch", [&] {
+                        prefilter_warp<5, true, false, 64, 2><<<g, 64>>>(bsrc + hbase[0], off, state, key, out, outc, n, eps, band, sum, cnt, 0xffffffffu, ktex);
+                        prefilter_warp<5, false, true, 64, 2><<<g, 64>>>(bsrc + hbase[1], off + (n + 4), state, key, out, outc, n, eps, band, sum, cnt, 0xffffffffu, ktex);
+                    });
+                    cudaDestroyTextureObject(ktex);
+                } else { printf("   texture object over %llu keys refused: %s\n", (unsigned long long)n, cudaGetErrorString(cudaGetLastError())); }
+            }
             // NOT RUN YET (added after the round's GPU budget was spent): mask / popc row find instead of the offset search
             shape(prefilter_warp<0, true, false, 64, 2, 1>, prefilter_warp<0, false, true, 64, 2, 1>, "chunk  64, 2 warps, mask row find", 2, -1);
             shape(prefilter_warp<0, true, false, 64, 4, 1>, prefilter_warp<0, false, true, 64, 4, 1>, "chunk  64, 4 warps, mask row find", 4, -1);
