@@ -333,8 +333,8 @@ int main(int argc, char** argv) {
             char nm2[96]; snprintf(nm2, sizeof nm2, "   nb=2 %s, carveout %d", what, co);
             const unsigned g = (unsigned)((n + 32 * wpb - 1) / (32 * wpb));
             b.run(nm2, [&] {
-                first<<<g, 32 * wpb>>>(bsrc + hbase[0], off, state, key, out, outc, n, eps, band, sum, cnt, 0xffffffffu);
-                last<<<g, 32 * wpb>>>(bsrc + hbase[1], off + (n + 4), state, key, out, outc, n, eps, band, sum, cnt, 0xffffffffu);
+                first<<<g, 32 * wpb>>>(bsrc + hbase[0], off, state, key, out, outc, n, eps, band, sum, cnt, 0xffffffffu, (cudaTextureObject_t)0);
+                last<<<g, 32 * wpb>>>(bsrc + hbase[1], off + (n + 4), state, key, out, outc, n, eps, band, sum, cnt, 0xffffffffu, (cudaTextureObject_t)0);
             });
         };
         if (nb == 2 && !getenv("SHAPES2")) for (int co : {-1, 15, 25, 35, 50}) {
