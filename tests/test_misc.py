@@ -93,3 +93,16 @@ def test_cabi_library_exports_every_declared_symbol():
         assert not missing, (path, missing)
     lib.vb_backend.restype = C.c_char_p
     assert lib.vb_backend() == b"cuda-sm100a"
+
+
+def test_nonmutating_apply(backend):  # src/Simulation.jl:847-856: apply = copy_simulation + apply! on the copy
+    from models import createsim
+    sim = createsim(backend)[0]
+    before = {T: sim.all_agents(T).tobytes() for T in ("AMortal", "AImm", "AImmFixed")}
+    n0 = sim.num_transitions()
+    new = vh.apply(sim, "kill_all", "AMortal", [], "AMortal")
+    assert new.num_agents("AMortal") == 0 and sim.num_agents("AMortal") > 0          # only the copy changed
+    assert {T: sim.all_agents(T).tobytes() for T in before} == before
+    assert sim.num_transitions() == n0 and new.num_transitions() == n0 + 1
+    new.finish_simulation()
+    sim.finish_simulation()

@@ -555,6 +555,13 @@ class Simulation:
         self._ck(self.lib.vb_apply(self.h, transition.encode(), c, nc, r, nr, w, nw, a, na, C.c_int(we), C.c_uint64(seed)))
         return self
 
+    def apply_copy(self, transition: str, call, read, write, **kwargs) -> "Simulation":
+        """apply(sim, f, call, read, write; kwargs...) (src/Simulation.jl:847-856): the non-mutating form — copy_simulation, then
+        apply! on the copy; returns the copy and leaves `self` untouched (meant for the REPL, not for production loops)."""
+        new = self.copy_simulation()
+        new.apply(transition, call, read, write, **kwargs)
+        return new
+
     def num_transitions(self) -> int:
         n = C.c_int64()
         self._ck(self.lib.vb_num_transitions(self.h, C.byref(n)))
@@ -783,6 +790,11 @@ class Simulation:
 def create_simulation(model: Model, params: Optional[dict] = None, globals_: Optional[dict] = None,
                       backend: Optional[Backend] = None, device: int = 0) -> Simulation:
     return Simulation(model, params, globals_, backend, device)
+
+
+def apply(sim: Simulation, transition: str, call, read, write, **kwargs) -> Simulation:
+    """apply(sim, f, call, read, write; kwargs...) — the non-mutating apply! of src/Simulation.jl:847-856."""
+    return sim.apply_copy(transition, call, read, write, **kwargs)
 
 
 def add_graph(sim: Simulation, edges_uv: np.ndarray, n: int, agent_type: str, agent_states, edge_type: str, edge_states=None,

@@ -7,7 +7,7 @@
 module VahanaB200
 
 export ModelTypes, register_agenttype!, register_edgetype!, register_param!, register_global!, create_model,
-       create_simulation, copy_simulation, finish_simulation!, finish_init!, apply!,
+       create_simulation, copy_simulation, finish_simulation!, finish_init!, apply!, apply,
        AgentID, Edge, agent_id, type_nr, process_nr, agent_nr,
        add_agent!, add_agents!, add_edge!, add_edges!, remove_edges!,
        agentstate, agentstate_flexible, edges, neighborids, edgestates, neighborstates, neighborstates_flexible,
@@ -259,6 +259,13 @@ function apply!(sim::Simulation, transition::String, call, read, write; add_exis
     check(ccall((:vb_apply, LIB), Cint, (Ptr{Cvoid}, Cstring, Ptr{Cint}, Cint, Ptr{Cint}, Cint, Ptr{Cint}, Cint, Ptr{Cint}, Cint, Cint, UInt64),
                 sim.handle, transition, c, length(c), r, length(r), w, length(w), a, length(a), we, seed))
     sim
+end
+
+"apply(sim, transition, call, read, write; kwargs...): the non-mutating form, src/Simulation.jl:847-856"
+function apply(sim::Simulation, transition::String, call, read, write; kwargs...)
+    newsim = copy_simulation(sim)
+    apply!(newsim, transition, call, read, write; kwargs...)
+    newsim
 end
 
 # ---- queries -------------------------------------------------------------------------------------------------------------
