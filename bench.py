@@ -231,6 +231,21 @@ def run_engine(args):
         metric = sim.mapreduce("opinion", "+", "HKAgent")     # device reduction, 8 B device->host
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # harsher variant: the host also wants every agent's new state after every step (all_agents: 8 B per agent device->host, pageable)
+    dl_steps = min(3, args.steps)
+    dl = None
+    try:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dl_bytes = 0
+        for _ in range(dl_steps):
+            step()
+            dl_bytes = sim.all_agents("HKAgent").nbytes
+        torch.cuda.synchronize()
+        dl = {"value": E_local * dl_steps / (time.perf_counter() - t0), "unit": "edges/s (this rank)", "steps": dl_steps, "d2h_bytes_per_step": int(dl_bytes),
+              "note": "apply! + all_agents(HKAgent) per step: every new state copied to host memory"}
+    except Exception as exc:      # a secondary figure must never cost the bench line
+        dl = {"error": repr(exc)[:200]}
     view_bytes = int(lib.vb_device_view_bytes())
     hb = C.c_uint64()
     lib.vb_halo_bytes(sim.h, C.byref(hb))
@@ -276,7 +291,8 @@ def run_engine(args):
             "value": cpu_eps, "unit": "edges/s", "cores": 1, "kind": "port",
             "sample": f"{args.cpu_agents} agents / {cpu_ne} edges of the same generator, 3 applies (oracle restatement, not Julia)"},
         "e2e": {"value": E * args.steps / e2e_s, "unit": "edges/s", "h2d_bytes_per_step": view_bytes, "d2h_bytes_per_step": 8 + 4,
-                "note": "apply! + mapreduce(opinion,+) through the Python/ctypes API per step; agent state stays resident on device as it stays resident in the reference's process"},
+                "note": "apply! + mapreduce(opinion,+) through the Python/ctypes API per step; agent state stays resident on device as it stays resident in the reference's process",
+                "with_state_download": dl},
         "gpu_launches": launches, "clocks": clk,
     }
     print(json.dumps(line), flush=True)
