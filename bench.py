@@ -235,6 +235,8 @@ def run_engine(args):
     dl_steps = min(3, args.steps)
     dl = None
     try:
+        if world > 1:
+            raise RuntimeError("single-GPU figure only")
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         dl_bytes = 0
