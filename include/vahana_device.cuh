@@ -1075,7 +1075,7 @@ __device__ __forceinline__ uint32_t ld_key(const uint8_t* p, uint64_t pol) {
     uint32_t r; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol)); return r;
 }
 }  // namespace blk
-template <class F> struct PrefilterStage {
+template <class F, int RF = 0> struct PrefilterStage {
     static constexpr int CHK = 64, QCAP = CHK + 32;
     uint32_t off[33];                   // entry positions of the warp's 32 rows (+ end)
     uint32_t qcnt[32];                  // queued entries per row
@@ -1083,16 +1083,23 @@ template <class F> struct PrefilterStage {
     uint32_t qidx[QCAP];                // queued source slots, in entry order
     typename F::Source qval[QCAP];      // their exact states
 };
+template <class F> struct PrefilterStage<F, 1> : PrefilterStage<F, 0> {
+    uint32_t nz[32];                    // RF = 1: the warp's non-empty rows, in order
+};
 // WPC = warps per CTA.  A CTA lives as long as its slowest warp, and a warp that meets a long power-law row is slow: small CTAs leave
 // fewer warps idle (profiles/r1_prefilter/prefilter_shapes2.txt: 11.65 / 10.86 / 10.59 ms with 8 / 4 / 2 warps per CTA).
-template <class F, bool FIRST, bool LAST, int WPC>
+// RF (row find) = 0: the row that owns an entry by a 5-step search of the 33 offsets in shared memory; RF = 1 (VB_PF_ROWFIND=1,
+// experimental: written after round 1's GPU budget was spent, index arithmetic checked on the CPU, not yet run on a GPU): one REDUX
+// per 32 entries marks where non-empty rows start, one ballot counts the rows started before, and an entry's row is
+// nz[started_before + popc(starts & lanes_le) - 1] — one shared-memory load per entry instead of five dependent ones.
+template <class F, bool FIRST, bool LAST, int WPC, int RF = 0>
 __global__ void __launch_bounds__(32 * WPC, 64 / WPC) reduce_prefilter_kernel(const __grid_constant__ KernelArgs ka) {
     constexpr uint32_t TPB = 32 * WPC, PFT = TPB < 64 ? TPB : 64;   // rows per CTA; threads that issue the look-ahead prefetches
     typedef BlockedCfg<F> C;
     typedef typename C::State State;
     typedef typename C::Source Source;
     typedef typename C::Acc Acc;
-    typedef PrefilterStage<F> Stage;
+    typedef PrefilterStage<F, RF> Stage;
     constexpr int CHK = Stage::CHK, QCAP = Stage::QCAP, U = CHK / 32;
     __shared__ Stage stages[WPC];
     const LaunchArgs& la = ka.la;
@@ -1158,6 +1165,10 @@ __global__ void __launch_bounds__(32 * WPC, 64 / WPC) reduce_prefilter_kernel(co
     if (lane == 31) sm.off[32] = hi;
     sm.qcnt[lane] = 0;
     const uint32_t alive = __ballot_sync(0xffffffffu, act);               // entries of died rows are never queued
+    if constexpr (RF == 1) {
+        const uint32_t nzmask = __ballot_sync(0xffffffffu, hi > lo);
+        if (hi > lo) sm.nz[__popc(nzmask & ((1u << lane) - 1u))] = lane;
+    }
     __syncwarp();
     const uint32_t e0 = sm.off[0], e1 = sm.off[32];
     const uint32_t len = hi - lo;
@@ -1173,8 +1184,16 @@ __global__ void __launch_bounds__(32 * WPC, 64 / WPC) reduce_prefilter_kernel(co
         for (int u = 0; u < U; ++u) {
             const uint32_t x = base + lane + 32 * u;
             uint32_t r = 0;                                                // the row that owns entry x: the last one starting at or before it
+            if constexpr (RF == 0) {
 #pragma unroll
-            for (int st = 16; st; st >>= 1) if (sm.off[r + st] <= x) r += st;
+                for (int st = 16; st; st >>= 1) if (sm.off[r + st] <= x) r += st;
+            } else {
+                const bool nonempty = hi > lo;
+                const uint32_t x0 = base + 32 * u, d = lo - x0;
+                const uint32_t before = __popc(__ballot_sync(0xffffffffu, nonempty && lo < x0));
+                const uint32_t starts = __reduce_or_sync(0xffffffffu, (nonempty && lo >= x0 && d < 32u) ? (1u << d) : 0u);
+                r = sm.nz[(before + __popc(starts & (lt | (1u << lane))) - 1u) & 31u];
+            }
             const bool pass = x < e1 && ((alive >> r) & 1u) && f.may_accept(sm.probe[r], ks[u]);
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             if (pass) { sm.qidx[qn + __popc(m & lt)] = six[u]; atomicAdd(&sm.qcnt[r], 1u); }
@@ -1338,7 +1357,7 @@ cudaError_t launch_stencil(const LaunchArgs& la) {
 #ifndef VB_PF_WARPS_DEFAULT
 #define VB_PF_WARPS_DEFAULT 2
 #endif
-template <class F, int WPC>
+template <class F, int WPC, int RF = 0>
 cudaError_t launch_prefilter(KernelArgs& ka, unsigned long long work) {
     const LaunchArgs& la = ka.la;
     constexpr unsigned TPB = 32 * WPC;
@@ -1347,16 +1366,16 @@ cudaError_t launch_prefilter(KernelArgs& ka, unsigned long long work) {
         int dev = 0, sms = 148, per_sm = 64 / WPC;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_prefilter_kernel<F, false, false, WPC>, (int)TPB, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_prefilter_kernel<F, false, false, WPC, RF>, (int)TPB, 0);
         pwave = sms * (per_sm > 0 ? per_sm : 1);
         if (getenv("VB_BLOCK_AHEAD")) pwave = atoi(getenv("VB_BLOCK_AHEAD"));
     }
     ka.la.blk_ahead = (uint32_t)pwave;
     const unsigned grid = (unsigned)((work + TPB - 1) / TPB);
-    if (la.blk_first && la.blk_last) reduce_prefilter_kernel<F, true, true, WPC><<<grid, TPB, 0, la.stream>>>(ka);   // all keys in one block
-    else if (la.blk_first) reduce_prefilter_kernel<F, true, false, WPC><<<grid, TPB, 0, la.stream>>>(ka);
-    else if (la.blk_last) reduce_prefilter_kernel<F, false, true, WPC><<<grid, TPB, 0, la.stream>>>(ka);
-    else reduce_prefilter_kernel<F, false, false, WPC><<<grid, TPB, 0, la.stream>>>(ka);
+    if (la.blk_first && la.blk_last) reduce_prefilter_kernel<F, true, true, WPC, RF><<<grid, TPB, 0, la.stream>>>(ka);   // all keys in one block
+    else if (la.blk_first) reduce_prefilter_kernel<F, true, false, WPC, RF><<<grid, TPB, 0, la.stream>>>(ka);
+    else if (la.blk_last) reduce_prefilter_kernel<F, false, true, WPC, RF><<<grid, TPB, 0, la.stream>>>(ka);
+    else reduce_prefilter_kernel<F, false, false, WPC, RF><<<grid, TPB, 0, la.stream>>>(ka);
     return cudaGetLastError();
 }
 template <class F>
@@ -1384,6 +1403,8 @@ cudaError_t launch_blocked(const LaunchArgs& la) {
             if (!la.blk_key) return cudaErrorInvalidValue;
             static const int wpc = [] { const char* e = getenv("VB_PF_WARPS"); const int v = e ? atoi(e) : VB_PF_WARPS_DEFAULT; return v == 2 || v == 4 ? v : 8; }();
             const unsigned long long work = listed ? la.blk_nrows : la.n;
+            static const bool rowfind = getenv("VB_PF_ROWFIND") && atoi(getenv("VB_PF_ROWFIND")) != 0;     // experimental, see reduce_prefilter_kernel
+            if (rowfind) return wpc == 8 ? launch_prefilter<F, 8, 1>(ka, work) : launch_prefilter<F, 2, 1>(ka, work);
             if (wpc == 2) return launch_prefilter<F, 2>(ka, work);
             if (wpc == 4) return launch_prefilter<F, 4>(ka, work);
             return launch_prefilter<F, 8>(ka, work);

@@ -11,5 +11,9 @@ cd ../..
 for w in 2 4 8; do                                                                                    # in-engine time of the sweep shapes (default 2)
   (VB_PF_WARPS=$w timeout 100 python bench.py --steps 5 --warmup 3 --no-cpu) > gpurun_out/bench_pf_warps$w.json 2> gpurun_out/bench_pf_warps$w.err
 done
+# experimental mask row find in the engine kernel: parity first, then time
+(VB_PF_ROWFIND=1 timeout 100 python -m pytest tests/test_hk.py -x -q -m gpu -k "not full_size") > gpurun_out/test_hk_rowfind.txt 2>&1
+(VB_PF_ROWFIND=1 timeout 100 python bench.py --steps 5 --warmup 3 --no-cpu) > gpurun_out/bench_pf_rowfind.json 2> gpurun_out/bench_pf_rowfind.err
+tail -n 3 gpurun_out/test_hk_rowfind.txt
 tail -n 40 gpurun_out/wavefront.txt gpurun_out/prefilter_shapes3.txt
 for w in 2 4 8; do python -c "import json,sys; d=json.load(open('gpurun_out/bench_pf_warps$w.json')); print('VB_PF_WARPS=$w', d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'])"; done
