@@ -541,6 +541,25 @@ class Simulation:
         self._ck(self.lib.vb_cellid(self.h, name.encode(), p, C.byref(out)))
         return out.value
 
+    def random_pos(self, name: str, weights=None, rng=None) -> tuple:
+        """random_pos([rng], sim, raster[, weights]) (src/Raster.jl:512-543): a 1-based position of the raster, uniform or with
+        probability proportional to `weights` (same shape as the raster; Julia's vec() order = column-major).  Host side, init phase."""
+        dims = self.raster_info(name)
+        rng = rng or np.random.default_rng()
+        n = int(np.prod(dims))
+        if weights is None:
+            lin = int(rng.integers(n))
+        else:
+            w = np.asarray(weights, dtype=np.float64)
+            assert tuple(w.shape) == tuple(dims), f"`weights` must have the same dimension as the raster :{name}"
+            p = w.reshape(-1, order="F")
+            lin = int(rng.choice(n, p=p / p.sum()))
+        return tuple(int(i) + 1 for i in np.unravel_index(lin, dims, order="F"))
+
+    def random_cell(self, name: str, weights=None, rng=None) -> int:
+        """random_cell([rng], sim, raster[, weights]) (src/Raster.jl:553-577): the id of a random cell."""
+        return self.cellid(name, self.random_pos(name, weights, rng))
+
     def finish_init(self):
         self._ck(self.lib.vb_finish_init(self.h))
         return self

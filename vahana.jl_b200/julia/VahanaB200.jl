@@ -14,6 +14,7 @@ export ModelTypes, register_agenttype!, register_edgetype!, register_param!, reg
        num_edges, has_edge, num_agents, all_agents, all_agentids, all_edges,
        param, set_param!, get_global, set_global!, push_global!, modify_global!,
        add_raster!, connect_raster_neighbors!, move_to!, cellid, calc_rasterstate, rastervalues, calc_raster_num_edges,
+       random_pos, random_cell,
        enable_asserts
 
 const LIB = get(ENV, "VAHANA_B200_LIB", joinpath(@__DIR__, "..", "csrc", "build", "libvahana_b200.so"))
@@ -415,6 +416,17 @@ function cellid(sim::Simulation, name::Symbol, pos)                       # src/
     check(ccall((:vb_cellid, LIB), Cint, (Ptr{Cvoid}, Cstring, Ptr{Int64}, Ref{AgentID}), sim.handle, string(name), Int64[pos...], id))
     id[]
 end
+"random_pos(sim, name[, weights]) / random_cell(sim, name[, weights]): src/Raster.jl:512-577 (host side; uniform or weight-proportional)"
+function random_pos(sim::Simulation, name::Symbol, weights::Union{Array,Nothing} = nothing)
+    dims, _ = sim.rasters[name]
+    positions = CartesianIndices(dims)
+    weights === nothing && return positions[rand(1:length(positions))]
+    @assert dims == size(weights) "`weights` must have the same dimension as the raster :$(name)"
+    c = cumsum(vec(weights))
+    positions[min(searchsortedfirst(c, rand() * c[end]), length(c))]
+end
+random_cell(sim::Simulation, name::Symbol, weights::Union{Array,Nothing} = nothing) = cellid(sim, name, Tuple(random_pos(sim, name, weights)))
+
 "rastervalues(sim, name, field) / calc_rasterstate(sim, name, field): src/Raster.jl:290-387 with f = c -> c.field"
 function rastervalues(sim::Simulation, name::Symbol, field::Symbol)
     dims, T = sim.rasters[name]
