@@ -106,3 +106,22 @@ def test_nonmutating_apply(backend):  # src/Simulation.jl:847-856: apply = copy_
     assert sim.num_transitions() == n0 and new.num_transitions() == n0 + 1
     new.finish_simulation()
     sim.finish_simulation()
+
+
+def test_duration_log_in_the_reference_format(oracle, tmp_path):  # src/Logging.jl:30-103: <Begin>/<End> pairs -> "x |#| Duration (ms)"
+    import re
+    from models import core_model, add_example_network
+    sim = vh.create_simulation(core_model(), backend=oracle, logging=True, log_path=str(tmp_path))
+    add_example_network(sim)
+    sim.finish_init()
+    sim.apply("identity", "AMortal", ["AMortal"], ["AMortal"])
+    sim.apply("kill_all", "AMortal", [], "AMortal")
+    path = sim.logger.path
+    assert path == str(tmp_path / "Test_Core_0.log")           # <name>_<rank>.log
+    sim.finish_simulation()
+    txt = open(path).read()
+    recs = re.findall(r"Start \(sec\): ([0-9.e+-]+)\n   (\S+) \|#\| Duration \(ms\): ([0-9.e+-]+)\n((?:    \w+ = .*\n)*)", txt)
+    assert [r[1] for r in recs] == ["finish_init!", "apply!", "apply!", "finish_simulation!"]
+    assert "func = identity" in recs[1][3] and "transition = 2" in recs[1][3]       # finish_init! set num_transitions to 1
+    assert "func = kill_all" in recs[2][3] and "transition = 3" in recs[2][3]
+    assert all(float(r[2]) >= 0 for r in recs) and float(recs[0][0]) <= float(recs[1][0]) <= float(recs[2][0])

@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 from typing import Any, Iterable, Optional, Sequence
 
 import numpy as np
@@ -285,11 +286,51 @@ def create_model(types: ModelTypes, name: str) -> Model:
     return Model(types, name)
 
 
+class VahanaLogger:
+    """The reference's duration log (src/Logging.jl:30-73, file log/<name>_<rank>.log, src/Logging.jl:75-103): a message tagged
+    `<Begin> x` is remembered, the matching `<End> x` writes
+        Start (sec): <begin - logger start>
+           x |#| Duration (ms): <duration>
+            key = value            (the keyword arguments of the <Begin> message)
+    so the reference's log tooling reads runs of this engine.  Host side only; nothing is written unless logging is switched on."""
+
+    def __init__(self, filename: str, log_path: Optional[str] = None, rank: int = 0):
+        d = log_path or "log"
+        os.makedirs(d, exist_ok=True)
+        self.path = os.path.join(d, f"{filename}_{rank}.log")
+        self.stream = open(self.path, "w")
+        self.starttime = time.time()
+        self.begintimes = {}
+        self.kwargs = {}
+
+    def begin(self, what: str, **kwargs) -> None:
+        self.begintimes[what] = time.time()
+        self.kwargs[what] = kwargs
+
+    def end(self, what: str) -> None:
+        now = time.time()
+        t0 = self.begintimes.get(what, now)
+        self.stream.write(f"Start (sec): {t0 - self.starttime}\n   {what} |#| Duration (ms): {(now - t0) * 1000}\n")
+        for k, v in self.kwargs.get(what, {}).items():
+            self.stream.write(f"    {k} = {v}\n")
+        self.stream.flush()
+
+    def info(self, message: str) -> None:
+        self.stream.write(f"Time (sec): {time.time() - self.starttime}\n  {message}\n")
+        self.stream.flush()
+
+    def close(self) -> None:
+        if not self.stream.closed:
+            self.stream.close()
+
+
 # --- Simulation -----------------------------------------------------------------------------------------
 class Simulation:
     def __init__(self, model: Model, params: Optional[dict] = None, globals_: Optional[dict] = None,
-                 backend: Optional[Backend] = None, device: int = 0, _handle=None):
+                 backend: Optional[Backend] = None, device: int = 0, _handle=None, logging: bool = False,
+                 log_path: Optional[str] = None):
         self.model = model
+        self.logger = VahanaLogger(model.name.replace(" ", "_"), log_path) if logging else None
         self.backend = backend or default_backend()
         self.backend.init(device)
         self.lib = self.backend.lib
@@ -366,10 +407,23 @@ class Simulation:
         return arr
 
     # -- lifecycle --
+    def _log_begin(self, what: str, **kw) -> None:
+        if self.logger is not None:
+            self.logger.begin(what, **kw)
+
+    def _log_end(self, what: str) -> None:
+        if self.logger is not None:
+            self.logger.end(what)
+
     def finish_simulation(self):
+        self._log_begin("finish_simulation!")
         if getattr(self, "h", None) is not None:
             self.lib.vb_sim_destroy(self.h)
             self.h = None
+        if getattr(self, "logger", None) is not None:
+            self.logger.end("finish_simulation!")
+            self.logger.close()
+            self.logger = None
 
     def __del__(self):
         try:
@@ -561,7 +615,9 @@ class Simulation:
         return self.cellid(name, self.random_pos(name, weights, rng))
 
     def finish_init(self):
+        self._log_begin("finish_init!")
         self._ck(self.lib.vb_finish_init(self.h))
+        self._log_end("finish_init!")
         return self
 
     # -- apply! (src/Simulation.jl:720-821) --
@@ -571,7 +627,9 @@ class Simulation:
         w, nw = self._refs(write)
         a, na = self._refs(add_existing)
         we = self._eid[with_edge] if with_edge is not None else -1
+        self._log_begin("apply!", func=transition, transition=(self.num_transitions() + 1) if self.logger is not None else 0)
         self._ck(self.lib.vb_apply(self.h, transition.encode(), c, nc, r, nr, w, nw, a, na, C.c_int(we), C.c_uint64(seed)))
+        self._log_end("apply!")
         return self
 
     def apply_copy(self, transition: str, call, read, write, **kwargs) -> "Simulation":
@@ -807,8 +865,10 @@ class Simulation:
 
 
 def create_simulation(model: Model, params: Optional[dict] = None, globals_: Optional[dict] = None,
-                      backend: Optional[Backend] = None, device: int = 0) -> Simulation:
-    return Simulation(model, params, globals_, backend, device)
+                      backend: Optional[Backend] = None, device: int = 0, logging: bool = False,
+                      log_path: Optional[str] = None) -> Simulation:
+    """create_simulation(model, params, globals; logging) (src/Simulation.jl:261-313); `logging` opens log/<name>_<rank>.log."""
+    return Simulation(model, params, globals_, backend, device, logging=logging, log_path=log_path)
 
 
 def apply(sim: Simulation, transition: str, call, read, write, **kwargs) -> Simulation:
