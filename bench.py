@@ -31,10 +31,28 @@ ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "libvahana_oracle.so")
 
 
 def measured_peaks():
+    """HBM roofline denominator: the driver-written MEASURED_PEAKS.json (the sustained figure when it has one — the sweeps are timed
+    inside a long step — else its HBM figure), else the fallback of B200_PROFILING.md."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    try:
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            d = json.load(f)
+        flat = {}
+
+        def walk(prefix, v):
+            if isinstance(v, dict):
+                for k, x in v.items():
+                    walk(prefix + "." + str(k).lower(), x)
+            elif isinstance(v, (int, float)) and not isinstance(v, bool):
+                flat[prefix] = float(v)
+        walk("", d)
+        hbm = {k: v for k, v in flat.items() if "hbm" in k and 1000.0 < v < 20000.0}     # GB/s figures only
+        for pick in (lambda k: "sust" in k, lambda k: k.endswith("hbm_gbs"), lambda k: True):
+            c = [k for k in hbm if pick(k)]
+            if c:
+                return hbm[sorted(c)[0]], "measured (MEASURED_PEAKS.json: %s)" % sorted(c)[0].lstrip(".")
+    except Exception:
+        pass
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
