@@ -298,7 +298,11 @@ def run_engine(args):
                    "parallelism": f"{world} GPU, contiguous equal blocks of agents, edges on the target's rank, NCCL halo of source states",
                    "halo_bytes_per_step_rank0": int(hb.value),
                    "l2": "inputs larger than L2 (source states 0.8 GB, CSR columns %.1f GB); no flush needed" % (4.0 * E / 1e9),
-                   "agent_updates_per_s": n * args.steps / (ms_total * 1e-3), "build_s": t_build, "opinion_sum": metric},
+                   "agent_updates_per_s": n * args.steps / (ms_total * 1e-3), "build_s": t_build, "opinion_sum": metric,
+                   "read_phase": ("prefiltered sweeps: every edge gathers the one-byte key of its source (opinion quantised to 1/256), the 8-byte state is "
+                                  "fetched where the key may pass; fold() always decides on the exact state, results identical to the unfiltered "
+                                  "sweeps (22.9 ms/step on one GPU, profiles/r1_bench_hk100m_v4.json; VB_PREFILTER=0 selects them)") if prefiltered
+                   else ("source-blocked sweeps" if sweeps else "direct gathers")},
         "roofline": {"bound": "hbm",
                      "kernel": ("build_keys_kernel<hk::Step> + reduce_prefilter_kernel<hk::Step> x %d key-block sweeps + transition_kernel<hk::Step, DIRECT, 256> (hub rows)" % sweeps)
                      if (sweeps and prefiltered) else
