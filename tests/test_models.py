@@ -41,6 +41,21 @@ def test_gol_gpu_vs_oracle(oracle, cuda):
     assert g.mapreduce("active", "+", "Cell", datatype="i8") == int(a.sum())
 
 
+@pytest.mark.gpu
+def test_gol_config2_full_size_vs_numpy(cuda):
+    """BASELINE config 2 at its named size (4096 x 4096 periodic Moore raster, B3/S23, density 0.35 from default_rng(2)): too large for
+    the oracle's explicit 134 M-edge containers, so the engine is compared with the independent numpy restatement that the oracle
+    matches at small sizes (test_gol_oracle_vs_numpy, tests/golden/gol_48x40.npz)."""
+    init = np.random.default_rng(2).random((4096, 4096)) < 0.35
+    sim = gol_sim(cuda, init)
+    a = init.copy()
+    for _ in range(5):
+        sim.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
+        a = _life_numpy(a)
+        assert np.array_equal(sim.rastervalues("grid", "active", "Cell"), a)
+    assert sim.mapreduce("active", "+", "Cell", datatype="i8") == int(a.sum())
+
+
 def _sir_counts(sim):
     s = sim.all_agents("Person")["state"]
     return [int((s == k).sum()) for k in range(3)]
