@@ -95,6 +95,32 @@ def test_sir_gpu_vs_oracle(oracle, cuda):
     assert _sir_counts(g)[2] > 0
 
 
+@pytest.mark.gpu
+def test_sir_config5_full_size_properties(cuda):
+    """BASELINE config 5 at its named size (5e7 persons x 5e6 locations, 2e8 edges rebuilt per step): far beyond the oracle's
+    containers, so the step is checked through size-independent properties: every person emits exactly two visits and receives exactly
+    two exposures, compartments are conserved, recoveries never decrease, and the locations' tallies add up to two visits per person
+    who was infectious when the step began."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~40 GB of free device memory")
+    n, nl = 50_000_000, 5_000_000
+    sim = sir_sim(cuda, n, nl, beta=0.3)
+    r_prev, i0 = 0, _sir_counts(sim)[1]
+    assert 0.009 * n < i0 < 0.011 * n                       # 1 % initially infectious
+    i = i0
+    for step in range(3):
+        i_before = i
+        sir_step(sim, step)
+        assert sim.num_edges("Visit") == 2 * n and sim.num_edges("Exposure") == 2 * n
+        s, i, r = _sir_counts(sim)
+        assert s + i + r == n and r >= r_prev and i >= i0    # nobody recovers before day 10
+        r_prev = r
+        assert sim.mapreduce("n_inf", "+", "Location") == 2 * i_before     # every infectious person made two infectious visits
+    assert i > i0                                            # beta = 0.3: the infection spreads
+
+
 # ---- predator / prey (BASELINE config 3) ----
 from models import pp_sim, pp_step, pp_globals, PP_EDGES  # noqa: E402
 
