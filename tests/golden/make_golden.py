@@ -23,6 +23,7 @@ HK = dict(n=2000, m=8, graph_seed=1, opinion_seed=1, steps=10)
 GOL = dict(shape=(48, 40), seed=2, density=0.35, generations=25)
 SIR = dict(n=3000, nl=250, beta=0.3, steps=12)
 PP = dict(dims=(30, 30), nprey=180, npred=45, steps=20)
+PP_DOCS = dict(dims=(100, 100), nprey=2000, npred=500, steps=400, every=25)      # BASELINE config 3 (a): the docs model at the docs size
 
 
 def hk_numpy(n, uv, op, eps, steps):
@@ -94,6 +95,14 @@ def main():
         g = pp_globals(sim)
         traj.append([g["prey_pop"], g["predator_pop"], g["cells_with_food"], g["prey_energy"], g["predator_energy"]])
     np.savez_compressed(os.path.join(HERE, "pp_30x30.npz"), trajectory=np.array(traj, dtype=np.int64), digest=np.array(pp_digest(sim)))
+    sim = pp_sim(ob, PP_DOCS["dims"], PP_DOCS["nprey"], PP_DOCS["npred"])
+    traj = []
+    for step in range(PP_DOCS["steps"]):
+        pp_step(sim, step)
+        if step % PP_DOCS["every"] == PP_DOCS["every"] - 1:
+            g = pp_globals(sim)
+            traj.append([step, g["prey_pop"], g["predator_pop"], g["cells_with_food"], g["prey_energy"], g["predator_energy"]])
+    np.savez_compressed(os.path.join(HERE, "pp_docs_100x100.npz"), trajectory=np.array(traj, dtype=np.int64), digest=np.array(pp_digest(sim)))
     print("golden fixtures written to", HERE)
 
 
