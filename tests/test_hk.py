@@ -348,3 +348,66 @@ def test_hk_config1_full_size_gpu_vs_oracle(oracle, cuda):
     go, oo = _opinions(g), _opinions(o)
     assert abs(go.mean() - oo.mean()) < 1e-9 and abs(go.var() - oo.var()) < 1e-9
     assert g.last_apply_stats()["edges_read"] == 1_699_872
+
+
+# ---- random multigraphs: duplicate edges, self loops, agents without any edge (mean of nothing = NaN, as in Julia) ---------------------
+def _random_multigraph(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 400))
+    ne = int(rng.integers(0, 6 * n))
+    fr = rng.integers(0, n, ne)
+    to = rng.integers(0, n, ne)
+    if ne:
+        dup = rng.integers(0, ne, ne // 5)
+        fr = np.concatenate([fr, fr[dup]])                       # parallel edges
+        to = np.concatenate([to, to[dup]])
+    to[rng.random(len(to)) < 0.1] = int(rng.integers(0, n))      # one hub target
+    op0 = rng.random(n)
+    op0[rng.random(n) < 0.2] = float(rng.random())               # many exactly equal opinions (differences of exactly 0)
+    eps = float(rng.choice([0.0, 0.02, 0.1, 0.5, 2.0]))
+    return n, fr.astype(np.int64), to.astype(np.int64), op0, eps
+
+
+def _hk_numpy_edges(n, fr, to, op, eps, steps):
+    order = np.argsort(to, kind="stable")                        # per-target order = add order
+    fr, to = fr[order], to[order]
+    for _ in range(steps):
+        v = op[fr]
+        m = np.abs(v - op[to]) < eps
+        with np.errstate(invalid="ignore", divide="ignore"):
+            op = np.bincount(to[m], weights=v[m], minlength=n) / np.bincount(to[m], minlength=n)
+    return op
+
+
+def _multigraph_sim(backend, n, fr, to, op0, eps):
+    from models import hk_model
+    sim = vh.create_simulation(hk_model(), params={"eps": eps}, backend=backend)
+    ids = sim.add_agents("HKAgent", op0.view([("opinion", "f8")]))
+    if len(fr):
+        sim.add_edges(ids[fr], ids[to], "Knows")
+    sim.finish_init()
+    return sim
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_hk_random_multigraph_oracle_vs_numpy(oracle, seed):
+    n, fr, to, op0, eps = _random_multigraph(seed)
+    sim = _multigraph_sim(oracle, n, fr, to, op0, eps)
+    assert sim.num_edges("Knows") == len(fr)
+    for _ in range(3):
+        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+    np.testing.assert_array_equal(_opinions(sim), _hk_numpy_edges(n, fr, to, op0, eps, 3))       # bit-exact, NaN where nothing is accepted
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(25))
+def test_hk_random_multigraph_gpu_vs_oracle(oracle, cuda, seed):
+    n, fr, to, op0, eps = _random_multigraph(seed)
+    g = _multigraph_sim(cuda, n, fr, to, op0, eps)
+    o = _multigraph_sim(oracle, n, fr, to, op0, eps)
+    if seed % 2:
+        g.set_read_blocking(0.0005, 0.0, 1)                      # odd seeds through the (prefiltered) sweeps, even seeds direct
+    for _ in range(3):
+        g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        np.testing.assert_allclose(_opinions(g), _opinions(o), rtol=RTOL, atol=0, equal_nan=True)
