@@ -298,116 +298,3 @@ def test_hk_mortal_agents_blocked_vs_oracle(oracle, cuda, blocked, prefilter):
     goff, gfrom, _ = g.export_csr("Knows", "HKAgent", n)
     ooff, ofrom, _ = o.export_csr("Knows", "HKAgent", n)
     assert np.array_equal(goff, ooff) and np.array_equal(gfrom, ofrom)
-
-
-# ---- BASELINE config 1 at its named size: 100k-agent Barabasi-Albert graph (m = 8, seed 1), 50 steps ----------------------------------
-def _config1():
-    n = 100_000
-    uv = ba_graph(n, 8, 1)
-    op0 = np.random.default_rng(1).random(n)
-    return n, uv, op0
-
-
-def _hk_numpy_vectorised(n, uv, op, eps, steps):
-    """The same step on flat arrays: edges in add order (u->v, v->u per graph edge, then the self loops), stable-sorted by target, so
-    np.bincount adds a row's accepted opinions left to right exactly like the reference's filter + mean."""
-    fr = np.concatenate([np.stack([uv[:, 0], uv[:, 1]], axis=1).reshape(-1), np.arange(n)])
-    to = np.concatenate([np.stack([uv[:, 1], uv[:, 0]], axis=1).reshape(-1), np.arange(n)])
-    order = np.argsort(to, kind="stable")
-    fr, to = fr[order], to[order]
-    for _ in range(steps):
-        v = op[fr]
-        m = np.abs(v - op[to]) < eps
-        op = np.bincount(to[m], weights=v[m], minlength=n) / np.bincount(to[m], minlength=n)
-    return op
-
-
-def test_hk_config1_full_size_oracle_vs_numpy(oracle):
-    n, uv, op0 = _config1()
-    assert len(uv) == 799_936                                   # SURVEY.md §8(d): E = 2 * 799 936 + 100 000 = 1 699 872
-    sim, _ = hk_sim(oracle, n, uv, op0, 0.02)
-    assert sim.num_edges("Knows") == 1_699_872
-    for _ in range(50):
-        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-    np.testing.assert_array_equal(_opinions(sim), _hk_numpy_vectorised(n, uv, op0, 0.02, 50))     # same order of additions: bit-exact
-
-
-@pytest.mark.gpu
-def test_hk_config1_full_size_gpu_vs_oracle(oracle, cuda):
-    """50 chained steps: compared every step; a handful of agents may drift apart if a 1-ulp difference ever flips an acceptance
-    (SURVEY.md A-36), the bulk must stay within the tolerance and the trajectory statistics must agree."""
-    n, uv, op0 = _config1()
-    g, _ = hk_sim(cuda, n, uv, op0, 0.02)
-    o, _ = hk_sim(oracle, n, uv, op0, 0.02)
-    for step in range(50):
-        g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-        o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-        if step % 7 == 0 or step == 49:
-            close = np.isclose(_opinions(g), _opinions(o), rtol=1e-10, atol=0)
-            assert close.mean() > 0.9999, (step, int((~close).sum()))
-    go, oo = _opinions(g), _opinions(o)
-    assert abs(go.mean() - oo.mean()) < 1e-9 and abs(go.var() - oo.var()) < 1e-9
-    assert g.last_apply_stats()["edges_read"] == 1_699_872
-
-
-# ---- random multigraphs: duplicate edges, self loops, agents without any edge (mean of nothing = NaN, as in Julia) ---------------------
-def _random_multigraph(seed):
-    rng = np.random.default_rng(seed)
-    n = int(rng.integers(2, 400))
-    ne = int(rng.integers(0, 6 * n))
-    fr = rng.integers(0, n, ne)
-    to = rng.integers(0, n, ne)
-    if ne:
-        dup = rng.integers(0, ne, ne // 5)
-        fr = np.concatenate([fr, fr[dup]])                       # parallel edges
-        to = np.concatenate([to, to[dup]])
-    to[rng.random(len(to)) < 0.1] = int(rng.integers(0, n))      # one hub target
-    op0 = rng.random(n)
-    op0[rng.random(n) < 0.2] = float(rng.random())               # many exactly equal opinions (differences of exactly 0)
-    eps = float(rng.choice([0.0, 0.02, 0.1, 0.5, 2.0]))
-    return n, fr.astype(np.int64), to.astype(np.int64), op0, eps
-
-
-def _hk_numpy_edges(n, fr, to, op, eps, steps):
-    order = np.argsort(to, kind="stable")                        # per-target order = add order
-    fr, to = fr[order], to[order]
-    for _ in range(steps):
-        v = op[fr]
-        m = np.abs(v - op[to]) < eps
-        with np.errstate(invalid="ignore", divide="ignore"):
-            op = np.bincount(to[m], weights=v[m], minlength=n) / np.bincount(to[m], minlength=n)
-    return op
-
-
-def _multigraph_sim(backend, n, fr, to, op0, eps):
-    from models import hk_model
-    sim = vh.create_simulation(hk_model(), params={"eps": eps}, backend=backend)
-    ids = sim.add_agents("HKAgent", op0.view([("opinion", "f8")]))
-    if len(fr):
-        sim.add_edges(ids[fr], ids[to], "Knows")
-    sim.finish_init()
-    return sim
-
-
-@pytest.mark.parametrize("seed", range(25))
-def test_hk_random_multigraph_oracle_vs_numpy(oracle, seed):
-    n, fr, to, op0, eps = _random_multigraph(seed)
-    sim = _multigraph_sim(oracle, n, fr, to, op0, eps)
-    assert sim.num_edges("Knows") == len(fr)
-    for _ in range(3):
-        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-    np.testing.assert_array_equal(_opinions(sim), _hk_numpy_edges(n, fr, to, op0, eps, 3))       # bit-exact, NaN where nothing is accepted
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("seed", range(25))
-def test_hk_random_multigraph_gpu_vs_oracle(oracle, cuda, seed):
-    n, fr, to, op0, eps = _random_multigraph(seed)
-    g = _multigraph_sim(cuda, n, fr, to, op0, eps)
-    o = _multigraph_sim(oracle, n, fr, to, op0, eps)
-    if seed % 2:
-        g.set_read_blocking(0.0005, 0.0, 1)                      # odd seeds through the (prefiltered) sweeps, even seeds direct
-    for _ in range(3):
-        g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-        o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-        np.testing.assert_allclose(_opinions(g), _opinions(o), rtol=RTOL, atol=0, equal_nan=True)

@@ -41,21 +41,6 @@ def test_gol_gpu_vs_oracle(oracle, cuda):
     assert g.mapreduce("active", "+", "Cell", datatype="i8") == int(a.sum())
 
 
-@pytest.mark.gpu
-def test_gol_config2_full_size_vs_numpy(cuda):
-    """BASELINE config 2 at its named size (4096 x 4096 periodic Moore raster, B3/S23, density 0.35 from default_rng(2)): too large for
-    the oracle's explicit 134 M-edge containers, so the engine is compared with the independent numpy restatement that the oracle
-    matches at small sizes (test_gol_oracle_vs_numpy, tests/golden/gol_48x40.npz)."""
-    init = np.random.default_rng(2).random((4096, 4096)) < 0.35
-    sim = gol_sim(cuda, init)
-    a = init.copy()
-    for _ in range(5):
-        sim.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
-        a = _life_numpy(a)
-        assert np.array_equal(sim.rastervalues("grid", "active", "Cell"), a)
-    assert sim.mapreduce("active", "+", "Cell", datatype="i8") == int(a.sum())
-
-
 def _sir_counts(sim):
     s = sim.all_agents("Person")["state"]
     return [int((s == k).sum()) for k in range(3)]
@@ -93,32 +78,6 @@ def test_sir_gpu_vs_oracle(oracle, cuda):
             assert np.array_equal(a[2].view("u1"), b[2].view("u1"))   # edge states bit-exact (incl. the Float32 risk)
     assert _sir_counts(g) == _sir_counts(o)
     assert _sir_counts(g)[2] > 0
-
-
-@pytest.mark.gpu
-def test_sir_config5_full_size_properties(cuda):
-    """BASELINE config 5 at its named size (5e7 persons x 5e6 locations, 2e8 edges rebuilt per step): far beyond the oracle's
-    containers, so the step is checked through size-independent properties: every person emits exactly two visits and receives exactly
-    two exposures, compartments are conserved, recoveries never decrease, and the locations' tallies add up to two visits per person
-    who was infectious when the step began."""
-    import torch
-    free, _ = torch.cuda.mem_get_info()
-    if free < 60e9:
-        pytest.skip("needs ~40 GB of free device memory")
-    n, nl = 50_000_000, 5_000_000
-    sim = sir_sim(cuda, n, nl, beta=0.3)
-    r_prev, i0 = 0, _sir_counts(sim)[1]
-    assert 0.009 * n < i0 < 0.011 * n                       # 1 % initially infectious
-    i = i0
-    for step in range(3):
-        i_before = i
-        sir_step(sim, step)
-        assert sim.num_edges("Visit") == 2 * n and sim.num_edges("Exposure") == 2 * n
-        s, i, r = _sir_counts(sim)
-        assert s + i + r == n and r >= r_prev and i >= i0    # nobody recovers before day 10
-        r_prev = r
-        assert sim.mapreduce("n_inf", "+", "Location") == 2 * i_before     # every infectious person made two infectious visits
-    assert i > i0                                            # beta = 0.3: the infection spreads
 
 
 # ---- predator / prey (BASELINE config 3) ----

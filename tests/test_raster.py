@@ -124,19 +124,3 @@ def test_implicit_stencil_row_order_matches_oracle(oracle, cuda, dims, kw):
     g.add_edge(int(ids[0]), int(ids[1]), "GridE"); o.add_edge(int(ids[0]), int(ids[1]), "GridE")
     a, b = g.export_csr("GridE", "GridA", n), o.export_csr("GridE", "GridA", n)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-
-
-def test_random_pos_one_hot_weights(backend):  # test/raster.jl:438-459 ("MoveTo_Dist": the only pinned use of StatsBase.sample)
-    sim = vh.create_simulation(raster_model(), backend=backend)
-    sim.add_raster("raster", (10, 20, 30), "Grid3D", lambda p: (p, True))
-    sim.finish_init()
-    w = np.zeros((10, 20, 30))
-    w[6, 18, 22] = 1.0                                    # Julia's w[7, 19, 23]
-    assert sim.random_pos("raster", w) == (7, 19, 23)
-    sim.disable_transition_checks(True)
-    assert tuple(sim.agentstate(sim.random_cell("raster", w), "Grid3D")["pos"]) == (7, 19, 23)
-    sim.disable_transition_checks(False)
-    p = sim.random_pos("raster", rng=np.random.default_rng(0))   # unweighted: any position of the raster
-    assert all(1 <= p[k] <= d for k, d in enumerate((10, 20, 30)))
-    with pytest.raises(AssertionError):
-        sim.random_pos("raster", np.zeros((10, 20)))
