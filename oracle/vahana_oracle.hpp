@@ -7,12 +7,15 @@
 // load the library built from this file.  The product (vahana.jl_b200/csrc) never includes,
 // links or calls it.
 //
-// Parity status: pinned against the reference's own known-answer tests (tests/test_oracle_*.py
-// restate test/core.jl, test/edges.jl, test/edgesiterator.jl, test/remove_agents.jl,
-// test/addexisting.jl, test/independent.jl, test/raster.jl, test/graphs.jl).  The model-level
-// outputs of the BASELINE configs (Hegselmann-Krause opinions, Game of Life, predator/prey,
-// SIR) are NOT pinned by any reference test and Julia cannot run here: "parity unpinned" for
-// those — oracle-vs-GPU comparison only.
+// Parity status: pinned against the reference's own known-answer tests, restated with the reference's values in
+// tests/test_core.py (test/core.jl), test_edges.py (test/edges.jl), test_lifecycle.py (test/remove_agents.jl,
+// test/addexisting.jl, test/independent.jl, test/graphs.jl, test/edgesiterator.jl), test_raster.py (test/raster.jl),
+// test_remove_edges.py (test/mpi/test_edgetypes.jl, single rank), test_zx_misc.py (test/globals.jl,
+// test/parametric_types.jl) and test_zy_full_size.py (random_pos, test/raster.jl:438-459).  The model-level outputs of the
+// BASELINE configs (Hegselmann-Krause opinions, Game of Life, predator/prey, SIR) are NOT pinned by any reference test and
+// Julia cannot run here: "parity unpinned" for those.  What stands in: independent numpy restatements that this
+// oracle matches bit for bit (HK at config 1's full size and on random multigraphs, Game of Life) and the committed fixtures of
+// tests/golden/ (oracle outputs, written by tests/golden/make_golden.py).
 //
 // Each function cites the reference lines it follows (paths relative to /root/reference).
 #pragma once
