@@ -91,6 +91,9 @@ struct EdgeView {
     uint64_t* rlog_to; uint64_t* rlog_from; uint8_t* rlog_st; uint32_t* rlog_dst; uint32_t rlog_cap;
     // remove_edges! records of the running apply: (row, source composite or 0xffffffff = all, append position at call time)
     uint32_t* rm_row; uint32_t* rm_from; uint32_t* rm_mark;
+    // multi-GPU: a record whose target lives on another rank keeps its AgentIDs here (rm_to64 = 0 marks a local record) and is
+    // exchanged after the transition loop (removeedges_alltoall!, src/MPI.jl:432-479); nullptr on one rank
+    uint64_t* rm_to64; uint64_t* rm_from64;
     uint32_t size, word, ncols;
     int32_t target;           // :SingleType target type id, else 0
     uint8_t hints, kind, readable, writeable;
@@ -687,10 +690,14 @@ class Ctx {
         uint32_t row = 0xffffffffu, fcomp = 0xffffffffu;
         const uint32_t tt = type_nr(to);
         const uint64_t tnr = agent_nr(to);
-        if (process_nr(to) != ds.rank) fail(DERR_REMOTE);
+        const bool remote = process_nr(to) != ds.rank;
+        if (remote) {   // queued for the target's rank (EdgeMethods.jl:531-532,547-548,559-560): the record stays inert here
+            if (!ev.rm_to64) fail(DERR_REMOTE);
+        }
         else if (tt >= 1 && tt <= ds.n_agent_types && tnr >= 1 && tnr <= ds.agents[tt].lcap && (!ev.target || (int)tt == ev.target))
             row = (ev.target ? 0u : ds.base[tt]) + (uint32_t)(tnr - 1);
-        if (has_from && !comp_of(from, fcomp)) row = 0xffffffffu;       // an id that names nobody matches no entry
+        if (!remote && has_from && !comp_of(from, fcomp)) row = 0xffffffffu;       // an id that names nobody matches no entry
+        if (ev.rm_to64) { ev.rm_to64[pos] = remote ? to : 0ull; ev.rm_from64[pos] = (remote && has_from) ? from : 0ull; }
         const int w = F::EdgeWrites::find(e);
         ev.rm_row[pos] = row;
         ev.rm_from[pos] = has_from ? fcomp : 0xffffffffu;

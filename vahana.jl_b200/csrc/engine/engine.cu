@@ -208,6 +208,58 @@ __global__ void count_adds_kernel(const uint32_t* __restrict__ rows, uint64_t n,
     if (i >= n) return;
     if (flag) cnt[rows[i]] = 1u; else atomicAdd(&cnt[rows[i]], 1u);
 }
+// remove_edges! records that arrived from other ranks (removeedges_alltoall!, src/MPI.jl:462-470: every received (source | 0, target)
+// is applied with the ordinary local remove_edges!) -> records of the local remove log.  An id that names nobody on this rank
+// (unknown type / slot, a remote source this rank never mirrored, a :SingleType mismatch) matches no entry: row = 0xffffffff.
+struct TranslateRmArgs {
+    const uint64_t* to; const uint64_t* from; uint32_t n;
+    uint32_t* rm_row; uint32_t* rm_from; uint32_t* rm_mark; uint64_t* rm_to64; uint64_t* rm_from64; uint32_t pos0; uint32_t mark;
+    uint32_t base[vb::MAX_AGENT_TYPES + 2]; uint32_t lcap[vb::MAX_AGENT_TYPES + 1]; uint32_t nghost[vb::MAX_AGENT_TYPES + 1];
+    const uint64_t* ghost_ids[vb::MAX_AGENT_TYPES + 1];
+    uint32_t ntypes; int32_t target; uint32_t rank;
+};
+__global__ void translate_removes_kernel(const TranslateRmArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint64_t to = a.to[i], fr = a.from[i];
+    const uint32_t tt = vb::type_nr(to);
+    const uint64_t tnr = vb::agent_nr(to);
+    uint32_t row = 0xffffffffu, fcomp = 0xffffffffu;
+    if (vb::process_nr(to) == a.rank && tt >= 1 && tt <= a.ntypes && tnr >= 1 && tnr <= a.lcap[tt] && (!a.target || (int)tt == a.target))
+        row = (a.target ? 0u : a.base[tt]) + (uint32_t)(tnr - 1);
+    if (fr) {
+        const uint32_t ft = vb::type_nr(fr);
+        const uint64_t fnr = vb::agent_nr(fr);
+        bool ok = ft >= 1 && ft <= a.ntypes && fnr >= 1;
+        if (ok && vb::process_nr(fr) != a.rank) {
+            uint32_t lo = 0, hi = a.nghost[ft];
+            const uint64_t* g = a.ghost_ids[ft];
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (g[mid] < fr) lo = mid + 1; else hi = mid; }
+            ok = lo < a.nghost[ft] && g[lo] == fr;
+            if (ok) fcomp = a.base[ft] + a.lcap[ft] + lo;
+        } else if (ok) {
+            ok = fnr <= a.lcap[ft];
+            if (ok) fcomp = a.base[ft] + (uint32_t)(fnr - 1);
+        }
+        if (!ok) row = 0xffffffffu;
+    }
+    const uint32_t p = a.pos0 + i;
+    a.rm_row[p] = row; a.rm_from[p] = fcomp; a.rm_mark[p] = a.mark;
+    if (a.rm_to64) { a.rm_to64[p] = 0ull; a.rm_from64[p] = 0ull; }
+}
+// records that travel: a target id was parked and names an existing rank (a target on a rank that does not exist matches nothing)
+__global__ void remote_remove_flags_kernel(const uint64_t* __restrict__ to, uint32_t n, uint32_t nranks, uint32_t* __restrict__ flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (to[i] != 0ull && vb::process_nr(to[i]) < nranks) ? 1u : 0u;
+}
+// compacts the flagged (to, from) pairs and notes the destination rank of each
+__global__ void compact_removes_kernel(const uint64_t* __restrict__ to, const uint64_t* __restrict__ from, const uint32_t* __restrict__ flag,
+                                       const uint32_t* __restrict__ pos, uint32_t n, uint64_t* __restrict__ oto, uint64_t* __restrict__ ofrom,
+                                       uint32_t* __restrict__ odst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    oto[pos[i]] = to[i]; ofrom[pos[i]] = from[i]; odst[pos[i]] = vb::process_nr(to[i]);
+}
 // keep only the last entry of every run of equal keys (:SingleEdge "overwrite the slot", EdgeMethods.jl:441-445);
 // flags a run whose entries differ (second add with another value asserts for Dict containers, :267-293)
 __global__ void last_of_run_flags_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ flag) {
@@ -561,6 +613,7 @@ __global__ void rebase_values_kernel(uint32_t* __restrict__ v, uint64_t n, const
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = v[i];
+    if (c == 0xffffffffu) return;   // "nobody" / "all" markers of the remove records
     uint32_t t = 1;
     while (t < a.ntypes && c >= a.old_base[t + 1]) ++t;
     uint32_t slot = c - a.old_base[t];
@@ -784,6 +837,7 @@ struct EdgeStore {
     uint32_t* wcnt = nullptr; uint32_t rows_w = 0;
     // remove_edges! records of the running apply
     uint32_t* rm_row = nullptr; uint32_t* rm_from = nullptr; uint32_t* rm_mark = nullptr; uint32_t rm_n = 0, rm_cap = 0;
+    uint64_t* rm_to64 = nullptr; uint64_t* rm_from64 = nullptr;   // multi-GPU: AgentIDs of the records that leave the rank (same positions)
     // connect_raster_neighbors! kept implicit (KIND_STENCIL on device) until something needs explicit rows
     bool implicit_stencil = false; int st_raster = -1; int st_metric = 0; double st_distance = 0; bool st_periodic = true;
     std::vector<int8_t> st_off_host; int8_t* st_off = nullptr; int st_n = 0; int st_reach = 0; uint32_t st_slot0 = 0;
@@ -877,6 +931,8 @@ struct vb_sim {
     void rebase(const uint32_t* old_base, const uint32_t* old_lcap = nullptr, const uint32_t* const* remap = nullptr);
     void exchange_ghost_requests();
     void transmit_edges(int e);
+    void transmit_removes(int e);
+    void ensure_rm(EdgeStore& e, uint64_t need);
     void upload_view(uint64_t seed);
     void check_device_error(const char* where);
     void flush_raw(int e);
@@ -916,9 +972,9 @@ void free_edge_read(EdgeStore& e) {
     e.off = e.src = e.cnt = nullptr; e.st = nullptr; e.nnz = e.st_cap = 0; e.rows = 0;
 }
 void free_edge_log(EdgeStore& e) {
-    dfree(e.log_to); dfree(e.log_from); dfree(e.log_st); dfree(e.wcnt); dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark);
+    dfree(e.log_to); dfree(e.log_from); dfree(e.log_st); dfree(e.wcnt); dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark); dfree(e.rm_to64); dfree(e.rm_from64);
     e.log_to = e.log_from = e.wcnt = nullptr; e.log_st = nullptr; e.log_n = e.log_cap = 0; e.rows_w = 0;
-    e.rm_row = e.rm_from = e.rm_mark = nullptr; e.rm_n = e.rm_cap = 0;
+    e.rm_row = e.rm_from = e.rm_mark = nullptr; e.rm_to64 = e.rm_from64 = nullptr; e.rm_n = e.rm_cap = 0;
     dfree(e.rlog_to); dfree(e.rlog_from); dfree(e.rlog_st); dfree(e.rlog_dst);
     e.rlog_to = e.rlog_from = nullptr; e.rlog_st = nullptr; e.rlog_dst = nullptr; e.rlog_n = e.rlog_cap = 0;
 }
@@ -1013,6 +1069,8 @@ void vb_sim::rebase(const uint32_t* old_base, const uint32_t* old_lcap, const ui
     for (auto& e : edges) {
         if (!same && e.src && e.nnz) { rebase_values_kernel<<<nblk(e.nnz), 256, 0, g_stream>>>(e.src, e.nnz, ra); LAUNCH_CHECK(); }
         if (!same && e.log_from && e.log_n) { rebase_values_kernel<<<nblk(e.log_n), 256, 0, g_stream>>>(e.log_from, e.log_n, ra); LAUNCH_CHECK(); }
+        if (!same && e.rm_from && e.rm_n) { rebase_values_kernel<<<nblk(e.rm_n), 256, 0, g_stream>>>(e.rm_from, e.rm_n, ra); LAUNCH_CHECK(); }
+        if (!same && !e.singletype && e.rm_row && e.rm_n) { rebase_values_kernel<<<nblk(e.rm_n), 256, 0, g_stream>>>(e.rm_row, e.rm_n, ra); LAUNCH_CHECK(); }
         const uint32_t nrows = rows_of(e);
         if (!e.singletype) {
             if (!same && e.log_to && e.log_n) { rebase_values_kernel<<<nblk(e.log_n), 256, 0, g_stream>>>(e.log_to, e.log_n, ra); LAUNCH_CHECK(); }
@@ -1082,7 +1140,7 @@ void vb_sim::upload_view(uint64_t seed) {
         vb::EdgeView& v = h.edges[i];
         v.off = e.off; v.src = e.src; v.st = e.st; v.cnt = e.cnt; v.rows = e.rows; v.st_cap = e.st_cap;
         v.log_to = e.log_to; v.log_from = e.log_from; v.log_st = e.log_st; v.wcnt = e.wcnt; v.log_cap = e.log_cap; v.rows_w = e.rows_w;
-        v.rm_row = e.rm_row; v.rm_from = e.rm_from; v.rm_mark = e.rm_mark;
+        v.rm_row = e.rm_row; v.rm_from = e.rm_from; v.rm_mark = e.rm_mark; v.rm_to64 = e.rm_to64; v.rm_from64 = e.rm_from64;
         v.rlog_to = e.rlog_to; v.rlog_from = e.rlog_from; v.rlog_st = e.rlog_st; v.rlog_dst = e.rlog_dst; v.rlog_cap = e.rlog_cap;
         v.size = e.size; v.word = e.word ? e.word : 1; v.ncols = e.ncols; v.target = e.singletype ? e.target : 0;
         v.hints = (uint8_t)e.hints; v.kind = e.implicit_stencil ? (uint8_t)vb::KIND_STENCIL : e.kind; v.readable = e.readable; v.writeable = e.writeable;
@@ -1134,7 +1192,7 @@ void vb_sim::check_device_error(const char* where) {
     if (err & vb::DERR_SINGLETYPE_MISMATCH) m += " :SingleType edge used with an agent of another type;";
     if (err & vb::DERR_RASTER_POS) m += " raster position out of range;";
     if (err & vb::DERR_INDEX) m += " neighbour index out of range;";
-    if (err & vb::DERR_REMOTE) m += " an edge was added to (or read for) an agent of another rank: edge redistribution is not implemented yet;";
+    if (err & vb::DERR_REMOTE) m += " the edges of an agent of another rank were read, or an edge of another rank was named outside of a transition (edges live on the rank of their target);";
     throw AssertionError(m);
 }
 
@@ -1625,6 +1683,124 @@ void vb_sim::exchange_ghost_requests() {
         dfree(req);
         a.halo_dirty = true;
     }
+}
+
+// room for `need` records in the remove log of `e` (on several ranks: plus the AgentID columns of the records that travel)
+void vb_sim::ensure_rm(EdgeStore& e, uint64_t need) {
+    const bool want64 = g_nranks > 1;
+    if (need <= e.rm_cap && (!want64 || e.rm_to64 || e.rm_cap == 0)) return;
+    if (need >= 0xffffffffull) throw ArgError("too many remove_edges! records in one apply");
+    const uint32_t ncap = need > e.rm_cap ? (uint32_t)std::max<uint64_t>(need, (uint64_t)e.rm_cap * 2 + 1024) : e.rm_cap;
+    uint32_t* nr = dalloc<uint32_t>(ncap); uint32_t* nf = dalloc<uint32_t>(ncap); uint32_t* nm = dalloc<uint32_t>(ncap);
+    uint64_t* nt64 = want64 ? dalloc<uint64_t>(ncap) : nullptr; uint64_t* nf64 = want64 ? dalloc<uint64_t>(ncap) : nullptr;
+    if (e.rm_n) {
+        CK(cudaMemcpyAsync(nr, e.rm_row, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+        CK(cudaMemcpyAsync(nf, e.rm_from, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+        CK(cudaMemcpyAsync(nm, e.rm_mark, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
+        if (want64) {
+            if (e.rm_to64) {
+                CK(cudaMemcpyAsync(nt64, e.rm_to64, (size_t)e.rm_n * 8, cudaMemcpyDeviceToDevice, g_stream));
+                CK(cudaMemcpyAsync(nf64, e.rm_from64, (size_t)e.rm_n * 8, cudaMemcpyDeviceToDevice, g_stream));
+            } else {   // records written before the columns existed are local ones
+                CK(cudaMemsetAsync(nt64, 0, (size_t)e.rm_n * 8, g_stream));
+                CK(cudaMemsetAsync(nf64, 0, (size_t)e.rm_n * 8, g_stream));
+            }
+        }
+    }
+    dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark); dfree(e.rm_to64); dfree(e.rm_from64);
+    e.rm_row = nr; e.rm_from = nf; e.rm_mark = nm; e.rm_to64 = nt64; e.rm_from64 = nf64; e.rm_cap = ncap;
+}
+
+// transmit_remove_edges! / removeedges_alltoall! (src/MPI.jl:432-479, called at src/Simulation.jl:792-795): the remove_edges! calls of
+// this apply whose target lives on another rank were parked as AgentID pairs (from | 0, to) beside the local records.  They are
+// bucketed by destination rank (stable), exchanged with grouped ncclSend/ncclRecv (all-to-all-v) and become ordinary records of
+// the receiver's remove log.  The reference applies them with the local remove_edges! after the transition loop and before
+// transmit_edges!: a received record sees the existing entries and *every* local add of this apply, none of the edges that
+// arrive afterwards -> mark = length of the local append log now.  Collective.
+void vb_sim::transmit_removes(int ei) {
+    EdgeStore& e = E(ei);
+    const uint32_t P = (uint32_t)g_nranks, n = e.rm_to64 ? e.rm_n : 0u;
+    std::vector<uint32_t> scnt(P + 1, 0);
+    uint64_t* sto = nullptr; uint64_t* sfrom = nullptr;
+    uint32_t nsend = 0;
+    if (n) {
+        uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
+        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+        remote_remove_flags_kernel<<<nblk(n), 256, 0, g_stream>>>(e.rm_to64, n, P, flag); LAUNCH_CHECK();
+        vbp::exclusive_scan(flag, pos, n, d_scalars, scr, g_stream); g_launches += 3;
+        CK(cudaMemcpyAsync(&nsend, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (nsend) {
+            uint64_t* cto = dalloc<uint64_t>(nsend); uint64_t* cfrom = dalloc<uint64_t>(nsend); uint32_t* cdst = dalloc<uint32_t>(nsend);
+            compact_removes_kernel<<<nblk(n), 256, 0, g_stream>>>(e.rm_to64, e.rm_from64, flag, pos, n, cto, cfrom, cdst); LAUNCH_CHECK();
+            uint32_t* perm = dalloc<uint32_t>(nsend); uint32_t* k1 = dalloc<uint32_t>(nsend); uint32_t* p1 = dalloc<uint32_t>(nsend);
+            vbp::iota_u32_kernel<<<nblk(nsend), 256, 0, g_stream>>>(perm, nsend); LAUNCH_CHECK();
+            uint32_t* scratch = dalloc<uint32_t>(vbp::rs_scratch_words(nsend));
+            const int res = vbp::radix_sort(cdst, k1, perm, p1, nullptr, nullptr, 0, nsend, vbp::bits_for(P), scratch, g_stream);
+            CK(cudaGetLastError());
+            dfree(scratch);
+            const uint32_t* sdst = res ? k1 : cdst; const uint32_t* sperm = res ? p1 : perm;
+            uint32_t* dc = dalloc<uint32_t>(P + 2);
+            CK(cudaMemsetAsync(dc, 0, (P + 2) * 4, g_stream));
+            vbp::csr_run_counts_kernel<<<nblk(nsend), 256, 0, g_stream>>>(sdst, nsend, dc); LAUNCH_CHECK();
+            CK(cudaMemcpyAsync(scnt.data(), dc, P * 4, cudaMemcpyDeviceToHost, g_stream));
+            sto = dalloc<uint64_t>(nsend); sfrom = dalloc<uint64_t>(nsend);
+            gather_u64_kernel<<<nblk(nsend), 256, 0, g_stream>>>(cto, sperm, nsend, sto); LAUNCH_CHECK();
+            gather_u64_kernel<<<nblk(nsend), 256, 0, g_stream>>>(cfrom, sperm, nsend, sfrom); LAUNCH_CHECK();
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(cto); dfree(cfrom); dfree(cdst); dfree(perm); dfree(k1); dfree(p1); dfree(dc);
+        }
+        dfree(flag); dfree(pos); dfree(scr);
+    }
+    // counts: everybody learns the whole P x P matrix
+    uint32_t* dcnt = dalloc<uint32_t>(P); uint32_t* dall = dalloc<uint32_t>((size_t)P * P);
+    std::vector<uint32_t> all((size_t)P * P);
+    CK(cudaMemcpyAsync(dcnt, scnt.data(), P * 4, cudaMemcpyHostToDevice, g_stream));
+    NK(g_nccl.AllGather(dcnt, dall, (size_t)P * 4, ncclUint8, g_comm, g_stream));
+    CK(cudaMemcpyAsync(all.data(), dall, all.size() * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(dcnt); dfree(dall);
+    std::vector<uint32_t> soff(P + 1, 0), roff(P + 1, 0);
+    for (uint32_t r = 0; r < P; ++r) { soff[r + 1] = soff[r] + scnt[r]; roff[r + 1] = roff[r] + (r == rank ? 0u : all[(size_t)r * P + rank]); }
+    const uint32_t nrecv = roff[P];
+    uint64_t total = 0;
+    for (uint32_t v : all) total += v;
+    if (total) {
+        uint64_t* rto = dalloc<uint64_t>(std::max<uint32_t>(nrecv, 1)); uint64_t* rfrom = dalloc<uint64_t>(std::max<uint32_t>(nrecv, 1));
+        NK(g_nccl.GroupStart());
+        for (uint32_t r = 0; r < P; ++r) {
+            if (r == rank) continue;
+            const uint32_t give = scnt[r], want = roff[r + 1] - roff[r];
+            if (give) {
+                NK(g_nccl.Send(sto + soff[r], (size_t)give * 8, ncclUint8, (int)r, g_comm, g_stream));
+                NK(g_nccl.Send(sfrom + soff[r], (size_t)give * 8, ncclUint8, (int)r, g_comm, g_stream));
+            }
+            if (want) {
+                NK(g_nccl.Recv(rto + roff[r], (size_t)want * 8, ncclUint8, (int)r, g_comm, g_stream));
+                NK(g_nccl.Recv(rfrom + roff[r], (size_t)want * 8, ncclUint8, (int)r, g_comm, g_stream));
+            }
+        }
+        NK(g_nccl.GroupEnd());
+        CK(cudaStreamSynchronize(g_stream));
+        halo_bytes += (uint64_t)nrecv * 16;
+        if (nrecv) {
+            ensure_rm(e, (uint64_t)e.rm_n + nrecv);
+            TranslateRmArgs ta{};
+            ta.to = rto; ta.from = rfrom; ta.n = nrecv;
+            ta.rm_row = e.rm_row; ta.rm_from = e.rm_from; ta.rm_mark = e.rm_mark; ta.rm_to64 = e.rm_to64; ta.rm_from64 = e.rm_from64;
+            ta.pos0 = e.rm_n; ta.mark = (e.kind == vb::KIND_CSR || e.ordered_log) ? e.log_n : 0u;
+            std::memcpy(ta.base, base, sizeof(ta.base));
+            for (size_t t = 1; t <= agents.size(); ++t) {
+                ta.lcap[t] = agents[t - 1].cap; ta.nghost[t] = agents[t - 1].nghost; ta.ghost_ids[t] = agents[t - 1].ghost_ids;
+            }
+            ta.ntypes = (uint32_t)agents.size(); ta.target = e.singletype ? e.target : 0; ta.rank = rank;
+            translate_removes_kernel<<<nblk(nrecv), 256, 0, g_stream>>>(ta); LAUNCH_CHECK();
+            e.rm_n += nrecv;
+            CK(cudaStreamSynchronize(g_stream));
+        }
+        dfree(rto); dfree(rfrom);
+    }
+    dfree(sto); dfree(sfrom);
 }
 
 // transmit_edges! (src/EdgeMethods.jl:686-689, edges_alltoall! src/MPI.jl:353-430): the appended edges that belong to another rank are
@@ -2239,18 +2415,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             for (int i = 0; i < ti->n_edge_removes; ++i) {
                 EdgeStore& e = s.E(ti->edge_removes[i]);
                 la.rbase[i] = e.rm_n; la.rmark[i] = e.log_n;
-                const uint64_t need = (uint64_t)e.rm_n + totals[RM0 + i];
-                if (need > e.rm_cap) {
-                    const uint32_t ncap = (uint32_t)std::max<uint64_t>(need, (uint64_t)e.rm_cap * 2 + 1024);
-                    uint32_t* nr = dalloc<uint32_t>(ncap); uint32_t* nf = dalloc<uint32_t>(ncap); uint32_t* nm = dalloc<uint32_t>(ncap);
-                    if (e.rm_n) {
-                        CK(cudaMemcpyAsync(nr, e.rm_row, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
-                        CK(cudaMemcpyAsync(nf, e.rm_from, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
-                        CK(cudaMemcpyAsync(nm, e.rm_mark, (size_t)e.rm_n * 4, cudaMemcpyDeviceToDevice, g_stream));
-                    }
-                    dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark);
-                    e.rm_row = nr; e.rm_from = nf; e.rm_mark = nm; e.rm_cap = ncap;
-                }
+                s.ensure_rm(e, (uint64_t)e.rm_n + totals[RM0 + i]);
             }
             s.upload_view(seed);
             la.mode = vb::MODE_EMIT;
@@ -2392,8 +2557,16 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     CK(cudaEventRecord(s.ev[1], g_stream));
     g_trace.end("transition loop", tname);
     s.check_device_error("apply!");
-    if (g_nranks > 1)   // transmit_edges! for every writable edge type (Simulation.jl:800), collective
+    if (g_nranks > 1) {
+        // transmit_remove_edges! (Simulation.jl:792-795) before transmit_edges! (:800).  Collective; every rank runs the same
+        // transition, so all of them agree on the edge types whose removes have to travel.
+        for (int w : write) if (w >= vb::EDGE_REF) {
+            bool removes = false;
+            for (auto* ti : tis) for (int i = 0; i < ti->n_edge_removes; ++i) removes |= ti->edge_removes[i] == w - vb::EDGE_REF;
+            if (removes) s.transmit_removes(w - vb::EDGE_REF);
+        }
         for (int w : write) if (w >= vb::EDGE_REF) s.transmit_edges(w - vb::EDGE_REF);
+    }
 
     // ---- finish_write! agents (Simulation.jl:807), then edges (:809), then the dead-agent purge ----
     std::vector<uint32_t*> died_flags(s.agents.size() + 1, nullptr);
@@ -2630,7 +2803,7 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
             f.log_to = f.log_from = f.wcnt = nullptr; f.log_st = nullptr; f.log_n = f.log_cap = 0; f.rows_w = 0;
             f.st_off = (int8_t*)dup(e.st_off, e.st_off_host.size());
             f.rlog_to = f.rlog_from = nullptr; f.rlog_st = nullptr; f.rlog_dst = nullptr; f.rlog_n = f.rlog_cap = 0;
-            f.rm_row = f.rm_from = f.rm_mark = nullptr; f.rm_n = f.rm_cap = 0; f.heavy_rows = nullptr; f.heavy_n = 0; f.heavy_version = ~0ull;
+            f.rm_row = f.rm_from = f.rm_mark = nullptr; f.rm_to64 = f.rm_from64 = nullptr; f.rm_n = f.rm_cap = 0; f.heavy_rows = nullptr; f.heavy_n = 0; f.heavy_version = ~0ull;
             f.blk = EdgeStore::Blocked{};
             for (auto& c : e.chunks) {
                 RawChunk d; d.n = c.n;
@@ -2801,7 +2974,7 @@ int vb_remove_edges(vb_sim* s, int ei, vb_agent_id from, vb_agent_id to) {
             if (ft < 1 || ft > s->agents.size() || fnr < 1 || fnr > s->agents[ft - 1].cap) return;
             rec[1] = s->base[ft] + (uint32_t)(fnr - 1);
         }
-        dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark);
+        dfree(e.rm_row); dfree(e.rm_from); dfree(e.rm_mark); dfree(e.rm_to64); dfree(e.rm_from64); e.rm_to64 = e.rm_from64 = nullptr;
         e.rm_row = dalloc<uint32_t>(1); e.rm_from = dalloc<uint32_t>(1); e.rm_mark = dalloc<uint32_t>(1); e.rm_cap = 1; e.rm_n = 1;
         CK(cudaMemcpyAsync(e.rm_row, &rec[0], 4, cudaMemcpyHostToDevice, g_stream));
         CK(cudaMemcpyAsync(e.rm_from, &rec[1], 4, cudaMemcpyHostToDevice, g_stream));
