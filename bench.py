@@ -114,7 +114,7 @@ def build_oracle_sim(vh, n):
     sim = vh.create_simulation(hk_model(), params={"eps": EPS}, backend=ob)
     sim.add_agents("HKAgent", op.view([("opinion", "f8")]))
     sim.add_edges(fr, to, "Knows")
-    sim.finish_init()
+    sim.finish_init(distribute=False)   # SPMD initialisation: every rank generated its own block on the device
     return sim, int(ne.value)
 
 
@@ -198,7 +198,7 @@ def run_engine(args):
     ne = C.c_uint64()
     be.check(lib.vbw_hk_powerlaw_build_sharded(sim.h, 1, 0, C.c_uint64(n), C.c_uint64(SEED_GRAPH), C.c_uint64(SEED_OPINION), C.c_double(C_PARETO),
                                                C.c_uint32(DMAX), C.c_uint64(1 << 22), C.c_uint32(rank), C.c_uint32(world), C.byref(ne)))
-    sim.finish_init()
+    sim.finish_init(distribute=False)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     E_local = int(ne.value)

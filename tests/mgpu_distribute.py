@@ -1,0 +1,64 @@
+"""Multi-GPU script (torchrun): finish_init!(distribute = true, partition_algo = :EqualAgentNumbers) (src/Simulation.jl:403-476,
+distribute! src/MPI.jl:11-84).  Every rank runs the same initialisation code (the docs' Hegselmann-Krause model on a
+Barabasi-Albert graph, BASELINE config 1 at a fifth of its size); finish_init hands rank 0's graph out, and the sharded run must
+follow the single-rank oracle on the same graph.  Written after round 1's GPU budget was spent: not run on GPUs yet."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import vahana_b200 as vh  # noqa: E402
+from models import hk_model, hk_sim, ba_graph  # noqa: E402
+
+
+def main():
+    n = int(os.environ.get("MGPU_N", "20000"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    be = vh.default_backend()
+    be.init(local)
+    be.set_stream(torch.cuda.current_stream().cuda_stream)
+    be.init_distributed()
+    uv = ba_graph(n, 8, 1)
+    op0 = np.random.default_rng(1).random(n)
+    g = vh.create_simulation(hk_model(), params={"eps": 0.02}, backend=be, device=local)
+    ids = vh.add_graph(g, uv, n, "HKAgent", op0.view([("opinion", "f8")]), "Knows")      # the same code on every rank
+    g.add_edges(ids, ids, "Knows")
+    m = g.finish_init(return_idmapping=True, partition_algo="EqualAgentNumbers")
+    b = vh.equal_partition(n, world)
+    old = np.array([vh.agent_id(1, 0, k) for k in range(1, n + 1)], dtype=np.uint64)     # rank 0's ids of the init phase
+    owner = np.searchsorted(np.array(b[1:]), np.arange(n), side="right")
+    assert len(m) == n and all(m[int(old[k])] == vh.agent_id(1, int(owner[k]), k - b[owner[k]] + 1) for k in range(0, n, 97))
+    assert len(g.all_agents("HKAgent")) == b[rank + 1] - b[rank]
+    assert g.num_agents("HKAgent") == n and g.num_edges("Knows") == 2 * len(uv) + n
+    o = None
+    if rank == 0:
+        import subprocess
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        o, _ = hk_sim(vh.load_backend(os.path.join(ROOT, "oracle", "_build", "libvahana_oracle.so")), n, uv, op0)
+    sizes = [b[r + 1] - b[r] for r in range(world)]
+    for step in range(5):
+        g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        mine = torch.from_numpy(g.all_agents("HKAgent")["opinion"].copy()).cuda()
+        parts = []
+        for r in range(world):
+            t = mine if r == rank else torch.empty(sizes[r], dtype=torch.float64, device="cuda")
+            dist.broadcast(t, src=r)
+            parts.append(t)
+        if rank == 0:
+            o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+            np.testing.assert_allclose(torch.cat(parts).cpu().numpy(), o.all_agents("HKAgent")["opinion"], rtol=1e-12, atol=0)
+    print(f"rank {rank}/{world}: ok", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,7 +30,7 @@ def main():
     ne = C.c_uint64()
     be.check(be.lib.vbw_hk_powerlaw_build_sharded(g.h, 1, 0, C.c_uint64(n), C.c_uint64(4), C.c_uint64(5), C.c_double(6.8333), C.c_uint32(1000000),
                                                    C.c_uint64(50000), C.c_uint32(rank), C.c_uint32(world), C.byref(ne)))
-    g.finish_init()
+    g.finish_init(distribute=False)   # SPMD initialisation: every rank added its own block
     bounds = vh.equal_partition(n, world)
     assert len(g.all_agents("HKAgent")) == bounds[rank + 1] - bounds[rank]
 

@@ -35,7 +35,7 @@ def main():
     for r in remote_ids:                       # and from its DAgent agents (these survive)
         sim.add_edge(r, int(ids[1]), "DEdge")
     sim.add_edge(int(ids[1]), int(ids[2]), "DEdge")
-    sim.finish_init()
+    sim.finish_init(distribute=False)   # SPMD initialisation
     assert sim.num_edges("DEdgeState") == 2 * world and sim.num_edges("DEdge") == 4 * world
     assert sim.num_agents("DAgentRemove") == 2 * world
     sim.apply("kill_all", ["DAgentRemove"], [], ["DAgentRemove"])

@@ -38,7 +38,7 @@ def graph_sim(be, local, rank, world, ET, kind):
     fr, to = gid[fg], gid[tg]
     stateful = "S" not in ET[4:]
     sim.add_edges(fr[mine], to[mine], ET, foos(np.zeros(int(mine.sum()), dtype=int)) if stateful else None)
-    sim.finish_init()
+    sim.finish_init(distribute=False)   # SPMD initialisation: every rank added its own block
     return sim
 
 

@@ -43,7 +43,7 @@ def main():
     g.add_agents("Location", np.zeros(lb[rank + 1] - lb[rank], dtype=[("n_inf", "i4")]))
     g.set_uniform_offset("Person", pb[rank])
     g.set_uniform_offset("Location", lb[rank])
-    g.finish_init()
+    g.finish_init(distribute=False)   # SPMD initialisation: every rank added its own block
     o = None
     if rank == 0:
         import subprocess

@@ -1,0 +1,174 @@
+"""finish_init!(distribute = true) (src/Simulation.jl:403-476, distribute! src/MPI.jl:11-84): the host-side plan as a pure function,
+and the exchange + rebuild on two gloo ranks against a recording stand-in for the engine library (the CUDA engine needs GPUs; the
+2-GPU variant is tests/mgpu_distribute.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import vahana_b200 as vh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ids(tid, n, rank=0):
+    return np.array([vh.agent_id(tid, rank, k) for k in range(1, n + 1)], dtype=np.uint64)
+
+
+def test_plan_equal_agent_numbers_matches_reference_partition():
+    """_create_equal_partition (src/Simulation.jl:353-367): rank i (1-based) owns ids[(i-1)s+1+min(i-1,r) : is+min(i,r)]"""
+    for n, world in [(10, 3), (7, 7), (100, 8), (5, 2), (3, 4), (0, 2)]:
+        ids = _ids(1, n)
+        states = np.arange(n, dtype=np.int64) * 10
+        shards, old, new, bounds = vh.plan_distribution({1: (ids, states)}, {}, world)
+        s, r = divmod(n, world)
+        for i in range(1, world + 1):
+            lo, hi = (i - 1) * s + 1 + min(i - 1, r), i * s + min(i, r)          # Julia's 1-based inclusive range
+            cnt, st = shards[i - 1]["agents"][1]
+            assert cnt == max(0, hi - lo + 1)
+            assert np.array_equal(st, states[lo - 1:hi])
+        assert np.array_equal(old, ids)
+        # new ids: dense per rank, in the old order
+        for k, (o, nw) in enumerate(zip(old, new)):
+            owner = int(np.searchsorted(np.array(bounds[1][1:]), k, side="right"))
+            assert vh.type_nr(nw) == 1 and vh.process_nr(nw) == owner and vh.agent_nr(nw) == k - bounds[1][owner] + 1
+
+
+def test_plan_edges_follow_their_target_in_add_order():
+    a, b = _ids(1, 6), _ids(2, 4)
+    rng = np.random.default_rng(0)
+    allids = np.concatenate([a, b])
+    fr, to = rng.choice(allids, 200), rng.choice(allids, 200)
+    st = np.arange(200, dtype=np.int64)
+    shards, old, new, _ = vh.plan_distribution({1: (a, None), 2: (b, np.arange(4.0))}, {"E": (fr, to, st), "S": (fr[:50], to[:50], None)}, 3)
+    m = dict(zip(old.tolist(), new.tolist()))
+    seen = []
+    for r in range(3):
+        f2, t2, s2 = shards[r]["edges"]["E"]
+        assert all(vh.process_nr(t) == r for t in t2)                              # stored on the target's rank (src/EdgeMethods.jl:396-398)
+        assert np.array_equal(f2, [m[int(x)] for x in fr[s2]]) and np.array_equal(t2, [m[int(x)] for x in to[s2]])
+        assert np.all(np.diff(s2) > 0)                                             # add order kept: every target keeps its push! order
+        seen += s2.tolist()
+        assert shards[r]["edges"]["S"][2] is None and len(shards[r]["edges"]["S"][0]) == int(np.isin(np.arange(50), s2).sum())
+    assert sorted(seen) == list(range(200))                                        # every edge on exactly one rank
+    assert sum(shards[r]["agents"][2][0] for r in range(3)) == 4 and shards[0]["agents"][1][1] is None
+
+
+def test_plan_explicit_partition_and_errors():
+    a = _ids(1, 5)
+    part = {int(a[0]): 2, int(a[1]): 1, int(a[2]): 2, int(a[3]): 2, int(a[4]): 1}    # 1-based ProcessIDs as in the reference
+    shards, old, new, bounds = vh.plan_distribution({1: (a, np.arange(5))}, {}, 2, part)
+    assert bounds == {}
+    assert np.array_equal(shards[0]["agents"][1][1], [1, 4]) and np.array_equal(shards[1]["agents"][1][1], [0, 2, 3])
+    m = dict(zip(old.tolist(), new.tolist()))
+    assert m[int(a[1])] == vh.agent_id(1, 0, 1) and m[int(a[4])] == vh.agent_id(1, 0, 2) and m[int(a[3])] == vh.agent_id(1, 1, 3)
+    assert np.array_equal(vh.updateids(m, a[:2]), [vh.agent_id(1, 1, 1), vh.agent_id(1, 0, 1)])
+    with pytest.raises(AssertionError):
+        vh.plan_distribution({1: (a, None)}, {}, 2, {int(a[0]): 1})                  # an agent without a rank
+    with pytest.raises(AssertionError):
+        vh.plan_distribution({1: (a, None)}, {}, 2, {int(x): 3 for x in a})          # rank outside of 1..mpi.size
+    with pytest.raises(AssertionError):
+        vh.plan_distribution({1: (a, None)}, {"E": (a[:1], np.array([vh.agent_id(1, 0, 99)], dtype=np.uint64), None)}, 2)   # dangling id
+
+
+def test_finish_init_single_rank_idmapping_is_identity(backend):
+    from models import edges_model, foos
+    sim = vh.create_simulation(edges_model(), backend=backend)
+    ids = sim.add_agents("Agent", foos([1, 2, 3]))
+    m = sim.finish_init(return_idmapping=True, partition_algo="EqualAgentNumbers")
+    assert m == {int(i): int(i) for i in ids}
+    sim2 = vh.create_simulation(edges_model(), backend=backend)
+    assert sim2.finish_init() is sim2 and sim2.finish_init.__doc__
+
+
+_GLOO = r'''
+import os, sys, ctypes as C
+import numpy as np, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import vahana_b200 as vh
+from models import edges_model, foos
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+
+
+class Recorder:
+    """stands in for the engine library: hands out ids of this rank and records what the mirror adds"""
+    def __init__(self):
+        self.next = {{}}; self.agents = {{}}; self.edges = {{}}; self.offsets = {{}}; self.created = 0; self.finished = 0
+    def vb_comm_rank(self, r, w):
+        r._obj.value, w._obj.value = rank, world; return 0
+    def vb_sim_create(self, md, params, h):
+        self.created += 1; self.next = {{}}; self.agents = {{}}; self.edges = {{}}; h._obj.value = 1000 + self.created; return 0
+    def vb_set_config(self, *a): return 0
+    def vb_sim_destroy(self, h): return 0
+    def vb_add_agents(self, h, tid, buf, n, ids):
+        tid, n = tid.value, n.value
+        first = self.next.get(tid, 1); self.next[tid] = first + n
+        out = (C.c_uint64 * n).from_address(ids.value)
+        for k in range(n): out[k] = vh.agent_id(tid, rank, first + k)
+        st = None if buf is None else np.frombuffer((C.c_uint8 * (n * 8)).from_address(buf.value), dtype=np.int64).copy()
+        self.agents.setdefault(tid, []).append((n, st)); return 0
+    def vb_add_edges(self, h, e, fr, to, st, n):
+        n = n.value
+        f = np.frombuffer((C.c_uint64 * n).from_address(fr.value), dtype=np.uint64).copy()
+        t = np.frombuffer((C.c_uint64 * n).from_address(to.value), dtype=np.uint64).copy()
+        self.edges.setdefault(e.value, []).append((f, t)); return 0
+    def vb_set_uniform_offset(self, h, tid, off): self.offsets[tid.value] = off.value; return 0
+    def vb_finish_init(self, h): self.finished += 1; return 0
+    def vb_last_error(self): return b""
+
+
+class FakeBackend:
+    name = "recorder"
+    def __init__(self): self.lib = Recorder()
+    def init(self, device=0): pass
+    def check(self, rc): assert rc == 0
+
+
+be = FakeBackend()
+sim = vh.create_simulation(edges_model(), backend=be)
+assert sim._stage is not None
+# every rank runs the same initialisation code; only rank 0's content counts (finish_init! docs, src/Simulation.jl:393-398)
+n = 11
+ids = sim.add_agents("Agent", foos(range(1, n + 1) if rank == 0 else range(100, 100 + n)))
+fr, to = ids, np.roll(ids, -1)
+sim.add_edges(fr, to, "EdgeS")
+rank0_ids = np.array([vh.agent_id(1, 0, k) for k in range(1, n + 1)], dtype=np.uint64)
+m = sim.finish_init(return_idmapping=True, partition_algo="EqualAgentNumbers")
+b = vh.equal_partition(n, world)
+lib = be.lib
+assert lib.created == 2 and lib.finished == 1                       # the initialisation phase was replaced by the shard
+cnt, st = lib.agents[1][0]
+assert cnt == b[rank + 1] - b[rank] and np.array_equal(st, np.arange(b[rank] + 1, b[rank + 1] + 1)), (cnt, st)   # rank 0's states
+assert lib.offsets[1] == b[rank]
+assert len(m) == n
+for k, old in enumerate(rank0_ids):
+    owner = int(np.searchsorted(np.array(b[1:]), k, side="right"))
+    assert m[int(old)] == vh.agent_id(1, owner, k - b[owner] + 1)
+f, t = lib.edges[sim._eid["EdgeS"]][0]
+mine = [k for k in range(n) if vh.process_nr(m[int(rank0_ids[(k + 1) % n])]) == rank]
+assert np.array_equal(t, [m[int(rank0_ids[(k + 1) % n])] for k in mine]) and np.array_equal(f, [m[int(rank0_ids[k])] for k in mine])
+# device-side bulk adds cannot be handed out
+sim2 = vh.create_simulation(edges_model(), backend=be)
+sim2._unstageable = "add_agents_device"
+try:
+    sim2.finish_init()
+    raise SystemExit("expected an AssertionError")
+except AssertionError:
+    pass
+sim2.finish_init(distribute=False)
+print("gloo rank", rank, "ok", flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_world2_distribute_plumbing(tmp_path):
+    script = tmp_path / "gloo_distribute.py"
+    script.write_text(_GLOO.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29531", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2

@@ -20,3 +20,16 @@ def test_remove_edges_across_ranks(cuda):
                         "--master-port", "29525", os.path.join(ROOT, "tests", "mgpu_remove.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(": ok") == min(ng, 4)
+
+
+@pytest.mark.gpu
+def test_finish_init_distribute_across_ranks(cuda):
+    """finish_init!(distribute = true) (src/MPI.jl:11-84): written after round 1's GPU budget was spent, not run on GPUs yet"""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ng, 4)), "--master-addr", "127.0.0.1",
+                        "--master-port", "29527", os.path.join(ROOT, "tests", "mgpu_distribute.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(": ok") == min(ng, 4)

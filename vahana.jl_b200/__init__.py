@@ -180,6 +180,74 @@ def equal_partition(n: int, nranks: int) -> list:
     return b
 
 
+def plan_distribution(agents: dict, edges: dict, world: int, partition: Optional[dict] = None) -> tuple:
+    """The host-side plan of distribute! (src/MPI.jl:11-84) as a pure function: which rank gets which agents under which new ids,
+    and which edges (with both ids rewritten) follow their target.
+
+    agents: {type id: (old ids in add order, states or None)}, edges: {edge name: (from ids, to ids, states or None)} - what rank 0
+    holds after the initialisation phase.  partition: {old id: rank, 1-based as the reference's ProcessID}; None = the reference's
+    :EqualAgentNumbers (contiguous equal blocks per type in id order, _create_equal_partition, src/Simulation.jl:353-367).
+    Within a rank the agents keep their old order (the reference's order is the iteration order of a Dict, i.e. unpinned); the new
+    id is (type, rank, position + 1) as add_agent! hands it out on the receiver (sendagents!, src/MPI.jl:112-149).  An edge goes to
+    the new owner of its target, in the order the edges were added, so every target keeps its push! order (sendedges!, :289-351).
+    Returns (shards, old, new, bounds): shards[r] = {"agents": {type id: (count, states)}, "edges": {name: (from, to, states)}},
+    old/new = the idmapping as two aligned uint64 arrays sorted by old id, bounds = {type id: block boundaries} for equal blocks."""
+    world = int(world)
+    olds, news = [], []
+    shards = [{"agents": {}, "edges": {}} for _ in range(world)]
+    bounds = {}
+    for tid in sorted(agents):
+        ids, states = agents[tid]
+        ids = np.asarray(ids, dtype=np.uint64).reshape(-1)
+        n = ids.shape[0]
+        if partition is None:
+            b = equal_partition(n, world)
+            bounds[tid] = b
+            owner = np.searchsorted(np.array(b[1:]), np.arange(n), side="right")
+        else:
+            try:
+                owner = np.array([int(partition[int(i)]) - 1 for i in ids], dtype=np.int64)
+            except KeyError as e:
+                raise AssertionError(f"the partition does not name a rank for agent {e.args[0]:#x}") from None
+            if n and (owner.min() < 0 or owner.max() >= world):
+                raise AssertionError("the partition names a rank outside of 1..mpi.size")
+        new = np.zeros(n, dtype=np.uint64)
+        for r in range(world):
+            sel = np.nonzero(owner == r)[0]                                      # ascending = old order
+            new[sel] = (np.uint64(tid) << np.uint64(SHIFT_TYPE)) | (np.uint64(r) << np.uint64(SHIFT_RANK)) | (np.arange(1, len(sel) + 1, dtype=np.uint64))
+            shards[r]["agents"][tid] = (len(sel), None if states is None else np.ascontiguousarray(np.asarray(states)[sel]))
+        olds.append(ids)
+        news.append(new)
+    old = np.concatenate(olds) if olds else np.zeros(0, dtype=np.uint64)
+    new = np.concatenate(news) if news else np.zeros(0, dtype=np.uint64)
+    order = np.argsort(old, kind="stable")
+    old, new = old[order], new[order]
+    if old.shape[0] > 1 and (old[1:] == old[:-1]).any():
+        raise AssertionError("an agent id was handed out twice")
+
+    def remap(x):
+        x = np.asarray(x, dtype=np.uint64).reshape(-1)
+        k = np.searchsorted(old, x)
+        k = np.minimum(k, max(old.shape[0] - 1, 0))
+        if x.shape[0] and (old.shape[0] == 0 or (old[k] != x).any()):
+            raise AssertionError("an edge names an agent that was never added")      # the reference: KeyError in idmapping[id]
+        return new[k] if x.shape[0] else x
+
+    for name in edges:
+        fr, to, states = edges[name]
+        nfr, nto = remap(fr), remap(to)
+        owner = ((nto >> np.uint64(SHIFT_RANK)) & np.uint64((1 << BITS_PROCESS) - 1)).astype(np.int64)
+        for r in range(world):
+            sel = np.nonzero(owner == r)[0]
+            shards[r]["edges"][name] = (nfr[sel], nto[sel], None if states is None else np.ascontiguousarray(np.asarray(states)[sel]))
+    return shards, old, new, bounds
+
+
+def updateids(idmapping, oldids):
+    """updateids(idmap, oldids) (src/Simulation.jl:479-483, a helper of the reference's tests)"""
+    return np.array([idmapping[int(i)] for i in np.asarray(oldids).reshape(-1)], dtype=np.uint64)
+
+
 def load_backend(path: Optional[str] = None) -> Backend:
     return Backend(path or os.environ.get("VAHANA_B200_LIB", DEFAULT_LIB))
 
@@ -347,9 +415,20 @@ class Simulation:
                 self._params[pname] = default
             for k, v in (params or {}).items():
                 self._params[k] = v
+        # multi-rank initialisation phase: what is added is also kept on the host, so that finish_init(distribute=True) can
+        # hand it out from rank 0 (distribute!, src/MPI.jl:11-84); released by finish_init
+        self._stage = None
+        self._unstageable = None
         if _handle is not None:
             self.h = _handle
             return
+        self.h = self._create_handle()
+        r, w = C.c_int(0), C.c_int(1)
+        if hasattr(self.lib, "vb_comm_rank") and self.lib.vb_comm_rank(C.byref(r), C.byref(w)) == 0 and w.value > 1:
+            self._stage = {"agents": {}, "edges": {}}
+
+    def _create_handle(self):
+        model, t = self.model, self.model.types
         at = (_AgentTypeDesc * max(1, len(t.agent_names)))()
         for i, n in enumerate(t.agent_names):
             dt = t.agent_dtypes[n]
@@ -368,8 +447,8 @@ class Simulation:
         h = C.c_void_p()
         pbuf = self._params.tobytes() if self._params is not None else None
         self.backend.check(self.lib.vb_sim_create(C.byref(md), pbuf, C.byref(h)))
-        self.h = h
-        self.lib.vb_set_config(self.h, C.c_int(int(config.asserts_enabled)), C.c_int(1))
+        self.lib.vb_set_config(h, C.c_int(int(config.asserts_enabled)), C.c_int(1))
+        return h
 
     # -- helpers --
     def _ck(self, rc):
@@ -481,16 +560,20 @@ class Simulation:
         ids = np.zeros(n, dtype=np.uint64)
         self._ck(self.lib.vb_add_agents(self.h, C.c_int(self._aid[type_name]), buf.ctypes.data_as(C.c_void_p) if buf is not None else None,
                                         C.c_uint64(n), ids.ctypes.data_as(C.c_void_p)))
+        if self._stage is not None:
+            self._stage["agents"].setdefault(self._aid[type_name], []).append((ids.copy(), None if buf is None else buf.copy()))
         return ids
 
     def add_agents_device(self, type_name: str, dev_ptr: int, n: int) -> None:
         """Bulk add from a device buffer of n AoS records (no ids returned: slots first..first+n-1 in order)."""
         self._ck(self.lib.vb_add_agents(self.h, C.c_int(self._aid[type_name]), C.c_void_p(dev_ptr), C.c_uint64(n), None))
+        self._unstageable = "add_agents_device"
 
     def add_edges_device(self, edge_name: str, from_ptr: int, to_ptr: int, n: int, states_ptr: int = 0) -> None:
         """Bulk add from device buffers of AgentIDs (uint64) in call order."""
         self._ck(self.lib.vb_add_edges(self.h, C.c_int(self._eid[edge_name]), C.c_void_p(from_ptr), C.c_void_p(to_ptr),
                                        C.c_void_p(states_ptr) if states_ptr else None, C.c_uint64(n)))
+        self._unstageable = "add_edges_device"
 
     def add_agent_per_process(self, type_name: str, state=None) -> int:
         """add_agent_per_process!(sim, agent) (src/Agent.jl:363-388): one agent on every rank, outside of transitions"""
@@ -524,6 +607,8 @@ class Simulation:
             buf = np.ascontiguousarray(np.broadcast_to(arr.reshape(-1) if arr.ndim else arr, (n,)))
         self._ck(self.lib.vb_add_edges(self.h, C.c_int(self._eid[edge_name]), fr.ctypes.data_as(C.c_void_p), to.ctypes.data_as(C.c_void_p),
                                        buf.ctypes.data_as(C.c_void_p) if buf is not None else None, C.c_uint64(n)))
+        if self._stage is not None:
+            self._stage["edges"].setdefault(edge_name, []).append((fr.copy(), to.copy(), None if buf is None else buf.copy()))
 
     def add_edge(self, from_id: int, to_id: int, edge_name: str, state=None):
         dt = self._edt(edge_name)
@@ -538,11 +623,14 @@ class Simulation:
             fr = 0
         else:
             fr, to, name = args
+        if self._stage is not None:
+            self._unstageable = "remove_edges! in the initialisation phase"
         self._ck(self.lib.vb_remove_edges(self.h, C.c_int(self._eid[name]), C.c_uint64(int(fr)), C.c_uint64(int(to))))
 
     def add_raster(self, name: str, dims: Sequence[int], type_name: str, agent_constructor) -> np.ndarray:
         """add_raster!(sim, name, dims, agent_constructor): the constructor is called with the 1-based position
         tuple of every cell in CartesianIndices (column-major) order, or is an array of states in that order."""
+        self._unstageable = "add_raster"   # rasters are not handed out by finish_init(distribute=True) yet (broadcastids, src/MPI.jl:64-75)
         dims = tuple(int(d) for d in dims)
         n = int(np.prod(dims))
         dt = self._adt(type_name)
@@ -614,11 +702,80 @@ class Simulation:
         """random_cell([rng], sim, raster[, weights]) (src/Raster.jl:553-577): the id of a random cell."""
         return self.cellid(name, self.random_pos(name, weights, rng))
 
-    def finish_init(self):
+    def finish_init(self, partition: Optional[dict] = None, return_idmapping: bool = False, partition_algo: str = "EqualAgentNumbers",
+                    distribute: bool = True):
+        """finish_init!(sim; partition, return_idmapping, partition_algo, distribute) (src/Simulation.jl:403-476).
+
+        One rank: nothing to distribute; `return_idmapping` gives the identity mapping.  Several ranks and `distribute=True` (the
+        reference's default): everything the initialisation phase added on rank 0 is handed out - agents by `partition` ({old id:
+        rank, 1-based}) or in contiguous equal blocks per type (:EqualAgentNumbers; Metis is not available, pass a partition
+        instead), every edge to the new owner of its target - and what the other ranks added is discarded, as in the reference.
+        `distribute=False` keeps what every rank added itself (SPMD initialisation: each rank adds its own block with ids of its
+        own rank; the bench-sized graphs are generated that way, on the device).  Returns the idmapping {old id: new id} when
+        `return_idmapping`, else the simulation."""
         self._log_begin("finish_init!")
+        rank, world = C.c_int(0), C.c_int(1)
+        if hasattr(self.lib, "vb_comm_rank"):
+            self.lib.vb_comm_rank(C.byref(rank), C.byref(world))
+        idmapping = None
+        if distribute and world.value > 1:
+            idmapping = self._distribute(partition, partition_algo, rank.value, world.value, return_idmapping)
+        self._stage = None
         self._ck(self.lib.vb_finish_init(self.h))
+        if distribute and return_idmapping and world.value == 1:
+            idmapping = {}
+            for name in self.model.types.agent_names:
+                for i in self.all_agentids(name):
+                    idmapping[int(i)] = int(i)
         self._log_end("finish_init!")
-        return self
+        return idmapping if (distribute and return_idmapping) else self
+
+    def _distribute(self, partition, partition_algo: str, rank: int, world: int, want_mapping: bool):
+        """distribute! (src/MPI.jl:11-84) on the host: rank 0 plans (plan_distribution), the shards travel with
+        torch.distributed (initialisation time, host data), every rank rebuilds its engine simulation from its shard."""
+        import torch.distributed as dist
+        if partition_algo not in ("EqualAgentNumbers", "Metis"):
+            raise ValueError("the partition_algo given is unknown")
+        if partition_algo == "Metis" and not partition:
+            raise NotImplementedError("Metis is not available: pass `partition` or partition_algo=\"EqualAgentNumbers\"")
+        if self._unstageable is not None or self._stage is None:
+            raise AssertionError(f"finish_init(distribute=True) on several ranks needs host-side adds ({self._unstageable or 'no staged init phase'}); "
+                                 "use distribute=False for an SPMD initialisation")
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() == world):
+            raise AssertionError("finish_init(distribute=True) needs torch.distributed initialised with one process per rank")
+        shards, meta = None, [None]
+        if rank == 0:
+            agents = {}
+            for tid, chunks in self._stage["agents"].items():
+                ids = np.concatenate([c[0] for c in chunks])
+                agents[tid] = (ids, None if chunks[0][1] is None else np.concatenate([c[1] for c in chunks]))
+            edges = {}
+            for name, chunks in self._stage["edges"].items():
+                edges[name] = (np.concatenate([c[0] for c in chunks]), np.concatenate([c[1] for c in chunks]),
+                               None if chunks[0][2] is None else np.concatenate([c[2] for c in chunks]))
+            shards, old, new, bounds = plan_distribution(agents, edges, world, partition or None)
+            meta = [(old, new, bounds)]
+        mine = [None]
+        dist.scatter_object_list(mine, shards, src=0)
+        dist.broadcast_object_list(meta, src=0)
+        old, new, bounds = meta[0]
+        shard = mine[0]
+        # rebuild: the initialisation phase of this rank is replaced by its shard
+        self.lib.vb_sim_destroy(self.h)
+        self.h = self._create_handle()
+        self._stage = None
+        names = {v: k for k, v in self._aid.items()}
+        for tid in sorted(shard["agents"]):
+            n, states = shard["agents"][tid]
+            if n:
+                ids = self.add_agents(names[tid], states, n)
+                assert int(ids[0]) == agent_id(tid, rank, 1) and int(ids[-1]) == agent_id(tid, rank, n), "receiver ids differ from the plan"
+            if tid in bounds:   # equal blocks: a sharded stochastic run draws what the single-rank run draws
+                self.set_uniform_offset(names[tid], bounds[tid][rank])
+        for name, (fr, to, states) in shard["edges"].items():
+            if to.shape[0]:
+                self.add_edges(fr, to, name, states)
+        return dict(zip(old.tolist(), new.tolist())) if want_mapping else None
 
     # -- apply! (src/Simulation.jl:720-821) --
     def apply(self, transition: str, call, read, write, add_existing=(), with_edge: Optional[str] = None, seed: int = 0):

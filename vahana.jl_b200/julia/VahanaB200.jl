@@ -248,8 +248,25 @@ remove_edges!(sim::Simulation, to::AgentID, ::Type{T}) where T =
 remove_edges!(sim::Simulation, from::AgentID, to::AgentID, ::Type{T}) where T =
     check(ccall((:vb_remove_edges, LIB), Cint, (Ptr{Cvoid}, Cint, AgentID, AgentID), sim.handle, edgeidx(sim, T), from, to))
 
-"finish_init!(sim): src/Simulation.jl:403-476 (single rank; every rank adds its own block in a multi-GPU run)"
-finish_init!(sim::Simulation) = (check(ccall((:vb_finish_init, LIB), Cint, (Ptr{Cvoid},), sim.handle)); sim)
+"finish_init!(sim; partition, return_idmapping, partition_algo, distribute): src/Simulation.jl:403-476.
+One rank: `return_idmapping` gives the identity mapping.  Several ranks: this wrapper only supports `distribute = false` (every rank
+adds its own block with ids of its own rank); the hand-out from rank 0 (distribute!, src/MPI.jl:11-84) is implemented in the Python
+mirror (`Simulation.finish_init`, `plan_distribution`) and needs a host-side exchange (MPI.jl) here."
+function finish_init!(sim::Simulation; partition = Dict{AgentID, Int}(), return_idmapping = false, partition_algo = :EqualAgentNumbers,
+                      distribute = true)
+    r, w = Ref{Cint}(0), Ref{Cint}(1)
+    ccall((:vb_comm_rank, LIB), Cint, (Ptr{Cint}, Ptr{Cint}), r, w)
+    @assert !(distribute && w[] > 1) "finish_init!(distribute = true) on several ranks: use the Python mirror or distribute = false"
+    check(ccall((:vb_finish_init, LIB), Cint, (Ptr{Cvoid},), sim.handle))
+    if distribute && return_idmapping
+        idmapping = Dict{AgentID, AgentID}()
+        for T in sim.model.types.agenttypes, id in all_agentids(sim, T)
+            idmapping[id] = id
+        end
+        return idmapping
+    end
+    sim
+end
 
 # ---- transitions -------------------------------------------------------------------------------------------------------
 "apply!(sim, transition, call, read, write; add_existing, with_edge, seed): src/Simulation.jl:720-821.
