@@ -283,3 +283,50 @@ def pp_globals(sim):
     return {"predator_pop": sim.mapreduce(None, "+", "Predator", init=0), "prey_pop": sim.mapreduce(None, "+", "Prey", init=0),
             "cells_with_food": sim.mapreduce("countdown", "+", "Cell", equals=0),
             "predator_energy": sim.mapreduce("energy", "+", "Predator", init=0), "prey_energy": sim.mapreduce("energy", "+", "Prey", init=0)}
+
+
+# ---- docs/examples/tutorial1.jl: the market model ("Excess Demand") ----
+BUYER = [("alpha", "f8"), ("B", "f8")]
+SELLER = [("p", "f8"), ("d_y", "f8")]
+BOUGHT = [("x", "f8"), ("y", "f8")]
+
+
+def market_model():
+    """tutorial1.jl:143-216: Buyer, Seller, KnownSeller (stateless), Bought; params numBuyer / numSeller / knownSellers; two globals"""
+    t = vh.ModelTypes()
+    t.register_agenttype("Buyer", BUYER)
+    t.register_agenttype("Seller", SELLER)
+    t.register_edgetype("KnownSeller")
+    t.register_edgetype("Bought", BOUGHT)
+    t.register_global("x_minus_y", [])
+    t.register_global("p", [])
+    return vh.create_model(t, "Excess Demand")
+
+
+def market_inputs(n_buyers, n_sellers, known, seed):
+    """Buyer() = Buyer(rand(), rand(1:100)), Seller() = Seller(rand() + 0.5, 0), `known` random sellers per buyer (tutorial1.jl:111-112,343-349)"""
+    rng = np.random.default_rng(seed)
+    buyers = np.zeros(n_buyers, dtype=BUYER)
+    buyers["alpha"], buyers["B"] = rng.random(n_buyers), rng.integers(1, 101, n_buyers)
+    sellers = np.zeros(n_sellers, dtype=SELLER)
+    sellers["p"] = rng.random(n_sellers) + 0.5
+    picks = rng.integers(0, n_sellers, (n_buyers, known))        # rand(sellerids, k): with replacement
+    return buyers, sellers, picks
+
+
+def market_sim(backend, buyers, sellers, picks):
+    sim = vh.create_simulation(market_model(), backend=backend)
+    bids = sim.add_agents("Buyer", buyers)
+    sids = sim.add_agents("Seller", sellers)
+    sim.add_edges(sids[picks.reshape(-1)], np.repeat(bids, picks.shape[1]), "KnownSeller")     # for b, for s: add_edge!(sim, s, b, KnownSeller())
+    sim.finish_init()
+    return sim
+
+
+def market_step(sim, step):
+    """run_simulation's loop body (tutorial1.jl:574-580); the two map closures that are not field selectors run on the host"""
+    sim.apply("market_calc_demand", "Buyer", ["Buyer", "Seller", "KnownSeller"], "Bought", seed=step)
+    sim.push_global("x_minus_y", sim.mapreduce("x", "+", "Bought") - sim.mapreduce("y", "+", "Bought"))
+    sim.apply("market_calc_price", "Seller", ["Seller", "Bought"], "Seller")
+    s = sim.all_agents("Seller")
+    sim.push_global("p", float((s["p"] * s["d_y"]).sum() / s["d_y"].sum()))                     # calc_average_price (:565-569)

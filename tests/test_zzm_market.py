@@ -1,0 +1,101 @@
+"""The market model of the reference's first tutorial (docs/examples/tutorial1.jl): add_edge! with a state inside a transition,
+agentstate of a neighbour, reduce(+, edgestates), edge mapreduce, globals.  No reference test pins its numbers (the tutorial draws
+from rand()): the oracle is checked bit for bit against an independent numpy restatement (own Philox4x32-10), the CUDA engine
+against the oracle.  (The GPU variant was written after round 1's GPU budget was spent; the file sorts behind the established suite.)"""
+import numpy as np
+import pytest
+
+from models import market_inputs, market_sim, market_step
+
+M32 = np.uint64(0xFFFFFFFF)
+
+
+def philox_uniform(seed, a, k):
+    """Philox4x32-10 of counter (a_lo, a_hi, k_lo, k_hi) with key (seed_lo, seed_hi); 53-bit uniform from the first two words"""
+    a = np.asarray(a, dtype=np.uint64)
+    c = [a & M32, a >> np.uint64(32), np.full_like(a, k) & M32, np.full_like(a, k) >> np.uint64(32)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c[0], np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & M32, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & M32]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & M32, (k1 + np.uint64(0xBB67AE85)) & M32
+    bits = ((c[0] << np.uint64(32)) | c[1]) >> np.uint64(11)
+    return bits.astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def numpy_market(buyers, sellers, picks, steps):
+    """tutorial1.jl:408-435,565-580 restated with numpy; a seller adds its Bought edges in the order the buyers were called"""
+    p, d_y = sellers["p"].copy(), sellers["d_y"].copy()
+    nb, known = picks.shape
+    xmy, avg = [], []
+    for step in range(steps):
+        k = np.minimum((philox_uniform(step, np.arange(nb), 0) * known).astype(np.int64), known - 1)
+        chosen = picks[np.arange(nb), k]
+        x = buyers["B"] * buyers["alpha"]
+        y = buyers["B"] * (1.0 - buyers["alpha"]) / p[chosen]
+        xmy.append(x.sum() - y.sum())
+        for s in range(len(p)):
+            idx = np.nonzero(chosen == s)[0]
+            if len(idx) == 0:
+                continue
+            qx, qy = x[idx[0]], y[idx[0]]
+            for i in idx[1:]:
+                qx, qy = qx + x[i], qy + y[i]
+            p[s], d_y[s] = qy / qx * p[s], qy
+        avg.append((p * d_y).sum() / d_y.sum())
+    return p, d_y, np.array(xmy), np.array(avg), (x, y, chosen)
+
+
+@pytest.mark.parametrize("nb,ns,known", [(50, 5, 2), (5000, 40, 3)])      # the tutorial's sizes (tutorial1.jl:184-187) and a larger market
+def test_market_oracle_vs_numpy(oracle, nb, ns, known):
+    buyers, sellers, picks = market_inputs(nb, ns, known, seed=8)
+    sim = market_sim(oracle, buyers, sellers, picks)
+    assert sim.num_edges("KnownSeller") == nb * known
+    steps = 20
+    for step in range(steps):
+        market_step(sim, step)
+    p, d_y, xmy, avg, (x, y, chosen) = numpy_market(buyers, sellers, picks, steps)
+    s = sim.all_agents("Seller")
+    assert np.array_equal(s["p"], p) and np.array_equal(s["d_y"], d_y)               # bit-exact: same draws, same order of additions
+    np.testing.assert_allclose(sim.get_global("x_minus_y"), xmy, rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(sim.get_global("p"), avg, rtol=1e-12)
+    assert sim.num_edges("Bought") == nb                                             # rebuilt every step: one purchase per buyer
+    # the Bought rows of the last step: from = the buyers of each seller in call order, states (x, y)
+    off, fr, st = sim.export_csr("Bought", "Seller", ns)
+    order = np.lexsort((np.arange(nb), chosen))
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(np.bincount(chosen, minlength=ns))]))
+    assert np.array_equal((fr & np.uint64((1 << 36) - 1)).astype(np.int64) - 1, order)
+    assert np.array_equal(st["x"], x[order]) and np.array_equal(st["y"], y[order])
+    # budget constraint x + y * p = B at the price the buyer saw (tutorial1.jl:36), through the demand of a first step
+    sim2 = market_sim(oracle, buyers, sellers, picks)
+    sim2.apply("market_calc_demand", "Buyer", ["Buyer", "Seller", "KnownSeller"], "Bought", seed=0)
+    off2, fr2, st2 = sim2.export_csr("Bought", "Seller", ns)
+    pseen = np.repeat(sellers["p"], np.diff(off2).astype(np.int64))
+    bidx = (fr2 & np.uint64((1 << 36) - 1)).astype(np.int64) - 1
+    np.testing.assert_allclose(st2["x"] + st2["y"] * pseen, buyers["B"][bidx], rtol=1e-13)
+
+
+def test_market_seller_without_customers_keeps_its_state(oracle):
+    """isnothing(edgestates(...)) -> return s (tutorial1.jl:429-431)"""
+    buyers, sellers, picks = market_inputs(10, 4, 1, seed=3)
+    picks[:] = 2
+    sim = market_sim(oracle, buyers, sellers, picks)
+    market_step(sim, 0)
+    s = sim.all_agents("Seller")
+    assert np.array_equal(s["p"][[0, 1, 3]], sellers["p"][[0, 1, 3]]) and np.all(s["d_y"][[0, 1, 3]] == 0) and s["d_y"][2] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nb,ns,known", [(50, 5, 2), (200000, 300, 4)])
+def test_market_gpu_vs_oracle(oracle, cuda, nb, ns, known):
+    buyers, sellers, picks = market_inputs(nb, ns, known, seed=8)
+    g, o = market_sim(cuda, buyers, sellers, picks), market_sim(oracle, buyers, sellers, picks)
+    for step in range(10):
+        market_step(g, step)
+        market_step(o, step)
+        a, b = g.all_agents("Seller"), o.all_agents("Seller")
+        assert np.array_equal(a["p"], b["p"]) and np.array_equal(a["d_y"], b["d_y"]), step      # sequential functors: bit-exact Float64
+        eg, eo = g.export_csr("Bought", "Seller", ns), o.export_csr("Bought", "Seller", ns)
+        assert all(np.array_equal(u, v) for u, v in zip(eg, eo)), step                         # rows, sources and (x, y) states of every seller
+    np.testing.assert_allclose(g.get_global("x_minus_y"), o.get_global("x_minus_y"), rtol=1e-10, atol=1e-7)    # tree vs sequential sum
+    np.testing.assert_allclose(g.get_global("p"), o.get_global("p"), rtol=1e-12)

@@ -2,6 +2,7 @@
 #pragma once
 #include "gol.h"
 #include "hk.h"
+#include "market.h"
 #include "predator.h"
 #include "sir.h"
 #include "testkit.h"
