@@ -136,6 +136,10 @@ int vb_all_edges(vb_sim* sim, int etype, vb_agent_id* to_out, vb_agent_id* from_
  * init: pointer to one value of the result dtype or NULL (=> identity, Helpers.jl:44-81).  */
 int vb_mapreduce(vb_sim* sim, int type_ref, int offset, int dt, int has_cmp, int64_t cmp, int op, int result_dt,
                  const void* init, void* result_out);
+/* The same with the map given by name: a functor registered with VB_REGISTER_MAP (include/vahana_device.cuh, vb::MapBase in
+ * include/vahana_model.h) for the agent / edge type `type_ref`, i.e. any closure f of mapreduce(sim, f, op, T), e.g.
+ * b -> b.x - b.y (docs/examples/tutorial1.jl:548).  result_dt must be floating point iff the functor's Result is.            */
+int vb_mapreduce_fn(vb_sim* sim, const char* map_name, int type_ref, int op, int result_dt, const void* init, void* result_out);
 
 /* ---- raster read-out (src/Raster.jl:206-387) ------------------------------------------- */
 int vb_rastervalues(vb_sim* sim, const char* name, int offset, int dt, void* out);       /* rastervalues / calc_rasterstate(field) */

@@ -34,6 +34,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "vahana_model.h"
 
@@ -200,6 +201,26 @@ struct TransitionInfo {
 };
 // exported by libvahana_b200.so; model libraries call it from static initialisers
 extern "C" int vb_register_transition(const TransitionInfo* info);
+
+// a compiled map functor (vb::MapBase): one kernel folds f(element) per CTA into `partial[blockIdx.x]` (double or long long)
+struct MapLaunchArgs {
+    const uint8_t* cols;      // SoA columns of the mapped states (agents: read buffer; edges: CSR state columns)
+    uint32_t stride;          // column stride in elements
+    uint64_t n;               // elements
+    const uint8_t* died;      // agents of a mortal type: skip died slots (else nullptr)
+    int op;                   // vb::OP_*
+    void* partial;            // [nblocks] partial results
+    uint32_t nblocks;
+    cudaStream_t stream;
+};
+struct MapInfo {
+    const char* name;
+    const char* type_name;    // agent or edge type the map is defined on (registered name)
+    uint32_t elem_size;       // sizeof(F::Elem)
+    int is_float;             // F::Result is floating point (partials are double) or integral (long long)
+    cudaError_t (*launch)(const MapLaunchArgs&);
+};
+extern "C" int vb_register_map(const MapInfo* info);
 
 #if defined(__CUDACC__)
 // ---- SoA word access ---------------------------------------------------------------------------------
@@ -1455,8 +1476,76 @@ TransitionInfo make_transition_info(const char* name, const char* agent_type) {
     return ti;
 }
 
+// ---- registered map functors of mapreduce (K8) ------------------------------------------------------------------------------------
+__device__ __forceinline__ double map_identity(int op, double) {
+    return op == OP_PROD ? 1.0 : op == OP_MIN ? INFINITY : op == OP_MAX ? -INFINITY : 0.0;
+}
+__device__ __forceinline__ long long map_identity(int op, long long) {
+    return op == OP_PROD ? 1LL : op == OP_MIN ? 0x7fffffffffffffffLL : op == OP_MAX ? (-0x7fffffffffffffffLL - 1) : op == OP_AND ? -1LL : 0LL;
+}
+__device__ __forceinline__ double map_fold(double a, double b, int op) {
+    return op == OP_SUM ? a + b : op == OP_PROD ? a * b : op == OP_MIN ? fmin(a, b) : fmax(a, b);
+}
+__device__ __forceinline__ long long map_fold(long long a, long long b, int op) {
+    switch (op) {
+        case OP_SUM: return (long long)((unsigned long long)a + (unsigned long long)b);
+        case OP_PROD: return (long long)((unsigned long long)a * (unsigned long long)b);
+        case OP_MIN: return a < b ? a : b;
+        case OP_MAX: return a > b ? a : b;
+        case OP_AND: return a & b;
+        default: return a | b;
+    }
+}
+template <class R> struct MapAcc { typedef long long type; };
+template <> struct MapAcc<double> { typedef double type; };
+template <> struct MapAcc<float> { typedef double type; };
+// grid-stride over the elements (coalesced SoA loads, HBM-bound), lanes -> warps -> CTA; the engine folds the partials
+template <class F>
+__global__ void __launch_bounds__(256) map_kernel(const MapLaunchArgs a) {
+    typedef typename F::Elem Elem;
+    typedef typename MapAcc<typename F::Result>::type T;
+    __shared__ T sm[8];
+    const F f{};
+    T acc = map_identity(a.op, T());
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (a.died && a.died[i]) continue;
+        acc = map_fold((T)f(soa_load<Elem>(a.cols, a.stride, (uint32_t)i)), acc, a.op);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = map_fold(acc, __shfl_xor_sync(0xffffffffu, acc, o), a.op);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T v = threadIdx.x < 8 ? sm[threadIdx.x] : map_identity(a.op, T());
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v = map_fold(v, __shfl_xor_sync(0xffffffffu, v, o), a.op);
+        if (threadIdx.x == 0) reinterpret_cast<T*>(a.partial)[blockIdx.x] = v;
+    }
+}
+template <class F>
+cudaError_t launch_map(const MapLaunchArgs& a) {
+    map_kernel<F><<<a.nblocks, 256, 0, a.stream>>>(a);
+    return cudaGetLastError();
+}
+template <class F>
+MapInfo make_map_info(const char* name, const char* type_name) {
+    static_assert(std::is_base_of<MapBase, F>::value, "map functors derive from vb::MapBase");
+    MapInfo mi{};
+    mi.name = name; mi.type_name = type_name;
+    mi.elem_size = (uint32_t)sizeof(typename F::Elem);
+    mi.is_float = std::is_floating_point<typename F::Result>::value ? 1 : 0;
+    mi.launch = &launch_map<F>;
+    return mi;
+}
+
 #define VB_CAT2(a, b) a##b
 #define VB_CAT(a, b) VB_CAT2(a, b)
+// Registers Functor as the map `mname` of mapreduce over agents / edges of type `tname`.
+#define VB_REGISTER_MAP(mname, tname, ...)                                                     \
+    static const int VB_CAT(vb_regmap_, __COUNTER__) = [] {                                    \
+        static const vb::MapInfo mi = vb::make_map_info<__VA_ARGS__>(mname, tname);            \
+        return vb_register_map(&mi);                                                           \
+    }();
 // Registers Functor as the transition `tname` for agents of type `atype` (a string: the registered name).
 #define VB_REGISTER_TRANSITION(tname, atype, ...)                                              \
     static const int VB_CAT(vb_reg_, __COUNTER__) = [] {                                       \

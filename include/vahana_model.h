@@ -92,6 +92,12 @@ struct Philox {
     }
 };
 
+// A registered map of mapreduce — the closure `f` of mapreduce(sim, f, op, T) (src/AgentMethods.jl:533-565, src/EdgeMethods.jl:972-994)
+// when it is more than a field selector, e.g. `b -> b.x - b.y` (docs/examples/tutorial1.jl:548).  Single source like the transitions:
+//     struct XMinusY : vb::MapBase { using Elem = Bought; using Result = double; VB_HD double operator()(const Bought& b) const { return b.x - b.y; } };
+// Elem = the agent state (live agents are mapped) or the edge state (every edge is mapped); Result = double or int64_t (Bool: 0 / 1).
+struct MapBase {};
+
 // Largest power-of-two word (<= 16 B) that divides a state size: the SoA column width
 // the engine stores agent and edge states in (see DESIGN.md "data layout").
 VB_HD uint32_t soa_word(uint32_t size) {

@@ -240,6 +240,20 @@ int vb_mapreduce(vb_sim* sim, int type_ref, int offset, int dt, int has_cmp, int
     });
 }
 
+int vb_mapreduce_fn(vb_sim* sim, const char* map_name, int type_ref, int op, int result_dt, const void* init, void* out) {
+    return guard([&] {
+        vo::Sim& s = *sim->s;
+        const std::string tname = type_ref < vb::EDGE_REF ? s.A(type_ref).desc.name : s.E(type_ref - vb::EDGE_REF).desc.name;
+        auto& maps = vo::Registry::get().maps;
+        auto it = maps.find({map_name ? map_name : "", tname});
+        if (it == maps.end()) throw vo::ArgError(std::string("map '") + (map_name ? map_name : "") + "' is not registered for type " + tname);
+        vo::Value iv;
+        if (init) iv = to_value(init, result_dt);
+        vo::Value r = vo::mapreduce(s, type_ref, 0, vb::DT_I64, false, 0, op, result_dt, init ? &iv : nullptr, &it->second);
+        from_value(r, result_dt, out);
+    });
+}
+
 static size_t dt_size(int dt) { return (dt == VB_DT_I64 || dt == VB_DT_F64) ? 8 : (dt == VB_DT_I32 || dt == VB_DT_F32) ? 4 : 1; }
 int vb_rastervalues(vb_sim* sim, const char* name, int offset, int dt, void* out) {   // Raster.jl:282-387
     return guard([&] {

@@ -5,7 +5,9 @@
 #include "../vahana.jl_b200/csrc/transitions/all.h"
 
 #define VB_TRANSITION(tname, atype, ...) VO_REGISTER_TRANSITION(tname, atype, __VA_ARGS__)
+#define VB_MAP(mname, tname, ...) VO_REGISTER_MAP(mname, tname, __VA_ARGS__)
 #include "../vahana.jl_b200/csrc/transitions/registry.inc"
+#undef VB_MAP
 #undef VB_TRANSITION
 
 // host generator of the synthetic HK power-law workload (same formulas as the device generator)

@@ -24,6 +24,7 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <type_traits>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -170,8 +171,14 @@ class Ctx;
 // i.e. the Val(T) form, AgentMethods.jl:232-245); return false = `nothing` (the agent dies).
 using TransitionFn = std::function<bool(Ctx&, void*, AgentID)>;
 
+struct MapFn {          // a registered map of mapreduce (vb::MapBase): f(element) as double or int64
+    uint32_t elem_size = 0;
+    bool is_float = false;
+    std::function<void(const uint8_t*, double&, int64_t&)> fn;
+};
 struct Registry {
     std::map<std::pair<std::string, std::string>, TransitionFn> fns;   // (transition, agent type name)
+    std::map<std::pair<std::string, std::string>, MapFn> maps;         // (map, agent / edge type name)
     static Registry& get() { static Registry r; return r; }
 };
 
@@ -911,13 +918,22 @@ inline void fold(Value& acc, const Value& x, int op) {   // reduced = op(f(x), r
     }
 }
 inline Value mapreduce(Sim& s, int type_ref, int offset, int dt, bool has_cmp, int64_t cmp, int op, int result_dt,
-                       const Value* init) {
+                       const Value* init, const MapFn* mf = nullptr) {
     if (s.intransition) throw AssertionError("You can not call mapreduce inside of a transition function.");
     Value acc = init ? *init : identity(op, result_dt);
     acc.dt = result_dt;
+    const bool risf = result_dt == vb::DT_F64 || result_dt == vb::DT_F32;
+    if (mf && mf->is_float != risf) throw ArgError("the result datatype does not match the map functor");
+    auto load_value = [&](const uint8_t* p, int offset_, int dt_, bool has_cmp_, int64_t cmp_, int result_dt_) -> Value {
+        if (!mf) return vo::load_value(p, offset_, dt_, has_cmp_, cmp_, result_dt_);
+        Value v; v.dt = result_dt_;
+        mf->fn(p, v.f, v.i);                                   // f(state): the closure of mapreduce(sim, f, op, T)
+        return v;
+    };
     if (type_ref < vb::EDGE_REF) {
         AgentFields& a = s.A(type_ref);
         const uint32_t sz = a.desc.size;
+        if (mf && mf->elem_size != sz) throw ArgError("sizeof(Elem) of the map functor does not match the agent type");
         static const uint8_t zeros[64] = {0};
         for (uint64_t i = 1; i < a.nextid; ++i) {
             if (!a.immortal && a.read.died[i - 1]) continue;
@@ -928,6 +944,7 @@ inline Value mapreduce(Sim& s, int type_ref, int offset, int dt, bool has_cmp, i
         EdgeFields& f = s.E(type_ref - vb::EDGE_REF);
         if (f.stateless) throw AssertionError("mapreduce is not defined for :Stateless edge types");
         const uint32_t sz = f.desc.size;
+        if (mf && mf->elem_size != sz) throw ArgError("sizeof(Elem) of the map functor does not match the edge type");
         auto row = [&](const Row& r) {
             for (size_t i = 0; i * sz < r.state.size(); ++i) { Value x = load_value(&r.state[i * sz], offset, dt, has_cmp, cmp, result_dt); fold(acc, x, op); }
         };
@@ -949,6 +966,22 @@ inline std::unique_ptr<Sim> copy_sim(const Sim& s) {   // copy_simulation: Simul
 
 }  // namespace vo
 
+// Registers a single-source map functor (vb::MapBase) with the oracle.
+#define VO_REGISTER_MAP(mname, type_name, ...)                                                                 \
+    static const bool VO_CAT(vo_regmap_, __COUNTER__) = [] {                                                   \
+        using VoMap = __VA_ARGS__;                                                                             \
+        vo::MapFn m;                                                                                           \
+        m.elem_size = (uint32_t)sizeof(typename VoMap::Elem);                                                  \
+        m.is_float = std::is_floating_point<typename VoMap::Result>::value;                                    \
+        m.fn = [](const uint8_t* p, double& f, int64_t& i) {                                                   \
+            typename VoMap::Elem e;                                                                            \
+            std::memcpy((void*)&e, p, sizeof(e));                                                              \
+            const typename VoMap::Result r = VoMap()(e);                                                       \
+            if (std::is_floating_point<typename VoMap::Result>::value) f = (double)r; else i = (int64_t)r;     \
+        };                                                                                                     \
+        vo::Registry::get().maps[{mname, type_name}] = m;                                                      \
+        return true;                                                                                           \
+    }();
 #define VO_CAT2(a, b) a##b
 #define VO_CAT(a, b) VO_CAT2(a, b)
 // Registers Functor (a single-source transition from vahana.jl_b200/csrc/transitions) with the oracle.

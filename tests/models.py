@@ -324,9 +324,10 @@ def market_sim(backend, buyers, sellers, picks):
 
 
 def market_step(sim, step):
-    """run_simulation's loop body (tutorial1.jl:574-580); the two map closures that are not field selectors run on the host"""
+    """run_simulation's loop body (tutorial1.jl:574-580); the map closures that are not field selectors are registered map functors"""
     sim.apply("market_calc_demand", "Buyer", ["Buyer", "Seller", "KnownSeller"], "Bought", seed=step)
-    sim.push_global("x_minus_y", sim.mapreduce("x", "+", "Bought") - sim.mapreduce("y", "+", "Bought"))
+    sim.push_global("x_minus_y", sim.mapreduce_fn("market_x_minus_y", "+", "Bought"))          # mapreduce(sim, b -> b.x - b.y, +, Bought)
     sim.apply("market_calc_price", "Seller", ["Seller", "Bought"], "Seller")
-    s = sim.all_agents("Seller")
-    sim.push_global("p", float((s["p"] * s["d_y"]).sum() / s["d_y"].sum()))                     # calc_average_price (:565-569)
+    m = sim.mapreduce_fn("market_revenue", "+", "Seller")                                       # calc_average_price (:565-569)
+    q = sim.mapreduce("d_y", "+", "Seller")
+    sim.push_global("p", m / q)

@@ -33,7 +33,7 @@ def numpy_market(buyers, sellers, picks, steps):
         chosen = picks[np.arange(nb), k]
         x = buyers["B"] * buyers["alpha"]
         y = buyers["B"] * (1.0 - buyers["alpha"]) / p[chosen]
-        xmy.append(x.sum() - y.sum())
+        xmy.append((x - y).sum())
         for s in range(len(p)):
             idx = np.nonzero(chosen == s)[0]
             if len(idx) == 0:
@@ -73,6 +73,51 @@ def test_market_oracle_vs_numpy(oracle, nb, ns, known):
     pseen = np.repeat(sellers["p"], np.diff(off2).astype(np.int64))
     bidx = (fr2 & np.uint64((1 << 36) - 1)).astype(np.int64) - 1
     np.testing.assert_allclose(st2["x"] + st2["y"] * pseen, buyers["B"][bidx], rtol=1e-13)
+
+
+def test_registered_maps(oracle):
+    """mapreduce(sim, f, op, T) with f a registered functor: float and integral results, init, identities, and the errors"""
+    buyers, sellers, picks = market_inputs(300, 7, 2, seed=5)
+    picks[picks == 3] = 4                                            # seller 3 has no customers
+    sim = market_sim(oracle, buyers, sellers, picks)
+    assert sim.mapreduce_fn("market_x_minus_y", "+", "Bought") == 0.0            # no Bought edge yet: the identity of + (Helpers.jl:44-50)
+    assert sim.mapreduce_fn("market_x_minus_y", "max", "Bought") == -np.inf
+    market_step(sim, 0)
+    off, fr, st = sim.export_csr("Bought", "Seller", 7)
+    s = sim.all_agents("Seller")
+    np.testing.assert_allclose(sim.mapreduce_fn("market_x_minus_y", "+", "Bought"), (st["x"] - st["y"]).sum(), rtol=1e-12)
+    np.testing.assert_allclose(sim.mapreduce_fn("market_x_minus_y", "+", "Bought", init=10.0), (st["x"] - st["y"]).sum() + 10.0, rtol=1e-12)
+    assert sim.mapreduce_fn("market_x_minus_y", "max", "Bought") == (st["x"] - st["y"]).max()
+    assert sim.mapreduce_fn("market_x_minus_y", "min", "Bought") == (st["x"] - st["y"]).min()
+    np.testing.assert_allclose(sim.mapreduce_fn("market_revenue", "+", "Seller"), (s["p"] * s["d_y"]).sum(), rtol=1e-12)
+    assert sim.mapreduce_fn("market_has_customers", "+", "Seller", datatype="i8") == 6 == int((s["d_y"] > 0).sum())
+    assert sim.mapreduce_fn("market_has_customers", "&", "Seller", datatype="i8") == 0
+    assert sim.mapreduce_fn("market_has_customers", "|", "Seller", datatype="i8") == 1
+    with pytest.raises(ValueError):
+        sim.mapreduce_fn("market_revenue", "+", "Buyer")                          # registered for Seller only
+    with pytest.raises(ValueError):
+        sim.mapreduce_fn("market_has_customers", "+", "Seller", datatype="f8")    # integral functor, float result
+    with pytest.raises(ValueError):
+        sim.mapreduce_fn("no_such_map", "+", "Seller")
+
+
+@pytest.mark.gpu
+def test_registered_maps_gpu_vs_oracle(oracle, cuda):
+    buyers, sellers, picks = market_inputs(100000, 200, 3, seed=5)
+    g, o = market_sim(cuda, buyers, sellers, picks), market_sim(oracle, buyers, sellers, picks)
+    assert g.mapreduce_fn("market_x_minus_y", "+", "Bought") == 0.0
+    for sim in (g, o):
+        market_step(sim, 0)
+    for name, op, T, dt in [("market_x_minus_y", "+", "Bought", "f8"), ("market_x_minus_y", "max", "Bought", "f8"), ("market_x_minus_y", "min", "Bought", "f8"),
+                            ("market_revenue", "+", "Seller", "f8"), ("market_revenue", "*", "Seller", "f8"),
+                            ("market_has_customers", "+", "Seller", "i8"), ("market_has_customers", "&", "Seller", "i8")]:
+        a, b = g.mapreduce_fn(name, op, T, datatype=dt), o.mapreduce_fn(name, op, T, datatype=dt)
+        if dt == "i8" or op in ("max", "min"):
+            assert a == b, (name, op)
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-11, err_msg=f"{name} {op}")          # tree vs left fold
+    with pytest.raises(ValueError):
+        g.mapreduce_fn("market_has_customers", "+", "Seller", datatype="f8")
 
 
 def test_market_seller_without_customers_keeps_its_state(oracle):

@@ -102,7 +102,7 @@ ABI_SYMBOLS = [
     "vb_sim_create", "vb_sim_copy", "vb_sim_destroy", "vb_set_param", "vb_set_config", "vb_disable_transition_checks",
     "vb_add_agents", "vb_add_edges", "vb_remove_edges", "vb_add_raster", "vb_connect_raster_neighbors", "vb_move_to",
     "vb_cellid", "vb_finish_init", "vb_apply", "vb_has_transition", "vb_load_model_library", "vb_num_agents",
-    "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce",
+    "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce", "vb_mapreduce_fn",
     "vb_rastervalues", "vb_calc_raster_num_edges", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
     "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes", "vb_set_uniform_offset", "vb_add_agent_per_process",
     "vb_last_apply_blocks", "vb_set_read_blocking", "vb_set_read_prefilter", "vb_last_apply_prefiltered",
@@ -982,6 +982,20 @@ class Simulation:
         self._ck(self.lib.vb_mapreduce(self.h, C.c_int(ref), C.c_int(off), C.c_int(fdt), C.c_int(int(equals is not None)),
                                        C.c_int64(int(equals) if equals is not None else 0), C.c_int(_OPS[op]), C.c_int(_DT[rdt]),
                                        ib.ctypes.data_as(C.c_void_p) if ib is not None else None, out.ctypes.data_as(C.c_void_p)))
+        return out[0].item()
+
+    def mapreduce_fn(self, map_name: str, op: str, type_name: str, datatype=None, init=None):
+        """mapreduce(sim, f, op, T; datatype, init) with f a registered map functor (VB_REGISTER_MAP), e.g.
+        mapreduce(sim, b -> b.x - b.y, +, Bought) (docs/examples/tutorial1.jl:548) = sim.mapreduce_fn("market_x_minus_y", "+", "Bought")."""
+        ref = self._ref(type_name)
+        if ref >= EDGE_REF:
+            assert "Stateless" not in self.model.types.edge_hints[type_name], \
+                f"mapreduce is not defined for the hint combination of {type_name}"
+        rdt = np.dtype(datatype if datatype is not None else "f8")
+        out = np.zeros(1, dtype=rdt)
+        ib = np.array([init], dtype=rdt) if init is not None else None
+        self._ck(self.lib.vb_mapreduce_fn(self.h, map_name.encode(), C.c_int(ref), C.c_int(_OPS[op]), C.c_int(_DT[rdt]),
+                                          ib.ctypes.data_as(C.c_void_p) if ib is not None else None, out.ctypes.data_as(C.c_void_p)))
         return out[0].item()
 
     # -- raster read-out (Raster.jl:206-387) --

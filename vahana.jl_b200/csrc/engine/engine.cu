@@ -163,6 +163,11 @@ std::map<std::pair<std::string, std::string>, const vb::TransitionInfo*>& regist
     return r;
 }
 
+std::map<std::pair<std::string, std::string>, const vb::MapInfo*>& map_registry() {
+    static std::map<std::pair<std::string, std::string>, const vb::MapInfo*> r;
+    return r;
+}
+
 // ---- engine-side kernels -------------------------------------------------------------------------------
 // raw (AgentID) adds -> composite append log.  Validation as in the reference's add_edge! (ids must
 // name an existing slot of a registered type; :SingleType target must match).
@@ -2654,6 +2659,10 @@ int vb_register_transition(const vb::TransitionInfo* info) {
     registry()[{info->name, info->agent_type}] = info;
     return 0;
 }
+int vb_register_map(const vb::MapInfo* info) {
+    map_registry()[{info->name, info->type_name}] = info;
+    return 0;
+}
 
 const char* vb_last_error(void) { return g_err.c_str(); }
 const char* vb_backend(void) { return "cuda-sm100a"; }
@@ -3445,7 +3454,9 @@ int vb_all_edges(vb_sim* s, int ei, vb_agent_id* to_out, vb_agent_id* from_out, 
     });
 }
 
-int vb_mapreduce(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64_t cmp, int op, int result_dt, const void* init, void* out) {
+// mapreduce with the map given as a field selector (mi == nullptr) or as a registered functor (mi)
+static int mapreduce_common(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64_t cmp, int op, int result_dt, const void* init, void* out,
+                            const vb::MapInfo* mi) {
     return guard([&] {
         require_device();
         if (s->intransition) throw AssertionError("You can not call mapreduce inside of a transition function.");
@@ -3462,20 +3473,29 @@ int vb_mapreduce(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64
             ma.cols = e.st; ma.stride = e.st_cap; ma.word = e.word; ma.n = e.nnz; ma.died = nullptr;
         }
         const bool isf = result_dt == vb::DT_F64 || result_dt == vb::DT_F32;
+        vb::MapLaunchArgs mla{};
+        if (mi) {
+            const uint32_t esize = type_ref < vb::EDGE_REF ? s->A(type_ref).size : s->E(type_ref - vb::EDGE_REF).size;
+            if (mi->elem_size != esize) throw ArgError(std::string("map '") + mi->name + "': sizeof(Elem) does not match the registered size of " + mi->type_name);
+            if ((mi->is_float != 0) != isf) throw ArgError(std::string("map '") + mi->name + "': the result datatype must be " + (mi->is_float ? "floating point" : "integral"));
+            mla.cols = ma.cols; mla.stride = (uint32_t)ma.stride; mla.n = ma.n; mla.died = ma.died; mla.op = op; mla.stream = g_stream;
+        }
         const bool isb = result_dt == vb::DT_BOOL;
         if (isf && (op == vb::OP_AND || op == vb::OP_OR)) throw AssertionError("& and | are only supported for integer and boolean types");
         const unsigned nb = std::max<unsigned>(1, std::min<unsigned>(1024, nblk(ma.n)));
         double fres = 0; long long ires = 0;
         if (isf) {
             double* part = dalloc<double>(1024 + 1);
-            mapreduce_kernel<true><<<nb, 256, 0, g_stream>>>(ma, part); LAUNCH_CHECK();
+            if (mi) { mla.partial = part; mla.nblocks = nb; CK(mi->launch(mla)); ++g_launches; }
+            else { mapreduce_kernel<true><<<nb, 256, 0, g_stream>>>(ma, part); LAUNCH_CHECK(); }
             mapreduce_final_kernel<true><<<1, 256, 0, g_stream>>>(part, nb, op, part + 1024); LAUNCH_CHECK();
             CK(cudaMemcpyAsync(&fres, part + 1024, 8, cudaMemcpyDeviceToHost, g_stream));
             CK(cudaStreamSynchronize(g_stream));
             dfree(part);
         } else {
             long long* part = dalloc<long long>(1024 + 1);
-            mapreduce_kernel<false><<<nb, 256, 0, g_stream>>>(ma, part); LAUNCH_CHECK();
+            if (mi) { mla.partial = part; mla.nblocks = nb; CK(mi->launch(mla)); ++g_launches; }
+            else { mapreduce_kernel<false><<<nb, 256, 0, g_stream>>>(ma, part); LAUNCH_CHECK(); }
             mapreduce_final_kernel<false><<<1, 256, 0, g_stream>>>(part, nb, op, part + 1024); LAUNCH_CHECK();
             CK(cudaMemcpyAsync(&ires, part + 1024, 8, cudaMemcpyDeviceToHost, g_stream));
             CK(cudaStreamSynchronize(g_stream));
@@ -3544,6 +3564,21 @@ int vb_mapreduce(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64
             }
         }
     });
+}
+
+int vb_mapreduce(vb_sim* s, int type_ref, int offset, int dt, int has_cmp, int64_t cmp, int op, int result_dt, const void* init, void* out) {
+    return mapreduce_common(s, type_ref, offset, dt, has_cmp, cmp, op, result_dt, init, out, nullptr);
+}
+int vb_mapreduce_fn(vb_sim* s, const char* map_name, int type_ref, int op, int result_dt, const void* init, void* out) {
+    const vb::MapInfo* mi = nullptr;
+    int rc = guard([&] {
+        const std::string tname = type_ref < vb::EDGE_REF ? s->A(type_ref).name : s->E(type_ref - vb::EDGE_REF).name;
+        auto it = map_registry().find({map_name ? map_name : "", tname});
+        if (it == map_registry().end()) throw ArgError(std::string("map '") + (map_name ? map_name : "") + "' is not registered for type " + tname);
+        mi = it->second;
+    });
+    if (rc != VB_OK) return rc;
+    return mapreduce_common(s, type_ref, 0, vb::DT_I64, 0, 0, op, result_dt, init, out, mi);
 }
 
 namespace { size_t dt_size(int dt) { return (dt == VB_DT_I64 || dt == VB_DT_F64) ? 8 : (dt == VB_DT_I32 || dt == VB_DT_F32) ? 4 : 1; } }

@@ -6,5 +6,7 @@
 
 #define VB_PART 0
 #define VB_TRANSITION(tname, atype, ...) VB_REGISTER_TRANSITION(tname, atype, __VA_ARGS__)
+#define VB_MAP(mname, tname, ...) VB_REGISTER_MAP(mname, tname, __VA_ARGS__)
 #include "registry.inc"
+#undef VB_MAP
 #undef VB_TRANSITION

@@ -50,4 +50,21 @@ struct CalcPrice : vb::TransitionBase {    // tutorial1.jl:427-435
     }
 };
 
+// the two map closures of the tutorial that are more than a field selector (registered maps of mapreduce, vb::MapBase)
+struct XMinusY : vb::MapBase {             // mapreduce(sim, b -> b.x - b.y, +, Bought)   tutorial1.jl:548,577
+    using Elem = Bought;
+    using Result = double;
+    VB_HD double operator()(const Bought& b) const { return b.x - b.y; }
+};
+struct Revenue : vb::MapBase {             // mapreduce(sim, s -> s.p * s.d_y, +, Seller)  tutorial1.jl:566
+    using Elem = Seller;
+    using Result = double;
+    VB_HD double operator()(const Seller& s) const { return s.p * s.d_y; }
+};
+struct HasCustomers : vb::MapBase {        // an integral map: mapreduce(sim, s -> s.d_y > 0, +, Seller)
+    using Elem = Seller;
+    using Result = int64_t;
+    VB_HD int64_t operator()(const Seller& s) const { return s.d_y > 0 ? 1 : 0; }
+};
+
 }  // namespace market

@@ -375,7 +375,7 @@ end
 # ---- reductions -------------------------------------------------------------------------------------------------------
 "mapreduce(sim, field, op, T; init, equals): the reference's mapreduce(sim, a -> a.field, op, T) (src/AgentMethods.jl:533-565,
 src/EdgeMethods.jl:972-994) for op in (+, *, min, max, &, |); `equals = v` maps a -> (a.field == v) first; `field = nothing` maps _ -> 1.
-The map is a field selector because it has to run on the device; closures over anything else become a transition."
+The map is a field selector because it has to run on the device; any other closure is registered as a map functor (next method)."
 function Base.mapreduce(sim::Simulation, field::Union{Symbol,Nothing}, op, ::Type{T}; init = nothing, equals = nothing) where T
     if field === nothing
         off, fdt, FT = 0, -1, Int64
@@ -390,6 +390,17 @@ function Base.mapreduce(sim::Simulation, field::Union{Symbol,Nothing}, op, ::Typ
     initref = init === nothing ? C_NULL : Ref{RT}(RT(init))
     GC.@preserve initref check(ccall((:vb_mapreduce, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Int64, Cint, Cint, Ptr{Cvoid}, Ref{RT}),
                                      sim.handle, ref(sim, T), off, fdt, equals !== nothing, equals === nothing ? 0 : Int64(equals), OPS[op], DTS[RT],
+                                     init === nothing ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, initref), out))
+    out[]
+end
+
+"mapreduce(sim, mapname::String, op, T; datatype, init): the map is a functor registered with VB_REGISTER_MAP for T, i.e. any closure of the
+reference's mapreduce(sim, f, op, T), e.g. b -> b.x - b.y (docs/examples/tutorial1.jl:548)."
+function Base.mapreduce(sim::Simulation, mapname::String, op, ::Type{T}; datatype::DataType = Float64, init = nothing) where T
+    out = Ref{datatype}()
+    initref = init === nothing ? C_NULL : Ref{datatype}(datatype(init))
+    GC.@preserve initref check(ccall((:vb_mapreduce_fn, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint, Cint, Cint, Ptr{Cvoid}, Ref{datatype}),
+                                     sim.handle, mapname, ref(sim, T), OPS[op], DTS[datatype],
                                      init === nothing ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, initref), out))
     out[]
 end
