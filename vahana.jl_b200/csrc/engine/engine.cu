@@ -2799,7 +2799,11 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
             AgentStore b = a;
             b.peers = AgentStore::PeerMap{};      // the copy maps its peers on its first halo exchange
             if (a.size && a.cap) { b.state[0] = (uint8_t*)dup(a.state[0], (size_t)a.stride() * a.size); b.state[1] = a.independent ? b.state[0] : (uint8_t*)dup(a.state[1], (size_t)a.stride() * a.size); }
-            if (!a.immortal && a.cap) { b.died[0] = (uint8_t*)dup(a.died[0], a.stride()); b.died[1] = (uint8_t*)dup(a.died[1], a.stride()); b.ghost_ids = (uint64_t*)dup(a.ghost_ids, (size_t)a.nghost * 8); b.send_slots = (uint32_t*)dup(a.send_slots, (a.send_off.empty() ? 0 : (size_t)a.send_off.back()) * 4); b.send_buf = nullptr; b.reuse = (uint32_t*)dup(a.reuse, (size_t)a.reuse_cap * 4); }
+            if (!a.immortal && a.cap) { b.died[0] = (uint8_t*)dup(a.died[0], a.stride()); b.died[1] = (uint8_t*)dup(a.died[1], a.stride()); b.reuse = (uint32_t*)dup(a.reuse, (size_t)a.reuse_cap * 4); }
+            // the ghost table and the per-peer send lists of a multi-rank simulation are owned per simulation, whatever the type's hints
+            b.ghost_ids = a.nghost ? (uint64_t*)dup(a.ghost_ids, (size_t)a.nghost * 8) : nullptr;
+            b.send_slots = (a.send_slots && !a.send_off.empty() && a.send_off.back()) ? (uint32_t*)dup(a.send_slots, (size_t)a.send_off.back() * 4) : nullptr;
+            b.send_buf = b.send_slots ? (uint8_t*)g_pool.alloc((size_t)a.send_off.back() * std::max<uint32_t>(a.size, 1)) : nullptr;   // pack buffer of the NCCL halo
             s->agents.push_back(b);
         }
         for (auto& e : o.edges) {
