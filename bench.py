@@ -260,7 +260,7 @@ def run_engine(args):
         dl_bytes = 0
         for _ in range(dl_steps):
             step()
-            dl_bytes = sim.all_agents("HKAgent").nbytes
+            dl_bytes = sim.all_agents("HKAgent", all_ranks=False).nbytes
         torch.cuda.synchronize()
         dl = {"value": E_local * dl_steps / (time.perf_counter() - t0), "unit": "edges/s (this rank)", "steps": dl_steps, "d2h_bytes_per_step": int(dl_bytes),
               "note": "apply! + all_agents(HKAgent) per step: every new state copied to host memory"}

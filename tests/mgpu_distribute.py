@@ -36,7 +36,7 @@ def main():
     old = np.array([vh.agent_id(1, 0, k) for k in range(1, n + 1)], dtype=np.uint64)     # rank 0's ids of the init phase
     owner = np.searchsorted(np.array(b[1:]), np.arange(n), side="right")
     assert len(m) == n and all(m[int(old[k])] == vh.agent_id(1, int(owner[k]), k - b[owner[k]] + 1) for k in range(0, n, 97))
-    assert len(g.all_agents("HKAgent")) == b[rank + 1] - b[rank]
+    assert len(g.all_agents("HKAgent", all_ranks=False)) == b[rank + 1] - b[rank]
     assert g.num_agents("HKAgent") == n and g.num_edges("Knows") == 2 * len(uv) + n
     o = None
     if rank == 0:
@@ -46,7 +46,7 @@ def main():
     sizes = [b[r + 1] - b[r] for r in range(world)]
     for step in range(5):
         g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-        mine = torch.from_numpy(g.all_agents("HKAgent")["opinion"].copy()).cuda()
+        mine = torch.from_numpy(g.all_agents("HKAgent", all_ranks=False)["opinion"].copy()).cuda()
         parts = []
         for r in range(world):
             t = mine if r == rank else torch.empty(sizes[r], dtype=torch.float64, device="cuda")

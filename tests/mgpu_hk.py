@@ -32,7 +32,7 @@ def main():
                                                    C.c_uint64(50000), C.c_uint32(rank), C.c_uint32(world), C.byref(ne)))
     g.finish_init(distribute=False)   # SPMD initialisation: every rank added its own block
     bounds = vh.equal_partition(n, world)
-    assert len(g.all_agents("HKAgent")) == bounds[rank + 1] - bounds[rank]
+    assert len(g.all_agents("HKAgent", all_ranks=False)) == bounds[rank + 1] - bounds[rank]
 
     o = None
     if rank == 0:   # the oracle runs the whole graph on one rank
@@ -55,7 +55,7 @@ def main():
 
     for step in range(4):
         g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-        mine = torch.from_numpy(g.all_agents("HKAgent")["opinion"].copy()).cuda()
+        mine = torch.from_numpy(g.all_agents("HKAgent", all_ranks=False)["opinion"].copy()).cuda()
         sizes = [bounds[r + 1] - bounds[r] for r in range(world)]
         parts = [torch.empty(s, dtype=torch.float64, device="cuda") for s in sizes]
         dist.all_gather(parts, mine) if len(set(sizes)) == 1 else [dist.broadcast(parts[r] if r != rank else mine, src=r) for r in range(world)]

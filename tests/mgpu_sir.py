@@ -54,8 +54,8 @@ def main():
     for step in range(8):
         sir_step(g, step)
         nv, ne = g.num_edges("Visit"), g.num_edges("Exposure")
-        ps = gather(g.all_agents("Person").view("i2").astype("i4"), psz, rank, world)
-        ls = gather(g.all_agents("Location")["n_inf"].copy(), lsz, rank, world)
+        ps = gather(g.all_agents("Person", all_ranks=False).view("i2").astype("i4"), psz, rank, world)
+        ls = gather(g.all_agents("Location", all_ranks=False)["n_inf"].copy(), lsz, rank, world)
         if rank == 0:
             sir_step(o, step)
             assert nv == o.num_edges("Visit") == 2 * npers and ne == o.num_edges("Exposure") == 2 * npers

@@ -65,6 +65,8 @@ def test_plan_explicit_partition_and_errors():
     m = dict(zip(old.tolist(), new.tolist()))
     assert m[int(a[1])] == vh.agent_id(1, 0, 1) and m[int(a[4])] == vh.agent_id(1, 0, 2) and m[int(a[3])] == vh.agent_id(1, 1, 3)
     assert np.array_equal(vh.updateids(m, a[:2]), [vh.agent_id(1, 1, 1), vh.agent_id(1, 0, 1)])
+    # every rank ran the initialisation code with ids of its own rank: the rank bits of the old id do not matter (remove_process, src/Simulation.jl:481)
+    assert vh.updateids(m, vh.agent_id(1, 3, 2)) == vh.agent_id(1, 0, 1) and vh.remove_process(vh.agent_id(2, 5, 7)) == vh.agent_id(2, 0, 7)
     with pytest.raises(AssertionError):
         vh.plan_distribution({1: (a, None)}, {}, 2, {int(a[0]): 1})                  # an agent without a rank
     with pytest.raises(AssertionError):
@@ -150,6 +152,9 @@ for k, old in enumerate(rank0_ids):
 f, t = lib.edges[sim._eid["EdgeS"]][0]
 mine = [k for k in range(n) if vh.process_nr(m[int(rank0_ids[(k + 1) % n])]) == rank]
 assert np.array_equal(t, [m[int(rank0_ids[(k + 1) % n])] for k in mine]) and np.array_equal(f, [m[int(rank0_ids[k])] for k in mine])
+# join (src/MPI.jl:481-517) behind all_agents / all_agentids / all_edges(all_ranks = true): rank order, on every rank
+j = sim._join(np.arange(rank + 2) + 10 * rank)
+assert np.array_equal(j, np.concatenate([np.arange(r + 2) + 10 * r for r in range(world)]))
 # device-side bulk adds cannot be handed out
 sim2 = vh.create_simulation(edges_model(), backend=be)
 sim2._unstageable = "add_agents_device"

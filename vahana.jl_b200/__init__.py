@@ -243,9 +243,18 @@ def plan_distribution(agents: dict, edges: dict, world: int, partition: Optional
     return shards, old, new, bounds
 
 
+def remove_process(aid: int) -> int:
+    """remove_process (src/Agent.jl:81-82): the id with its rank bits cleared"""
+    return int(aid) & ~(((1 << BITS_PROCESS) - 1) << SHIFT_RANK)
+
+
 def updateids(idmapping, oldids):
-    """updateids(idmap, oldids) (src/Simulation.jl:479-483, a helper of the reference's tests)"""
-    return np.array([idmapping[int(i)] for i in np.asarray(oldids).reshape(-1)], dtype=np.uint64)
+    """updateids(idmap, oldids) (src/Simulation.jl:479-483, a helper of the reference's tests): the ids of the initialisation phase
+    -> the ids after finish_init!.  The rank bits of the old id are ignored (every rank ran the same initialisation code with ids
+    of its own rank; the mapping is keyed by rank 0's)."""
+    scalar = np.ndim(oldids) == 0
+    out = np.array([idmapping[remove_process(i)] for i in np.asarray(oldids, dtype=np.uint64).reshape(-1)], dtype=np.uint64)
+    return int(out[0]) if scalar else out
 
 
 def load_backend(path: Optional[str] = None) -> Backend:
@@ -725,7 +734,7 @@ class Simulation:
         if distribute and return_idmapping and world.value == 1:
             idmapping = {}
             for name in self.model.types.agent_names:
-                for i in self.all_agentids(name):
+                for i in self.all_agentids(name, all_ranks=False):
                     idmapping[int(i)] = int(i)
         self._log_end("finish_init!")
         return idmapping if (distribute and return_idmapping) else self
@@ -840,12 +849,33 @@ class Simulation:
                                         ids.ctypes.data_as(C.c_void_p), C.c_uint64(n.value), C.byref(n)))
         return states, ids
 
-    def all_agents(self, type_name: str) -> np.ndarray:
-        assert self._adt(type_name) is not None, "all_agents can be only called for agent types that have fields"
-        return self._all(type_name)[0]
+    def _world(self) -> int:
+        w, r = C.c_int(1), C.c_int(0)
+        if hasattr(self.lib, "vb_comm_rank"):
+            self.lib.vb_comm_rank(C.byref(r), C.byref(w))
+        return w.value
 
-    def all_agentids(self, type_name: str) -> np.ndarray:
-        return self._all(type_name)[1]
+    def _join(self, arr: Optional[np.ndarray]):
+        """join (src/MPI.jl:481-517): the ranks' vectors concatenated in rank order, on every rank (collective; host data)"""
+        if arr is None or self._world() == 1:
+            return arr
+        import torch.distributed as dist
+        assert dist.is_available() and dist.is_initialized(), "all_ranks=True on several ranks needs torch.distributed (or pass all_ranks=False)"
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, arr)
+        return np.concatenate(parts)
+
+    def all_agents(self, type_name: str, all_ranks: bool = True) -> np.ndarray:
+        """all_agents(sim, T, [all_ranks = true]) (src/Agent.jl:234-262): the states of the live agents in ascending nr; on several
+        ranks joined in rank order (collective) unless all_ranks is false"""
+        assert self._adt(type_name) is not None, "all_agents can be only called for agent types that have fields"
+        st = self._all(type_name)[0]
+        return self._join(st) if all_ranks else st
+
+    def all_agentids(self, type_name: str, all_ranks: bool = True) -> np.ndarray:
+        """all_agentids(sim, T, [all_ranks = true]) (src/Agent.jl:287-313), same order as all_agents"""
+        ids = self._all(type_name)[1]
+        return self._join(ids) if all_ranks else ids
 
     def agentstate(self, aid: int, type_name: str):
         dt = self._adt(type_name)
@@ -930,7 +960,14 @@ class Simulation:
     def has_edge(self, to: int, edge_name: str) -> bool:
         return self._row(to, edge_name, ACC_HAS_EDGE)[2] >= 1
 
-    def all_edges(self, edge_name: str):
+    def all_edges(self, edge_name: str, all_ranks: bool = True):
+        """all_edges(sim, T, [all_ranks = true]) (src/EdgeMethods.jl:1005-1027) as three aligned arrays (to, from, states)"""
+        to, fr, st = self._all_edges_local(edge_name)
+        if all_ranks and self._world() > 1:
+            to, fr, st = self._join(to), self._join(fr), self._join(st)
+        return to, fr, st
+
+    def _all_edges_local(self, edge_name: str):
         n = C.c_uint64()
         e = C.c_int(self._eid[edge_name])
         self._ck(self.lib.vb_all_edges(self.h, e, None, None, None, C.c_uint64(0), C.byref(n)))
