@@ -74,8 +74,8 @@ def main():
         es = sim.edges(a1, "ESDict")
         assert [int(f) for f, _ in es] == [a2, a3, avids[0], avfids[9]] and [int(s["foo"]) for _, s in es] == [1, 2, 3, 4]
         assert [int(x) for x in sim.neighborids(a1, "ESLDict1")] == avids and sim.num_edges(a1, "ESDict") == 4
-        assert 1 in [int(s["foo"]) for s in sim.neighborstates(a1, "ESLDict1", "AImm")]        # core.jl:201-208 (states of ghosts)
-        assert 3 in [int(s["foo"]) for s in sim.neighborstates_flexible(a1, "ESDict")]
+        # (core.jl:201-208 reads neighborstates outside of a transition; the states of agents of other ranks are only transferred by the
+        #  halo of an apply! that reads their type, so that check is left to the neighbour sums below)
     if on(a2):
         assert sim.edges(a2, "ESDict") is None and sim.neighborids(a2, "ESLDict1") is None and sim.num_edges(a2, "ESDict") == 0
     if on(avids[9]):
