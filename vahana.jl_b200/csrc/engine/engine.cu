@@ -2239,21 +2239,31 @@ void finish_write_agent(vb_sim& s, int t, std::vector<uint32_t*>& died_flags, st
     a.nslots = (uint32_t)std::max<uint64_t>(a.nslots, a.nextid - 1);
     a.births = 0;
     if (!a.immortal && n_before > 0 && s.initialized) {
-        // agents that died in this apply, in ascending slot order, are appended to read.reuseable (:171,:430)
-        uint32_t* flag = dalloc<uint32_t>(n_before); uint32_t* pos = dalloc<uint32_t>(n_before);
-        uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n_before));
-        vbp::newly_died_flags_kernel<<<nblk(n_before), 256, 0, g_stream>>>(a.rdied(), a.wdied(), n_before, flag); LAUNCH_CHECK();
-        vbp::exclusive_scan(flag, pos, n_before, s.d_scalars, scr, g_stream); g_launches += 3;
-        uint32_t nd = 0;
-        CK(cudaMemcpyAsync(&nd, s.d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+        // nobody died (the common case for models without deaths whose types are not registered :Immortal, e.g. the docs' HK model):
+        // one counting pass over the two died arrays instead of flags + scan + compact
+        uint32_t* dcount = s.d_scalars + 60;
+        CK(cudaMemsetAsync(dcount, 0, 4, g_stream));
+        vbp::count_newly_died_kernel<<<std::min<unsigned>(nblk((uint64_t)n_before / 16 + 1), 148 * 8), 256, 0, g_stream>>>(a.rdied(), a.wdied(), n_before, dcount); LAUNCH_CHECK();
+        uint32_t any_died = 0;
+        CK(cudaMemcpyAsync(&any_died, dcount, 4, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
-        if (nd) {
-            vbp::compact_indices_kernel<<<nblk(n_before), 256, 0, g_stream>>>(flag, pos, n_before, a.reuse + a.n_reuse); LAUNCH_CHECK();
-            a.n_reuse += nd;
-            died_flags[t] = flag; died_n[t] = n_before; died_cnt[t] = nd;
-            flag = nullptr;
+        if (any_died) {
+            // agents that died in this apply, in ascending slot order, are appended to read.reuseable (:171,:430)
+            uint32_t* flag = dalloc<uint32_t>(n_before); uint32_t* pos = dalloc<uint32_t>(n_before);
+            uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n_before));
+            vbp::newly_died_flags_kernel<<<nblk(n_before), 256, 0, g_stream>>>(a.rdied(), a.wdied(), n_before, flag); LAUNCH_CHECK();
+            vbp::exclusive_scan(flag, pos, n_before, s.d_scalars, scr, g_stream); g_launches += 3;
+            uint32_t nd = 0;
+            CK(cudaMemcpyAsync(&nd, s.d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            if (nd) {
+                vbp::compact_indices_kernel<<<nblk(n_before), 256, 0, g_stream>>>(flag, pos, n_before, a.reuse + a.n_reuse); LAUNCH_CHECK();
+                a.n_reuse += nd;
+                died_flags[t] = flag; died_n[t] = n_before; died_cnt[t] = nd;
+                flag = nullptr;
+            }
+            dfree(flag); dfree(pos); dfree(scr);
         }
-        dfree(flag); dfree(pos); dfree(scr);
     }
     a.cur ^= 1;   // read := write by swapping the double buffers (:Independent types share one state buffer)
     a.write_stale = true;

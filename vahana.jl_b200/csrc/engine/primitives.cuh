@@ -558,6 +558,29 @@ static __global__ void newly_died_flags_kernel(const uint8_t* __restrict__ died_
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = (died_w[i] && !died_r[i]) ? 1u : 0u;
 }
+// how many slots died in this apply (same predicate), without materialising the flags: one 16-byte load of each array per 16 slots.
+// finish_write! of a mortal type whose transition killed nobody (the common case) then skips the flags + scan + compact passes
+// (1.8 GB of traffic at 1e8 slots against 0.2 GB for this count).  Both arrays are 16-byte aligned (pool allocations).
+static __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) { return (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u; }
+static __global__ void __launch_bounds__(256) count_newly_died_kernel(const uint8_t* __restrict__ died_r, const uint8_t* __restrict__ died_w, uint32_t n,
+                                                                      uint32_t* __restrict__ count) {
+    const uint32_t nvec = n / 16;
+    const uint4* r4 = reinterpret_cast<const uint4*>(died_r);
+    const uint4* w4 = reinterpret_cast<const uint4*>(died_w);
+    uint32_t c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 r = r4[i], w = w4[i];
+        c += __popc(nonzero_bytes(w.x) & ~nonzero_bytes(r.x)) + __popc(nonzero_bytes(w.y) & ~nonzero_bytes(r.y)) +
+             __popc(nonzero_bytes(w.z) & ~nonzero_bytes(r.z)) + __popc(nonzero_bytes(w.w) & ~nonzero_bytes(r.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - nvec * 16) {      // tail of fewer than 16 slots
+        const uint32_t i = nvec * 16 + threadIdx.x;
+        c += (died_w[i] && !died_r[i]) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
 static __global__ void alive_flags_kernel(const uint8_t* __restrict__ died, uint32_t n, uint32_t* __restrict__ flag) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = died ? (died[i] ? 0u : 1u) : 1u;
