@@ -65,6 +65,22 @@ def main():
             sim = fresh(ET, "cycle")
             sim.apply(f"remove_and_readd_{ET}", "Agent", ET, ET, add_existing=ET)
             assert sim.num_edges(ET) == 100, (ET, sim.num_edges(ET))
+    # the order rule (src/Simulation.jl:792-800): a travelling removal is applied before the new edges arrive.  Every agent clears its
+    # neighbour's row (on the previous rank for a block's first agent) and points an edge back at it: 100 edges, all reversed.
+    for ET in ["EdgeD", "EdgeS", "EdgeT"]:
+        sim = fresh(ET, "cycle")
+        sim.apply(f"clear_neighbor_row_and_point_back_{ET}", "Agent", ["Agent", ET], ET, add_existing=ET)
+        assert sim.num_edges(ET) == 100, (ET, sim.num_edges(ET))
+        bounds = vh.equal_partition(N, world)
+        mine = sim.all_agentids("Agent", all_ranks=False)
+        sim.disable_transition_checks(True)
+        for k, aid in enumerate(mine):
+            g = bounds[rank] + k                                                  # global index; the successor owns the only edge of this row
+            succ = (g + 1) % N
+            owner = int(np.searchsorted(np.array(bounds[1:]), succ, side="right"))
+            nb = sim.neighborids(int(aid), ET)
+            assert [int(x) for x in np.atleast_1d(nb)] == [vh.agent_id(1, owner, succ - bounds[owner] + 1)], (ET, g, nb)
+        sim.disable_transition_checks(False)
     for ET in REMOVE_FROM_TYPES:                                                  # test_edgetypes.jl:354-449
         single = "E" in ET[4:]
         kind = "cycle" if single else "complete"

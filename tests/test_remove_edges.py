@@ -74,6 +74,24 @@ def test_remove_edges_gpu_matches_oracle_exactly(oracle, cuda, ET):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+@pytest.mark.parametrize("ET", ["EdgeD", "EdgeS", "EdgeT"])
+def test_remove_other_row_then_add(oracle, ET):
+    """a removal that names another agent's row, followed by an add to that row (the order rule of src/Simulation.jl:792-800):
+    on the cycle i-1 -> i every row ends up with exactly the reversed edge.  (GPU variant: tests/test_zzn_remove_order.py)"""
+    _check_reversed_cycle(_graph_sim(oracle, ET, "cycle"), ET)
+
+
+def _check_reversed_cycle(sim, ET, n=100):
+    ids = sim.all_agentids("Agent")
+    sim.apply(f"clear_neighbor_row_and_point_back_{ET}", "Agent", ["Agent", ET], ET, add_existing=ET)
+    assert sim.num_edges(ET) == n
+    off, fr, st = sim.export_csr(ET, "Agent", n)
+    assert np.array_equal(off, np.arange(n + 1))
+    assert np.array_equal(fr, np.roll(ids, -1))                      # row i holds the edge from i + 1
+    if st is not None:
+        assert np.all(st["foo"] == 7)
+
+
 def test_remove_edges_init_phase(backend):   # remove_edges! is allowed until finish_init! (EdgeMethods.jl:101-106)
     sim = vh.create_simulation(edges_model(), backend=backend)
     a, b, c = (int(x) for x in sim.add_agents("Agent", foos([1, 2, 3])))

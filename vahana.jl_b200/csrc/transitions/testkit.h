@@ -123,6 +123,21 @@ template <int E, bool kStateful> struct RemoveAndReadd : vb::TransitionBase {   
         return true;
     }
 };
+// The order rule of a removal that names another agent's row (src/Simulation.jl:792-800: removes travel and are applied before the
+// new edges arrive): every agent clears the row of its neighbour and then points an edge back at it.  On the cycle i-1 -> i every row
+// ends up holding exactly the reversed edge, on one rank (program order) and on several (the removal request reaches the row's rank
+// before the new edge does).
+template <int E, bool kStateful> struct ClearNeighborRowAndPointBack : vb::TransitionBase {
+    using State = Foo;
+    using EdgeRemoves = vb::IntList<E>;
+    using EdgeWrites = vb::IntList<E>;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
+        const vb::AgentID nid = ctx.neighbor_at(E, id, 0);
+        ctx.remove_edges(E, nid);
+        if (kStateful) ctx.add_edge(E, id, nid, EFoo{7}); else ctx.add_edge(E, id, nid);
+        return true;
+    }
+};
 template <int E, bool kSingle> struct RemoveFirstTwoFrom : vb::TransitionBase {   // :385-392
     using State = Foo;
     using EdgeRemoves = vb::IntList<E>;
