@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import vahana_b200 as vh  # noqa: E402
+from mgpu_common import setup  # noqa: E402
 from models import core_model, add_example_network  # noqa: E402
 
 ALLAGENTTYPES = ["AMortal", "AImm", "AImmFixed"]
@@ -39,14 +40,7 @@ def createsim(be, local, loops=()):
 
 
 def main():
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rank, world = dist.get_rank(), dist.get_world_size()
-    be = vh.default_backend()
-    be.init(local)
-    be.set_stream(torch.cuda.current_stream().cuda_stream)
-    be.init_distributed()
+    be, local, rank, world, _ = setup()
     on = lambda aid: vh.process_nr(aid) == rank   # noqa: E731  (@onrankof)
 
     sim, a1, a2, a3, avids, avfids = createsim(be, local)

@@ -13,19 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import vahana_b200 as vh  # noqa: E402
+from mgpu_common import setup, oracle_backend  # noqa: E402
 from models import hk_model, hk_sim, ba_graph  # noqa: E402
 
 
 def main():
     n = int(os.environ.get("MGPU_N", "20000"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rank, world = dist.get_rank(), dist.get_world_size()
-    be = vh.default_backend()
-    be.init(local)
-    be.set_stream(torch.cuda.current_stream().cuda_stream)
-    be.init_distributed()
+    be, local, rank, world, dev = setup()
     uv = ba_graph(n, 8, 1)
     op0 = np.random.default_rng(1).random(n)
     g = vh.create_simulation(hk_model(), params={"eps": 0.02}, backend=be, device=local)
@@ -40,16 +34,14 @@ def main():
     assert g.num_agents("HKAgent") == n and g.num_edges("Knows") == 2 * len(uv) + n
     o = None
     if rank == 0:
-        import subprocess
-        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-        o, _ = hk_sim(vh.load_backend(os.path.join(ROOT, "oracle", "_build", "libvahana_oracle.so")), n, uv, op0)
+        o, _ = hk_sim(oracle_backend(), n, uv, op0)
     sizes = [b[r + 1] - b[r] for r in range(world)]
     for step in range(5):
         g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
-        mine = torch.from_numpy(g.all_agents("HKAgent", all_ranks=False)["opinion"].copy()).cuda()
+        mine = torch.from_numpy(g.all_agents("HKAgent", all_ranks=False)["opinion"].copy()).to(dev)
         parts = []
         for r in range(world):
-            t = mine if r == rank else torch.empty(sizes[r], dtype=torch.float64, device="cuda")
+            t = mine if r == rank else torch.empty(sizes[r], dtype=torch.float64, device=dev)
             dist.broadcast(t, src=r)
             parts.append(t)
         if rank == 0:

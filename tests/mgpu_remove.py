@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import vahana_b200 as vh  # noqa: E402
+from mgpu_common import setup  # noqa: E402
 from models import edges_model, foos  # noqa: E402
 
 REMOVE_TYPES = ["EdgeD", "EdgeS", "EdgeE", "EdgeI", "EdgeSE", "EdgeSI", "EdgeEI", "EdgeSEI", "EdgeSTI", "EdgeSETI", "EdgeT", "EdgeST"]
@@ -43,14 +44,7 @@ def graph_sim(be, local, rank, world, ET, kind):
 
 
 def main():
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rank, world = dist.get_rank(), dist.get_world_size()
-    be = vh.default_backend()
-    be.init(local)
-    be.set_stream(torch.cuda.current_stream().cuda_stream)
-    be.init_distributed()
+    be, local, rank, world, _ = setup()
     fresh = lambda ET, kind: graph_sim(be, local, rank, world, ET, kind)    # noqa: E731  (a new simulation per apply: no copy_simulation)
     for ET in REMOVE_TYPES:                                                       # test_edgetypes.jl:295-352
         sim = fresh(ET, "cycle")
