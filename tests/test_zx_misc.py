@@ -125,3 +125,26 @@ def test_duration_log_in_the_reference_format(oracle, tmp_path):  # src/Logging.
     assert "func = identity" in recs[1][3] and "transition = 2" in recs[1][3]       # finish_init! set num_transitions to 1
     assert "func = kill_all" in recs[2][3] and "transition = 3" in recs[2][3]
     assert all(float(r[2]) >= 0 for r in recs) and float(recs[0][0]) <= float(recs[1][0]) <= float(recs[2][0])
+
+
+def test_graph_bridges(oracle):
+    """add_graph! from a graph object and vahanagraph (src/GraphsSupport.jl:34-57,212-289; test/graphs.jl:37-43: K4 id sums)"""
+    import networkx as nx
+    from models import hk_model
+    sim = vh.create_simulation(hk_model(), backend=oracle)
+    g = nx.complete_graph(4)
+    ids = vh.add_graph(sim, g, None, "HKAgent", np.arange(4.0).view([("opinion", "f8")]), "Knows")
+    sim.finish_init()
+    assert sim.num_edges("Knows") == 12 and len(ids) == 4
+    vg = vh.vahanagraph(sim)
+    assert np.array_equal(vg["g2v"], ids) and len(vg["src"]) == 12 and set(vg["edgetype"].tolist()) == {0}
+    assert sorted(zip(vg["src"].tolist(), vg["dst"].tolist())) == sorted((u, v) for u in range(4) for v in range(4) if u != v)
+    back = vh.to_networkx(sim)
+    assert back.number_of_nodes() == 4 and back.number_of_edges() == 12 and back.nodes[2]["id"] == int(ids[2])
+    d = nx.DiGraph([(0, 1), (1, 2), (2, 0), (0, 1)])            # a directed graph: one Vahana edge per graph edge
+    sim2 = vh.create_simulation(hk_model(), backend=oracle)
+    vh.add_graph(sim2, d, None, "HKAgent", np.zeros(3).view([("opinion", "f8")]), "Knows")
+    sim2.add_edges(sim2.all_agentids("HKAgent")[:1], sim2.all_agentids("HKAgent")[1:2], "Knows")    # a parallel edge 0 -> 1
+    sim2.finish_init()
+    assert sim2.num_edges("Knows") == 4
+    assert len(vh.vahanagraph(sim2, drop_multiedges=True)["src"]) == 3

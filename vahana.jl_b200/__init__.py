@@ -1084,10 +1084,17 @@ def apply(sim: Simulation, transition: str, call, read, write, **kwargs) -> Simu
     return sim.apply_copy(transition, call, read, write, **kwargs)
 
 
-def add_graph(sim: Simulation, edges_uv: np.ndarray, n: int, agent_type: str, agent_states, edge_type: str, edge_states=None,
+def add_graph(sim: Simulation, edges_uv, n: Optional[int], agent_type: str, agent_states, edge_type: str, edge_states=None,
               directed: bool = False) -> np.ndarray:
     """add_graph!(sim, graph, agent_constructor, edge_constructor) (src/GraphsSupport.jl:34-57): one agent per vertex, then
-    for every edge (u,v) of the graph an edge u->v and, for undirected graphs, v->u, in the graph's edge order."""
+    for every edge (u,v) of the graph an edge u->v and, for undirected graphs, v->u, in the graph's edge order.
+    `edges_uv` is an (m, 2) array of 0-based vertex pairs, or a networkx graph with vertices 0..n-1 (then `n` and `directed` are
+    taken from the graph)."""
+    if hasattr(edges_uv, "number_of_nodes") and hasattr(edges_uv, "edges"):          # a networkx (Di)Graph
+        g = edges_uv
+        n = g.number_of_nodes()
+        directed = bool(g.is_directed())
+        edges_uv = np.array(list(g.edges()), dtype=np.int64).reshape(-1, 2)
     ids = sim.add_agents(agent_type, agent_states, n)
     uv = np.asarray(edges_uv, dtype=np.int64).reshape(-1, 2)
     if directed:
@@ -1099,3 +1106,55 @@ def add_graph(sim: Simulation, edges_uv: np.ndarray, n: int, agent_type: str, ag
         st = None if edge_states is None else np.repeat(np.asarray(edge_states), 2)
     sim.add_edges(fr, to, edge_type, st)
     return ids
+
+
+def vahanagraph(sim: Simulation, agenttypes=None, edgetypes=None, drop_multiedges: bool = False) -> dict:
+    """vahanagraph(sim; agenttypes, edgetypes, drop_multiedges) (src/GraphsSupport.jl:212-289) as plain arrays: the live agents of
+    `agenttypes` become vertices 0..nv-1 (type order, then ascending nr: `g2v` maps vertex -> AgentID), every edge of `edgetypes`
+    whose two ends are vertices becomes (src, dst) with `edgetype` = index into `edgetypes`; :IgnoreFrom types are skipped as in
+    the reference.  Returns {"g2v", "src", "dst", "edgetype"}; `to_networkx` wraps it into a networkx.MultiDiGraph for plotting."""
+    t = sim.model.types
+    agenttypes = list(agenttypes) if agenttypes is not None else list(t.agent_names)
+    edgetypes = list(edgetypes) if edgetypes is not None else list(t.edge_names)
+    g2v = np.concatenate([sim.all_agentids(a, all_ranks=False) for a in agenttypes]) if agenttypes else np.zeros(0, dtype=np.uint64)
+    order = np.argsort(g2v, kind="stable")
+    sorted_ids = g2v[order]
+
+    def vertex(ids):
+        k = np.searchsorted(sorted_ids, ids)
+        k = np.minimum(k, max(len(sorted_ids) - 1, 0))
+        ok = (sorted_ids[k] == ids) if len(sorted_ids) else np.zeros(len(ids), dtype=bool)
+        return np.where(ok, order[k] if len(sorted_ids) else 0, -1)
+    src, dst, et = [], [], []
+    seen = set()
+    for idx, name in enumerate(edgetypes):
+        if "IgnoreFrom" in t.edge_hints[name]:
+            continue
+        to, fr, _ = sim.all_edges(name, all_ranks=False)
+        f, d = vertex(fr), vertex(to)
+        keep = (f >= 0) & (d >= 0)
+        f, d = f[keep], d[keep]
+        if drop_multiedges:
+            sel = []
+            for i, pair in enumerate(zip(f.tolist(), d.tolist())):
+                if pair not in seen:
+                    seen.add(pair)
+                    sel.append(i)
+            f, d = f[sel], d[sel]
+        src.append(f)
+        dst.append(d)
+        et.append(np.full(len(f), idx, dtype=np.int64))
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, dtype=np.int64)   # noqa: E731
+    return {"g2v": g2v, "src": cat(src), "dst": cat(dst), "edgetype": cat(et)}
+
+
+def to_networkx(sim: Simulation, agenttypes=None, edgetypes=None, drop_multiedges: bool = False):
+    """the vahanagraph as a networkx.MultiDiGraph (vertex attribute `id` = AgentID, edge attribute `edgetype`)"""
+    import networkx as nx
+    vg = vahanagraph(sim, agenttypes, edgetypes, drop_multiedges)
+    g = nx.MultiDiGraph()
+    for v, aid in enumerate(vg["g2v"].tolist()):
+        g.add_node(v, id=aid)
+    for s_, d_, e_ in zip(vg["src"].tolist(), vg["dst"].tolist(), vg["edgetype"].tolist()):
+        g.add_edge(s_, d_, edgetype=e_)
+    return g
