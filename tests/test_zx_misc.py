@@ -148,3 +148,29 @@ def test_graph_bridges(oracle):
     sim2.finish_init()
     assert sim2.num_edges("Knows") == 4
     assert len(vh.vahanagraph(sim2, drop_multiedges=True)["src"]) == 3
+
+
+def test_show_and_dataframes(oracle):
+    """show(sim) (src/REPL.jl:81-168), DataFrame(sim, T) and GlobalsDataFrame(sim) (src/optional/DataFrames.jl:54-185)"""
+    from models import market_inputs, market_sim, market_step
+    buyers, sellers, picks = market_inputs(20, 3, 2, seed=1)
+    sim = market_sim(oracle, buyers, sellers, picks)
+    for step in range(3):
+        market_step(sim, step)
+    text = sim.show()
+    assert "Model Name: Excess Demand" in text and "Type Buyer with 20 agent(s)" in text and "Type Seller with 3 agent(s)" in text
+    assert "Type KnownSeller with 40 edge(s)" in text and "Type Bought with 20 edge(s)" in text
+    assert ":x_minus_y |> last :" in text and "(length: 3)" in text and "initialization" not in text
+    df = sim.dataframe("Seller")
+    assert list(df.columns) == ["id", "p", "d_y"] and len(df) == 3 and np.array_equal(df["p"].to_numpy(), sim.all_agents("Seller")["p"])
+    assert np.array_equal(df["id"].to_numpy(), sim.all_agentids("Seller"))
+    de = sim.dataframe("Bought", types=True)
+    assert list(de.columns) == ["from", "from_type", "to", "to_type", "x", "y"] and len(de) == 20
+    assert set(de["from_type"]) == {"Buyer"} and set(de["to_type"]) == {"Seller"}
+    assert sim.dataframe("Bought", localnr=True)["to"].max() <= 3
+    g = sim.globals_dataframe()
+    assert list(g.columns) == ["x_minus_y", "p"] and len(g) == 3
+    # a simulation that is still being initialised says so, a raster is listed with its dimensions
+    from models import hk_model
+    s2 = vh.create_simulation(hk_model(), backend=oracle)
+    assert "Still in initialization process!." in s2.show() and ":eps : 0.02" in s2.show()

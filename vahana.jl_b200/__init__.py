@@ -641,6 +641,9 @@ class Simulation:
         tuple of every cell in CartesianIndices (column-major) order, or is an array of states in that order."""
         self._unstageable = "add_raster"   # rasters are not handed out by finish_init(distribute=True) yet (broadcastids, src/MPI.jl:64-75)
         dims = tuple(int(d) for d in dims)
+        if not hasattr(self, "_rasters"):
+            self._rasters = {}
+        self._rasters[name] = dims
         n = int(np.prod(dims))
         dt = self._adt(type_name)
         if callable(agent_constructor):
@@ -1034,6 +1037,83 @@ class Simulation:
         self._ck(self.lib.vb_mapreduce_fn(self.h, map_name.encode(), C.c_int(ref), C.c_int(_OPS[op]), C.c_int(_DT[rdt]),
                                           ib.ctypes.data_as(C.c_void_p) if ib is not None else None, out.ctypes.data_as(C.c_void_p)))
         return out[0].item()
+
+    # -- observability (src/REPL.jl:81-168, src/optional/DataFrames.jl:54-163) --
+    def show(self) -> str:
+        """show(sim): the summary the reference prints at the REPL (model name, agents / edges per type, parameters, rasters, globals)"""
+        t = self.model.types
+        rank, world = C.c_int(0), C.c_int(1)
+        if hasattr(self.lib, "vb_comm_rank"):
+            self.lib.vb_comm_rank(C.byref(rank), C.byref(world))
+        out = [f"Model Name: {self.model.name}"]
+        if t.agent_names:
+            out.append("Agent(s):")
+        for a in t.agent_names:
+            line = f"\t Type {a} with {self.num_agents(a)} agent(s)"
+            if world.value > 1:
+                line += f" ({len(self.all_agentids(a, all_ranks=False))} on rank {rank.value})"
+            out.append(line)
+        if t.edge_names:
+            out.append("Edge(s):")
+        for e in t.edge_names:
+            out.append(f"\t Type {e} with {self.num_edges(e)} edge(s)")
+        if self._params is not None:
+            out.append("Parameter(s):")
+            for k in self._params.dtype.names:
+                out.append(f"\t :{k} : {self._params[k]}")
+        if getattr(self, "_rasters", None):
+            out.append("Raster(s):")
+            for k, dims in self._rasters.items():
+                out.append(f"\t :{k} with dimension {tuple(dims)}")
+        if self.globals:
+            out.append("Global(s):")
+            for k, v in self.globals.items():
+                if isinstance(v, (list, np.ndarray)):
+                    out.append(f"\t :{k} (empty)" if len(v) == 0 else f"\t :{k} |> last : {v[-1]} (length: {len(v)})")
+                else:
+                    out.append(f"\t :{k} : {v}")
+        n = C.c_int64(0)
+        self.lib.vb_num_transitions(self.h, C.byref(n))
+        if n.value == 0:
+            out.append("Still in initialization process!.")
+        return "\n".join(out)
+
+    def dataframe(self, type_name: str, types: bool = False, localnr: bool = False):
+        """DataFrame(sim, T; types, localnr) (src/optional/DataFrames.jl:54-163) as a pandas DataFrame: agents -> id + one column per
+        field; edges -> from, to + one column per field.  As in the reference only the local partition of a parallel run."""
+        import pandas as pd
+        if localnr:
+            types = True
+        names = {v: k for k, v in self._aid.items()}
+        nr = lambda ids: (ids & np.uint64((1 << BITS_AGENTNR) - 1)) if localnr else ids          # noqa: E731
+        tn = lambda ids: [names.get(int(i) >> SHIFT_TYPE) for i in ids]                            # noqa: E731
+        if type_name in self._aid:
+            states, ids = self._all(type_name)
+            df = pd.DataFrame({"id": nr(ids)})
+            if states is not None:
+                for f in states.dtype.names:
+                    df[f] = states[f]
+            return df
+        to, fr, st = self.all_edges(type_name, all_ranks=False)
+        df = pd.DataFrame()
+        if "IgnoreFrom" not in self.model.types.edge_hints[type_name]:
+            df["from"] = nr(fr)
+            if types:
+                df["from_type"] = tn(fr)
+        df["to"] = nr(to)
+        if types:
+            df["to_type"] = tn(to)
+        if st is not None:
+            for f in st.dtype.names:
+                df[f] = st[f]
+        return df
+
+    def globals_dataframe(self):
+        """GlobalsDataFrame(sim) (src/optional/DataFrames.jl:165-185): the vector-valued globals as columns"""
+        import pandas as pd
+        cols = {k: list(v) for k, v in self.globals.items() if isinstance(v, (list, np.ndarray))}
+        n = max([len(v) for v in cols.values()], default=0)
+        return pd.DataFrame({k: v + [None] * (n - len(v)) for k, v in cols.items()})
 
     # -- raster read-out (Raster.jl:206-387) --
     def raster_info(self, name: str):
