@@ -75,7 +75,8 @@ def test_plan_explicit_partition_and_errors():
         vh.plan_distribution({1: (a, None)}, {"E": (a[:1], np.array([vh.agent_id(1, 0, 99)], dtype=np.uint64), None)}, 2)   # dangling id
 
 
-def test_finish_init_single_rank_idmapping_is_identity(backend):
+def test_finish_init_single_rank_idmapping_is_identity(oracle):
+    backend = oracle   # host logic of the mirror; the CUDA engine takes the same path in every GPU test that calls finish_init()
     from models import edges_model, foos
     sim = vh.create_simulation(edges_model(), backend=backend)
     ids = sim.add_agents("Agent", foos([1, 2, 3]))
