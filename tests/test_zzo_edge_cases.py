@@ -1,0 +1,64 @@
+"""Empty and ragged inputs: types without agents, edge types without edges, the identities of mapreduce on nothing (val4empty,
+src/Helpers.jl:44-81), rows of 0 / 1 / 3000 entries side by side.  Oracle in the CPU suite; the GPU variants sort behind the
+established suite (written after round 1's GPU budget was spent)."""
+import numpy as np
+import pytest
+
+import vahana_b200 as vh
+from models import core_model, foos
+
+INT_MAX = np.iinfo(np.int64).max
+
+
+def _empty_checks(backend):
+    sim = vh.create_simulation(core_model(), backend=backend)
+    sim.finish_init()
+    for T in ["AMortal", "AImm"]:
+        assert sim.num_agents(T) == 0 and len(sim.all_agentids(T)) == 0 and len(sim.all_agents(T)) == 0
+        assert sim.mapreduce("foo", "+", T) == 0 and sim.mapreduce("foo", "*", T) == 1
+        assert sim.mapreduce("foo", "max", T) == -INT_MAX and sim.mapreduce("foo", "min", T) == INT_MAX
+        assert sim.mapreduce("foo", "|", T, datatype="i8") == 0 and sim.mapreduce("foo", "&", T, datatype="i8") == INT_MAX
+        assert sim.mapreduce("foo", "+", T, init=5) == 5
+        sim.apply("identity" if T == "AMortal" else "sum_state_neighbors_ESLDict2", [T], [T] if T == "AMortal" else ["AMortal", "AImm", "AImmFixed", "ESLDict2"], [T])
+        assert sim.num_agents(T) == 0
+    for E in ["ESDict", "ESLDict1", "ESLDict2"]:
+        assert sim.num_edges(E) == 0
+    assert sim.mapreduce("foo", "+", "ESDict") == 0
+    assert sim.num_transitions() >= 2
+
+
+def _ragged_checks(backend):
+    """AMortal agents with 0, 1 and 3000 neighbours of type AImm (ESLDict1 is stateless): sum_state_neighbors folds each row"""
+    sim = vh.create_simulation(core_model(), backend=backend)
+    a = sim.add_agents("AMortal", foos([100, 200, 300]))
+    nb = sim.add_agents("AImm", foos(range(1, 3001)))
+    sim.add_edges(nb[:1], a[1:2], "ESLDict1")
+    sim.add_edges(nb, np.full(3000, a[2], dtype=np.uint64), "ESLDict1")
+    sim.finish_init()
+    sim.disable_transition_checks(True)
+    assert sim.num_edges(int(a[0]), "ESLDict1") == 0 and sim.num_edges(int(a[1]), "ESLDict1") == 1 and sim.num_edges(int(a[2]), "ESLDict1") == 3000
+    assert sim.neighborids(int(a[0]), "ESLDict1") is None and sim.has_edge(int(a[0]), "ESLDict1") is False
+    assert [int(x) for x in sim.neighborids(int(a[2]), "ESLDict1")] == [int(x) for x in nb]          # insertion order of a long row
+    sim.disable_transition_checks(False)
+    sim.apply("sum_state_neighbors_ESLDict1", ["AMortal"], ["AMortal", "AImm", "AImmFixed", "ESLDict1"], ["AMortal"])
+    got = sim.all_agents("AMortal")["foo"].tolist()
+    assert got == [0, 1, 3000 * 3001 // 2], got
+    assert sim.num_edges("ESLDict1") == 3001
+
+
+def test_empty_inputs_oracle(oracle):
+    _empty_checks(oracle)
+
+
+def test_ragged_rows_oracle(oracle):
+    _ragged_checks(oracle)
+
+
+@pytest.mark.gpu
+def test_empty_inputs_gpu(cuda):
+    _empty_checks(cuda)
+
+
+@pytest.mark.gpu
+def test_ragged_rows_gpu(cuda):
+    _ragged_checks(cuda)
