@@ -14,7 +14,8 @@
 // test/parametric_types.jl) and test_zy_full_size.py (random_pos, test/raster.jl:438-459).  The model-level outputs of the
 // BASELINE configs (Hegselmann-Krause opinions, Game of Life, predator/prey, SIR) are NOT pinned by any reference test and
 // Julia cannot run here: "parity unpinned" for those.  What stands in: independent numpy restatements that this
-// oracle matches bit for bit (HK at config 1's full size and on random multigraphs, Game of Life) and the committed fixtures of
+// oracle matches bit for bit (HK at config 1's full size and on random multigraphs, Game of Life, the market model of
+// docs/examples/tutorial1.jl with an independent Philox4x32-10: tests/test_zzm_market.py) and the committed fixtures of
 // tests/golden/ (oracle outputs, written by tests/golden/make_golden.py).
 //
 // Each function cites the reference lines it follows (paths relative to /root/reference).
