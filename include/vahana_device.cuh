@@ -48,7 +48,8 @@ enum Mode : int { MODE_DIRECT = 0, MODE_COUNT = 1, MODE_EMIT = 2 };
 enum DevError : uint32_t {
     DERR_EDGE_NOT_READABLE = 1, DERR_AGENT_NOT_READABLE = 2, DERR_AGENT_TYPE_MISMATCH = 4, DERR_AGENT_DIED = 8,
     DERR_IMMORTAL_DIED = 16, DERR_ACCESSOR_UNAVAILABLE = 32, DERR_BAD_ID = 64, DERR_EDGE_NOT_DECLARED = 128,
-    DERR_SINGLETYPE_MISMATCH = 256, DERR_RASTER_POS = 512, DERR_INDEX = 1024, DERR_REMOTE = 2048
+    DERR_SINGLETYPE_MISMATCH = 256, DERR_RASTER_POS = 512, DERR_INDEX = 1024, DERR_REMOTE = 2048,
+    DERR_MODEL_ASSERT = 4096
 };
 
 // ---- device views of the simulation state (filled by the engine, read by every kernel) -----------
@@ -312,6 +313,8 @@ class Ctx {
         for (int i = 0; i <= F::EdgeRemoves::size; ++i) rcnt[i] = 0;
     }
     __device__ __forceinline__ void fail(uint32_t code) const { atomicOr(ds.error, code); }
+    // @assert cond inside a transition closure: apply! raises an AssertionError after the launch (the kernel runs on)
+    __device__ __forceinline__ void require(bool cond) const { if (!cond) fail(DERR_MODEL_ASSERT); }
 
     template <class P> __device__ __forceinline__ const P& param() const { return *reinterpret_cast<const P*>(ds.params); }
     __device__ __forceinline__ double uniform(int k) const { return Philox::uniform(ds.seed, ds.agents[la.type].uoffset + slot, (uint64_t)k); }

@@ -677,6 +677,7 @@ class Ctx {
 
     template <class P> const P& param() const { return *reinterpret_cast<const P*>(s.params.data()); }
     double uniform(int k) const { return vb::Philox::uniform(s.seed, slot, (uint64_t)k); }
+    void require(bool cond) const { if (!cond) throw AssertionError("an assertion inside the transition function failed (ctx.require)"); }   // @assert in a closure
     // cooperative-group surface: the oracle is a group of one
     int lanes() const { return 1; }
     int lane() const { return 0; }

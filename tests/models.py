@@ -331,3 +331,36 @@ def market_step(sim, step):
     m = sim.mapreduce_fn("market_revenue", "+", "Seller")                                       # calc_average_price (:565-569)
     q = sim.mapreduce("d_y", "+", "Seller")
     sim.push_global("p", m / q)
+
+
+# ---- test/mpi/test_agentstate.jl ----
+def agentstate_model(immortal=True):
+    """test_agentstate.jl:25-46 (:Immortal agents) and :107-113 (mortal agents)"""
+    t = vh.ModelTypes()
+    t.register_agenttype("ASAgent", FOO, *(["Immortal"] if immortal else []))
+    t.register_edgetype("EdgeState", FOO, "SingleEdge")
+    t.register_edgetype("NewEdge", FOO, "SingleEdge")
+    return vh.create_model(t, "agentstatetest" if immortal else "agentstatetest-mortal")
+
+
+def agentstate_scenario(backend, n, immortal, device=0):
+    """test_agentstate.jl:46-105 / :107-185: a chain ids[to-1] -> ids[to] whose edge states repeat the source's state; every check is an
+    assertion inside a transition (ctx.require = the closure's @test), so a stale source state raises an AssertionError in apply!"""
+    sim = vh.create_simulation(agentstate_model(immortal), backend=backend, device=device)
+    ids = sim.add_agents("ASAgent", foos(range(1, n + 1)))
+    for to in range(1, n):
+        sim.add_edge(int(ids[to - 1]), int(ids[to]), "EdgeState", to)
+    sim.finish_init(partition_algo="EqualAgentNumbers")
+    A, ES, NE = "ASAgent", "EdgeState", "NewEdge"
+    sim.apply("as_check_x1_EdgeState", [A], [A, ES], [])                 # the state can be read after the initialisation
+    if not immortal:
+        sim.apply("as_check_x1_EdgeState", [A], [A, ES], [])             # a second time: already transferred states (:137-144)
+    sim.apply("as_double", [A], [A], [A])
+    sim.apply("as_check_x2_EdgeState", [A], [A, ES], [])                 # the accessible state follows the update
+    sim.apply("as_halve", [A], [A], [A])
+    sim.apply("as_require_no_NewEdge", [A], [A, NE], [])                 # reading another edge type transfers nothing new
+    sim.apply("as_copy_edges", [A], [ES], [NE])
+    sim.apply("as_check_x1_EdgeState", [A], [A, ES], [])
+    sim.apply("as_check_x1_NewEdge", [A], [A, NE], [])                   # and through the new edges
+    assert sim.num_edges(NE) == n - 1 == sim.num_edges(ES)
+    return sim

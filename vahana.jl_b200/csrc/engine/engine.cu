@@ -1197,6 +1197,7 @@ void vb_sim::check_device_error(const char* where) {
     if (err & vb::DERR_SINGLETYPE_MISMATCH) m += " :SingleType edge used with an agent of another type;";
     if (err & vb::DERR_RASTER_POS) m += " raster position out of range;";
     if (err & vb::DERR_INDEX) m += " neighbour index out of range;";
+    if (err & vb::DERR_MODEL_ASSERT) m += " an assertion inside the transition function failed (ctx.require);";
     if (err & vb::DERR_REMOTE) m += " the edges of an agent of another rank were read, or an edge of another rank was named outside of a transition (edges live on the rank of their target);";
     throw AssertionError(m);
 }

@@ -98,6 +98,42 @@ template <int E> struct TouchEdge : vb::TransitionBase {
     template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const { (void)ctx.has_edge(E, id); return true; }
 };
 
+// ---- test/mpi/test_agentstate.jl: the state of an edge's source (an agent of another rank under mpiexec) stays fresh ----
+// model: Agent{state} (:Immortal in the first half, mortal in the second), EdgeState{state} and NewEdge{state}, both :SingleEdge
+// apply!(sim, [Agent], [Agent, E], []) do _, id, sim; e = edges(sim, id, E); isnothing(e) || @test e.state.state * MUL == agentstate(sim, e.from, Agent).state
+template <int E, int MUL> struct CheckSourceState : vb::TransitionBase {            // :53-60, :69-75, :97-103
+    using State = Foo;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
+        if (!ctx.has_edge(E, id)) return true;
+        ctx.template for_each_edge<EFoo>(E, id, [&](vb::AgentID from, const EFoo& e) {
+            const Foo a = ctx.template agentstate<Foo>((int)vb::type_nr(from), from);
+            ctx.require(e.foo * MUL == a.foo);
+        });
+        return true;
+    }
+};
+template <int MUL, int DIV> struct ScaleState : vb::TransitionBase {                 // Agent(state.state * 2) :64-66, Agent(state.state / 2) :79-81
+    using State = Foo;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx&, Foo& s, vb::AgentID) const { s.foo = s.foo * MUL / DIV; return true; }
+};
+template <int E> struct RequireNoEdge : vb::TransitionBase {                         // @test isnothing(edges(sim, id, NewEdge)) :83-86
+    using State = Foo;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const { ctx.require(!ctx.has_edge(E, id)); return true; }
+};
+template <int FROM_E, int TO_E> struct CopyEdges : vb::TransitionBase {              // add_edge!(sim, e.from, id, NewEdge(e.state.state)) :89-94
+    using State = Foo;
+    using EdgeWrites = vb::IntList<TO_E>;
+    static constexpr bool kCooperative = false;
+    template <class Ctx> VB_HD bool operator()(Ctx& ctx, Foo&, vb::AgentID id) const {
+        if (!ctx.has_edge(FROM_E, id)) return true;
+        ctx.template for_each_edge<EFoo>(FROM_E, id, [&](vb::AgentID from, const EFoo& e) { ctx.add_edge(TO_E, from, id, EFoo{e.foo}); });
+        return true;
+    }
+};
+
 // ---- remove_edges! inside transitions (test/mpi/test_edgetypes.jl:295-449, single process) ----
 template <int E> struct RemoveOwnIfEven : vb::TransitionBase {          // :311-317
     using State = Foo;
