@@ -17,12 +17,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import vahana_b200 as vh  # noqa: E402
-from models import ba_graph, gol_sim, hk_sim, pp_globals, pp_sim, pp_step, sir_sim, sir_step  # noqa: E402
+from models import ba_graph, gol_sim, hk_sim, market_inputs, market_sim, market_step, pp_globals, pp_sim, pp_step, sir_sim, sir_step  # noqa: E402
 
 HK = dict(n=2000, m=8, graph_seed=1, opinion_seed=1, steps=10)
 GOL = dict(shape=(48, 40), seed=2, density=0.35, generations=25)
 SIR = dict(n=3000, nl=250, beta=0.3, steps=12)
 PP = dict(dims=(30, 30), nprey=180, npred=45, steps=20)
+MARKET = dict(nb=5000, ns=40, known=3, seed=8, steps=20)            # the tutorial's market model (docs/examples/tutorial1.jl), 100 x its size
 PP_DOCS = dict(dims=(100, 100), nprey=2000, npred=500, steps=400, every=25)      # BASELINE config 3 (a): the docs model at the docs size
 
 
@@ -51,10 +52,29 @@ def pp_digest(sim):
     return h.hexdigest()
 
 
+def market(ob):
+    """sellers' (p, d_y) after MARKET['steps'] steps and the two global series; the oracle is bit-exact with the independent numpy
+    restatement of tests/test_zzm_market.py (own Philox4x32-10), which is asserted here before the fixture is written"""
+    from test_zzm_market import numpy_market
+    buyers, sellers, picks = market_inputs(MARKET["nb"], MARKET["ns"], MARKET["known"], MARKET["seed"])
+    sim = market_sim(ob, buyers, sellers, picks)
+    for step in range(MARKET["steps"]):
+        market_step(sim, step)
+    s = sim.all_agents("Seller")
+    p, d_y, xmy, avg, _ = numpy_market(buyers, sellers, picks, MARKET["steps"])
+    assert np.array_equal(s["p"], p) and np.array_equal(s["d_y"], d_y)                                # independent restatement
+    np.testing.assert_allclose(sim.get_global("p"), avg, rtol=1e-12)
+    np.savez_compressed(os.path.join(HERE, "market_5000x40.npz"), p=s["p"], d_y=s["d_y"], x_minus_y=np.array(sim.get_global("x_minus_y")),
+                        avg_p=np.array(sim.get_global("p")))
+
+
 def main():
     import subprocess
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
     ob = vh.load_backend(os.path.join(ROOT, "oracle", "_build", "libvahana_oracle.so"))
+    market(ob)
+    if "--only-market" in sys.argv:
+        return
 
     uv = ba_graph(HK["n"], HK["m"], HK["graph_seed"])
     op0 = np.random.default_rng(HK["opinion_seed"]).random(HK["n"])

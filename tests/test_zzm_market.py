@@ -144,3 +144,30 @@ def test_market_gpu_vs_oracle(oracle, cuda, nb, ns, known):
         assert all(np.array_equal(u, v) for u, v in zip(eg, eo)), step                         # rows, sources and (x, y) states of every seller
     np.testing.assert_allclose(g.get_global("x_minus_y"), o.get_global("x_minus_y"), rtol=1e-10, atol=1e-7)    # tree vs sequential sum
     np.testing.assert_allclose(g.get_global("p"), o.get_global("p"), rtol=1e-12)
+
+
+def _golden_market(backend):
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from make_golden import MARKET
+    g = np.load(os.path.join(here, "golden", "market_5000x40.npz"))
+    buyers, sellers, picks = market_inputs(MARKET["nb"], MARKET["ns"], MARKET["known"], MARKET["seed"])
+    sim = market_sim(backend, buyers, sellers, picks)
+    for step in range(MARKET["steps"]):
+        market_step(sim, step)
+    s = sim.all_agents("Seller")
+    assert np.array_equal(s["p"], g["p"]) and np.array_equal(s["d_y"], g["d_y"])          # sequential functors: bit-exact on both sides
+    np.testing.assert_allclose(sim.get_global("x_minus_y"), g["x_minus_y"], rtol=1e-10, atol=1e-7)
+    np.testing.assert_allclose(sim.get_global("p"), g["avg_p"], rtol=1e-12)
+
+
+def test_golden_market_oracle(oracle):
+    """the committed fixture tests/golden/market_5000x40.npz (tests/golden/make_golden.py --only-market)"""
+    _golden_market(oracle)
+
+
+@pytest.mark.gpu
+def test_golden_market_gpu(cuda):
+    _golden_market(cuda)
