@@ -26,6 +26,8 @@
 //     add_edge(E,from,to[,state])                  add_edge!                    :388-523
 //     add_agent<A>(T,state) -> id                  add_agent!                   src/AgentMethods.jl:65-89
 //     move_to(raster,id,pos,Efrom,Eto,...) cellid(raster,pos)                   src/Raster.jl:403-477
+//     remove_edges(E,to) remove_edges(E,from,to)   remove_edges!                src/EdgeMethods.jl:527-599 (a target of another rank: the request travels)
+//     require(cond)                                @assert cond inside the closure: apply! raises an AssertionError
 //     sum(x) max(x) min(x) lanes() lane() leader() cooperative group of the agent (1 lane in the oracle)
 //
 // In a cooperative functor all lanes of the group run the functor for the same agent; for_each_* hand
