@@ -144,6 +144,9 @@ int vb_mapreduce_fn(vb_sim* sim, const char* map_name, int type_ref, int op, int
 /* ---- raster read-out (src/Raster.jl:206-387) ------------------------------------------- */
 int vb_rastervalues(vb_sim* sim, const char* name, int offset, int dt, void* out);       /* rastervalues / calc_rasterstate(field) */
 int vb_calc_raster_num_edges(vb_sim* sim, const char* name, int etype, int64_t* out);    /* calc_raster(id -> num_edges(sim,id,E)) */
+/* calc_rasterstate(sim, raster, f, f_returns) (src/Raster.jl:238-280) with f a registered map functor (VB_REGISTER_MAP) of the cells'
+ * agent type: out[i] = f(state of the cell at column-major position i), as double (is_float_out = 1) or int64_t (0).             */
+int vb_calc_rasterstate_fn(vb_sim* sim, const char* name, const char* map_name, int is_float_out, void* out);
 int vb_raster_info(vb_sim* sim, const char* name, int* ndims_out, int64_t* dims_out, vb_agent_id* ids_out);
 
 /* ---- introspection used by tests/bench -------------------------------------------------- */

@@ -216,12 +216,21 @@ struct MapLaunchArgs {
     uint32_t nblocks;
     cudaStream_t stream;
 };
+// the same functor evaluated per raster cell without folding (calc_rasterstate, src/Raster.jl:238-280): out[i] = f(state of cell i)
+struct MapCellsArgs {
+    const uint8_t* cols; uint32_t stride;   // read states of the cells' agent type
+    const uint32_t* cells; uint32_t cbase;  // composite index of the cell at each column-major position, and the type's base
+    uint64_t n;
+    void* out;                              // [n] double or long long
+    cudaStream_t stream;
+};
 struct MapInfo {
     const char* name;
     const char* type_name;    // agent or edge type the map is defined on (registered name)
     uint32_t elem_size;       // sizeof(F::Elem)
     int is_float;             // F::Result is floating point (partials are double) or integral (long long)
     cudaError_t (*launch)(const MapLaunchArgs&);
+    cudaError_t (*launch_cells)(const MapCellsArgs&);
 };
 extern "C" int vb_register_map(const MapInfo* info);
 
@@ -1528,6 +1537,20 @@ __global__ void __launch_bounds__(256) map_kernel(const MapLaunchArgs a) {
     }
 }
 template <class F>
+__global__ void __launch_bounds__(256) map_cells_kernel(const MapCellsArgs a) {
+    typedef typename F::Elem Elem;
+    typedef typename MapAcc<typename F::Result>::type T;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const F f{};
+    reinterpret_cast<T*>(a.out)[i] = (T)f(soa_load<Elem>(a.cols, a.stride, a.cells[i] - a.cbase));
+}
+template <class F>
+cudaError_t launch_map_cells(const MapCellsArgs& a) {
+    if (a.n) map_cells_kernel<F><<<(unsigned)((a.n + 255) / 256), 256, 0, a.stream>>>(a);
+    return cudaGetLastError();
+}
+template <class F>
 cudaError_t launch_map(const MapLaunchArgs& a) {
     map_kernel<F><<<a.nblocks, 256, 0, a.stream>>>(a);
     return cudaGetLastError();
@@ -1540,6 +1563,7 @@ MapInfo make_map_info(const char* name, const char* type_name) {
     mi.elem_size = (uint32_t)sizeof(typename F::Elem);
     mi.is_float = std::is_floating_point<typename F::Result>::value ? 1 : 0;
     mi.launch = &launch_map<F>;
+    mi.launch_cells = &launch_map_cells<F>;
     return mi;
 }
 

@@ -269,6 +269,29 @@ int vb_rastervalues(vb_sim* sim, const char* name, int offset, int dt, void* out
         s.check_readable = cr;
     });
 }
+int vb_calc_rasterstate_fn(vb_sim* sim, const char* name, const char* map_name, int is_float_out, void* out) {   // Raster.jl:238-280
+    return guard([&] {
+        vo::Sim& s = *sim->s;
+        if (!s.initialized) throw vo::AssertionError("calc_rasterstate can be only called after finish_init!");
+        vo::Raster& r = vo::find_raster(s, name);
+        if (r.ids.empty()) return;
+        const int type = (int)vb::type_nr(r.ids[0]);
+        auto& maps = vo::Registry::get().maps;
+        auto it = maps.find({map_name ? map_name : "", s.A(type).desc.name});
+        if (it == maps.end()) throw vo::ArgError(std::string("map '") + (map_name ? map_name : "") + "' is not registered for type " + s.A(type).desc.name);
+        const vo::MapFn& mf = it->second;
+        if (mf.elem_size != s.A(type).desc.size) throw vo::ArgError("sizeof(Elem) of the map functor does not match the agent type");
+        if (mf.is_float != (is_float_out != 0)) throw vo::ArgError("the result datatype does not match the map functor");
+        bool cr = s.check_readable; s.check_readable = false;
+        for (size_t i = 0; i < r.ids.size(); ++i) {
+            const uint8_t* p = (const uint8_t*)vo::agentstate(s, r.ids[i], type);
+            double f = 0; int64_t v = 0;
+            mf.fn(p, f, v);
+            if (is_float_out) ((double*)out)[i] = f; else ((int64_t*)out)[i] = v;
+        }
+        s.check_readable = cr;
+    });
+}
 int vb_calc_raster_num_edges(vb_sim* sim, const char* name, int e, int64_t* out) {   // Raster.jl:206-236
     return guard([&] {
         vo::Sim& s = *sim->s;

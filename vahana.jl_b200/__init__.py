@@ -103,7 +103,7 @@ ABI_SYMBOLS = [
     "vb_add_agents", "vb_add_edges", "vb_remove_edges", "vb_add_raster", "vb_connect_raster_neighbors", "vb_move_to",
     "vb_cellid", "vb_finish_init", "vb_apply", "vb_has_transition", "vb_load_model_library", "vb_num_agents",
     "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce", "vb_mapreduce_fn",
-    "vb_rastervalues", "vb_calc_raster_num_edges", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
+    "vb_rastervalues", "vb_calc_raster_num_edges", "vb_calc_rasterstate_fn", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
     "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes", "vb_set_uniform_offset", "vb_add_agent_per_process",
     "vb_last_apply_blocks", "vb_set_read_blocking", "vb_set_read_prefilter", "vb_last_apply_prefiltered",
 ]
@@ -1144,6 +1144,16 @@ class Simulation:
 
     def calc_rasterstate(self, name: str, field: str, type_name: str) -> np.ndarray:
         return self.rastervalues(name, field, type_name)
+
+    def calc_rasterstate_fn(self, name: str, map_name: str, datatype="f8") -> np.ndarray:
+        """calc_rasterstate(sim, raster, f, f_returns) (src/Raster.jl:238-280) with f a registered map functor of the cells' type,
+        e.g. calc_rasterstate(sim, :raster, c -> c.countdown == 0, Bool) = sim.calc_rasterstate_fn("raster", "pp_has_food", "?")"""
+        dims = self.raster_info(name)
+        rdt = np.dtype(datatype)
+        isf = rdt.kind == "f"
+        out = np.zeros(int(np.prod(dims)), dtype="f8" if isf else "i8")
+        self._ck(self.lib.vb_calc_rasterstate_fn(self.h, name.encode(), map_name.encode(), C.c_int(int(isf)), out.ctypes.data_as(C.c_void_p)))
+        return out.astype(rdt).reshape(dims, order="F")
 
     def calc_raster_num_edges(self, name: str, edge_name: str) -> np.ndarray:
         dims = self.raster_info(name)

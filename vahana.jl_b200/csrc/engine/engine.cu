@@ -3612,6 +3612,27 @@ int vb_rastervalues(vb_sim* s, const char* name, int offset, int dt, void* out) 
         dfree(tmp);
     });
 }
+int vb_calc_rasterstate_fn(vb_sim* s, const char* name, const char* map_name, int is_float_out, void* out) {
+    return guard([&] {   // Raster.jl:238-280 with f = a registered map functor
+        require_device();
+        if (!s->initialized) throw AssertionError("calc_rasterstate can be only called after finish_init!");
+        RasterStore& r = find_raster(s, name);
+        AgentStore& a = s->A(r.type);
+        auto it = map_registry().find({map_name ? map_name : "", a.name});
+        if (it == map_registry().end()) throw ArgError(std::string("map '") + (map_name ? map_name : "") + "' is not registered for type " + a.name);
+        const vb::MapInfo* mi = it->second;
+        if (mi->elem_size != a.size) throw ArgError(std::string("map '") + mi->name + "': sizeof(Elem) does not match the registered size of " + a.name);
+        if ((mi->is_float != 0) != (is_float_out != 0)) throw ArgError(std::string("map '") + mi->name + "': the result datatype must be " + (mi->is_float ? "floating point" : "integral"));
+        const size_t n = r.ids.size();
+        uint8_t* tmp = (uint8_t*)g_pool.alloc(std::max<size_t>(n, 1) * 8);
+        vb::MapCellsArgs ca{};
+        ca.cols = a.rstate(); ca.stride = a.stride(); ca.cells = r.cells; ca.cbase = s->base[r.type]; ca.n = n; ca.out = tmp; ca.stream = g_stream;
+        CK(mi->launch_cells(ca)); ++g_launches;
+        CK(cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        dfree(tmp);
+    });
+}
 int vb_calc_raster_num_edges(vb_sim* s, const char* name, int ei, int64_t* out) {
     return guard([&] {   // Raster.jl:206-236 with f = id -> num_edges(sim, id, E)
         require_device();

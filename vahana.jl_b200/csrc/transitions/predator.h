@@ -175,4 +175,16 @@ template <int T, int E_POS, int E_VIEW, bool kIsPrey> struct TryReproduce : vb::
     }
 };
 
+// map closures of the docs example that are more than a field selector (registered maps: mapreduce / calc_rasterstate)
+struct HasFood : vb::MapBase {                 // c -> c.countdown == 0   (predator.jl:487-489, cells with food)
+    using Elem = Cell;
+    using Result = int64_t;
+    VB_HD int64_t operator()(const Cell& c) const { return c.countdown == 0 ? 1 : 0; }
+};
+struct GrowthProgress : vb::MapBase {          // a Float64-valued read-out for plots: 1 = food, falling to 0 right after grazing
+    using Elem = Cell;
+    using Result = double;
+    VB_HD double operator()(const Cell& c) const { return 1.0 / (1.0 + (double)c.countdown); }
+};
+
 }  // namespace pp

@@ -472,4 +472,13 @@ function calc_raster_num_edges(sim::Simulation, name::Symbol, ::Type{E}) where E
     out
 end
 
+"calc_rasterstate(sim, raster, mapname::String, f_returns): src/Raster.jl:238-280 with f a map functor registered (VB_REGISTER_MAP) for the cells' type"
+function calc_rasterstate(sim::Simulation, name::Symbol, mapname::String, ::Type{R} = Float64) where R
+    dims = sim.rasters[name][1]
+    isf = R <: AbstractFloat
+    out = isf ? Vector{Float64}(undef, prod(dims)) : Vector{Int64}(undef, prod(dims))
+    check(ccall((:vb_calc_rasterstate_fn, LIB), Cint, (Ptr{Cvoid}, Cstring, Cstring, Cint, Ptr{Cvoid}), sim.handle, String(name), mapname, isf, out))
+    reshape(R.(out), dims)
+end
+
 end # module
