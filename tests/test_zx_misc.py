@@ -174,3 +174,58 @@ def test_show_and_dataframes(oracle):
     from models import hk_model
     s2 = vh.create_simulation(hk_model(), backend=oracle)
     assert "Still in initialization process!." in s2.show() and ":eps : 0.02" in s2.show()
+
+
+def test_julia_ccall_argument_counts_match_the_header():
+    """no Julia in the image: at least the number of arguments of every `ccall` in the wrapper must equal the number of parameters of
+    the C prototype it binds (include/vahana_b200.h), and the argument-type tuple must be as long as the argument list"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "vahana.jl_b200", "julia", "VahanaB200.jl")).read()
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "vahana_b200.h")).read(), flags=re.S)
+
+    def split_top(s):
+        out, depth, cur = [], 0, ""
+        for ch in s:
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            if ch == "," and depth == 0:
+                out.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            out.append(cur.strip())
+        return out
+
+    def balanced(s, start):          # text between the parenthesis at `start` and its partner
+        depth = 0
+        for i in range(start, len(s)):
+            if s[i] == "(":
+                depth += 1
+            elif s[i] == ")":
+                depth -= 1
+                if depth == 0:
+                    return s[start + 1:i]
+        raise AssertionError("unbalanced")
+
+    nparams = {}
+    for m in re.finditer(r"\b(vb_\w+)\s*\(", header):
+        params = balanced(header, m.end() - 1).strip()
+        nparams[m.group(1)] = 0 if params in ("", "void") else len(split_top(params))
+    checked = 0
+    for m in re.finditer(r"ccall\(\(:(vb_\w+), LIB\)", src):
+        args = split_top(balanced(src, m.start() + len("ccall")))
+        # args = [(:sym, LIB), RetType, (ArgTypes...), actual arguments...]
+        types = args[2].strip()
+        assert types.startswith("(") and types.endswith(")"), (m.group(1), types)
+        ntypes = len(split_top(types[1:-1].rstrip(",")))
+        if types[1:-1].strip() == "":
+            ntypes = 0
+        assert ntypes == nparams[m.group(1)], f"{m.group(1)}: {ntypes} ccall argument types, {nparams[m.group(1)]} parameters in the header"
+        assert len(args) - 3 == ntypes, f"{m.group(1)}: {len(args) - 3} arguments passed for {ntypes} argument types"
+        checked += 1
+    assert checked > 30
