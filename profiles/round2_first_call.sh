@@ -16,7 +16,7 @@ done
 (VB_PF_ROWFIND=1 timeout 100 python -m pytest tests/test_hk.py -x -q -m gpu -k "not full_size") > gpurun_out/test_hk_rowfind.txt 2>&1
 (VB_PF_ROWFIND=1 timeout 100 python bench.py --steps 5 --warmup 3 --no-cpu) > gpurun_out/bench_pf_rowfind.json 2> gpurun_out/bench_pf_rowfind.err
 # GPU variants written after round 1's GPU budget was spent (market model, registered maps, golden replays, full-size cases)
-(timeout 400 python -m pytest tests/test_zzm_market.py tests/test_zzn_remove_order.py tests/test_zzo_edge_cases.py tests/test_zzp_agentstate.py tests/test_zzq_raster_maps.py tests/test_zw_golden.py tests/test_zx_misc.py tests/test_zy_full_size.py tests/test_zz_long_runs.py -q -m gpu) > gpurun_out/test_gpu_late.txt 2>&1
+(timeout 400 python -m pytest tests/test_zzm_market.py tests/test_zzn_remove_order.py tests/test_zzo_edge_cases.py tests/test_zzp_agentstate.py tests/test_zzq_raster_maps.py tests/test_zzr_ext_model_gpu.py tests/test_zw_golden.py tests/test_zx_misc.py tests/test_zy_full_size.py tests/test_zz_long_runs.py -q -m gpu) > gpurun_out/test_gpu_late.txt 2>&1
 tail -n 5 gpurun_out/test_gpu_late.txt
 tail -n 3 gpurun_out/test_hk_rowfind.txt
 cat gpurun_out/stencil.txt

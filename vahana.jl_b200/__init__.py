@@ -139,6 +139,14 @@ class Backend:
             self.check(self.lib.vb_init(C.c_int(device)))
             self._initialized = True
 
+    def load_model_library(self, path: str) -> None:
+        """dlopen a model library (a separately compiled .cu that registers its transitions / maps with VB_REGISTER_TRANSITION /
+        VB_REGISTER_MAP): the counterpart of `include("model.jl")` defining the closures."""
+        self.check(self.lib.vb_load_model_library(os.path.abspath(path).encode()))
+
+    def has_transition(self, name: str, agent_type: str) -> bool:
+        return bool(self.lib.vb_has_transition(name.encode(), agent_type.encode()))
+
     def set_stream(self, cuda_stream: int) -> None:
         """Run all engine work on the given cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
         self.check(self.lib.vb_set_stream(C.c_void_p(cuda_stream)))
