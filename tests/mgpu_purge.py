@@ -13,17 +13,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import vahana_b200 as vh  # noqa: E402
 from models import remove_agents_model  # noqa: E402
+from mgpu_common import setup  # noqa: E402
 
 
 def main():
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rank, world = dist.get_rank(), dist.get_world_size()
-    be = vh.default_backend()
-    be.init(local)
-    be.set_stream(torch.cuda.current_stream().cuda_stream)
-    be.init_distributed()
+    be, local, rank, world, _ = setup()
     sim = vh.create_simulation(remove_agents_model(), backend=be, device=local)
     ids = sim.add_agents("DAgent", np.array([(i,) for i in range(1, 4)], dtype=[("idx", "i8")]))
     rids = sim.add_agents("DAgentRemove", None, 2)

@@ -14,12 +14,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import vahana_b200 as vh  # noqa: E402
 from models import sir_model, sir_step, sir_sim, PERSON  # noqa: E402
+from mgpu_common import setup, oracle_backend  # noqa: E402
 
 
-def gather(local, sizes, rank, world):
+def gather(local, sizes, rank, world, dev="cuda"):
     parts = []
     for r in range(world):
-        t = torch.from_numpy(local.copy()).cuda() if r == rank else torch.empty(sizes[r], dtype=torch.from_numpy(local[:0].copy()).dtype, device="cuda")
+        t = torch.from_numpy(local.copy()).to(dev) if r == rank else torch.empty(sizes[r], dtype=torch.from_numpy(local[:0].copy()).dtype, device=dev)
         dist.broadcast(t, src=r)
         parts.append(t.cpu().numpy())
     return np.concatenate(parts)
@@ -27,14 +28,7 @@ def gather(local, sizes, rank, world):
 
 def main():
     npers, nloc = int(os.environ.get("MGPU_N", "60000")), int(os.environ.get("MGPU_L", "4001"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rank, world = dist.get_rank(), dist.get_world_size()
-    be = vh.default_backend()
-    be.init(local)
-    be.set_stream(torch.cuda.current_stream().cuda_stream)
-    be.init_distributed()
+    be, local, rank, world, dev = setup()
     pb, lb = vh.equal_partition(npers, world), vh.equal_partition(nloc, world)
     st = np.zeros(npers, dtype=np.dtype(PERSON, align=True))
     st["state"] = (np.random.default_rng(7).random(npers) < 0.01).astype("u1")
@@ -46,16 +40,14 @@ def main():
     g.finish_init(distribute=False)   # SPMD initialisation: every rank added its own block
     o = None
     if rank == 0:
-        import subprocess
-        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-        o = sir_sim(vh.load_backend(os.path.join(ROOT, "oracle", "_build", "libvahana_oracle.so")), npers, nloc, beta=0.3)
+        o = sir_sim(oracle_backend(), npers, nloc, beta=0.3)
     psz = [pb[r + 1] - pb[r] for r in range(world)]
     lsz = [lb[r + 1] - lb[r] for r in range(world)]
     for step in range(8):
         sir_step(g, step)
         nv, ne = g.num_edges("Visit"), g.num_edges("Exposure")
-        ps = gather(g.all_agents("Person", all_ranks=False).view("i2").astype("i4"), psz, rank, world)
-        ls = gather(g.all_agents("Location", all_ranks=False)["n_inf"].copy(), lsz, rank, world)
+        ps = gather(g.all_agents("Person", all_ranks=False).view("i2").astype("i4"), psz, rank, world, dev)
+        ls = gather(g.all_agents("Location", all_ranks=False)["n_inf"].copy(), lsz, rank, world, dev)
         if rank == 0:
             sir_step(o, step)
             assert nv == o.num_edges("Visit") == 2 * npers and ne == o.num_edges("Exposure") == 2 * npers
