@@ -394,13 +394,13 @@ function Base.mapreduce(sim::Simulation, field::Union{Symbol,Nothing}, op, ::Typ
     out[]
 end
 
-"mapreduce(sim, mapname::String, op, T; datatype, init): the map is a functor registered with VB_REGISTER_MAP for T, i.e. any closure of the
-reference's mapreduce(sim, f, op, T), e.g. b -> b.x - b.y (docs/examples/tutorial1.jl:548)."
-function Base.mapreduce(sim::Simulation, mapname::String, op, ::Type{T}; datatype::DataType = Float64, init = nothing) where T
-    out = Ref{datatype}()
-    initref = init === nothing ? C_NULL : Ref{datatype}(datatype(init))
-    GC.@preserve initref check(ccall((:vb_mapreduce_fn, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint, Cint, Cint, Ptr{Cvoid}, Ref{datatype}),
-                                     sim.handle, mapname, ref(sim, T), OPS[op], DTS[datatype],
+"mapreduce(sim, mapname::String, op, T, R = Float64; init): the map is a functor registered with VB_REGISTER_MAP for T, i.e. any closure of
+the reference's mapreduce(sim, f, op, T; datatype = R), e.g. b -> b.x - b.y (docs/examples/tutorial1.jl:548)."
+function Base.mapreduce(sim::Simulation, mapname::String, op, ::Type{T}, ::Type{R} = Float64; init = nothing) where {T, R}
+    out = Ref{R}()
+    initref = init === nothing ? C_NULL : Ref{R}(R(init))
+    GC.@preserve initref check(ccall((:vb_mapreduce_fn, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint, Cint, Cint, Ptr{Cvoid}, Ref{R}),
+                                     sim.handle, mapname, ref(sim, T), OPS[op], DTS[R],
                                      init === nothing ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, initref), out))
     out[]
 end
