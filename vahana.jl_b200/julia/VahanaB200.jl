@@ -386,10 +386,14 @@ function Base.mapreduce(sim::Simulation, field::Union{Symbol,Nothing}, op, ::Typ
     end
     RT = equals !== nothing ? ((op == (&) || op == (|)) ? Bool : Int64) :
          FT <: AbstractFloat ? Float64 : (FT == Bool && (op == (&) || op == (|)) ? Bool : Int64)
+    _mapreduce(sim, ref(sim, T), off, fdt, equals, op, RT, init)
+end
+# the result type reaches ccall as a static type parameter (ccall's argument types cannot depend on local variables)
+function _mapreduce(sim::Simulation, tref, off, fdt, equals, op, ::Type{RT}, init) where RT
     out = Ref{RT}()
     initref = init === nothing ? C_NULL : Ref{RT}(RT(init))
     GC.@preserve initref check(ccall((:vb_mapreduce, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Int64, Cint, Cint, Ptr{Cvoid}, Ref{RT}),
-                                     sim.handle, ref(sim, T), off, fdt, equals !== nothing, equals === nothing ? 0 : Int64(equals), OPS[op], DTS[RT],
+                                     sim.handle, tref, off, fdt, equals !== nothing, equals === nothing ? 0 : Int64(equals), OPS[op], DTS[RT],
                                      init === nothing ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, initref), out))
     out[]
 end
