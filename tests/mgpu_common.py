@@ -35,3 +35,19 @@ def setup():
 def oracle_backend():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
     return vh.load_backend(os.path.join(ROOT, "oracle", "_build", "libvahana_oracle.so"))
+
+
+def run_ranks(script, port, nranks=None, env=None, timeout=600):
+    """Run tests/<script> under torchrun with one rank per visible GPU (at most 4); on failure the assertion message carries the
+    ranks' own tracebacks only (torchrun's elastic report is dropped)."""
+    import subprocess
+    import torch
+    ng = torch.cuda.device_count() if nranks is None else nranks
+    n = min(ng, 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", script)], capture_output=True, text=True, timeout=timeout,
+                       env=dict(os.environ, **(env or {})))
+    if r.returncode != 0 or r.stdout.count(": ok") != n:
+        keep = [ln for ln in r.stderr.splitlines() if ln.startswith("[rank") or "Error" in ln and "elastic" not in ln]
+        raise AssertionError(f"{script} on {n} ranks: rc {r.returncode}\n" + r.stdout[-1500:] + "\n" + "\n".join(keep[-40:]))
+    return r.stdout

@@ -66,7 +66,8 @@ def main():
     # edges & neighborids (core.jl:177-199): the sources are agents of other ranks now, the order is the insertion order
     if on(a1):
         es = sim.edges(a1, "ESDict")
-        assert [int(f) for f, _ in es] == [a2, a3, avids[0], avfids[9]] and [int(s["foo"]) for _, s in es] == [1, 2, 3, 4]
+        assert [int(f) for f, _ in es] == [a2, a3, avids[0], avfids[9]], ([hex(int(f)) for f, _ in es], [hex(x) for x in (a2, a3, avids[0], avfids[9])])
+        assert [int(s["foo"]) for _, s in es] == [1, 2, 3, 4]
         assert [int(x) for x in sim.neighborids(a1, "ESLDict1")] == avids and sim.num_edges(a1, "ESDict") == 4
         # (core.jl:201-208 reads neighborstates outside of a transition; the states of agents of other ranks are only transferred by the
         #  halo of an apply! that reads their type, so that check is left to the neighbour sums below)

@@ -70,7 +70,10 @@ def main():
             assert abs(total - o.mapreduce("opinion", "+", "HKAgent")) < 1e-9 * n
     hb = C.c_uint64()
     be.lib.vb_halo_bytes(g.h, C.byref(hb))
-    print(f"rank {rank}/{world}: ok, ghosts bytes/step {hb.value}", flush=True)
+    st = g.last_apply_stats()
+    if os.environ.get("MGPU_EXPECT_PREFILTER"):      # the swept [local | ghost] read phase must be the one that ran
+        assert st["prefiltered"] and st["source_blocks"] >= 2, st
+    print(f"rank {rank}/{world}: ok, ghosts bytes/step {hb.value}, prefiltered {st['prefiltered']}, key blocks {st['source_blocks']}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

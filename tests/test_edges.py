@@ -121,6 +121,24 @@ def test_edgetype_in_read_and_write(backend):  # test/edges.jl:250-273
         sim.copy_simulation().apply(f"touch_edge_{i}", "Agent", [t], [])
 
 
+def test_single_edge_conflict_with_add_existing(backend):  # _can_add, src/EdgeMethods.jl:267-293
+    """With `add_existing` the write container already holds the target's edge: adding a different one asserts (Dict containers,
+    i.e. :SingleEdge without :SingleType), adding the identical one is allowed."""
+    for t in ["EdgeE", "EdgeSE", "EdgeEI"]:
+        i = EDGE_TYPES.index(t)
+        sim, a1, a2, a3 = _build(backend)          # a3 <- a2 and a1 <- a3 exist; the self loops differ from both
+        if t == "EdgeEI":                          # :IgnoreFrom: the value is the state alone; 0 differs from the stored 1 / 3
+            with pytest.raises(AssertionError):
+                sim.apply(f"add_self_loop_{i}", "Agent", [], [t], add_existing=[t])
+        else:
+            with pytest.raises(AssertionError):
+                sim.apply(f"add_self_loop_{i}", "Agent", [], [t], add_existing=[t])
+        # without add_existing the write container starts empty: every agent simply gets its self loop
+        sim2, *_ = _build(backend)
+        sim2.apply(f"add_self_loop_{i}", "Agent", [], [t])
+        assert sim2.num_edges(t) == 3
+
+
 def test_num_edges_write_flag(backend):  # test/edges.jl:278-316
     sim = vh.create_simulation(edges_model(), backend=backend)
     for t in EDGE_TYPES:

@@ -321,6 +321,7 @@ struct MergeArgs {
     const uint32_t* noff; const uint32_t* nsrc; const uint8_t* nst; uint32_t nstride;
     const uint32_t* off; uint32_t* src; uint8_t* st; uint32_t stride;
     uint32_t rows; uint32_t word, ncols; int single_edge;
+    uint32_t* conflict;     // :SingleEdge with add_existing: set when a row's kept entry and its new entry differ (_can_add, EdgeMethods.jl:267-293)
 };
 __global__ void merge_counts_kernel(const uint32_t* __restrict__ ooff, uint32_t orows, const uint32_t* __restrict__ ncnt, uint32_t rows, int single_edge,
                                     uint32_t* __restrict__ cnt) {
@@ -336,6 +337,16 @@ __global__ void merge_copy_kernel(const MergeArgs a) {
     if (r >= a.rows) return;
     uint32_t d = a.off[r];
     const uint32_t nb = a.noff[r], ne = a.noff[r + 1];
+    if (a.conflict && a.single_edge && ne > nb && r < a.orows && a.ooff[r + 1] > a.ooff[r]) {
+        // the write container already held an edge for this target (add_existing) and the transition added another one: allowed only
+        // when the value is identical
+        const uint32_t ko = a.ooff[r], kn = ne - 1;
+        bool same = !a.src || a.osrc[ko] == a.nsrc[kn];
+        for (uint32_t c = 0; a.st && c < a.ncols; ++c)
+            for (uint32_t b = 0; b < a.word; ++b)
+                same &= a.ost[(size_t)c * a.ostride * a.word + (size_t)ko * a.word + b] == a.nst[(size_t)c * a.nstride * a.word + (size_t)kn * a.word + b];
+        if (!same) atomicOr(a.conflict, 1u);
+    }
     if (!(a.single_edge && ne > nb) && r < a.orows) {
         for (uint32_t k = a.ooff[r]; k < a.ooff[r + 1]; ++k, ++d) {
             if (a.src) a.src[d] = a.osrc[k];
@@ -468,6 +479,11 @@ __global__ void ghost_bounds_kernel(const uint64_t* __restrict__ ids, uint32_t n
     uint32_t lo = 0, hi = n;
     while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ids[mid] < key) lo = mid + 1; else hi = mid; }
     bounds[i] = lo;
+}
+__global__ void find_ghost_kernel(const uint64_t* __restrict__ ids, uint32_t n, uint64_t id, int64_t* __restrict__ out) {   // binary search of the sorted ghost table
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ids[mid] < id) lo = mid + 1; else hi = mid; }
+    *out = (lo < n && ids[lo] == id) ? (int64_t)lo : -1;
 }
 __global__ void ids_to_slots_kernel(const uint64_t* __restrict__ ids, uint32_t n, uint32_t* __restrict__ slots) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -662,13 +678,17 @@ __global__ void rebase_cnt_kernel(const uint32_t* __restrict__ ocnt, uint32_t or
     const uint32_t ocap = a.old_base[t + 1] - a.old_base[t];
     ncnt[r] = (slot < ocap && a.old_base[t] + slot < orows) ? ocnt[a.old_base[t] + slot] : 0;
 }
+// composite index -> AgentID: a local slot is (type, this rank, slot + 1); a ghost slot (>= the local capacity old_lcap[t]) is the id the
+// sorted ghost table of the type holds for it (ghost_ids passed through `remap`, reinterpreted: two words per id)
 __global__ void comp_to_id_kernel(const uint32_t* __restrict__ comp, uint64_t n, uint64_t* __restrict__ ids, const RebaseArgs a, uint32_t rank) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t c = comp[i];
     uint32_t t = 1;
     while (t < a.ntypes && c >= a.old_base[t + 1]) ++t;
-    ids[i] = vb::agent_id(t, rank, (uint64_t)(c - a.old_base[t]) + 1);
+    const uint32_t slot = c - a.old_base[t];
+    if (slot >= a.old_lcap[t] && a.remap[t]) ids[i] = reinterpret_cast<const uint64_t*>(a.remap[t])[slot - a.old_lcap[t]];
+    else ids[i] = vb::agent_id(t, rank, (uint64_t)slot + 1);
 }
 __global__ void raster_cells_kernel(const uint64_t* __restrict__ ids, uint64_t n, uint32_t* __restrict__ cells, const RebaseArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1503,7 +1523,19 @@ void vb_sim::build_container(int ei, bool add_existing) {
         ma.noff = noff; ma.nsrc = sfrom; ma.nst = sst; ma.nstride = sstride;
         ma.off = off; ma.src = e.has_src() ? dalloc<uint32_t>(cap) : nullptr; ma.st = e.has_state() ? (uint8_t*)g_pool.alloc((size_t)cap * e.size) : nullptr;
         ma.stride = cap; ma.rows = rows; ma.word = e.word; ma.ncols = e.ncols; ma.single_edge = e.singleedge;
+        const bool check_single = e.singleedge && !e.singletype && asserts_enabled && n > 0;
+        if (check_single) { ma.conflict = d_scalars + 1; CK(cudaMemsetAsync(ma.conflict, 0, 4, g_stream)); }
         merge_copy_kernel<<<nblk(rows), 256, 0, g_stream>>>(ma); LAUNCH_CHECK();
+        if (check_single) {
+            uint32_t conflict = 0;
+            CK(cudaMemcpyAsync(&conflict, ma.conflict, 4, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            if (conflict) {
+                dfree(ma.src); dfree(ma.st); dfree(noff); dfree(cnt); dfree(off); dfree(ncnt); dfree(scr);
+                free_edge_log(e);
+                throw AssertionError("An edge has already been added to this agent (the edge type has the :SingleEdge hint)");
+            }
+        }
         free_edge_read(e);
         e.off = off; e.rows = rows; e.nnz = total; e.src = ma.src; e.st = ma.st; e.st_cap = cap;
         dfree(noff); dfree(cnt);
@@ -2938,11 +2970,14 @@ int vb_add_edges(vb_sim* s, int ei, const vb_agent_id* from, const vb_agent_id* 
             const uint64_t t = to[i], f = from ? from[i] : 0;
             if (s->asserts_enabled) {   // ids must name existing agents (the reference dereferences them)
                 const uint32_t tt = vb::type_nr(t);
-                if (tt < 1 || tt > s->agents.size() || vb::agent_nr(t) < 1 || vb::agent_nr(t) >= s->agents[tt - 1].nextid) throw AssertionError("add_edge!: invalid target id");
+                // the agent number can only be range-checked for agents of this rank: another rank's block may be longer than ours
+                // (n % nranks != 0, explicit partitions); unknown remote ids are rejected by the ghost build / translation later
+                const bool t_local = vb::process_nr(t) == s->rank, f_local = vb::process_nr(f) == s->rank;
+                if (tt < 1 || tt > s->agents.size() || vb::agent_nr(t) < 1 || (t_local && vb::agent_nr(t) >= s->agents[tt - 1].nextid)) throw AssertionError("add_edge!: invalid target id");
                 if (e.singletype && (int)tt != e.target) throw AssertionError("add_edge!: the :SingleType hint is set and the target has another type");
                 if (e.has_src()) {
                     const uint32_t ft = vb::type_nr(f);
-                    if (ft < 1 || ft > s->agents.size() || vb::agent_nr(f) < 1 || vb::agent_nr(f) >= s->agents[ft - 1].nextid) throw AssertionError("add_edge!: invalid source id");
+                    if (ft < 1 || ft > s->agents.size() || vb::agent_nr(f) < 1 || (f_local && vb::agent_nr(f) >= s->agents[ft - 1].nextid)) throw AssertionError("add_edge!: invalid source id");
                 }
             }
             const uint8_t* st = (e.has_state() && states) ? (const uint8_t*)states + i * e.size : nullptr;
@@ -3275,9 +3310,22 @@ int vb_agentstate(vb_sim* s, vb_agent_id id, int type, void* out) {
         AgentStore& a = s->A(type);
         s->mayassert((int)vb::type_nr(id) == type, "The id of the agent does not match the given type");
         s->mayassert(a.prepared || !s->check_readable, "agent type must be in the `read` argument of the transition function");
-        const uint64_t nr = vb::agent_nr(id);
-        if (nr < 1 || nr > a.nslots) throw AssertionError("agentstate: agent does not exist");
-        if (!a.immortal) {
+        uint64_t nr = vb::agent_nr(id);
+        bool ghost = false;
+        if (g_nranks > 1 && vb::process_nr(id) != s->rank) {
+            // an agent of another rank (the reference answers from `foreignstate`, AgentMethods.jl:103-111): the ghost slot that mirrors it,
+            // as of the last halo exchange of an apply! that read the type
+            int64_t* found = (int64_t*)(s->d_scalars + 56);
+            find_ghost_kernel<<<1, 1, 0, g_stream>>>(a.ghost_ids, a.nghost, id, found); LAUNCH_CHECK();
+            int64_t k = -1;
+            CK(cudaMemcpyAsync(&k, found, 8, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            if (k < 0) throw AssertionError("agentstate: the agent lives on another rank and is not mirrored here (no local edge refers to it)");
+            nr = (uint64_t)a.cap + (uint64_t)k + 1;
+            ghost = true;
+        }
+        if (nr < 1 || (!ghost && nr > a.nslots)) throw AssertionError("agentstate: agent does not exist");
+        if (!a.immortal && !ghost) {
             uint8_t d = 0;
             CK(cudaMemcpyAsync(&d, a.rdied() + (nr - 1), 1, cudaMemcpyDeviceToHost, g_stream));
             CK(cudaStreamSynchronize(g_stream));
@@ -3343,7 +3391,12 @@ int64_t fetch_row(vb_sim* s, EdgeStore& e, vb_agent_id to, std::vector<uint64_t>
         for (uint32_t i = 0; i < n; ++i) {
             uint32_t t = 1;
             while (t < s->agents.size() && c[i] >= s->base[t + 1]) ++t;
-            (*from)[i] = vb::agent_id(t, s->rank, (uint64_t)(c[i] - s->base[t]) + 1);
+            const AgentStore& ga = s->agents[t - 1];
+            const uint32_t slot = c[i] - s->base[t];
+            if (slot >= ga.cap && slot - ga.cap < ga.nghost) {        // a source on another rank: the id its ghost slot mirrors
+                CK(cudaMemcpyAsync(&(*from)[i], ga.ghost_ids + (slot - ga.cap), 8, cudaMemcpyDeviceToHost, g_stream));
+                CK(cudaStreamSynchronize(g_stream));
+            } else (*from)[i] = vb::agent_id(t, s->rank, (uint64_t)slot + 1);
         }
     }
     if (st && e.has_state()) {
@@ -3427,7 +3480,11 @@ int vb_export_csr(vb_sim* s, int ei, int target_type, uint64_t* offsets, uint64_
         if (!n || cap < n) return;
         if (from_out && e.has_src()) {
             uint64_t* ids = dalloc<uint64_t>(n);
-            RebaseArgs ra; std::memcpy(ra.old_base, s->base, sizeof(ra.old_base)); std::memcpy(ra.new_base, s->base, sizeof(ra.new_base)); ra.ntypes = (uint32_t)s->agents.size();
+            RebaseArgs ra{}; std::memcpy(ra.old_base, s->base, sizeof(ra.old_base)); std::memcpy(ra.new_base, s->base, sizeof(ra.new_base)); ra.ntypes = (uint32_t)s->agents.size();
+            for (size_t t = 1; t <= s->agents.size(); ++t) {     // sources on other ranks are ghost slots: their ids come from the ghost table
+                const AgentStore& ga = s->agents[t - 1];
+                ra.old_lcap[t] = ga.cap; ra.remap[t] = ga.nghost ? reinterpret_cast<const uint32_t*>(ga.ghost_ids) : nullptr;
+            }
             comp_to_id_kernel<<<nblk(n), 256, 0, g_stream>>>(e.src + o0, n, ids, ra, s->rank); LAUNCH_CHECK();
             CK(cudaMemcpyAsync(from_out, ids, n * 8, cudaMemcpyDeviceToHost, g_stream));
             CK(cudaStreamSynchronize(g_stream));
