@@ -172,6 +172,15 @@ struct LaunchArgs {
     uint8_t* blk_key;                     // prefilter (F::kPrefilter): one key byte per slot of the source type, written by launch_keys
     uint32_t blk_nkeys;                   //   slots of the source type covered by blk_key (local + ghosts)
     int blk_prefilter;                    //   sweeps gather keys and fetch the exact state only where may_accept() holds
+    // segmented view (prefiltered sweeps): rows longer than the segment length are cut into segments, a warp owns 32
+    // consecutive segments, an entry is (source slot - blk_base) | (segment & 31) << 27, accumulators are parked per segment
+    const uint32_t* blk_seg_row;          // [blk_nseg] slot of the called agent a segment belongs to | SEG_MULTI (its row has several segments)
+    uint32_t blk_nseg;
+    uint32_t blk_base;                    // first source slot of the swept block
+    const uint32_t* blk_hub_rows;         // blk_op == 1: the rows with several segments, ascending
+    const uint32_t* blk_hub_seg;          //   [2 blk_nhub] their segment ranges [first, end)
+    uint32_t blk_nhub;
+    int blk_op;                           // 0 = sweep one block, 1 = merge the hub rows' segment accumulators and finish them
     cudaStream_t stream;
 };
 // what the kernel actually receives: launch arguments + the whole simulation view, by value in the
@@ -1275,6 +1284,173 @@ __global__ void __launch_bounds__(32 * WPC, 64 / WPC) reduce_prefilter_kernel(co
         }
     }
 }
+// ---- prefiltered sweep over the SEGMENTED view --------------------------------------------------------------------------------------
+// Second shape of the prefiltered sweep (profiles/microbench/twophase.cu, profiles/r2_microbench/): the blocked view is built over
+// SEGMENTS — a row of more than SEG_LEN entries is cut into segments of SEG_LEN — and every entry carries, above its 27-bit source slot
+// (relative to the block), the index of its segment inside the warp's group of 32.  Consequences:
+//   * hub rows need no pass of their own: no warp ever walks more than 32 x SEG_LEN entries, the segments' partial accumulators are
+//     merged (in segment order) and finished by reduce_hubmerge_kernel;
+//   * the row that owns an entry is a shift, its probe comes from the owner lane by shuffle: no offset table in shared memory, no
+//     search, no per-row counters; at a flush a lane finds the run of its segment by a binary search over the ascending tags;
+//   * U = 4 key gathers per lane and round in flight.
+// The queue keeps entry order, so a segment's candidates are folded in entry order; fold() decides on the exact state.
+enum : uint32_t { SEG_MULTI = 0x80000000u, SEG_SRC_MASK = 0x07ffffffu, SEG_TAG_SHIFT = 27 };
+template <class T> __device__ __forceinline__ T shfl_struct(const T& v, uint32_t src) {
+    static_assert(sizeof(T) % 4 == 0, "shuffled structs are whole words");
+    union U { T t; uint32_t w[sizeof(T) / 4]; __device__ U() {} } a, b;
+    a.t = v;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) b.w[i] = __shfl_sync(0xffffffffu, a.w[i], src);
+    return b.t;
+}
+template <class F, int U, int QX> struct SegStage {
+    static constexpr int QCAP = 32 * U + QX;
+    uint32_t qe[QCAP];                  // queued entries (tag | source slot in the block), in entry order
+    typename F::Source qv[QCAP];        // their exact states
+};
+#ifndef VB_SEG_U
+#define VB_SEG_U 4
+#endif
+#ifndef VB_SEG_QX
+#define VB_SEG_QX 64
+#endif
+template <class F, bool FIRST, bool LAST, int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) reduce_segsweep_kernel(const __grid_constant__ KernelArgs ka) {
+    typedef BlockedCfg<F> C;
+    typedef typename C::State State;
+    typedef typename C::Source Source;
+    typedef typename C::Acc Acc;
+    typedef typename F::Probe Probe;
+    constexpr int U = VB_SEG_U, QX = VB_SEG_QX;
+    typedef SegStage<F, U, QX> Stage;
+    __shared__ Stage stages[WPC];
+    const LaunchArgs& la = ka.la;
+    const DeviceSim& ds = ka.ds;
+    const uint32_t lane = threadIdx.x & 31;
+    Stage& sm = stages[threadIdx.x >> 5];
+    const uint64_t g = (uint64_t)blockIdx.x * WPC + (threadIdx.x >> 5);
+    const uint64_t s0 = g * 32;
+    if (s0 >= la.blk_nseg) return;                                        // whole warp
+    const uint32_t ns = la.blk_nseg - s0 < 32 ? (uint32_t)(la.blk_nseg - s0) : 32u;
+    const AgentView& av = ds.agents[la.type];
+    const AgentView& sv = ds.agents[F::kSourceType];
+    const uint8_t* __restrict__ src_st = sv.state_r;
+    const uint32_t src_cap = sv.cap;
+    const uint32_t* __restrict__ gsrc = la.blk_src;
+    const uint8_t* __restrict__ keys = la.blk_key + la.blk_base;
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    // look-ahead: pull the offsets / segment rows of the CTA one residency wave later into L2 now, its entry range at the end
+    const uint32_t pc = blockIdx.x + la.blk_ahead;
+    uint32_t pa = 0, pb = 0;
+    const bool ahead = la.blk_ahead && pc < gridDim.x;
+    if (ahead && threadIdx.x < 32) {
+        const uint64_t r0 = (uint64_t)pc * 32 * WPC;
+        const uint32_t nr = la.blk_nseg - r0 < 32u * WPC ? (uint32_t)(la.blk_nseg - r0) : 32u * WPC;
+        if (lane == 0) { pa = __ldg(la.blk_off + r0); pb = __ldg(la.blk_off + r0 + nr); }
+        blk::prefetch_l2(la.blk_off + r0, (size_t)(nr + 1) * 4, lane, 32);
+        blk::prefetch_l2(la.blk_seg_row + r0, (size_t)nr * 4, lane, 32);
+        if (!FIRST) {
+#pragma unroll
+            for (int c = 0; c < C::A8; ++c) blk::prefetch_l2(la.blk_acc + ((size_t)c * la.blk_stride + r0) * 8, (size_t)nr * 8, lane, 32);
+#pragma unroll
+            for (int c = 0; c < C::A4; ++c) blk::prefetch_l2(la.blk_acc + (size_t)C::A8 * la.blk_stride * 8 + ((size_t)c * la.blk_stride + r0) * 4, (size_t)nr * 4, lane, 32);
+        }
+    }
+    const uint32_t e0 = __ldcs(la.blk_off + s0), e1 = __ldcs(la.blk_off + s0 + ns);
+    const uint32_t rowm = lane < ns ? __ldcs(la.blk_seg_row + s0 + lane) : 0u;
+    const uint32_t idx = rowm & ~SEG_MULTI;
+    const bool act = lane < ns && !(av.died_r && av.died_r[idx]);        // jump over died agents (AgentMethods.jl:199-203)
+    const F f{};
+    Ctx<F, MODE_DIRECT, 1> ctx(ds, la, idx, 0);
+    State self;
+    Acc acc;
+    Probe probe;
+    if (act) {
+        self = blk::soa_load_cs<State>(av.state_r, av.cap, idx);
+        if (FIRST) f.init(ctx, self, acc); else C::acc_load(la.blk_acc, la.blk_stride, (uint32_t)s0 + lane, acc);
+        probe = f.probe(ctx, self);
+    } else {
+        memset(&self, 0, sizeof(State));
+        memset(&acc, 0, sizeof(Acc));
+        memset(&probe, 0, sizeof(Probe));
+    }
+    const uint32_t alive = __ballot_sync(0xffffffffu, act);              // entries of died rows are never queued
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t qn = 0;
+    for (uint32_t base = e0; base < e1; base += 32 * U) {
+        uint32_t ent[U], ks[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const uint32_t x = base + lane + 32 * u; ent[u] = x < e1 ? __ldcs(gsrc + x) : 0xffffffffu; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) ks[u] = ent[u] != 0xffffffffu ? blk::ld_key(keys + (ent[u] & SEG_SRC_MASK), pol) : 0u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t tag = ent[u] >> SEG_TAG_SHIFT;
+            const Probe pr = shfl_struct(probe, tag);
+            const bool pass = ent[u] != 0xffffffffu && ((alive >> tag) & 1u) && f.may_accept(pr, ks[u]);
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (pass) sm.qe[qn + __popc(m & lt)] = ent[u];
+            qn += __popc(m);
+        }
+        __syncwarp();
+        if (qn > (uint32_t)QX || base + 32 * U >= e1) {                   // flush: exact states edge-parallel, then the per-segment folds
+            for (uint32_t i = lane; i < qn; i += 32) sm.qv[i] = soa_gather<Source>(src_st, src_cap, la.blk_base + (sm.qe[i] & SEG_SRC_MASK));
+            uint32_t lo = 0, hi = qn;                                     // first queued candidate whose tag is >= my lane
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((sm.qe[mid] >> SEG_TAG_SHIFT) < lane) lo = mid + 1; else hi = mid; }
+            uint32_t end = __shfl_down_sync(0xffffffffu, lo, 1);
+            if (lane == 31) end = qn;
+            __syncwarp();
+            for (uint32_t j = lo; j < end; ++j) f.fold(ctx, self, sm.qv[j], acc);
+            qn = 0;
+            __syncwarp();
+        }
+    }
+    if (threadIdx.x < 32 && ahead) {
+        pa = __shfl_sync(0xffffffffu, pa, 0); pb = __shfl_sync(0xffffffffu, pb, 0);
+        blk::prefetch_l2(gsrc + pa, (size_t)(pb - pa) * 4, lane, 32);
+    }
+    if (lane == 0 && e1 > e0) atomicAdd(la.stats + ((blockIdx.x & 1023u) << 2), (unsigned long long)(e1 - e0));
+    if (!act) return;
+    if (!LAST || (rowm & SEG_MULTI)) C::acc_store(la.blk_acc, la.blk_stride, (uint32_t)s0 + lane, acc);      // hub rows: finished by reduce_hubmerge_kernel
+    else {
+        const AgentID id = agent_id((uint32_t)la.type, ds.rank, (uint64_t)idx + 1);
+        const bool alive_after = f.finish(ctx, self, id, acc);
+        if (la.in_write) {                                                 // transition_with_write! (AgentMethods.jl:159-181)
+            if (alive_after) { if (av.size) soa_store<State>(av.independent ? av.state_r : av.state_w, av.cap, idx, self); }
+            else if (av.immortal) atomicOr(ds.error, (uint32_t)DERR_IMMORTAL_DIED);
+            else av.died_w[idx] = 1;
+        }
+    }
+}
+// rows cut into several segments: merge the parked segment accumulators in segment order, then finish() and the write rules
+template <class F>
+__global__ void __launch_bounds__(128) reduce_hubmerge_kernel(const __grid_constant__ KernelArgs ka) {
+    typedef BlockedCfg<F> C;
+    typedef typename C::State State;
+    typedef typename C::Acc Acc;
+    const LaunchArgs& la = ka.la;
+    const DeviceSim& ds = ka.ds;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= la.blk_nhub) return;
+    const uint32_t idx = la.blk_hub_rows[t];
+    const AgentView& av = ds.agents[la.type];
+    if (av.died_r && av.died_r[idx]) return;
+    const F f{};
+    Ctx<F, MODE_DIRECT, 1> ctx(ds, la, idx, 0);
+    State self = soa_load<State>(av.state_r, av.cap, idx);
+    Acc acc, part;
+    const uint32_t k0 = la.blk_hub_seg[2 * t], k1 = la.blk_hub_seg[2 * t + 1];
+    C::acc_load(la.blk_acc, la.blk_stride, k0, acc);
+    for (uint32_t k = k0 + 1; k < k1; ++k) { C::acc_load(la.blk_acc, la.blk_stride, k, part); f.merge(acc, part); }
+    const AgentID id = agent_id((uint32_t)la.type, ds.rank, (uint64_t)idx + 1);
+    const bool alive_after = f.finish(ctx, self, id, acc);
+    if (la.in_write) {
+        if (alive_after) { if (av.size) soa_store<State>(av.independent ? av.state_r : av.state_w, av.cap, idx, self); }
+        else if (av.immortal) atomicOr(ds.error, (uint32_t)DERR_IMMORTAL_DIED);
+        else av.died_w[idx] = 1;
+    }
+}
 // key column of the source type: four slots per thread, one packed store
 template <class F>
 __global__ void __launch_bounds__(256) build_keys_kernel(const __grid_constant__ KernelArgs ka) {
@@ -1420,6 +1596,34 @@ cudaError_t launch_prefilter(KernelArgs& ka, unsigned long long work) {
     else reduce_prefilter_kernel<F, false, false, WPC, RF><<<grid, TPB, 0, la.stream>>>(ka);
     return cudaGetLastError();
 }
+#ifndef VB_SEG_WARPS
+#define VB_SEG_WARPS 2
+#endif
+#ifndef VB_SEG_MINB
+#define VB_SEG_MINB 24
+#endif
+template <class F>
+cudaError_t launch_segsweep(KernelArgs& ka) {
+    const LaunchArgs& la = ka.la;
+    constexpr int WPC = VB_SEG_WARPS, MINB = VB_SEG_MINB;
+    static int pwave = 0;                                               // resident CTAs of this shape on the whole device
+    if (!pwave) {
+        int dev = 0, sms = 148, per_sm = MINB;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_segsweep_kernel<F, false, false, WPC, MINB>, 32 * WPC, 0);
+        pwave = sms * (per_sm > 0 ? per_sm : 1);
+        if (getenv("VB_BLOCK_AHEAD")) pwave = atoi(getenv("VB_BLOCK_AHEAD"));
+    }
+    ka.la.blk_ahead = (uint32_t)pwave;
+    const unsigned long long groups = ((unsigned long long)la.blk_nseg + 31) / 32;
+    const unsigned grid = (unsigned)((groups + WPC - 1) / WPC);
+    if (la.blk_first && la.blk_last) reduce_segsweep_kernel<F, true, true, WPC, MINB><<<grid, 32 * WPC, 0, la.stream>>>(ka);
+    else if (la.blk_first) reduce_segsweep_kernel<F, true, false, WPC, MINB><<<grid, 32 * WPC, 0, la.stream>>>(ka);
+    else if (la.blk_last) reduce_segsweep_kernel<F, false, true, WPC, MINB><<<grid, 32 * WPC, 0, la.stream>>>(ka);
+    else reduce_segsweep_kernel<F, false, false, WPC, MINB><<<grid, 32 * WPC, 0, la.stream>>>(ka);
+    return cudaGetLastError();
+}
 template <class F>
 cudaError_t launch_blocked(const LaunchArgs& la) {
     static thread_local KernelArgs ka;
@@ -1441,6 +1645,15 @@ cudaError_t launch_blocked(const LaunchArgs& la) {
     }
     ka.la.blk_ahead = (uint32_t)wave;
     if constexpr (F::kPrefilter) {
+        if (la.blk_op == 1) {                                           // hub rows of the segmented view
+            if (la.blk_nhub == 0) return cudaSuccess;
+            reduce_hubmerge_kernel<F><<<(la.blk_nhub + 127) / 128, 128, 0, la.stream>>>(ka);
+            return cudaGetLastError();
+        }
+        if (la.blk_prefilter && la.blk_seg_row) {                       // segmented view
+            if (!la.blk_key || la.blk_nseg == 0) return la.blk_key ? cudaSuccess : cudaErrorInvalidValue;
+            return launch_segsweep<F>(ka);
+        }
         if (la.blk_prefilter) {
             if (!la.blk_key) return cudaErrorInvalidValue;
             static const int wpc = [] { const char* e = getenv("VB_PF_WARPS"); const int v = e ? atoi(e) : VB_PF_WARPS_DEFAULT; return v == 2 || v == 4 ? v : 8; }();

@@ -619,6 +619,65 @@ __global__ void blk_fill_kernel(const BlkBuildArgs a) {
         a.bsrc[a.boff[(size_t)b * a.rpad + i] + cur[b]++] = s;    // row order is kept inside every block
     }
 }
+// ---- segmented source-blocked view (prefiltered sweeps): rows of more than seg_len entries are cut into segments ---------------------
+struct SegBuildArgs {
+    const uint32_t* off; const uint32_t* src; uint32_t row0, n, rows, seg_len;
+    uint32_t tb, nsl, bsize, nb, spad, nseg;
+    const uint32_t* sfirst;          // [n + 1] first segment of every called row
+    uint32_t* seg_row; uint32_t* seg_lo; uint32_t* seg_hi;
+    uint32_t* boff; uint32_t* bsrc; uint32_t* error;
+};
+__global__ void seg_count_kernel(const uint32_t* __restrict__ off, uint32_t row0, uint32_t n, uint32_t rows, uint32_t seg_len, uint32_t* __restrict__ cnt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { cnt[i] = 0; return; }
+    const uint32_t r = row0 + (uint32_t)i;
+    const uint32_t len = r < rows ? off[r + 1] - off[r] : 0u;
+    cnt[i] = len <= seg_len ? 1u : (len + seg_len - 1) / seg_len;
+}
+__global__ void seg_fill_kernel(const SegBuildArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint32_t r = a.row0 + (uint32_t)i;
+    const uint32_t lo = r < a.rows ? a.off[r] : 0u, hi = r < a.rows ? a.off[r + 1] : 0u;
+    const uint32_t s0 = a.sfirst[i], ns = a.sfirst[i + 1] - s0;
+    for (uint32_t k = 0; k < ns; ++k) {
+        a.seg_row[s0 + k] = (uint32_t)i | (ns > 1 ? 0x80000000u : 0u);
+        const uint32_t l = lo + k * a.seg_len;
+        a.seg_lo[s0 + k] = l;
+        a.seg_hi[s0 + k] = (hi - l > a.seg_len) ? l + a.seg_len : hi;
+    }
+}
+__global__ void seg_blk_count_kernel(const SegBuildArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nseg) return;
+    for (uint32_t k = a.seg_lo[t]; k < a.seg_hi[t]; ++k) {
+        const uint32_t s = a.src[k] - a.tb;
+        if (s >= a.nsl) { atomicOr(a.error, 1u); continue; }     // a source of another agent type
+        a.boff[(size_t)(s / a.bsize) * a.spad + t] += 1;          // one thread per segment: no atomics
+    }
+}
+__global__ void seg_blk_fill_kernel(const SegBuildArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nseg) return;
+    uint16_t cur[64];                                             // entries of this segment already placed, per block (seg_len <= 65535)
+    for (uint32_t b = 0; b < a.nb; ++b) cur[b] = 0;
+    const uint32_t tag = ((uint32_t)t & 31u) << 27;
+    for (uint32_t k = a.seg_lo[t]; k < a.seg_hi[t]; ++k) {
+        const uint32_t s = a.src[k] - a.tb;
+        if (s >= a.nsl) continue;
+        const uint32_t b = s / a.bsize;
+        a.bsrc[a.boff[(size_t)b * a.spad + t] + cur[b]++] = (s - b * a.bsize) | tag;    // entry order is kept inside every block
+    }
+}
+__global__ void seg_hub_flags_kernel(const uint32_t* __restrict__ sfirst, uint32_t n, uint32_t* __restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = sfirst[i + 1] - sfirst[i] > 1 ? 1u : 0u;
+}
+__global__ void seg_hub_first_kernel(const uint32_t* __restrict__ hub_rows, uint32_t nhub, const uint32_t* __restrict__ sfirst, uint32_t* __restrict__ hub_seg) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nhub) { hub_seg[2 * i] = sfirst[hub_rows[i]]; hub_seg[2 * i + 1] = sfirst[hub_rows[i] + 1]; }    // [first, end) of every hub row
+}
 __global__ void mark_dead_kernel(const uint32_t* __restrict__ flag, uint32_t n, uint8_t* __restrict__ dead, uint32_t base) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) dead[base + i] = 1;
@@ -884,6 +943,11 @@ struct EdgeStore {
     struct Blocked {
         uint32_t* boff = nullptr; uint32_t* bsrc = nullptr; uint32_t* heavy_bits = nullptr; uint8_t* acc = nullptr;
         uint8_t* key = nullptr; uint32_t key_n = 0;   // prefiltered sweeps: one key byte per slot of the source type (rebuilt by every apply)
+        // segmented form (prefiltered sweeps): boff / acc are indexed by segment, rpad = padded segment count
+        bool segmented = false;
+        uint32_t nseg = 0, seg_len = 0, nhub = 0;
+        uint32_t* seg_row = nullptr;                  // [nseg] called row | 0x80000000 when the row has several segments
+        uint32_t* hub_rows = nullptr; uint32_t* hub_seg = nullptr;   // rows with several segments, [2 nhub] their segment ranges [first, end)
         uint32_t nb = 0, bsize = 0, rpad = 0, n = 0, acc_bytes = 0, heavy_min = 0;
         std::vector<uint32_t> bstart;                 // position in bsrc where each block's entries start (nb + 1 values)
         std::vector<uint32_t*> arows;                 // per block: ascending list of the rows that own an entry in it
@@ -988,6 +1052,7 @@ void free_blocked(EdgeStore& e) {
     for (auto p : e.blk.arows) dfree(p);
     for (auto p : e.blk.aoff) dfree(p);
     dfree(e.blk.boff); dfree(e.blk.bsrc); dfree(e.blk.heavy_bits); dfree(e.blk.acc); dfree(e.blk.key);
+    dfree(e.blk.seg_row); dfree(e.blk.hub_rows); dfree(e.blk.hub_seg);
     e.blk = EdgeStore::Blocked{};
 }
 void free_edge_read(EdgeStore& e) {
@@ -1990,8 +2055,13 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
         if (nb > 64) { bsize = (nsl + 63) / 64; nb = (nsl + bsize - 1) / bsize; }
     }
     EdgeStore::Blocked& k = pe.blk;
+    // prefiltered sweeps walk the SEGMENTED view (rows cut into segments of seg_len entries, no hub pass); VB_PF_SEG=0 keeps the
+    // row-based view with the block-per-agent pass for hub rows
+    static const bool env_seg = !(getenv("VB_PF_SEG") && atoi(getenv("VB_PF_SEG")) == 0);
+    static const uint32_t env_seg_len = getenv("VB_SEG_LEN") ? (uint32_t)std::min(65535, std::max(32, atoi(getenv("VB_SEG_LEN")))) : 2048u;
+    const bool seg = pf && env_seg && bsize <= (1u << 27);
     if (k.boff && k.version == pe.version && k.epoch == layout_epoch && k.called == C && k.source == ti->source_type && k.n == n &&
-        k.acc_bytes == ti->acc_bytes && k.bsize == bsize && k.heavy_min == heavy_min && (k.key != nullptr) == pf)
+        k.acc_bytes == ti->acc_bytes && k.bsize == bsize && k.heavy_min == heavy_min && (k.key != nullptr) == pf && k.segmented == seg)
         return true;
     if (k.seen_version != pe.version) { k.seen_version = pe.version; k.seen = 1; k.refused = false; }
     else if (k.seen < 0xffffffffu) ++k.seen;
@@ -2004,6 +2074,77 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
         k.seen_version = sv; k.seen = sn;
     }
     g_trace.begin();
+    if (seg) {
+        uint32_t *sfirst = nullptr, *seg_lo = nullptr, *seg_hi = nullptr, *scr = nullptr, *flag = nullptr, *pos = nullptr;
+        try {
+            // segments of the called rows: count -> scan -> fill
+            sfirst = dalloc<uint32_t>((uint64_t)n + 2);
+            const uint32_t row0 = pe.singletype ? 0u : base[C];
+            seg_count_kernel<<<nblk((uint64_t)n + 1), 256, 0, g_stream>>>(pe.off, row0, n, pe.rows, env_seg_len, sfirst); LAUNCH_CHECK();
+            scr = dalloc<uint32_t>(vbp::scan_scratch_words((uint64_t)n + 1));
+            vbp::exclusive_scan(sfirst, sfirst, (uint64_t)n + 1, d_scalars, scr, g_stream); g_launches += 3;
+            uint32_t nseg = 0;
+            CK(cudaMemcpyAsync(&nseg, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(scr); scr = nullptr;
+            const uint64_t spad = ((uint64_t)nseg + 1 + 3) & ~3ull;
+            if (spad * nb >= 0xfffffff0ull) throw CudaError("segmented view too large");
+            k.seg_row = dalloc<uint32_t>((uint64_t)nseg + 1);
+            seg_lo = dalloc<uint32_t>((uint64_t)nseg + 1); seg_hi = dalloc<uint32_t>((uint64_t)nseg + 1);
+            const uint64_t total = spad * nb;
+            k.boff = dalloc<uint32_t>(total + 4);
+            CK(cudaMemsetAsync(k.boff, 0, (total + 4) * 4, g_stream));
+            CK(cudaMemsetAsync(d_scalars, 0, 8, g_stream));
+            SegBuildArgs sa{};
+            sa.off = pe.off; sa.src = pe.src; sa.row0 = row0; sa.n = n; sa.rows = pe.rows; sa.seg_len = env_seg_len;
+            sa.tb = base[ti->source_type]; sa.nsl = nsl; sa.bsize = bsize; sa.nb = nb; sa.spad = (uint32_t)spad; sa.nseg = nseg;
+            sa.sfirst = sfirst; sa.seg_row = k.seg_row; sa.seg_lo = seg_lo; sa.seg_hi = seg_hi; sa.boff = k.boff; sa.bsrc = nullptr; sa.error = d_scalars + 1;
+            seg_fill_kernel<<<nblk(n), 256, 0, g_stream>>>(sa); LAUNCH_CHECK();
+            seg_blk_count_kernel<<<nblk(nseg), 256, 0, g_stream>>>(sa); LAUNCH_CHECK();
+            scr = dalloc<uint32_t>(vbp::scan_scratch_words(total + 1));
+            vbp::exclusive_scan(k.boff, k.boff, total + 1, d_scalars, scr, g_stream); g_launches += 3;
+            uint32_t res[2] = {0, 0};
+            CK(cudaMemcpyAsync(res, d_scalars, 8, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(scr); scr = nullptr;
+            if (res[1]) throw CudaError("a source of another agent type");
+            k.bstart.assign(nb + 1, res[0]);
+            for (uint32_t b = 0; b < nb; ++b) CK(cudaMemcpyAsync(&k.bstart[b], k.boff + (size_t)b * spad, 4, cudaMemcpyDeviceToHost, g_stream));
+            k.bsrc = dalloc<uint32_t>((uint64_t)res[0] + 64);
+            sa.bsrc = k.bsrc;
+            seg_blk_fill_kernel<<<nblk(nseg), 256, 0, g_stream>>>(sa); LAUNCH_CHECK();
+            // rows with several segments: their accumulators are merged by a pass of their own
+            flag = dalloc<uint32_t>(n); pos = dalloc<uint32_t>(n);
+            scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
+            seg_hub_flags_kernel<<<nblk(n), 256, 0, g_stream>>>(sfirst, n, flag); LAUNCH_CHECK();
+            vbp::exclusive_scan(flag, pos, n, d_scalars, scr, g_stream); g_launches += 3;
+            uint32_t nhub = 0;
+            CK(cudaMemcpyAsync(&nhub, d_scalars, 4, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            if (nhub) {
+                k.hub_rows = dalloc<uint32_t>(nhub); k.hub_seg = dalloc<uint32_t>((uint64_t)nhub * 2);
+                vbp::compact_indices_kernel<<<nblk(n), 256, 0, g_stream>>>(flag, pos, n, k.hub_rows); LAUNCH_CHECK();
+                seg_hub_first_kernel<<<nblk(nhub), 256, 0, g_stream>>>(k.hub_rows, nhub, sfirst, k.hub_seg); LAUNCH_CHECK();
+            }
+            k.acc = (uint8_t*)g_pool.alloc((size_t)spad * ti->acc_bytes);
+            k.key_n = nsl; k.key = dalloc<uint8_t>((uint64_t)nsl + 64);
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(sfirst); dfree(seg_lo); dfree(seg_hi); dfree(scr); dfree(flag); dfree(pos);
+            k.arows.assign(nb, nullptr); k.aoff.assign(nb, nullptr); k.acount.assign(nb, 0);
+            k.segmented = true; k.nseg = nseg; k.seg_len = env_seg_len; k.nhub = nhub; k.rpad = (uint32_t)spad;
+        } catch (...) {
+            dfree(sfirst); dfree(seg_lo); dfree(seg_hi); dfree(scr); dfree(flag); dfree(pos);
+            free_blocked(pe);
+            k.seen_version = pe.version; k.seen = 2; k.refused = true;     // e.g. out of memory: stay on the direct path
+            cudaGetLastError();
+            return false;
+        }
+        k.heavy_min = heavy_min;
+        k.nb = nb; k.bsize = bsize; k.n = n; k.acc_bytes = ti->acc_bytes; k.called = C; k.source = ti->source_type;
+        k.version = pe.version; k.epoch = layout_epoch;
+        g_trace.end("build segmented source-blocked view", pe.name);
+        return true;
+    }
     try {
         const uint64_t total = rpad * nb;
         k.boff = dalloc<uint32_t>(total + 4);
@@ -2490,7 +2631,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                     constexpr uint32_t HEAVY_DIRECT = 1024, HEAVY_BLOCKED = 16384;
                     blocked = ti->reduce && s.ensure_blocked(ti->primary_edge, ti, C, n, HEAVY_BLOCKED);
                     const uint32_t HEAVY_MIN = blocked ? HEAVY_BLOCKED : HEAVY_DIRECT;
-                    if (pe.heavy_version != pe.version || pe.heavy_type != C || pe.heavy_min != HEAVY_MIN) {
+                    const bool segmented = blocked && pe.blk.segmented;          // hub rows are cut into segments: no pass of their own
+                    if (!segmented && (pe.heavy_version != pe.version || pe.heavy_type != C || pe.heavy_min != HEAVY_MIN)) {
                         dfree(pe.heavy_rows); pe.heavy_rows = nullptr; pe.heavy_n = 0;
                         uint32_t* flag = dalloc<uint32_t>(n); uint32_t* pos = dalloc<uint32_t>(n);
                         uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
@@ -2507,7 +2649,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                         CK(cudaStreamSynchronize(g_stream));
                         dfree(flag); dfree(pos); dfree(scr);
                     }
-                    heavy_n = pe.heavy_n; heavy_rows = pe.heavy_rows;
+                    if (!segmented) { heavy_n = pe.heavy_n; heavy_rows = pe.heavy_rows; }
                     la.primary_edge = ti->primary_edge; la.heavy_min = HEAVY_MIN;
                     const double avg = (double)pe.nnz / std::max<uint32_t>(1, n);
                     la.group = avg < 48.0 ? 8 : 32;
@@ -2527,6 +2669,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 lb.blk_src = k.bsrc; lb.blk_acc = k.acc; lb.blk_stride = k.rpad; lb.blk_heavy = heavy_n ? k.heavy_bits : nullptr;
                 const bool pf = k.key != nullptr && s.prefilter_on(ti);
                 lb.blk_key = pf ? k.key : nullptr; lb.blk_nkeys = pf ? k.key_n : 0; lb.blk_prefilter = pf ? 1 : 0;
+                if (k.segmented) { lb.blk_seg_row = k.seg_row; lb.blk_nseg = k.nseg; lb.blk_heavy = nullptr; }
                 if (pf) { CK(ti->launch_keys(lb)); ++g_launches; }          // keys of this step's read states (inside the timed region)
                 // sweeps over blocks that hold no entry (capacity beyond the agents in use) are skipped; the first sweep that runs
                 // initialises the accumulators, the last one runs finish()
@@ -2549,6 +2692,11 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 for (size_t i = 0; i < todo.size(); ++i) {
                     lb.blk_off = k.boff + (size_t)todo[i] * k.rpad; lb.blk_first = i == 0; lb.blk_last = i + 1 == todo.size();
                     lb.blk_rows = use_lists ? k.arows[todo[i]] : nullptr; lb.blk_roff = k.aoff[todo[i]]; lb.blk_nrows = k.acount[todo[i]];
+                    lb.blk_base = todo[i] * k.bsize;
+                    CK(ti->launch_blocked(lb)); ++g_launches;
+                }
+                if (k.segmented && k.nhub) {       // rows cut into several segments: merge their parked accumulators, finish
+                    lb.blk_op = 1; lb.blk_hub_rows = k.hub_rows; lb.blk_hub_seg = k.hub_seg; lb.blk_nhub = k.nhub;
                     CK(ti->launch_blocked(lb)); ++g_launches;
                 }
                 swept = (uint32_t)todo.size();
