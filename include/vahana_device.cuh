@@ -171,6 +171,7 @@ struct LaunchArgs {
     const uint32_t* blk_roff;             // with a row list: [blk_nrows + 1] entry positions of the listed rows (their entries are contiguous)
     uint8_t* blk_key;                     // prefilter (F::kPrefilter): one key byte per slot of the source type, written by launch_keys
     uint32_t blk_nkeys;                   //   slots of the source type covered by blk_key (local + ghosts)
+    uint32_t blk_key_first;               //   launch_keys: first slot of the range to (re)build, blk_nkeys slots from there
     int blk_prefilter;                    //   sweeps gather keys and fetch the exact state only where may_accept() holds
     // segmented view (prefiltered sweeps): rows longer than the segment length are cut into segments, a warp owns 32
     // consecutive segments, an entry is (source slot - blk_base) | (segment & 31) << 27, accumulators are parked per segment
@@ -1458,17 +1459,19 @@ __global__ void __launch_bounds__(256) build_keys_kernel(const __grid_constant__
     const LaunchArgs& la = ka.la;
     const DeviceSim& ds = ka.ds;
     const AgentView& sv = ds.agents[F::kSourceType];
-    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i0 >= la.blk_nkeys) return;
+    // slots [first, end): four per thread on 4-aligned groups (one packed store), single bytes at a ragged head or tail
+    const uint64_t first = la.blk_key_first, end = first + la.blk_nkeys;
+    const uint64_t i0 = (first & ~3ull) + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= end) return;
     const F f{};
     Ctx<F, MODE_DIRECT, 1> ctx(ds, la, (uint32_t)i0, 0);
-    if (i0 + 3 < la.blk_nkeys) {
+    if (i0 >= first && i0 + 3 < end) {
         uint32_t packed = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) packed |= (uint32_t)f.key(ctx, soa_load<Source>(sv.state_r, sv.cap, (uint32_t)i0 + j)) << (8 * j);
         *reinterpret_cast<uint32_t*>(la.blk_key + i0) = packed;
     } else
-        for (uint64_t i = i0; i < la.blk_nkeys; ++i) la.blk_key[i] = f.key(ctx, soa_load<Source>(sv.state_r, sv.cap, (uint32_t)i));
+        for (uint64_t i = i0 < first ? first : i0; i < i0 + 4 && i < end; ++i) la.blk_key[i] = f.key(ctx, soa_load<Source>(sv.state_r, sv.cap, (uint32_t)i));
 }
 template <class F>
 cudaError_t launch_keys(const LaunchArgs& la) {
@@ -1477,7 +1480,7 @@ cudaError_t launch_keys(const LaunchArgs& la) {
     ka.ds = *la.ds;
     ka.la.ds = nullptr;
     if (la.blk_nkeys == 0) return cudaSuccess;
-    build_keys_kernel<F><<<(unsigned)(((unsigned long long)la.blk_nkeys + 1023) / 1024), 256, 0, la.stream>>>(ka);
+    build_keys_kernel<F><<<(unsigned)(((unsigned long long)la.blk_nkeys + 3 + 1023) / 1024), 256, 0, la.stream>>>(ka);
     return cudaGetLastError();
 }
 

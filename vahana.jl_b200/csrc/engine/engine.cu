@@ -104,6 +104,25 @@ struct Trace {
         fprintf(stderr, "[vb trace] %-28s %-24s %9.3f ms\n", what, detail.c_str(), ms);
         t0 = std::chrono::steady_clock::now();
     }
+    // VB_TRACE=2: device times between marks on the main stream (CUDA events), printed by flush_marks() after a synchronize
+    bool marks_on = getenv("VB_TRACE") != nullptr && atoi(getenv("VB_TRACE")) >= 2;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void mark(const std::string& what) {
+        if (!marks_on) return;
+        cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, g_stream);
+        marks.emplace_back(what, e);
+    }
+    void flush_marks() {
+        if (!marks_on || marks.empty()) return;
+        cudaStreamSynchronize(g_stream);
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0; cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, "[vb mark ] %-54s %9.3f ms\n", marks[i].first.c_str(), ms);
+        }
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
 };
 Trace g_trace;
 
@@ -525,6 +544,21 @@ __global__ void halo_push_kernel(const HaloPushArgs a) {
     else if (a.word == 16) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
     else for (uint32_t b = 0; b < a.word; ++b) dp[b] = sp[b];
 }
+// Cross-rank barrier over peer memory: every rank owns a small flag array mapped into the peers (CUDA IPC); a rank announces epoch E
+// by storing it into slot [rank] of every peer's array and waits until its own array holds >= E in every peer's slot.  One warp, a few
+// microseconds over NVLink, stream-ordered like any kernel (the ncclAllGather it replaces costs a collective launch per barrier).
+struct PeerFlagPtrs { unsigned long long* p[16]; };
+__global__ void peer_barrier_kernel(unsigned long long* mine, const PeerFlagPtrs peers, uint32_t rank, uint32_t P, unsigned long long epoch) {
+    const uint32_t r = threadIdx.x;
+    __threadfence_system();                                   // everything this stream wrote before (also into peer memory) is visible first
+    if (r < P && r != rank) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.p[r] + rank), "l"(epoch) : "memory");
+        unsigned long long seen = 0;
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine + r) : "memory"); } while (seen < epoch);
+    }
+    __syncwarp();
+    __threadfence_system();
+}
 // died-agent ids of the other ranks (C7: join(aids), src/AgentMethods.jl:338): mark the ghosts that mirror them
 struct MarkDeadArgs {
     const uint64_t* ids; uint32_t n; uint8_t* dead; uint32_t rank; uint32_t ntypes;
@@ -622,8 +656,16 @@ __global__ void blk_fill_kernel(const BlkBuildArgs a) {
 // ---- segmented source-blocked view (prefiltered sweeps): rows of more than seg_len entries are cut into segments ---------------------
 struct SegBuildArgs {
     const uint32_t* off; const uint32_t* src; uint32_t row0, n, rows, seg_len;
-    uint32_t tb, nsl, bsize, nb, spad, nseg;
+    uint32_t tb, nsl, nb, spad, nseg;
+    // blocks of the source type's slots: nbl blocks of bsize_l slots over the local slots [0, lcap), then blocks of bsize_g over the ghosts
+    uint32_t lcap, bsize_l, nbl, bsize_g;
     const uint32_t* sfirst;          // [n + 1] first segment of every called row
+    __device__ __forceinline__ uint32_t block_of(uint32_t s, uint32_t& first) const {
+        uint32_t b;
+        if (s < lcap) { b = s / bsize_l; if (b >= nbl) b = nbl - 1; first = b * bsize_l; }
+        else { b = (s - lcap) / bsize_g; if (nbl + b >= nb) b = nb - nbl - 1; first = lcap + b * bsize_g; b += nbl; }
+        return b;
+    }
     uint32_t* seg_row; uint32_t* seg_lo; uint32_t* seg_hi;
     uint32_t* boff; uint32_t* bsrc; uint32_t* error;
 };
@@ -654,7 +696,8 @@ __global__ void seg_blk_count_kernel(const SegBuildArgs a) {
     for (uint32_t k = a.seg_lo[t]; k < a.seg_hi[t]; ++k) {
         const uint32_t s = a.src[k] - a.tb;
         if (s >= a.nsl) { atomicOr(a.error, 1u); continue; }     // a source of another agent type
-        a.boff[(size_t)(s / a.bsize) * a.spad + t] += 1;          // one thread per segment: no atomics
+        uint32_t first;
+        a.boff[(size_t)a.block_of(s, first) * a.spad + t] += 1;   // one thread per segment: no atomics
     }
 }
 __global__ void seg_blk_fill_kernel(const SegBuildArgs a) {
@@ -666,8 +709,9 @@ __global__ void seg_blk_fill_kernel(const SegBuildArgs a) {
     for (uint32_t k = a.seg_lo[t]; k < a.seg_hi[t]; ++k) {
         const uint32_t s = a.src[k] - a.tb;
         if (s >= a.nsl) continue;
-        const uint32_t b = s / a.bsize;
-        a.bsrc[a.boff[(size_t)b * a.spad + t] + cur[b]++] = (s - b * a.bsize) | tag;    // entry order is kept inside every block
+        uint32_t first;
+        const uint32_t b = a.block_of(s, first);
+        a.bsrc[a.boff[(size_t)b * a.spad + t] + cur[b]++] = (s - first) | tag;          // entry order is kept inside every block
     }
 }
 __global__ void seg_hub_flags_kernel(const uint32_t* __restrict__ sfirst, uint32_t n, uint32_t* __restrict__ flag) {
@@ -892,7 +936,15 @@ struct AgentStore {
         std::vector<void*> opened;            // cudaIpcOpenMemHandle results to close on refresh
         uint64_t sig = 0;                     // layout signature the map was exchanged for (0 = never)
         bool ok = false;
+        bool check = true;                    // some rank's layout may have changed since the exchange: the next halo re-checks (collective)
+        // the halo travels in `ng` phases, one per ghost block (the same count on every rank; a rank's ghost block holds gblock[rank]
+        // slots): phase j carries the states a peer mirrors in ITS ghost block j, so that the sweep over block j can start while the
+        // later blocks are still on the wire
+        uint32_t ng = 1;
+        std::vector<uint32_t> gblock, goff_me; // [nranks] peer r's ghost block size; position of MY agents' range in peer r's ghost segment
     } peers;
+    std::vector<cudaEvent_t> ev_phase;        // recorded on the halo stream after phase j has landed everywhere
+    uint32_t halo_pending = 0, halo_waited = 0;   // phases started by this apply / already awaited by the main stream
     uint8_t* send_buf = nullptr;              // packed states for the halo exchange
     bool halo_dirty = true;
     uint32_t stride() const { return cap + gcap; }
@@ -946,6 +998,15 @@ struct EdgeStore {
         // segmented form (prefiltered sweeps): boff / acc are indexed by segment, rpad = padded segment count
         bool segmented = false;
         uint32_t nseg = 0, seg_len = 0, nhub = 0;
+        uint32_t lcap = 0, nbl = 0, bsize_g = 0;     // blocks: nbl of bsize slots over the local slots [0, lcap), the others of bsize_g over the ghosts
+        uint32_t block_first(uint32_t b) const { return b < nbl ? b * bsize : lcap + (b - nbl) * bsize_g; }
+        // slots of block b that can hold a source: the last block of a range takes its tail; local slots end at `used` (slots in use)
+        uint32_t block_slots(uint32_t b, uint32_t used, uint32_t nsl) const {
+            const uint32_t f = block_first(b), sz = b < nbl ? bsize : bsize_g;
+            const uint32_t lend = std::min(lcap, used);
+            const uint32_t lim = b < nbl ? (b + 1 == nbl ? lend : std::min(lend, f + sz)) : (b + 1 == nb ? nsl : std::min(nsl, f + sz));
+            return lim > f ? lim - f : 0u;
+        }
         uint32_t* seg_row = nullptr;                  // [nseg] called row | 0x80000000 when the row has several segments
         uint32_t* hub_rows = nullptr; uint32_t* hub_seg = nullptr;   // rows with several segments, [2 nhub] their segment ranges [first, end)
         uint32_t nb = 0, bsize = 0, rpad = 0, n = 0, acc_bytes = 0, heavy_min = 0;
@@ -1007,8 +1068,13 @@ struct vb_sim {
     void compute_bases(uint32_t* out) const;
     void ensure_agent_cap(int t, uint64_t need, uint32_t ghost_need = 0, bool do_rebase = true);
     void build_ghosts(const uint64_t* const* extra = nullptr, const uint64_t* extra_n = nullptr, int n_extra = 0);
-    void halo_exchange(int t);
+    void halo_exchange(int t);                // starts the exchange (peer-memory path: on the halo stream, in phases); halo_wait() joins
+    void halo_wait(int t, uint32_t phases);   // the main stream waits until the first `phases` phases of type t's halo have landed
+    void halo_wait_all();
     bool refresh_peer_map(int t);
+    // some rank's buffers / ghost tables may have changed (called at the same events on every rank): the next halo exchange of every
+    // agent type re-checks the peer maps
+    void mark_peer_check() { for (auto& a : agents) a.peers.check = true; }
     uint64_t halo_bytes = 0;   // bytes received by the last apply's halo exchanges
     double blk_block_mb = -1, blk_min_mb = -1; int blk_eager = -1;   // vb_set_read_blocking (negative = environment / default)
     int blk_prefilter = -1;                                          // vb_set_read_prefilter (negative = environment / default)
@@ -1044,6 +1110,8 @@ void free_agent(AgentStore& a) {
     for (void* q : a.peers.opened) cudaIpcCloseMemHandle(q);
     cudaGetLastError();
     a.peers = AgentStore::PeerMap{};
+    for (cudaEvent_t e : a.ev_phase) cudaEventDestroy(e);
+    a.ev_phase.clear();
     dfree(a.state[0]); if (a.state[1] != a.state[0]) dfree(a.state[1]);
     dfree(a.died[0]); dfree(a.died[1]); dfree(a.reuse); dfree(a.ghost_ids); dfree(a.send_slots); dfree(a.send_buf);
     a.state[0] = a.state[1] = a.died[0] = a.died[1] = nullptr; a.reuse = nullptr; a.ghost_ids = nullptr; a.send_slots = nullptr; a.send_buf = nullptr;
@@ -2059,9 +2127,27 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
     // row-based view with the block-per-agent pass for hub rows
     static const bool env_seg = !(getenv("VB_PF_SEG") && atoi(getenv("VB_PF_SEG")) == 0);
     static const uint32_t env_seg_len = getenv("VB_SEG_LEN") ? (uint32_t)std::min(65535, std::max(32, atoi(getenv("VB_SEG_LEN")))) : 2048u;
-    const bool seg = pf && env_seg && bsize <= (1u << 27);
+    bool seg = pf && env_seg;
+    uint32_t g_lcap = 0, g_nbl = 0, g_bsl = 0, g_bsg = 0;
+    if (seg) {
+        // blocks of keys: the local slots in as few even blocks as the key budget allows; the ghosts in the blocks the halo travels in
+        // (AgentStore::PeerMap: the same count on every rank), so that a ghost block can be swept as soon as its phase has landed
+        const double key_slots = std::max(1.0, (blk_block_mb > 0 ? block_mb / 75.0 : 1.0) * env_key_block_mb * 1e6);
+        g_lcap = src.nghost ? src.cap : nsl;
+        const uint32_t used = std::max<uint32_t>(1u, std::min<uint32_t>(g_lcap, std::max<uint32_t>(src.nslots, 1u)));   // capacity beyond the slots in use holds no source
+        g_nbl = (uint32_t)std::max<double>(1.0, std::ceil((double)used / key_slots));
+        g_bsl = (((used + g_nbl - 1) / g_nbl) + 63u) & ~63u;
+        uint32_t ngb = 0;
+        if (src.nghost) {
+            if (src.peers.ok && !src.peers.gblock.empty()) { ngb = src.peers.ng; g_bsg = src.peers.gblock[rank]; }
+            else { ngb = (uint32_t)std::max<double>(1.0, std::ceil((double)src.nghost / key_slots)); g_bsg = (((src.nghost + ngb - 1) / ngb) + 63u) & ~63u; }
+        }
+        if (g_nbl + ngb > 64 || g_bsl > (1u << 27) || g_bsg > (1u << 27)) seg = false;      // (the row-based view below takes over)
+        else { nb = g_nbl + ngb; bsize = g_bsl; }
+    }
     if (k.boff && k.version == pe.version && k.epoch == layout_epoch && k.called == C && k.source == ti->source_type && k.n == n &&
-        k.acc_bytes == ti->acc_bytes && k.bsize == bsize && k.heavy_min == heavy_min && (k.key != nullptr) == pf && k.segmented == seg)
+        k.acc_bytes == ti->acc_bytes && k.bsize == bsize && k.heavy_min == heavy_min && (k.key != nullptr) == pf && k.segmented == seg &&
+        (!seg || (k.nb == nb && k.lcap == g_lcap && k.nbl == g_nbl && k.bsize_g == g_bsg)))
         return true;
     if (k.seen_version != pe.version) { k.seen_version = pe.version; k.seen = 1; k.refused = false; }
     else if (k.seen < 0xffffffffu) ++k.seen;
@@ -2097,7 +2183,8 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
             CK(cudaMemsetAsync(d_scalars, 0, 8, g_stream));
             SegBuildArgs sa{};
             sa.off = pe.off; sa.src = pe.src; sa.row0 = row0; sa.n = n; sa.rows = pe.rows; sa.seg_len = env_seg_len;
-            sa.tb = base[ti->source_type]; sa.nsl = nsl; sa.bsize = bsize; sa.nb = nb; sa.spad = (uint32_t)spad; sa.nseg = nseg;
+            sa.tb = base[ti->source_type]; sa.nsl = nsl; sa.nb = nb; sa.spad = (uint32_t)spad; sa.nseg = nseg;
+            sa.lcap = g_lcap; sa.bsize_l = g_bsl; sa.nbl = g_nbl; sa.bsize_g = std::max(g_bsg, 1u);
             sa.sfirst = sfirst; sa.seg_row = k.seg_row; sa.seg_lo = seg_lo; sa.seg_hi = seg_hi; sa.boff = k.boff; sa.bsrc = nullptr; sa.error = d_scalars + 1;
             seg_fill_kernel<<<nblk(n), 256, 0, g_stream>>>(sa); LAUNCH_CHECK();
             seg_blk_count_kernel<<<nblk(nseg), 256, 0, g_stream>>>(sa); LAUNCH_CHECK();
@@ -2132,6 +2219,7 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
             dfree(sfirst); dfree(seg_lo); dfree(seg_hi); dfree(scr); dfree(flag); dfree(pos);
             k.arows.assign(nb, nullptr); k.aoff.assign(nb, nullptr); k.acount.assign(nb, 0);
             k.segmented = true; k.nseg = nseg; k.seg_len = env_seg_len; k.nhub = nhub; k.rpad = (uint32_t)spad;
+            k.lcap = g_lcap; k.nbl = g_nbl; k.bsize_g = g_bsg;
         } catch (...) {
             dfree(sfirst); dfree(seg_lo); dfree(seg_hi); dfree(scr); dfree(flag); dfree(pos);
             free_blocked(pe);
@@ -2208,19 +2296,93 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
     return true;
 }
 
-// stream-ordered barrier across the ranks: a collective completes on a rank only after every rank's stream has reached it
-static void stream_barrier() {
+// ---- barriers between the ranks --------------------------------------------------------------------------------------------------
+// stream-ordered barrier through NCCL: a collective completes on a rank only after every rank's stream has reached it (fallback)
+static void nccl_stream_barrier(cudaStream_t st) {
     static uint64_t* buf = nullptr;
     if (!buf) buf = dalloc<uint64_t>((size_t)g_nranks + 1);
-    NK(g_nccl.AllGather(buf + g_nranks, buf, 8, ncclUint8, g_comm, g_stream));
+    NK(g_nccl.AllGather(buf + g_nranks, buf, 8, ncclUint8, g_comm, st));
 }
-// (Re)maps the peers' state buffers of agent type t when any rank's layout changed (collective).  Returns false when the
+// flag barrier over peer memory (peer_barrier_kernel): set up once, collectively
+static struct PeerBarrier {
+    unsigned long long* mine = nullptr; PeerFlagPtrs peers{}; unsigned long long epoch = 0; bool tried = false, ok = false;
+} g_pb;
+static void peer_barrier_setup() {     // collective
+    if (g_pb.tried) return;
+    g_pb.tried = true;
+    static const bool enabled = !(getenv("VB_PEER_BARRIER") && atoi(getenv("VB_PEER_BARRIER")) == 0);
+    const uint32_t P = (uint32_t)g_nranks;
+    struct H { cudaIpcMemHandle_t h; uint64_t good; };
+    static_assert(sizeof(H) % 8 == 0, "exchanged in 8-byte units");
+    H mine{};
+    bool ok = enabled && P <= 16;
+    if (ok && cudaMalloc(&g_pb.mine, 64 * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); ok = false; g_pb.mine = nullptr; }
+    if (ok) {
+        CK(cudaMemsetAsync(g_pb.mine, 0, 64 * sizeof(unsigned long long), g_stream));
+        if (cudaIpcGetMemHandle(&mine.h, g_pb.mine) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    }
+    mine.good = ok ? 1 : 0;
+    uint8_t* dsend = (uint8_t*)g_pool.alloc(sizeof(H)); uint8_t* drecv = (uint8_t*)g_pool.alloc(sizeof(H) * P);
+    CK(cudaMemcpyAsync(dsend, &mine, sizeof(H), cudaMemcpyHostToDevice, g_stream));
+    NK(g_nccl.AllGather(dsend, drecv, sizeof(H), ncclUint8, g_comm, g_stream));      // also: every rank's flags are zero before anybody writes one
+    std::vector<H> all(P);
+    CK(cudaMemcpyAsync(all.data(), drecv, sizeof(H) * P, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    dfree(dsend); dfree(drecv);
+    for (uint32_t r = 0; r < P; ++r) ok &= all[r].good == 1;
+    for (uint32_t r = 0; r < P && ok; ++r) {
+        if ((int)r == g_rank) { g_pb.peers.p[r] = g_pb.mine; continue; }
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        g_pb.peers.p[r] = (unsigned long long*)q;
+    }
+    uint64_t good = ok ? 1 : 0;
+    std::vector<uint64_t> ag;
+    allgather8_host(&good, ag);
+    for (uint64_t v : ag) ok &= v != 0;
+    g_pb.ok = ok;
+}
+static void stream_barrier(cudaStream_t st) {
+    if (g_pb.ok) {
+        ++g_pb.epoch;
+        peer_barrier_kernel<<<1, 32, 0, st>>>(g_pb.mine, g_pb.peers, (uint32_t)g_rank, (uint32_t)g_nranks, g_pb.epoch); LAUNCH_CHECK();
+    } else nccl_stream_barrier(st);
+}
+// the stream the halo pushes and their barriers run on (high priority: a push kernel gets SM slots next to the sweeps)
+static cudaStream_t halo_stream() {
+    static cudaStream_t st = nullptr;
+    if (!st) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
+    }
+    return st;
+}
+
+// (Re)maps the peers' state buffers of agent type t when some rank's layout may have changed (collective).  Returns false when the
 // peer-memory path is not available (more than 16 ranks, IPC refused): the caller falls back to ncclSend/ncclRecv.
+// The check itself costs a host-synchronising all-gather, so it only runs when `peer_check` is set: after finish_init!, after an
+// apply! that can add agents or edges (births grow buffers, received edges grow ghost tables) and after host-side additions — the
+// same events on every rank.  A static network (the reference skips the exchange of unchanged agents the same way, src/MPI.jl:178-179)
+// never pays for it again.
 bool vb_sim::refresh_peer_map(int t) {
     AgentStore& a = A(t);
     static const bool enabled = !(getenv("VB_HALO_P2P") && atoi(getenv("VB_HALO_P2P")) == 0);
     const uint32_t P = (uint32_t)g_nranks;
     if (!enabled || P > 16) return false;
+    if (!a.peers.check && a.peers.sig != 0) {
+        // no collective event since the last exchange: the layout must be what the peers know (a buffer reallocated by a rank-local
+        // call in between would make them push into freed memory)
+        uint64_t sig0 = 1469598103934665603ull;
+        auto mix0 = [&](uint64_t v) { sig0 = (sig0 ^ v) * 1099511628211ull; };
+        mix0((uint64_t)(uintptr_t)a.state[0]); mix0((uint64_t)(uintptr_t)a.state[1]); mix0(a.stride()); mix0(a.cap); mix0(a.nghost);
+        for (uint32_t r = 0; r <= P; ++r) mix0(a.ghost_off[r]);
+        if (sig0 == 0) sig0 = 1;
+        if (sig0 != a.peers.sig) throw CudaError("multi-rank: the buffers of agent type " + a.name + " changed outside of a collective operation");
+        return a.peers.ok;
+    }
+    a.peers.check = false;
+    peer_barrier_setup();
     // layout signature of this rank: buffers, stride, ghost table
     uint64_t sig = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { sig = (sig ^ v) * 1099511628211ull; };
@@ -2233,8 +2395,8 @@ bool vb_sim::refresh_peer_map(int t) {
     bool any = false;
     for (uint64_t v : all) any |= v != 0;
     if (!any) return a.peers.ok;
-    // exchange {ipc handles of both buffers, stride, cap, ghost_off[]}
-    struct Desc { cudaIpcMemHandle_t h[2]; uint32_t same, stride, cap, pad; uint32_t ghost_off[17]; uint32_t pad2; };
+    // exchange {ipc handles of both buffers, stride, cap, ghost_off[], wanted halo phases}
+    struct Desc { cudaIpcMemHandle_t h[2]; uint32_t same, stride, cap, pad; uint32_t ghost_off[17]; uint32_t ng_want; };
     static_assert(sizeof(Desc) % 8 == 0, "descriptor is exchanged in 8-byte units");
     Desc mine{};
     bool ok = true;
@@ -2244,6 +2406,15 @@ bool vb_sim::refresh_peer_map(int t) {
     }
     mine.stride = a.stride(); mine.cap = a.cap; mine.pad = ok ? 1u : 0u;
     for (uint32_t r = 0; r <= P; ++r) mine.ghost_off[r] = a.ghost_off[r];
+    {   // halo phases = ghost blocks of the prefiltered sweeps: one per VB_KEY_BLOCK_MB of ghost keys; at least four when the ghosts
+        // outnumber the local agents (then the local sweep alone cannot hide the transfer).  VB_HALO_PHASES overrides.
+        static const double key_mb = getenv("VB_KEY_BLOCK_MB") ? atof(getenv("VB_KEY_BLOCK_MB")) : 52.0;
+        static const int env_phases = getenv("VB_HALO_PHASES") ? atoi(getenv("VB_HALO_PHASES")) : 0;
+        uint32_t want = (uint32_t)std::max<double>(1.0, std::ceil((double)a.nghost / std::max(1.0, key_mb * 1e6)));
+        if (a.nghost > (1u << 20) && (uint64_t)a.nghost > 2ull * std::max<uint32_t>(a.nslots, 1)) want = std::max(want, 4u);
+        if (env_phases > 0) want = (uint32_t)env_phases;
+        mine.ng_want = std::min(want, 16u);
+    }
     uint8_t* dsend = (uint8_t*)g_pool.alloc(sizeof(Desc)); uint8_t* drecv = (uint8_t*)g_pool.alloc(sizeof(Desc) * P);
     CK(cudaMemcpyAsync(dsend, &mine, sizeof(Desc), cudaMemcpyHostToDevice, g_stream));
     NK(g_nccl.AllGather(dsend, drecv, sizeof(Desc), ncclUint8, g_comm, g_stream));
@@ -2255,7 +2426,15 @@ bool vb_sim::refresh_peer_map(int t) {
     cudaGetLastError();
     a.peers.opened.clear();
     a.peers.base[0].assign(P, nullptr); a.peers.base[1].assign(P, nullptr); a.peers.stride.assign(P, 0); a.peers.ghost0.assign(P, 0);
-    for (uint32_t r = 0; r < P; ++r) ok &= descs[r].pad == 1u;
+    a.peers.gblock.assign(P, 1); a.peers.goff_me.assign(P, 0);
+    uint32_t ng = 1;
+    for (uint32_t r = 0; r < P; ++r) { ok &= descs[r].pad == 1u; ng = std::max(ng, descs[r].ng_want); }
+    a.peers.ng = ng;
+    for (uint32_t r = 0; r < P; ++r) {     // the same arithmetic on every rank: rank r's ghost blocks hold gblock[r] slots (a multiple of 64)
+        const uint32_t nghost_r = descs[r].ghost_off[P];
+        a.peers.gblock[r] = (std::max<uint32_t>((nghost_r + ng - 1) / ng, 1u) + 63u) & ~63u;
+        a.peers.goff_me[r] = descs[r].ghost_off[rank];
+    }
     for (uint32_t r = 0; r < P && ok; ++r) {
         if (r == rank) continue;
         for (int b = 0; b < 2; ++b) {
@@ -2274,31 +2453,53 @@ bool vb_sim::refresh_peer_map(int t) {
     for (uint64_t v : all) ok &= v != 0;
     a.peers.ok = ok;
     a.peers.sig = sig;
+    ++layout_epoch;        // ghost block sizes may have changed: blocked views over [local | ghost] slots are rebuilt
     return ok;
 }
 
+// transmit_agents! (src/MPI.jl:155-267) for agent type t.  Peer-memory path: the exchange runs on the halo stream in `ng` phases —
+//   barrier (no peer still reads last step's ghosts) -> for every ghost block j: pack + push in one kernel -> barrier (phase j has
+//   landed everywhere) -> event j —
+// and returns at once; halo_wait(t, j + 1) makes the main stream wait for phases 0..j.  The pushes read this rank's READ buffer, which
+// no kernel of the apply writes (states are double buffered; :Independent types are joined before the first kernel), so sweeps over
+// the local agents and over ghost blocks that have already arrived overlap with the blocks still on the wire.
 void vb_sim::halo_exchange(int t) {
     AgentStore& a = A(t);
+    a.halo_pending = 0; a.halo_waited = 0;
     if (g_nranks <= 1 || !a.halo_dirty) return;
     a.halo_dirty = false;
     if (!a.size || a.send_off.empty()) return;
     const uint32_t P = (uint32_t)g_nranks, ns = a.send_off[P];
     if (refresh_peer_map(t)) {
-        // peer-memory path: barrier (no peer still reads last step's ghosts) -> pack + push in one kernel -> barrier (all pushes landed)
-        stream_barrier();
-        if (ns) {
+        cudaStream_t hs = halo_stream();
+        static cudaEvent_t ev_begin = nullptr;
+        if (!ev_begin) CK(cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming));
+        const uint32_t ng = a.peers.ng;
+        while (a.ev_phase.size() < ng) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); a.ev_phase.push_back(e); }
+        CK(cudaEventRecord(ev_begin, g_stream));
+        CK(cudaStreamWaitEvent(hs, ev_begin, 0));
+        stream_barrier(hs);
+        for (uint32_t j = 0; j < ng; ++j) {
             HaloPushArgs h{};
-            h.cols = a.rstate(); h.stride = a.stride(); h.slots = a.send_slots; h.n = ns; h.word = a.word; h.ncols = a.ncols; h.npeers = P - 1;
+            h.cols = a.rstate(); h.stride = a.stride(); h.slots = a.send_slots; h.word = a.word; h.ncols = a.ncols; h.npeers = P - 1;
             for (uint32_t k = 0; k + 1 < P; ++k) {
                 const uint32_t r = (rank + 1 + k) % P;
-                h.voff[k + 1] = h.voff[k] + (a.send_off[r + 1] - a.send_off[r]);
-                h.first[k] = a.send_off[r];
-                h.remote[k] = a.peers.base[a.cur][r]; h.rstride[k] = a.peers.stride[r]; h.rghost0[k] = a.peers.ghost0[r];
+                // peer r's ghost block j = its ghost positions [j G, (j + 1) G); my agents sit at [go, go + len) of them
+                const uint64_t G = a.peers.gblock[r], go = a.peers.goff_me[r], len = a.send_off[r + 1] - a.send_off[r];
+                const uint64_t blo = (uint64_t)j * G, bhi = blo + G;
+                const uint64_t lo = blo > go ? std::min<uint64_t>(blo - go, len) : 0, hi = bhi > go ? std::min<uint64_t>(bhi - go, len) : 0;
+                h.voff[k + 1] = h.voff[k] + (uint32_t)(hi - lo);
+                h.first[k] = a.send_off[r] + (uint32_t)lo;
+                h.remote[k] = a.peers.base[a.cur][r]; h.rstride[k] = a.peers.stride[r]; h.rghost0[k] = a.peers.ghost0[r] + (uint32_t)lo;
             }
-            halo_push_kernel<<<nblk((uint64_t)ns * a.ncols), 256, 0, g_stream>>>(h); LAUNCH_CHECK();
+            h.n = h.voff[P - 1];
+            if (h.n) { halo_push_kernel<<<nblk((uint64_t)h.n * a.ncols), 256, 0, hs>>>(h); LAUNCH_CHECK(); }
+            stream_barrier(hs);
+            CK(cudaEventRecord(a.ev_phase[j], hs));
         }
-        stream_barrier();
+        a.halo_pending = ng;
         halo_bytes += (uint64_t)a.nghost * a.size;
+        (void)ns;
         return;
     }
     if (ns) { halo_pack_kernel<<<nblk((uint64_t)ns * a.ncols), 256, 0, g_stream>>>(a.rstate(), a.stride(), a.send_slots, ns, a.send_buf, a.word, a.ncols); LAUNCH_CHECK(); }
@@ -2313,6 +2514,14 @@ void vb_sim::halo_exchange(int t) {
     }
     NK(g_nccl.GroupEnd());
     halo_bytes += (uint64_t)a.nghost * a.size;
+}
+void vb_sim::halo_wait(int t, uint32_t phases) {
+    AgentStore& a = A(t);
+    phases = std::min(phases, a.halo_pending);
+    for (; a.halo_waited < phases; ++a.halo_waited) CK(cudaStreamWaitEvent(g_stream, a.ev_phase[a.halo_waited], 0));
+}
+void vb_sim::halo_wait_all() {
+    for (size_t t = 1; t <= agents.size(); ++t) if (agents[t - 1].halo_pending) halo_wait((int)t, agents[t - 1].halo_pending);
 }
 
 // rows of an implicit raster stencil, enumerated exactly like Ctx::stencil_row on the device
@@ -2543,6 +2752,11 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         const uint32_t n = a.nslots;
         if (n == 0) continue;
         s.st_agents_called += n;
+        // the halo of this apply may still be on the wire (halo stream): only the segmented prefiltered sweeps below start before it has
+        // landed (local blocks first, a ghost block when its phase is there); every other form waits here
+        const bool pipelined = ti->reduce && ti->prefilter && ti->n_edge_writes + ti->n_agent_writes + ti->n_edge_removes == 0 && call.size() == 1 &&
+                               !a.independent && with_edge < 0;
+        if (!pipelined) s.halo_wait_all();
         vb::LaunchArgs la{};
         la.ds = &s.h_ds; la.type = C; la.n = n; la.in_read = contains(read, C); la.in_write = contains(write, C);
         la.with_edge = with_edge; la.stats = s.d_stats; la.stream = g_stream;
@@ -2670,7 +2884,13 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 const bool pf = k.key != nullptr && s.prefilter_on(ti);
                 lb.blk_key = pf ? k.key : nullptr; lb.blk_nkeys = pf ? k.key_n : 0; lb.blk_prefilter = pf ? 1 : 0;
                 if (k.segmented) { lb.blk_seg_row = k.seg_row; lb.blk_nseg = k.nseg; lb.blk_heavy = nullptr; }
-                if (pf) { CK(ti->launch_keys(lb)); ++g_launches; }          // keys of this step's read states (inside the timed region)
+                if (!k.segmented) s.halo_wait_all();
+                else for (size_t t2 = 1; t2 <= s.agents.size(); ++t2) if ((int)t2 != ti->source_type) s.halo_wait((int)t2, s.agents[t2 - 1].halo_pending);
+                const uint32_t src_nsl = s.A(ti->source_type).cap + s.A(ti->source_type).nghost;
+                // keys of this step's read states (inside the timed region): the whole column at once, or block by block when the ghost
+                // blocks arrive in phases
+                g_trace.mark("sweeps begin");
+                if (pf && !k.segmented) { lb.blk_key_first = 0; CK(ti->launch_keys(lb)); ++g_launches; g_trace.mark("keys"); }
                 // sweeps over blocks that hold no entry (capacity beyond the agents in use) are skipped; the first sweep that runs
                 // initialises the accumulators, the last one runs finish()
                 std::vector<uint32_t> todo;
@@ -2693,11 +2913,24 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                     lb.blk_off = k.boff + (size_t)todo[i] * k.rpad; lb.blk_first = i == 0; lb.blk_last = i + 1 == todo.size();
                     lb.blk_rows = use_lists ? k.arows[todo[i]] : nullptr; lb.blk_roff = k.aoff[todo[i]]; lb.blk_nrows = k.acount[todo[i]];
                     lb.blk_base = todo[i] * k.bsize;
+                    if (k.segmented) {
+                        const uint32_t b = todo[i];
+                        if (b >= k.nbl) s.halo_wait(ti->source_type, b - k.nbl + 1);      // a ghost block: its phase of the halo must have landed
+                        lb.blk_base = k.block_first(b);
+                        lb.blk_key_first = lb.blk_base; lb.blk_nkeys = k.block_slots(b, s.A(ti->source_type).nslots, src_nsl);
+                        g_trace.mark("(wait for the halo phase of block " + std::to_string(b) + ")");
+                        CK(ti->launch_keys(lb)); ++g_launches;
+                        g_trace.mark("keys of block " + std::to_string(b) + ": " + std::to_string(lb.blk_nkeys) + " slots");
+                        lb.blk_nkeys = k.key_n;
+                    }
                     CK(ti->launch_blocked(lb)); ++g_launches;
+                    g_trace.mark("sweep of block " + std::to_string(todo[i]) + ": " + std::to_string(k.bstart[todo[i] + 1] - k.bstart[todo[i]]) + " entries");
                 }
+                s.halo_wait_all();
                 if (k.segmented && k.nhub) {       // rows cut into several segments: merge their parked accumulators, finish
                     lb.blk_op = 1; lb.blk_hub_rows = k.hub_rows; lb.blk_hub_seg = k.hub_seg; lb.blk_nhub = k.nhub;
                     CK(ti->launch_blocked(lb)); ++g_launches;
+                    g_trace.mark("hub rows: merge of " + std::to_string(k.nhub) + " rows");
                 }
                 swept = (uint32_t)todo.size();
                 if (heavy_n) CK(cudaStreamWaitEvent(g_stream, ev_join, 0));
@@ -2707,6 +2940,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 cudaGetLastError();
                 s.last_blocked_nb = swept; s.last_prefiltered = pf;
             } else {
+            s.halo_wait_all();
             s.last_blocked_nb = 0; s.last_prefiltered = false;
             s.upload_view(seed);
             // Gather-bound read phases (state array far larger than L2): keep the head of the gathered type's state resident in
@@ -2750,6 +2984,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         { float mk = 0; cudaEventElapsedTime(&mk, s.evk[0], s.evk[1]); s.ms_kernel += mk; }
         for (auto p : tmp) dfree(p);
     }
+    s.halo_wait_all();          // (a rank without agents of the called type launched nothing: join the halo stream before the buffers swap)
     CK(cudaEventRecord(s.ev[1], g_stream));
     g_trace.end("transition loop", tname);
     s.check_device_error("apply!");
@@ -2839,6 +3074,13 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     const unsigned long long er = 0;
     s.st_edges_read = er; s.st_edges_appended = appended; s.st_launches = g_launches - launches0;
     s.num_transitions += 1;
+    g_trace.flush_marks();
+    if (g_nranks > 1) {     // births grow buffers, received edges grow ghost tables: the peer maps are re-checked by the next halo (every rank
+                            // runs the same transition, so every rank decides the same)
+        bool writes = false;
+        for (auto* ti : tis) writes |= ti->n_agent_writes > 0 || ti->n_edge_writes > 0 || ti->n_edge_removes > 0;
+        if (writes) s.mark_peer_check();
+    }
 }
 
 }  // namespace
@@ -2989,6 +3231,7 @@ int vb_sim_copy(const vb_sim* src, vb_sim** out) {   // copy_simulation: Simulat
         for (auto& a : o.agents) {
             AgentStore b = a;
             b.peers = AgentStore::PeerMap{};      // the copy maps its peers on its first halo exchange
+            b.ev_phase.clear(); b.halo_pending = 0; b.halo_waited = 0;
             if (a.size && a.cap) { b.state[0] = (uint8_t*)dup(a.state[0], (size_t)a.stride() * a.size); b.state[1] = a.independent ? b.state[0] : (uint8_t*)dup(a.state[1], (size_t)a.stride() * a.size); }
             if (!a.immortal && a.cap) { b.died[0] = (uint8_t*)dup(a.died[0], a.stride()); b.died[1] = (uint8_t*)dup(a.died[1], a.stride()); b.reuse = (uint32_t*)dup(a.reuse, (size_t)a.reuse_cap * 4); }
             // the ghost table and the per-peer send lists of a multi-rank simulation are owned per simulation, whatever the type's hints
@@ -3089,6 +3332,7 @@ int vb_add_agent_per_process(vb_sim* s, int type, const void* state, vb_agent_id
         }
         if (!a.immortal) { CK(cudaMemsetAsync(a.died[0] + slot, 0, 1, g_stream)); CK(cudaMemsetAsync(a.died[1] + slot, 0, 1, g_stream)); }
         a.halo_dirty = true;
+        s->mark_peer_check();            // collective by contract (one agent on every rank): the buffers may have grown
         a.last_change = s->num_transitions;
         if (id_out) *id_out = vb::agent_id((uint32_t)type, s->rank, (uint64_t)slot + 1);
     });
@@ -3361,6 +3605,7 @@ int vb_finish_init(vb_sim* s) {
             if (!a.immortal && a.cap) CK(cudaMemsetAsync(a.rdied(), 0, a.stride(), g_stream));
         }
         s->initialized = true;
+        s->mark_peer_check();
         s->build_ghosts();
         s->merge_all_pending();
         for (auto& e : s->edges) {   // every container exists after init, even if empty
