@@ -10,6 +10,6 @@ OUT=gpurun_out/r2_mgpu_tests_${N}gpu.txt
   echo "# $(nvidia-smi -L | wc -l) GPUs visible; $(date -u +%FT%TZ)"
   timeout 1500 python -m pytest tests/test_multigpu.py tests/test_zzz_mgpu_next.py -m gpu -v -rs --tb=short 2>&1 | grep -v "^W1\|^\*\*\*\|OMP_NUM" | tail -n 150
   echo "# sharded HK, prefiltered sweeps forced on the parity graph (VB_BLOCK_EAGER=1 VB_BLOCK_MIN_MB=0 VB_KEY_BLOCK_MB=0.05)"
-  MGPU_EXPECT_PREFILTER=1 VB_BLOCK_EAGER=1 VB_BLOCK_MIN_MB=0 VB_KEY_BLOCK_MB=0.05 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $((N<4?N:4)) --master-addr 127.0.0.1 --master-port 29529 tests/mgpu_hk.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -n 30
+  MGPU_EXPECT_PREFILTER=1 VB_BLOCK_EAGER=1 VB_BLOCK_MIN_MB=0 VB_KEY_BLOCK_MB=0.05 VB_HALO_PHASES=3 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $((N<4?N:4)) --master-addr 127.0.0.1 --master-port 29529 tests/mgpu_hk.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -n 30
 } > $OUT 2>&1
 cat $OUT

@@ -99,4 +99,4 @@ def test_hk_sharded_prefiltered_sweeps_vs_oracle(cuda):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     from mgpu_common import run_ranks
-    run_ranks("mgpu_hk.py", 29529, env={"MGPU_EXPECT_PREFILTER": "1", "VB_BLOCK_EAGER": "1", "VB_BLOCK_MIN_MB": "0", "VB_KEY_BLOCK_MB": "0.05"})
+    run_ranks("mgpu_hk.py", 29529, env={"MGPU_EXPECT_PREFILTER": "1", "VB_BLOCK_EAGER": "1", "VB_BLOCK_MIN_MB": "0", "VB_KEY_BLOCK_MB": "0.05", "VB_HALO_PHASES": "3"})

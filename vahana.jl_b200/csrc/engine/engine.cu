@@ -106,26 +106,42 @@ struct Trace {
     }
     // VB_TRACE=2: device times between marks on the main stream (CUDA events), printed by flush_marks() after a synchronize
     bool marks_on = getenv("VB_TRACE") != nullptr && atoi(getenv("VB_TRACE")) >= 2;
-    std::vector<std::pair<std::string, cudaEvent_t>> marks;
-    void mark(const std::string& what) {
+    std::vector<std::pair<std::string, cudaEvent_t>> marks, side_marks;
+    void mark(const std::string& what, cudaStream_t side = nullptr) {
         if (!marks_on) return;
         cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return;
-        cudaEventRecord(e, g_stream);
-        marks.emplace_back(what, e);
+        cudaEventRecord(e, side ? side : g_stream);
+        (side ? side_marks : marks).emplace_back(what, e);
     }
     void flush_marks() {
         if (!marks_on || marks.empty()) return;
-        cudaStreamSynchronize(g_stream);
+        cudaDeviceSynchronize();
         for (size_t i = 1; i < marks.size(); ++i) {
             float ms = 0; cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
             fprintf(stderr, "[vb mark ] %-54s %9.3f ms\n", marks[i].first.c_str(), ms);
         }
+        for (size_t i = 0; i < side_marks.size(); ++i) {    // halo stream: since the previous mark there, and since the first mark of the main stream
+            float ms = 0, at = 0;
+            if (i) cudaEventElapsedTime(&ms, side_marks[i - 1].second, side_marks[i].second);
+            cudaEventElapsedTime(&at, marks[0].second, side_marks[i].second);
+            fprintf(stderr, "[vb halo ] %-54s %9.3f ms   (at %8.3f ms)\n", side_marks[i].first.c_str(), ms, at);
+        }
+        { float at = 0; cudaEventElapsedTime(&at, marks[0].second, marks.back().second); fprintf(stderr, "[vb mark ] %-54s             (at %8.3f ms)\n", "last mark of the main stream", at); }
         for (auto& m : marks) cudaEventDestroy(m.second);
-        marks.clear();
+        for (auto& m : side_marks) cudaEventDestroy(m.second);
+        marks.clear(); side_marks.clear();
     }
 };
 Trace g_trace;
 
+// persisting-L2 set-aside: only touched when the wanted size changes (cudaDeviceSetLimit synchronises the device)
+void set_persisting_l2_mb(int mb) {
+    static int current = -1;
+    if (current == mb) return;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)mb << 20);
+    cudaGetLastError();
+    current = mb;
+}
 void require_device() {
     if (g_device < 0) throw CudaError("vahana_b200: vb_init() has not been called or no CUDA device is available (no CPU fallback)");
 }
@@ -559,6 +575,22 @@ __global__ void peer_barrier_kernel(unsigned long long* mine, const PeerFlagPtrs
     __syncwarp();
     __threadfence_system();
 }
+// the same selection (one phase's sub-range of every peer's list), packed into the send buffer at the list positions: the copy engines
+// then move every peer's part over NVLink without occupying an SM (halo_exchange)
+__global__ void halo_pack_ranges_kernel(const HaloPushArgs a, uint8_t* __restrict__ out, uint32_t ns) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)a.n * a.ncols) return;
+    const uint32_t v = (uint32_t)(t % a.n), c = (uint32_t)(t / a.n);
+    uint32_t k = 0;
+    while (k + 1 < a.npeers && v >= a.voff[k + 1]) ++k;
+    const uint32_t i = a.first[k] + (v - a.voff[k]);
+    const uint8_t* sp = a.cols + (size_t)c * a.stride * a.word + (size_t)a.slots[i] * a.word;
+    uint8_t* dp = out + ((size_t)c * ns + i) * a.word;
+    if (a.word == 8) *reinterpret_cast<uint64_t*>(dp) = *reinterpret_cast<const uint64_t*>(sp);
+    else if (a.word == 4) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
+    else if (a.word == 16) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
+    else for (uint32_t b = 0; b < a.word; ++b) dp[b] = sp[b];
+}
 // died-agent ids of the other ranks (C7: join(aids), src/AgentMethods.jl:338): mark the ghosts that mirror them
 struct MarkDeadArgs {
     const uint64_t* ids; uint32_t n; uint8_t* dead; uint32_t rank; uint32_t ntypes;
@@ -657,13 +689,26 @@ __global__ void blk_fill_kernel(const BlkBuildArgs a) {
 struct SegBuildArgs {
     const uint32_t* off; const uint32_t* src; uint32_t row0, n, rows, seg_len;
     uint32_t tb, nsl, nb, spad, nseg;
-    // blocks of the source type's slots: nbl blocks of bsize_l slots over the local slots [0, lcap), then blocks of bsize_g over the ghosts
-    uint32_t lcap, bsize_l, nbl, bsize_g;
+    // blocks of the source type's slots: nbl blocks of bsize_l slots over the local slots [0, lcap); behind them ng ghost blocks, block
+    // nbl + j = the j-th part (gpart[p] slots) of every owner p's range [goff[p], goff[p + 1]) of the ghost segment.  Entries of a
+    // ghost block are stored relative to lcap.
+    // The ghost blocks start at block gfirst: nbl (behind the local blocks) or nbl - 1 (the first ghost part shares the last local
+    // block: one sweep less).  absolute != 0: entries hold the slot itself (all slots < 2^27), which is what lets a block mix ranges.
+    uint32_t lcap, bsize_l, nbl, ng, nowners, gfirst, absolute;
+    uint32_t goff[17], gpart[16];
     const uint32_t* sfirst;          // [n + 1] first segment of every called row
     __device__ __forceinline__ uint32_t block_of(uint32_t s, uint32_t& first) const {
         uint32_t b;
         if (s < lcap) { b = s / bsize_l; if (b >= nbl) b = nbl - 1; first = b * bsize_l; }
-        else { b = (s - lcap) / bsize_g; if (nbl + b >= nb) b = nb - nbl - 1; first = lcap + b * bsize_g; b += nbl; }
+        else {
+            const uint32_t g = s - lcap;
+            uint32_t p = 0;
+            while (p + 1 < nowners && g >= goff[p + 1]) ++p;
+            b = (g - goff[p]) / gpart[p];
+            if (b >= ng) b = ng - 1;
+            b += gfirst; first = lcap;
+        }
+        if (absolute) first = 0;
         return b;
     }
     uint32_t* seg_row; uint32_t* seg_lo; uint32_t* seg_hi;
@@ -937,12 +982,13 @@ struct AgentStore {
         uint64_t sig = 0;                     // layout signature the map was exchanged for (0 = never)
         bool ok = false;
         bool check = true;                    // some rank's layout may have changed since the exchange: the next halo re-checks (collective)
-        // the halo travels in `ng` phases, one per ghost block (the same count on every rank; a rank's ghost block holds gblock[rank]
-        // slots): phase j carries the states a peer mirrors in ITS ghost block j, so that the sweep over block j can start while the
-        // later blocks are still on the wire
+        // the halo travels in `ng` phases (the same count on every rank): phase j carries the j-th part of every owner's range of a
+        // receiver's ghost segment (ghost_part() slots of it), so every rank sends in every phase; the receiver's ghost key block j is
+        // the union of those parts and can be swept while the later phases are still on the wire
         uint32_t ng = 1;
-        std::vector<uint32_t> gblock, goff_me; // [nranks] peer r's ghost block size; position of MY agents' range in peer r's ghost segment
     } peers;
+    // slots per phase of a range of `len` ghosts travelling in `ng` phases (the same arithmetic on the sender and on the receiver)
+    static uint32_t ghost_part(uint32_t len, uint32_t ng) { return (std::max<uint32_t>((len + ng - 1) / ng, 1u) + 63u) & ~63u; }
     std::vector<cudaEvent_t> ev_phase;        // recorded on the halo stream after phase j has landed everywhere
     uint32_t halo_pending = 0, halo_waited = 0;   // phases started by this apply / already awaited by the main stream
     uint8_t* send_buf = nullptr;              // packed states for the halo exchange
@@ -998,13 +1044,16 @@ struct EdgeStore {
         // segmented form (prefiltered sweeps): boff / acc are indexed by segment, rpad = padded segment count
         bool segmented = false;
         uint32_t nseg = 0, seg_len = 0, nhub = 0;
-        uint32_t lcap = 0, nbl = 0, bsize_g = 0;     // blocks: nbl of bsize slots over the local slots [0, lcap), the others of bsize_g over the ghosts
-        uint32_t block_first(uint32_t b) const { return b < nbl ? b * bsize : lcap + (b - nbl) * bsize_g; }
-        // slots of block b that can hold a source: the last block of a range takes its tail; local slots end at `used` (slots in use)
-        uint32_t block_slots(uint32_t b, uint32_t used, uint32_t nsl) const {
-            const uint32_t f = block_first(b), sz = b < nbl ? bsize : bsize_g;
-            const uint32_t lend = std::min(lcap, used);
-            const uint32_t lim = b < nbl ? (b + 1 == nbl ? lend : std::min(lend, f + sz)) : (b + 1 == nb ? nsl : std::min(nsl, f + sz));
+        // blocks: nbl of bsize slots over the local slots [0, lcap); then ng ghost blocks, block nbl + j = the j-th part of every owner's
+        // range of the ghost segment (goff = the ghost table's ranges the view was built for); entries of ghost blocks are relative to lcap
+        uint32_t lcap = 0, nbl = 0, ng = 0, gfirst = 0;   // ghost part j lives in block gfirst + j (gfirst = nbl - 1: it shares the last local block)
+        bool absolute = false;                             // entries hold the slot itself, not the slot relative to the block
+        std::vector<uint32_t> goff;
+        uint32_t block_first(uint32_t b) const { return absolute ? 0u : (b < nbl ? b * bsize : lcap); }
+        // local block b: the slots that can hold a source (the last local block takes the tail up to `used`, the slots in use)
+        uint32_t local_block_slots(uint32_t b, uint32_t used) const {
+            const uint32_t f = b * bsize, lend = std::min(lcap, used);
+            const uint32_t lim = b + 1 == nbl ? lend : std::min(lend, f + bsize);
             return lim > f ? lim - f : 0u;
         }
         uint32_t* seg_row = nullptr;                  // [nseg] called row | 0x80000000 when the row has several segments
@@ -2128,7 +2177,8 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
     static const bool env_seg = !(getenv("VB_PF_SEG") && atoi(getenv("VB_PF_SEG")) == 0);
     static const uint32_t env_seg_len = getenv("VB_SEG_LEN") ? (uint32_t)std::min(65535, std::max(32, atoi(getenv("VB_SEG_LEN")))) : 2048u;
     bool seg = pf && env_seg;
-    uint32_t g_lcap = 0, g_nbl = 0, g_bsl = 0, g_bsg = 0;
+    uint32_t g_lcap = 0, g_nbl = 0, g_bsl = 0, g_ng = 0, g_gfirst = 0;
+    bool g_abs = false;
     if (seg) {
         // blocks of keys: the local slots in as few even blocks as the key budget allows; the ghosts in the blocks the halo travels in
         // (AgentStore::PeerMap: the same count on every rank), so that a ghost block can be swept as soon as its phase has landed
@@ -2137,17 +2187,25 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
         const uint32_t used = std::max<uint32_t>(1u, std::min<uint32_t>(g_lcap, std::max<uint32_t>(src.nslots, 1u)));   // capacity beyond the slots in use holds no source
         g_nbl = (uint32_t)std::max<double>(1.0, std::ceil((double)used / key_slots));
         g_bsl = (((used + g_nbl - 1) / g_nbl) + 63u) & ~63u;
-        uint32_t ngb = 0;
-        if (src.nghost) {
-            if (src.peers.ok && !src.peers.gblock.empty()) { ngb = src.peers.ng; g_bsg = src.peers.gblock[rank]; }
-            else { ngb = (uint32_t)std::max<double>(1.0, std::ceil((double)src.nghost / key_slots)); g_bsg = (((src.nghost + ngb - 1) / ngb) + 63u) & ~63u; }
+        if (src.nghost) g_ng = src.peers.ok ? src.peers.ng : (uint32_t)std::min<double>(16.0, std::max<double>(1.0, std::ceil((double)src.nghost / key_slots)));
+        g_abs = nsl <= (1u << 27);
+        g_gfirst = g_nbl;
+        if (g_ng && g_abs) {
+            // the first ghost part joins the last local block when both fit one key block (VB_KEY_BLOCK_MAX_MB, 60 MB of keys: still
+            // inside the L2 set-aside): every block less is one pass less over the rows' offsets, states and parked accumulators
+            static const double env_key_max_mb = getenv("VB_KEY_BLOCK_MAX_MB") ? atof(getenv("VB_KEY_BLOCK_MAX_MB")) : 60.0;
+            const double last_local = (double)used - (double)(g_nbl - 1) * g_bsl;
+            double part0 = 0;
+            for (size_t p2 = 0; p2 + 1 < src.ghost_off.size(); ++p2) part0 += std::min<double>(AgentStore::ghost_part(src.ghost_off[p2 + 1] - src.ghost_off[p2], g_ng), src.ghost_off[p2 + 1] - src.ghost_off[p2]);
+            if (last_local + part0 <= std::max(key_slots, env_key_max_mb * 1e6 * (key_slots / (env_key_block_mb * 1e6)))) g_gfirst = g_nbl - 1;
         }
-        if (g_nbl + ngb > 64 || g_bsl > (1u << 27) || g_bsg > (1u << 27)) seg = false;      // (the row-based view below takes over)
-        else { nb = g_nbl + ngb; bsize = g_bsl; }
+        if (g_gfirst + g_ng > 64 || g_bsl > (1u << 27) || src.nghost > (1u << 27) || g_ng > 16 || (src.nghost && src.ghost_off.size() > 17))
+            seg = false;                                                  // (the row-based view below takes over)
+        else { nb = g_gfirst + g_ng; bsize = g_bsl; }
     }
     if (k.boff && k.version == pe.version && k.epoch == layout_epoch && k.called == C && k.source == ti->source_type && k.n == n &&
         k.acc_bytes == ti->acc_bytes && k.bsize == bsize && k.heavy_min == heavy_min && (k.key != nullptr) == pf && k.segmented == seg &&
-        (!seg || (k.nb == nb && k.lcap == g_lcap && k.nbl == g_nbl && k.bsize_g == g_bsg)))
+        (!seg || (k.nb == nb && k.lcap == g_lcap && k.nbl == g_nbl && k.ng == g_ng && k.gfirst == g_gfirst && k.absolute == g_abs && (!g_ng || k.goff == src.ghost_off))))
         return true;
     if (k.seen_version != pe.version) { k.seen_version = pe.version; k.seen = 1; k.refused = false; }
     else if (k.seen < 0xffffffffu) ++k.seen;
@@ -2184,7 +2242,12 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
             SegBuildArgs sa{};
             sa.off = pe.off; sa.src = pe.src; sa.row0 = row0; sa.n = n; sa.rows = pe.rows; sa.seg_len = env_seg_len;
             sa.tb = base[ti->source_type]; sa.nsl = nsl; sa.nb = nb; sa.spad = (uint32_t)spad; sa.nseg = nseg;
-            sa.lcap = g_lcap; sa.bsize_l = g_bsl; sa.nbl = g_nbl; sa.bsize_g = std::max(g_bsg, 1u);
+            sa.lcap = g_lcap; sa.bsize_l = g_bsl; sa.nbl = g_nbl; sa.ng = g_ng; sa.nowners = g_ng ? (uint32_t)src.ghost_off.size() - 1 : 0;
+            sa.gfirst = g_gfirst; sa.absolute = g_abs ? 1u : 0u;
+            for (uint32_t p2 = 0; p2 < sa.nowners; ++p2) {
+                sa.goff[p2] = src.ghost_off[p2]; sa.goff[p2 + 1] = src.ghost_off[p2 + 1];
+                sa.gpart[p2] = AgentStore::ghost_part(src.ghost_off[p2 + 1] - src.ghost_off[p2], g_ng);
+            }
             sa.sfirst = sfirst; sa.seg_row = k.seg_row; sa.seg_lo = seg_lo; sa.seg_hi = seg_hi; sa.boff = k.boff; sa.bsrc = nullptr; sa.error = d_scalars + 1;
             seg_fill_kernel<<<nblk(n), 256, 0, g_stream>>>(sa); LAUNCH_CHECK();
             seg_blk_count_kernel<<<nblk(nseg), 256, 0, g_stream>>>(sa); LAUNCH_CHECK();
@@ -2219,7 +2282,8 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
             dfree(sfirst); dfree(seg_lo); dfree(seg_hi); dfree(scr); dfree(flag); dfree(pos);
             k.arows.assign(nb, nullptr); k.aoff.assign(nb, nullptr); k.acount.assign(nb, 0);
             k.segmented = true; k.nseg = nseg; k.seg_len = env_seg_len; k.nhub = nhub; k.rpad = (uint32_t)spad;
-            k.lcap = g_lcap; k.nbl = g_nbl; k.bsize_g = g_bsg;
+            k.lcap = g_lcap; k.nbl = g_nbl; k.ng = g_ng; k.goff = g_ng ? src.ghost_off : std::vector<uint32_t>();
+            k.gfirst = g_gfirst; k.absolute = g_abs;
         } catch (...) {
             dfree(sfirst); dfree(seg_lo); dfree(seg_hi); dfree(scr); dfree(flag); dfree(pos);
             free_blocked(pe);
@@ -2406,12 +2470,11 @@ bool vb_sim::refresh_peer_map(int t) {
     }
     mine.stride = a.stride(); mine.cap = a.cap; mine.pad = ok ? 1u : 0u;
     for (uint32_t r = 0; r <= P; ++r) mine.ghost_off[r] = a.ghost_off[r];
-    {   // halo phases = ghost blocks of the prefiltered sweeps: one per VB_KEY_BLOCK_MB of ghost keys; at least four when the ghosts
-        // outnumber the local agents (then the local sweep alone cannot hide the transfer).  VB_HALO_PHASES overrides.
+    {   // halo phases = ghost blocks of the prefiltered sweeps: one per VB_KEY_BLOCK_MB of ghost keys (every further block costs a pass
+        // over the rows' offsets, states and parked accumulators).  VB_HALO_PHASES overrides.
         static const double key_mb = getenv("VB_KEY_BLOCK_MB") ? atof(getenv("VB_KEY_BLOCK_MB")) : 52.0;
         static const int env_phases = getenv("VB_HALO_PHASES") ? atoi(getenv("VB_HALO_PHASES")) : 0;
         uint32_t want = (uint32_t)std::max<double>(1.0, std::ceil((double)a.nghost / std::max(1.0, key_mb * 1e6)));
-        if (a.nghost > (1u << 20) && (uint64_t)a.nghost > 2ull * std::max<uint32_t>(a.nslots, 1)) want = std::max(want, 4u);
         if (env_phases > 0) want = (uint32_t)env_phases;
         mine.ng_want = std::min(want, 16u);
     }
@@ -2426,15 +2489,9 @@ bool vb_sim::refresh_peer_map(int t) {
     cudaGetLastError();
     a.peers.opened.clear();
     a.peers.base[0].assign(P, nullptr); a.peers.base[1].assign(P, nullptr); a.peers.stride.assign(P, 0); a.peers.ghost0.assign(P, 0);
-    a.peers.gblock.assign(P, 1); a.peers.goff_me.assign(P, 0);
     uint32_t ng = 1;
     for (uint32_t r = 0; r < P; ++r) { ok &= descs[r].pad == 1u; ng = std::max(ng, descs[r].ng_want); }
     a.peers.ng = ng;
-    for (uint32_t r = 0; r < P; ++r) {     // the same arithmetic on every rank: rank r's ghost blocks hold gblock[r] slots (a multiple of 64)
-        const uint32_t nghost_r = descs[r].ghost_off[P];
-        a.peers.gblock[r] = (std::max<uint32_t>((nghost_r + ng - 1) / ng, 1u) + 63u) & ~63u;
-        a.peers.goff_me[r] = descs[r].ghost_off[rank];
-    }
     for (uint32_t r = 0; r < P && ok; ++r) {
         if (r == rank) continue;
         for (int b = 0; b < 2; ++b) {
@@ -2476,25 +2533,45 @@ void vb_sim::halo_exchange(int t) {
         if (!ev_begin) CK(cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming));
         const uint32_t ng = a.peers.ng;
         while (a.ev_phase.size() < ng) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); a.ev_phase.push_back(e); }
+        g_trace.mark("halo exchange of " + a.name + " starts");
         CK(cudaEventRecord(ev_begin, g_stream));
         CK(cudaStreamWaitEvent(hs, ev_begin, 0));
+        g_trace.mark("begin", hs);
         stream_barrier(hs);
+        g_trace.mark("barrier: every rank is here", hs);
         for (uint32_t j = 0; j < ng; ++j) {
             HaloPushArgs h{};
             h.cols = a.rstate(); h.stride = a.stride(); h.slots = a.send_slots; h.word = a.word; h.ncols = a.ncols; h.npeers = P - 1;
             for (uint32_t k = 0; k + 1 < P; ++k) {
                 const uint32_t r = (rank + 1 + k) % P;
-                // peer r's ghost block j = its ghost positions [j G, (j + 1) G); my agents sit at [go, go + len) of them
-                const uint64_t G = a.peers.gblock[r], go = a.peers.goff_me[r], len = a.send_off[r + 1] - a.send_off[r];
-                const uint64_t blo = (uint64_t)j * G, bhi = blo + G;
-                const uint64_t lo = blo > go ? std::min<uint64_t>(blo - go, len) : 0, hi = bhi > go ? std::min<uint64_t>(bhi - go, len) : 0;
+                // the j-th part of the range peer r mirrors of my agents (the part belongs to its ghost key block j)
+                const uint64_t len = a.send_off[r + 1] - a.send_off[r], part = AgentStore::ghost_part((uint32_t)len, ng);
+                const uint64_t lo = std::min<uint64_t>((uint64_t)j * part, len), hi = std::min<uint64_t>((uint64_t)(j + 1) * part, len);
                 h.voff[k + 1] = h.voff[k] + (uint32_t)(hi - lo);
                 h.first[k] = a.send_off[r] + (uint32_t)lo;
                 h.remote[k] = a.peers.base[a.cur][r]; h.rstride[k] = a.peers.stride[r]; h.rghost0[k] = a.peers.ghost0[r] + (uint32_t)lo;
             }
             h.n = h.voff[P - 1];
-            if (h.n) { halo_push_kernel<<<nblk((uint64_t)h.n * a.ncols), 256, 0, hs>>>(h); LAUNCH_CHECK(); }
+            // VB_HALO_CE=1 (default): pack this phase's parts into the send buffer, then one peer copy per peer and column on the copy
+            // engines — the transfer occupies no SM, so the sweeps that run beside it keep the whole device (with the push kernel a
+            // local sweep ran at a third of its rate while a phase was on the wire, profiles/r2_scaling.md).  0: one kernel packs and pushes.
+            static const int env_ce = getenv("VB_HALO_CE") ? atoi(getenv("VB_HALO_CE")) : -1;
+            // default: the first phase by the push kernel (nothing runs beside it: the first sweep waits for it; 560 GB/s against 430 GB/s
+            // of the copy engines on 4 B200), the later phases, which overlap with sweeps, by the copy engines
+            const bool use_ce = env_ce >= 0 ? env_ce != 0 : j > 0;
+            if (h.n && use_ce && a.send_buf) {
+                halo_pack_ranges_kernel<<<nblk((uint64_t)h.n * a.ncols), 256, 0, hs>>>(h, a.send_buf, ns); LAUNCH_CHECK();
+                for (uint32_t k = 0; k + 1 < P; ++k) {
+                    const uint32_t cnt = h.voff[k + 1] - h.voff[k];
+                    if (!cnt) continue;
+                    for (uint32_t c = 0; c < a.ncols; ++c)
+                        CK(cudaMemcpyAsync(h.remote[k] + ((size_t)c * h.rstride[k] + h.rghost0[k]) * a.word, a.send_buf + ((size_t)c * ns + h.first[k]) * a.word,
+                                           (size_t)cnt * a.word, cudaMemcpyDeviceToDevice, hs));
+                }
+            } else if (h.n) { halo_push_kernel<<<nblk((uint64_t)h.n * a.ncols), 256, 0, hs>>>(h); LAUNCH_CHECK(); }
+            g_trace.mark("push of phase " + std::to_string(j) + ": " + std::to_string((uint64_t)h.n * a.size) + " B", hs);
             stream_barrier(hs);
+            g_trace.mark("barrier: phase landed everywhere", hs);
             CK(cudaEventRecord(a.ev_phase[j], hs));
         }
         a.halo_pending = ng;
@@ -2754,7 +2831,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         s.st_agents_called += n;
         // the halo of this apply may still be on the wire (halo stream): only the segmented prefiltered sweeps below start before it has
         // landed (local blocks first, a ghost block when its phase is there); every other form waits here
-        const bool pipelined = ti->reduce && ti->prefilter && ti->n_edge_writes + ti->n_agent_writes + ti->n_edge_removes == 0 && call.size() == 1 &&
+        static const bool env_overlap = !(getenv("VB_HALO_OVERLAP") && atoi(getenv("VB_HALO_OVERLAP")) == 0);
+        const bool pipelined = env_overlap && ti->reduce && ti->prefilter && ti->n_edge_writes + ti->n_agent_writes + ti->n_edge_removes == 0 && call.size() == 1 &&
                                !a.independent && with_edge < 0;
         if (!pipelined) s.halo_wait_all();
         vb::LaunchArgs la{};
@@ -2875,8 +2953,10 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 uint32_t swept = 0;
                 static const bool use_lists = !(getenv("VB_BLOCK_LISTS") && atoi(getenv("VB_BLOCK_LISTS")) == 0);
                 static const int l2_mb = getenv("VB_BLOCK_L2_MB") ? atoi(getenv("VB_BLOCK_L2_MB")) : 64;
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)l2_mb << 20);   // room for the evict_last source block
-                cudaGetLastError();
+                g_trace.mark("blocked read phase: host reaches the launch sequence");
+                {   // room for the evict_last source block (set once: the call synchronises the device, which would serialise the halo stream)
+                    set_persisting_l2_mb(l2_mb);
+                }
                 s.upload_view(seed);
                 CK(cudaEventRecord(s.evk[0], g_stream));
                 vb::LaunchArgs lb = la;
@@ -2886,7 +2966,6 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                 if (k.segmented) { lb.blk_seg_row = k.seg_row; lb.blk_nseg = k.nseg; lb.blk_heavy = nullptr; }
                 if (!k.segmented) s.halo_wait_all();
                 else for (size_t t2 = 1; t2 <= s.agents.size(); ++t2) if ((int)t2 != ti->source_type) s.halo_wait((int)t2, s.agents[t2 - 1].halo_pending);
-                const uint32_t src_nsl = s.A(ti->source_type).cap + s.A(ti->source_type).nghost;
                 // keys of this step's read states (inside the timed region): the whole column at once, or block by block when the ghost
                 // blocks arrive in phases
                 g_trace.mark("sweeps begin");
@@ -2915,12 +2994,24 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                     lb.blk_base = todo[i] * k.bsize;
                     if (k.segmented) {
                         const uint32_t b = todo[i];
-                        if (b >= k.nbl) s.halo_wait(ti->source_type, b - k.nbl + 1);      // a ghost block: its phase of the halo must have landed
+                        if (k.ng && b >= k.gfirst) s.halo_wait(ti->source_type, b - k.gfirst + 1);      // a block with a ghost part: its phase of the halo must have landed
                         lb.blk_base = k.block_first(b);
-                        lb.blk_key_first = lb.blk_base; lb.blk_nkeys = k.block_slots(b, s.A(ti->source_type).nslots, src_nsl);
                         g_trace.mark("(wait for the halo phase of block " + std::to_string(b) + ")");
-                        CK(ti->launch_keys(lb)); ++g_launches;
-                        g_trace.mark("keys of block " + std::to_string(b) + ": " + std::to_string(lb.blk_nkeys) + " slots");
+                        if (b < k.nbl) {
+                            lb.blk_key_first = b * k.bsize; lb.blk_nkeys = k.local_block_slots(b, s.A(ti->source_type).nslots);
+                            CK(ti->launch_keys(lb)); ++g_launches;
+                        }
+                        if (k.ng && b >= k.gfirst) {                         // the part of every owner's range that belongs to this block
+                            const uint32_t j = b - k.gfirst;
+                            for (size_t p2 = 0; p2 + 1 < k.goff.size(); ++p2) {
+                                const uint32_t len = k.goff[p2 + 1] - k.goff[p2], part = AgentStore::ghost_part(len, k.ng);
+                                const uint32_t lo = std::min<uint64_t>((uint64_t)j * part, len), hi = std::min<uint64_t>((uint64_t)(j + 1) * part, len);
+                                if (hi == lo) continue;
+                                lb.blk_key_first = k.lcap + k.goff[p2] + lo; lb.blk_nkeys = hi - lo;
+                                CK(ti->launch_keys(lb)); ++g_launches;
+                            }
+                        }
+                        g_trace.mark("keys of block " + std::to_string(b));
                         lb.blk_nkeys = k.key_n;
                     }
                     CK(ti->launch_blocked(lb)); ++g_launches;
@@ -2952,7 +3043,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             const int persist_mb = persist_env >= 0 ? persist_env : (ti->cooperative && ti->primary_edge >= 0 && state_bytes > ((size_t)256 << 20) ? 48 : 0);
             bool persisting = false;
             if (persist_mb > 0 && a.size) {
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_mb << 20);
+                set_persisting_l2_mb(persist_mb);
                 cudaStreamAttrValue av{};
                 av.accessPolicyWindow.base_ptr = a.rstate();
                 av.accessPolicyWindow.num_bytes = std::min<size_t>(state_bytes, (size_t)persist_mb << 20);
