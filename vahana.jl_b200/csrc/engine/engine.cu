@@ -695,7 +695,7 @@ struct SegBuildArgs {
     // The ghost blocks start at block gfirst: nbl (behind the local blocks) or nbl - 1 (the first ghost part shares the last local
     // block: one sweep less).  absolute != 0: entries hold the slot itself (all slots < 2^27), which is what lets a block mix ranges.
     uint32_t lcap, bsize_l, nbl, ng, nowners, gfirst, absolute;
-    uint32_t goff[17], gpart[16];
+    uint32_t goff[17], gfirst_len[16], gpart[16];      // owner p's range, the length of its first part and of each later part
     const uint32_t* sfirst;          // [n + 1] first segment of every called row
     __device__ __forceinline__ uint32_t block_of(uint32_t s, uint32_t& first) const {
         uint32_t b;
@@ -704,7 +704,8 @@ struct SegBuildArgs {
             const uint32_t g = s - lcap;
             uint32_t p = 0;
             while (p + 1 < nowners && g >= goff[p + 1]) ++p;
-            b = (g - goff[p]) / gpart[p];
+            const uint32_t x = g - goff[p];
+            b = x < gfirst_len[p] ? 0u : 1u + (x - gfirst_len[p]) / gpart[p];
             if (b >= ng) b = ng - 1;
             b += gfirst; first = lcap;
         }
@@ -988,7 +989,24 @@ struct AgentStore {
         uint32_t ng = 1;
     } peers;
     // slots per phase of a range of `len` ghosts travelling in `ng` phases (the same arithmetic on the sender and on the receiver)
-    static uint32_t ghost_part(uint32_t len, uint32_t ng) { return (std::max<uint32_t>((len + ng - 1) / ng, 1u) + 63u) & ~63u; }
+    // The first part is smaller (VB_HALO_FIRST, 0.3 of the range when there are several phases): the first sweep that needs ghosts
+    // waits for it with nothing to overlap, the later parts travel beside sweeps.
+    static uint32_t ghost_first(uint32_t len, uint32_t ng) {
+        static const double frac = getenv("VB_HALO_FIRST") ? std::min(1.0, std::max(0.01, atof(getenv("VB_HALO_FIRST")))) : 0.3;
+        if (ng <= 1) return len;
+        return std::min<uint32_t>(len, ((uint32_t)std::ceil((double)len * std::min(frac, 1.0 / ng)) + 63u) & ~63u);     // never more than an equal share
+    }
+    static uint32_t ghost_rest(uint32_t len, uint32_t ng) {     // slots of each later part
+        if (ng <= 1) return 1;
+        const uint32_t rest = len - ghost_first(len, ng);
+        return (std::max<uint32_t>((rest + ng - 2) / (ng - 1), 1u) + 63u) & ~63u;
+    }
+    static void ghost_part_range(uint32_t len, uint32_t ng, uint32_t j, uint32_t& lo, uint32_t& hi) {     // part j of a range of len slots
+        const uint64_t f = ghost_first(len, ng), r = ghost_rest(len, ng);
+        if (j == 0) { lo = 0; hi = (uint32_t)f; return; }
+        lo = (uint32_t)std::min<uint64_t>(f + (uint64_t)(j - 1) * r, len); hi = (uint32_t)std::min<uint64_t>(f + (uint64_t)j * r, len);
+        if (j + 1 == ng) hi = len;
+    }
     std::vector<cudaEvent_t> ev_phase;        // recorded on the halo stream after phase j has landed everywhere
     uint32_t halo_pending = 0, halo_waited = 0;   // phases started by this apply / already awaited by the main stream
     uint8_t* send_buf = nullptr;              // packed states for the halo exchange
@@ -2196,7 +2214,7 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
             static const double env_key_max_mb = getenv("VB_KEY_BLOCK_MAX_MB") ? atof(getenv("VB_KEY_BLOCK_MAX_MB")) : 60.0;
             const double last_local = (double)used - (double)(g_nbl - 1) * g_bsl;
             double part0 = 0;
-            for (size_t p2 = 0; p2 + 1 < src.ghost_off.size(); ++p2) part0 += std::min<double>(AgentStore::ghost_part(src.ghost_off[p2 + 1] - src.ghost_off[p2], g_ng), src.ghost_off[p2 + 1] - src.ghost_off[p2]);
+            for (size_t p2 = 0; p2 + 1 < src.ghost_off.size(); ++p2) part0 += AgentStore::ghost_first(src.ghost_off[p2 + 1] - src.ghost_off[p2], g_ng);
             if (last_local + part0 <= std::max(key_slots, env_key_max_mb * 1e6 * (key_slots / (env_key_block_mb * 1e6)))) g_gfirst = g_nbl - 1;
         }
         if (g_gfirst + g_ng > 64 || g_bsl > (1u << 27) || src.nghost > (1u << 27) || g_ng > 16 || (src.nghost && src.ghost_off.size() > 17))
@@ -2246,7 +2264,8 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
             sa.gfirst = g_gfirst; sa.absolute = g_abs ? 1u : 0u;
             for (uint32_t p2 = 0; p2 < sa.nowners; ++p2) {
                 sa.goff[p2] = src.ghost_off[p2]; sa.goff[p2 + 1] = src.ghost_off[p2 + 1];
-                sa.gpart[p2] = AgentStore::ghost_part(src.ghost_off[p2 + 1] - src.ghost_off[p2], g_ng);
+                sa.gfirst_len[p2] = AgentStore::ghost_first(src.ghost_off[p2 + 1] - src.ghost_off[p2], g_ng);
+                sa.gpart[p2] = AgentStore::ghost_rest(src.ghost_off[p2 + 1] - src.ghost_off[p2], g_ng);
             }
             sa.sfirst = sfirst; sa.seg_row = k.seg_row; sa.seg_lo = seg_lo; sa.seg_hi = seg_hi; sa.boff = k.boff; sa.bsrc = nullptr; sa.error = d_scalars + 1;
             seg_fill_kernel<<<nblk(n), 256, 0, g_stream>>>(sa); LAUNCH_CHECK();
@@ -2545,8 +2564,8 @@ void vb_sim::halo_exchange(int t) {
             for (uint32_t k = 0; k + 1 < P; ++k) {
                 const uint32_t r = (rank + 1 + k) % P;
                 // the j-th part of the range peer r mirrors of my agents (the part belongs to its ghost key block j)
-                const uint64_t len = a.send_off[r + 1] - a.send_off[r], part = AgentStore::ghost_part((uint32_t)len, ng);
-                const uint64_t lo = std::min<uint64_t>((uint64_t)j * part, len), hi = std::min<uint64_t>((uint64_t)(j + 1) * part, len);
+                uint32_t lo = 0, hi = 0;
+                AgentStore::ghost_part_range(a.send_off[r + 1] - a.send_off[r], ng, j, lo, hi);
                 h.voff[k + 1] = h.voff[k] + (uint32_t)(hi - lo);
                 h.first[k] = a.send_off[r] + (uint32_t)lo;
                 h.remote[k] = a.peers.base[a.cur][r]; h.rstride[k] = a.peers.stride[r]; h.rghost0[k] = a.peers.ghost0[r] + (uint32_t)lo;
@@ -3004,8 +3023,8 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                         if (k.ng && b >= k.gfirst) {                         // the part of every owner's range that belongs to this block
                             const uint32_t j = b - k.gfirst;
                             for (size_t p2 = 0; p2 + 1 < k.goff.size(); ++p2) {
-                                const uint32_t len = k.goff[p2 + 1] - k.goff[p2], part = AgentStore::ghost_part(len, k.ng);
-                                const uint32_t lo = std::min<uint64_t>((uint64_t)j * part, len), hi = std::min<uint64_t>((uint64_t)(j + 1) * part, len);
+                                uint32_t lo = 0, hi = 0;
+                                AgentStore::ghost_part_range(k.goff[p2 + 1] - k.goff[p2], k.ng, j, lo, hi);
                                 if (hi == lo) continue;
                                 lb.blk_key_first = k.lcap + k.goff[p2] + lo; lb.blk_nkeys = hi - lo;
                                 CK(ti->launch_keys(lb)); ++g_launches;
