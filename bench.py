@@ -169,6 +169,217 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---- secondary configs (configs 1, 2, 3, 5 and the docs' second value of eps): rank 0, one GPU, bounded in time --------
+def _nz(x):
+    """a duration that may be reported as zero (the CPU dry run has no device timers)"""
+    return x if x > 0 else 1e-9
+
+
+def _b_fin(appended, rows, s_e):
+    """B_fin = E'(4 + p 2 (8 + s_E) + 4) + 4 N with p = ceil(log2(rows) / 8) radix passes"""
+    p = int(np.ceil(np.log2(max(rows, 2)) / 8))
+    return appended * (4 + p * 2 * (8 + s_e) + 4) + 4 * rows
+
+
+def secondary_hk_eps(vh, be, torch, peak, n, eps, steps):
+    """HK-100M with the docs' other confidence bound (hegselmann.jl:164): half of the neighbours pass the key band, the engine's
+    pass-rate policy takes the unfiltered source-blocked sweeps"""
+    from models import hk_model
+    sim = vh.create_simulation(hk_model(), params={"eps": eps}, backend=be)
+    ne = C.c_uint64()
+    be.check(be.lib.vbw_hk_powerlaw_build_sharded(sim.h, 1, 0, C.c_uint64(n), C.c_uint64(SEED_GRAPH), C.c_uint64(SEED_OPINION), C.c_double(C_PARETO),
+                                                  C.c_uint32(DMAX), C.c_uint64(1 << 22), C.c_uint32(0), C.c_uint32(1), C.byref(ne)))
+    sim.finish_init(distribute=False)
+    for _ in range(3):
+        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+    torch.cuda.synchronize()
+    k_ms, st = 0.0, None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        st = sim.last_apply_stats()
+        k_ms += st["ms_kernel"]
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = _nz(ev0.elapsed_time(ev1)) / steps
+    alg = 12.0 * ne.value + 20.0 * n
+    out = {"workload": "hk-powerlaw-100M, eps = %.2f (hegselmann.jl:164)" % eps, "ms_per_step": ms, "edges_per_s": ne.value / (ms * 1e-3), "pass_rate": st["pass_rate"],
+           "read_phase": "prefiltered sweeps" if st["prefiltered"] else ("unfiltered source-blocked sweeps x %d" % st["source_blocks"] if st["source_blocks"] else "direct"),
+           "algorithmic_bytes": alg, "frac": alg / (_nz(k_ms) / steps * 1e-3) / 1e9 / peak}
+    sim.finish_simulation()
+    return out
+
+
+def secondary_gol(vh, be, torch, peak, n=4096, gens=100):
+    """BASELINE config 2: Game of Life on a 4096 x 4096 periodic raster (implicit Moore stencil), 100 generations + calc_raster"""
+    from models import gol_sim
+    init = np.random.default_rng(2).random((n, n)) < 0.35
+    sim = gol_sim(be, init)
+    for _ in range(3):
+        sim.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
+    torch.cuda.synchronize()
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    k_ms = 0.0
+    ev0.record()
+    for _ in range(gens):
+        sim.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
+        k_ms += sim.last_apply_stats()["ms_kernel"]
+    ev1.record()
+    grid = sim.calc_rasterstate("grid", "active", "Cell")
+    ev2.record()
+    torch.cuda.synchronize()
+    cells = n * n
+    ms, kms = _nz(ev0.elapsed_time(ev1)) / gens, _nz(k_ms) / gens
+    out = {"workload": "Game of Life %d x %d, %d generations + calc_raster (BASELINE config 2)" % (n, n, gens), "ms_per_generation": ms, "ms_kernel": kms,
+           "cell_updates_per_s": cells / (ms * 1e-3), "edges_per_s": 8 * cells / (ms * 1e-3), "calc_raster_ms": ev1.elapsed_time(ev2),
+           "algorithmic_bytes": 2.0 * cells, "frac": 2.0 * cells / (kms * 1e-3) / 1e9 / peak, "alive": int(np.asarray(grid).sum()),
+           "note": "2 B per cell of algorithmic bytes: a generation is bound by launch latency and the L2 round trip long before HBM"}
+    sim.finish_simulation()
+    return out
+
+
+def secondary_sir(vh, be, torch, peak, npers=50_000_000, nloc=5_000_000, steps=5):
+    """BASELINE config 5: 5e7 persons x 5e6 locations, the Visit / Exposure edges rebuilt every step (finish_write! = sort + CSR rebuild)"""
+    from models import sir_sim
+    sim = sir_sim(be, npers, nloc, beta=0.3)
+    per = {k: {"rw": [], "fin": [], "app": []} for k in ("visit", "tally", "expose", "infect")}
+    calls = (("visit", ("sir_visit", "Person", ["Person"], ["Visit"])), ("tally", ("sir_tally", "Location", ["Visit"], ["Location"])),
+             ("expose", ("sir_expose", "Location", ["Location", "Visit"], ["Exposure"])), ("infect", ("sir_infect", "Person", ["Person", "Exposure"], ["Person"])))
+
+    def step(i, rec):
+        for j, (name, a) in enumerate(calls):
+            sim.apply(*a, seed=4 * i + j)
+            if rec:
+                st = sim.last_apply_stats()
+                per[name]["rw"].append(st["ms_read_write"]); per[name]["fin"].append(st["ms_finish"]); per[name]["app"].append(st["edges_appended"])
+    for i in range(2):
+        step(i, False)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        step(2 + i, True)
+    ev1.record()
+    torch.cuda.synchronize()
+    out = {"workload": "SIR %g persons x %g locations, 2 visits per person and step (BASELINE config 5)" % (npers, nloc), "ms_per_step": ev0.elapsed_time(ev1) / steps}
+    appended = 0.0
+    for name, v in per.items():
+        rw, fin, app = float(np.mean(v["rw"])), float(np.mean(v["fin"])), float(np.mean(v["app"]))
+        out[name] = {"ms_read_write": rw, "ms_finish_write": fin, "edges_appended": app}
+        appended += app
+        if app:
+            s_e, rows = (1, nloc) if name == "visit" else (4, npers)
+            bfin = _b_fin(app, rows, s_e)
+            out[name].update({"finish_write_GBs": bfin / (_nz(fin) * 1e-3) / 1e9, "finish_write_frac": bfin / (_nz(fin) * 1e-3) / 1e9 / peak, "b_fin_bytes": bfin})
+    out["edges_appended_and_sorted_per_s"] = appended / (_nz(out["ms_per_step"]) * 1e-3)
+    sim.finish_simulation()
+    return out
+
+
+def secondary_pp(vh, be, torch, peak, d=2048, steps=5):
+    """BASELINE config 3 (b): the docs' predator/prey model on a 2048 x 2048 raster (838 861 prey, 209 715 predators), six applies per step"""
+    from models import pp_model, pp_step, PPCELL, ANIMAL
+    nprey, npred = max(8, int(838861 * (d / 2048.0) ** 2)), max(4, int(209715 * (d / 2048.0) ** 2))
+    rng = np.random.default_rng(3)
+    sim = vh.create_simulation(pp_model(), backend=be)
+    n = d * d
+    cells = np.zeros(n, dtype=np.dtype(PPCELL, align=True))
+    ii, jj = np.meshgrid(np.arange(1, d + 1), np.arange(1, d + 1), indexing="ij")
+    cells["pos"][:, 0] = ii.reshape(-1, order="F"); cells["pos"][:, 1] = jj.reshape(-1, order="F")
+    cells["countdown"] = np.where(rng.random(n) < 0.5, 0, rng.integers(1, 6, n))
+    cellids = sim.add_raster("raster", (d, d), "Cell", cells).reshape(-1, order="F")
+    offs = [(0, 0), (0, -1), (-1, 0), (1, 0), (0, 1)]       # stencil(:manhatten, 2, 1) with the centre first (move_to!)
+    for species, count in (("Prey", nprey), ("Predator", npred)):
+        st = np.zeros(count, dtype=np.dtype(ANIMAL, align=True))
+        st["energy"] = rng.integers(1, 11, count)
+        st["pos"][:, 0] = rng.integers(1, d + 1, count); st["pos"][:, 1] = rng.integers(1, d + 1, count)
+        ids = sim.add_agents(species, st)
+        x, y = st["pos"][:, 0] - 1, st["pos"][:, 1] - 1
+        sim.add_edges(ids, cellids[x + y * d], f"Position{{{species}}}")
+        fr, to = [], []
+        for dx, dy in offs:
+            c = cellids[((x + dx) % d) + ((y + dy) % d) * d]
+            fr += [c, ids]; to += [ids, c]
+        sim.add_edges(np.stack(fr, axis=1).reshape(-1), np.stack(to, axis=1).reshape(-1), f"View{{{species}}}")
+    sim.finish_init()
+    names = ["move_prey", "find_prey", "move_pred", "grow_food", "try_eat", "try_reproduce"]
+    per = {k: {"rw": [], "fin": [], "app": []} for k in names}
+    orig_apply, counter = sim.apply, {"i": 0, "rec": False}
+
+    def apply_rec(*a, **kw):
+        orig_apply(*a, **kw)
+        if counter["rec"]:
+            st = sim.last_apply_stats()
+            k = names[counter["i"] % 6]
+            per[k]["rw"].append(st["ms_read_write"]); per[k]["fin"].append(st["ms_finish"]); per[k]["app"].append(st["edges_appended"])
+        counter["i"] += 1
+    sim.apply = apply_rec
+    for i in range(3):
+        pp_step(sim, i)
+    counter["rec"] = True
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        pp_step(sim, 3 + i)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    out = {"workload": "predator/prey %d x %d raster (BASELINE config 3 b)" % (d, d), "ms_per_step": ms, "applies_per_step": 6,
+           "prey": sim.mapreduce(None, "+", "Prey", init=0), "predators": sim.mapreduce(None, "+", "Predator", init=0)}
+    appended, fin_ms = 0.0, 0.0
+    for k, v in per.items():
+        out[k] = {"ms_read_write": float(np.mean(v["rw"])), "ms_finish_write": float(np.mean(v["fin"])), "edges_appended": float(np.mean(v["app"]))}
+        appended += out[k]["edges_appended"]; fin_ms += out[k]["ms_finish_write"]
+    out["edges_appended_per_step"] = appended
+    out["finish_write_frac"] = _b_fin(appended, n + nprey + npred, 0) / (_nz(fin_ms) * 1e-3) / 1e9 / peak
+    sim.finish_simulation()
+    return out
+
+
+def secondary_hk100k(vh, be, torch, peak, n=100_000, steps=50):
+    """BASELINE config 1 on the GPU: the docs' HK model on a 100k-agent Barabasi-Albert graph (latency-bound: 1.7e6 edges per apply)"""
+    from models import hk_sim, ba_graph
+    uv = ba_graph(n, 8, 1)
+    sim, _ = hk_sim(be, n, uv, np.random.default_rng(1).random(n), 0.02)
+    E = sim.num_edges("Knows")
+    for _ in range(3):
+        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ms = 0.0
+    ev0.record()
+    for _ in range(steps):
+        sim.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        k_ms += sim.last_apply_stats()["ms_kernel"]
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = _nz(ev0.elapsed_time(ev1)) / steps
+    alg = 12.0 * E + 20.0 * n
+    out = {"workload": "hk on a %d-agent Barabasi-Albert graph (BASELINE config 1), %d steps" % (n, steps), "edges": int(E), "ms_per_step": ms, "ms_kernel": k_ms / steps,
+           "edges_per_s": E / (ms * 1e-3), "algorithmic_bytes": alg, "frac": alg / (_nz(k_ms) / steps * 1e-3) / 1e9 / peak,
+           "note": "latency-bound: the whole state (0.8 MB) and the CSR (6.8 MB) sit in L2, an apply is a handful of launches and host synchronisations"}
+    sim.finish_simulation()
+    return out
+
+
+def run_secondary(vh, be, torch, peak, n_main, scale=1.0):
+    """scale < 1 shrinks every workload (agent counts by `scale`, raster edges by its square root): the CPU dry run of the plumbing"""
+    out = {}
+    lin = scale ** 0.5
+    for name, fn in (("hk_eps025", lambda: secondary_hk_eps(vh, be, torch, peak, n_main, 0.25, 5)),
+                     ("gol_4096", lambda: secondary_gol(vh, be, torch, peak, n=max(16, int(4096 * lin)), gens=100 if scale == 1.0 else 3)),
+                     ("sir_50M_x_5M", lambda: secondary_sir(vh, be, torch, peak, npers=max(2000, int(5e7 * scale)), nloc=max(200, int(5e6 * scale)), steps=5 if scale == 1.0 else 2)),
+                     ("predator_prey_2048", lambda: secondary_pp(vh, be, torch, peak, d=max(16, int(2048 * lin)), steps=5 if scale == 1.0 else 2)),
+                     ("hk_100k", lambda: secondary_hk100k(vh, be, torch, peak, n=max(300, int(1e5 * scale)), steps=50 if scale == 1.0 else 3))):
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+        except Exception as exc:        # a secondary figure must never cost the bench line
+            out[name] = {"error": repr(exc)[:300]}
+        out[name]["wall_s"] = time.perf_counter() - t0
+    return out
+
+
 def run_engine(args):
     import torch
     import torch.distributed as dist
@@ -289,6 +500,13 @@ def run_engine(args):
         if bool(tj.get("prefiltered", False)) == bool(prefiltered):     # a capture of the other kernel shape says nothing about this one
             traffic = tj.get("dram_bytes_per_launch")
     cpu_eps, cpu_ms, cpu_ne = time_oracle(vh, args.cpu_agents, 3, 1) if (not args.no_cpu and world == 1) else (None, None, None)
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        pass_rate_main = sim.last_apply_stats()["pass_rate"]
+        sim.finish_simulation()          # free the 100M-agent simulation before the other workloads are built
+        secondary = run_secondary(vh, be, torch, peak, n, args.secondary_scale)
+    else:
+        pass_rate_main = sim.last_apply_stats()["pass_rate"]
     value = E * args.steps / (ms_total * 1e-3)
     line = {
         "metric": "edges/sec per apply! (Hegselmann-Krause read+write phase)", "value": value, "unit": "edges/s",
@@ -299,17 +517,21 @@ def run_engine(args):
                    "halo_bytes_per_step_rank0": int(hb.value),
                    "l2": "inputs larger than L2 (source states 0.8 GB, CSR columns %.1f GB); no flush needed" % (4.0 * E / 1e9),
                    "agent_updates_per_s": n * args.steps / (ms_total * 1e-3), "build_s": t_build, "opinion_sum": metric,
+                   "prefilter_pass_rate": pass_rate_main, "secondary": secondary,
                    "read_phase": ("prefiltered sweeps: every edge gathers the one-byte key of its source (opinion quantised to 1/256), the 8-byte state is "
                                   "fetched where the key may pass; fold() always decides on the exact state, results identical to the unfiltered "
                                   "sweeps (22.9 ms/step on one GPU, profiles/r1_bench_hk100m_v4.json; VB_PREFILTER=0 selects them)") if prefiltered
                    else ("source-blocked sweeps" if sweeps else "direct gathers")},
         "roofline": {"bound": "hbm",
-                     "kernel": ("build_keys_kernel<hk::Step> + reduce_prefilter_kernel<hk::Step> x %d key-block sweeps + transition_kernel<hk::Step, DIRECT, 256> (hub rows)" % sweeps)
+                     "kernel": ("build_keys_kernel<hk::Step> + reduce_segsweep_kernel<hk::Step> x %d key-block sweeps + reduce_hubmerge_kernel<hk::Step> (rows cut into segments)" % sweeps)
                      if (sweeps and prefiltered) else
                      ("reduce_blocked_kernel<hk::Step> x %d source-block sweeps + transition_kernel<hk::Step, DIRECT, 256> (hub rows)" % sweeps)
                      if sweeps else "transition_kernel<hk::Step, DIRECT, 8 lanes per agent> + <..., 256> (hub rows)",
                      "launches_per_step": (sweeps + 1 + int(prefiltered)) if sweeps else 2, "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": None if traffic is None else "ncu --set full capture of the same command (profiles/hk_step_traffic.json), not measured in this run",
+                     "achieved_is": "algorithmic bytes of SURVEY 8(d) (12 B per edge + 20 B per agent) / kernel time; the sweeps move fewer bytes per edge (1 B key + 4 B index, 8 B state for the ~5 % that pass) and are bound by the L1 gather rate, see traffic",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "frac_of_8TBs_spec": achieved / 8000.0},
         "cpu_baseline": None if cpu_eps is None else {
             "value": cpu_eps, "unit": "edges/s", "cores": 1, "kind": "port",
@@ -335,6 +557,8 @@ def main():
     ap.add_argument("--cpu-agents", type=int, default=1_000_000)
     ap.add_argument("--cpu-procs", type=int, default=32, help="--impl reference: oracle processes run side by side (capped at the core count)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--secondary-scale", type=float, default=1.0, help="shrink the secondary workloads (plumbing tests)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip config.secondary (BASELINE configs 1, 2, 3, 5 and eps = 0.25 on one GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

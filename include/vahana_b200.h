@@ -169,6 +169,11 @@ int vb_last_apply_blocks(vb_sim* sim, uint32_t* nblocks_out);
    whether the last apply's sweeps were prefiltered. */
 int vb_set_read_prefilter(vb_sim* sim, int on);
 int vb_last_apply_prefiltered(vb_sim* sim, int* on_out);
+/* Share of sampled edges whose source key the target's probe let through, as estimated by the last apply that checked (every 16th apply
+   of a prefilter-capable reduce transition; negative = never estimated).  Above VB_PF_MAX_PASS (0.30) the engine takes the unfiltered
+   sweeps — a key that passes costs a DRAM-random fetch of the exact state, e.g. ϵ = 0.25 in hegselmann.jl:164 — below VB_PF_MIN_PASS
+   (0.22) it returns to the prefiltered ones.  The reference has no counterpart (its loop visits every neighbour state). */
+int vb_last_pass_rate(vb_sim* sim, double* rate_out);
 
 #ifdef __cplusplus
 }

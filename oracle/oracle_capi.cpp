@@ -346,6 +346,7 @@ int vb_last_apply_stats(vb_sim* sim, double* ms_rw, double* ms_fin, uint64_t* er
 }
 int vb_set_read_prefilter(vb_sim*, int) { return VB_OK; }                        // no keys: every neighbour state is read
 int vb_last_apply_prefiltered(vb_sim*, int* on) { if (on) *on = 0; return VB_OK; }
+int vb_last_pass_rate(vb_sim*, double* rate) { if (rate) *rate = -1.0; return VB_OK; }
 int vb_set_read_blocking(vb_sim*, double, double, int) { return VB_OK; }   // the oracle walks every row left to right
 int vb_last_apply_blocks(vb_sim*, uint32_t* nb) { if (nb) *nb = 0; return VB_OK; }
 

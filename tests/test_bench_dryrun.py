@@ -67,7 +67,8 @@ def test_bench_engine_arm_plumbing(oracle, monkeypatch):
     monkeypatch.setattr(vh.Simulation, "last_apply_stats", stats)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
-    args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="engine", agents=3000.0, cpu_agents=2000, cpu_procs=1, no_cpu=False)
+    args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="engine", agents=3000.0, cpu_agents=2000, cpu_procs=1, no_cpu=False, no_secondary=False,
+                              secondary_scale=1e-4)
     buf = io.StringIO()
     with redirect_stdout(buf):
         bench.run_engine(args)
@@ -89,4 +90,11 @@ def test_bench_engine_arm_plumbing(oracle, monkeypatch):
     assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 0 and e["d2h_bytes_per_step"] > 0      # (the oracle uploads no device view)
     assert e["with_state_download"]["d2h_bytes_per_step"] == 8 * 3000
     assert d["value"] > 0 and d["ms_per_step"] > 0 and isinstance(d["gpu_launches"], int)
+    sec = d["config"]["secondary"]          # BASELINE configs 1, 2, 3, 5 and the docs' second eps, at toy sizes here
+    assert set(sec) == {"hk_eps025", "gol_4096", "sir_50M_x_5M", "predator_prey_2048", "hk_100k"}
+    for name, v in sec.items():
+        assert "error" not in v, (name, v)
+    assert sec["gol_4096"]["ms_per_generation"] > 0 and sec["gol_4096"]["algorithmic_bytes"] > 0
+    assert sec["sir_50M_x_5M"]["visit"]["edges_appended"] > 0 and sec["sir_50M_x_5M"]["visit"]["finish_write_frac"] > 0
+    assert sec["predator_prey_2048"]["applies_per_step"] == 6 and sec["hk_100k"]["edges_per_s"] > 0 and sec["hk_eps025"]["ms_per_step"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -181,6 +181,28 @@ def test_hk_blocked_read_phase_vs_oracle(oracle, cuda, n, m, block_mb, prefilter
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("eps,expect_pf", [(0.02, True), (0.25, False)])
+def test_hk_prefilter_policy_follows_pass_rate(oracle, cuda, eps, expect_pf):
+    """The engine samples how many keys the probes let through and keeps the prefiltered sweeps only while they are selective: the docs'
+    two values of eps (hegselmann.jl:44 and :164) end on different forms, both equal to the oracle.  (vb_set_read_prefilter is left at
+    its default: the policy decides.)"""
+    n = 20000
+    uv = ba_graph(n, 8, 1)
+    op0 = np.random.default_rng(1).random(n)
+    g, _ = hk_sim(cuda, n, uv, op0, eps)
+    o, _ = hk_sim(oracle, n, uv, op0, eps)
+    g.set_read_blocking(0.02, 0.0, 1)                  # tiny blocks, no size threshold, build at first sight
+    for step in range(3):
+        g.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        o.apply("hk_step", "HKAgent", ["HKAgent", "Knows"], "HKAgent")
+        st = g.last_apply_stats()
+        assert st["source_blocks"] >= 1 and st["pass_rate"] is not None, st
+        assert st["prefiltered"] == expect_pf, st
+        assert (st["pass_rate"] < 0.22) if expect_pf else (st["pass_rate"] > 0.30), st
+        np.testing.assert_allclose(_opinions(g), _opinions(o), rtol=RTOL, atol=0)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("eps", [0.0, 0.003, 0.25, 0.7, 2.0])
 def test_hk_prefilter_band_edges_vs_oracle(oracle, cuda, eps):
     """Acceptance band against the key grid: eps below one key step, eps wider than the clamp, opinions on key boundaries and at

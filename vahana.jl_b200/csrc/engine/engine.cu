@@ -1086,6 +1086,8 @@ struct EdgeStore {
         uint64_t seen_version = ~0ull; uint32_t seen = 0;   // how many applies found the same container (static network => worth building)
         bool refused = false;                          // the build found a source of another type: stay on the direct path
     } blk;
+    // prefilter policy: the sampled pass rate decides between prefiltered and unfiltered sweeps (checked every 16th apply)
+    bool pf_off = false; uint32_t pf_check_in = 0; double pf_rate = -1.0;
     bool has_src() const { return !ignorefrom; }
     bool has_state() const { return !stateless && size > 0; }
 };
@@ -1148,8 +1150,9 @@ struct vb_sim {
     bool prefilter_on(const vb::TransitionInfo* ti) const;
     uint32_t last_blocked_nb = 0;   // source blocks swept by the last apply's read phase (0 = direct path)
     bool last_prefiltered = false;  // those sweeps gathered keys (prefilter) instead of states
+    double last_pass_rate = -1.0;   // last estimate of the prefilter's pass rate (vb_last_pass_rate)
     uint64_t layout_epoch = 0; // bumped whenever stored composite indices are renumbered (rebase): invalidates blocked views
-    bool ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min);
+    bool ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min, const vb::LaunchArgs* la = nullptr, uint64_t seed = 0);
     void rebase(const uint32_t* old_base, const uint32_t* old_lcap = nullptr, const uint32_t* const* remap = nullptr);
     void exchange_ghost_requests();
     void transmit_edges(int e);
@@ -2156,9 +2159,8 @@ bool vb_sim::prefilter_on(const vb::TransitionInfo* ti) const {
     static const bool env_on = !(getenv("VB_PREFILTER") && atoi(getenv("VB_PREFILTER")) == 0);
     return ti->prefilter && ti->launch_keys && (blk_prefilter >= 0 ? blk_prefilter != 0 : env_on);
 }
-bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min) {
+bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_t n, uint32_t heavy_min, const vb::LaunchArgs* la, uint64_t seed) {
     static const double env_key_block_mb = getenv("VB_KEY_BLOCK_MB") ? atof(getenv("VB_KEY_BLOCK_MB")) : 52.0;
-    const bool pf = prefilter_on(ti);
     static const bool enabled = !(getenv("VB_BLOCK") && atoi(getenv("VB_BLOCK")) == 0);
     static const double env_block_mb = getenv("VB_BLOCK_MB") ? atof(getenv("VB_BLOCK_MB")) : 75.0;
     static const double env_min_mb = getenv("VB_BLOCK_MIN_MB") ? atof(getenv("VB_BLOCK_MIN_MB")) : 192.0;
@@ -2176,6 +2178,31 @@ bool vb_sim::ensure_blocked(int ei, const vb::TransitionInfo* ti, int C, uint32_
     if (a.independent && ti->source_type == C) return false;          // in-place states: a later sweep would read updated sources
     const uint32_t nsl = src.cap + src.nghost;
     if ((double)nsl * src.size < min_mb * 1e6) return false;
+    if (la && ti->launch_passrate && prefilter_on(ti) && blk_prefilter < 0) {
+        // Is the prefilter selective at the moment?  Every 16th apply samples 65 536 entries (one launch, one 16-byte read-back) and
+        // switches between the prefiltered and the unfiltered sweeps with some hysteresis.  vb_set_read_prefilter(sim, 1 / 0) pins a form.
+        static const double max_pass = getenv("VB_PF_MAX_PASS") ? atof(getenv("VB_PF_MAX_PASS")) : 0.30;
+        static const double min_pass = getenv("VB_PF_MIN_PASS") ? atof(getenv("VB_PF_MIN_PASS")) : 0.22;
+        if (pe.pf_check_in == 0) {
+            unsigned long long* cnt = (unsigned long long*)(d_scalars + 48);
+            CK(cudaMemsetAsync(cnt, 0, 16, g_stream));
+            vb::LaunchArgs lp = *la;
+            lp.stats = cnt;
+            upload_view(seed);
+            CK(ti->launch_passrate(lp)); ++g_launches;
+            unsigned long long h2[2] = {0, 0};
+            CK(cudaMemcpyAsync(h2, cnt, 16, cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            if (h2[0]) {
+                pe.pf_rate = (double)h2[1] / (double)h2[0];
+                if (pe.pf_rate > max_pass) pe.pf_off = true; else if (pe.pf_rate < min_pass) pe.pf_off = false;
+            }
+            pe.pf_check_in = 16;
+        }
+        --pe.pf_check_in;
+        last_pass_rate = pe.pf_rate;
+    }
+    const bool pf = prefilter_on(ti) && !pe.pf_off;
     uint32_t bsize = (uint32_t)std::max<double>(1.0, block_mb * 1e6 / src.size);
     uint32_t nb = (nsl + bsize - 1) / bsize;
     if (nb > 64) { bsize = (nsl + 63) / 64; nb = (nsl + bsize - 1) / bsize; }
@@ -2940,7 +2967,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
                     // source block; only hub rows of >= 16384 entries are left to the block-per-agent pass there (the sweeps fold
                     // long rows warp-cooperatively), the direct path hands over rows of >= 1024 entries.
                     constexpr uint32_t HEAVY_DIRECT = 1024, HEAVY_BLOCKED = 16384;
-                    blocked = ti->reduce && s.ensure_blocked(ti->primary_edge, ti, C, n, HEAVY_BLOCKED);
+                    blocked = ti->reduce && s.ensure_blocked(ti->primary_edge, ti, C, n, HEAVY_BLOCKED, &la, seed);
                     const uint32_t HEAVY_MIN = blocked ? HEAVY_BLOCKED : HEAVY_DIRECT;
                     const bool segmented = blocked && pe.blk.segmented;          // hub rows are cut into segments: no pass of their own
                     if (!segmented && (pe.heavy_version != pe.version || pe.heavy_type != C || pe.heavy_min != HEAVY_MIN)) {
@@ -4245,6 +4272,7 @@ int vb_last_apply_stats(vb_sim* s, double* ms_rw, double* ms_fin, uint64_t* er, 
 int vb_last_kernel_ms(vb_sim* s, double* ms) { *ms = s->ms_kernel; return VB_OK; }
 int vb_set_read_prefilter(vb_sim* s, int on) { if (!s) return VB_ERR_ARG; s->blk_prefilter = on; return VB_OK; }
 int vb_last_apply_prefiltered(vb_sim* s, int* on) { if (on) *on = s->last_prefiltered ? 1 : 0; return VB_OK; }
+int vb_last_pass_rate(vb_sim* s, double* rate) { if (rate) *rate = s->last_pass_rate; return VB_OK; }
 int vb_set_read_blocking(vb_sim* s, double block_mb, double min_mb, int eager) {
     s->blk_block_mb = block_mb; s->blk_min_mb = min_mb; s->blk_eager = eager;
     return VB_OK;
