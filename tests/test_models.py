@@ -41,6 +41,28 @@ def test_gol_gpu_vs_oracle(oracle, cuda):
     assert g.mapreduce("active", "+", "Cell", datatype="i8") == int(a.sum())
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,periodic", [((37, 45), True), ((37, 45), False), ((3, 3), True), ((3, 3), False), ((64, 5), False), ((31, 33), True),
+                                            ((200, 130), False), ((5, 96), True)])
+def test_gol_strip_kernel_shapes_vs_oracle(oracle, cuda, shape, periodic):
+    """The strip-shaped grid-stencil kernel (a warp per 30 cells of the first dimension, sliding window of three rows): rasters that do
+    not fill the last strip or band, rasters narrower than a strip, and clipped (non-periodic) borders where cells have 3 or 5 neighbours."""
+    init = np.random.default_rng(5).random(shape) < 0.4
+
+    def build(be):
+        sim = vh.create_simulation(gol_sim.__globals__["gol_model"](), backend=be)
+        sim.add_raster("grid", init.shape, "Cell", np.asarray(init, dtype="?").reshape(-1, order="F").view([("active", "?")]))
+        sim.connect_raster_neighbors("grid", "Neighbor", periodic=periodic)
+        sim.finish_init()
+        return sim
+    g, o = build(cuda), build(oracle)
+    for _ in range(6):
+        g.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
+        o.apply("gol_life", "Cell", ["Cell", "Neighbor"], "Cell")
+        assert np.array_equal(g.rastervalues("grid", "active", "Cell"), o.rastervalues("grid", "active", "Cell"))
+        assert g.last_apply_stats()["edges_read"] == o.last_apply_stats()["edges_read"] or o.last_apply_stats()["edges_read"] == 0
+
+
 def _sir_counts(sim):
     s = sim.all_agents("Person")["state"]
     return [int((s == k).sum()) for k in range(3)]

@@ -1120,7 +1120,15 @@ struct vb_sim {
     unsigned long long* d_stats = nullptr;
     // stats of the last apply
     double ms_rw = 0, ms_fin = 0;
-    bool stats_pending = false;
+    bool stats_pending = false, times_pending = false;
+    void fetch_times() {
+        if (!times_pending) return;
+        times_pending = false;
+        float m0 = 0, m1 = 0;
+        if (cudaEventSynchronize(ev[2]) == cudaSuccess) { cudaEventElapsedTime(&m0, ev[0], ev[1]); cudaEventElapsedTime(&m1, ev[1], ev[2]); }
+        cudaGetLastError();
+        ms_rw = m0; ms_fin = m1;
+    }
     uint64_t st_edges_read = 0, st_edges_appended = 0, st_agents_called = 0, st_launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t evk[2] = {nullptr, nullptr};   // around the transition kernels themselves
@@ -2865,6 +2873,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
     if (g_nranks > 1) g_trace.end("halo exchange", tname);
     s.st_agents_called = 0;
     s.ms_kernel = 0;
+    bool kernel_time_pending = false;
     uint64_t appended = 0;
 
     // ---- the transition loop over `call` (Simulation.jl:774-788) ----
@@ -2887,6 +2896,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         const int nw = ti->n_edge_writes + ti->n_agent_writes + ti->n_edge_removes;
         std::vector<uint32_t*> tmp;
         if (nw > 0) {
+            set_persisting_l2_mb(0);
             // count pass -> exclusive scans -> totals
             uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words(n));
             tmp.push_back(scr);
@@ -3088,6 +3098,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             const size_t state_bytes = (size_t)a.stride() * a.size;
             const int persist_mb = persist_env >= 0 ? persist_env : (ti->cooperative && ti->primary_edge >= 0 && state_bytes > ((size_t)256 << 20) ? 48 : 0);
             bool persisting = false;
+            if (persist_mb == 0) set_persisting_l2_mb(0);      // hand a set-aside left by swept read phases back: sorts and scatters want the whole L2
             if (persist_mb > 0 && a.size) {
                 set_persisting_l2_mb(persist_mb);
                 cudaStreamAttrValue av{};
@@ -3117,14 +3128,17 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
             }
             }
         }
-        CK(cudaStreamSynchronize(g_stream));
-        { float mk = 0; cudaEventElapsedTime(&mk, s.evk[0], s.evk[1]); s.ms_kernel += mk; }
-        for (auto p : tmp) dfree(p);
+        if (call.size() > 1) {       // the event pair is reused by the next called type
+            CK(cudaStreamSynchronize(g_stream));
+            float mk = 0; cudaEventElapsedTime(&mk, s.evk[0], s.evk[1]); s.ms_kernel += mk;
+        } else kernel_time_pending = true;      // read after the synchronisation of the error check below: one host round trip less per apply!
+        for (auto p : tmp) dfree(p);            // (the pool hands buffers out again in stream order)
     }
     s.halo_wait_all();          // (a rank without agents of the called type launched nothing: join the halo stream before the buffers swap)
     CK(cudaEventRecord(s.ev[1], g_stream));
     g_trace.end("transition loop", tname);
     s.check_device_error("apply!");
+    if (kernel_time_pending) { float mk = 0; if (cudaEventElapsedTime(&mk, s.evk[0], s.evk[1]) == cudaSuccess) s.ms_kernel += mk; cudaGetLastError(); }
     if (g_nranks > 1) {
         // transmit_remove_edges! (Simulation.jl:792-795) before transmit_edges! (:800).  Collective; every rank runs the same
         // transition, so all of them agree on the edge types whose removes have to travel.
@@ -3202,11 +3216,7 @@ void do_apply(vb_sim& s, const std::string& tname, const std::vector<int>& call,
         for (auto p : died_flags) dfree(p);
     }
     CK(cudaEventRecord(s.ev[2], g_stream));
-    CK(cudaStreamSynchronize(g_stream));
-    float m0 = 0, m1 = 0;
-    cudaEventElapsedTime(&m0, s.ev[0], s.ev[1]);
-    cudaEventElapsedTime(&m1, s.ev[1], s.ev[2]);
-    s.ms_rw = m0; s.ms_fin = m1;
+    s.times_pending = true;   // the phase times are read when somebody asks (vb_last_apply_stats): apply! does not wait for its last kernels
     s.stats_pending = true;   // the 1024 spread counters are fetched lazily by vb_last_apply_stats
     const unsigned long long er = 0;
     s.st_edges_read = er; s.st_edges_appended = appended; s.st_launches = g_launches - launches0;
@@ -4256,6 +4266,7 @@ int vb_raster_info(vb_sim* s, const char* name, int* ndims, int64_t* dims, vb_ag
 }
 int vb_num_transitions(vb_sim* s, int64_t* n) { *n = s->num_transitions; return VB_OK; }
 int vb_last_apply_stats(vb_sim* s, double* ms_rw, double* ms_fin, uint64_t* er, uint64_t* ea, uint64_t* ac, uint64_t* kl) {
+    s->fetch_times();
     if (s->stats_pending) {
         s->stats_pending = false;
         std::vector<unsigned long long> hs(4096);
