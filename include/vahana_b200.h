@@ -96,6 +96,10 @@ int vb_add_edges(vb_sim* sim, int etype, const vb_agent_id* from, const vb_agent
 int vb_remove_edges(vb_sim* sim, int etype, vb_agent_id from /*0 = all*/, vb_agent_id to);      /* EdgeMethods.jl:527-599 */
 int vb_add_raster(vb_sim* sim, const char* name, int ndims, const int64_t* dims, int type, const void* states,
                   vb_agent_id* ids_out);                                                         /* Raster.jl:32-54 */
+/* The receiver side of broadcastids (src/MPI.jl:59-73, src/Raster.jl:64-75): a raster over agents that exist already — `ids` in
+   CartesianIndices (column-major) order, some of them agents of other ranks after finish_init!(distribute = true) handed the cells
+   out.  Init phase.  calc_raster / calc_rasterstate / rastervalues of such a raster join the ranks (src/Raster.jl:227,318,378). */
+int vb_set_raster(vb_sim* sim, const char* name, int ndims, const int64_t* dims, int type, const vb_agent_id* ids);
 int vb_connect_raster_neighbors(vb_sim* sim, const char* name, int etype, double distance, int metric, int periodic,
                                 const void* edge_state);                                         /* Raster.jl:139-167 */
 int vb_move_to(vb_sim* sim, const char* name, vb_agent_id id, const int64_t* pos, int etype_from /*-1 = nothing*/,

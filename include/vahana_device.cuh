@@ -109,7 +109,8 @@ struct EdgeView {
     uint8_t st_periodic, st_reach;
 };
 struct RasterView {
-    const uint32_t* cells;    // composite index of the cell agent at each position (column-major)
+    const uint32_t* cells;    // composite index of the cell agent at each position (column-major); 0xffffffff = a cell of another rank
+    const uint64_t* cell_ids; // AgentIDs of the cells when some of them live on other ranks (else nullptr)
     int32_t ndims;
     int32_t type;             // agent type of the cells
     int64_t dims[MAX_RASTER_DIMS];
@@ -761,7 +762,7 @@ class Ctx {
             idx += (size_t)(p.v[k] - 1) * stride;
             stride *= (size_t)rv.dims[k];
         }
-        return id_of(rv.cells[idx]);
+        return rv.cell_ids ? rv.cell_ids[idx] : id_of(rv.cells[idx]);
     }
     // move_to! for stateless edge types (Raster.jl:437-477); stencil enumeration as _stencil_core :82-96
     __device__ void move_to(int r, AgentID id, const Pos& p, int e_from, int e_to, double distance = 0, int metric = CHEBYSHEV,
@@ -1902,6 +1903,7 @@ __global__ void __launch_bounds__(256) map_cells_kernel(const MapCellsArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const F f{};
+    if (a.cells[i] == 0xffffffffu) { reinterpret_cast<T*>(a.out)[i] = (T)0; return; }     // a cell of another rank: its owner fills it in (joined by the engine)
     reinterpret_cast<T*>(a.out)[i] = (T)f(soa_load<Elem>(a.cols, a.stride, a.cells[i] - a.cbase));
 }
 template <class F>

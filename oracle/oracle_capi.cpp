@@ -97,6 +97,18 @@ int vb_remove_edges(vb_sim* sim, int e, vb_agent_id from, vb_agent_id to) {
 int vb_add_raster(vb_sim* sim, const char* name, int ndims, const int64_t* dims, int type, const void* states, vb_agent_id* ids_out) {
     return guard([&] { vo::add_raster(*sim->s, name, std::vector<int64_t>(dims, dims + ndims), type, states, ids_out); });
 }
+int vb_set_raster(vb_sim* sim, const char* name, int ndims, const int64_t* dims, int type, const vb_agent_id* ids) {
+    return guard([&] {   // a raster over existing agents (broadcastids, src/MPI.jl:59-73); one rank: all of them are local
+        (void)type;
+        if (sim->s->initialized) throw vo::AssertionError("rasters can only be defined before finish_init!");
+        vo::Raster r;
+        r.name = name; r.dims.assign(dims, dims + ndims);
+        size_t n = 1;
+        for (int i = 0; i < ndims; ++i) n *= (size_t)dims[i];
+        r.ids.assign(ids, ids + n);
+        sim->s->rasters.push_back(std::move(r));
+    });
+}
 int vb_connect_raster_neighbors(vb_sim* sim, const char* name, int e, double distance, int metric, int periodic, const void* st) {
     return guard([&] { vo::connect_raster_neighbors(*sim->s, name, e, distance, metric, periodic, st); });
 }

@@ -86,6 +86,39 @@ def test_finish_init_single_rank_idmapping_is_identity(oracle):
     assert sim2.finish_init() is sim2 and sim2.finish_init.__doc__
 
 
+def test_raster_is_staged_for_the_hand_out(oracle):
+    """add_raster! / connect_raster_neighbors! of the initialisation phase are kept on the host like every other add, so that
+    finish_init!(distribute = true) can hand the cells out and broadcast the id grid (broadcastids, src/MPI.jl:59-73): the staged agents
+    and edges are exactly what the engine holds, row order (per-target push! order) included."""
+    from models import gol_model
+    init = np.random.default_rng(3).random((5, 4)) < 0.5
+    sim = vh.create_simulation(gol_model(), backend=oracle)
+    sim._stage = {"agents": {}, "edges": {}}                    # what a multi-rank backend switches on
+    ids = sim.add_raster("grid", init.shape, "Cell", np.asarray(init, dtype="?").reshape(-1, order="F").view([("active", "?")]))
+    sim.connect_raster_neighbors("grid", "Neighbor")
+    sim.connect_raster_neighbors("grid", "Neighbor", distance=1, metric="manhatten", periodic=False)     # a second call appends to the rows
+    assert sim._unstageable is None
+    (sids, sstates), = sim._stage["agents"][sim._aid["Cell"]]
+    assert np.array_equal(sids, ids.reshape(-1, order="F")) and np.array_equal(sstates["active"], init.reshape(-1, order="F"))
+    dims, tid, rids = sim._stage["rasters"]["grid"]
+    assert dims == (5, 4) and tid == sim._aid["Cell"] and np.array_equal(rids, sids)
+    fr = np.concatenate([c[0] for c in sim._stage["edges"]["Neighbor"]])
+    to = np.concatenate([c[1] for c in sim._stage["edges"]["Neighbor"]])
+    sim._stage = None
+    sim.finish_init()
+    off, efrom, _ = sim.export_csr("Neighbor", "Cell", init.size)
+    assert fr.shape[0] == int(off[-1]) == 8 * 20 + (2 * 4 * 4 + 2 * 5 * 3)       # Moore, periodic + von Neumann, clipped (62 directed edges on 5 x 4)
+    # per target: the staged edges in staging order are the engine's row
+    for k, cid in enumerate(sids):
+        assert np.array_equal(fr[to == cid], efrom[int(off[k]):int(off[k + 1])]), k
+    # the plan hands cells and grid out consistently
+    shards, old, new, bounds = vh.plan_distribution({tid: (sids, sstates)}, {"Neighbor": (fr, to, None)}, 2)
+    grid_new = new[np.searchsorted(old, rids)]
+    b = bounds[tid]
+    assert [vh.process_nr(int(x)) for x in grid_new] == [0] * b[1] + [1] * (20 - b[1])
+    assert sum(s_["edges"]["Neighbor"][1].shape[0] for s_ in shards) == fr.shape[0]
+
+
 _GLOO = r'''
 import os, sys, ctypes as C
 import numpy as np, torch.distributed as dist

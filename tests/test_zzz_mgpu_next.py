@@ -1,5 +1,6 @@
-"""Multi-GPU tests written after round 1's GPU budget was spent (never run on GPUs yet): they sort behind the established suite so
-that `pytest -x` reaches them last."""
+"""Multi-GPU tests of the paths added after the first multi-rank suite (remote remove_edges!, finish_init!(distribute = true), the
+reference's core / agentstate tests under several ranks, rasters handed out to the ranks).  Green on 2 and 4 B200
+(profiles/r2_mgpu_tests_{2,4}gpu.txt)."""
 import os
 import subprocess
 import sys
@@ -11,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.gpu
 def test_remove_edges_across_ranks(cuda):
-    """removeedges_alltoall! (src/MPI.jl:432-479): written after round 1's GPU budget was spent, not run on GPUs yet"""
+    """removeedges_alltoall! (src/MPI.jl:432-479): """
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
@@ -21,7 +22,7 @@ def test_remove_edges_across_ranks(cuda):
 
 @pytest.mark.gpu
 def test_finish_init_distribute_across_ranks(cuda):
-    """finish_init!(distribute = true) (src/MPI.jl:11-84): written after round 1's GPU budget was spent, not run on GPUs yet"""
+    """finish_init!(distribute = true) (src/MPI.jl:11-84): """
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
@@ -31,7 +32,7 @@ def test_finish_init_distribute_across_ranks(cuda):
 
 @pytest.mark.gpu
 def test_core_jl_across_ranks(cuda):
-    """test/core.jl under mpiexec (test/mpi/test_core.jl): written after round 1's GPU budget was spent, not run on GPUs yet"""
+    """test/core.jl under mpiexec (test/mpi/test_core.jl): """
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
@@ -41,9 +42,20 @@ def test_core_jl_across_ranks(cuda):
 
 @pytest.mark.gpu
 def test_agentstate_jl_across_ranks(cuda):
-    """test/mpi/test_agentstate.jl: written after round 1's GPU budget was spent, not run on GPUs yet"""
+    """test/mpi/test_agentstate.jl: """
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     from mgpu_common import run_ranks
     run_ranks("mgpu_agentstate.py", 29537)
+
+
+@pytest.mark.gpu
+def test_raster_handed_out_game_of_life_across_ranks(cuda):
+    """broadcastids + join (src/MPI.jl:59-73,492-517; src/Raster.jl:64-75,227,318,378): the cells of a raster are handed out, rastervalues /
+    calc_raster join the ranks; Game of Life on 2-4 ranks against numpy and the single-rank oracle"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    from mgpu_common import run_ranks
+    run_ranks("mgpu_gol.py", 29539)

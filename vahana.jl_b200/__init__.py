@@ -105,7 +105,7 @@ ABI_SYMBOLS = [
     "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce", "vb_mapreduce_fn",
     "vb_rastervalues", "vb_calc_raster_num_edges", "vb_calc_rasterstate_fn", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
     "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes", "vb_set_uniform_offset", "vb_add_agent_per_process",
-    "vb_last_apply_blocks", "vb_set_read_blocking", "vb_set_read_prefilter", "vb_last_apply_prefiltered", "vb_last_pass_rate",
+    "vb_last_apply_blocks", "vb_set_read_blocking", "vb_set_read_prefilter", "vb_last_apply_prefiltered", "vb_last_pass_rate", "vb_set_raster",
 ]
 
 
@@ -254,6 +254,43 @@ def plan_distribution(agents: dict, edges: dict, world: int, partition: Optional
 def remove_process(aid: int) -> int:
     """remove_process (src/Agent.jl:81-82): the id with its rank bits cleared"""
     return int(aid) & ~(((1 << BITS_PROCESS) - 1) << SHIFT_RANK)
+
+
+def raster_stencil(metric: str, ndims: int, distance: float):
+    """_stencil_core (src/Raster.jl:82-96): the offsets within `distance` under `metric`, the first dimension running fastest, the
+    centre left out"""
+    d = int(np.floor(distance))
+    if d < 0:
+        return np.zeros((0, ndims), dtype=np.int64)
+    axes = [np.arange(-d, d + 1, dtype=np.int64)] * ndims
+    grid = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, ndims, order="F")      # first dimension fastest
+    keep = (grid != 0).any(axis=1)
+    if metric == "euclidean":
+        keep &= np.sqrt((grid * grid).sum(axis=1).astype(np.float64)) <= distance
+    elif metric == "manhatten":
+        keep &= np.abs(grid).sum(axis=1).astype(np.float64) <= distance
+    return grid[keep]
+
+
+def raster_neighbor_edges(dims, cell_ids, distance=1, metric: str = "chebyshev", periodic: bool = True):
+    """The edges connect_raster_neighbors! adds (src/Raster.jl:139-167), in its order: for every cell `org` in CartesianIndices order
+    and every stencil offset o, an edge FROM the cell at org TO the cell at org + o (wrapped on a periodic raster, dropped when it
+    leaves a clipped one).  Returns (from ids, to ids)."""
+    dims = tuple(int(x) for x in dims)
+    nd, n = len(dims), int(np.prod(dims))
+    cell_ids = np.asarray(cell_ids, dtype=np.uint64).reshape(-1)
+    st = raster_stencil(metric, nd, distance)
+    pos = np.stack(np.unravel_index(np.arange(n), dims, order="F"), axis=1).astype(np.int64)          # 0-based positions, column-major order
+    sh = pos[:, None, :] + st[None, :, :]                                                              # [cell, offset, dim]
+    dd = np.array(dims, dtype=np.int64)
+    inside = ((sh >= 0) & (sh < dd)).all(axis=2)
+    keep = np.ones(inside.shape, dtype=bool) if periodic else inside
+    sh = np.mod(sh, dd)
+    strides = np.concatenate([[1], np.cumprod(dd[:-1])]).astype(np.int64)
+    lin = (sh * strides).sum(axis=2)
+    fr = np.broadcast_to(cell_ids[:, None], lin.shape)[keep]
+    to = cell_ids[lin[keep]]
+    return np.ascontiguousarray(fr), np.ascontiguousarray(to)
 
 
 def updateids(idmapping, oldids):
@@ -647,7 +684,6 @@ class Simulation:
     def add_raster(self, name: str, dims: Sequence[int], type_name: str, agent_constructor) -> np.ndarray:
         """add_raster!(sim, name, dims, agent_constructor): the constructor is called with the 1-based position
         tuple of every cell in CartesianIndices (column-major) order, or is an array of states in that order."""
-        self._unstageable = "add_raster"   # rasters are not handed out by finish_init(distribute=True) yet (broadcastids, src/MPI.jl:64-75)
         dims = tuple(int(d) for d in dims)
         if not hasattr(self, "_rasters"):
             self._rasters = {}
@@ -667,6 +703,9 @@ class Simulation:
         self._ck(self.lib.vb_add_raster(self.h, name.encode(), C.c_int(len(dims)), d, C.c_int(self._aid[type_name]),
                                         states.ctypes.data_as(C.c_void_p) if states is not None else None,
                                         ids.ctypes.data_as(C.c_void_p)))
+        if self._stage is not None:     # the cells are agents like any other; the id grid is handed out by finish_init (broadcastids)
+            self._stage["agents"].setdefault(self._aid[type_name], []).append((ids.copy(), None if states is None else states.copy()))
+            self._stage.setdefault("rasters", {})[name] = (dims, self._aid[type_name], ids.copy())
         return ids.reshape(dims, order="F")
 
     def connect_raster_neighbors(self, name: str, edge_name: str, edge_state=None, distance=1, metric: str = "chebyshev",
@@ -678,10 +717,22 @@ class Simulation:
         self._ck(self.lib.vb_connect_raster_neighbors(self.h, name.encode(), C.c_int(self._eid[edge_name]), C.c_double(float(distance)),
                                                       C.c_int(_METRICS[metric]), C.c_int(int(periodic)),
                                                       buf.ctypes.data_as(C.c_void_p) if buf is not None else None))
+        if self._stage is not None:
+            if name in self._stage.get("rasters", {}):
+                # stage the edges the engine just added (it keeps a raster stencil implicit) in the reference's add order:
+                # cells in CartesianIndices order, per cell the stencil offsets in _stencil_core order (src/Raster.jl:82-110,139-167)
+                dims, _tid, cells = self._stage["rasters"][name]
+                fr, to = raster_neighbor_edges(dims, cells, distance, metric, periodic)
+                st = None if buf is None else np.broadcast_to(buf, (fr.shape[0],)).copy()
+                self._stage["edges"].setdefault(edge_name, []).append((fr, to, st))
+            else:
+                self._unstageable = "connect_raster_neighbors on a raster that was not added through add_raster"
 
     def move_to(self, name: str, aid: int, pos, edge_from_raster: Optional[str], edge_to_raster: Optional[str],
                 state_from=None, state_to=None, distance=0, metric: str = "chebyshev", periodic: bool = True,
                 only_surrounding: bool = False):
+        if self._stage is not None:
+            self._unstageable = "move_to in the initialisation phase"      # (its edges are added inside the engine; not handed out yet)
         p = (C.c_int64 * len(pos))(*[int(x) for x in pos])
 
         def sb(ename, st):
@@ -774,11 +825,14 @@ class Simulation:
                 edges[name] = (np.concatenate([c[0] for c in chunks]), np.concatenate([c[1] for c in chunks]),
                                None if chunks[0][2] is None else np.concatenate([c[2] for c in chunks]))
             shards, old, new, bounds = plan_distribution(agents, edges, world, partition or None)
-            meta = [(old, new, bounds)]
+            rasters = {}
+            for rname, (dims, tid, ids) in self._stage.get("rasters", {}).items():      # broadcastids (src/MPI.jl:59-73): the grids with the new ids
+                rasters[rname] = (dims, tid, new[np.searchsorted(old, ids)])
+            meta = [(old, new, bounds, rasters)]
         mine = [None]
         dist.scatter_object_list(mine, shards, src=0)
         dist.broadcast_object_list(meta, src=0)
-        old, new, bounds = meta[0]
+        old, new, bounds, rasters = meta[0]
         shard = mine[0]
         # rebuild: the initialisation phase of this rank is replaced by its shard
         self.lib.vb_sim_destroy(self.h)
@@ -795,6 +849,13 @@ class Simulation:
         for name, (fr, to, states) in shard["edges"].items():
             if to.shape[0]:
                 self.add_edges(fr, to, name, states)
+        for rname, (dims, tid, ids) in rasters.items():        # every rank knows the whole id grid; its read-outs join the ranks
+            d = (C.c_int64 * len(dims))(*dims)
+            ids = np.ascontiguousarray(ids, dtype=np.uint64)
+            self._ck(self.lib.vb_set_raster(self.h, rname.encode(), C.c_int(len(dims)), d, C.c_int(tid), ids.ctypes.data_as(C.c_void_p)))
+            if not hasattr(self, "_rasters"):
+                self._rasters = {}
+            self._rasters[rname] = tuple(dims)
         return dict(zip(old.tolist(), new.tolist())) if want_mapping else None
 
     # -- apply! (src/Simulation.jl:720-821) --

@@ -66,6 +66,7 @@ struct Nccl {
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, int /*ncclRedOp_t: 0 = sum*/, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
         if (h) return true;
@@ -76,7 +77,7 @@ struct Nccl {
 #define VB_SYM(field, name) field = (decltype(field))dlsym(h, name); if (!field) return false;
         VB_SYM(GetUniqueId, "ncclGetUniqueId") VB_SYM(CommInitRank, "ncclCommInitRank") VB_SYM(CommDestroy, "ncclCommDestroy")
         VB_SYM(Send, "ncclSend") VB_SYM(Recv, "ncclRecv") VB_SYM(GroupStart, "ncclGroupStart") VB_SYM(GroupEnd, "ncclGroupEnd")
-        VB_SYM(AllGather, "ncclAllGather") VB_SYM(GetErrorString, "ncclGetErrorString")
+        VB_SYM(AllGather, "ncclAllGather") VB_SYM(AllReduce, "ncclAllReduce") VB_SYM(GetErrorString, "ncclGetErrorString")
 #undef VB_SYM
         return true;
     }
@@ -839,10 +840,10 @@ __global__ void comp_to_id_kernel(const uint32_t* __restrict__ comp, uint64_t n,
     if (slot >= a.old_lcap[t] && a.remap[t]) ids[i] = reinterpret_cast<const uint64_t*>(a.remap[t])[slot - a.old_lcap[t]];
     else ids[i] = vb::agent_id(t, rank, (uint64_t)slot + 1);
 }
-__global__ void raster_cells_kernel(const uint64_t* __restrict__ ids, uint64_t n, uint32_t* __restrict__ cells, const RebaseArgs a) {
+__global__ void raster_cells_kernel(const uint64_t* __restrict__ ids, uint64_t n, uint32_t* __restrict__ cells, const RebaseArgs a, uint32_t rank) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    cells[i] = a.new_base[vb::type_nr(ids[i])] + (uint32_t)(vb::agent_nr(ids[i]) - 1);
+    cells[i] = vb::process_nr(ids[i]) == rank ? a.new_base[vb::type_nr(ids[i])] + (uint32_t)(vb::agent_nr(ids[i]) - 1) : 0xffffffffu;
 }
 
 // mapreduce (src/AgentMethods.jl:533-565, src/EdgeMethods.jl:972-994): map = field at byte offset (optionally
@@ -937,6 +938,7 @@ __global__ void field_out_kernel(const uint8_t* __restrict__ cols, uint32_t stri
                                  uint64_t n, int offset, uint32_t fsize, uint8_t* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (cells[i] == 0xffffffffu) { for (uint32_t b = 0; b < fsize; ++b) out[i * fsize + b] = 0; return; }     // a cell of another rank (joined afterwards)
     const uint32_t s = cells[i] - cbase;
     for (uint32_t b = 0; b < fsize; ++b) {
         const uint32_t p = offset + b, c = p / word;
@@ -948,7 +950,7 @@ __global__ void raster_num_edges_kernel(const uint32_t* __restrict__ cells, uint
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t r = cells[i] - row_shift;
-    out[i] = r < rows ? (off ? (long long)(off[r + 1] - off[r]) : (long long)cnt[r]) : 0;
+    out[i] = (cells[i] != 0xffffffffu && r < rows) ? (off ? (long long)(off[r + 1] - off[r]) : (long long)cnt[r]) : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1097,7 +1099,9 @@ struct RasterStore {
     std::vector<int64_t> dims;
     int type = 0;
     std::vector<uint64_t> ids;    // host copy (column-major)
-    uint32_t* cells = nullptr;    // device composite indices (rebuilt when bases change)
+    uint32_t* cells = nullptr;    // device composite indices (rebuilt when bases change); 0xffffffff = a cell of another rank
+    uint64_t* cell_ids = nullptr; // device copy of `ids`, kept when the cells are spread over the ranks (vb_set_raster)
+    bool distributed = false;     // read-outs join the ranks (collective)
 };
 
 }  // namespace
@@ -1224,7 +1228,7 @@ void free_chunks(EdgeStore& e) {
 vb_sim::~vb_sim() {
     for (auto& a : agents) free_agent(a);
     for (auto& e : edges) { free_edge_read(e); free_edge_log(e); free_chunks(e); dfree(e.st_off); dfree(e.heavy_rows); free_blocked(e); }
-    for (auto& r : rasters) dfree(r.cells);
+    for (auto& r : rasters) { dfree(r.cells); dfree(r.cell_ids); }
     dfree(d_error); dfree(d_scalars); dfree(d_stats);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : evk) if (e) cudaEventDestroy(e);
@@ -1351,9 +1355,9 @@ void vb_sim::rebase(const uint32_t* old_base, const uint32_t* old_lcap, const ui
         if (!r.cells) r.cells = dalloc<uint32_t>(r.ids.size());
         uint64_t* tmp = dalloc<uint64_t>(r.ids.size());
         CK(cudaMemcpyAsync(tmp, r.ids.data(), r.ids.size() * 8, cudaMemcpyHostToDevice, g_stream));
-        raster_cells_kernel<<<nblk(r.ids.size()), 256, 0, g_stream>>>(tmp, r.ids.size(), r.cells, ra); LAUNCH_CHECK();
+        raster_cells_kernel<<<nblk(r.ids.size()), 256, 0, g_stream>>>(tmp, r.ids.size(), r.cells, ra, rank); LAUNCH_CHECK();
         CK(cudaStreamSynchronize(g_stream));
-        dfree(tmp);
+        if (r.distributed && !r.cell_ids) r.cell_ids = tmp; else dfree(tmp);
     }
 }
 
@@ -1398,7 +1402,7 @@ void vb_sim::upload_view(uint64_t seed) {
     }
     for (size_t i = 0; i < rasters.size(); ++i) {
         vb::RasterView& v = h.rasters[i];
-        v.cells = rasters[i].cells; v.ndims = (int)rasters[i].dims.size(); v.type = rasters[i].type;
+        v.cells = rasters[i].cells; v.cell_ids = rasters[i].cell_ids; v.ndims = (int)rasters[i].dims.size(); v.type = rasters[i].type;
         uint64_t st = 1;
         for (int k = 0; k < vb::MAX_RASTER_DIMS; ++k) { v.dim32[k] = 1; v.stride32[k] = 0; }
         for (size_t k = 0; k < rasters[i].dims.size(); ++k) { v.dims[k] = rasters[i].dims[k]; v.dim32[k] = (uint32_t)rasters[i].dims[k]; v.stride32[k] = (uint32_t)st; st *= (uint64_t)rasters[i].dims[k]; }
@@ -3293,6 +3297,11 @@ int vb_comm_init(int rank, int nranks, const uint8_t* idbytes) {
         std::memcpy(&id, idbytes, 128);
         NK(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
         g_rank = rank; g_nranks = nranks;
+        // NCCL connects its channels on the first collective (seconds on 8 GPUs): do that here, once, instead of inside the first
+        // finish_init! (the scaling bench's build time grew with the rank count for that reason)
+        std::vector<uint64_t> warm;
+        const uint64_t me = (uint64_t)rank;
+        allgather8_host(&me, warm);
     });
 }
 int vb_comm_rank(int* r, int* n) { *r = g_rank; *n = g_nranks; return VB_OK; }
@@ -3609,7 +3618,35 @@ int vb_add_raster(vb_sim* s, const char* name, int ndims, const int64_t* dims, i
     });
 }
 
+int vb_set_raster(vb_sim* s, const char* name, int ndims, const int64_t* dims, int type, const vb_agent_id* ids) {
+    return guard([&] {   // broadcastids (src/MPI.jl:59-73): the id grid of a raster whose cells were handed out to the ranks
+        if (s->initialized) throw AssertionError("rasters can only be defined before finish_init!");
+        if (ndims < 1 || ndims > vb::MAX_RASTER_DIMS) throw ArgError("rasters with 1..4 dimensions are supported");
+        if (s->rasters.size() >= vb::MAX_RASTERS) throw ArgError("too many rasters (MAX_RASTERS)");
+        RasterStore r;
+        r.name = name; r.dims.assign(dims, dims + ndims); r.type = type;
+        uint64_t n = 1;
+        for (int i = 0; i < ndims; ++i) n *= (uint64_t)dims[i];
+        r.ids.assign(ids, ids + n);
+        for (uint64_t i = 0; i < n; ++i) {
+            if ((int)vb::type_nr(ids[i]) != type) throw AssertionError("vb_set_raster: a cell id of another agent type");
+            if (vb::process_nr(ids[i]) == s->rank && vb::agent_nr(ids[i]) >= s->A(type).nextid) throw AssertionError("vb_set_raster: a cell id that names no agent of this rank");
+        }
+        r.distributed = g_nranks > 1;
+        s->rasters.push_back(std::move(r));
+        uint32_t ob[vb::MAX_AGENT_TYPES + 2];
+        std::memcpy(ob, s->base, sizeof(ob));
+        s->rebase(ob);   // builds the device cell table (cells of other ranks are marked) and keeps the id table on the device
+    });
+}
+
 namespace {
+// Raster read-outs of a distributed raster: every rank has filled in the cells it owns and zeros elsewhere; the byte-wise sum over the
+// ranks is the joined array (exactly one rank contributes to a byte, so nothing carries).  join(), src/MPI.jl:492-517.  Collective.
+void raster_join(const RasterStore& r, void* dev, size_t bytes) {
+    if (!r.distributed || g_nranks <= 1 || !bytes) return;
+    NK(g_nccl.AllReduce(dev, dev, bytes, ncclUint8, 0 /* ncclSum */, g_comm, g_stream));
+}
 // host-side stencil enumeration for the init-phase helpers (Raster.jl:82-110)
 std::vector<std::vector<int64_t>> stencil(int metric, int n, double distance) {
     int64_t d = (int64_t)std::floor(distance);
@@ -4204,6 +4241,7 @@ int vb_rastervalues(vb_sim* s, const char* name, int offset, int dt, void* out) 
         const size_t w = dt_size(dt), n = r.ids.size();
         uint8_t* tmp = (uint8_t*)g_pool.alloc(n * w);
         field_out_kernel<<<nblk(n), 256, 0, g_stream>>>(a.rstate(), a.stride(), a.word, r.cells, s->base[r.type], n, offset, (uint32_t)w, tmp); LAUNCH_CHECK();
+        raster_join(r, tmp, n * w);
         CK(cudaMemcpyAsync(out, tmp, n * w, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
         dfree(tmp);
@@ -4225,6 +4263,7 @@ int vb_calc_rasterstate_fn(vb_sim* s, const char* name, const char* map_name, in
         vb::MapCellsArgs ca{};
         ca.cols = a.rstate(); ca.stride = a.stride(); ca.cells = r.cells; ca.cbase = s->base[r.type]; ca.n = n; ca.out = tmp; ca.stream = g_stream;
         CK(mi->launch_cells(ca)); ++g_launches;
+        raster_join(r, tmp, n * 8);
         CK(cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
         dfree(tmp);
@@ -4249,8 +4288,14 @@ int vb_calc_raster_num_edges(vb_sim* s, const char* name, int ei, int64_t* out) 
         }
         long long* tmp = dalloc<long long>(n);
         const uint32_t shift = e.singletype ? s->base[e.target] : 0;
-        if (e.singletype && e.target != r.type) { std::memset(out, 0, n * 8); dfree(tmp); return; }
+        if (e.singletype && e.target != r.type) {
+            CK(cudaMemsetAsync(tmp, 0, n * 8, g_stream));
+            raster_join(r, tmp, n * 8);               // (collective on a distributed raster: every rank takes part)
+            CK(cudaStreamSynchronize(g_stream));
+            std::memset(out, 0, n * 8); dfree(tmp); return;
+        }
         raster_num_edges_kernel<<<nblk(n), 256, 0, g_stream>>>(r.cells, n, e.kind == vb::KIND_CSR ? e.off : nullptr, e.cnt, e.rows, shift, tmp); LAUNCH_CHECK();
+        raster_join(r, tmp, n * 8);
         CK(cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
         dfree(tmp);
