@@ -1630,7 +1630,7 @@ template <class T> __device__ __forceinline__ T shfl_any(const T& v, uint32_t sr
     for (int i = 0; i < NW; ++i) b.w[i] = __shfl_sync(0xffffffffu, a.w[i], src);
     return b.t;
 }
-template <class F, int RY>
+template <class F, int RY, bool PERIODIC>
 __global__ void __launch_bounds__(256) reduce_stencil_strip_kernel(const __grid_constant__ KernelArgs ka) {
     typedef typename F::State State;
     typedef typename F::Acc Acc;
@@ -1645,7 +1645,7 @@ __global__ void __launch_bounds__(256) reduce_stencil_strip_kernel(const __grid_
     const uint32_t strips = (nx + 29) / 30, bands = (ny + RY - 1) / RY;
     if (warp >= strips * bands) return;
     const uint32_t sx = warp % strips, by = warp / strips;
-    const bool periodic = ev.st_periodic != 0;
+    constexpr bool periodic = PERIODIC;                                     // a periodic raster has no invalid neighbours: the tests below fold away
     const int32_t xs = (int32_t)(sx * 30) - 1 + (int32_t)lane;              // the column this lane carries (lanes 0 / 31: halo)
     const bool xin = xs >= 0 && (uint32_t)xs < nx;
     const uint32_t x = (uint32_t)((xs % (int32_t)nx + (int32_t)nx) % (int32_t)nx);
@@ -1661,11 +1661,13 @@ __global__ void __launch_bounds__(256) reduce_stencil_strip_kernel(const __grid_
     State up = row(y0 ? y0 - 1 : ny - 1), mid = row(y0);
     State upl = shfl_any(up, (lane + 31) & 31), upr = shfl_any(up, (lane + 1) & 31);
     State midl = shfl_any(mid, (lane + 31) & 31), midr = shfl_any(mid, (lane + 1) & 31);
-    const bool lv = __shfl_sync(0xffffffffu, (int)xvalid, (lane + 31) & 31) != 0, rvd = __shfl_sync(0xffffffffu, (int)xvalid, (lane + 1) & 31) != 0;
+    const bool lv = periodic || __shfl_sync(0xffffffffu, (int)xvalid, (lane + 31) & 31) != 0, rvd = periodic || __shfl_sync(0xffffffffu, (int)xvalid, (lane + 1) & 31) != 0;
     uint32_t nedges = 0;
+    State nxt = row(y0 + 1 < ny ? y0 + 1 : 0);                              // the row below is loaded one iteration ahead of its use
     for (uint32_t y = y0; y < y1; ++y) {
         const bool dnv = periodic || y + 1 < ny;
-        const State dn = row(y + 1 < ny ? y + 1 : 0);
+        const State dn = nxt;
+        if (y + 1 < y1) nxt = row(y + 2 < ny ? y + 2 : y + 2 - ny);
         const State dnl = shfl_any(dn, (lane + 31) & 31), dnr = shfl_any(dn, (lane + 1) & 31);
         if (owner) {
             const uint32_t idx = y * nx + x;
@@ -1709,7 +1711,8 @@ cudaError_t launch_stencil(const LaunchArgs& la) {
             if (ok) {
                 constexpr int RY = 32;
                 const unsigned long long warps = (unsigned long long)((rv.dim32[0] + 29) / 30) * ((rv.dim32[1] + RY - 1) / RY);
-                reduce_stencil_strip_kernel<F, RY><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, la.stream>>>(ka);
+                if (ev.st_periodic) reduce_stencil_strip_kernel<F, RY, true><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, la.stream>>>(ka);
+                else reduce_stencil_strip_kernel<F, RY, false><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, la.stream>>>(ka);
                 return cudaGetLastError();
             }
         }
