@@ -162,7 +162,9 @@ def run_reference(args):
         "impl": "reference", "metric": "edges/sec per apply! (Hegselmann-Krause read+write phase)", "value": eps_, "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "hk-powerlaw (BASELINE config 4)", "agents": int(args.agents), "eps": EPS, "note": "oracle restatement of the reference's CPU apply!, not Julia (Julia/MPI are not installed in this image)"},
+        "config": {"workload": "hk-powerlaw: a bounded SAMPLE of BASELINE config 4's generator (%d independent shards of %d agents, no halo), not the 100M-agent graph" % (cores, n),
+                   "agents": int(cores * n), "agents_of_the_gpu_arm": int(args.agents), "eps": EPS,
+                   "note": "oracle restatement of the reference's CPU apply!, not Julia (Julia/MPI are not installed in this image); each shard's gathered state (2 MB) sits in the CPU's caches, so this is an upper bound of the CPU path"},
         "cpu_baseline": {"value": eps_, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": eps_, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
