@@ -42,7 +42,7 @@
 
 namespace vb {
 
-enum : int { MAX_AGENT_TYPES = 16, MAX_EDGE_TYPES = 32, MAX_RASTERS = 4, MAX_PARAM_BYTES = 512 };
+enum : int { MAX_AGENT_TYPES = 48, MAX_EDGE_TYPES = 64, MAX_RASTERS = 4, MAX_PARAM_BYTES = 512 };   // the view travels in the kernel parameter block (<= 32 764 B)
 enum : int { MAX_EDGE_WRITES = 6, MAX_AGENT_WRITES = 3, MAX_EDGE_REMOVES = 3 };
 enum EdgeKind : uint8_t { KIND_CSR = 0, KIND_COUNT = 1, KIND_FLAG = 2, KIND_STENCIL = 3 };
 enum : int { MAX_IMPLICIT_STENCIL = 32 };

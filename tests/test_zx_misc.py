@@ -108,10 +108,10 @@ def test_nonmutating_apply(backend):  # src/Simulation.jl:847-856: apply = copy_
     sim.finish_simulation()
 
 
-def test_duration_log_in_the_reference_format(oracle, tmp_path):  # src/Logging.jl:30-103: <Begin>/<End> pairs -> "x |#| Duration (ms)"
+def test_duration_log_in_the_reference_format(backend, tmp_path):  # src/Logging.jl:30-103: <Begin>/<End> pairs -> "x |#| Duration (ms)"
     import re
     from models import core_model, add_example_network
-    sim = vh.create_simulation(core_model(), backend=oracle, logging=True, log_path=str(tmp_path))
+    sim = vh.create_simulation(core_model(), backend=backend, logging=True, log_path=str(tmp_path))
     add_example_network(sim)
     sim.finish_init()
     sim.apply("identity", "AMortal", ["AMortal"], ["AMortal"])
@@ -127,11 +127,11 @@ def test_duration_log_in_the_reference_format(oracle, tmp_path):  # src/Logging.
     assert all(float(r[2]) >= 0 for r in recs) and float(recs[0][0]) <= float(recs[1][0]) <= float(recs[2][0])
 
 
-def test_graph_bridges(oracle):
+def test_graph_bridges(backend):
     """add_graph! from a graph object and vahanagraph (src/GraphsSupport.jl:34-57,212-289; test/graphs.jl:37-43: K4 id sums)"""
     import networkx as nx
     from models import hk_model
-    sim = vh.create_simulation(hk_model(), backend=oracle)
+    sim = vh.create_simulation(hk_model(), backend=backend)
     g = nx.complete_graph(4)
     ids = vh.add_graph(sim, g, None, "HKAgent", np.arange(4.0).view([("opinion", "f8")]), "Knows")
     sim.finish_init()
@@ -142,7 +142,7 @@ def test_graph_bridges(oracle):
     back = vh.to_networkx(sim)
     assert back.number_of_nodes() == 4 and back.number_of_edges() == 12 and back.nodes[2]["id"] == int(ids[2])
     d = nx.DiGraph([(0, 1), (1, 2), (2, 0), (0, 1)])            # a directed graph: one Vahana edge per graph edge
-    sim2 = vh.create_simulation(hk_model(), backend=oracle)
+    sim2 = vh.create_simulation(hk_model(), backend=backend)
     vh.add_graph(sim2, d, None, "HKAgent", np.zeros(3).view([("opinion", "f8")]), "Knows")
     sim2.add_edges(sim2.all_agentids("HKAgent")[:1], sim2.all_agentids("HKAgent")[1:2], "Knows")    # a parallel edge 0 -> 1
     sim2.finish_init()
@@ -150,11 +150,11 @@ def test_graph_bridges(oracle):
     assert len(vh.vahanagraph(sim2, drop_multiedges=True)["src"]) == 3
 
 
-def test_show_and_dataframes(oracle):
+def test_show_and_dataframes(backend):
     """show(sim) (src/REPL.jl:81-168), DataFrame(sim, T) and GlobalsDataFrame(sim) (src/optional/DataFrames.jl:54-185)"""
     from models import market_inputs, market_sim, market_step
     buyers, sellers, picks = market_inputs(20, 3, 2, seed=1)
-    sim = market_sim(oracle, buyers, sellers, picks)
+    sim = market_sim(backend, buyers, sellers, picks)
     for step in range(3):
         market_step(sim, step)
     text = sim.show()
@@ -172,7 +172,7 @@ def test_show_and_dataframes(oracle):
     assert list(g.columns) == ["x_minus_y", "p"] and len(g) == 3
     # a simulation that is still being initialised says so, a raster is listed with its dimensions
     from models import hk_model
-    s2 = vh.create_simulation(hk_model(), backend=oracle)
+    s2 = vh.create_simulation(hk_model(), backend=backend)
     assert "Still in initialization process!." in s2.show() and ":eps : 0.02" in s2.show()
 
 

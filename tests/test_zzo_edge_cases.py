@@ -62,3 +62,38 @@ def test_empty_inputs_gpu(cuda):
 @pytest.mark.gpu
 def test_ragged_rows_gpu(cuda):
     _ragged_checks(cuda)
+
+
+def test_many_types(backend):
+    """40 agent types and 50 edge types in one model (the reference allows 255 types, src/Agent.jl:30-64; this build 48 / 64): ids carry
+    the right type number, rows of every edge type are kept apart, queries work for the last type as for the first."""
+    t = vh.ModelTypes()
+    for k in range(40):
+        t.register_agenttype(f"A{k}", [("foo", "i8")], *(["Immortal"] if k % 2 else []))
+    for k in range(50):
+        t.register_edgetype(f"E{k}", [("foo", "i8")] if k % 3 == 0 else None, *([] if k % 3 == 0 else ["Stateless"]))
+    sim = vh.create_simulation(vh.create_model(t, "many types"), backend=backend)
+    ids = {}
+    for k in range(40):
+        ids[k] = sim.add_agents(f"A{k}", foos(range(10 * k, 10 * k + 3 + k % 4)))
+        assert all(vh.type_nr(int(i)) == k + 1 for i in ids[k])
+    for k in range(50):
+        a, b = ids[k % 40], ids[(k * 7 + 1) % 40]
+        fr = np.array([a[j % len(a)] for j in range(5)], dtype=np.uint64)
+        to = np.array([b[(2 * j) % len(b)] for j in range(5)], dtype=np.uint64)
+        sim.add_edges(fr, to, f"E{k}", np.arange(5) + k if k % 3 == 0 else None)
+    sim.finish_init()
+    for k in range(40):
+        assert sim.num_agents(f"A{k}") == 3 + k % 4
+        assert sim.mapreduce("foo", "+", f"A{k}") == sum(range(10 * k, 10 * k + 3 + k % 4))
+    sim.disable_transition_checks(True)
+    for k in range(50):
+        assert sim.num_edges(f"E{k}") == 5
+        b = ids[(k * 7 + 1) % 40]
+        a = ids[k % 40]
+        got = sim.neighborids(int(b[0]), f"E{k}")
+        want = [int(a[j % len(a)]) for j in range(5) if (2 * j) % len(b) == 0]
+        assert [int(x) for x in got] == want, (k, got, want)
+    sim.disable_transition_checks(False)
+    for k in range(0, 50, 3):
+        assert sim.mapreduce("foo", "+", f"E{k}") == sum(range(k, k + 5))
