@@ -1709,7 +1709,28 @@ void vb_sim::build_container(int ei, bool add_existing) {
         }
         dfree(flag); dfree(pos); dfree(scr);
     }
-    // --- row counts of the new entries -> offsets ---
+    if (!have_old) {
+        // --- the sorted log becomes the container: its offsets come straight from the sorted keys (no counts, no scan over the rows) ---
+        uint32_t* off = dalloc<uint32_t>((size_t)rows + 2);
+        if (n == 0) CK(cudaMemsetAsync(off, 0, ((size_t)rows + 2) * 4, g_stream));
+        else {
+            uint32_t* gaps = dalloc<uint32_t>(3 * ((size_t)rows / 32 + 2) + 1);
+            uint32_t* gap_count = d_scalars + 2;
+            CK(cudaMemsetAsync(gap_count, 0, 4, g_stream));
+            vbp::csr_offsets_kernel<<<nblk((uint64_t)n + 1), 256, 0, g_stream>>>(skey, n, rows, off, gaps, gap_count); LAUNCH_CHECK();
+            vbp::csr_offset_gaps_kernel<<<296, 256, 0, g_stream>>>(off, gaps, gap_count); LAUNCH_CHECK();
+            CK(cudaMemsetAsync(off + rows + 1, 0, 4, g_stream));
+            dfree(gaps);
+        }
+        CK(cudaGetLastError());
+        free_edge_read(e);
+        e.off = off; e.rows = rows; e.nnz = n;
+        e.src = e.log_from; e.st = e.log_st; e.st_cap = e.log_cap;       // the sorted log becomes the container
+        e.log_from = nullptr; e.log_st = nullptr;
+        dfree(e.log_to); e.log_to = nullptr; e.log_n = 0; e.log_cap = 0;
+        return;
+    }
+    // --- add_existing: row counts of the new entries -> run offsets, merged with the old rows ---
     uint32_t* ncnt = dalloc<uint32_t>((size_t)rows + 2);
     CK(cudaMemsetAsync(ncnt, 0, ((size_t)rows + 2) * 4, g_stream));
     if (n) { vbp::csr_run_counts_kernel<<<nblk(n), 256, 0, g_stream>>>(skey, n, ncnt); LAUNCH_CHECK(); }

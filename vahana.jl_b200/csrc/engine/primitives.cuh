@@ -491,6 +491,28 @@ static __global__ void csr_run_counts_kernel(const uint32_t* __restrict__ keys, 
     if (i == 0 || keys[i - 1] != k) atomicSub(&cnt[k], (uint32_t)i);
     if (i == n - 1 || keys[i + 1] != k) atomicAdd(&cnt[k], (uint32_t)i + 1u);
 }
+// ---- CSR offsets straight from the sorted keys: off[r] = first position whose key is >= r (off[rows] = n).  Thread i looks at the
+//      boundary between keys[i - 1] and keys[i] (i = 0: before the first key, i = n: behind the last one) and writes the offsets of the
+//      rows that start there.  No atomics, no counts, no scan over the rows.  A boundary that skips more than 32 empty rows is parked
+//      in `gaps` ((first row, last row, value) triples, at most rows / 32 + 2 of them) and filled by csr_offset_gaps_kernel. ------------
+static __global__ void csr_offsets_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t rows, uint32_t* __restrict__ off,
+                                          uint32_t* __restrict__ gaps, uint32_t* __restrict__ gap_count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const uint32_t cur = i < n ? __ldcs(keys + i) : rows;
+    uint32_t lo = 0;
+    if (i) { const uint32_t prev = __ldcs(keys + i - 1); if (prev == cur) return; lo = prev + 1; }
+    if (cur - lo < 32u) { for (uint32_t r = lo; r <= cur; ++r) off[r] = (uint32_t)i; return; }
+    const uint32_t g = atomicAdd(gap_count, 1u);
+    gaps[3 * g] = lo; gaps[3 * g + 1] = cur; gaps[3 * g + 2] = (uint32_t)i;
+}
+static __global__ void csr_offset_gaps_kernel(uint32_t* __restrict__ off, const uint32_t* __restrict__ gaps, const uint32_t* __restrict__ gap_count) {
+    const uint32_t ng = *gap_count;
+    for (uint32_t g = blockIdx.x; g < ng; g += gridDim.x) {
+        const uint32_t lo = gaps[3 * g], hi = gaps[3 * g + 1], v = gaps[3 * g + 2];
+        for (uint64_t r = (uint64_t)lo + threadIdx.x; r <= hi; r += blockDim.x) off[r] = v;
+    }
+}
 static __global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

@@ -443,6 +443,20 @@ function move_to!(sim::Simulation, name::Symbol, id::AgentID, pos, edge_from_ras
                                    et, rt === nothing ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, rt), distance, METRICS[metric], periodic, only_surrounding))
     nothing
 end
+"""broadcastids (src/MPI.jl:59-73, src/Raster.jl:64-75), receiver side: a raster over agents that exist already, `ids` in CartesianIndices
+order; after finish_init!(distribute = true) some of them live on other ranks and the raster's read-outs join the ranks"""
+function set_raster!(sim::Simulation, name::Symbol, ids::Array{AgentID,N}, ::Type{T}) where {N,T}
+    d = Int64[size(ids)...]
+    check(ccall((:vb_set_raster, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint, Ptr{Int64}, Cint, Ptr{AgentID}), sim.handle, string(name), N, d, typeid(sim, T), ids))
+    sim.rasters[name] = (size(ids), T)
+    nothing
+end
+"share of sampled edges whose source key passed the prefilter at the last check (negative: never checked); engine-side policy, no reference counterpart"
+function last_pass_rate(sim::Simulation)
+    r = Ref{Float64}(-1.0)
+    check(ccall((:vb_last_pass_rate, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}), sim.handle, r))
+    r[]
+end
 function cellid(sim::Simulation, name::Symbol, pos)                       # src/Raster.jl:403-405
     id = Ref{AgentID}(0)
     check(ccall((:vb_cellid, LIB), Cint, (Ptr{Cvoid}, Cstring, Ptr{Int64}, Ref{AgentID}), sim.handle, string(name), Int64[pos...], id))
