@@ -283,30 +283,10 @@ def secondary_sir(vh, be, torch, peak, npers=50_000_000, nloc=5_000_000, steps=5
 
 def secondary_pp(vh, be, torch, peak, d=2048, steps=5):
     """BASELINE config 3 (b): the docs' predator/prey model on a 2048 x 2048 raster (838 861 prey, 209 715 predators), six applies per step"""
-    from models import pp_model, pp_step, PPCELL, ANIMAL
+    from models import pp_sim_bulk, pp_step
     nprey, npred = max(8, int(838861 * (d / 2048.0) ** 2)), max(4, int(209715 * (d / 2048.0) ** 2))
-    rng = np.random.default_rng(3)
-    sim = vh.create_simulation(pp_model(), backend=be)
+    sim = pp_sim_bulk(be, d, nprey, npred)
     n = d * d
-    cells = np.zeros(n, dtype=np.dtype(PPCELL, align=True))
-    ii, jj = np.meshgrid(np.arange(1, d + 1), np.arange(1, d + 1), indexing="ij")
-    cells["pos"][:, 0] = ii.reshape(-1, order="F"); cells["pos"][:, 1] = jj.reshape(-1, order="F")
-    cells["countdown"] = np.where(rng.random(n) < 0.5, 0, rng.integers(1, 6, n))
-    cellids = sim.add_raster("raster", (d, d), "Cell", cells).reshape(-1, order="F")
-    offs = [(0, 0), (0, -1), (-1, 0), (1, 0), (0, 1)]       # stencil(:manhatten, 2, 1) with the centre first (move_to!)
-    for species, count in (("Prey", nprey), ("Predator", npred)):
-        st = np.zeros(count, dtype=np.dtype(ANIMAL, align=True))
-        st["energy"] = rng.integers(1, 11, count)
-        st["pos"][:, 0] = rng.integers(1, d + 1, count); st["pos"][:, 1] = rng.integers(1, d + 1, count)
-        ids = sim.add_agents(species, st)
-        x, y = st["pos"][:, 0] - 1, st["pos"][:, 1] - 1
-        sim.add_edges(ids, cellids[x + y * d], f"Position{{{species}}}")
-        fr, to = [], []
-        for dx, dy in offs:
-            c = cellids[((x + dx) % d) + ((y + dy) % d) * d]
-            fr += [c, ids]; to += [ids, c]
-        sim.add_edges(np.stack(fr, axis=1).reshape(-1), np.stack(to, axis=1).reshape(-1), f"View{{{species}}}")
-    sim.finish_init()
     names = ["move_prey", "find_prey", "move_pred", "grow_food", "try_eat", "try_reproduce"]
     per = {k: {"rw": [], "fin": [], "app": []} for k in names}
     orig_apply, counter = sim.apply, {"i": 0, "rec": False}

@@ -2,7 +2,8 @@
 distribute! src/MPI.jl:11-84).  Every rank runs the same initialisation code (the docs' Hegselmann-Krause model on a
 Barabasi-Albert graph, BASELINE config 1 at a fifth of its size); finish_init hands rank 0's graph out, and the sharded run must
 follow the single-rank oracle on the same graph.  Three hand-outs: equal blocks, equal blocks of an agent count that the ranks do not
-divide (blocks of different length: a remote source number may exceed this rank's own block), and an explicit, unequal `partition`."""
+divide (blocks of different length: a remote source number may exceed this rank's own block), an explicit, unequal `partition`, and
+`partition_algo = :Metis` (the reference's default) through the graph-growing stand-in."""
 import os
 import sys
 
@@ -25,7 +26,12 @@ def run_case(be, local, rank, world, dev, n, partition_of):
     ids = vh.add_graph(g, uv, n, "HKAgent", op0.view([("opinion", "f8")]), "Knows")      # the same code on every rank
     g.add_edges(ids, ids, "Knows")
     old = np.array([vh.agent_id(1, 0, k) for k in range(1, n + 1)], dtype=np.uint64)     # rank 0's ids of the init phase
-    if partition_of is None:
+    if partition_of == "Metis":        # the reference's default; graph growing stands in for Metis (vh.graph_growing_partition)
+        m = g.finish_init(return_idmapping=True, partition_algo="Metis")
+        owner = np.array([vh.process_nr(m[int(old[k])]) for k in range(n)])
+        sizes_ = np.bincount(owner, minlength=world)
+        assert sizes_.max() - sizes_.min() <= 1
+    elif partition_of is None:
         m = g.finish_init(return_idmapping=True, partition_algo="EqualAgentNumbers")
         b = vh.equal_partition(n, world)
         owner = np.searchsorted(np.array(b[1:]), np.arange(n), side="right")
@@ -68,6 +74,7 @@ def main():
     run_case(be, local, rank, world, dev, n + 1 if world > 1 and (n + 1) % world else n + world + 1, None)     # blocks of different length
     # an explicit partition: rank 0 gets three quarters of the agents, interleaved with the others'
     run_case(be, local, rank, world, dev, n // 2, lambda nn, w: np.where(np.arange(nn) % 4 != 3, 0, 1 + (np.arange(nn) // 4) % max(w - 1, 1)) % w)
+    run_case(be, local, rank, world, dev, n // 4, "Metis")
     print(f"rank {rank}/{world}: ok", flush=True)
     dist.barrier()
     dist.destroy_process_group()

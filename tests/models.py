@@ -265,6 +265,39 @@ def pp_sim(backend, dims=(100, 100), nprey=2000, npred=500, seed=3):
     return sim
 
 
+
+def pp_sim_bulk(backend, d=2048, nprey=838861, npred=209715, seed=3):
+    """BASELINE config 3 (b): the docs' predator/prey model on a d x d raster, built with bulk adds (the per-animal move_to! calls of
+    predator.jl:199-215 written out as edge arrays in the same order: position edge, then cell -> animal and animal -> cell for the
+    position and its four von Neumann neighbours)."""
+    rng = np.random.default_rng(seed)
+    sim = vh.create_simulation(pp_model(), backend=backend)
+    n = d * d
+    cells = np.zeros(n, dtype=np.dtype(PPCELL, align=True))
+    ii, jj = np.meshgrid(np.arange(1, d + 1), np.arange(1, d + 1), indexing="ij")
+    cells["pos"][:, 0] = ii.reshape(-1, order="F")
+    cells["pos"][:, 1] = jj.reshape(-1, order="F")
+    cells["countdown"] = np.where(rng.random(n) < 0.5, 0, rng.integers(1, 6, n))
+    cellids = sim.add_raster("raster", (d, d), "Cell", cells).reshape(-1, order="F")
+    offs = [(0, 0), (0, -1), (-1, 0), (1, 0), (0, 1)]       # stencil(:manhatten, 2, 1) with the centre first (move_to!)
+    for species, count in (("Prey", nprey), ("Predator", npred)):
+        st = np.zeros(count, dtype=np.dtype(ANIMAL, align=True))
+        st["energy"] = rng.integers(1, 11, count)
+        st["pos"][:, 0] = rng.integers(1, d + 1, count)
+        st["pos"][:, 1] = rng.integers(1, d + 1, count)
+        ids = sim.add_agents(species, st)
+        x, y = st["pos"][:, 0] - 1, st["pos"][:, 1] - 1
+        sim.add_edges(ids, cellids[x + y * d], f"Position{{{species}}}")
+        fr, to = [], []
+        for dx, dy in offs:
+            c = cellids[((x + dx) % d) + ((y + dy) % d) * d]
+            fr += [c, ids]
+            to += [ids, c]
+        sim.add_edges(np.stack(fr, axis=1).reshape(-1), np.stack(to, axis=1).reshape(-1), f"View{{{species}}}")
+    sim.finish_init()
+    return sim
+
+
 def pp_step(sim, step):
     """step!(sim), predator.jl:437-469: six applies; `seed` keys each apply's uniform table"""
     s = 6 * step

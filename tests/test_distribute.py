@@ -86,6 +86,34 @@ def test_finish_init_single_rank_idmapping_is_identity(oracle):
     assert sim2.finish_init() is sim2 and sim2.finish_init.__doc__
 
 
+def test_graph_growing_partition_stands_in_for_metis():
+    """partition_algo = :Metis (the reference's default, src/Simulation.jl:420-446) without Metis: parts of equal size (up to one agent),
+    every agent placed, fewer cut edges than blocks of a shuffled numbering, deterministic"""
+    rng = np.random.default_rng(4)
+    side = 24
+    n = side * side
+    perm = rng.permutation(n)                                   # a grid graph whose agent numbers say nothing about positions
+    ids = np.array([vh.agent_id(1, 0, int(k) + 1) for k in range(n)], dtype=np.uint64)
+    x, y = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    lin = (x * side + y)
+    pairs = np.concatenate([np.stack([lin[:-1, :].ravel(), lin[1:, :].ravel()], 1), np.stack([lin[:, :-1].ravel(), lin[:, 1:].ravel()], 1)])
+    fr, to = ids[perm[pairs[:, 0]]], ids[perm[pairs[:, 1]]]
+    agents, edges = {1: (ids, None)}, {"E": (fr, to, None)}
+    for world in (2, 3, 4):
+        part = vh.graph_growing_partition(agents, edges, world)
+        assert part == vh.graph_growing_partition(agents, edges, world)
+        owner = np.array([part[int(i)] for i in ids])
+        counts = np.bincount(owner, minlength=world + 1)[1:]
+        assert counts.sum() == n and counts.max() - counts.min() <= 1 and owner.min() == 1 and owner.max() == world
+        cut = int((np.array([part[int(i)] for i in fr]) != np.array([part[int(i)] for i in to])).sum())
+        b = vh.equal_partition(n, world)
+        blocks = np.searchsorted(np.array(b[1:]), np.arange(n), side="right")
+        cut_blocks = int((blocks[perm[pairs[:, 0]]] != blocks[perm[pairs[:, 1]]]).sum())
+        assert cut < cut_blocks / 3, (world, cut, cut_blocks)
+        shards, old, new, _ = vh.plan_distribution(agents, edges, world, part)         # the plan takes it like any explicit partition
+        assert sum(s_["agents"][1][0] for s_ in shards) == n
+
+
 def test_raster_is_staged_for_the_hand_out(oracle):
     """add_raster! / connect_raster_neighbors! of the initialisation phase are kept on the host like every other add, so that
     finish_init!(distribute = true) can hand the cells out and broadcast the id grid (broadcastids, src/MPI.jl:59-73): the staged agents

@@ -185,3 +185,31 @@ def test_random_pos_one_hot_weights(backend):  # test/raster.jl:438-459 ("MoveTo
     assert all(1 <= p[k] <= d for k, d in enumerate((10, 20, 30)))
     with pytest.raises(AssertionError):
         sim.random_pos("raster", np.zeros((10, 20)))
+
+
+# ---- BASELINE config 3 (b): the docs' predator/prey model on a 2048 x 2048 raster ------------------------------------------------------
+@pytest.mark.gpu
+def test_predator_prey_config3b_full_size_vs_oracle(oracle, cuda):
+    """838 861 prey and 209 715 predators on 4.2 M cells, bulk-built (models.pp_sim_bulk, the builder bench.py times): every apply of two
+    steps — moves with edge rebuilds, births into reused slots, deaths with the dead-agent edge purge — bit-exact with the oracle: agent
+    tables incl. the ids of reused slots, edge counts per type, and the rows of two edge types.  (The oracle needs about half a minute
+    per step at this size; PP_FULL_D shrinks the raster for a quick run.)"""
+    import os
+    from models import pp_sim_bulk, pp_step, pp_globals, PP_EDGES
+    d = int(os.environ.get("PP_FULL_D", "2048"))
+    nprey, npred = int(838861 * (d / 2048.0) ** 2), int(209715 * (d / 2048.0) ** 2)
+    g, o = pp_sim_bulk(cuda, d, nprey, npred), pp_sim_bulk(oracle, d, nprey, npred)
+    for step in range(2):
+        pp_step(g, step)
+        pp_step(o, step)
+        assert pp_globals(g) == pp_globals(o), step
+        for T in ("Predator", "Prey", "Cell"):
+            assert np.array_equal(g.all_agentids(T), o.all_agentids(T)), (step, T)
+            assert g.all_agents(T).tobytes() == o.all_agents(T).tobytes(), (step, T)
+        for e in PP_EDGES:
+            assert g.num_edges(e) == o.num_edges(e), (step, e)
+    for e, tt in (("View{Prey}", "Prey"), ("Position{Predator}", "Cell")):
+        rows = int(o.num_agents(tt) * 1.5) + 64
+        a, b = g.export_csr(e, tt, rows), o.export_csr(e, tt, rows)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), e
+    assert pp_globals(g)["prey_pop"] > nprey // 2

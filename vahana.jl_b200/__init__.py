@@ -293,6 +293,51 @@ def raster_neighbor_edges(dims, cell_ids, distance=1, metric: str = "chebyshev",
     return np.ascontiguousarray(fr), np.ascontiguousarray(to)
 
 
+def graph_growing_partition(agents: dict, edges: dict, world: int) -> dict:
+    """A stand-in for the reference's default `partition_algo = :Metis` (src/Simulation.jl:420-446: Metis.partition on the graph of all
+    agents and edges): greedy graph growing — the initial-partitioning step of Metis' own multilevel scheme — on the undirected agent
+    graph.  Part p grows breadth-first from the unassigned vertex of smallest degree until it holds its share of the agents, so parts
+    are connected where the graph allows it and equal in size up to one agent.  Deterministic.  Returns {old id: rank, 1-based} like the
+    `partition` argument of finish_init!.  (Metis itself is not installed here; the partition only decides where agents live.)"""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import breadth_first_order
+    ids = np.concatenate([np.asarray(agents[t][0], dtype=np.uint64).reshape(-1) for t in sorted(agents)]) if agents else np.zeros(0, dtype=np.uint64)
+    n = ids.shape[0]
+    order = np.argsort(ids, kind="stable")
+    sid = ids[order]
+
+    def index(x):
+        k = np.searchsorted(sid, np.asarray(x, dtype=np.uint64).reshape(-1))
+        k = np.minimum(k, max(n - 1, 0))
+        ok = sid[k] == np.asarray(x, dtype=np.uint64).reshape(-1) if n else np.zeros(0, dtype=bool)
+        return order[k], ok
+    rows, cols = [], []
+    for name in edges:
+        (u, oku), (v, okv) = index(edges[name][0]), index(edges[name][1])
+        keep = oku & okv & (u != v)
+        rows += [u[keep], v[keep]]
+        cols += [v[keep], u[keep]]
+    r = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+    c = np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64)
+    adj = coo_matrix((np.ones(r.shape[0], dtype=np.int8), (r, c)), shape=(n, n)).tocsr()
+    deg = np.diff(adj.indptr)
+    part = np.full(n, -1, dtype=np.int64)
+    remaining = n
+    for p in range(world):
+        want = remaining // (world - p)
+        got = 0
+        while got < want:
+            free = np.nonzero(part < 0)[0]
+            seed = free[np.argmin(deg[free])]
+            sub = adj[free][:, free]                                  # the graph of the unassigned vertices
+            bfs = breadth_first_order(sub, int(np.searchsorted(free, seed)), directed=False, return_predecessors=False)
+            take = free[bfs[: want - got]]
+            part[take] = p
+            got += take.shape[0]
+        remaining -= want
+    return {int(ids[k]): int(part[k]) + 1 for k in range(n)}
+
+
 def updateids(idmapping, oldids):
     """updateids(idmap, oldids) (src/Simulation.jl:479-483, a helper of the reference's tests): the ids of the initialisation phase
     -> the ids after finish_init!.  The rank bits of the old id are ignored (every rank ran the same initialisation code with ids
@@ -779,8 +824,8 @@ class Simulation:
 
         One rank: nothing to distribute; `return_idmapping` gives the identity mapping.  Several ranks and `distribute=True` (the
         reference's default): everything the initialisation phase added on rank 0 is handed out - agents by `partition` ({old id:
-        rank, 1-based}) or in contiguous equal blocks per type (:EqualAgentNumbers; Metis is not available, pass a partition
-        instead), every edge to the new owner of its target - and what the other ranks added is discarded, as in the reference.
+        rank, 1-based}), in contiguous equal blocks per type (:EqualAgentNumbers) or by graph growing (partition_algo="Metis": Metis itself
+        is not installed, graph_growing_partition stands in), every edge to the new owner of its target - and what the other ranks added is discarded, as in the reference.
         `distribute=False` keeps what every rank added itself (SPMD initialisation: each rank adds its own block with ids of its
         own rank; the bench-sized graphs are generated that way, on the device).  Returns the idmapping {old id: new id} when
         `return_idmapping`, else the simulation."""
@@ -807,8 +852,7 @@ class Simulation:
         import torch.distributed as dist
         if partition_algo not in ("EqualAgentNumbers", "Metis"):
             raise ValueError("the partition_algo given is unknown")
-        if partition_algo == "Metis" and not partition:
-            raise NotImplementedError("Metis is not available: pass `partition` or partition_algo=\"EqualAgentNumbers\"")
+        use_growing = partition_algo == "Metis" and not partition      # Metis itself is not installed: greedy graph growing stands in
         if self._unstageable is not None or self._stage is None:
             raise AssertionError(f"finish_init(distribute=True) on several ranks needs host-side adds ({self._unstageable or 'no staged init phase'}); "
                                  "use distribute=False for an SPMD initialisation")
@@ -824,6 +868,8 @@ class Simulation:
             for name, chunks in self._stage["edges"].items():
                 edges[name] = (np.concatenate([c[0] for c in chunks]), np.concatenate([c[1] for c in chunks]),
                                None if chunks[0][2] is None else np.concatenate([c[2] for c in chunks]))
+            if use_growing:
+                partition = graph_growing_partition(agents, edges, world)
             shards, old, new, bounds = plan_distribution(agents, edges, world, partition or None)
             rasters = {}
             for rname, (dims, tid, ids) in self._stage.get("rasters", {}).items():      # broadcastids (src/MPI.jl:59-73): the grids with the new ids
