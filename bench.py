@@ -469,6 +469,8 @@ def run_engine(args):
     view_bytes = int(lib.vb_device_view_bytes())
     hb = C.c_uint64()
     lib.vb_halo_bytes(sim.h, C.byref(hb))
+    hms = C.c_double(-1.0)
+    lib.vb_last_halo_ms(sim.h, C.byref(hms))
 
     if rank != 0:
         dist.barrier()
@@ -504,6 +506,10 @@ def run_engine(args):
         "config": {"workload": "hk-powerlaw-100M (BASELINE config 4)", "agents": n, "edges": E, "eps": EPS,
                    "parallelism": f"{world} GPU, contiguous equal blocks of agents, edges on the target's rank, NCCL halo of source states",
                    "halo_bytes_per_step_rank0": int(hb.value),
+                   "halo_ms_rank0": hms.value if hms.value >= 0 else None,
+                   "halo_gbs_rank0": (hb.value / (hms.value * 1e-3) / 1e9) if hms.value > 0 else None,
+                   "halo_frac_of_nvlink_900gbs": (hb.value / (hms.value * 1e-3) / 1e9 / 900.0) if hms.value > 0 else None,
+                   "halo_note": "ghost states received per step and the device time of the phased exchange on its own stream (partly beside the sweeps); 900 GB/s = NVLink 5 per direction",
                    "l2": "inputs larger than L2 (source states 0.8 GB, CSR columns %.1f GB); no flush needed" % (4.0 * E / 1e9),
                    "agent_updates_per_s": n * args.steps / (ms_total * 1e-3), "build_s": t_build, "opinion_sum": metric,
                    "prefilter_pass_rate": pass_rate_main, "secondary": secondary,

@@ -78,6 +78,9 @@ int vb_comm_init(int rank, int nranks, const uint8_t id[128]);
 int vb_comm_rank(int* rank_out, int* nranks_out);
 int vb_set_uniform_offset(vb_sim* sim, int type, uint64_t offset); /* global row of this rank's first agent in the per-agent uniform table */
 int vb_halo_bytes(vb_sim* sim, uint64_t* bytes_out); /* bytes this rank received in the halo exchanges of the last apply */
+/* Device time of the last apply's halo exchange on its own stream: from behind the entry barrier to behind the last phase's barrier
+   (transmit_agents!, src/MPI.jl:155-267); negative when the last apply exchanged nothing through peer memory. */
+int vb_last_halo_ms(vb_sim* sim, double* ms_out);
 
 /* ---- lifecycle: create_simulation / copy_simulation / finish_simulation!
  *      (src/Simulation.jl:261, :500, :551) --------------------------------------------- */

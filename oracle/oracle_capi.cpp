@@ -34,6 +34,7 @@ int vb_comm_unique_id(uint8_t id_out[128]) { std::memset(id_out, 0, 128); return
 int vb_comm_init(int, int nranks, const uint8_t*) { if (nranks != 1) { g_err = "oracle C-ABI is single rank"; return VB_ERR_ARG; } return VB_OK; }
 int vb_comm_rank(int* r, int* n) { *r = 0; *n = 1; return VB_OK; }
 int vb_halo_bytes(vb_sim*, uint64_t* out) { *out = 0; return VB_OK; }
+int vb_last_halo_ms(vb_sim*, double* ms) { if (ms) *ms = -1.0; return VB_OK; }
 int vb_set_uniform_offset(vb_sim*, int, uint64_t) { return VB_OK; }
 
 int vb_sim_create(const vb_model_desc* m, const void* params, vb_sim** out) {

@@ -105,7 +105,7 @@ ABI_SYMBOLS = [
     "vb_all_agents", "vb_agentstate", "vb_num_edges_total", "vb_edges_of", "vb_all_edges", "vb_mapreduce", "vb_mapreduce_fn",
     "vb_rastervalues", "vb_calc_raster_num_edges", "vb_calc_rasterstate_fn", "vb_raster_info", "vb_num_transitions", "vb_export_csr",
     "vb_last_apply_stats", "vb_set_stream", "vb_last_kernel_ms", "vb_device_view_bytes", "vb_halo_bytes", "vb_set_uniform_offset", "vb_add_agent_per_process",
-    "vb_last_apply_blocks", "vb_set_read_blocking", "vb_set_read_prefilter", "vb_last_apply_prefiltered", "vb_last_pass_rate", "vb_set_raster",
+    "vb_last_apply_blocks", "vb_set_read_blocking", "vb_set_read_prefilter", "vb_last_apply_prefiltered", "vb_last_pass_rate", "vb_set_raster", "vb_last_halo_ms",
 ]
 
 

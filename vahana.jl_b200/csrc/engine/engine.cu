@@ -1158,6 +1158,8 @@ struct vb_sim {
     // agent type re-checks the peer maps
     void mark_peer_check() { for (auto& a : agents) a.peers.check = true; }
     uint64_t halo_bytes = 0;   // bytes received by the last apply's halo exchanges
+    cudaEvent_t ev_halo[2] = {nullptr, nullptr};   // on the halo stream: behind the entry barrier / behind the last phase's barrier
+    bool halo_timed = false;
     double blk_block_mb = -1, blk_min_mb = -1; int blk_eager = -1;   // vb_set_read_blocking (negative = environment / default)
     int blk_prefilter = -1;                                          // vb_set_read_prefilter (negative = environment / default)
     bool prefilter_on(const vb::TransitionInfo* ti) const;
@@ -1233,6 +1235,7 @@ vb_sim::~vb_sim() {
     dfree(d_error); dfree(d_scalars); dfree(d_stats);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : evk) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_halo) if (e) cudaEventDestroy(e);
 }
 
 void vb_sim::compute_bases(uint32_t* out) const {
@@ -2619,6 +2622,8 @@ void vb_sim::halo_exchange(int t) {
         g_trace.mark("begin", hs);
         stream_barrier(hs);
         g_trace.mark("barrier: every rank is here", hs);
+        if (!ev_halo[0]) { CK(cudaEventCreate(&ev_halo[0])); CK(cudaEventCreate(&ev_halo[1])); }
+        CK(cudaEventRecord(ev_halo[0], hs));
         for (uint32_t j = 0; j < ng; ++j) {
             HaloPushArgs h{};
             h.cols = a.rstate(); h.stride = a.stride(); h.slots = a.send_slots; h.word = a.word; h.ncols = a.ncols; h.npeers = P - 1;
@@ -2654,6 +2659,8 @@ void vb_sim::halo_exchange(int t) {
             g_trace.mark("barrier: phase landed everywhere", hs);
             CK(cudaEventRecord(a.ev_phase[j], hs));
         }
+        CK(cudaEventRecord(ev_halo[1], hs));
+        halo_timed = true;
         a.halo_pending = ng;
         halo_bytes += (uint64_t)a.nghost * a.size;
         (void)ns;
@@ -3344,6 +3351,15 @@ void allgather8_host(const void* mine, std::vector<uint64_t>& all) {
 }  // namespace
 extern "C" {
 int vb_halo_bytes(vb_sim* s, uint64_t* out) { *out = s->halo_bytes; return VB_OK; }
+int vb_last_halo_ms(vb_sim* s, double* ms) {     // device time of the last phased halo exchange (entry barrier excluded), negative = none
+    *ms = -1.0;
+    if (s->halo_timed && s->ev_halo[1] && cudaEventSynchronize(s->ev_halo[1]) == cudaSuccess) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, s->ev_halo[0], s->ev_halo[1]) == cudaSuccess) *ms = t;
+    }
+    cudaGetLastError();
+    return VB_OK;
+}
 int vb_set_uniform_offset(vb_sim* s, int type, uint64_t offset) { return guard([&] { s->A(type).uoffset = offset; }); }
 
 int vb_sim_create(const vb_model_desc* m, const void* params, vb_sim** out) {
