@@ -3331,6 +3331,20 @@ int vb_comm_init(int rank, int nranks, const uint8_t* idbytes) {
         std::vector<uint64_t> warm;
         const uint64_t me = (uint64_t)rank;
         allgather8_host(&me, warm);
+        {   // ... and its point-to-point connections on the first ncclSend / ncclRecv between a pair of ranks: one grouped 8-byte exchange
+            // with every peer (what the ghost-request exchange of finish_init! and the edge exchanges use)
+            uint64_t* buf = dalloc<uint64_t>((size_t)2 * nranks);
+            CK(cudaMemsetAsync(buf, 0, (size_t)2 * nranks * 8, g_stream));
+            NK(g_nccl.GroupStart());
+            for (int r = 0; r < nranks; ++r) {
+                if (r == rank) continue;
+                NK(g_nccl.Send(buf + r, 8, ncclUint8, r, g_comm, g_stream));
+                NK(g_nccl.Recv(buf + nranks + r, 8, ncclUint8, r, g_comm, g_stream));
+            }
+            NK(g_nccl.GroupEnd());
+            CK(cudaStreamSynchronize(g_stream));
+            dfree(buf);
+        }
     });
 }
 int vb_comm_rank(int* r, int* n) { *r = g_rank; *n = g_nranks; return VB_OK; }
