@@ -180,6 +180,15 @@ class Recorder:
         t = np.frombuffer((C.c_uint64 * n).from_address(to.value), dtype=np.uint64).copy()
         self.edges.setdefault(e.value, []).append((f, t)); return 0
     def vb_set_uniform_offset(self, h, tid, off): self.offsets[tid.value] = off.value; return 0
+    def vb_add_raster(self, h, name, nd, dims, tid, buf, ids):
+        n = int(np.prod([dims[k] for k in range(nd.value)]))
+        return self.vb_add_agents(h, tid, buf, C.c_uint64(n), ids)
+    def vb_connect_raster_neighbors(self, *a): return 0
+    def vb_set_raster(self, h, name, nd, dims, tid, ids):
+        n = int(np.prod([dims[k] for k in range(nd.value)]))
+        self.rasters = getattr(self, "rasters", {{}})
+        self.rasters[name.decode()] = (tuple(dims[k] for k in range(nd.value)), tid.value, np.frombuffer((C.c_uint64 * n).from_address(ids.value), dtype=np.uint64).copy())
+        return 0
     def vb_finish_init(self, h): self.finished += 1; return 0
     def vb_last_error(self): return b""
 
@@ -217,6 +226,28 @@ assert np.array_equal(t, [m[int(rank0_ids[(k + 1) % n])] for k in mine]) and np.
 # join (src/MPI.jl:481-517) behind all_agents / all_agentids / all_edges(all_ranks = true): rank order, on every rank
 j = sim._join(np.arange(rank + 2) + 10 * rank)
 assert np.array_equal(j, np.concatenate([np.arange(r + 2) + 10 * r for r in range(world)]))
+# a raster: its cells are handed out like every agent, the stencil edges follow their targets, every rank receives the id grid
+# (broadcastids, src/MPI.jl:59-73)
+from models import gol_model
+be3 = FakeBackend()
+sim3 = vh.create_simulation(gol_model(), backend=be3)
+dims = (6, 5)
+init = (np.arange(30) % 3 == 0)
+sim3.add_raster("grid", dims, "Cell", init.view([("active", "?")]))
+sim3.connect_raster_neighbors("grid", "Neighbor")
+m3 = sim3.finish_init(return_idmapping=True)
+b3 = vh.equal_partition(30, world)
+rdims, rtid, rids = be3.lib.rasters["grid"]
+assert rdims == dims and rtid == 1
+want = [vh.agent_id(1, int(np.searchsorted(np.array(b3[1:]), k, side="right")), k - b3[int(np.searchsorted(np.array(b3[1:]), k, side="right"))] + 1) for k in range(30)]
+assert [int(x) for x in rids] == want                                   # the whole grid with the new ids, on every rank
+cnt3, _st3 = be3.lib.agents[1][0]
+assert cnt3 == b3[rank + 1] - b3[rank]
+f3, t3 = be3.lib.edges[sim3._eid["Neighbor"]][0]
+assert len(t3) == 8 * cnt3 and all(vh.process_nr(int(x)) == rank for x in t3)      # 8 stencil edges per local cell, stored with their target
+fr_all, to_all = vh.raster_neighbor_edges(dims, np.array([vh.agent_id(1, 0, k + 1) for k in range(30)], dtype=np.uint64))
+sel = [i for i in range(len(to_all)) if vh.process_nr(m3[int(to_all[i])]) == rank]
+assert [int(x) for x in f3] == [m3[int(fr_all[i])] for i in sel] and [int(x) for x in t3] == [m3[int(to_all[i])] for i in sel]
 # device-side bulk adds cannot be handed out
 sim2 = vh.create_simulation(edges_model(), backend=be)
 sim2._unstageable = "add_agents_device"
