@@ -105,6 +105,23 @@ def main():
                 assert sim.agentstate(target, tname)["foo"] == expect, (tname, expect, sim.agentstate(target, tname)["foo"])
             sim.disable_transition_checks(False)
     sums(("a1",), "AMortal", "ESLDict1", lambda a1, av, avf: a1, (sum(r) + 1, 2 * sum(r) + 1))
+    if world > 1:
+        # agentstate of an agent of another rank (the reference's `foreignstate`, src/AgentMethods.jl:103-111): answered from the ghost
+        # slot that mirrors it, as of the last halo exchange of an apply! that read its type; an agent nobody here refers to is refused
+        simf, a1f, _, _, avf_ids, avff_ids = createsim(be, local, ("a1",))
+        simf.apply("sum_state_neighbors_ESLDict1", ["AMortal"], ALLAGENTTYPES + ["ESLDict1"], ["AMortal"])
+        simf.disable_transition_checks(True)
+        if on(a1f):
+            far = avf_ids[9]                                     # a source of a1's row, owned by the last rank
+            assert not on(far) and simf.agentstate(far, "AImm")["foo"] == 10
+            lonely = avff_ids[5]                                 # its only edge points to avids[5], which does not live here either
+            if not on(lonely) and not on(avf_ids[5]):
+                try:
+                    simf.agentstate(lonely, "AImmFixed")
+                    raise SystemExit("expected an AssertionError for an agent of another rank that is not mirrored here")
+                except AssertionError:
+                    pass
+        simf.disable_transition_checks(False)
     sums(("avids",), "AImm", "ESLDict2", lambda a1, av, avf: av[0], (2, 3, 4))
     sums(("avfids",), "AImmFixed", "ESLDict1", lambda a1, av, avf: avf[0], (3, 5, 7))
     # add_agent_per_process! (core.jl:442-466): one new agent on every rank
