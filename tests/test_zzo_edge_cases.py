@@ -97,3 +97,29 @@ def test_many_types(backend):
     sim.disable_transition_checks(False)
     for k in range(0, 50, 3):
         assert sim.mapreduce("foo", "+", f"E{k}") == sum(range(k, k + 5))
+
+
+@pytest.mark.parametrize("nagents", [300, 70000])
+def test_small_edge_states_through_finish_write(backend, nagents):
+    """Edge states of one and two bytes (SIR's `Visit` carries a Bool): the engine's sort carries them in the key's unused high bits
+    where they fit (rows below 2^24 resp. 2^16) and widens them to four bytes otherwise — either way a row holds its edges in add order
+    with their own states (stable sort, src/EdgeMethods.jl:495-496)."""
+    t = vh.ModelTypes()
+    t.register_agenttype("A", [("foo", "i8")], "Immortal")
+    t.register_edgetype("E1", [("flag", "u1")])
+    t.register_edgetype("E2", [("code", "u2")])
+    sim = vh.create_simulation(vh.create_model(t, "small states"), backend=backend)
+    ids = sim.add_agents("A", foos(range(nagents)))
+    rng = np.random.default_rng(9)
+    m = 6000
+    fr, to = ids[rng.integers(0, nagents, m)], ids[rng.integers(0, min(nagents, 500), m)]      # some crowded rows
+    s1, s2 = rng.integers(0, 256, m).astype("u1"), rng.integers(0, 65536, m).astype("u2")
+    sim.add_edges(fr, to, "E1", s1.view([("flag", "u1")]))
+    sim.add_edges(fr, to, "E2", s2.view([("code", "u2")]))
+    sim.finish_init()
+    order = np.argsort(to, kind="stable")
+    want_off = np.concatenate([[0], np.cumsum(np.bincount((to & ((1 << 36) - 1)).astype(np.int64) - 1, minlength=nagents))])
+    for name, st, field in (("E1", s1, "flag"), ("E2", s2, "code")):
+        off, efrom, est = sim.export_csr(name, "A", nagents)
+        assert np.array_equal(np.asarray(off, dtype=np.int64), want_off)
+        assert np.array_equal(efrom, fr[order]) and np.array_equal(est[field], st[order]), name

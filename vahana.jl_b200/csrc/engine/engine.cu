@@ -337,6 +337,21 @@ __global__ void widen_state_kernel(const uint8_t* __restrict__ in, uint32_t n, u
     if (i >= n) return;
     out[i] = word == 1 ? (uint32_t)in[i] : (uint32_t)reinterpret_cast<const uint16_t*>(in)[i];
 }
+// a one- or two-byte edge state rides in the key's unused high bits through the sort (the passes only look at the low `bits` bits): the
+// log is sorted as (key, from) instead of (key, from, state widened to 4 bytes)
+__global__ void pack_state_into_key_kernel(uint32_t* __restrict__ key, const uint8_t* __restrict__ st, uint32_t n, uint32_t word, int bits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = word == 1 ? (uint32_t)st[i] : (uint32_t)reinterpret_cast<const uint16_t*>(st)[i];
+    key[i] |= v << bits;
+}
+__global__ void unpack_state_from_key_kernel(uint32_t* __restrict__ key, uint8_t* __restrict__ st, uint32_t n, uint32_t word, int bits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = key[i];
+    if (word == 1) st[i] = (uint8_t)(k >> bits); else reinterpret_cast<uint16_t*>(st)[i] = (uint16_t)(k >> bits);
+    key[i] = k & ((1u << bits) - 1u);
+}
 __global__ void narrow_state_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t word, uint8_t* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1641,13 +1656,16 @@ void vb_sim::build_container(int ei, bool add_existing) {
     if (n > 1) {
         const int bits = vbp::bits_for(rows);
         const bool direct = e.has_state() && e.ncols == 1 && (e.word == 4 || e.word == 8);
-        const bool widened = e.has_state() && e.ncols == 1 && (e.word == 1 || e.word == 2);
-        const bool via_perm = e.has_state() && !direct && !widened;
+        const int pbits = (bits + 7) & ~7;                 // whole digits: the passes look at all of the key's low pbits bits
+        const bool packed = e.has_state() && e.ncols == 1 && (e.word == 1 || e.word == 2) && pbits + 8 * (int)e.word <= 32;     // the state fits above the sorted digits
+        const bool widened = e.has_state() && e.ncols == 1 && (e.word == 1 || e.word == 2) && !packed;
+        const bool via_perm = e.has_state() && !direct && !widened && !packed;
         // buffer set A = the log itself, set B = scratch of the same capacity; the sort ping-pongs between them
         uint32_t* kA = e.log_to; uint32_t* kB = dalloc<uint32_t>(e.log_cap);
         uint32_t* fA = e.log_from; uint32_t* fB = e.has_src() ? dalloc<uint32_t>(e.log_cap) : nullptr;
         void* pA = nullptr; void* pB = nullptr; int p2b = 0;
         if (direct) { p2b = (int)e.word; pA = e.log_st; pB = g_pool.alloc((size_t)e.log_cap * e.word); }
+        else if (packed) { pack_state_into_key_kernel<<<nblk(n), 256, 0, g_stream>>>(kA, e.log_st, n, e.word, pbits); LAUNCH_CHECK(); }
         else if (widened) {
             p2b = 4; pA = dalloc<uint32_t>(e.log_cap); pB = dalloc<uint32_t>(e.log_cap);
             widen_state_kernel<<<nblk(n), 256, 0, g_stream>>>(e.log_st, n, e.word, (uint32_t*)pA); LAUNCH_CHECK();
@@ -1665,6 +1683,7 @@ void vb_sim::build_container(int ei, bool add_existing) {
         e.log_to = kA; e.log_from = fA;
         dfree(kB); dfree(fB);
         if (direct) { e.log_st = (uint8_t*)pA; dfree(pB); }
+        else if (packed) { unpack_state_from_key_kernel<<<nblk(n), 256, 0, g_stream>>>(kA, e.log_st, n, e.word, pbits); LAUNCH_CHECK(); }
         else if (widened) {
             narrow_state_kernel<<<nblk(n), 256, 0, g_stream>>>((const uint32_t*)pA, n, e.word, e.log_st); LAUNCH_CHECK();
             dfree(pA); dfree(pB);
