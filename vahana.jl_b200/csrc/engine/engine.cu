@@ -1757,16 +1757,7 @@ void vb_sim::build_container(int ei, bool add_existing) {
     CK(cudaMemsetAsync(ncnt, 0, ((size_t)rows + 2) * 4, g_stream));
     if (n) { vbp::csr_run_counts_kernel<<<nblk(n), 256, 0, g_stream>>>(skey, n, ncnt); LAUNCH_CHECK(); }
     uint32_t* scr = dalloc<uint32_t>(vbp::scan_scratch_words((uint64_t)rows + 1));
-    if (!have_old) {
-        uint32_t* off = dalloc<uint32_t>((size_t)rows + 2);
-        vbp::exclusive_scan(ncnt, off, (uint64_t)rows + 1, nullptr, scr, g_stream); g_launches += 3;
-        CK(cudaGetLastError());
-        free_edge_read(e);
-        e.off = off; e.rows = rows; e.nnz = n;
-        e.src = e.log_from; e.st = e.log_st; e.st_cap = e.log_cap;       // the sorted log becomes the container
-        e.log_from = nullptr; e.log_st = nullptr;
-        dfree(e.log_to); e.log_to = nullptr; e.log_n = 0; e.log_cap = 0;
-    } else {
+    {
         uint32_t* noff = dalloc<uint32_t>((size_t)rows + 2);
         vbp::exclusive_scan(ncnt, noff, (uint64_t)rows + 1, nullptr, scr, g_stream); g_launches += 3;   // run offsets of the new entries
         uint32_t* cnt = dalloc<uint32_t>((size_t)rows + 2);
