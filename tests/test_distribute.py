@@ -147,6 +147,37 @@ def test_raster_is_staged_for_the_hand_out(oracle):
     assert sum(s_["edges"]["Neighbor"][1].shape[0] for s_ in shards) == fr.shape[0]
 
 
+def test_move_to_is_staged_for_the_hand_out(oracle):
+    """move_to! of the initialisation phase (src/Raster.jl:437-477) is kept on the host as the edges it adds — the cell at `pos`, then
+    the stencil cells, per cell the from-raster edge before the to-raster edge — so that finish_init!(distribute = true) can hand out a
+    model whose agents are placed on a raster (predator/prey, docs): the staged edges are exactly the rows the engine holds."""
+    from models import raster_model
+    sim = vh.create_simulation(raster_model(), backend=oracle)
+    sim._stage = {"agents": {}, "edges": {}}
+    cells = sim.add_raster("raster", (7, 5), "Position", lambda p: (0,))
+    movers = [sim.add_agent("MovingAgent", v) for v in range(1, 7)]
+    sim.move_to("raster", movers[0], (1, 1), "OnPosition", "OnPosition")                                         # both directions in one edge type
+    sim.move_to("raster", movers[1], (4, 3), "OnPosition", None, distance=2)
+    sim.move_to("raster", movers[2], (7, 5), None, "OnPosition", distance=2, metric="manhatten", periodic=False)   # clipped at the corner
+    sim.move_to("raster", movers[3], (2, 2), "OnPosition", "OnPosition", distance=1.5, metric="euclidean", only_surrounding=True)
+    sim.move_to("raster", movers[4], (4, 3), "OnPosition", "GridE", distance=1)                                  # two edge types
+    sim.move_to("raster", movers[5], (4, 3), "OnPosition", None)
+    assert sim._unstageable is None
+    st = {name: (np.concatenate([c[0] for c in ch]), np.concatenate([c[1] for c in ch])) for name, ch in sim._stage["edges"].items()}
+    sim._stage = None
+    sim.finish_init()
+    assert len(st["OnPosition"][0]) == sim.num_edges("OnPosition") == 2 + 25 + 6 + 2 * 8 + 9 + 1
+    assert len(st["GridE"][0]) == sim.num_edges("GridE") == 9
+    sim.disable_transition_checks(True)
+    for name, (fr, to) in st.items():
+        for target in [int(x) for x in np.unique(to)]:
+            got = sim.neighborids(target, name)
+            assert np.array_equal(fr[to == np.uint64(target)], np.asarray(got, dtype=np.uint64)), (name, target)
+    assert int(cells[3, 2]) in [int(x) for x in st["GridE"][1]]
+    # only rasters added through add_raster can be staged
+    assert list(vh.raster_move_cells((3, 3), np.arange(9, dtype=np.uint64), (1, 1), 1, "chebyshev", False)) == [0, 1, 3, 4]
+
+
 _GLOO = r'''
 import os, sys, ctypes as C
 import numpy as np, torch.distributed as dist
@@ -248,6 +279,23 @@ assert len(t3) == 8 * cnt3 and all(vh.process_nr(int(x)) == rank for x in t3)   
 fr_all, to_all = vh.raster_neighbor_edges(dims, np.array([vh.agent_id(1, 0, k + 1) for k in range(30)], dtype=np.uint64))
 sel = [i for i in range(len(to_all)) if vh.process_nr(m3[int(to_all[i])]) == rank]
 assert [int(x) for x in f3] == [m3[int(fr_all[i])] for i in sel] and [int(x) for x in t3] == [m3[int(to_all[i])] for i in sel]
+# agents placed on a raster in the initialisation phase (move_to!, src/Raster.jl:437-477): both edge directions follow their targets
+from models import raster_model
+be4 = FakeBackend(); be4.lib.vb_move_to = lambda *a: 0
+sim4 = vh.create_simulation(raster_model(), backend=be4)
+grid4 = sim4.add_raster("raster", (4, 3), "Position", lambda p: (0,))
+movers = [sim4.add_agent("MovingAgent", v) for v in range(1, 6)]
+for k, a in enumerate(movers):
+    sim4.move_to("raster", a, (1 + k % 4, 1 + k % 3), "OnPosition", "OnPosition", distance=1 if k == 2 else 0)
+stage_fr = np.concatenate([c[0] for c in sim4._stage["edges"]["OnPosition"]]); stage_to = np.concatenate([c[1] for c in sim4._stage["edges"]["OnPosition"]])
+assert len(stage_fr) == 2 * (4 + 9)
+m4 = sim4.finish_init(return_idmapping=True)
+stage_fr, stage_to = [vh.remove_process(x) for x in stage_fr], [vh.remove_process(x) for x in stage_to]      # the mapping is keyed by rank 0's ids (its content is what is handed out)
+f4, t4 = be4.lib.edges[sim4._eid["OnPosition"]][0]
+sel = [i for i in range(len(stage_to)) if vh.process_nr(m4[int(stage_to[i])]) == rank]
+assert len(sel) > 0 and all(vh.process_nr(int(x)) == rank for x in t4)
+assert [int(x) for x in f4] == [m4[int(stage_fr[i])] for i in sel] and [int(x) for x in t4] == [m4[int(stage_to[i])] for i in sel]
+assert [int(x) for x in be4.lib.rasters["raster"][2]] == [m4[vh.remove_process(x)] for x in grid4.reshape(-1, order="F")]
 # device-side bulk adds cannot be handed out
 sim2 = vh.create_simulation(edges_model(), backend=be)
 sim2._unstageable = "add_agents_device"

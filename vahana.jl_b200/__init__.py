@@ -293,6 +293,23 @@ def raster_neighbor_edges(dims, cell_ids, distance=1, metric: str = "chebyshev",
     return np.ascontiguousarray(fr), np.ascontiguousarray(to)
 
 
+def raster_move_cells(dims, cell_ids, pos, distance=0, metric: str = "chebyshev", periodic: bool = True, only_surrounding: bool = False):
+    """The cells move_to! connects an agent with (src/Raster.jl:437-477), in its order: the cell at `pos` (1-based; left out with
+    only_surrounding), then, for distance >= 1, the cell at pos + o for every stencil offset o (wrapped on a periodic raster, skipped
+    when it leaves a clipped one).  Returns their ids."""
+    dd = np.array([int(x) for x in dims], dtype=np.int64)
+    cell_ids = np.asarray(cell_ids, dtype=np.uint64).reshape(-1)
+    p0 = np.array([int(x) - 1 for x in pos], dtype=np.int64)
+    assert p0.shape[0] == dd.shape[0] and ((p0 >= 0) & (p0 < dd)).all(), "position outside the raster"
+    strides = np.concatenate([[1], np.cumprod(dd[:-1])]).astype(np.int64)
+    cells = [] if only_surrounding else [int((p0 * strides).sum())]
+    if distance >= 1:
+        sh = p0[None, :] + raster_stencil(metric, dd.shape[0], distance)
+        keep = np.ones(sh.shape[0], dtype=bool) if periodic else ((sh >= 0) & (sh < dd)).all(axis=1)
+        cells += [int(x) for x in (np.mod(sh, dd) * strides).sum(axis=1)[keep]]
+    return cell_ids[np.array(cells, dtype=np.int64)]
+
+
 def graph_growing_partition(agents: dict, edges: dict, world: int) -> dict:
     """A stand-in for the reference's default `partition_algo = :Metis` (src/Simulation.jl:420-446: Metis.partition on the graph of all
     agents and edges): greedy graph growing — the initial-partitioning step of Metis' own multilevel scheme — on the undirected agent
@@ -776,8 +793,6 @@ class Simulation:
     def move_to(self, name: str, aid: int, pos, edge_from_raster: Optional[str], edge_to_raster: Optional[str],
                 state_from=None, state_to=None, distance=0, metric: str = "chebyshev", periodic: bool = True,
                 only_surrounding: bool = False):
-        if self._stage is not None:
-            self._unstageable = "move_to in the initialisation phase"      # (its edges are added inside the engine; not handed out yet)
         p = (C.c_int64 * len(pos))(*[int(x) for x in pos])
 
         def sb(ename, st):
@@ -785,6 +800,22 @@ class Simulation:
                 return None
             return np.array([st if isinstance(st, (tuple, np.void)) else (st,)], dtype=self._edt(ename))
         bf, bt = sb(edge_from_raster, state_from), sb(edge_to_raster, state_to)
+        if self._stage is not None:
+            if name in self._stage.get("rasters", {}):     # the edges the engine adds below, staged in move_to!'s order (from-raster edge, then to-raster edge, per cell)
+                dims, _tid, grid = self._stage["rasters"][name]
+                cells = raster_move_cells(dims, grid, pos, distance, metric, periodic, only_surrounding)
+                me = np.full(cells.shape[0], int(aid), dtype=np.uint64)
+                if edge_from_raster is not None and edge_from_raster == edge_to_raster:
+                    fr, to = np.stack([cells, me], axis=1).reshape(-1), np.stack([me, cells], axis=1).reshape(-1)
+                    st = None if bf is None else np.stack([np.broadcast_to(bf, cells.shape), np.broadcast_to(bt, cells.shape)], axis=1).reshape(-1)
+                    self._stage["edges"].setdefault(edge_from_raster, []).append((fr, to, st))
+                else:
+                    if edge_from_raster is not None:
+                        self._stage["edges"].setdefault(edge_from_raster, []).append((cells, me, None if bf is None else np.broadcast_to(bf, cells.shape).copy()))
+                    if edge_to_raster is not None:
+                        self._stage["edges"].setdefault(edge_to_raster, []).append((me, cells, None if bt is None else np.broadcast_to(bt, cells.shape).copy()))
+            else:
+                self._unstageable = "move_to on a raster that was not added through add_raster"
         self._ck(self.lib.vb_move_to(self.h, name.encode(), C.c_uint64(int(aid)), p,
                                      C.c_int(self._eid[edge_from_raster] if edge_from_raster else -1),
                                      bf.ctypes.data_as(C.c_void_p) if bf is not None else None,
