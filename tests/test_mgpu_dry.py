@@ -9,7 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("script", ["mgpu_core.py", "mgpu_remove.py", "mgpu_distribute.py", "mgpu_agentstate.py", "mgpu_purge.py", "mgpu_sir.py", "mgpu_gol.py"])
+@pytest.mark.parametrize("script", ["mgpu_core.py", "mgpu_remove.py", "mgpu_distribute.py", "mgpu_agentstate.py", "mgpu_purge.py", "mgpu_sir.py", "mgpu_gol.py", "mgpu_moveto.py"])
 def test_mgpu_script_dry_run(oracle, script):
     env = dict(os.environ, MGPU_DRY="1", MGPU_N="4000", MGPU_L="301")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script)], capture_output=True, text=True, timeout=600, env=env)

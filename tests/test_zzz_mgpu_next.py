@@ -59,3 +59,15 @@ def test_raster_handed_out_game_of_life_across_ranks(cuda):
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     from mgpu_common import run_ranks
     run_ranks("mgpu_gol.py", 29539)
+
+
+@pytest.mark.gpu
+def test_agents_placed_on_a_handed_out_raster_across_ranks(cuda):
+    """move_to! in the initialisation phase and inside a transition with cells of other ranks (src/Raster.jl:437-477; test/raster.jl:242-303
+    as mpiexec runs it): the staged edges are handed out with their targets, Ctx::move_to towards a remote cell sends both edges through
+    transmit_edges!, the joined calc_rasterstate follows the single-rank oracle"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    from mgpu_common import run_ranks
+    run_ranks("mgpu_moveto.py", 29541)
