@@ -3671,10 +3671,11 @@ int vb_add_raster(vb_sim* s, const char* name, int ndims, const int64_t* dims, i
         if (s->initialized) throw AssertionError("add_raster! can be only called before finish_init!");
         if (ndims < 1 || ndims > vb::MAX_RASTER_DIMS) throw ArgError("rasters with 1..4 dimensions are supported");
         if (s->rasters.size() >= vb::MAX_RASTERS) throw ArgError("too many rasters (MAX_RASTERS)");
+        if (!name || !dims) throw ArgError("vb_add_raster: name and dims must be given");
         RasterStore r;
         r.name = name; r.dims.assign(dims, dims + ndims); r.type = type;
         uint64_t n = 1;
-        for (int i = 0; i < ndims; ++i) n *= (uint64_t)dims[i];
+        for (int i = 0; i < ndims; ++i) { if (dims[i] < 1) throw ArgError("raster dimensions must be positive"); n *= (uint64_t)dims[i]; }
         r.ids.resize(n);
         int rc = vb_add_agents(s, type, states, n, r.ids.data());
         if (rc != VB_OK) throw AssertionError(g_err);
@@ -3691,10 +3692,12 @@ int vb_set_raster(vb_sim* s, const char* name, int ndims, const int64_t* dims, i
         if (s->initialized) throw AssertionError("rasters can only be defined before finish_init!");
         if (ndims < 1 || ndims > vb::MAX_RASTER_DIMS) throw ArgError("rasters with 1..4 dimensions are supported");
         if (s->rasters.size() >= vb::MAX_RASTERS) throw ArgError("too many rasters (MAX_RASTERS)");
+        if (!name || !dims || !ids) throw ArgError("vb_set_raster: name, dims and ids must be given");
+        s->A(type);      // a registered agent type
         RasterStore r;
         r.name = name; r.dims.assign(dims, dims + ndims); r.type = type;
         uint64_t n = 1;
-        for (int i = 0; i < ndims; ++i) n *= (uint64_t)dims[i];
+        for (int i = 0; i < ndims; ++i) { if (dims[i] < 1) throw ArgError("raster dimensions must be positive"); n *= (uint64_t)dims[i]; }
         r.ids.assign(ids, ids + n);
         for (uint64_t i = 0; i < n; ++i) {
             if ((int)vb::type_nr(ids[i]) != type) throw AssertionError("vb_set_raster: a cell id of another agent type");
