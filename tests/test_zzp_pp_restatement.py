@@ -247,3 +247,24 @@ def test_predator_prey_golden_fixture_vs_python_restatement():
         row = [len(w.agents[PREY]), len(w.agents[PRED]), sum(1 for _, cd in w.agents[CELL].values() if cd == 0),
                sum(e for e, _ in w.agents[PREY].values()), sum(e for e, _ in w.agents[PRED].values())]
         assert row == g["trajectory"][step].tolist(), step
+
+
+def test_predator_prey_docs_size_fixture_vs_python_restatement():
+    """BASELINE config 3 (a) — the docs' own size, 100 x 100 cells, 2000 prey, 500 predators — against tests/golden/pp_docs_100x100.npz:
+    the first two samples (steps 25 and 50) of the 400-step trajectory the GPU suite replays, from the Python restatement alone"""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from make_golden import PP_DOCS
+    g = np.load(os.path.join(here, "golden", "pp_docs_100x100.npz"))
+    w = build_world(PP_DOCS["dims"], PP_DOCS["nprey"], PP_DOCS["npred"])
+    samples = 0
+    for step in range(2 * PP_DOCS["every"]):
+        w.step(step)
+        if step % PP_DOCS["every"] == PP_DOCS["every"] - 1:
+            row = [step, len(w.agents[PREY]), len(w.agents[PRED]), sum(1 for _, cd in w.agents[CELL].values() if cd == 0),
+                   sum(e for e, _ in w.agents[PREY].values()), sum(e for e, _ in w.agents[PRED].values())]
+            assert row == g["trajectory"][samples].tolist(), step
+            samples += 1
+    assert samples == 2
