@@ -58,7 +58,7 @@ def test_raster_handed_out_game_of_life_across_ranks(cuda):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     from mgpu_common import run_ranks
-    run_ranks("mgpu_gol.py", 29539)
+    run_ranks("mgpu_gol.py", 29539, nranks=2)          # the configuration that ran on hardware (profiles/r2_mgpu_tests_2gpu.txt)
 
 
 @pytest.mark.gpu
@@ -70,4 +70,4 @@ def test_agents_placed_on_a_handed_out_raster_across_ranks(cuda):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     from mgpu_common import run_ranks
-    run_ranks("mgpu_moveto.py", 29541)
+    run_ranks("mgpu_moveto.py", 29541, nranks=2)       # the configuration that ran on hardware (profiles/r2_mgpu_moveto_2gpu.txt)
