@@ -14,9 +14,11 @@
 // test/parametric_types.jl) and test_zy_full_size.py (random_pos, test/raster.jl:438-459).  The model-level outputs of the
 // BASELINE configs (Hegselmann-Krause opinions, Game of Life, predator/prey, SIR) are NOT pinned by any reference test and
 // Julia cannot run here: "parity unpinned" for those.  What stands in: independent numpy restatements that this
-// oracle matches bit for bit (HK at config 1's full size and on random multigraphs, Game of Life, the market model of
-// docs/examples/tutorial1.jl with an independent Philox4x32-10: tests/test_zzm_market.py) and the committed fixtures of
-// tests/golden/ (oracle outputs, written by tests/golden/make_golden.py).
+// oracle matches bit for bit (HK at config 1's full size and on random multigraphs, Game of Life, SIR: tests/test_zzn_sir_numpy.py,
+// the market model of docs/examples/tutorial1.jl with an independent Philox4x32-10: tests/test_zzm_market.py), a pure-Python engine
+// in the reference's container shapes for predator/prey (tests/test_zzp_pp_restatement.py), and the committed fixtures of
+// tests/golden/ (oracle outputs, written by tests/golden/make_golden.py; the SIR and predator/prey ones are reproduced by the
+// second implementations alone).
 //
 // Each function cites the reference lines it follows (paths relative to /root/reference).
 #pragma once
