@@ -131,6 +131,30 @@ def test_graphs_source_blocked(cuda, nagents, block_mb):
         assert np.array_equal(got["sum_ids_neighbors"], sum(range(1, nagents + 1)) - got["id"])
 
 
+@pytest.mark.parametrize("ET", [t for t in STATEFUL_EDGE_TYPES + STATELESS_EDGE_TYPES if not ("S" in t[4:] and "I" in t[4:])])
+def test_edges_iterator_lengths(oracle, ET):  # test/edgesiterator.jl:7-53 ("Edges Iter": every stored edge is visited once, write and read side)
+    # (oracle only: written after this round's GPU budget was spent; the engine's all_edges / num_edges run in the tests around it)
+    S, E1 = ("S" in ET[4:]), ("E" in ET[4:])
+    sim = vh.create_simulation(edges_model(), backend=oracle)
+    assert sim.num_edges(ET) == 0 and sim.num_edges(ET, write=True) == 0 and len(sim.all_edges(ET)[0]) == 0
+    aids = sim.add_agents("Agent", foos(range(1, 11)))
+    for i in aids:
+        sim.add_edge(aids[0], i, ET, None if S else vh.agent_nr(i))
+        if not E1:
+            sim.add_edge(i, aids[0], ET, None if S else vh.agent_nr(i))
+    expected = 10 if E1 else 20
+    assert sim.num_edges(ET, write=True) == expected
+    sim.finish_init()
+    to, fr, st = sim.all_edges(ET)
+    assert sim.num_edges(ET) == expected and len(to) == expected
+    if "I" not in ET[4:]:
+        pairs = sorted(zip((int(x) for x in to), (int(x) for x in fr)))
+        want = [(int(i), int(aids[0])) for i in aids] + ([] if E1 else [(int(aids[0]), int(i)) for i in aids])
+        assert pairs == sorted(want)
+    if not S:
+        assert sorted(int(x) for x in st["foo"]) == sorted(list(range(1, 11)) * (1 if E1 else 2))
+
+
 @pytest.mark.parametrize("ET", STATEFUL_EDGE_TYPES)
 def test_edges_aggregate(backend, ET):  # test/edgesiterator.jl:59-98
     sim = vh.create_simulation(edges_model(), backend=backend)

@@ -4152,7 +4152,7 @@ int vb_all_edges(vb_sim* s, int ei, vb_agent_id* to_out, vb_agent_id* from_out, 
     return guard([&] {   // EdgeMethods.jl:1005-1027; emitted in ascending target id order
         require_device();
         EdgeStore& e = s->E(ei);
-        if (!s->initialized) throw AssertionError("all_edges before finish_init! is not supported by the CUDA engine");
+        if (!s->initialized) { *n_out = 0; return; }   // the reference returns [] while the read container is empty (num_edges(sim, T) == 0, EdgeMethods.jl:1006-1008)
         s->merge_pending(ei);
         uint64_t n = 0;
         for (size_t t = 1; t <= s->agents.size(); ++t) {
