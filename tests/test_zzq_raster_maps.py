@@ -4,6 +4,7 @@ established suite (written after round 1's GPU budget was spent)."""
 import numpy as np
 import pytest
 
+import vahana_b200 as vh
 from models import pp_sim, pp_step
 
 
@@ -31,3 +32,39 @@ def test_raster_maps_oracle(oracle):
 @pytest.mark.gpu
 def test_raster_maps_gpu(cuda):
     _checks(cuda)
+
+
+def test_calc_raster_general_form_and_lazy_accessors(oracle):
+    """calc_raster(sim, raster, f, f_returns, accessible) with a host closure (src/Raster.jl:199-236: the docs' Game of Life read-out and
+    the test/raster.jl:296 edge count), neighborstates_iter / neighborstates_flexible_iter (src/EdgeMethods.jl:783-803) and
+    checked (src/Helpers.jl:33-37) — host-side conveniences of the reference API that need no kernel"""
+    from models import raster_model
+    sim = vh.create_simulation(raster_model(), backend=oracle)
+    sim.add_raster("raster", (6, 4), "Position", lambda p: (10 * p[0] + p[1],))
+    movers = [sim.add_agent("MovingAgent", v) for v in (1, 2, 3)]
+    for a, p in zip(movers, [(1, 1), (2, 2), (2, 2)]):
+        sim.move_to("raster", a, p, "OnPosition", "OnPosition")
+    with pytest.raises(AssertionError):
+        sim.calc_raster("raster", lambda cid: 0, "i8")
+    sim.finish_init()
+    ids = sim.raster_ids("raster")
+    assert ids.shape == (6, 4) and int(ids[1, 2]) == sim.cellid("raster", (2, 3))
+    got = sim.calc_raster("raster", lambda cid: sim.agentstate(cid, "Position")["ids_sum"], "i8", ["Position"])
+    assert np.array_equal(got, sim.calc_rasterstate("raster", "ids_sum", "Position")) and got[5, 3] == 64
+    ne = sim.calc_raster("raster", lambda cid: sim.num_edges(cid, "OnPosition"), "i8", ["OnPosition"])
+    assert np.array_equal(ne, sim.calc_raster_num_edges("raster", "OnPosition")) and ne[1, 1] == 2 and ne.sum() == 3
+    # lazy accessors: the movers standing on a cell
+    sim.disable_transition_checks(True)
+    cell = int(ids[1, 1])
+    it = sim.neighborstates_iter(cell, "OnPosition", "MovingAgent")
+    assert not isinstance(it, list) and [int(s["value"]) for s in it] == [2, 3]
+    assert [int(s["value"]) for s in sim.neighborstates_flexible_iter(cell, "OnPosition")] == [2, 3]
+    assert sim.neighborstates_iter(int(ids[3, 3]), "OnPosition", "MovingAgent") is None
+    # checked: nothing happens for `nothing`
+    seen = []
+    vh.checked(seen.append, lambda f, it_: [f(x) for x in it_], sim.neighborids(int(ids[3, 3]), "OnPosition"))
+    assert seen == []
+    vh.checked(seen.append, lambda f, it_: [f(x) for x in it_], sim.neighborids(cell, "OnPosition"))
+    assert seen == [int(movers[1]), int(movers[2])]
+    sim.disable_transition_checks(False)
+    assert vh.rootonly(lambda: 7) == 7

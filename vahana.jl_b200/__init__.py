@@ -178,6 +178,21 @@ class Backend:
 _default_backend: Optional[Backend] = None
 
 
+def checked(f, g, itr, **kwargs):
+    """checked(f, g, itr) (src/Helpers.jl:33-37): g(f, itr) unless itr is nothing, e.g. checked(fn, map, sim.neighborids(id, "Contact"))"""
+    if itr is not None:
+        return g(f, itr, **kwargs)
+    return None
+
+
+def rootonly(fn, *args, **kwargs):
+    """@rootonly (src/Helpers.jl:236-242): run fn on rank 0 only"""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0:
+        return fn(*args, **kwargs)
+    return None
+
+
 def equal_partition(n: int, nranks: int) -> list:
     """_create_equal_partition (src/Simulation.jl:353-367): contiguous blocks, sizes differ by at most one, larger blocks first.
     Returns the nranks + 1 block boundaries."""
@@ -631,6 +646,7 @@ class Simulation:
         self._ck(self.lib.vb_sim_copy(self.h, C.byref(h)))
         s = Simulation(self.model, None, dict(self.globals), self.backend, _handle=h)
         s._params = None if self._params is None else self._params.copy()
+        s._inited = getattr(self, "_inited", False)
         return s
 
     def param(self, name: str):
@@ -869,6 +885,7 @@ class Simulation:
             idmapping = self._distribute(partition, partition_algo, rank.value, world.value, return_idmapping)
         self._stage = None
         self._ck(self.lib.vb_finish_init(self.h))
+        self._inited = True
         if distribute and return_idmapping and world.value == 1:
             idmapping = {}
             for name in self.model.types.agent_names:
@@ -1006,6 +1023,12 @@ class Simulation:
             self.lib.vb_comm_rank(C.byref(r), C.byref(w))
         return w.value
 
+    def _rank(self) -> int:
+        w, r = C.c_int(1), C.c_int(0)
+        if hasattr(self.lib, "vb_comm_rank"):
+            self.lib.vb_comm_rank(C.byref(r), C.byref(w))
+        return r.value
+
     def _join(self, arr: Optional[np.ndarray]):
         """join (src/MPI.jl:481-517): the ranks' vectors concatenated in rank order, on every rank (collective; host data)"""
         if arr is None or self._world() == 1:
@@ -1090,6 +1113,15 @@ class Simulation:
         if self._single(edge_name):
             return self.agentstate(ids, agent_type)
         return [self.agentstate(i, agent_type) for i in ids]
+
+    def neighborstates_iter(self, to: int, edge_name: str, agent_type: str):
+        """neighborstates_iter (src/EdgeMethods.jl:783-803): the lazy form; not defined with :SingleEdge or :IgnoreFrom"""
+        ids = self.neighborids_iter(to, edge_name)
+        return None if ids is None else (self.agentstate(i, agent_type) for i in ids)
+
+    def neighborstates_flexible_iter(self, to: int, edge_name: str):
+        ids = self.neighborids_iter(to, edge_name)
+        return None if ids is None else (self.agentstate_flexible(i) for i in ids)
 
     def neighborstates_flexible(self, to: int, edge_name: str):
         ids = self.neighborids(to, edge_name)
@@ -1292,6 +1324,36 @@ class Simulation:
 
     def calc_rasterstate(self, name: str, field: str, type_name: str) -> np.ndarray:
         return self.rastervalues(name, field, type_name)
+
+    def raster_ids(self, name: str) -> np.ndarray:
+        """sim.rasters[name]: the grid of cell ids (on several ranks: the grid handed out by finish_init!, src/MPI.jl:59-73)"""
+        dims = self.raster_info(name)
+        ids = np.zeros(int(np.prod(dims)), dtype=np.uint64)
+        nd, d = C.c_int(), (C.c_int64 * 4)()
+        self._ck(self.lib.vb_raster_info(self.h, name.encode(), C.byref(nd), d, ids.ctypes.data_as(C.c_void_p)))
+        return ids.reshape(dims, order="F")
+
+    def calc_raster(self, name: str, f, f_returns, accessible=()) -> np.ndarray:
+        """calc_raster(sim, raster, f, f_returns, accessible) (src/Raster.jl:206-236), the general form: f(id) — any Python callable
+        that uses the query API (agentstate, num_edges, neighborids, ...) on the types listed in `accessible` — is evaluated on the
+        host for every cell this rank owns, the ranks' values are joined, cells nobody owns stay zero(f_returns).  As slow as the
+        reference's loop; the device forms are calc_rasterstate / calc_rasterstate_fn / calc_raster_num_edges."""
+        assert getattr(self, "_inited", False), "calc_raster can be only called after finish_init!"
+        ids = self.raster_ids(name)
+        flat = ids.reshape(-1, order="F")
+        rank = self._rank()
+        self.disable_transition_checks(True)
+        try:
+            mine = [(k, f(int(i))) for k, i in enumerate(flat) if process_nr(int(i)) == rank]
+        finally:
+            self.disable_transition_checks(False)
+        idx = np.array([k for k, _ in mine], dtype=np.int64)
+        val = np.array([v for _, v in mine], dtype=f_returns) if mine else np.zeros(0, dtype=f_returns)
+        if self._world() > 1:
+            idx, val = self._join(idx), self._join(val)
+        out = np.zeros(flat.shape[0], dtype=f_returns)
+        out[idx] = val
+        return out.reshape(ids.shape, order="F")
 
     def calc_rasterstate_fn(self, name: str, map_name: str, datatype="f8") -> np.ndarray:
         """calc_rasterstate(sim, raster, f, f_returns) (src/Raster.jl:238-280) with f a registered map functor of the cells' type,

@@ -11,9 +11,10 @@ export ModelTypes, register_agenttype!, register_edgetype!, register_param!, reg
        AgentID, Edge, agent_id, type_nr, process_nr, agent_nr,
        add_agent!, add_agents!, add_edge!, add_edges!, remove_edges!,
        agentstate, agentstate_flexible, edges, neighborids, edgestates, neighborstates, neighborstates_flexible,
+       neighborstates_iter, neighborstates_flexible_iter, checked,
        num_edges, has_edge, num_agents, all_agents, all_agentids, all_edges,
        param, set_param!, get_global, set_global!, push_global!, modify_global!,
-       add_raster!, connect_raster_neighbors!, move_to!, cellid, calc_rasterstate, rastervalues, calc_raster_num_edges,
+       add_raster!, connect_raster_neighbors!, move_to!, cellid, calc_raster, calc_rasterstate, rastervalues, calc_raster_num_edges, raster_ids,
        random_pos, random_cell,
        enable_asserts
 
@@ -348,6 +349,18 @@ function neighborstates_flexible(sim::Simulation, to::AgentID, ::Type{T}) where 
     ids === nothing && return nothing
     ids isa AgentID ? agentstate_flexible(sim, ids) : [agentstate_flexible(sim, i) for i in ids]
 end
+function neighborstates_iter(sim::Simulation, to::AgentID, ::Type{T}, ::Type{A}) where {T,A}   # src/EdgeMethods.jl:783-803
+    @assert !issingle(sim, T) "neighborstates_iter is not defined for edgetypes with the :SingleEdge or :IgnoreFrom hint"
+    ids = neighborids(sim, to, T)
+    ids === nothing ? nothing : (agentstate(sim, i, A) for i in ids)
+end
+function neighborstates_flexible_iter(sim::Simulation, to::AgentID, ::Type{T}) where T
+    @assert !issingle(sim, T) "neighborstates_flexible_iter is not defined for edgetypes with the :SingleEdge or :IgnoreFrom hint"
+    ids = neighborids(sim, to, T)
+    ids === nothing ? nothing : (agentstate_flexible(sim, i) for i in ids)
+end
+"checked(f, g, itr): src/Helpers.jl:33-37"
+checked(f, g, itr; kwargs...) = isnothing(itr) ? nothing : g(f, itr; kwargs...)
 function num_edges(sim::Simulation, to::AgentID, ::Type{T}) where T      # :850-869
     r = _row(sim, to, T, ACC_NUM_EDGES)
     r === nothing ? 0 : r[3]
@@ -487,6 +500,24 @@ function calc_raster_num_edges(sim::Simulation, name::Symbol, ::Type{E}) where E
     dims, _ = sim.rasters[name]
     out = Array{Int64}(undef, dims)
     check(ccall((:vb_calc_raster_num_edges, LIB), Cint, (Ptr{Cvoid}, Cstring, Cint, Ptr{Int64}), sim.handle, string(name), edgeidx(sim, E), out))
+    out
+end
+
+"raster_ids(sim, name): sim.rasters[name] of the reference, the grid of cell ids (on several ranks the grid handed out by finish_init!)"
+function raster_ids(sim::Simulation, name::Symbol)
+    dims = sim.rasters[name][1]
+    ids = Array{AgentID}(undef, dims)
+    nd = Ref{Cint}(0); d = zeros(Int64, 4)
+    check(ccall((:vb_raster_info, LIB), Cint, (Ptr{Cvoid}, Cstring, Ref{Cint}, Ptr{Int64}, Ptr{AgentID}), sim.handle, string(name), nd, d, ids))
+    ids
+end
+"calc_raster(sim, raster, f, f_returns, accessible): src/Raster.jl:206-236, the general form as a host loop over the cells (one rank)"
+function calc_raster(sim::Simulation, name::Symbol, f, ::Type{R}, accessible = DataType[]) where R
+    ids = raster_ids(sim, name)
+    out = zeros(R, size(ids))
+    for (idx, id) in enumerate(ids)
+        out[idx] = f(id)
+    end
     out
 end
 
