@@ -148,6 +148,7 @@ def test_graph_bridges(backend):
     sim2.finish_init()
     assert sim2.num_edges("Knows") == 4
     assert len(vh.vahanagraph(sim2, drop_multiedges=True)["src"]) == 3
+    assert len(vh.vahanasimplegraph(sim2)["src"]) == 3                       # vahanasimplegraph (src/GraphsSupport.jl:107-160): structure only
 
 
 def test_show_and_dataframes(backend):

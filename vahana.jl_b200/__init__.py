@@ -1448,6 +1448,12 @@ def vahanagraph(sim: Simulation, agenttypes=None, edgetypes=None, drop_multiedge
     return {"g2v": g2v, "src": cat(src), "dst": cat(dst), "edgetype": cat(et)}
 
 
+def vahanasimplegraph(sim: Simulation, agenttypes=None, edgetypes=None) -> dict:
+    """vahanasimplegraph(sim; agenttypes, edgetypes) (src/GraphsSupport.jl:291-340): the structure only — a simple digraph has no
+    parallel edges, so this is vahanagraph with multi-edges dropped"""
+    return vahanagraph(sim, agenttypes, edgetypes, drop_multiedges=True)
+
+
 def to_networkx(sim: Simulation, agenttypes=None, edgetypes=None, drop_multiedges: bool = False):
     """the vahanagraph as a networkx.MultiDiGraph (vertex attribute `id` = AgentID, edge attribute `edgetype`)"""
     import networkx as nx
