@@ -219,6 +219,7 @@ def plan_distribution(agents: dict, edges: dict, world: int, partition: Optional
     olds, news = [], []
     shards = [{"agents": {}, "edges": {}} for _ in range(world)]
     bounds = {}
+    pkeys = pvals = None
     for tid in sorted(agents):
         ids, states = agents[tid]
         ids = np.asarray(ids, dtype=np.uint64).reshape(-1)
@@ -228,10 +229,16 @@ def plan_distribution(agents: dict, edges: dict, world: int, partition: Optional
             bounds[tid] = b
             owner = np.searchsorted(np.array(b[1:]), np.arange(n), side="right")
         else:
-            try:
-                owner = np.array([int(partition[int(i)]) - 1 for i in ids], dtype=np.int64)
-            except KeyError as e:
-                raise AssertionError(f"the partition does not name a rank for agent {e.args[0]:#x}") from None
+            if pkeys is None:      # the partition as two aligned arrays, sorted by id: one vectorised lookup per type
+                pkeys = np.fromiter((int(k) for k in partition.keys()), dtype=np.uint64, count=len(partition))
+                pvals = np.fromiter((int(v) for v in partition.values()), dtype=np.int64, count=len(partition))
+                o = np.argsort(pkeys, kind="stable")
+                pkeys, pvals = pkeys[o], pvals[o]
+            k = np.minimum(np.searchsorted(pkeys, ids), max(pkeys.shape[0] - 1, 0))
+            found = (pkeys[k] == ids) if pkeys.shape[0] else np.zeros(n, dtype=bool)
+            if n and not found.all():
+                raise AssertionError(f"the partition does not name a rank for agent {int(ids[np.argmin(found)]):#x}")
+            owner = (pvals[k] - 1) if n else np.zeros(0, dtype=np.int64)
             if n and (owner.min() < 0 or owner.max() >= world):
                 raise AssertionError("the partition names a rank outside of 1..mpi.size")
         new = np.zeros(n, dtype=np.uint64)
