@@ -75,6 +75,28 @@ def test_plan_explicit_partition_and_errors():
         vh.plan_distribution({1: (a, None)}, {"E": (a[:1], np.array([vh.agent_id(1, 0, 99)], dtype=np.uint64), None)}, 2)   # dangling id
 
 
+def test_plan_remaps_dense_and_sparse_ids_alike():
+    """the id rewrite of the edges goes through a per-type table when the ids are dense (what add_agents! hands out) and through a
+    search otherwise: same result, same errors"""
+    rng = np.random.default_rng(5)
+    dense, dense2 = _ids(1, 5000), _ids(2, 300)
+    sparse = _ids(1, 200000)[::97]                                        # holes: more than four numbers per agent
+    for a_ids in (dense, sparse):
+        allids = np.concatenate([a_ids, dense2])
+        fr, to = allids[rng.integers(0, len(allids), 20000)], allids[rng.integers(0, len(allids), 20000)]
+        shards, old, new, _ = vh.plan_distribution({1: (a_ids, None), 2: (dense2, None)}, {"E": (fr, to, None)}, 3)
+        m = dict(zip(old.tolist(), new.tolist()))
+        got_f = np.concatenate([shards[r]["edges"]["E"][0] for r in range(3)])
+        got_t = np.concatenate([shards[r]["edges"]["E"][1] for r in range(3)])
+        owner = np.array([vh.process_nr(m[int(x)]) for x in to])
+        order = np.concatenate([np.nonzero(owner == r)[0] for r in range(3)])
+        assert [int(x) for x in got_f] == [m[int(x)] for x in fr[order]] and [int(x) for x in got_t] == [m[int(x)] for x in to[order]]
+        for bad in (np.uint64(int(a_ids[-1]) + 1), np.uint64(int(a_ids[0]) - 1) if vh.agent_nr(int(a_ids[0])) > 1 else np.uint64(vh.agent_id(3, 0, 1)),
+                    np.uint64(vh.agent_id(2, 0, 301))):
+            with pytest.raises(AssertionError):
+                vh.plan_distribution({1: (a_ids, None), 2: (dense2, None)}, {"E": (fr[:1], np.array([bad], dtype=np.uint64), None)}, 3)
+
+
 def test_finish_init_single_rank_idmapping_is_identity(oracle):
     backend = oracle   # host logic of the mirror; the CUDA engine takes the same path in every GPU test that calls finish_init()
     from models import edges_model, foos
